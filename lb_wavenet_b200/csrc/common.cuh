@@ -1,0 +1,104 @@
+// Shared device/host helpers for the lb-wavenet B200 kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <mma.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "model.h"
+
+namespace wn {
+
+typedef __nv_bfloat16 bf16;
+
+extern int64_t g_launches;  // kernels launched by this library (bench.py gpu_launches)
+
+#define WN_CUDA_CHECK(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      wn::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return WN_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+#define WN_LAUNCH_CHECK()                                                                       \
+  do {                                                                                          \
+    ++wn::g_launches;                                                                           \
+    cudaError_t _e = cudaGetLastError();                                                        \
+    if (_e != cudaSuccess) {                                                                    \
+      wn::set_error("%s:%d: kernel launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return WN_ERR_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+// ---- math ------------------------------------------------------------------------------
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return 0.5f * tanh_fast(0.5f * x) + 0.5f; }
+
+__device__ __forceinline__ float bf2f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ bf16 f2bf(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- legacy-tensor-path tile GEMM (nvcuda::wmma, HMMA) ---------------------------------
+// C_s[TM x N] (=|+=) A_s[TM x K] * B[K x N];  A_s bf16 in shared memory (row-major, lda),
+// B bf16 in GLOBAL memory: row-major [K][N] (ldb = row length) or, with COLB, stored as
+// B^T row-major [N][K] (ldb = K-extent of the stored matrix).  All warps of the CTA take
+// part; caller synchronises before and after.
+template <int TM, bool COLB, bool ACCUM>
+__device__ __forceinline__ void tile_mma(const bf16* A_s, int lda, const bf16* __restrict__ Bg,
+                                         int ldb, float* C_s, int ldc, int K, int N) {
+  using namespace nvcuda;
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int ntn = N >> 4;
+  const int ntiles = (TM / 16) * ntn;
+  for (int tile = warp; tile < ntiles; tile += nwarps) {
+    const int mi = tile % (TM / 16), ni = tile / (TM / 16);
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
+    float* cptr = C_s + mi * 16 * ldc + ni * 16;
+    if (ACCUM)
+      wmma::load_matrix_sync(acc, cptr, ldc, wmma::mem_row_major);
+    else
+      wmma::fill_fragment(acc, 0.f);
+    for (int k0 = 0; k0 < K; k0 += 16) {
+      wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> fa;
+      wmma::load_matrix_sync(fa, A_s + mi * 16 * lda + k0, lda);
+      if (COLB) {
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::col_major> fb;
+        wmma::load_matrix_sync(fb, Bg + (size_t)(ni * 16) * ldb + k0, ldb);
+        wmma::mma_sync(acc, fa, fb, acc);
+      } else {
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> fb;
+        wmma::load_matrix_sync(fb, Bg + (size_t)k0 * ldb + ni * 16, ldb);
+        wmma::mma_sync(acc, fa, fb, acc);
+      }
+    }
+    wmma::store_matrix_sync(cptr, acc, ldc, wmma::mem_row_major);
+  }
+}
+
+// copy `ncols` bf16 (multiple of 8) of one global row into shared memory, 16 B at a time,
+// executed by the calling thread for chunk index c
+__device__ __forceinline__ void copy16(bf16* dst, const bf16* src, bool valid) {
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (valid) v = *reinterpret_cast<const uint4*>(src);
+  *reinterpret_cast<uint4*>(dst) = v;
+}
+
+}  // namespace wn

@@ -1,0 +1,198 @@
+// Host-only part of the C ABI: model handle, variable registry, workspace carve-up.
+// Needs no GPU (CPU tests call it to check names/shapes against the reference contract).
+#include "model.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace wn {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static const int64_t kArenaAlign = 64;  // elements (256 B for fp32, 128 B for the bf16 mirror)
+
+static int64_t add_param(wn_model* m, const std::string& name, std::initializer_list<int64_t> shape,
+                         int32_t kind) {
+  ParamEntry e;
+  e.name = name;
+  e.offset = m->n_param_elems;
+  e.ndim = (int32_t)shape.size();
+  e.shape[0] = e.shape[1] = e.shape[2] = 1;
+  int i = 0;
+  for (int64_t s : shape) e.shape[i++] = s;
+  e.kind = kind;
+  m->params.push_back(e);
+  m->n_param_elems = align_up(m->n_param_elems + e.numel(), kArenaAlign);
+  return e.offset;
+}
+
+const WorkspaceLayout& workspace_layout(wn_model* m, int32_t T) {
+  if (m->wl.T == T) return m->wl;
+  WorkspaceLayout w;
+  const wn_arch& a = m->a;
+  const int64_t B = m->n_slots, L = m->L, R = a.n_res, D = a.n_dil, S = a.n_skip, P = a.n_post,
+                Q = a.n_quant;
+  const int64_t rows = B * (int64_t)T;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    int64_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  w.T = T;
+  w.wbf = take(m->n_param_elems * 2);
+  w.xfull.resize(L);
+  for (int64_t l = 0; l < L; ++l) w.xfull[l] = take(B * (m->layers[l].dil + (int64_t)T) * R * 2);
+  w.z = take(rows * L * D * 2);
+  w.h1 = take(rows * S * 2);
+  w.h2 = take(rows * P * 2);
+  w.dlogits = take(rows * Q * 2);
+  w.dp1 = take(rows * P * 2);
+  w.dskip = take(rows * S * 2);
+  w.dz = take(rows * L * D * 2);
+  w.dv = take(rows * 2 * D * 2);
+  w.dx[0] = take(rows * R * 2);
+  w.dx[1] = take(rows * R * 2);
+  const int64_t gc_elems = a.n_gc_embed > 0 ? L * (int64_t)(a.n_gc_category + 1) * 2 * D : 0;
+  w.gc_tbl = take(gc_elems * 4);
+  w.dgc_tbl = take(gc_elems * 4);
+  w.skip_bias = take(S * 4);
+  w.total = off;
+  m->wl = w;
+  return m->wl;
+}
+
+}  // namespace wn
+
+using namespace wn;
+
+extern "C" {
+
+int32_t wn_abi_version(void) { return WN_ABI_VERSION; }
+
+const char* wn_last_error(void) { return g_err; }
+
+int wn_model_create(const wn_arch* arch, int32_t n_slots, wn_model** out) {
+  if (!arch || !out) {
+    set_error("wn_model_create: null argument");
+    return WN_ERR_INVALID;
+  }
+  const wn_arch& a = *arch;
+  auto bad = [&](const char* what) {
+    set_error("wn_model_create: unsupported architecture: %s", what);
+    return (int)WN_ERR_UNSUPPORTED;
+  };
+  if (a.n_quant != 256) return bad("n_quant must be 256");
+  if (a.n_blocks < 1 || a.n_block_layers < 1 || a.n_block_layers > 14) return bad("n_blocks/n_block_layers");
+  if (a.n_res % 16 || a.n_res < 16 || a.n_res > 128) return bad("n_res must be a multiple of 16 in [16,128]");
+  if (a.n_dil % 16 || a.n_dil < 16 || a.n_dil > 128) return bad("n_dil must be a multiple of 16 in [16,128]");
+  if (a.n_skip % 16 || a.n_skip < 16 || a.n_skip > 512) return bad("n_skip must be a multiple of 16 in [16,512]");
+  if (a.n_post % 16 || a.n_post < 16 || a.n_post > 512) return bad("n_post must be a multiple of 16 in [16,512]");
+  if (a.n_gc_embed < 0 || a.n_gc_embed > 64) return bad("n_gc_embed must be in [0,64]");
+  if (a.n_gc_embed > 0 && a.n_gc_category < 1) return bad("n_gc_category must be >= 1 with global conditioning");
+  if (n_slots < 1) return bad("n_slots must be >= 1");
+
+  wn_model* m = new wn_model();
+  m->a = a;
+  m->n_slots = n_slots;
+  m->L = a.n_blocks * a.n_block_layers;
+  m->n_param_elems = 0;
+  m->save_elems = 0;
+  const int64_t R = a.n_res, D = a.n_dil, S = a.n_skip, P = a.n_post, Q = a.n_quant, G = a.n_gc_embed;
+  const bool gc = G > 0, ub = a.use_bias != 0;
+  // registration order == graph construction order of the reference (tmodel.py:292-328)
+  m->off_gc_embed = gc ? add_param(m, "GC_EMBED", {a.n_gc_category + 1, G}, WN_KIND_FILTER) : -1;
+  m->off_pre = add_param(m, "PRE", {Q, R}, WN_KIND_FILTER);
+  m->off_pre_b = ub ? add_param(m, "PRE_BIAS", {R}, WN_KIND_BIAS) : -1;
+  for (int b = 0; b < a.n_blocks; ++b) {
+    for (int bl = 0; bl < a.n_block_layers; ++bl) {
+      char sfx[32];
+      snprintf(sfx, sizeof(sfx), "_%d_%d", b, bl);
+      LayerDesc d;
+      memset(&d, 0, sizeof(d));
+      d.dil = 1 << bl;  // tmodel.py:318
+      d.save_off = m->save_elems;
+      m->save_elems += (int64_t)n_slots * d.dil * R;
+      d.sig = add_param(m, std::string("SIGNAL") + sfx, {2, R, D}, WN_KIND_FILTER);
+      d.sig_b = ub ? add_param(m, std::string("SIGNAL_BIAS") + sfx, {D}, WN_KIND_BIAS) : -1;
+      d.gate = add_param(m, std::string("GATE") + sfx, {2, R, D}, WN_KIND_FILTER);
+      d.gate_b = ub ? add_param(m, std::string("GATE_BIAS") + sfx, {D}, WN_KIND_BIAS) : -1;
+      d.gc_sig = gc ? add_param(m, std::string("GC_SIGNAL") + sfx, {G, D}, WN_KIND_FILTER) : -1;
+      d.gc_gate = gc ? add_param(m, std::string("GC_GATE") + sfx, {G, D}, WN_KIND_FILTER) : -1;
+      d.res = add_param(m, std::string("RESIDUAL") + sfx, {D, R}, WN_KIND_FILTER);
+      d.res_b = ub ? add_param(m, std::string("RESIDUAL_BIAS") + sfx, {R}, WN_KIND_BIAS) : -1;
+      d.skip = add_param(m, std::string("SKIP") + sfx, {D, S}, WN_KIND_FILTER);
+      d.skip_b = ub ? add_param(m, std::string("SKIP_BIAS") + sfx, {S}, WN_KIND_BIAS) : -1;
+      m->layers.push_back(d);
+    }
+  }
+  m->off_post1 = add_param(m, "POST1", {S, P}, WN_KIND_FILTER);
+  m->off_post1_b = ub ? add_param(m, "POST1_BIAS", {P}, WN_KIND_BIAS) : -1;
+  m->off_post2 = add_param(m, "POST2", {P, Q}, WN_KIND_FILTER);
+  m->off_post2_b = ub ? add_param(m, "POST2_BIAS", {Q}, WN_KIND_BIAS) : -1;
+  *out = m;
+  return WN_OK;
+}
+
+int32_t wn_n_layers(const wn_model* m) { return m->L; }
+
+int32_t wn_recep_field(const wn_model* m) {
+  // reference tmodel.py:50-51
+  return m->a.n_blocks * ((1 << m->a.n_block_layers) - 1);
+}
+
+int32_t wn_param_count(const wn_model* m) { return (int32_t)m->params.size(); }
+
+int64_t wn_param_elems(const wn_model* m) { return m->n_param_elems; }
+
+int wn_param_info(const wn_model* m, int32_t i, char* name, int32_t name_cap, int64_t* offset,
+                  int32_t* ndim, int64_t* shape3, int32_t* kind) {
+  if (i < 0 || i >= (int32_t)m->params.size()) {
+    set_error("wn_param_info: index %d out of range", i);
+    return WN_ERR_INVALID;
+  }
+  const ParamEntry& e = m->params[i];
+  if (name && name_cap > 0) {
+    strncpy(name, e.name.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (offset) *offset = e.offset;
+  if (ndim) *ndim = e.ndim;
+  if (shape3) {
+    shape3[0] = e.shape[0];
+    shape3[1] = e.shape[1];
+    shape3[2] = e.shape[2];
+  }
+  if (kind) *kind = e.kind;
+  return WN_OK;
+}
+
+int64_t wn_save_elems(const wn_model* m) { return m->save_elems; }
+
+int wn_save_info(const wn_model* m, int32_t layer, int64_t* offset, int32_t* dil) {
+  if (layer < 0 || layer >= m->L) {
+    set_error("wn_save_info: layer %d out of range", layer);
+    return WN_ERR_INVALID;
+  }
+  if (offset) *offset = m->layers[layer].save_off;
+  if (dil) *dil = m->layers[layer].dil;
+  return WN_OK;
+}
+
+int64_t wn_workspace_bytes(const wn_model* m, int32_t slice_sz) {
+  if (slice_sz < 2) {
+    set_error("wn_workspace_bytes: slice_sz must be >= 2");
+    return WN_ERR_INVALID;
+  }
+  return workspace_layout(const_cast<wn_model*>(m), slice_sz).total;
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+// Internal model description shared by the host-side registry and the kernel launchers.
+// Mirrors the reference's variable registry (arch.py:85-103,112-142) as a flat-arena layout.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/wavenet_b200.h"
+
+namespace wn {
+
+struct ParamEntry {
+  std::string name;
+  int64_t offset;  // element offset into the fp32 arena
+  int32_t ndim;
+  int64_t shape[3];
+  int32_t kind;  // WN_KIND_*
+  int64_t numel() const {
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) n *= shape[i];
+    return n;
+  }
+};
+
+// Per-layer offsets (elements, fp32 arena) -- plain-old-data, passed to kernels by value
+// and also uploaded as a device table.  -1 == tensor absent (no bias / no GC).
+struct LayerDesc {
+  int64_t sig, sig_b, gate, gate_b, gc_sig, gc_gate, res, res_b, skip, skip_b;
+  int64_t save_off;   // element offset into the bf16 SAVE arena, layout [n_slots][dil][R]
+  int64_t xfull_off;  // byte offset of xfull_l in the workspace (filled per slice_sz)
+  int32_t dil;
+  int32_t pad;
+};
+
+// Workspace carve-up for a given slice_sz (byte offsets)
+struct WorkspaceLayout {
+  int32_t T = -1;
+  int64_t wbf;        // bf16 mirror of the parameter arena
+  int64_t z;          // [B*T][L*D] bf16
+  int64_t h1, h2;     // [B*T][S], [B*T][P] bf16
+  int64_t dlogits;    // [B*T][Q] bf16
+  int64_t dp1, dskip; // [B*T][P], [B*T][S] bf16
+  int64_t dz;         // [B*T][L*D] bf16
+  int64_t dv;         // [B*T][2D] bf16
+  int64_t dx[2];      // [B*T][R] bf16 ping/pong
+  int64_t gc_tbl;     // [L][C+1][2D] fp32 (GC projections incl. nothing else)
+  int64_t dgc_tbl;    // same shape, gradient
+  int64_t skip_bias;  // [S] fp32, sum over layers of SKIP_BIAS
+  int64_t total;
+  std::vector<int64_t> xfull;  // per layer: [B][dil+T][R] bf16
+};
+
+}  // namespace wn
+
+struct wn_model {
+  wn_arch a;
+  int32_t n_slots;
+  int32_t L;
+  std::vector<wn::ParamEntry> params;
+  int64_t n_param_elems;
+  int64_t off_pre, off_pre_b, off_gc_embed, off_post1, off_post1_b, off_post2, off_post2_b;
+  std::vector<wn::LayerDesc> layers;
+  int64_t save_elems;
+  wn::WorkspaceLayout wl;  // cached for the last slice_sz
+  // lazily created device-side tables (owned by the handle)
+  wn::LayerDesc* d_layers = nullptr;
+  int32_t d_layers_T = -1;
+  uint8_t* d_kind = nullptr;  // per arena element: 1 == L2-regularised filter
+  int sm_count = 0;
+};
+
+namespace wn {
+void set_error(const char* fmt, ...);
+const WorkspaceLayout& workspace_layout(wn_model* m, int32_t T);
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+}  // namespace wn
