@@ -114,6 +114,14 @@ int wn_train_backward(wn_model* m, const float* d_params, const int32_t* d_wav,
                       const int32_t* d_ids, int32_t slice_sz, void* d_ws, float* d_grads,
                       void* stream);
 
+/* The same computation issued in phases so that data-parallel ranks can overlap the gradient
+ * all-reduce with the rest of backward: phase 0 = post-net (+ every SKIP weight gradient);
+ * phase p in [1, L] = layer L-p; phase L+1 = PRE gather + global-conditioning gradients.
+ * Phases must be issued in ascending order on one stream; [0, L+2) == wn_train_backward. */
+int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* d_wav,
+                             const int32_t* d_ids, int32_t slice_sz, void* d_ws, float* d_grads,
+                             int32_t phase_begin, int32_t phase_end, void* stream);
+
 /* wn_adam_step replaces tf.train.AdamOptimizer(lr).apply_gradients (reference
  * train.py:178,186): TF "epsilon-hat" Adam, beta1=.9 beta2=.999 eps=1e-8 by default.
  *   g = d_grads / max(n_valid,1) (0 if n_valid==0, tmodel.py:246-249) + l2_factor * w [filters]
@@ -169,6 +177,16 @@ int wn_sample_logits(const float* d_logits, int32_t n_rows, uint64_t seed, int64
  * TMA + tcgen05.mma + TMEM pipeline used by the training kernels.  swizzle in {32,64,128}. */
 int wn_selftest_umma_gemm(const void* d_a, const void* d_b, float* d_c, int32_t M, int32_t N,
                           int32_t K, int32_t swizzle, void* stream);
+
+/* Per-category kernel timing with CUDA events recorded on the launch stream around every kernel
+ * launch (bench.py's roofline figures).  Categories: 0 prep/embed/SAVE, 1 layer forward, 2 post-net
+ * forward + loss, 3 post-net backward, 4 layer backward (gate), 5 layer backward (data), 6 weight
+ * gradients, 7 PRE/GC backward, 8 Adam, 9 generator.  wn_prof_collect synchronises the device,
+ * writes the summed milliseconds and launch counts of the WN_PROF_NCAT categories to HOST arrays
+ * and clears the records. */
+#define WN_PROF_NCAT 16
+int wn_prof_enable(int32_t on);
+int wn_prof_collect(double* h_ms, int64_t* h_launches);
 
 /* number of kernels launched by this library since the last call (for bench.py's
  * gpu_launches claim); resets the counter */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "wn_workspace_bytes": (_i64, [_vp, _i32]),
     "wn_train_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "wn_train_backward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "wn_train_backward_phases": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp]),
     "wn_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _vp]),
     "wn_l2_loss": (C.c_int, [_vp, _vp, _vp, _vp]),
     "wn_debug_read": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
@@ -57,6 +58,8 @@ SIGNATURES = {
     "wn_mu_decode": (C.c_int, [_vp, _vp, _i64, _vp]),
     "wn_sample_logits": (C.c_int, [_vp, _i32, _u64, _i64, _vp, _vp]),
     "wn_selftest_umma_gemm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "wn_prof_enable": (C.c_int, [_i32]),
+    "wn_prof_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(_i64)]),
     "wn_launch_count_reset": (_i64, []),
 }
 

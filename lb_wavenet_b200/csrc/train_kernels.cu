@@ -8,12 +8,43 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
 namespace wn {
 
 int64_t g_launches = 0;
+
+// ---- per-category event timing ------------------------------------------------------------
+struct ProfState {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;
+  size_t used = 0;
+  struct Rec { int cat; size_t e0, e1; int64_t launches; };
+  std::vector<Rec> recs;
+};
+static ProfState g_prof;
+
+static size_t prof_event(cudaStream_t st) {
+  if (g_prof.used == g_prof.pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_prof.pool.push_back(e);
+  }
+  cudaEventRecord(g_prof.pool[g_prof.used], st);
+  return g_prof.used++;
+}
+
+ProfScope::ProfScope(int cat_, cudaStream_t st_) : cat(cat_), st(st_), on(g_prof.enabled) {
+  if (on) g_prof.recs.push_back({cat, prof_event(st), 0, g_launches});
+}
+ProfScope::~ProfScope() {
+  if (on) {
+    g_prof.recs.back().e1 = prof_event(st);
+    g_prof.recs.back().launches = g_launches - g_prof.recs.back().launches;
+  }
+}
 
 constexpr int TM = 64;   // timesteps per CTA tile
 constexpr int NT = 256;  // threads per CTA
@@ -875,6 +906,32 @@ void wn_model_destroy(wn_model* m) {
   delete m;
 }
 
+int wn_prof_enable(int32_t on) {
+  g_prof.enabled = on != 0;
+  if (on) {
+    g_prof.used = 0;
+    g_prof.recs.clear();
+  }
+  return WN_OK;
+}
+
+int wn_prof_collect(double* h_ms, int64_t* h_launches) {
+  WN_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int i = 0; i < PROF_NCAT; ++i) {
+    if (h_ms) h_ms[i] = 0.0;
+    if (h_launches) h_launches[i] = 0;
+  }
+  for (const ProfState::Rec& r : g_prof.recs) {
+    float ms = 0.f;
+    WN_CUDA_CHECK(cudaEventElapsedTime(&ms, g_prof.pool[r.e0], g_prof.pool[r.e1]));
+    if (h_ms) h_ms[r.cat] += ms;
+    if (h_launches) h_launches[r.cat] += r.launches;
+  }
+  g_prof.used = 0;
+  g_prof.recs.clear();
+  return WN_OK;
+}
+
 int64_t wn_launch_count_reset(void) {
   int64_t n = g_launches;
   g_launches = 0;
@@ -897,6 +954,8 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
   bf16* wbf = reinterpret_cast<bf16*>(ws + wl.wbf);
   const bool gc = d.G > 0;
 
+  {
+  ProfScope ps_prep(PROF_PREP, st);
   k_cast_params<<<(unsigned)((m->n_param_elems + 255) / 256), 256, 0, st>>>(d_params, wbf, m->n_param_elems);
   WN_LAUNCH_CHECK();
   if (d.use_bias) {
@@ -919,10 +978,12 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
                                                          m->layers[0].dil, d.Q);
     WN_LAUNCH_CHECK();
   }
+  }
   const size_t lsm = layer_fwd_smem(d.R, d.D);
   rc = set_smem(k_layer_fwd, lsm);
   if (rc) return rc;
   for (int l = 0; l < d.L; ++l) {
+    ProfScope ps(PROF_LAYER_FWD, st);
     LayerArgs la;
     la.wbf = wbf; la.params = d_params; la.ld = m->layers[l];
     la.xin = reinterpret_cast<const bf16*>(ws + wl.xfull[l]);
@@ -935,19 +996,26 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
     k_layer_fwd<<<dim3((T + TM - 1) / TM, d.B), NT, lsm, st>>>(la);
     WN_LAUNCH_CHECK();
   }
-  k_save_store<<<dim3(64, d.L), 256, 0, st>>>(reinterpret_cast<bf16*>(d_save), ws, m->d_layers, d.B, T, d.R);
-  WN_LAUNCH_CHECK();
+  {
+    ProfScope ps(PROF_PREP, st);
+    k_save_store<<<dim3(64, d.L), 256, 0, st>>>(reinterpret_cast<bf16*>(d_save), ws, m->d_layers, d.B, T, d.R);
+    WN_LAUNCH_CHECK();
+  }
   PostArgs pa = make_post_args(m, d, wl, ws, d_params);
   pa.logits_out = d_logits; pa.wav = d_wav; pa.ids = d_ids; pa.stats = d_stats;
   const size_t psm = post_smem(pa.AW, pa.CW);
   rc = set_smem(k_post_fwd, psm);
   if (rc) return rc;
-  k_post_fwd<<<(unsigned)((d.rows + TM - 1) / TM), NT, psm, st>>>(pa);
-  WN_LAUNCH_CHECK();
+  {
+    ProfScope ps(PROF_POST_FWD, st);
+    k_post_fwd<<<(unsigned)((d.rows + TM - 1) / TM), NT, psm, st>>>(pa);
+    WN_LAUNCH_CHECK();
+  }
   return WN_OK;
 }
 
 static int launch_wgrad(const WgradArgs& base, int sm_count, cudaStream_t st) {
+  ProfScope ps(PROF_WGRAD, st);
   WgradArgs a = base;
   const int64_t rows = (int64_t)a.B * a.T;
   const int nf = a.N > 64 ? 4 : 1;
@@ -970,7 +1038,20 @@ static int launch_wgrad(const WgradArgs& base, int sm_count, cudaStream_t st) {
 
 int wn_train_backward(wn_model* m, const float* d_params, const int32_t* d_wav, const int32_t* d_ids,
                       int32_t T, void* d_ws, float* d_grads, void* stream_) {
-  if (!m || !d_params || !d_wav || !d_ids || !d_ws || !d_grads || T < 2) {
+  return wn_train_backward_phases(m, d_params, d_wav, d_ids, T, d_ws, d_grads, 0, m ? m->L + 2 : 0, stream_);
+}
+
+// phases: 0 = zero grads, post-net backward, post-net and SKIP weight gradients;
+//         p in [1, L] = layer L-p (gate backward, weight gradients, data gradient);
+//         L+1 = PRE gather backward and global-conditioning gradients.
+// Gradients of layer l are final once phase L-l has been issued (global-conditioning projections:
+// only after phase L+1), which lets data-parallel ranks start all-reducing finished arena ranges
+// while earlier layers are still being differentiated.
+int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* d_wav, const int32_t* d_ids,
+                             int32_t T, void* d_ws, float* d_grads, int32_t phase_begin, int32_t phase_end,
+                             void* stream_) {
+  if (!m || !d_params || !d_wav || !d_ids || !d_ws || !d_grads || T < 2 || phase_begin < 0 ||
+      phase_end > m->L + 2 || phase_begin > phase_end) {
     set_error("wn_train_backward: invalid argument");
     return WN_ERR_INVALID;
   }
@@ -982,20 +1063,24 @@ int wn_train_backward(wn_model* m, const float* d_params, const int32_t* d_wav, 
   unsigned char* ws = (unsigned char*)d_ws;
   const bf16* wbf = reinterpret_cast<const bf16*>(ws + wl.wbf);
   const bool gc = d.G > 0;
-  WN_CUDA_CHECK(cudaMemsetAsync(d_grads, 0, sizeof(float) * m->n_param_elems, st));
-  if (gc)
-    WN_CUDA_CHECK(cudaMemsetAsync(ws + wl.dgc_tbl, 0, sizeof(float) * (size_t)d.L * d.C1 * 2 * d.D, st));
-
   PostArgs pa = make_post_args(m, d, wl, ws, d_params);
   pa.grads = d_grads;
-  const size_t psm = post_smem(pa.AW, pa.CW);
-  rc = set_smem(k_post_bwd, psm);
-  if (rc) return rc;
-  k_post_bwd<<<(unsigned)((d.rows + TM - 1) / TM), NT, psm, st>>>(pa);
-  WN_LAUNCH_CHECK();
-  if (d.use_bias && d.L > 1) {
-    k_bcast_skip_bias<<<(d.S + 127) / 128, 128, 0, st>>>(d_grads, m->d_layers, d.L, d.S);
-    WN_LAUNCH_CHECK();
+  if (phase_begin == 0) {
+    WN_CUDA_CHECK(cudaMemsetAsync(d_grads, 0, sizeof(float) * m->n_param_elems, st));
+    if (gc)
+      WN_CUDA_CHECK(cudaMemsetAsync(ws + wl.dgc_tbl, 0, sizeof(float) * (size_t)d.L * d.C1 * 2 * d.D, st));
+    const size_t psm = post_smem(pa.AW, pa.CW);
+    rc = set_smem(k_post_bwd, psm);
+    if (rc) return rc;
+    {
+      ProfScope ps(PROF_POST_BWD, st);
+      k_post_bwd<<<(unsigned)((d.rows + TM - 1) / TM), NT, psm, st>>>(pa);
+      WN_LAUNCH_CHECK();
+    }
+    if (d.use_bias && d.L > 1) {
+      k_bcast_skip_bias<<<(d.S + 127) / 128, 128, 0, st>>>(d_grads, m->d_layers, d.L, d.S);
+      WN_LAUNCH_CHECK();
+    }
   }
   // post-net weight gradients
   WgradArgs wa;
@@ -1008,18 +1093,22 @@ int wn_train_backward(wn_model* m, const float* d_params, const int32_t* d_wav, 
     wa.out = out; wa.ldo = ldo;
     return launch_wgrad(wa, m->sm_count, st);
   };
-  if ((rc = flat(pa.h2, d.P, 0, d.P, pa.dlogits, d.Q, 0, d.Q, d_grads + m->off_post2, d.Q))) return rc;
-  if ((rc = flat(pa.h1, d.S, 0, d.S, pa.dp1, d.P, 0, d.P, d_grads + m->off_post1, d.P))) return rc;
-  for (int l = 0; l < d.L; ++l)
-    if ((rc = flat(pa.z, d.LD, l * d.D, d.D, pa.dskip, d.S, 0, d.S, d_grads + m->layers[l].skip, d.S))) return rc;
+  if (phase_begin == 0) {
+    if ((rc = flat(pa.h2, d.P, 0, d.P, pa.dlogits, d.Q, 0, d.Q, d_grads + m->off_post2, d.Q))) return rc;
+    if ((rc = flat(pa.h1, d.S, 0, d.S, pa.dp1, d.P, 0, d.P, d_grads + m->off_post1, d.P))) return rc;
+    for (int l = 0; l < d.L; ++l)
+      if ((rc = flat(pa.z, d.LD, l * d.D, d.D, pa.dskip, d.S, 0, d.S, d_grads + m->layers[l].skip, d.S))) return rc;
+  }
 
   const size_t sa = layer_bwd_a_smem(d.R, d.D), sb = layer_bwd_b_smem(d.R, d.D);
   if ((rc = set_smem(k_layer_bwd_a, sa))) return rc;
   if ((rc = set_smem(k_layer_bwd_b, sb))) return rc;
   bf16* dxbuf[2] = {reinterpret_cast<bf16*>(ws + wl.dx[0]), reinterpret_cast<bf16*>(ws + wl.dx[1])};
   bf16* dv = reinterpret_cast<bf16*>(ws + wl.dv);
-  const bf16* dx_next = nullptr;
   for (int l = d.L - 1; l >= 0; --l) {
+    const int phase = d.L - l;
+    if (phase < phase_begin || phase >= phase_end) continue;
+    const bf16* dx_next = (l == d.L - 1) ? nullptr : dxbuf[(l + 1) & 1];
     LayerBwdArgs la;
     memset(&la, 0, sizeof(la));
     la.wbf = wbf; la.params = d_params; la.ld = m->layers[l];
@@ -1032,8 +1121,11 @@ int wn_train_backward(wn_model* m, const float* d_params, const int32_t* d_wav, 
     la.ids = d_ids; la.grads = d_grads;
     la.B = d.B; la.T = T; la.R = d.R; la.D = d.D; la.LD = d.LD; la.l = l; la.C1 = d.C1;
     const dim3 grid((T + TM - 1) / TM, d.B);
-    k_layer_bwd_a<<<grid, NT, sa, st>>>(la);
-    WN_LAUNCH_CHECK();
+    {
+      ProfScope ps(PROF_LAYER_BWD_A, st);
+      k_layer_bwd_a<<<grid, NT, sa, st>>>(la);
+      WN_LAUNCH_CHECK();
+    }
     // weight gradients of this layer
     if (dx_next != nullptr)  // RESIDUAL_l [D][R] = z_l^T dx_{l+1}  (the last layer's output is unused)
       if ((rc = flat(pa.z, d.LD, l * d.D, d.D, dx_next, d.R, 0, d.R, d_grads + m->layers[l].res, d.R))) return rc;
@@ -1046,11 +1138,16 @@ int wn_train_backward(wn_model* m, const float* d_params, const int32_t* d_wav, 
         if ((rc = launch_wgrad(wa, m->sm_count, st))) return rc;
       }
     }
-    k_layer_bwd_b<<<grid, NT, sb, st>>>(la);
-    WN_LAUNCH_CHECK();
-    dx_next = la.dx_out;
+    {
+      ProfScope ps(PROF_LAYER_BWD_B, st);
+      k_layer_bwd_b<<<grid, NT, sb, st>>>(la);
+      WN_LAUNCH_CHECK();
+    }
   }
+  if (phase_end < d.L + 2) return WN_OK;
+  ProfScope ps_tail(PROF_EMBED_GC_BWD, st);
   {
+    const bf16* dx_next = dxbuf[0];  // gradient wrt the layer-0 input
     const size_t esm = ((size_t)d.Q * d.R + d.R) * sizeof(float);
     if ((rc = set_smem(k_embed_bwd, esm))) return rc;
     const int nblk = (int)std::min<int64_t>(m->sm_count * 2, (d.rows + 255) / 256);
@@ -1081,6 +1178,7 @@ int wn_adam_step(wn_model* m, float* d_params, const float* d_grads, float* d_m,
   if ((rc = ensure_kind(m))) return rc;
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step));
   const int64_t n = m->n_param_elems;
+  ProfScope ps(PROF_ADAM, (cudaStream_t)stream_);
   k_adam<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
       d_params, d_grads, d_m, d_v, m->d_kind, d_n_valid, n, (float)lr_t, l2_factor, beta1, beta2, eps);
   WN_LAUNCH_CHECK();
