@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Benchmark of the lb-wavenet hot path on B200 (contract: see the task's bench.py section).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric: training output timesteps/s (= B*(T-1) loss positions per optimiser step / step time,
+forward + backward + gradient all-reduce + Adam), BASELINE.json configs[1]: classic 3x10 stack,
+R=D=32, S=P=256, 32 slots per GPU, slice_sz 16384, bf16 operands.  N>1 (torchrun): the B=32*N
+slots are sharded 32 per GPU (weak scaling, BASELINE.json configs[2] at N=8).
+Extra keys: `gen` = batched incremental generation audio samples/s on 1 GPU (256 streams).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ARCH_FILE = os.path.join(ROOT, "par", "arch_classic_3x10.json")
+SLOTS_PER_GPU = 32
+SLICE_SZ = 16384
+GEN_STREAMS = 256
+GEN_STEPS = 1000
+
+
+def train_flop_per_timestep(a) -> float:
+    """fwd = L*(8RD + 2DR + 2DS [+4GD]) + 2SP + 2PQ ; train = 3 x fwd."""
+    L = a["n_blocks"] * a["n_block_layers"]
+    R, D, S, P, Q, G = a["n_res"], a["n_dil"], a["n_skip"], a["n_post"], a["n_quant"], a["n_gc_embed"]
+    fwd = L * (8 * R * D + 2 * D * R + 2 * D * S + 4 * G * D) + 2 * S * P + 2 * P * Q
+    return 3.0 * fwd
+
+
+def post_fwd_flop_per_timestep(a) -> float:
+    """skip GEMM (concat-K over layers) + POST1 + POST2: the dominant forward kernel."""
+    L = a["n_blocks"] * a["n_block_layers"]
+    D, S, P, Q = a["n_dil"], a["n_skip"], a["n_post"], a["n_quant"]
+    return 2.0 * L * D * S + 2.0 * S * P + 2.0 * P * Q
+
+
+def synth_slots(n_slots, T, n_batches, seed, recep_field):
+    """Synthetic 16 kHz audio per slot: 3 sinusoids + noise, mu-law encoded by the loader's own
+    dealer from in-memory 'files' of length U[2F, 8F], ids from the real slot dealer."""
+    from lb_wavenet_b200.data import SlotDealer
+    rng = np.random.default_rng(seed)
+    files = []
+    for i in range(max(8, n_slots)):
+        n = int(rng.integers(2 * recep_field, 8 * recep_field))
+        t = np.arange(n)
+        f = rng.uniform(100, 4000, 3) / 16000.0
+        x = sum(0.3 * np.sin(2 * np.pi * fi * t + rng.uniform(0, 6.28)) for fi in f) + rng.normal(0, 0.05, n)
+        x = np.clip(x, -1, 1)
+        q = (np.sign(x) * np.log1p(255 * np.abs(x)) / np.log1p(255) + 1) * 0.5 * 255 + 0.5  # mu-law codes
+        files.append((int(rng.integers(1, 100)), q.astype(np.int32)))
+    d = SlotDealer(files, n_slots, T, recep_field, 1, seed, 0, quiet=True)
+    return [d.next_batch()[1:] for _ in range(n_batches)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(arch, steps, warmup, n_threads=None):
+    """The reference's CPU implementation of the path: the oracle port (torch CPU fp32, op for op
+    as tmodel.py:292-340 + TF Adam), timed on a bounded sample of the workload with all host threads."""
+    import torch
+    from oracle import wavenet_oracle as O
+    n_threads = n_threads or os.cpu_count() or 1
+    torch.set_num_threads(n_threads)
+    a = O.Arch(arch["n_blocks"], arch["n_block_layers"], arch["n_quant"], arch["n_res"], arch["n_dil"],
+               arch["n_skip"], arch["n_post"], arch["n_gc_embed"], arch["n_gc_category"], bool(arch["use_bias"]))
+    B, T = 8, 8192
+    p = O.init_params(a, B, seed=0)
+    wav, ids = synth_slots(B, T, 1, 1234, a.recep_field())[0]
+    ids = np.maximum(ids, 1)  # bounded sample: keep every position valid so the work is the same per step
+    m = {k: np.zeros_like(v) for k, v in p.items() if v.dtype.kind == "f" and not k.startswith("SAVE")}
+    v2 = {k: np.zeros_like(v) for k, v in m.items()}
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        grads, L, fwd = O.train_step_autograd(a, p, wav, ids, 1e-3, torch.float32)
+        for k in m:
+            g = grads[k].astype(np.float32)
+            p[k], m[k], v2[k] = O.adam_tf_step(p[k], g, m[k], v2[k], it + 1, 1e-3)
+            p[k] = p[k].astype(np.float32)
+        for li, name in enumerate(n for n in p if n.startswith("SAVE")):
+            p[name] = fwd.new_save[li].numpy().astype(np.float32)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    per_step = float(np.mean(times))
+    return dict(value=B * (T - 1) / per_step, ms_per_step=per_step * 1e3, cores=n_threads,
+                sample="%d slots x %d timesteps per step, %d steps, torch-CPU fp32 port of the reference graph "
+                       "(TensorFlow 1.x not installable)" % (B, T, steps), B=B, T=T)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-gen", action="store_true", help="skip the generation leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--slots", type=int, default=SLOTS_PER_GPU)
+    ap.add_argument("--slice", type=int, default=SLICE_SZ)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    from lb_wavenet_b200 import config
+    arch = config.load_arch(ARCH_FILE)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    base = {
+        "metric": "train output timesteps/s", "unit": "timesteps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1]: classic 3x10 (R=D=32,S=P=256), %d slots/GPU x slice_sz %d, "
+                               "one stage-wise training step (fwd+bwd+allreduce+Adam)" % (args.slots, args.slice),
+                   "arch_file": "par/arch_classic_3x10.json", "slots_per_gpu": args.slots, "slice_sz": args.slice,
+                   "global_slots": args.slots * args.gpus, "parallelism": "dp%d over slots" % args.gpus,
+                   "l2_flush": "inputs and activation stash (>4 GB/step) far exceed the 126 MB L2"},
+    }
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_reference_run(arch, args.steps, args.warmup)
+        line = dict(base)
+        line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"],
+                     "dtype": "f32", "gpu_launches": 0,
+                     "cpu_baseline": {"value": r["value"], "unit": "timesteps/s", "cores": r["cores"], "kind": "port",
+                                      "sample": r["sample"]},
+                     "e2e": {"value": r["value"], "unit": "timesteps/s", "h2d_bytes_per_step": 0,
+                             "d2h_bytes_per_step": 0}})
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    from lb_wavenet_b200 import _lib
+    from lb_wavenet_b200.dist import DistContext
+    from lb_wavenet_b200.tmodel import AdamOptimizer, WaveNetTrain
+    lib = _lib.load()
+    ctx = DistContext.from_env("nccl" if world > 1 else None)
+    if world == 1:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", ctx.local_rank)
+    B_total, T = args.slots * max(world, 1), args.slice
+    net = WaveNetTrain(**arch, batch_sz=B_total, l2_factor=1e-3, add_summary=False, n_keep_checkpoints=1,
+                       ckpt_path="/tmp/bench.net", resume_step=0, n_valid_total=1, print_interval=0, dist=ctx,
+                       init_seed=0, device=str(dev))
+    net.build()
+    net.init_vars()
+    opt = AdamOptimizer(1e-3)
+    F = net.get_recep_field_sz()
+    n_batches = 2
+    host_batches = synth_slots(args.slots, T, n_batches, 1234 + rank, F)
+    pinned = [(torch.as_tensor(w).pin_memory(), torch.as_tensor(i).pin_memory()) for w, i in host_batches]
+    dev_batches = [(w.to(dev), i.to(dev)) for w, i in pinned]
+    torch.cuda.synchronize()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        ctx.barrier()
+
+    # ---- device-resident timing: `value` ---------------------------------------------------
+    for s in range(args.warmup):
+        w, i = dev_batches[s % n_batches]
+        net.train_step(w, i, opt, want_loss=False)
+    sync_all()
+    clocks = ClockSampler(ctx.local_rank)
+    if rank == 0:
+        clocks.start()
+    lib.wn_launch_count_reset()
+    lib.wn_prof_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        w, i = dev_batches[s % n_batches]
+        net.train_step(w, i, opt, want_loss=False)
+    e1.record()
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    launches = int(lib.wn_launch_count_reset())
+    import ctypes as C
+    prof_ms = (C.c_double * 16)()
+    prof_n = (C.c_int64 * 16)()
+    lib.wn_prof_collect(prof_ms, prof_n)
+    lib.wn_prof_enable(0)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = B_total * (T - 1) / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the public API with host buffers: `e2e` --------------------------------
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss = None
+    for s in range(args.steps):
+        w, i = pinned[s % n_batches]
+        loss = net.train_step(w, i, opt, want_loss=True)  # H2D of the inputs + D2H of the loss inside
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / args.steps
+    e2e = {"value": B_total * (T - 1) / (e2e_ms * 1e-3), "unit": "timesteps/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(2 * args.slots * T * 4 * max(world, 1)),
+           "d2h_bytes_per_step": int(8 * _lib.WN_NSTATS * max(world, 1)), "loss": loss}
+
+    if rank != 0:
+        ctx.barrier()
+        return 0
+
+    # ---- roofline of the dominant kernel (category timing from CUDA events on the launch stream) ----
+    cats = ["prep_embed_save", "layer_fwd", "post_fwd_loss", "post_bwd", "layer_bwd_gate", "layer_bwd_data",
+            "wgrad", "pre_gc_bwd", "adam", "gen"]
+    shares = {c: {"ms_per_step": prof_ms[k] / args.steps, "launches_per_step": prof_n[k] / args.steps}
+              for k, c in enumerate(cats) if prof_n[k] > 0}
+    peaks = {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        with open(pk) as f:
+            mp = json.load(f)
+        peaks = {"bf16_tflops": mp.get("bf16_tflops_sustained", mp["bf16_tflops"]), "hbm_gbs": mp["hbm_gbs"],
+                 "source": "MEASURED_PEAKS.json (sustained bf16: kernel timed inside a long step)"}
+    dom = max(shares, key=lambda c: shares[c]["ms_per_step"]) if shares else None
+    rows = args.slots * T
+    flop_by_cat = {
+        "post_fwd_loss": post_fwd_flop_per_timestep(arch) * rows,
+        "post_bwd": post_fwd_flop_per_timestep(arch) * rows,       # dgrad chain: same contractions transposed
+        "wgrad": train_flop_per_timestep(arch) / 3.0 * rows,          # every contraction once more
+    }
+    roofline = None
+    if dom is not None:
+        dms = shares[dom]["ms_per_step"]
+        if dom in flop_by_cat:
+            ach = flop_by_cat[dom] / (dms * 1e-3) / 1e12
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"],
+                        "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
+                        "peak_source": peaks["source"], "ms_per_step": dms}
+        else:
+            L = arch["n_blocks"] * arch["n_block_layers"]
+            byts = {"layer_fwd": L * 3 * arch["n_res"] * 2, "layer_bwd_gate": L * (2 * arch["n_res"] + 4 * arch["n_dil"]) * 2,
+                    "layer_bwd_data": L * (4 * arch["n_dil"] + 2 * arch["n_res"]) * 2}.get(dom, 0) * rows
+            ach = byts / (dms * 1e-3) / 1e9
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                        "ms_per_step": dms}
+    whole = value * train_flop_per_timestep(arch) / 1e12
+
+    line = dict(base)
+    line.update({"value": value, "ms_per_step": ms_per_step, "e2e": e2e, "gpu_launches": launches,
+                 "clocks": clk, "roofline": roofline,
+                 "whole_step_tflops": whole, "whole_step_frac_of_bf16_peak": whole / peaks["bf16_tflops"] / max(world, 1),
+                 "kernel_shares": shares})
+
+    # ---- generation leg (1 GPU, rank 0): batched incremental generation samples/s --------------------
+    if not args.no_gen and world == 1:
+        try:
+            from lb_wavenet_b200.engine import GenEngine
+            g = GenEngine(net._arch_dict, GEN_STREAMS, str(dev))
+            g.load_params(net.engine.params)
+            g.run(50, seed=0)
+            torch.cuda.synchronize()
+            lib.wn_launch_count_reset()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.run(GEN_STEPS, seed=0)
+            e1.record()
+            torch.cuda.synchronize()
+            gms = e0.elapsed_time(e1)
+            sps = GEN_STREAMS * GEN_STEPS / (gms * 1e-3)
+            L = arch["n_blocks"] * arch["n_block_layers"]
+            ring_bytes = L * 2 * arch["n_res"] * 2
+            line["gen"] = {"metric": "batched gen audio samples/s", "value": sps, "streams": GEN_STREAMS,
+                           "steps": GEN_STEPS, "us_per_step": gms * 1e3 / GEN_STEPS,
+                           "realtime_multiple_per_stream": sps / GEN_STREAMS / 16000.0,
+                           "ring_gbs": sps * ring_bytes / 1e9, "gpu_launches": int(lib.wn_launch_count_reset())}
+        except Exception as e:  # the training line must survive a generator failure
+            line["gen"] = {"error": repr(e)}
+
+    # ---- CPU baseline beside it (bounded sample) ------------------------------------------------------
+    if not args.no_cpu and world == 1:
+        r = cpu_reference_run(arch, 3, 1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "timesteps/s", "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"]}
+    print(json.dumps(line))
+    if world > 1:
+        ctx.barrier()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
