@@ -40,7 +40,8 @@ class Variable:
         self._get, self._set, self.trainable = get, set, trainable
 
     def numpy(self) -> np.ndarray:
-        return np.ascontiguousarray(np.asarray(self._get()).astype(self.dtype).reshape(self.shape))
+        # (np.ascontiguousarray would turn a 0-d scalar into shape (1,))
+        return np.array(np.asarray(self._get()), dtype=self.dtype, order="C").reshape(self.shape)
 
     def assign(self, value) -> None:
         v = np.asarray(value)
@@ -85,18 +86,22 @@ class Checkpoint(object):
                     steps.append(int(m.group(1)))
         return sorted(steps)
 
-    def save(self, step: int) -> str:
-        """reference ckpt.py:54-62 -> '<ckpt_path>-<step>'"""
+    def save(self, step: int, write: bool = True) -> str:
+        """reference ckpt.py:54-62 -> '<ckpt_path>-<step>'.  Data-parallel ranks all call save() (reading a
+        sharded variable is a collective gather); only the rank with write=True touches the disk."""
         if not self.initialized:
             raise ValueError("add_saveable_objects has not been called")
         path_pfx = "{}-{}".format(self.ckpt_path, int(step))
+        values = {key: self.saveable_objects[key].numpy() for key in sorted(self.saveable_objects)}
+        if not write:
+            return path_pfx
         d = os.path.dirname(path_pfx)
         if d:
             os.makedirs(d, exist_ok=True)
         index, off = {}, 0
         with open(path_pfx + ".data-00000-of-00001.tmp", "wb") as f:
-            for key in sorted(self.saveable_objects):
-                arr = self.saveable_objects[key].numpy()
+            for key in sorted(values):
+                arr = values[key]
                 raw = arr.astype(arr.dtype.newbyteorder("<")).tobytes()
                 f.write(raw)
                 index[key] = dict(dtype=arr.dtype.name, shape=list(arr.shape), offset=off, size=len(raw),

@@ -245,6 +245,7 @@ class FwdResult:
     xs: List[torch.Tensor] = field(default_factory=list)  # layer inputs x_l  [B,T,R]
     zs: List[torch.Tensor] = field(default_factory=list)  # gated outputs z_l [B,T,D]
     skip_sum: Optional[torch.Tensor] = None
+    x_out: Optional[torch.Tensor] = None  # residual stream after the last layer (unused by the loss)
 
 
 def _t(p, name, dtype):
@@ -326,7 +327,7 @@ def train_forward(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.Tensor],
     logits = h2 @ W("POST2")
     if a.use_bias:
         logits = logits + p["POST2_BIAS"]
-    return FwdResult(logits=logits, new_save=new_save, xs=xs, zs=zs, skip_sum=skp_sum)
+    return FwdResult(logits=logits, new_save=new_save, xs=xs, zs=zs, skip_sum=skp_sum, x_out=cur)
 
 
 @dataclass
