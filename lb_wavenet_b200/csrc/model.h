@@ -46,6 +46,11 @@ struct WorkspaceLayout {
   int64_t gc_tbl;     // [L][C+1][2D] fp32 (GC projections incl. nothing else)
   int64_t dgc_tbl;    // same shape, gradient
   int64_t skip_bias;  // [S] fp32, sum over layers of SKIP_BIAS
+  // transposed / concatenated bf16 weight copies for the tcgen05 kernels (B operands, N x K K-major)
+  int64_t wsT;        // [S][L*D]   = SKIP_l[d][s] at [s][l*D+d]
+  int64_t wsCat;      // [L*D][S]   = SKIP_l stacked over layers
+  int64_t w1T;        // [P][S]     = POST1^T
+  int64_t w2T;        // [Q][P]     = POST2^T
   int64_t total;
   std::vector<int64_t> xfull;  // per layer: [B][dil+T][R] bf16
 };

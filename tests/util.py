@@ -14,6 +14,7 @@ WIDE = dict(n_blocks=1, n_block_layers=3, n_quant=256, n_res=128, n_dil=128, n_s
             n_gc_embed=0, n_gc_category=0, use_bias=1)
 CLASSIC = dict(n_blocks=3, n_block_layers=10, n_quant=256, n_res=32, n_dil=32, n_skip=256, n_post=256,
                n_gc_embed=0, n_gc_category=0, use_bias=1)
+CLASSIC_SHALLOW = dict(CLASSIC, n_blocks=1, n_block_layers=4)
 C1 = dict(n_blocks=5, n_block_layers=10, n_quant=256, n_res=32, n_dil=32, n_skip=512, n_post=512,
           n_gc_embed=17, n_gc_category=377, use_bias=1)
 
