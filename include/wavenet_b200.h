@@ -178,6 +178,11 @@ int wn_sample_logits(const float* d_logits, int32_t n_rows, uint64_t seed, int64
 int wn_selftest_umma_gemm(const void* d_a, const void* d_b, float* d_c, int32_t M, int32_t N,
                           int32_t K, int32_t swizzle, void* stream);
 
+/* C[M,N] fp32 += A[K,M]^T x B[K,N] (both bf16 row-major, i.e. MN-major operands: the contraction index
+ * is the slow one in memory) through the split-K weight-gradient kernel; zero d_c first. */
+int wn_selftest_umma_gemm_tn(const void* d_a, const void* d_b, float* d_c, int32_t M, int32_t N,
+                             int32_t K, void* stream);
+
 /* Per-category kernel timing with CUDA events recorded on the launch stream around every kernel
  * launch (bench.py's roofline figures).  Categories: 0 prep/embed/SAVE, 1 layer forward, 2 post-net
  * forward + loss, 3 post-net backward, 4 layer backward (gate), 5 layer backward (data), 6 weight

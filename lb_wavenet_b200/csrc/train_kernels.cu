@@ -49,6 +49,9 @@ ProfScope::~ProfScope() {
 // tcgen05 generation (train_umma.cu)
 bool umma_post_supported(const wn_model* m);
 int launch_prep_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st);
+bool umma_wgrad_supported(const wn_model* m, int lda, int ldy, int N);
+int launch_wgrad_umma(wn_model* m, const bf16* A, int lda, int a_col0, int M_total, const bf16* Y, int ldy, int N,
+                      int64_t rows, float* out, int ldo, int mode, float* grads, cudaStream_t st);
 int launch_post_bwd_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, cudaStream_t st);
 int launch_post_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_wav,
                          const int32_t* d_ids, int T, double* d_stats, float* d_logits, cudaStream_t st);
@@ -1108,10 +1111,21 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
     return launch_wgrad(wa, m->sm_count, st);
   };
   if (phase_begin == 0) {
-    if ((rc = flat(pa.h2, d.P, 0, d.P, pa.dlogits, d.Q, 0, d.Q, d_grads + m->off_post2, d.Q))) return rc;
-    if ((rc = flat(pa.h1, d.S, 0, d.S, pa.dp1, d.P, 0, d.P, d_grads + m->off_post1, d.P))) return rc;
-    for (int l = 0; l < d.L; ++l)
-      if ((rc = flat(pa.z, d.LD, l * d.D, d.D, pa.dskip, d.S, 0, d.S, d_grads + m->layers[l].skip, d.S))) return rc;
+    if (umma_wgrad_supported(m, d.P, d.Q, d.Q) && umma_wgrad_supported(m, d.S, d.P, d.P) &&
+        umma_wgrad_supported(m, d.LD, d.S, d.S)) {
+      // POST2 [P][Q] = h2^T dlogits ; POST1 [S][P] = h1^T dp1 ; SKIP_l [D][S] = z_l^T dskip for all layers at once
+      if ((rc = launch_wgrad_umma(m, pa.h2, d.P, 0, d.P, pa.dlogits, d.Q, d.Q, d.rows, d_grads + m->off_post2, d.Q, 0,
+                                  d_grads, st))) return rc;
+      if ((rc = launch_wgrad_umma(m, pa.h1, d.S, 0, d.S, pa.dp1, d.P, d.P, d.rows, d_grads + m->off_post1, d.P, 0,
+                                  d_grads, st))) return rc;
+      if ((rc = launch_wgrad_umma(m, pa.z, d.LD, 0, d.LD, pa.dskip, d.S, d.S, d.rows, nullptr, d.S, 1, d_grads, st)))
+        return rc;
+    } else {
+      if ((rc = flat(pa.h2, d.P, 0, d.P, pa.dlogits, d.Q, 0, d.Q, d_grads + m->off_post2, d.Q))) return rc;
+      if ((rc = flat(pa.h1, d.S, 0, d.S, pa.dp1, d.P, 0, d.P, d_grads + m->off_post1, d.P))) return rc;
+      for (int l = 0; l < d.L; ++l)
+        if ((rc = flat(pa.z, d.LD, l * d.D, d.D, pa.dskip, d.S, 0, d.S, d_grads + m->layers[l].skip, d.S))) return rc;
+    }
   }
 
   const size_t sa = layer_bwd_a_smem(d.R, d.D), sb = layer_bwd_b_smem(d.R, d.D);

@@ -696,3 +696,174 @@ int launch_post_bwd_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, 
 }
 
 }  // namespace wn
+
+// =====================================================================================================
+// k_wgrad_umma: dW[m][n] += sum_rows A[row][a_col0 + m] * Y[row][n]      (weight gradients, split-K)
+// Both operands are MN-major for the tensor core (the contraction index -- time -- is the slow one in
+// memory), staged by TMA as 64-column SW128 panels.  One CTA owns a 128 x N output tile (N <= 256) in TMEM
+// and a contiguous range of 64-row K blocks; partial sums are reduced with coalesced fp32 atomics.
+// =====================================================================================================
+namespace wn {
+
+constexpr int WG_BK = 64;                 // rows (timesteps) per K block
+constexpr int WG_PANEL = WG_BK * 128;     // one 64-column panel: 8 KB
+constexpr int WG_STAGES = 4;
+constexpr int WG_A_BYTES = 2 * WG_PANEL;  // M = 128
+constexpr int WG_B_BYTES = 4 * WG_PANEL;  // N <= 256
+
+struct WgradUmmaArgs {
+  float* out;                 // mode 0: out[m * ldo + n]
+  const LayerDesc* layers;    // mode 1: row m = l*D + d -> grads + layers[l].skip + d * ldo
+  float* grads;
+  int mode, D, ldo;
+  int M_total, N;
+  int a_col0;
+  int64_t kblocks_total, kblocks_per_cta;
+};
+
+__global__ void __launch_bounds__(UPOST_THREADS, 1)
+k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_y, WgradUmmaArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* stage_a = smem;
+  unsigned char* stage_b = smem + WG_STAGES * WG_A_BYTES;
+  __shared__ __align__(8) uint64_t full_bar[WG_STAGES], empty_bar[WG_STAGES], acc_full;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * 128;
+  const int64_t kb0 = (int64_t)blockIdx.y * a.kblocks_per_cta;
+  const int64_t kb1 = min(a.kblocks_total, kb0 + a.kblocks_per_cta);
+  const int nkb = (int)max((int64_t)0, kb1 - kb0);
+  const int N = a.N, npan = (N + 63) / 64;
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)N) ncols <<= 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < WG_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&acc_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_y);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int it = 0; it < nkb; ++it) {
+          const int st = it % WG_STAGES;
+          mbar_wait(&empty_bar[st], ((uint32_t)(it / WG_STAGES) & 1u) ^ 1u);
+          mbar_expect_tx(&full_bar[st], (uint32_t)((2 + npan) * WG_PANEL));
+          const int row = (int)((kb0 + it) * WG_BK);
+          for (int c = 0; c < 2; ++c)
+            tma_load_2d(stage_a + st * WG_A_BYTES + c * WG_PANEL, &map_a, &full_bar[st], a.a_col0 + m0 + c * 64, row);
+          for (int c = 0; c < npan; ++c)
+            tma_load_2d(stage_b + st * WG_B_BYTES + c * WG_PANEL, &map_y, &full_bar[st], c * 64, row);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N, true, true);
+        for (int it = 0; it < nkb; ++it) {
+          const int st = it % WG_STAGES;
+          mbar_wait(&full_bar[st], (uint32_t)(it / WG_STAGES) & 1u);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(stage_a + st * WG_A_BYTES), sb = smem_u32(stage_b + st * WG_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < WG_BK / 16; ++k)
+            mma_bf16_ss(tmem_base, make_mnmajor_desc(sa + k * 16 * 128, 128, WG_PANEL),
+                        make_mnmajor_desc(sb + k * 16 * 128, 128, WG_PANEL), idesc, (it | k) != 0);
+          mma_commit(&empty_bar[st]);
+        }
+        mma_commit(&acc_full);
+      }
+    } else {
+      // epilogue: TMEM -> fp32 staging in the (now idle) pipeline buffers -> coalesced atomics
+      const int q4 = warp & 3;
+      const int r = q4 * 32 + lane;
+      const int et = (warp - 2) * 32 + lane;
+      float* stg = reinterpret_cast<float*>(smem);  // [128][N + 1]
+      const int lds = N + 1;
+      mbar_wait(&acc_full, 0);
+      tc_fence_after_sync();
+      uint32_t v[32];
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < N) stg[r * lds + c0 + j] = __uint_as_float(v[j]);
+      }
+      epi_bar_sync();
+      for (int idx = et; idx < 128 * N; idx += 128) {
+        const int rr = idx / N, c = idx % N;
+        const int m = m0 + rr;
+        if (m < a.M_total) {
+          const float val = stg[rr * lds + c];
+          float* dst = a.mode == 0 ? a.out + (size_t)m * a.ldo + c
+                                   : a.grads + a.layers[m / a.D].skip + (size_t)(m % a.D) * a.ldo + c;
+          if (val != 0.f) atomicAdd(dst, val);
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// A: [rows][lda] bf16 (columns a_col0 .. a_col0 + M_total), Y: [rows][N] bf16 (row pitch ldy)
+int launch_wgrad_umma(wn_model* m, const bf16* A, int lda, int a_col0, int M_total, const bf16* Y, int ldy, int N,
+                      int64_t rows, float* out, int ldo, int mode, float* grads, cudaStream_t st) {
+  CUtensorMap ma, my;
+  int rc;
+  if ((rc = map2d(&ma, A, (uint64_t)lda, (uint64_t)rows, 64, WG_BK))) return rc;
+  if ((rc = map2d(&my, Y, (uint64_t)ldy, (uint64_t)rows, 64, WG_BK))) return rc;
+  WgradUmmaArgs wa;
+  memset(&wa, 0, sizeof(wa));
+  wa.out = out; wa.layers = m->d_layers; wa.grads = grads; wa.mode = mode; wa.D = m->a.n_dil; wa.ldo = ldo;
+  wa.M_total = M_total; wa.N = N; wa.a_col0 = a_col0;
+  wa.kblocks_total = (rows + WG_BK - 1) / WG_BK;
+  const int m_tiles = (M_total + 127) / 128;
+  const int sms = std::max(1, m->sm_count);
+  int64_t splits = std::max<int64_t>(1, std::min<int64_t>(wa.kblocks_total, sms / m_tiles));
+  wa.kblocks_per_cta = (wa.kblocks_total + splits - 1) / splits;
+  splits = (wa.kblocks_total + wa.kblocks_per_cta - 1) / wa.kblocks_per_cta;
+  const size_t smem = (size_t)WG_STAGES * (WG_A_BYTES + WG_B_BYTES) + 1024;
+  WN_CUDA_CHECK(cudaFuncSetAttribute(k_wgrad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps(PROF_WGRAD, st);
+  k_wgrad_umma<<<dim3(m_tiles, (unsigned)splits), UPOST_THREADS, smem, st>>>(ma, my, wa);
+  WN_LAUNCH_CHECK();
+  return WN_OK;
+}
+
+bool umma_wgrad_supported(const wn_model* m, int lda, int ldy, int N) {
+  return umma_post_supported(m) && N % 16 == 0 && N <= 256 && lda % 8 == 0 && ldy % 8 == 0;
+}
+
+}  // namespace wn
+
+// C[M][N] (fp32, accumulated into: zero it first) += A[K][M]^T . B[K][N]; both operands MN-major
+extern "C" int wn_selftest_umma_gemm_tn(const void* d_a, const void* d_b, float* d_c, int32_t M, int32_t N,
+                                        int32_t K, void* stream_) {
+  using namespace wn;
+  if (!d_a || !d_b || !d_c || M < 1 || N < 16 || N > 256 || N % 16 || M % 8 || K < 1) {
+    set_error("wn_selftest_umma_gemm_tn: invalid argument");
+    return WN_ERR_INVALID;
+  }
+  wn_model fake;
+  fake.a.n_dil = 1;
+  fake.d_layers = nullptr;
+  int dev = 0;
+  WN_CUDA_CHECK(cudaGetDevice(&dev));
+  WN_CUDA_CHECK(cudaDeviceGetAttribute(&fake.sm_count, cudaDevAttrMultiProcessorCount, dev));
+  return launch_wgrad_umma(&fake, reinterpret_cast<const bf16*>(d_a), M, 0, M, reinterpret_cast<const bf16*>(d_b), N, N,
+                           K, d_c, N, 0, nullptr, (cudaStream_t)stream_);
+}

@@ -159,6 +159,22 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t tile_smem_addr, in
   return d;
 }
 
+// MN-major operand (the contraction index is the slow one in memory): shared memory holds, for every
+// chunk of swizzle_bytes/2 MN-elements, a [K rows][swizzle_bytes] panel -- exactly what TMA writes for a
+// box {swizzle_bytes/2, BK} with that swizzle mode; panels of consecutive MN chunks are chunk_stride
+// bytes apart (LBO); 8-row K groups are 8*swizzle_bytes apart (SBO).  `addr` points at the K row the
+// instruction starts from (advance by 16 rows = 16*swizzle_bytes per UMMA_K step).
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t addr, int swizzle_bytes, uint32_t chunk_stride) {
+  const uint32_t sbo = 8u * (uint32_t)swizzle_bytes;
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((chunk_stride >> 4) & 0x3FFFu) << 16;  // LBO
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;           // SBO
+  d |= (uint64_t)1u << 46;
+  d |= (uint64_t)swizzle_layout_type(swizzle_bytes) << 61;
+  return d;
+}
+
 // kind::f16 instruction descriptor: BF16 x BF16 -> F32, both operands K-major, M x N tile
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major = false,
                                                        bool b_mn_major = false) {

@@ -69,3 +69,19 @@ def test_umma_selftest_gemm(lib, sw, M, N, K):
     ref = A.float().cpu() @ B.float().cpu().T
     err = (Cd.cpu() - ref).abs().max().item()
     assert err <= 1e-3 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 640), (960, 256, 1000), (64, 64, 200), (256, 96, 4096), (200, 16, 77)])
+def test_umma_selftest_gemm_tn_mn_major(lib, M, N, K):
+    """The split-K weight-gradient kernel (both operands MN-major, TMA SW128 panels, fp32 atomics) against
+    a plain fp32 matmul: C = A^T B with A [K, M], B [K, N] row-major; ragged M, N, K included."""
+    from lb_wavenet_b200 import _lib
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    A = torch.randn(K, M, generator=g).to(torch.bfloat16).cuda()
+    B = torch.randn(K, N, generator=g).to(torch.bfloat16).cuda()
+    Cd = torch.zeros(M, N, dtype=torch.float32, device="cuda")
+    _lib.check(lib.wn_selftest_umma_gemm_tn(A.data_ptr(), B.data_ptr(), Cd.data_ptr(), M, N, K, _lib.cur_stream()))
+    torch.cuda.synchronize()
+    ref = A.float().cpu().T @ B.float().cpu()
+    err = (Cd.cpu() - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), err
