@@ -49,6 +49,11 @@ ProfScope::~ProfScope() {
 // tcgen05 generation (train_umma.cu)
 bool umma_post_supported(const wn_model* m);
 int launch_prep_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st);
+bool umma_layer_supported(const wn_model* m);
+int launch_prep_layer_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st);
+int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_ids, int T, int l,
+                          cudaStream_t st);
+int launch_layer_bwd_dx_umma(wn_model* m, unsigned char* ws, int T, int l, cudaStream_t st);
 bool umma_wgrad_supported(const wn_model* m, int lda, int ldy, int N);
 int launch_wgrad_umma(wn_model* m, const bf16* A, int lda, int a_col0, int M_total, const bf16* Y, int ldy, int N,
                       int64_t rows, float* out, int ldo, int mode, float* grads, cudaStream_t st);
@@ -965,6 +970,7 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
   const bool gc = d.G > 0;
 
   const bool umma_post = umma_post_supported(m);
+  const bool umma_layer = umma_layer_supported(m);
   {
   ProfScope ps_prep(PROF_PREP, st);
   k_cast_params<<<(unsigned)((m->n_param_elems + 255) / 256), 256, 0, st>>>(d_params, wbf, m->n_param_elems);
@@ -980,6 +986,7 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
     WN_LAUNCH_CHECK();
   }
   if (umma_post && (rc = launch_prep_umma(m, d_params, ws, st))) return rc;
+  if (umma_layer && (rc = launch_prep_layer_umma(m, d_params, ws, st))) return rc;
   WN_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(double) * 3, st));
   k_save_load<<<dim3(64, d.L), 256, 0, st>>>(reinterpret_cast<const bf16*>(d_save), ws, m->d_layers, d.B, T, d.R);
   WN_LAUNCH_CHECK();
@@ -995,6 +1002,10 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
   rc = set_smem(k_layer_fwd, lsm);
   if (rc) return rc;
   for (int l = 0; l < d.L; ++l) {
+    if (umma_layer) {
+      if ((rc = launch_layer_fwd_umma(m, d_params, ws, d_ids, T, l, st))) return rc;
+      continue;
+    }
     ProfScope ps(PROF_LAYER_FWD, st);
     LayerArgs la;
     la.wbf = wbf; la.params = d_params; la.ld = m->layers[l];
@@ -1166,7 +1177,9 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
         if ((rc = launch_wgrad(wa, m->sm_count, st))) return rc;
       }
     }
-    {
+    if (umma_layer_supported(m)) {
+      if ((rc = launch_layer_bwd_dx_umma(m, ws, T, l, st))) return rc;
+    } else {
       ProfScope ps(PROF_LAYER_BWD_B, st);
       k_layer_bwd_b<<<grid, NT, sb, st>>>(la);
       WN_LAUNCH_CHECK();
