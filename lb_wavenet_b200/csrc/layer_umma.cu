@@ -310,6 +310,274 @@ k_layer_bwd_dx_umma(const __grid_constant__ CUtensorMap map_dv, const __grid_con
   if (warp == 0) tmem_dealloc(tmem_base_s, NCOL);
 }
 
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// =====================================================================================================
+// k_layer_bwd_gate_umma: persistent gate-backward kernel with in-TMEM weight-gradient accumulation.
+//   per 128-timestep tile (one slot):
+//     acc_v = x[t-dil] . W[0] + x[t] . W[1]                  (recomputed pre-activations, SIGNAL | GATE)
+//     acc_d = dx_{l+1}[t] . RESIDUAL^T                       (residual part of dz)
+//     th = tanh(v_s + b), sg = sigmoid(v_g + b), z = th * sg (bf16, the tile the forward stored)
+//     dz = dz_skip (from the post-net backward) + acc_d
+//     dv = [dz * sg * (1 - th^2) | dz * th * sg * (1 - sg)]   -> bf16 tile -> TMA store (data-gradient kernel)
+//   weight gradients, accumulated across ALL tiles of the CTA in tensor memory (MN-major operands are the
+//   very same shared-memory tiles, re-described):
+//     acc_wc[0:64 , 0:64] += [x[t-dil] | x[t]]^T . dv         (SIGNAL / GATE taps 0 and 1)
+//     acc_wr[64:96, 0:32] += z^T . dx_{l+1}                    (RESIDUAL)
+//   bias gradients = column sums of the dv / dx_{l+1} tiles, accumulated in registers across tiles.
+//   One flush (coalesced fp32 atomics) per CTA at the end.
+// =====================================================================================================
+struct LayerGateUmmaArgs {
+  const float* params;
+  float* grads;
+  int64_t sig, gate, res, sig_b, gate_b, res_b;
+  int T, dil, l, has_next, n_tiles, tiles_per_slot;
+};
+
+template <int R, int D>
+__global__ void __launch_bounds__(192, 1)
+k_layer_bwd_gate_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz,
+                      const __grid_constant__ CUtensorMap map_dxn, const __grid_constant__ CUtensorMap map_dv,
+                      const __grid_constant__ CUtensorMap map_wc, const __grid_constant__ CUtensorMap map_wrn,
+                      LayerGateUmmaArgs a) {
+  static_assert(R == 32 && D == 32, "tile bookkeeping below assumes 64-byte activation rows");
+  constexpr int XB = 64, VB = 128;
+  constexpr int PANEL = 128 * XB;                 // 8 KB: one [128 x 32] bf16 tile
+  constexpr int STAGE = 5 * PANEL + 128 * VB;     // x0 | x1 | z | dz | dxn | dv(16 KB)
+  constexpr int NST = 2;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* wc0 = smem + NST * STAGE;        // [2D rows][R]   4 KB
+  unsigned char* wc1 = wc0 + 2 * D * XB;
+  unsigned char* wrn = wc1 + 2 * D * XB;          // [D rows][R]    2 KB
+  float* stg = reinterpret_cast<float*>(smem);    // end-of-kernel staging (aliases the stages)
+  __shared__ __align__(8) uint64_t w_full, in_full[NST], stage_free[NST], v_full[2], acc_free[2], dv_ready[NST], g_full;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (tid == 0) {
+    mbar_init(&w_full, 1);
+    mbar_init(&g_full, 1);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&in_full[i], 1);
+      mbar_init(&stage_free[i], 2);
+      mbar_init(&dv_ready[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&acc_free[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tm = tmem_base_s;
+  // TMEM columns: per-tile buffers a in {0,1}: acc_v at a*128 (64 cols), acc_d at a*128 + 64 (32 cols);
+  // persistent: acc_wc at 256 (64 cols), acc_wr at 320 (32 cols)
+  const uint32_t acc_wc = tm + 256, acc_wr = tm + 320;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&w_full, (uint32_t)(2 * 2 * D * XB + D * XB));
+      tma_load_2d(wc0, &map_wc, &w_full, 0, (a.l * 2 + 0) * 2 * D);
+      tma_load_2d(wc1, &map_wc, &w_full, 0, (a.l * 2 + 1) * 2 * D);
+      tma_load_2d(wrn, &map_wrn, &w_full, 0, a.l * D);
+      for (int i = 0; i < n_my; ++i) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
+        const int s = i % NST;
+        unsigned char* st = smem + s * STAGE;
+        mbar_wait(&stage_free[s], ((uint32_t)(i / NST) & 1u) ^ 1u);
+        mbar_expect_tx(&in_full[s], (uint32_t)((a.has_next ? 4 : 3) * PANEL));
+        tma_load_3d(st, &map_x, &in_full[s], 0, t0, b);
+        tma_load_3d(st + PANEL, &map_x, &in_full[s], 0, t0 + a.dil, b);
+        tma_load_3d(st + 3 * PANEL, &map_dz, &in_full[s], a.l * D, t0, b);
+        if (a.has_next) tma_load_3d(st + 4 * PANEL, &map_dxn, &in_full[s], 0, t0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(&w_full, 0);
+      const uint32_t idv = make_idesc_bf16(128, 2 * D), idd = make_idesc_bf16(128, D);
+      const uint32_t idwc = make_idesc_bf16(128, 2 * D, true, true), idwr = make_idesc_bf16(128, R, true, true);
+      auto issue_wgrad = [&](int j) {  // weight gradients of tile j (its dv / z tiles are in shared memory)
+        const int s = j % NST;
+        const uint32_t st = smem_u32(smem + s * STAGE);
+        mbar_wait(&dv_ready[s], (uint32_t)(j / NST) & 1u);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // K = 128 timesteps, 16 per instruction
+          mma_bf16_ss(acc_wc, make_mnmajor_desc(st + k * 16 * XB, XB, PANEL),
+                      make_mnmajor_desc(st + 5 * PANEL + k * 16 * VB, VB, 0), idwc, (j | k) != 0);
+        if (a.has_next) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            mma_bf16_ss(acc_wr, make_mnmajor_desc(st + k * 16 * XB, XB, PANEL),
+                        make_mnmajor_desc(st + 4 * PANEL + k * 16 * XB, XB, 0), idwr, (j | k) != 0);
+        }
+        mma_commit(&stage_free[s]);
+      };
+      for (int i = 0; i < n_my; ++i) {
+        const int s = i % NST, ab = i & 1;
+        const uint32_t st = smem_u32(smem + s * STAGE);
+        mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);
+        mbar_wait(&acc_free[ab], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t av = tm + ab * 128, ad = av + 64;
+#pragma unroll
+        for (int k = 0; k < R / 16; ++k)
+          mma_bf16_ss(av, make_kmajor_desc(st, XB, k * 32), make_kmajor_desc(smem_u32(wc0), XB, k * 32), idv, k != 0);
+#pragma unroll
+        for (int k = 0; k < R / 16; ++k)
+          mma_bf16_ss(av, make_kmajor_desc(st + PANEL, XB, k * 32), make_kmajor_desc(smem_u32(wc1), XB, k * 32), idv, true);
+        if (a.has_next) {
+#pragma unroll
+          for (int k = 0; k < R / 16; ++k)  // dz(res) = dx' . RESIDUAL^T : B = RESIDUAL [D rows][R]
+            mma_bf16_ss(ad, make_kmajor_desc(st + 4 * PANEL, XB, k * 32), make_kmajor_desc(smem_u32(wrn), XB, k * 32), idd, k != 0);
+        }
+        mma_commit(&v_full[ab]);
+        if (i > 0) issue_wgrad(i - 1);  // overlaps the epilogue of tile i with the tensor work of tile i-1
+      }
+      if (n_my > 0) issue_wgrad(n_my - 1);
+      mma_commit(&g_full);
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const int et = (warp - 2) * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    const bool elected = (warp == 2 && lane == 0);
+    // bias-gradient accumulators: thread et owns dv column (et & 63), rows half (et >> 6); dx' column (et & 31),
+    // rows quarter (et >> 5)
+    float bsum_v = 0.f, bsum_x = 0.f;
+    float bias_s[32], bias_g[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) {
+      bias_s[d] = a.sig_b >= 0 ? __ldg(a.params + a.sig_b + d) : 0.f;
+      bias_g[d] = a.gate_b >= 0 ? __ldg(a.params + a.gate_b + d) : 0.f;
+    }
+    for (int i = 0; i < n_my; ++i) {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
+      const int s = i % NST, ab = i & 1;
+      unsigned char* st = smem + s * STAGE;
+      mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);  // dz tile (TMA) visible to this thread
+      mbar_wait(&v_full[ab], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after_sync();
+      uint32_t vs[32], vg[32], vd[32], dzs[16], pz[16], pvs[16], pvg[16];
+      tmem_ld_32x32b_x32(tm + ab * 128 + lane_sel, vs);
+      tmem_ld_32x32b_x32(tm + ab * 128 + 32 + lane_sel, vg);
+      if (a.has_next) tmem_ld_32x32b_x32(tm + ab * 128 + 64 + lane_sel, vd);
+      row_load<XB, 64>(st + 3 * PANEL, r, 0, dzs);
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&acc_free[ab]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float zz[2], ds[2], dg[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int d = 2 * j + e;
+          const float th = tanh_fast(__uint_as_float(vs[d]) + bias_s[d]);
+          const float sg = sigmoid_fast(__uint_as_float(vg[d]) + bias_g[d]);
+          float dz = e == 0 ? __uint_as_float(dzs[j] << 16) : __uint_as_float(dzs[j] & 0xffff0000u);
+          if (a.has_next) dz += __uint_as_float(vd[d]);
+          zz[e] = th * sg;
+          ds[e] = dz * sg * (1.f - th * th);
+          dg[e] = dz * th * sg * (1.f - sg);
+        }
+        pz[j] = pack2(zz[0], zz[1]);
+        pvs[j] = pack2(ds[0], ds[1]);
+        pvg[j] = pack2(dg[0], dg[1]);
+      }
+      row_store<XB, 64>(st + 2 * PANEL, r, 0, pz);          // z tile (A panel 2 of the weight-gradient MMA)
+      row_store<VB, 64>(st + 5 * PANEL, r, 0, pvs);         // dv tile: signal half | gate half
+      row_store<VB, 64>(st + 5 * PANEL, r, 64, pvg);
+      fence_proxy_async_smem();
+      epi_bar_sync();
+      if (elected) {
+        tma_store_3d(&map_dv, st + 5 * PANEL, 0, t0, b);
+        tma_store_commit();
+        mbar_arrive(&dv_ready[s]);
+      }
+      {  // bias gradients from the tiles (bf16 values, as stored)
+        const int c = et & 63, h = et >> 6;
+        const unsigned char* dvt = st + 5 * PANEL;
+        float acc = 0.f;
+        for (int rr = h * 64; rr < h * 64 + 64; ++rr) {
+          const uint16_t w = *reinterpret_cast<const uint16_t*>(dvt + swizzled_offset((uint32_t)rr, (uint32_t)c * 2, VB));
+          acc += __uint_as_float((uint32_t)w << 16);
+        }
+        bsum_v += acc;
+        if (a.has_next) {
+          const int cx = et & 31, qx = et >> 5;
+          const unsigned char* dxt = st + 4 * PANEL;
+          float ax = 0.f;
+          for (int rr = qx * 32; rr < qx * 32 + 32; ++rr) {
+            const uint16_t w = *reinterpret_cast<const uint16_t*>(dxt + swizzled_offset((uint32_t)rr, (uint32_t)cx * 2, XB));
+            ax += __uint_as_float((uint32_t)w << 16);
+          }
+          bsum_x += ax;
+        }
+      }
+      epi_bar_sync();  // every thread is done reading this stage's tiles
+      if (elected) {
+        tma_store_wait_read<0>();
+        mbar_arrive(&stage_free[s]);
+      }
+    }
+    // ---- flush: weight gradients TMEM -> staging -> coalesced atomics; bias sums ----
+    mbar_wait(&g_full, 0);
+    tc_fence_after_sync();
+    epi_bar_sync();
+    if (n_my > 0) {
+      uint32_t v[32];
+      // acc_wc rows 0..63 live in lanes 0..63 (warps with q4 = 0, 1); acc_wr rows 64..95 in lanes 64..95 (q4 = 2)
+      if (q4 < 2) {
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          tmem_ld_32x32b_x32(acc_wc + lane_sel + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[r * 65 + c0 + j] = __uint_as_float(v[j]);
+        }
+      } else if (q4 == 2 && a.has_next) {
+        tmem_ld_32x32b_x32(acc_wr + lane_sel, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[64 * 65 + (r - 64) * 33 + j] = __uint_as_float(v[j]);
+      }
+      epi_bar_sync();
+      // dWc row m = tap*R + rr, column n: n < D -> SIGNAL[tap][rr][n], else GATE[tap][rr][n-D]
+      for (int idx = et; idx < 64 * 64; idx += 128) {
+        const int m = idx >> 6, n = idx & 63;
+        const float val = stg[m * 65 + n];
+        const int tap = m >> 5, rr = m & 31;
+        float* dst = a.grads + (n < D ? a.sig : a.gate) + ((size_t)tap * R + rr) * D + (n & 31);
+        if (val != 0.f) atomicAdd(dst, val);
+      }
+      if (a.has_next) {
+        for (int idx = et; idx < 32 * 32; idx += 128) {
+          const int d = idx >> 5, c = idx & 31;
+          const float val = stg[64 * 65 + d * 33 + c];
+          if (val != 0.f) atomicAdd(a.grads + a.res + (size_t)d * R + c, val);
+        }
+      }
+      if (a.sig_b >= 0 && bsum_v != 0.f) {
+        const int c = et & 63;
+        atomicAdd(a.grads + (c < D ? a.sig_b + c : a.gate_b + (c - D)), bsum_v);
+      }
+      if (a.has_next && a.res_b >= 0 && bsum_x != 0.f) atomicAdd(a.grads + a.res_b + (et & 31), bsum_x);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tm, 512);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 static int map3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
                  int swizzle) {
@@ -331,7 +599,7 @@ struct LayerMaps {
   const void* model = nullptr;
   int T = -1;
   std::vector<CUtensorMap> x;  // per layer: xfull_l [B][dil+T][R]
-  CUtensorMap z, wc, wr, wd, dv, dx[2];
+  CUtensorMap z, wc, wr, wd, dv, dx[2], dz, wrn;
 };
 
 bool umma_layer_supported(const wn_model* m) {
@@ -359,6 +627,8 @@ static LayerMaps* get_maps(wn_model* m, unsigned char* ws, int T, int* rc) {
   if ((*rc = map3d(&cache.dv, ws + wl.dv, 2 * D, (uint64_t)T, B, (uint32_t)(2 * D), 128, (int)D * 4))) return nullptr;
   for (int i = 0; i < 2; ++i)
     if ((*rc = map3d(&cache.dx[i], ws + wl.dx[i], R, (uint64_t)T, B, (uint32_t)R, 128, (int)R * 2))) return nullptr;
+  if ((*rc = map3d(&cache.dz, ws + wl.dz, LD, (uint64_t)T, B, (uint32_t)D, 128, (int)D * 2))) return nullptr;
+  if ((*rc = map2ds(&cache.wrn, ws + wl.wrN, R, (uint64_t)m->L * D, (uint32_t)R, (uint32_t)D, (int)R * 2))) return nullptr;
   cache.ws = ws;
   cache.T = T;
   cache.model = m;
@@ -415,6 +685,38 @@ int launch_layer_bwd_dx_umma(wn_model* m, unsigned char* ws, int T, int l, cudaS
   WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_dx_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps(PROF_LAYER_BWD_B, st);
   k_layer_bwd_dx_umma<32, 32><<<grid, 128, smem, st>>>(mp->dv, mp->wd, mp->dx[(l + 1) & 1], mp->dx[l & 1], da);
+  WN_LAUNCH_CHECK();
+  return WN_OK;
+}
+
+}  // namespace wn
+
+namespace wn {
+
+bool umma_gate_supported(const wn_model* m) { return umma_layer_supported(m) && m->a.n_gc_embed == 0; }
+
+// gate backward + conv / residual weight and bias gradients of layer l (dx_next = dxbuf[(l+1)&1])
+int launch_layer_bwd_gate_umma(wn_model* m, const float* d_params, unsigned char* ws, int T, int l, float* d_grads,
+                               cudaStream_t st) {
+  int rc;
+  LayerMaps* mp = get_maps(m, ws, T, &rc);
+  if (!mp) return rc;
+  const LayerDesc& ld = m->layers[l];
+  LayerGateUmmaArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.params = d_params;
+  ga.grads = d_grads;
+  ga.sig = ld.sig; ga.gate = ld.gate; ga.res = ld.res;
+  ga.sig_b = ld.sig_b; ga.gate_b = ld.gate_b; ga.res_b = ld.res_b;
+  ga.T = T; ga.dil = ld.dil; ga.l = l;
+  ga.has_next = (l + 1 < m->L);
+  ga.tiles_per_slot = (T + 127) / 128;
+  ga.n_tiles = ga.tiles_per_slot * m->n_slots;
+  const size_t smem = 2 * (5 * 128 * 64 + 128 * 128) + 2 * 64 * 64 + 32 * 64 + 1024;
+  WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_gate_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::max(1, std::min(ga.n_tiles, m->sm_count));
+  ProfScope ps(PROF_LAYER_BWD_A, st);
+  k_layer_bwd_gate_umma<32, 32><<<grid, 192, smem, st>>>(mp->x[l], mp->dz, mp->dx[(l + 1) & 1], mp->dv, mp->wc, mp->wrn, ga);
   WN_LAUNCH_CHECK();
   return WN_OK;
 }

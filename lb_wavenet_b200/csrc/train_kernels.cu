@@ -54,6 +54,9 @@ int launch_prep_layer_umma(wn_model* m, const float* d_params, unsigned char* ws
 int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_ids, int T, int l,
                           cudaStream_t st);
 int launch_layer_bwd_dx_umma(wn_model* m, unsigned char* ws, int T, int l, cudaStream_t st);
+bool umma_gate_supported(const wn_model* m);
+int launch_layer_bwd_gate_umma(wn_model* m, const float* d_params, unsigned char* ws, int T, int l, float* d_grads,
+                               cudaStream_t st);
 bool umma_wgrad_supported(const wn_model* m, int lda, int ldy, int N);
 int launch_wgrad_umma(wn_model* m, const bf16* A, int lda, int a_col0, int M_total, const bf16* Y, int ldy, int N,
                       int64_t rows, float* out, int ldo, int mode, float* grads, cudaStream_t st);
@@ -1160,6 +1163,10 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
     la.ids = d_ids; la.grads = d_grads;
     la.B = d.B; la.T = T; la.R = d.R; la.D = d.D; la.LD = d.LD; la.l = l; la.C1 = d.C1;
     const dim3 grid((T + TM - 1) / TM, d.B);
+    if (umma_gate_supported(m)) {
+      // gate backward, conv / residual weight + bias gradients in one persistent tcgen05 kernel
+      if ((rc = launch_layer_bwd_gate_umma(m, d_params, ws, T, l, d_grads, st))) return rc;
+    } else {
     {
       ProfScope ps(PROF_LAYER_BWD_A, st);
       k_layer_bwd_a<<<grid, NT, sa, st>>>(la);
@@ -1176,6 +1183,7 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
         wa.out = d_grads + (sg ? la.ld.gate : la.ld.sig) + (int64_t)tap * d.R * d.D; wa.ldo = d.D;
         if ((rc = launch_wgrad(wa, m->sm_count, st))) return rc;
       }
+    }
     }
     if (umma_layer_supported(m)) {
       if ((rc = launch_layer_bwd_dx_umma(m, ws, T, l, st))) return rc;
