@@ -269,6 +269,8 @@ def main():
 
     if rank != 0:
         ctx.barrier()
+        import torch.distributed as dist
+        dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel (category timing from CUDA events on the launch stream) ----
@@ -347,6 +349,8 @@ def main():
     print(json.dumps(line))
     if world > 1:
         ctx.barrier()
+        import torch.distributed as dist
+        dist.destroy_process_group()
     return 0
 
 
