@@ -10,9 +10,20 @@
 // no grid-wide sync: streams are independent).  Per-layer ring buffers (length dil, index
 // t mod dil) replace the reference's chunk-shifted lookback buffers (imodel.py:88-97,199-201).
 #include "common.cuh"
-#include "tables.inc"
+#include "sampler.cuh"
+
+#include <cstring>
+#include <vector>
 
 namespace wn {
+
+// generation 2 (gen_umma.cu)
+bool gen2_supported(const wn_model* m);
+int64_t gen2_blob_bytes(const wn_model* m);
+int gen2_prepare(wn_model* m, const float* d_params, unsigned char* blob, cudaStream_t st);
+int gen2_run(wn_model* m, const unsigned char* blob, const int64_t* ring_off, bf16* rings, int32_t* codes,
+             int n_streams, int64_t t0, int n_steps, uint64_t seed, const int32_t* teacher, int n_teacher, int32_t* out,
+             float* logits, cudaStream_t st);
 
 __constant__ uint32_t c_mu_thr[255];
 __constant__ uint32_t c_mu_dec[256];
@@ -51,76 +62,6 @@ __global__ void k_mu_decode(const int32_t* __restrict__ q, float* __restrict__ x
   x[i] = __uint_as_float(c_mu_dec[c]);
 }
 
-// ---- counter-based sampler ------------------------------------------------------------
-__device__ __forceinline__ uint32_t philox4x32_10_w0(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                     uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  return c0;
-}
-
-__device__ __forceinline__ float sampler_uniform(uint64_t seed, uint64_t step, uint32_t stream) {
-  const uint32_t w0 = philox4x32_10_w0((uint32_t)step, (uint32_t)(step >> 32), stream, 0u, (uint32_t)seed,
-                                       (uint32_t)(seed >> 32));
-  return (float)(w0 >> 8) * 5.9604644775390625e-8f;  // 24 bits -> [0,1)
-}
-
-// exp(x), x <= 0, with separately rounded multiplies and adds only (never contracted to fma)
-__device__ __forceinline__ float det_exp(float x) {
-  const float t = __fmul_rn(x, __uint_as_float(kLog2eBits));
-  if (t < -120.f) return 0.f;
-  const float n = rintf(t);
-  const float f = __fsub_rn(t, n);
-  constexpr uint32_t kCoef[7] = WN_EXP2_COEF_BITS;
-  float p = __uint_as_float(kCoef[6]);
-#pragma unroll
-  for (int i = 5; i >= 0; --i) p = __fadd_rn(__fmul_rn(p, f), __uint_as_float(kCoef[i]));
-  const float scale = __int_as_float(((int)n + 127) << 23);
-  return __fmul_rn(p, scale);
-}
-
-// one warp samples one row of 256 logits; lane owns entries 8*lane .. 8*lane+7
-__device__ __forceinline__ int warp_sample(const float* lg, float u) {
-  const int lane = threadIdx.x & 31;
-  float v[8];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    v[j] = lg[lane * 8 + j];
-    mx = fmaxf(mx, v[j]);
-  }
-  mx = warp_max(mx);
-  float s[8];
-  float run = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    run = __fadd_rn(run, det_exp(__fsub_rn(v[j], mx)));
-    s[j] = run;
-  }
-  float incl = run;  // Kogge-Stone inclusive scan over lane totals
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const float o = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl = __fadd_rn(incl, o);
-  }
-  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-  if (lane == 0) excl = 0.f;
-  const float total = __shfl_sync(0xffffffffu, incl, 31);
-  const float thr = __fmul_rn(u, total);
-  int cnt = 0;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) cnt += (__fadd_rn(excl, s[j]) <= thr) ? 1 : 0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  return min(cnt, 255);
-}
-
 __global__ void k_sample_logits(const float* __restrict__ logits, int n_rows, uint64_t seed, uint64_t step,
                                 int32_t* __restrict__ out) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -140,6 +81,7 @@ struct GenLayout {
   int64_t wbf;       // bf16 mirror of the parameter arena
   int64_t pf32;      // fp32 copy of the arena (PRE table, biases)
   int64_t gcproj;    // fp32 [n_streams][L][2D]
+  int64_t blob2;     // generation-2 fragment-ready weight blob (gen_umma.cu)
   int64_t rings;     // bf16, layer l: [n_streams][dil][R]
   int64_t ring_elems;
   int64_t total;
@@ -158,6 +100,7 @@ static GenLayout gen_layout(const wn_model* m, int n_streams) {
   g.wbf = take(m->n_param_elems * 2);
   g.pf32 = take(m->n_param_elems * 4);
   g.gcproj = take(m->a.n_gc_embed > 0 ? (int64_t)n_streams * m->L * 2 * m->a.n_dil * 4 : 0);
+  g.blob2 = take(gen2_supported(m) ? gen2_blob_bytes(m) : 0);
   int64_t e = 0;
   for (int l = 0; l < m->L; ++l) e += (int64_t)n_streams * m->layers[l].dil * m->a.n_res;
   g.ring_elems = e;
@@ -340,6 +283,7 @@ __global__ void k_cast_params_gen(const float* __restrict__ p, bf16* __restrict_
 
 int ensure_layer_table(wn_model* m);  // train_kernels.cu
 
+
 }  // namespace wn
 
 using namespace wn;
@@ -417,6 +361,7 @@ int wn_gen_load_params(wn_model* m, const float* d_params, const int32_t* d_gc_i
   k_cast_params_gen<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_params, reinterpret_cast<bf16*>(ws + g.wbf),
                                                                        reinterpret_cast<float*>(ws + g.pf32), n);
   WN_LAUNCH_CHECK();
+  if (gen2_supported(m) && (rc = gen2_prepare(m, d_params, ws + g.blob2, st))) return rc;
   if (m->a.n_gc_embed > 0) {
     k_gen_gcproj<<<dim3(n_streams, m->L), 2 * m->a.n_dil, 0, st>>>(
         d_params, m->off_gc_embed, m->d_layers, d_gc_ids, m->a.n_gc_category + 1, m->a.n_gc_embed, m->a.n_dil,
@@ -437,6 +382,10 @@ int wn_gen_run(wn_model* m, void* d_gws, int32_t n_streams, int64_t t0, int32_t 
   if (rc) return rc;
   const GenLayout g = gen_layout(m, n_streams);
   unsigned char* ws = (unsigned char*)d_gws;
+  if (gen2_supported(m))
+    return gen2_run(m, ws + g.blob2, reinterpret_cast<const int64_t*>(ws + g.ring_off),
+                    reinterpret_cast<bf16*>(ws + g.rings), reinterpret_cast<int32_t*>(ws + g.codes), n_streams, t0,
+                    n_steps, seed, d_teacher, d_teacher ? n_teacher : 0, d_out, d_logits, st);
   GenArgs a;
   memset(&a, 0, sizeof(a));
   a.wbf = reinterpret_cast<const bf16*>(ws + g.wbf);

@@ -1,0 +1,501 @@
+// Incremental generator, generation 2 (reference imodel.py:214-272 for batch_sz independent streams).
+//
+// One persistent CTA owns 16 streams (the M of mma.sync.m16n8k16) and walks the whole stack for every
+// timestep without leaving the kernel.  The per-sample dependency chain (30 layers -> post-net -> sampler)
+// is latency bound, so everything that does not depend on the sample is taken off it:
+//   * all weights stream through shared memory in FRAGMENT-READY order (every lane fetches its B fragment
+//     with one conflict-free 8-byte load) via cp.async.bulk into a 5-slot ring fed by a producer warp;
+//     the sequence is the same every timestep, so the producer runs arbitrarily far ahead;
+//   * x[t-dil] of every layer is prefetched from the HBM ring buffers ONE STEP AHEAD with cp.async
+//     (addresses depend on t only); dil == 1 layers keep their previous input in shared memory;
+//   * skip accumulators stay in registers across the 30 layers (each warp owns 32 skip channels);
+//   * the input embedding bf16(PRE[code] + bias) is a 16 KB shared-memory table.
+// 8 compute warps + 1 producer warp.  Two named barriers per layer.
+// Shapes: R = D = 32, S = P = 256, Q = 256, no global conditioning (others: generation-1 kernel k_gen).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "sampler.cuh"
+#include "umma.cuh"
+
+namespace wn {
+
+using namespace umma;
+
+namespace g2 {
+constexpr int GS = 16;            // streams per CTA
+constexpr int R = 32, D = 32, S = 256, P = 256, Q = 256;
+constexpr int NCW = 8;            // compute warps
+constexpr int THREADS = (NCW + 1) * 32;
+constexpr int SLOT = 16384;       // weight ring slot
+constexpr int NSLOT = 5;
+// fragment-ready block: [n-tile][k-step][lane][2 x u32]  (256 B per (n-tile, k-step))
+constexpr int CONV_BYTES = 8 * 4 * 256;   // N = 64 (signal | gate), K = 64 (x[t-dil] | x[t])
+constexpr int RES_BYTES = 4 * 2 * 256;    // N = 32, K = 32
+constexpr int LAYER_A_BYTES = CONV_BYTES + RES_BYTES + 512;  // + biases: sig[32] gate[32] res[32] fp32 (pad to 512)
+constexpr int CHUNK_BYTES = 32 * 2 * 256; // N = 256, two k-steps (K = 32): SKIP_l, or a K-slice of POST1 / POST2
+constexpr int XP = 40;            // padded row (bf16 elements) of the 32-wide activation tiles
+constexpr int HP = 264;           // padded row of the 256-wide activation tiles
+}  // namespace g2
+
+struct Gen2Layout {  // byte offsets inside the generation-2 weight blob (device memory)
+  int64_t layer_a;   // L x LAYER_A_BYTES
+  int64_t skip;      // L x CHUNK_BYTES
+  int64_t post1;     // 8 x CHUNK_BYTES
+  int64_t post2;     // 8 x CHUNK_BYTES
+  int64_t x0tab;     // bf16 [257][32]: bf16(PRE[code] + bias), row 256 = all-zero input
+  int64_t biases;    // fp32: skip-bias sum [256] | POST1_BIAS [256] | POST2_BIAS [256]
+  int64_t total;
+};
+
+static Gen2Layout gen2_layout(int L) {
+  Gen2Layout g;
+  int64_t off = 0;
+  auto take = [&](int64_t b) { int64_t o = off; off = align_up(off + b, 1024); return o; };
+  g.layer_a = take((int64_t)L * g2::LAYER_A_BYTES);
+  g.skip = take((int64_t)L * g2::CHUNK_BYTES);
+  g.post1 = take(8 * g2::CHUNK_BYTES);
+  g.post2 = take(8 * g2::CHUNK_BYTES);
+  g.x0tab = take(257 * 32 * 2);
+  g.biases = take(3 * 256 * 4);
+  g.total = off;
+  return g;
+}
+
+// value of B[k][n] for mma fragment register `reg` of `lane`: k = k0 + 2*(lane%4) + 8*reg (+0,+1), n = n0 + lane/4
+__device__ __forceinline__ uint32_t frag_pack(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Builds the fragment-ready blob from the fp32 arena.  One block per (kind, index).
+__global__ void k_gen2_prep(const float* __restrict__ p, const LayerDesc* __restrict__ layers, int L, int64_t off_pre,
+                            int64_t off_pre_b, int64_t off_post1, int64_t off_post1_b, int64_t off_post2,
+                            int64_t off_post2_b, unsigned char* __restrict__ blob, Gen2Layout g) {
+  using namespace g2;
+  const int bid = blockIdx.x, tid = threadIdx.x;
+  auto frag_store = [&](uint32_t* dst, int nt, int ks, int nks, auto Bfun) {
+    // dst: [nt][ks][lane][2]
+    for (int i = tid; i < nt * nks * 32; i += blockDim.x) {
+      const int lane = i & 31, k_s = (i >> 5) % nks, n_t = (i >> 5) / nks;
+      const int n = n_t * 8 + (lane >> 2), k = k_s * 16 + 2 * (lane & 3);
+      dst[(size_t)i * 2 + 0] = frag_pack(Bfun(k, n), Bfun(k + 1, n));
+      dst[(size_t)i * 2 + 1] = frag_pack(Bfun(k + 8, n), Bfun(k + 9, n));
+    }
+    (void)ks;
+  };
+  if (bid < L) {
+    const LayerDesc ld = layers[bid];
+    unsigned char* la = blob + g.layer_a + (size_t)bid * LAYER_A_BYTES;
+    // conv: K index 0..31 = tap 0 (x[t-dil]), 32..63 = tap 1 (x[t]); N index 0..31 signal, 32..63 gate
+    frag_store(reinterpret_cast<uint32_t*>(la), 8, 0, 4, [&](int k, int n) {
+      const int tap = k >> 5, r = k & 31;
+      return p[(n < D ? ld.sig : ld.gate) + ((int64_t)tap * R + r) * D + (n & 31)];
+    });
+    frag_store(reinterpret_cast<uint32_t*>(la + CONV_BYTES), 4, 0, 2,
+               [&](int k, int n) { return p[ld.res + (int64_t)k * R + n]; });
+    float* bias = reinterpret_cast<float*>(la + CONV_BYTES + RES_BYTES);
+    for (int i = tid; i < 128; i += blockDim.x) {
+      float v = 0.f;
+      if (i < 32 && ld.sig_b >= 0) v = p[ld.sig_b + i];
+      else if (i >= 32 && i < 64 && ld.gate_b >= 0) v = p[ld.gate_b + i - 32];
+      else if (i >= 64 && i < 96 && ld.res_b >= 0) v = p[ld.res_b + i - 64];
+      bias[i] = v;
+    }
+    frag_store(reinterpret_cast<uint32_t*>(blob + g.skip + (size_t)bid * CHUNK_BYTES), 32, 0, 2,
+               [&](int k, int n) { return p[ld.skip + (int64_t)k * S + n]; });
+  } else if (bid < L + 8) {
+    const int c = bid - L;  // K slice [32c, 32c+32) of POST1 [S][P]
+    frag_store(reinterpret_cast<uint32_t*>(blob + g.post1 + (size_t)c * CHUNK_BYTES), 32, 0, 2,
+               [&](int k, int n) { return p[off_post1 + (int64_t)(c * 32 + k) * P + n]; });
+  } else if (bid < L + 16) {
+    const int c = bid - L - 8;
+    frag_store(reinterpret_cast<uint32_t*>(blob + g.post2 + (size_t)c * CHUNK_BYTES), 32, 0, 2,
+               [&](int k, int n) { return p[off_post2 + (int64_t)(c * 32 + k) * Q + n]; });
+  } else {
+    bf16* tab = reinterpret_cast<bf16*>(blob + g.x0tab);
+    for (int i = tid; i < 257 * 32; i += blockDim.x) {
+      const int code = i >> 5, r = i & 31;
+      float v = code < 256 ? p[off_pre + (int64_t)code * R + r] : 0.f;
+      if (off_pre_b >= 0) v += p[off_pre_b + r];
+      tab[i] = f2bf(v);
+    }
+    float* b = reinterpret_cast<float*>(blob + g.biases);
+    for (int i = tid; i < 768; i += blockDim.x) {
+      float v = 0.f;
+      const int which = i >> 8, c = i & 255;
+      if (which == 0) {
+        for (int l = 0; l < L; ++l)
+          if (layers[l].skip_b >= 0) v += p[layers[l].skip_b + c];
+      } else if (which == 1) {
+        if (off_post1_b >= 0) v = p[off_post1_b + c];
+      } else {
+        if (off_post2_b >= 0) v = p[off_post2_b + c];
+      }
+      b[i] = v;
+    }
+  }
+}
+
+// ---- device helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// A fragment (16 x 16) of a row-major bf16 tile in shared memory (row pitch `ld` elements), columns k0..k0+15
+__device__ __forceinline__ void lda_frag(uint32_t (&a)[4], const bf16* tile, int ld, int k0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  a[0] = *reinterpret_cast<const uint32_t*>(tile + g * ld + k0 + 2 * t);
+  a[1] = *reinterpret_cast<const uint32_t*>(tile + (g + 8) * ld + k0 + 2 * t);
+  a[2] = *reinterpret_cast<const uint32_t*>(tile + g * ld + k0 + 8 + 2 * t);
+  a[3] = *reinterpret_cast<const uint32_t*>(tile + (g + 8) * ld + k0 + 8 + 2 * t);
+}
+__device__ __forceinline__ uint2 ldb_frag(const unsigned char* blk, int nt, int ks, int nks, int lane) {
+  return *reinterpret_cast<const uint2*>(blk + ((size_t)(nt * nks + ks) * 32 + lane) * 8);
+}
+__device__ __forceinline__ void cbar() { asm volatile("bar.sync 2, 256;" ::: "memory"); }  // compute warps only
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct Gen2Args {
+  const unsigned char* blob;
+  Gen2Layout g;
+  const LayerDesc* layers;
+  const int64_t* ring_off;
+  bf16* rings;
+  int32_t* codes;
+  const int32_t* teacher;
+  int32_t* out;
+  float* logits_out;
+  int64_t t0;
+  uint64_t seed;
+  int n_streams, n_steps, n_teacher, L;
+};
+
+__global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
+  using namespace g2;
+  extern __shared__ __align__(1024) unsigned char sm[];
+  unsigned char* wring = sm;                                         // NSLOT x 16 KB
+  bf16* x0tab = reinterpret_cast<bf16*>(sm + NSLOT * SLOT);          // [257][32]
+  bf16* xbuf = x0tab + 257 * 32;                                     // [2][GS][XP]   current layer input (ping-pong)
+  bf16* zbuf = xbuf + 2 * GS * XP;                                   // [GS][XP]
+  bf16* hbuf = zbuf + GS * XP;                                       // [2][GS][HP]   h1 / h2
+  float* lgbuf = reinterpret_cast<float*>(hbuf + 2 * GS * HP);       // [GS][Q]
+  bf16* oldbuf = reinterpret_cast<bf16*>(lgbuf + GS * Q);            // [2][L][GS][XP] prefetched x[t-dil]
+  float* bias3 = reinterpret_cast<float*>(oldbuf + 2 * a.L * GS * XP);  // [768]
+  __shared__ __align__(8) uint64_t full[NSLOT], empty[NSLOT];
+  __shared__ int code_s[GS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s0 = blockIdx.x * GS;
+  const int L = a.L;
+
+  if (tid == 0) {
+    for (int i = 0; i < NSLOT; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], NCW);
+    }
+    fence_mbar_init();
+  }
+  for (int i = tid; i < 257 * 32 / 8; i += THREADS)
+    reinterpret_cast<uint4*>(x0tab)[i] = reinterpret_cast<const uint4*>(a.blob + a.g.x0tab)[i];
+  for (int i = tid; i < 768; i += THREADS) bias3[i] = reinterpret_cast<const float*>(a.blob + a.g.biases)[i];
+  if (tid < GS) code_s[tid] = (s0 + tid < a.n_streams) ? a.codes[s0 + tid] : -1;
+  __syncthreads();
+
+  const int items_per_step = 2 * L + 16;
+  if (warp == NCW) {
+    // ===== weight producer: same item sequence every timestep =====
+    if (lane == 0) {
+      int64_t it = 0;
+      for (int step = 0; step < a.n_steps; ++step) {
+        for (int j = 0; j < items_per_step; ++j, ++it) {
+          const int slot = (int)(it % NSLOT);
+          mbar_wait(&empty[slot], ((uint32_t)(it / NSLOT) & 1u) ^ 1u);
+          const unsigned char* src;
+          uint32_t bytes;
+          if (j < 2 * L) {
+            const int l = j >> 1;
+            if ((j & 1) == 0) { src = a.blob + a.g.layer_a + (size_t)l * LAYER_A_BYTES; bytes = LAYER_A_BYTES; }
+            else { src = a.blob + a.g.skip + (size_t)l * CHUNK_BYTES; bytes = CHUNK_BYTES; }
+          } else if (j < 2 * L + 8) {
+            src = a.blob + a.g.post1 + (size_t)(j - 2 * L) * CHUNK_BYTES; bytes = CHUNK_BYTES;
+          } else {
+            src = a.blob + a.g.post2 + (size_t)(j - 2 * L - 8) * CHUNK_BYTES; bytes = CHUNK_BYTES;
+          }
+          mbar_expect_tx(&full[slot], bytes);
+          bulk_g2s(wring + slot * SLOT, src, bytes, &full[slot]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== compute warps =====
+  const int g = lane >> 2, t4 = lane & 3;
+  int64_t it = 0;  // weight-ring consumer position (same sequence as the producer)
+  auto slot_wait = [&]() -> const unsigned char* {
+    const int slot = (int)(it % NSLOT);
+    mbar_wait(&full[slot], (uint32_t)(it / NSLOT) & 1u);
+    return wring + slot * SLOT;
+  };
+  auto slot_release = [&]() {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[(int)(it % NSLOT)]);
+    ++it;
+  };
+  // prefetch of x[t-dil] for timestep `ts` into oldbuf[pb]: layers with dil >= 2 read the HBM ring (the slot was
+  // written >= 1 timestep ago), dil == 1 layers are served from `prevx` kept in oldbuf by the layer itself
+  auto prefetch_old = [&](int64_t ts, int pb) {
+    for (int i = tid; i < L * GS * 4; i += NCW * 32) {  // 16-byte chunks: 4 per (layer, stream) row
+      const int ch = i & 3, s = (i >> 2) % GS, l = (i >> 2) / GS;
+      const int dil = a.layers[l].dil;
+      if (dil < 2 || s0 + s >= a.n_streams) continue;
+      const bf16* src = a.rings + a.ring_off[l] + ((int64_t)(s0 + s) * dil + (ts % dil)) * R + ch * 8;
+      cp_async16(oldbuf + ((size_t)(pb * L + l) * GS + s) * XP + ch * 8, src);
+    }
+    cp_async_commit();
+  };
+  // initial state: previous inputs of dil == 1 layers come from their length-1 rings; first prefetch
+  for (int i = tid; i < L * GS * R; i += NCW * 32) {
+    const int r = i % R, s = (i / R) % GS, l = i / (R * GS);
+    if (a.layers[l].dil == 1) {
+      const bf16 v = (s0 + s < a.n_streams) ? a.rings[a.ring_off[l] + (int64_t)(s0 + s) * R + r] : f2bf(0.f);
+      oldbuf[((size_t)(0 * L + l) * GS + s) * XP + r] = v;
+    }
+  }
+  prefetch_old(a.t0, 0);
+  cp_async_wait_all();
+  cbar();
+
+  for (int step = 0; step < a.n_steps; ++step) {
+    const int64_t t = a.t0 + step;
+    const int pb = step & 1;
+    // next step's ring reads are issued now (addresses depend on t only)
+    if (step + 1 < a.n_steps) prefetch_old(t + 1, pb ^ 1);
+    // input embedding (imodel.py:66-74): table row of the pending code; -1 -> all-zero vector -> bias only
+    for (int i = tid; i < GS * 4; i += NCW * 32) {
+      const int s = i >> 2, ch = i & 3;
+      const int c = code_s[s];
+      const int row = (c >= 0 && c < 256) ? c : 256;
+      *reinterpret_cast<uint4*>(xbuf + s * XP + ch * 8) = *reinterpret_cast<const uint4*>(x0tab + row * 32 + ch * 8);
+    }
+    float skip[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) skip[i][j] = 0.f;
+    cbar();
+    int xb = 0;
+    for (int l = 0; l < L; ++l) {
+      const int dil = a.layers[l].dil;
+      const bf16* xin = xbuf + xb * GS * XP;
+      bf16* xout = xbuf + (xb ^ 1) * GS * XP;
+      const bf16* oldx = oldbuf + ((size_t)(pb * L + l) * GS) * XP;
+      const unsigned char* wa = slot_wait();
+      const float* bias = reinterpret_cast<const float*>(wa + CONV_BYTES + RES_BYTES);
+      if (warp < 4) {
+        // conv + gate: this warp owns channels [8w, 8w+8): signal n-tile w, gate n-tile w + 4
+        float cs[4] = {0.f, 0.f, 0.f, 0.f}, cg[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t af[4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          lda_frag(af, ks < 2 ? oldx : xin, XP, (ks & 1) * 16, lane);
+          const uint2 bs = ldb_frag(wa, warp, ks, 4, lane), bg = ldb_frag(wa, warp + 4, ks, 4, lane);
+          mma16816(cs, af, bs.x, bs.y);
+          mma16816(cg, af, bg.x, bg.y);
+        }
+        const int c = warp * 8 + 2 * t4;
+        const float bs0 = bias[c], bs1 = bias[c + 1], bg0 = bias[32 + c], bg1 = bias[32 + c + 1];
+        const float z00 = tanh_fast(cs[0] + bs0) * sigmoid_fast(cg[0] + bg0);
+        const float z01 = tanh_fast(cs[1] + bs1) * sigmoid_fast(cg[1] + bg1);
+        const float z10 = tanh_fast(cs[2] + bs0) * sigmoid_fast(cg[2] + bg0);
+        const float z11 = tanh_fast(cs[3] + bs1) * sigmoid_fast(cg[3] + bg1);
+        *reinterpret_cast<uint32_t*>(zbuf + g * XP + c) = frag_pack(z00, z01);
+        *reinterpret_cast<uint32_t*>(zbuf + (g + 8) * XP + c) = frag_pack(z10, z11);
+      } else {
+        // meanwhile: ring <- x[t] (imodel.py:97).  dil >= 2: HBM ring slot t mod dil; dil == 1: next step's "old"
+        const int i = (warp - 4) * 32 + lane;  // 128 threads: 16 streams x 4 chunks of 16 B ... two passes
+        for (int q = i; q < GS * 4; q += 128) {
+          const int s = q >> 2, ch = q & 3;
+          const uint4 v = *reinterpret_cast<const uint4*>(xin + s * XP + ch * 8);
+          if (dil >= 2) {
+            if (s0 + s < a.n_streams)
+              *reinterpret_cast<uint4*>(a.rings + a.ring_off[l] + ((int64_t)(s0 + s) * dil + (t % dil)) * R + ch * 8) = v;
+          } else {
+            *reinterpret_cast<uint4*>(oldbuf + ((size_t)((pb ^ 1) * L + l) * GS + s) * XP + ch * 8) = v;
+          }
+        }
+      }
+      cbar();
+      {
+        // residual (warps 0..3: n-tile w) and skip (every warp: n-tiles 4w..4w+3), A = z
+        const unsigned char* wsk = nullptr;
+        uint32_t af[2][4];
+        lda_frag(af[0], zbuf, XP, 0, lane);
+        lda_frag(af[1], zbuf, XP, 16, lane);
+        if (warp < 4 && l + 1 < L) {
+          float cr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint2 b = ldb_frag(wa + CONV_BYTES, warp, ks, 2, lane);
+            mma16816(cr, af[ks], b.x, b.y);
+          }
+          const int c = warp * 8 + 2 * t4;
+          const float br0 = bias[64 + c], br1 = bias[64 + c + 1];
+          const __nv_bfloat162 x_lo = *reinterpret_cast<const __nv_bfloat162*>(xin + g * XP + c);
+          const __nv_bfloat162 x_hi = *reinterpret_cast<const __nv_bfloat162*>(xin + (g + 8) * XP + c);
+          *reinterpret_cast<uint32_t*>(xout + g * XP + c) =
+              frag_pack(__low2float(x_lo) + cr[0] + br0, __high2float(x_lo) + cr[1] + br1);  // imodel.py:245
+          *reinterpret_cast<uint32_t*>(xout + (g + 8) * XP + c) =
+              frag_pack(__low2float(x_hi) + cr[2] + br0, __high2float(x_hi) + cr[3] + br1);
+        }
+        slot_release();  // layer item A
+        wsk = slot_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint2 b = ldb_frag(wsk, warp * 4 + j, ks, 2, lane);
+            mma16816(skip[j], af[ks], b.x, b.y);  // imodel.py:247 (bias added once, below)
+          }
+        }
+        slot_release();
+      }
+      cbar();
+      xb ^= 1;
+    }
+    // ---- post-net (imodel.py:140-164) ----
+    bf16* h1 = hbuf;
+    bf16* h2 = hbuf + GS * HP;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = (warp * 4 + j) * 8 + 2 * t4;
+      *reinterpret_cast<uint32_t*>(h1 + g * HP + c) =
+          frag_pack(fmaxf(skip[j][0] + bias3[c], 0.f), fmaxf(skip[j][1] + bias3[c + 1], 0.f));
+      *reinterpret_cast<uint32_t*>(h1 + (g + 8) * HP + c) =
+          frag_pack(fmaxf(skip[j][2] + bias3[c], 0.f), fmaxf(skip[j][3] + bias3[c + 1], 0.f));
+    }
+    cbar();
+    float acc[4][4];
+    auto dense256 = [&](const bf16* A) {  // acc[j] = A[16 x 256] . W[256 x (n-tiles 4w..4w+3)], W streamed in 8 K slices
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int c8 = 0; c8 < 8; ++c8) {
+        const unsigned char* w = slot_wait();
+        uint32_t af[4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          lda_frag(af, A, HP, c8 * 32 + ks * 16, lane);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint2 b = ldb_frag(w, warp * 4 + j, ks, 2, lane);
+            mma16816(acc[j], af, b.x, b.y);
+          }
+        }
+        slot_release();
+      }
+    };
+    dense256(h1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = (warp * 4 + j) * 8 + 2 * t4;
+      *reinterpret_cast<uint32_t*>(h2 + g * HP + c) =
+          frag_pack(fmaxf(acc[j][0] + bias3[256 + c], 0.f), fmaxf(acc[j][1] + bias3[256 + c + 1], 0.f));
+      *reinterpret_cast<uint32_t*>(h2 + (g + 8) * HP + c) =
+          frag_pack(fmaxf(acc[j][2] + bias3[256 + c], 0.f), fmaxf(acc[j][3] + bias3[256 + c + 1], 0.f));
+    }
+    cbar();
+    dense256(h2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = (warp * 4 + j) * 8 + 2 * t4;
+      lgbuf[g * Q + c] = acc[j][0] + bias3[512 + c];
+      lgbuf[g * Q + c + 1] = acc[j][1] + bias3[512 + c + 1];
+      lgbuf[(g + 8) * Q + c] = acc[j][2] + bias3[512 + c];
+      lgbuf[(g + 8) * Q + c + 1] = acc[j][3] + bias3[512 + c + 1];
+    }
+    cbar();
+    // ---- sampling (imodel.py:167-187) + teacher forcing (imodel.py:260-267): warp w -> streams 2w, 2w+1 ----
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int s = warp * 2 + k;
+      if (s0 + s < a.n_streams) {
+        if (a.logits_out != nullptr)
+          for (int q = lane; q < Q; q += 32)
+            a.logits_out[((int64_t)(s0 + s) * a.n_steps + step) * Q + q] = lgbuf[s * Q + q];
+        const float u = sampler_uniform(a.seed, (uint64_t)t, (uint32_t)(s0 + s));
+        const int samp = warp_sample(lgbuf + s * Q, u);
+        if (lane == 0) {
+          a.out[(int64_t)(s0 + s) * a.n_steps + step] = samp;
+          code_s[s] = (t < a.n_teacher) ? a.teacher[t] : samp;
+        }
+      }
+    }
+    cp_async_wait_all();  // next step's x[t-dil] rows have landed
+    cbar();
+  }
+  // persist the state a later launch continues from: pending codes, previous inputs of the dil == 1 layers
+  if (tid < GS && s0 + tid < a.n_streams) a.codes[s0 + tid] = code_s[tid];
+  const int pbn = a.n_steps & 1;
+  for (int i = tid; i < L * GS * R; i += NCW * 32) {
+    const int r = i % R, s = (i / R) % GS, l = i / (R * GS);
+    if (a.layers[l].dil == 1 && s0 + s < a.n_streams)
+      a.rings[a.ring_off[l] + (int64_t)(s0 + s) * R + r] = oldbuf[((size_t)(pbn * L + l) * GS + s) * XP + r];
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------
+bool gen2_supported(const wn_model* m) {
+  static const bool disabled = getenv("WN_DISABLE_GEN2") != nullptr;
+  const wn_arch& a = m->a;
+  return !disabled && a.n_res == 32 && a.n_dil == 32 && a.n_skip == 256 && a.n_post == 256 && a.n_quant == 256 &&
+         a.n_gc_embed == 0 && m->L <= 64;
+}
+int64_t gen2_blob_bytes(const wn_model* m) { return gen2_layout(m->L).total; }
+
+int gen2_prepare(wn_model* m, const float* d_params, unsigned char* blob, cudaStream_t st) {
+  const Gen2Layout g = gen2_layout(m->L);
+  k_gen2_prep<<<m->L + 17, 256, 0, st>>>(d_params, m->d_layers, m->L, m->off_pre, m->off_pre_b, m->off_post1,
+                                         m->off_post1_b, m->off_post2, m->off_post2_b, blob, g);
+  WN_LAUNCH_CHECK();
+  return WN_OK;
+}
+
+int gen2_run(wn_model* m, const unsigned char* blob, const int64_t* ring_off, bf16* rings, int32_t* codes,
+             int n_streams, int64_t t0, int n_steps, uint64_t seed, const int32_t* teacher, int n_teacher, int32_t* out,
+             float* logits, cudaStream_t st) {
+  using namespace g2;
+  Gen2Args a;
+  memset(&a, 0, sizeof(a));
+  a.blob = blob; a.g = gen2_layout(m->L); a.layers = m->d_layers; a.ring_off = ring_off; a.rings = rings;
+  a.codes = codes; a.teacher = teacher; a.n_teacher = teacher ? n_teacher : 0; a.out = out; a.logits_out = logits;
+  a.t0 = t0; a.seed = seed; a.n_streams = n_streams; a.n_steps = n_steps; a.L = m->L;
+  const size_t smem = (size_t)NSLOT * SLOT + 257 * 32 * 2 + (size_t)(2 * GS * XP + GS * XP + 2 * GS * HP) * 2 +
+                      (size_t)GS * Q * 4 + (size_t)2 * m->L * GS * XP * 2 + 768 * 4 + 1024;
+  if (smem > 227 * 1024) {
+    set_error("gen2_run: %zu bytes of shared memory needed", smem);
+    return WN_ERR_UNSUPPORTED;
+  }
+  WN_CUDA_CHECK(cudaFuncSetAttribute(k_gen2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps(PROF_GEN, st);
+  k_gen2<<<(n_streams + GS - 1) / GS, THREADS, smem, st>>>(a);
+  WN_LAUNCH_CHECK();
+  return WN_OK;
+}
+
+}  // namespace wn

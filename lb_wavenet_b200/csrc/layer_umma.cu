@@ -92,15 +92,15 @@ k_layer_fwd_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   unsigned char* x0 = smem;
   unsigned char* x1 = x0 + X_TILE;
   unsigned char* ztile = x1 + X_TILE;
-  unsigned char* otile = ztile + Z_TILE;
-  unsigned char* wc0 = otile + X_TILE;
+  unsigned char* otile = x0;  // x[t-dil] is only read by the first MMA, complete before the output tile is written
+  unsigned char* wc0 = ztile + Z_TILE;
   unsigned char* wc1 = wc0 + WC_TILE;
   unsigned char* wr = wc1 + WC_TILE;
   __shared__ __align__(8) uint64_t bar_in, bar_v, bar_r;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.y, t0 = blockIdx.x * 128;
-  constexpr uint32_t NCOL = (2 * D + R) <= 128 ? 128 : 256;
+  constexpr uint32_t NCOL = 2 * D <= 64 ? 64 : (2 * D <= 128 ? 128 : 256);  // acc_r reuses acc_v's columns
 
   if (tid == 0) {
     mbar_init(&bar_in, 1);
@@ -112,7 +112,7 @@ k_layer_fwd_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t acc_v = tmem_base_s, acc_r = tmem_base_s + 2 * D;
+  const uint32_t acc_v = tmem_base_s, acc_r = tmem_base_s;  // second MMA is issued after every thread drained acc_v
 
   if (tid == 0) {
     mbar_expect_tx(&bar_in, (uint32_t)(2 * X_TILE + 2 * WC_TILE + (a.last ? 0 : WR_TILE)));
@@ -242,7 +242,7 @@ k_layer_bwd_dx_umma(const __grid_constant__ CUtensorMap map_dv, const __grid_con
   unsigned char* wd0 = dvb + V_TILE;
   unsigned char* wd1 = wd0 + WD_TILE;
   unsigned char* dxn = wd1 + WD_TILE;
-  unsigned char* otile = dxn + X_TILE;
+  unsigned char* otile = dva;  // dv[t] is only read by the MMAs, complete before the output tile is written
   __shared__ __align__(8) uint64_t bar_in, bar_acc;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -663,7 +663,7 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
   fa.last = (l + 1 == m->L);
   fa.dil_next = fa.last ? 0 : m->layers[l + 1].dil;
   const CUtensorMap& mxo = fa.last ? mp->x[l] : mp->x[l + 1];
-  const size_t smem = 4 * 128 * 64 + 2 * 64 * 64 + 32 * 64 + 1024;
+  const size_t smem = 3 * 128 * 64 + 2 * 64 * 64 + 32 * 64 + 1024;
   const dim3 grid((T + 127) / 128, m->n_slots);
   ProfScope ps(PROF_LAYER_FWD, st);
   k_layer_fwd_umma<32, 32><<<grid, 128, smem, st>>>(mp->x[l], mxo, mp->z, mp->wc, mp->wr, fa);
@@ -680,7 +680,7 @@ int launch_layer_bwd_dx_umma(wn_model* m, unsigned char* ws, int T, int l, cudaS
   da.dil = m->layers[l].dil;
   da.l = l;
   da.has_next = (l + 1 < m->L);
-  const size_t smem = 2 * 128 * 128 + 2 * 32 * 128 + 2 * 128 * 64 + 1024;
+  const size_t smem = 2 * 128 * 128 + 2 * 32 * 128 + 128 * 64 + 1024;
   const dim3 grid((T + 127) / 128, m->n_slots);
   WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_dx_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps(PROF_LAYER_BWD_B, st);

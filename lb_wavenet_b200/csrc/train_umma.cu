@@ -102,9 +102,20 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
   unsigned char* htile = stage_b + USTAGES * UB_BYTES;            // 64 KB
   __shared__ __align__(8) uint64_t full_bar[USTAGES], empty_bar[USTAGES], acc_full[3], h_ready[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[3 * 256];  // skip-bias sum | POST1_BIAS | POST2_BIAS (broadcast reads in the epilogues)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = a.S, P = a.P, Q = a.Q;
+  for (int i = tid; i < 3 * 256; i += UPOST_THREADS) {
+    float v = 0.f;
+    if (a.use_bias) {
+      const int which = i >> 8, c = i & 255;
+      if (which == 0 && c < S) v = a.skip_bias[c];
+      if (which == 1 && c < P) v = a.params[a.off_post1_b + c];
+      if (which == 2 && c < Q) v = a.params[a.off_post2_b + c];
+    }
+    bias_s[i] = v;
+  }
   const int64_t row0 = (int64_t)blockIdx.x * UM;
   const int nkb1 = (a.LD + UKB - 1) / UKB, nkb2 = S / UKB, nkb3 = P / UKB;
 
@@ -212,11 +223,8 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
-        if (a.use_bias) {
-          x0 += __ldg(a.skip_bias + c0 + 2 * j);
-          x1 += __ldg(a.skip_bias + c0 + 2 * j + 1);
-        }
+        const float x0 = __uint_as_float(v[2 * j]) + bias_s[c0 + 2 * j];
+        const float x1 = __uint_as_float(v[2 * j + 1]) + bias_s[c0 + 2 * j + 1];
         pk[j] = pack_bf16x2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
       }
       htile_store32(htile, r, c0, pk);
@@ -240,11 +248,8 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
-        if (a.use_bias) {
-          x0 += __ldg(a.params + a.off_post1_b + c0 + 2 * j);
-          x1 += __ldg(a.params + a.off_post1_b + c0 + 2 * j + 1);
-        }
+        const float x0 = __uint_as_float(v[2 * j]) + bias_s[256 + c0 + 2 * j];
+        const float x1 = __uint_as_float(v[2 * j + 1]) + bias_s[256 + c0 + 2 * j + 1];
         pk[j] = pack_bf16x2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
       }
       htile_store32(htile, r, c0, pk);
@@ -274,8 +279,7 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (a.use_bias) x += __ldg(a.params + a.off_post2_b + c0 + j);
+        const float x = __uint_as_float(v[j]) + bias_s[512 + c0 + j];
         if (x > mx) {
           mx = x;
           arg = c0 + j;
@@ -290,8 +294,7 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (a.use_bias) x += __ldg(a.params + a.off_post2_b + c0 + j);
+        const float x = __uint_as_float(v[j]) + bias_s[512 + c0 + j];
         sum += __expf(x - mx);
       }
     }
@@ -303,11 +306,8 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
-        if (a.use_bias) {
-          x0 += __ldg(a.params + a.off_post2_b + c0 + 2 * j);
-          x1 += __ldg(a.params + a.off_post2_b + c0 + 2 * j + 1);
-        }
+        const float x0 = __uint_as_float(v[2 * j]) + bias_s[512 + c0 + 2 * j];
+        const float x1 = __uint_as_float(v[2 * j + 1]) + bias_s[512 + c0 + 2 * j + 1];
         float g0 = __expf(x0 - mx) * inv - ((c0 + 2 * j) == label ? 1.f : 0.f);
         float g1 = __expf(x1 - mx) * inv - ((c0 + 2 * j + 1) == label ? 1.f : 0.f);
         pk[j] = valid ? pack_bf16x2(g0, g1) : 0u;

@@ -29,9 +29,12 @@ def _mk(arch, n_streams, seed, gc_ids=None):
     return a, p, eng
 
 
-@pytest.mark.parametrize("arch,gc", [(util.TINY, False), (util.TINY_GC, True), (util.TINY_ASYM, False)])
-def test_teacher_forced_logits(lib, arch, gc):
-    n_streams, n = 5, 80
+@pytest.mark.parametrize("arch,gc,n_streams", [(util.TINY, False, 5), (util.TINY_GC, True, 5), (util.TINY_ASYM, False, 5),
+                                               (util.CLASSIC_SHALLOW, False, 20), (util.CLASSIC, False, 3)])
+def test_teacher_forced_logits(lib, arch, gc, n_streams):
+    """TINY*: generation-1 kernel; CLASSIC*: generation-2 kernel (mma.sync, streamed weights; 20 streams = one full
+    and one partial 16-stream CTA)."""
+    n = 80
     gc_ids = np.array([1, 3, 5, 7, 2], np.int32) if gc else None
     a, p, eng = _mk(arch, n_streams, 4, gc_ids)
     teacher = np.random.default_rng(2).integers(0, 256, n).astype(np.int32)
@@ -48,8 +51,9 @@ def test_teacher_forced_logits(lib, arch, gc):
         assert np.array_equal(codes[:, i].cpu().numpy(), O.sample_from_logits(got[:, i], u)), i
 
 
-def test_free_running_fixed_seed(lib):
-    arch, n_streams, n = util.TINY, 6, 300
+@pytest.mark.parametrize("arch,n_streams", [(util.TINY, 6), (util.CLASSIC_SHALLOW, 18)])
+def test_free_running_fixed_seed(lib, arch, n_streams):
+    n = 300
     a, p, eng = _mk(arch, n_streams, 8)
     # two launches (150 + 150) must equal one continuous run: state carried in the workspace
     c1, l1 = eng.run(150, seed=1234, want_logits=True)
@@ -62,7 +66,7 @@ def test_free_running_fixed_seed(lib):
         assert np.array_equal(codes[:, i], O.sample_from_logits(logits[:, i], u)), i
     assert len(np.unique(codes)) > 8  # not degenerate
     # (c) oracle teacher-forced per stream with the kernel's own output
-    for s in range(n_streams):
+    for s in range(0, n_streams, 3):
         ora = O.GenOracle(a, p, 1, torch.float64, emulate_bf16=True)
         _, ref = ora.run(n, 0, teacher=codes[s], return_logits=True)
         assert np.abs(ref[0] - logits[s]).max() <= 0.05, (s, np.abs(ref[0] - logits[s]).max())
