@@ -335,7 +335,7 @@ struct LayerGateUmmaArgs {
 };
 
 template <int R, int D>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 k_layer_bwd_gate_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz,
                       const __grid_constant__ CUtensorMap map_dxn, const __grid_constant__ CUtensorMap map_dv,
                       const __grid_constant__ CUtensorMap map_wc, const __grid_constant__ CUtensorMap map_wrn,
@@ -343,8 +343,11 @@ k_layer_bwd_gate_umma(const __grid_constant__ CUtensorMap map_x, const __grid_co
   static_assert(R == 32 && D == 32, "tile bookkeeping below assumes 64-byte activation rows");
   constexpr int XB = 64, VB = 128;
   constexpr int PANEL = 128 * XB;                 // 8 KB: one [128 x 32] bf16 tile
-  constexpr int STAGE = 5 * PANEL + 128 * VB;     // x0 | x1 | z | dz | dxn | dv(16 KB)
-  constexpr int NST = 2;
+  // stage: x0 | x1 | z | ones | dz | dxn | dv(16 KB).  Panels 0..3 are the MN-major A operand of the weight-gradient
+  // MMAs (M = 128: rows 0..63 conv taps, 64..95 z, 96..127 constant one -> bias gradients for free)
+  constexpr int STAGE = 6 * PANEL + 128 * VB;
+  constexpr int NST = 3;  // two tiles of TMA prefetch distance (the kernel is load-latency bound otherwise)
+  constexpr int NEPI = 256;                       // 8 epilogue warps: (TMEM lane quarter) x (channel half)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* wc0 = smem + NST * STAGE;        // [2D rows][R]   4 KB
@@ -353,6 +356,7 @@ k_layer_bwd_gate_umma(const __grid_constant__ CUtensorMap map_x, const __grid_co
   float* stg = reinterpret_cast<float*>(smem);    // end-of-kernel staging (aliases the stages)
   __shared__ __align__(8) uint64_t w_full, in_full[NST], stage_free[NST], v_full[2], acc_free[2], dv_ready[NST], g_full;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_sm[64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -366,16 +370,24 @@ k_layer_bwd_gate_umma(const __grid_constant__ CUtensorMap map_x, const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&v_full[i], 1);
-      mbar_init(&acc_free[i], 128);
+      mbar_init(&acc_free[i], NEPI);
     }
     fence_mbar_init();
   }
+  if (tid < 64) bias_sm[tid] = tid < 32 ? (a.sig_b >= 0 ? a.params[a.sig_b + tid] : 0.f)
+                                        : (a.gate_b >= 0 ? a.params[a.gate_b + tid - 32] : 0.f);
+  // constant-one panels (bf16 1.0 = 0x3f80); the swizzle permutes equal values, so a plain fill is exact
+  for (int i = tid; i < NST * PANEL / 16; i += blockDim.x) {
+    const int s = i / (PANEL / 16), o = i % (PANEL / 16);
+    *reinterpret_cast<uint4*>(smem + s * STAGE + 3 * PANEL + o * 16) = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+  }
+  fence_proxy_async_smem();
   if (warp == 1) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tm = tmem_base_s;
-  // TMEM columns: per-tile buffers a in {0,1}: acc_v at a*128 (64 cols), acc_d at a*128 + 64 (32 cols);
+  // TMEM columns: per-tile buffers ab in {0,1}: acc_v at ab*128 (64 cols), acc_d at ab*128 + 64 (32 cols);
   // persistent: acc_wc at 256 (64 cols), acc_wr at 320 (32 cols)
   const uint32_t acc_wc = tm + 256, acc_wr = tm + 320;
 
@@ -394,8 +406,8 @@ k_layer_bwd_gate_umma(const __grid_constant__ CUtensorMap map_x, const __grid_co
         mbar_expect_tx(&in_full[s], (uint32_t)((a.has_next ? 4 : 3) * PANEL));
         tma_load_3d(st, &map_x, &in_full[s], 0, t0, b);
         tma_load_3d(st + PANEL, &map_x, &in_full[s], 0, t0 + a.dil, b);
-        tma_load_3d(st + 3 * PANEL, &map_dz, &in_full[s], a.l * D, t0, b);
-        if (a.has_next) tma_load_3d(st + 4 * PANEL, &map_dxn, &in_full[s], 0, t0, b);
+        tma_load_3d(st + 4 * PANEL, &map_dz, &in_full[s], a.l * D, t0, b);
+        if (a.has_next) tma_load_3d(st + 5 * PANEL, &map_dxn, &in_full[s], 0, t0, b);
       }
     }
   } else if (warp == 1) {
@@ -411,12 +423,12 @@ k_layer_bwd_gate_umma(const __grid_constant__ CUtensorMap map_x, const __grid_co
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // K = 128 timesteps, 16 per instruction
           mma_bf16_ss(acc_wc, make_mnmajor_desc(st + k * 16 * XB, XB, PANEL),
-                      make_mnmajor_desc(st + 5 * PANEL + k * 16 * VB, VB, 0), idwc, (j | k) != 0);
+                      make_mnmajor_desc(st + 6 * PANEL + k * 16 * VB, VB, 0), idwc, (j | k) != 0);
         if (a.has_next) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             mma_bf16_ss(acc_wr, make_mnmajor_desc(st + k * 16 * XB, XB, PANEL),
-                        make_mnmajor_desc(st + 4 * PANEL + k * 16 * XB, XB, 0), idwr, (j | k) != 0);
+                        make_mnmajor_desc(st + 5 * PANEL + k * 16 * XB, XB, 0), idwr, (j | k) != 0);
         }
         mma_commit(&stage_free[s]);
       };
@@ -436,7 +448,7 @@ k_layer_bwd_gate_umma(const __grid_constant__ CUtensorMap map_x, const __grid_co
         if (a.has_next) {
 #pragma unroll
           for (int k = 0; k < R / 16; ++k)  // dz(res) = dx' . RESIDUAL^T : B = RESIDUAL [D rows][R]
-            mma_bf16_ss(ad, make_kmajor_desc(st + 4 * PANEL, XB, k * 32), make_kmajor_desc(smem_u32(wrn), XB, k * 32), idd, k != 0);
+            mma_bf16_ss(ad, make_kmajor_desc(st + 5 * PANEL, XB, k * 32), make_kmajor_desc(smem_u32(wrn), XB, k * 32), idd, k != 0);
         }
         mma_commit(&v_full[ab]);
         if (i > 0) issue_wgrad(i - 1);  // overlaps the epilogue of tile i with the tensor work of tile i-1
@@ -445,114 +457,111 @@ k_layer_bwd_gate_umma(const __grid_constant__ CUtensorMap map_x, const __grid_co
       mma_commit(&g_full);
     }
   } else {
-    const int q4 = warp & 3;
+    const int e = warp - 2;                    // 0..7
+    const int q4 = warp & 3, half = e >> 2;    // TMEM lane quarter, channel half [16*half, 16*half+16)
     const int r = q4 * 32 + lane;
-    const int et = (warp - 2) * 32 + lane;
+    const int et = e * 32 + lane;              // 0..255
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
     const bool elected = (warp == 2 && lane == 0);
-    // bias-gradient accumulators: thread et owns dv column (et & 63), rows half (et >> 6); dx' column (et & 31),
-    // rows quarter (et >> 5)
-    float bsum_v = 0.f, bsum_x = 0.f;
-    float bias_s[32], bias_g[32];
-#pragma unroll
-    for (int d = 0; d < 32; ++d) {
-      bias_s[d] = a.sig_b >= 0 ? __ldg(a.params + a.sig_b + d) : 0.f;
-      bias_g[d] = a.gate_b >= 0 ? __ldg(a.params + a.gate_b + d) : 0.f;
-    }
+    const int c0 = 16 * half;
+    auto ebar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     for (int i = 0; i < n_my; ++i) {
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
       const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
       const int s = i % NST, ab = i & 1;
       unsigned char* st = smem + s * STAGE;
+      if (elected && i > 0) {  // release the previous tile's stage once its dv store has finished reading it
+        tma_store_wait_read<0>();
+        mbar_arrive(&stage_free[(i - 1) % NST]);
+      }
       mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);  // dz tile (TMA) visible to this thread
       mbar_wait(&v_full[ab], (uint32_t)(i >> 1) & 1u);
       tc_fence_after_sync();
-      uint32_t vs[32], vg[32], vd[32], dzs[16], pz[16], pvs[16], pvg[16];
-      tmem_ld_32x32b_x32(tm + ab * 128 + lane_sel, vs);
-      tmem_ld_32x32b_x32(tm + ab * 128 + 32 + lane_sel, vg);
-      if (a.has_next) tmem_ld_32x32b_x32(tm + ab * 128 + 64 + lane_sel, vd);
-      row_load<XB, 64>(st + 3 * PANEL, r, 0, dzs);
+      uint32_t vs[16], vg[16], vd[16], dzs[8], pz[8], pvs[8], pvg[8];
+      tmem_ld_32x32b_x16(tm + ab * 128 + c0 + lane_sel, vs);
+      tmem_ld_32x32b_x16(tm + ab * 128 + 32 + c0 + lane_sel, vg);
+      if (a.has_next) tmem_ld_32x32b_x16(tm + ab * 128 + 64 + c0 + lane_sel, vd);
+      row_load<XB, 32>(st + 4 * PANEL, r, 32 * half, dzs);
       tmem_ld_wait();
       tc_fence_before_sync();
       mbar_arrive(&acc_free[ab]);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < 8; ++j) {
         float zz[2], ds[2], dg[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int d = 2 * j + e;
-          const float th = tanh_fast(__uint_as_float(vs[d]) + bias_s[d]);
-          const float sg = sigmoid_fast(__uint_as_float(vg[d]) + bias_g[d]);
-          float dz = e == 0 ? __uint_as_float(dzs[j] << 16) : __uint_as_float(dzs[j] & 0xffff0000u);
+        for (int k = 0; k < 2; ++k) {
+          const int d = 2 * j + k;
+          const float th = tanh_fast(__uint_as_float(vs[d]) + bias_sm[c0 + d]);
+          const float sg = sigmoid_fast(__uint_as_float(vg[d]) + bias_sm[32 + c0 + d]);
+          float dz = k == 0 ? __uint_as_float(dzs[j] << 16) : __uint_as_float(dzs[j] & 0xffff0000u);
           if (a.has_next) dz += __uint_as_float(vd[d]);
-          zz[e] = th * sg;
-          ds[e] = dz * sg * (1.f - th * th);
-          dg[e] = dz * th * sg * (1.f - sg);
+          zz[k] = th * sg;
+          ds[k] = dz * sg * (1.f - th * th);
+          dg[k] = dz * th * sg * (1.f - sg);
         }
         pz[j] = pack2(zz[0], zz[1]);
         pvs[j] = pack2(ds[0], ds[1]);
         pvg[j] = pack2(dg[0], dg[1]);
       }
-      row_store<XB, 64>(st + 2 * PANEL, r, 0, pz);          // z tile (A panel 2 of the weight-gradient MMA)
-      row_store<VB, 64>(st + 5 * PANEL, r, 0, pvs);         // dv tile: signal half | gate half
-      row_store<VB, 64>(st + 5 * PANEL, r, 64, pvg);
+      row_store<XB, 32>(st + 2 * PANEL, r, 32 * half, pz);            // z tile (A panel 2 of the weight-gradient MMA)
+      row_store<VB, 32>(st + 6 * PANEL, r, 32 * half, pvs);           // dv tile: signal half | gate half
+      row_store<VB, 32>(st + 6 * PANEL, r, 64 + 32 * half, pvg);
       fence_proxy_async_smem();
-      epi_bar_sync();
+      ebar();
       if (elected) {
-        tma_store_3d(&map_dv, st + 5 * PANEL, 0, t0, b);
+        tma_store_3d(&map_dv, st + 6 * PANEL, 0, t0, b);
         tma_store_commit();
         mbar_arrive(&dv_ready[s]);
       }
-      {  // bias gradients from the tiles (bf16 values, as stored)
-        const int c = et & 63, h = et >> 6;
-        const unsigned char* dvt = st + 5 * PANEL;
-        float acc = 0.f;
-        for (int rr = h * 64; rr < h * 64 + 64; ++rr) {
-          const uint16_t w = *reinterpret_cast<const uint16_t*>(dvt + swizzled_offset((uint32_t)rr, (uint32_t)c * 2, VB));
-          acc += __uint_as_float((uint32_t)w << 16);
-        }
-        bsum_v += acc;
-        if (a.has_next) {
-          const int cx = et & 31, qx = et >> 5;
-          const unsigned char* dxt = st + 4 * PANEL;
-          float ax = 0.f;
-          for (int rr = qx * 32; rr < qx * 32 + 32; ++rr) {
-            const uint16_t w = *reinterpret_cast<const uint16_t*>(dxt + swizzled_offset((uint32_t)rr, (uint32_t)cx * 2, XB));
-            ax += __uint_as_float((uint32_t)w << 16);
-          }
-          bsum_x += ax;
-        }
-      }
-      epi_bar_sync();  // every thread is done reading this stage's tiles
-      if (elected) {
-        tma_store_wait_read<0>();
-        mbar_arrive(&stage_free[s]);
-      }
     }
-    // ---- flush: weight gradients TMEM -> staging -> coalesced atomics; bias sums ----
+    if (elected && n_my > 0) {
+      tma_store_wait_read<0>();
+      mbar_arrive(&stage_free[(n_my - 1) % NST]);
+    }
+    // ---- flush: weight gradients TMEM -> staging -> coalesced atomics; bias gradients from the ones-row ----
     mbar_wait(&g_full, 0);
     tc_fence_after_sync();
-    epi_bar_sync();
+    ebar();
     if (n_my > 0) {
       uint32_t v[32];
-      // acc_wc rows 0..63 live in lanes 0..63 (warps with q4 = 0, 1); acc_wr rows 64..95 in lanes 64..95 (q4 = 2)
+      // acc_wc[128 x 64]: rows 0..63 = conv taps (lanes 0..63), row 96 = column sums of dv (lane 96);
+      // acc_wr[128 x 32]: rows 64..95 = RESIDUAL (lanes 64..95), row 96 = column sums of dx'
       if (q4 < 2) {
-#pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          tmem_ld_32x32b_x32(acc_wc + lane_sel + (uint32_t)c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) stg[r * 65 + c0 + j] = __uint_as_float(v[j]);
-        }
-      } else if (q4 == 2 && a.has_next) {
-        tmem_ld_32x32b_x32(acc_wr + lane_sel, v);
+        tmem_ld_32x32b_x32(acc_wc + lane_sel + (uint32_t)(32 * half), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[64 * 65 + (r - 64) * 33 + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) stg[r * 65 + 32 * half + j] = __uint_as_float(v[j]);
+      } else if (q4 == 2 && a.has_next) {
+        uint32_t w[16];
+        tmem_ld_32x32b_x16(acc_wr + lane_sel + (uint32_t)c0, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) stg[64 * 65 + (r - 64) * 33 + c0 + j] = __uint_as_float(w[j]);
+      } else if (q4 == 3) {
+        tmem_ld_32x32b_x32(acc_wc + lane_sel + (uint32_t)(32 * half), v);
+        uint32_t w[16];
+        if (a.has_next) tmem_ld_32x32b_x16(acc_wr + lane_sel + (uint32_t)c0, w);
+        tmem_ld_wait();
+        if (lane == 0) {  // row 96
+          if (a.sig_b >= 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float val = __uint_as_float(v[j]);
+              if (val != 0.f) atomicAdd(a.grads + (half == 0 ? a.sig_b : a.gate_b) + j, val);
+            }
+          }
+          if (a.has_next && a.res_b >= 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float val = __uint_as_float(w[j]);
+              if (val != 0.f) atomicAdd(a.grads + a.res_b + c0 + j, val);
+            }
+          }
+        }
       }
-      epi_bar_sync();
+      ebar();
       // dWc row m = tap*R + rr, column n: n < D -> SIGNAL[tap][rr][n], else GATE[tap][rr][n-D]
-      for (int idx = et; idx < 64 * 64; idx += 128) {
+      for (int idx = et; idx < 64 * 64; idx += NEPI) {
         const int m = idx >> 6, n = idx & 63;
         const float val = stg[m * 65 + n];
         const int tap = m >> 5, rr = m & 31;
@@ -560,22 +569,318 @@ k_layer_bwd_gate_umma(const __grid_constant__ CUtensorMap map_x, const __grid_co
         if (val != 0.f) atomicAdd(dst, val);
       }
       if (a.has_next) {
-        for (int idx = et; idx < 32 * 32; idx += 128) {
+        for (int idx = et; idx < 32 * 32; idx += NEPI) {
           const int d = idx >> 5, c = idx & 31;
           const float val = stg[64 * 65 + d * 33 + c];
           if (val != 0.f) atomicAdd(a.grads + a.res + (size_t)d * R + c, val);
         }
       }
-      if (a.sig_b >= 0 && bsum_v != 0.f) {
-        const int c = et & 63;
-        atomicAdd(a.grads + (c < D ? a.sig_b + c : a.gate_b + (c - D)), bsum_v);
-      }
-      if (a.has_next && a.res_b >= 0 && bsum_x != 0.f) atomicAdd(a.grads + a.res_b + (et & 31), bsum_x);
     }
   }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tm, 512);
+}
+
+// =====================================================================================================
+// Persistent variants of the forward and data-gradient kernels (the per-tile work is a short latency chain
+// TMA -> MMA -> epilogue -> TMA; a deep TMA ring and double-buffered TMEM keep HBM busy).
+// Roles: warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue ((TMEM lane quarter) x (channel half)).
+// =====================================================================================================
+struct LayerFwdPArgs {
+  const float* params;
+  int64_t sig_b, gate_b, res_b;
+  int T, dil, dil_next, l, last, n_tiles, tiles_per_slot;
+};
+
+template <int R, int D>
+__global__ void __launch_bounds__(320, 2)
+k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_xout,
+                   const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_wc,
+                   const __grid_constant__ CUtensorMap map_wr, LayerFwdPArgs a) {
+  static_assert(R == 32 && D == 32, "64-byte activation rows");
+  constexpr int XB = 64;
+  constexpr int PANEL = 128 * XB;       // 8 KB
+  constexpr int STAGE = 2 * PANEL;      // x[t-dil] | x[t]
+  constexpr int NST = 4;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* zt = smem + NST * STAGE;       // [2] z tiles
+  unsigned char* ot = zt + 2 * PANEL;           // [2] output tiles
+  unsigned char* wc0 = ot + 2 * PANEL;
+  unsigned char* wc1 = wc0 + 2 * D * XB;
+  unsigned char* wr = wc1 + 2 * D * XB;
+  __shared__ __align__(8) uint64_t w_full, in_full[NST], stage_free[NST], v_full[2], r_full[2], acc_free[2], z_ready[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_sm[96];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (tid == 0) {
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&in_full[i], 1);
+      mbar_init(&stage_free[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&r_full[i], 1);
+      mbar_init(&acc_free[i], 256);
+      mbar_init(&z_ready[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (tid < 96)
+    bias_sm[tid] = tid < 32 ? (a.sig_b >= 0 ? a.params[a.sig_b + tid] : 0.f)
+                 : tid < 64 ? (a.gate_b >= 0 ? a.params[a.gate_b + tid - 32] : 0.f)
+                            : (a.res_b >= 0 ? a.params[a.res_b + tid - 64] : 0.f);
+  if (warp == 1) tmem_alloc(&tmem_base_s, 256);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tm = tmem_base_s;  // buffer ab: acc_v at ab*128 (64 cols), acc_r at ab*128 + 64 (32 cols)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&w_full, (uint32_t)(2 * 2 * D * XB + (a.last ? 0 : R * XB)));
+      tma_load_2d(wc0, &map_wc, &w_full, 0, (a.l * 2 + 0) * 2 * D);
+      tma_load_2d(wc1, &map_wc, &w_full, 0, (a.l * 2 + 1) * 2 * D);
+      if (!a.last) tma_load_2d(wr, &map_wr, &w_full, 0, a.l * R);
+      for (int i = 0; i < n_my; ++i) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
+        const int s = i % NST;
+        mbar_wait(&stage_free[s], ((uint32_t)(i / NST) & 1u) ^ 1u);
+        mbar_expect_tx(&in_full[s], (uint32_t)STAGE);
+        tma_load_3d(smem + s * STAGE, &map_x, &in_full[s], 0, t0, b);
+        tma_load_3d(smem + s * STAGE + PANEL, &map_x, &in_full[s], 0, t0 + a.dil, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(&w_full, 0);
+      const uint32_t idv = make_idesc_bf16(128, 2 * D), idr = make_idesc_bf16(128, R);
+      auto mma1 = [&](int i) {
+        const int s = i % NST, ab = i & 1;
+        const uint32_t st = smem_u32(smem + s * STAGE), av = tm + ab * 128;
+        mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);
+        mbar_wait(&acc_free[ab], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < R / 16; ++k)
+          mma_bf16_ss(av, make_kmajor_desc(st, XB, k * 32), make_kmajor_desc(smem_u32(wc0), XB, k * 32), idv, k != 0);
+#pragma unroll
+        for (int k = 0; k < R / 16; ++k)
+          mma_bf16_ss(av, make_kmajor_desc(st + PANEL, XB, k * 32), make_kmajor_desc(smem_u32(wc1), XB, k * 32), idv, true);
+        mma_commit(&v_full[ab]);
+      };
+      if (n_my > 0) mma1(0);
+      for (int i = 0; i < n_my; ++i) {
+        if (i + 1 < n_my) mma1(i + 1);  // next tile's conv runs while this tile's gate epilogue works
+        if (!a.last) {
+          const int ab = i & 1;
+          mbar_wait(&z_ready[ab], (uint32_t)(i >> 1) & 1u);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int k = 0; k < D / 16; ++k)
+            mma_bf16_ss(tm + ab * 128 + 64, make_kmajor_desc(smem_u32(zt + ab * PANEL), XB, k * 32),
+                        make_kmajor_desc(smem_u32(wr), XB, k * 32), idr, k != 0);
+          mma_commit(&r_full[ab]);
+        }
+      }
+    }
+  } else {
+    const int e = warp - 2, q4 = warp & 3, half = e >> 2;
+    const int r = q4 * 32 + lane, c0 = 16 * half;
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    const bool elected = (warp == 2 && lane == 0);
+    auto ebar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    for (int i = 0; i < n_my; ++i) {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
+      const int s = i % NST, ab = i & 1;
+      unsigned char* ztile = zt + ab * PANEL;
+      unsigned char* otile = ot + ab * PANEL;
+      uint32_t vs[16], vg[16], pk[8];
+      mbar_wait(&v_full[ab], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after_sync();
+      tmem_ld_32x32b_x16(tm + ab * 128 + c0 + lane_sel, vs);
+      tmem_ld_32x32b_x16(tm + ab * 128 + 32 + c0 + lane_sel, vg);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z0 = tanh_fast(__uint_as_float(vs[2 * j]) + bias_sm[c0 + 2 * j]) *
+                         sigmoid_fast(__uint_as_float(vg[2 * j]) + bias_sm[32 + c0 + 2 * j]);
+        const float z1 = tanh_fast(__uint_as_float(vs[2 * j + 1]) + bias_sm[c0 + 2 * j + 1]) *
+                         sigmoid_fast(__uint_as_float(vg[2 * j + 1]) + bias_sm[32 + c0 + 2 * j + 1]);
+        pk[j] = pack2(z0, z1);
+      }
+      row_store<XB, 32>(ztile, r, 32 * half, pk);
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      ebar();
+      if (elected) {
+        if (!a.last) mbar_arrive(&z_ready[ab]);
+        tma_store_3d(&map_z, ztile, a.l * D, t0, b);
+        tma_store_commit();
+      }
+      if (!a.last) {
+        uint32_t vr[16], xin[8];
+        mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);  // x[t] tile (TMA) visible to this thread
+        mbar_wait(&r_full[ab], (uint32_t)(i >> 1) & 1u);
+        tc_fence_after_sync();
+        tmem_ld_32x32b_x16(tm + ab * 128 + 64 + c0 + lane_sel, vr);
+        row_load<XB, 32>(smem + s * STAGE + PANEL, r, 32 * half, xin);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&acc_free[ab]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          pk[j] = pack2(__uint_as_float(vr[2 * j]) + __uint_as_float(xin[j] << 16) + bias_sm[64 + c0 + 2 * j],
+                        __uint_as_float(vr[2 * j + 1]) + __uint_as_float(xin[j] & 0xffff0000u) + bias_sm[64 + c0 + 2 * j + 1]);
+        row_store<XB, 32>(otile, r, 32 * half, pk);
+        fence_proxy_async_smem();
+        if (elected) tma_store_wait_read<1>();  // every store but this tile's z store has finished reading smem
+        ebar();
+        if (elected) {
+          tma_store_3d(&map_xout, otile, 0, a.dil_next + t0, b);
+          tma_store_commit();
+          mbar_arrive(&stage_free[s]);
+        }
+      } else {
+        tc_fence_before_sync();
+        mbar_arrive(&acc_free[ab]);
+        if (elected) tma_store_wait_read<1>();
+        ebar();
+        if (elected) mbar_arrive(&stage_free[s]);
+      }
+    }
+    if (elected) tma_store_wait_all<0>();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tm, 256);
+}
+
+struct LayerDxPArgs {
+  int dil, l, has_next, n_tiles, tiles_per_slot;
+};
+
+template <int R, int D>
+__global__ void __launch_bounds__(320, 1)
+k_layer_bwd_dx_p_umma(const __grid_constant__ CUtensorMap map_dv, const __grid_constant__ CUtensorMap map_wd,
+                      const __grid_constant__ CUtensorMap map_dxn, const __grid_constant__ CUtensorMap map_dxo,
+                      LayerDxPArgs a) {
+  static_assert(R == 32 && D == 32, "64-byte activation rows");
+  constexpr int XB = 64, VB = 128;
+  constexpr int PANEL = 128 * XB, VT = 128 * VB;
+  constexpr int STAGE = 2 * VT + PANEL;  // dv[t] | dv[t+dil] | dx'
+  constexpr int NST = 4;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* ot = smem + NST * STAGE;  // [3] output tiles (a store may still be reading two tiles back)
+  unsigned char* wd0 = ot + 3 * PANEL;
+  unsigned char* wd1 = wd0 + R * VB;
+  __shared__ __align__(8) uint64_t w_full, in_full[NST], stage_free[NST], a_full[2], acc_free[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (tid == 0) {
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&in_full[i], 1);
+      mbar_init(&stage_free[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&acc_free[i], 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 64);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tm = tmem_base_s;  // buffer ab at ab*32
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&w_full, (uint32_t)(2 * R * VB));
+      tma_load_2d(wd0, &map_wd, &w_full, 0, (a.l * 2 + 0) * R);
+      tma_load_2d(wd1, &map_wd, &w_full, 0, (a.l * 2 + 1) * R);
+      for (int i = 0; i < n_my; ++i) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
+        const int s = i % NST;
+        unsigned char* st = smem + s * STAGE;
+        mbar_wait(&stage_free[s], ((uint32_t)(i / NST) & 1u) ^ 1u);
+        mbar_expect_tx(&in_full[s], (uint32_t)(2 * VT + (a.has_next ? PANEL : 0)));
+        tma_load_3d(st, &map_dv, &in_full[s], 0, t0, b);
+        tma_load_3d(st + VT, &map_dv, &in_full[s], 0, t0 + a.dil, b);  // rows >= T: zero fill == truncated gradient
+        if (a.has_next) tma_load_3d(st + 2 * VT, &map_dxn, &in_full[s], 0, t0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(&w_full, 0);
+      const uint32_t idesc = make_idesc_bf16(128, R);
+      for (int i = 0; i < n_my; ++i) {
+        const int s = i % NST, ab = i & 1;
+        const uint32_t st = smem_u32(smem + s * STAGE);
+        mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);
+        mbar_wait(&acc_free[ab], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 2 * D / 16; ++k)  // dv[t] . W[1]^T
+          mma_bf16_ss(tm + ab * 32, make_kmajor_desc(st, VB, k * 32), make_kmajor_desc(smem_u32(wd1), VB, k * 32), idesc, k != 0);
+#pragma unroll
+        for (int k = 0; k < 2 * D / 16; ++k)  // dv[t+dil] . W[0]^T
+          mma_bf16_ss(tm + ab * 32, make_kmajor_desc(st + VT, VB, k * 32), make_kmajor_desc(smem_u32(wd0), VB, k * 32), idesc, true);
+        mma_commit(&a_full[ab]);
+      }
+    }
+  } else {
+    const int e = warp - 2, q4 = warp & 3, half = e >> 2;
+    const int r = q4 * 32 + lane, c0 = 16 * half;
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    const bool elected = (warp == 2 && lane == 0);
+    auto ebar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    for (int i = 0; i < n_my; ++i) {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
+      const int s = i % NST, ab = i & 1;
+      unsigned char* otile = ot + (i % 3) * PANEL;
+      uint32_t vr[16], xin[8], pk[8];
+      mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);
+      mbar_wait(&a_full[ab], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after_sync();
+      tmem_ld_32x32b_x16(tm + ab * 32 + c0 + lane_sel, vr);
+      if (a.has_next) {
+        row_load<XB, 32>(smem + s * STAGE + 2 * VT, r, 32 * half, xin);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xin[j] = 0u;
+      }
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&acc_free[ab]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        pk[j] = pack2(__uint_as_float(vr[2 * j]) + __uint_as_float(xin[j] << 16),
+                      __uint_as_float(vr[2 * j + 1]) + __uint_as_float(xin[j] & 0xffff0000u));
+      row_store<XB, 32>(otile, r, 32 * half, pk);
+      fence_proxy_async_smem();
+      if (elected) tma_store_wait_read<1>();  // all stores but the previous tile's have drained: buffer (i+1)%3 is free
+      ebar();
+      if (elected) {
+        tma_store_3d(&map_dxo, otile, 0, t0, b);
+        tma_store_commit();
+        mbar_arrive(&stage_free[s]);
+      }
+    }
+    if (elected) tma_store_wait_all<0>();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tm, 64);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
@@ -652,21 +957,39 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
   const WorkspaceLayout& wl = m->wl;
   const wn_arch& a = m->a;
   const LayerDesc& ld = m->layers[l];
-  LayerFwdUmmaArgs fa;
-  memset(&fa, 0, sizeof(fa));
-  fa.params = d_params;
-  fa.sig_b = ld.sig_b; fa.gate_b = ld.gate_b; fa.res_b = ld.res_b;
   const int C1 = a.n_gc_category + 1;
-  fa.gc_tbl = a.n_gc_embed > 0 ? reinterpret_cast<const float*>(ws + wl.gc_tbl) + (size_t)l * C1 * 2 * a.n_dil : nullptr;
-  fa.ids = d_ids;
-  fa.T = T; fa.dil = ld.dil; fa.l = l; fa.C1 = C1;
-  fa.last = (l + 1 == m->L);
-  fa.dil_next = fa.last ? 0 : m->layers[l + 1].dil;
-  const CUtensorMap& mxo = fa.last ? mp->x[l] : mp->x[l + 1];
-  const size_t smem = 3 * 128 * 64 + 2 * 64 * 64 + 32 * 64 + 1024;
+  const bool last = (l + 1 == m->L);
+  const CUtensorMap& mxo = last ? mp->x[l] : mp->x[l + 1];
   const dim3 grid((T + 127) / 128, m->n_slots);
+  if (a.n_gc_embed > 0) {  // global conditioning: per-tile variant (reads the per-id projection table)
+    LayerFwdUmmaArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.params = d_params;
+    fa.sig_b = ld.sig_b; fa.gate_b = ld.gate_b; fa.res_b = ld.res_b;
+    fa.gc_tbl = reinterpret_cast<const float*>(ws + wl.gc_tbl) + (size_t)l * C1 * 2 * a.n_dil;
+    fa.ids = d_ids;
+    fa.T = T; fa.dil = ld.dil; fa.l = l; fa.C1 = C1;
+    fa.last = last;
+    fa.dil_next = last ? 0 : m->layers[l + 1].dil;
+    const size_t smem = 3 * 128 * 64 + 2 * 64 * 64 + 32 * 64 + 1024;
+    ProfScope ps(PROF_LAYER_FWD, st);
+    k_layer_fwd_umma<32, 32><<<grid, 128, smem, st>>>(mp->x[l], mxo, mp->z, mp->wc, mp->wr, fa);
+    WN_LAUNCH_CHECK();
+    return WN_OK;
+  }
+  LayerFwdPArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.params = d_params;
+  pa.sig_b = ld.sig_b; pa.gate_b = ld.gate_b; pa.res_b = ld.res_b;
+  pa.T = T; pa.dil = ld.dil; pa.l = l; pa.last = last;
+  pa.dil_next = last ? 0 : m->layers[l + 1].dil;
+  pa.tiles_per_slot = (T + 127) / 128;
+  pa.n_tiles = pa.tiles_per_slot * m->n_slots;
+  const size_t smem = 4 * 2 * 8192 + 4 * 8192 + 2 * 64 * 64 + 32 * 64 + 1024;
+  WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_fwd_p_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nblk = std::max(1, std::min(pa.n_tiles, 2 * m->sm_count));
   ProfScope ps(PROF_LAYER_FWD, st);
-  k_layer_fwd_umma<32, 32><<<grid, 128, smem, st>>>(mp->x[l], mxo, mp->z, mp->wc, mp->wr, fa);
+  k_layer_fwd_p_umma<32, 32><<<nblk, 320, smem, st>>>(mp->x[l], mxo, mp->z, mp->wc, mp->wr, pa);
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
@@ -676,15 +999,17 @@ int launch_layer_bwd_dx_umma(wn_model* m, unsigned char* ws, int T, int l, cudaS
   int rc;
   LayerMaps* mp = get_maps(m, ws, T, &rc);
   if (!mp) return rc;
-  LayerDxUmmaArgs da;
+  LayerDxPArgs da;
   da.dil = m->layers[l].dil;
   da.l = l;
   da.has_next = (l + 1 < m->L);
-  const size_t smem = 2 * 128 * 128 + 2 * 32 * 128 + 128 * 64 + 1024;
-  const dim3 grid((T + 127) / 128, m->n_slots);
-  WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_dx_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  da.tiles_per_slot = (T + 127) / 128;
+  da.n_tiles = da.tiles_per_slot * m->n_slots;
+  const size_t smem = 4 * (2 * 16384 + 8192) + 3 * 8192 + 2 * 32 * 128 + 1024;
+  WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_dx_p_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nblk = std::max(1, std::min(da.n_tiles, m->sm_count));
   ProfScope ps(PROF_LAYER_BWD_B, st);
-  k_layer_bwd_dx_umma<32, 32><<<grid, 128, smem, st>>>(mp->dv, mp->wd, mp->dx[(l + 1) & 1], mp->dx[l & 1], da);
+  k_layer_bwd_dx_p_umma<32, 32><<<nblk, 320, smem, st>>>(mp->dv, mp->wd, mp->dx[(l + 1) & 1], mp->dx[l & 1], da);
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
@@ -712,11 +1037,11 @@ int launch_layer_bwd_gate_umma(wn_model* m, const float* d_params, unsigned char
   ga.has_next = (l + 1 < m->L);
   ga.tiles_per_slot = (T + 127) / 128;
   ga.n_tiles = ga.tiles_per_slot * m->n_slots;
-  const size_t smem = 2 * (5 * 128 * 64 + 128 * 128) + 2 * 64 * 64 + 32 * 64 + 1024;
+  const size_t smem = 3 * (6 * 128 * 64 + 128 * 128) + 2 * 64 * 64 + 32 * 64 + 1024;
   WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_gate_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::max(1, std::min(ga.n_tiles, m->sm_count));
   ProfScope ps(PROF_LAYER_BWD_A, st);
-  k_layer_bwd_gate_umma<32, 32><<<grid, 192, smem, st>>>(mp->x[l], mp->dz, mp->dx[(l + 1) & 1], mp->dv, mp->wc, mp->wrn, ga);
+  k_layer_bwd_gate_umma<32, 32><<<grid, 320, smem, st>>>(mp->x[l], mp->dz, mp->dx[(l + 1) & 1], mp->dv, mp->wc, mp->wrn, ga);
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
