@@ -899,6 +899,14 @@ static int map2ds(CUtensorMap* out, const void* base, uint64_t inner, uint64_t o
   return make_tensor_map_bf16(out, base, 2, dims, strides, box, swizzle);
 }
 
+// test knob: WN_PERSIST_GRID=<n> caps the grid of the persistent kernels so that small problems exercise many
+// ring / phase wrap-arounds per CTA
+static int persist_grid(int want) {
+  const char* e = getenv("WN_PERSIST_GRID");
+  if (e != nullptr && atoi(e) > 0) return std::max(1, std::min(want, atoi(e)));
+  return want;
+}
+
 struct LayerMaps {
   const void* ws = nullptr;
   const void* model = nullptr;
@@ -987,7 +995,7 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
   pa.n_tiles = pa.tiles_per_slot * m->n_slots;
   const size_t smem = 4 * 2 * 8192 + 4 * 8192 + 2 * 64 * 64 + 32 * 64 + 1024;
   WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_fwd_p_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int nblk = std::max(1, std::min(pa.n_tiles, 2 * m->sm_count));
+  const int nblk = persist_grid(std::max(1, std::min(pa.n_tiles, 2 * m->sm_count)));
   ProfScope ps(PROF_LAYER_FWD, st);
   k_layer_fwd_p_umma<32, 32><<<nblk, 320, smem, st>>>(mp->x[l], mxo, mp->z, mp->wc, mp->wr, pa);
   WN_LAUNCH_CHECK();
@@ -1007,7 +1015,7 @@ int launch_layer_bwd_dx_umma(wn_model* m, unsigned char* ws, int T, int l, cudaS
   da.n_tiles = da.tiles_per_slot * m->n_slots;
   const size_t smem = 4 * (2 * 16384 + 8192) + 3 * 8192 + 2 * 32 * 128 + 1024;
   WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_dx_p_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int nblk = std::max(1, std::min(da.n_tiles, m->sm_count));
+  const int nblk = persist_grid(std::max(1, std::min(da.n_tiles, m->sm_count)));
   ProfScope ps(PROF_LAYER_BWD_B, st);
   k_layer_bwd_dx_p_umma<32, 32><<<nblk, 320, smem, st>>>(mp->dv, mp->wd, mp->dx[(l + 1) & 1], mp->dx[l & 1], da);
   WN_LAUNCH_CHECK();
@@ -1039,7 +1047,7 @@ int launch_layer_bwd_gate_umma(wn_model* m, const float* d_params, unsigned char
   ga.n_tiles = ga.tiles_per_slot * m->n_slots;
   const size_t smem = 3 * (6 * 128 * 64 + 128 * 128) + 2 * 64 * 64 + 32 * 64 + 1024;
   WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_gate_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = std::max(1, std::min(ga.n_tiles, m->sm_count));
+  const int grid = persist_grid(std::max(1, std::min(ga.n_tiles, m->sm_count)));
   ProfScope ps(PROF_LAYER_BWD_A, st);
   k_layer_bwd_gate_umma<32, 32><<<grid, 320, smem, st>>>(mp->x[l], mp->dz, mp->dx[(l + 1) & 1], mp->dv, mp->wc, mp->wrn, ga);
   WN_LAUNCH_CHECK();

@@ -90,7 +90,14 @@ __device__ __forceinline__ void htile_store32(unsigned char* htile, int row, int
   }
 }
 
-__global__ void __launch_bounds__(UPOST_THREADS, 1)
+constexpr int UPOST_P_THREADS = 320;  // producer warp, MMA warp, 8 epilogue warps
+
+__device__ __forceinline__ void epi_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Persistent: one CTA per SM loops over 128-row tiles.  TMEM holds two 256-column accumulators whose roles rotate
+// with the tile parity p: GEMM1 -> buf[p], GEMM2 -> buf[p^1], GEMM3 -> buf[p]; therefore the MMA warp can issue
+// tile i+1's skip GEMM (the long one, K = L*D) while the epilogue warps are still busy with tile i's loss.
+__global__ void __launch_bounds__(UPOST_P_THREADS, 1)
 k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_wsT,
                 const __grid_constant__ CUtensorMap map_w1T, const __grid_constant__ CUtensorMap map_w2T,
                 const __grid_constant__ CUtensorMap map_h1, const __grid_constant__ CUtensorMap map_h2,
@@ -100,13 +107,17 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
   unsigned char* stage_a = smem;                                  // USTAGES x 16 KB
   unsigned char* stage_b = smem + USTAGES * UA_BYTES;             // USTAGES x 32 KB
   unsigned char* htile = stage_b + USTAGES * UB_BYTES;            // 64 KB
-  __shared__ __align__(8) uint64_t full_bar[USTAGES], empty_bar[USTAGES], acc_full[3], h_ready[2];
+  __shared__ __align__(8) uint64_t full_bar[USTAGES], empty_bar[USTAGES], acc_full[2], acc_empty[2], h_ready[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[3 * 256];  // skip-bias sum | POST1_BIAS | POST2_BIAS (broadcast reads in the epilogues)
+  __shared__ float x_mx[2][128], x_sum[2][128], x_vl[2][128];  // softmax partials exchanged between the two
+  __shared__ int x_arg[2][128];                                 // column halves of a row
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = a.S, P = a.P, Q = a.Q;
-  for (int i = tid; i < 3 * 256; i += UPOST_THREADS) {
+  const int n_tiles = (int)((a.rows + UM - 1) / UM);
+  const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  for (int i = tid; i < 3 * 256; i += UPOST_P_THREADS) {
     float v = 0.f;
     if (a.use_bias) {
       const int which = i >> 8, c = i & 255;
@@ -116,7 +127,6 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
     }
     bias_s[i] = v;
   }
-  const int64_t row0 = (int64_t)blockIdx.x * UM;
   const int nkb1 = (a.LD + UKB - 1) / UKB, nkb2 = S / UKB, nkb3 = P / UKB;
 
   if (tid == 0) {
@@ -124,8 +134,11 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 3; ++i) mbar_init(&acc_full[i], 1);
-    for (int i = 0; i < 2; ++i) mbar_init(&h_ready[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 256);
+      mbar_init(&h_ready[i], 1);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&map_z);
     tma_prefetch_desc(&map_wsT);
@@ -137,28 +150,29 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t acc0 = tmem_base, acc1 = tmem_base + 256;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       int it = 0;
-      for (int kb = 0; kb < nkb1 + nkb2 + nkb3; ++kb, ++it) {
-        const int st = it % USTAGES;
-        const uint32_t ph = (uint32_t)(it / USTAGES) & 1u;
-        mbar_wait(&empty_bar[st], ph ^ 1u);
-        unsigned char* sa = stage_a + st * UA_BYTES;
-        unsigned char* sb = stage_b + st * UB_BYTES;
-        if (kb < nkb1) {
-          mbar_expect_tx(&full_bar[st], (uint32_t)(UA_BYTES + S * 128));
-          tma_load_2d(sa, &map_z, &full_bar[st], kb * UKB, (int)row0);
-          tma_load_2d(sb, &map_wsT, &full_bar[st], kb * UKB, 0);
-        } else if (kb < nkb1 + nkb2) {
-          mbar_expect_tx(&full_bar[st], (uint32_t)(P * 128));
-          tma_load_2d(sb, &map_w1T, &full_bar[st], (kb - nkb1) * UKB, 0);
-        } else {
-          mbar_expect_tx(&full_bar[st], (uint32_t)(Q * 128));
-          tma_load_2d(sb, &map_w2T, &full_bar[st], (kb - nkb1 - nkb2) * UKB, 0);
+      for (int i = 0; i < n_my; ++i) {
+        const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * UM;
+        for (int kb = 0; kb < nkb1 + nkb2 + nkb3; ++kb, ++it) {
+          const int st = it % USTAGES;
+          mbar_wait(&empty_bar[st], ((uint32_t)(it / USTAGES) & 1u) ^ 1u);
+          unsigned char* sa = stage_a + st * UA_BYTES;
+          unsigned char* sb = stage_b + st * UB_BYTES;
+          if (kb < nkb1) {
+            mbar_expect_tx(&full_bar[st], (uint32_t)(UA_BYTES + S * 128));
+            tma_load_2d(sa, &map_z, &full_bar[st], kb * UKB, row0);
+            tma_load_2d(sb, &map_wsT, &full_bar[st], kb * UKB, 0);
+          } else if (kb < nkb1 + nkb2) {
+            mbar_expect_tx(&full_bar[st], (uint32_t)(P * 128));
+            tma_load_2d(sb, &map_w1T, &full_bar[st], (kb - nkb1) * UKB, 0);
+          } else {
+            mbar_expect_tx(&full_bar[st], (uint32_t)(Q * 128));
+            tma_load_2d(sb, &map_w2T, &full_bar[st], (kb - nkb1 - nkb2) * UKB, 0);
+          }
         }
       }
     }
@@ -166,171 +180,190 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
     // ===== MMA issuer =====
     if (lane == 0) {
       int it = 0;
+      uint32_t use[2] = {0, 0};  // number of contractions issued into each accumulator buffer so far
       const uint32_t idesc1 = make_idesc_bf16(UM, S), idesc2 = make_idesc_bf16(UM, P), idesc3 = make_idesc_bf16(UM, Q);
-      for (int kb = 0; kb < nkb1; ++kb, ++it) {
-        const int st = it % USTAGES;
-        mbar_wait(&full_bar[st], (uint32_t)(it / USTAGES) & 1u);
+      auto gemm = [&](int buf, int nkb, uint32_t idesc, bool a_from_htile) {
+        mbar_wait(&acc_empty[buf], (use[buf] & 1u) ^ 1u);  // the previous contraction of this buffer has been drained
         tc_fence_after_sync();
-        const uint32_t sa = smem_u32(stage_a + st * UA_BYTES), sb = smem_u32(stage_b + st * UB_BYTES);
+        const uint32_t acc = tmem_base + (uint32_t)buf * 256;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int st = it % USTAGES;
+          mbar_wait(&full_bar[st], (uint32_t)(it / USTAGES) & 1u);
+          tc_fence_after_sync();
+          const uint32_t sa = a_from_htile ? smem_u32(htile + kb * UA_BYTES) : smem_u32(stage_a + st * UA_BYTES);
+          const uint32_t sb = smem_u32(stage_b + st * UB_BYTES);
 #pragma unroll
-        for (int k = 0; k < UKB / 16; ++k)
-          mma_bf16_ss(acc0, make_kmajor_desc(sa, 128, k * 32), make_kmajor_desc(sb, 128, k * 32), idesc1, (kb | k) != 0);
-        mma_commit(&empty_bar[st]);
-      }
-      mma_commit(&acc_full[0]);
-      mbar_wait(&h_ready[0], 0);
-      tc_fence_after_sync();
-      for (int kb = 0; kb < nkb2; ++kb, ++it) {
-        const int st = it % USTAGES;
-        mbar_wait(&full_bar[st], (uint32_t)(it / USTAGES) & 1u);
+          for (int k = 0; k < UKB / 16; ++k)
+            mma_bf16_ss(acc, make_kmajor_desc(sa, 128, k * 32), make_kmajor_desc(sb, 128, k * 32), idesc, (kb | k) != 0);
+          mma_commit(&empty_bar[st]);
+        }
+        mma_commit(&acc_full[buf]);
+        ++use[buf];
+      };
+      for (int i = 0; i < n_my; ++i) {
+        const int p = i & 1;
+        gemm(p, nkb1, idesc1, false);
+        mbar_wait(&h_ready[0], (uint32_t)i & 1u);
         tc_fence_after_sync();
-        const uint32_t sa = smem_u32(htile + kb * UA_BYTES), sb = smem_u32(stage_b + st * UB_BYTES);
-#pragma unroll
-        for (int k = 0; k < UKB / 16; ++k)
-          mma_bf16_ss(acc1, make_kmajor_desc(sa, 128, k * 32), make_kmajor_desc(sb, 128, k * 32), idesc2, (kb | k) != 0);
-        mma_commit(&empty_bar[st]);
-      }
-      mma_commit(&acc_full[1]);
-      mbar_wait(&h_ready[1], 0);
-      tc_fence_after_sync();
-      for (int kb = 0; kb < nkb3; ++kb, ++it) {
-        const int st = it % USTAGES;
-        mbar_wait(&full_bar[st], (uint32_t)(it / USTAGES) & 1u);
+        gemm(p ^ 1, nkb2, idesc2, true);
+        mbar_wait(&h_ready[1], (uint32_t)i & 1u);
         tc_fence_after_sync();
-        const uint32_t sa = smem_u32(htile + kb * UA_BYTES), sb = smem_u32(stage_b + st * UB_BYTES);
-#pragma unroll
-        for (int k = 0; k < UKB / 16; ++k)
-          mma_bf16_ss(acc0, make_kmajor_desc(sa, 128, k * 32), make_kmajor_desc(sb, 128, k * 32), idesc3, (kb | k) != 0);
-        mma_commit(&empty_bar[st]);
+        gemm(p, nkb3, idesc3, true);
       }
-      mma_commit(&acc_full[2]);
     }
   } else {
-    // ===== epilogue warps: thread <-> row =====
-    const int q4 = warp & 3;                 // TMEM lane quarter this warp may access
-    const int r = q4 * 32 + lane;            // row inside the tile
-    const int64_t row = row0 + r;
+    // ===== epilogue warps: thread <-> (row, column half) =====
+    const int e = warp - 2, q4 = warp & 3, half = e >> 2;
+    const int r = q4 * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
     const bool elected = (warp == 2 && lane == 0);
+    uint32_t use[2] = {0, 0};
     uint32_t v[32];
     uint32_t pk[16];
-
-    // ---- h1 = relu(skip_sum + bias) ----
-    mbar_wait(&acc_full[0], 0);
-    tc_fence_after_sync();
-    for (int c0 = 0; c0 < S; c0 += 32) {
-      tmem_ld_32x32b_x32(acc0 + lane_sel + (uint32_t)c0, v);
-      tmem_ld_wait();
+    float acc_x = 0.f, acc_n = 0.f, acc_d = 0.f;  // loss statistics over all tiles of this CTA
+    auto acc_wait = [&](int buf) -> uint32_t {
+      mbar_wait(&acc_full[buf], use[buf] & 1u);
+      tc_fence_after_sync();
+      return tmem_base + (uint32_t)buf * 256 + lane_sel;
+    };
+    auto acc_release = [&](int buf) {
+      tc_fence_before_sync();
+      mbar_arrive(&acc_empty[buf]);
+      ++use[buf];
+    };
+    for (int i = 0; i < n_my; ++i) {
+      const int p = i & 1;
+      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * UM;
+      const int64_t row = row0 + r;
+      // ---- h1 = relu(skip_sum + bias) ----
+      {
+        const uint32_t acc = acc_wait(p);
+        if (elected) tma_store_wait_read<0>();  // the previous tile's dlogits store has finished reading the tile
+        epi_bar_sync256();
+        const int cb = half * (S / 2);
+        for (int c0 = cb; c0 < cb + S / 2; c0 += 32) {
+          tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+          tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float x0 = __uint_as_float(v[2 * j]) + bias_s[c0 + 2 * j];
-        const float x1 = __uint_as_float(v[2 * j + 1]) + bias_s[c0 + 2 * j + 1];
-        pk[j] = pack_bf16x2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
-      }
-      htile_store32(htile, r, c0, pk);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    epi_bar_sync();
-    if (elected) {
-      for (int kb = 0; kb < nkb2; ++kb) tma_store_2d(&map_h1, htile + kb * UA_BYTES, kb * UKB, (int)row0);
-      tma_store_commit();
-      mbar_arrive(&h_ready[0]);
-    }
-
-    // ---- h2 = relu(h1 . POST1 + b1) ----
-    mbar_wait(&acc_full[1], 0);
-    tc_fence_after_sync();
-    if (elected) tma_store_wait_read<0>();  // the h1 store has finished reading the tile
-    epi_bar_sync();
-    for (int c0 = 0; c0 < P; c0 += 32) {
-      tmem_ld_32x32b_x32(acc1 + lane_sel + (uint32_t)c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float x0 = __uint_as_float(v[2 * j]) + bias_s[256 + c0 + 2 * j];
-        const float x1 = __uint_as_float(v[2 * j + 1]) + bias_s[256 + c0 + 2 * j + 1];
-        pk[j] = pack_bf16x2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
-      }
-      htile_store32(htile, r, c0, pk);
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    epi_bar_sync();
-    if (elected) {
-      for (int kb = 0; kb < nkb3; ++kb) tma_store_2d(&map_h2, htile + kb * UA_BYTES, kb * UKB, (int)row0);
-      tma_store_commit();
-      mbar_arrive(&h_ready[1]);
-    }
-
-    // ---- logits, masked softmax cross entropy, dlogits ----
-    mbar_wait(&acc_full[2], 0);
-    tc_fence_after_sync();
-    const bool in_range = row < a.rows;
-    const int b = in_range ? (int)(row / a.T) : 0, t = in_range ? (int)(row % a.T) : 0;
-    const bool has_next = in_range && (t + 1 < a.T);
-    const bool valid = has_next && (a.ids[(size_t)b * a.T + t + 1] != 0);  // tmodel.py:232
-    int label = has_next ? a.wav[(size_t)b * a.T + t + 1] : 0;              // tmodel.py:230
-    label = min(max(label, 0), Q - 1);
-    float mx = -INFINITY, vl = 0.f;
-    int arg = 0;
-    for (int c0 = 0; c0 < Q; c0 += 32) {  // pass 1: max, argmax (smallest index on ties), label logit
-      tmem_ld_32x32b_x32(acc0 + lane_sel + (uint32_t)c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = __uint_as_float(v[j]) + bias_s[512 + c0 + j];
-        if (x > mx) {
-          mx = x;
-          arg = c0 + j;
+          for (int j = 0; j < 16; ++j)
+            pk[j] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + bias_s[c0 + 2 * j], 0.f),
+                                fmaxf(__uint_as_float(v[2 * j + 1]) + bias_s[c0 + 2 * j + 1], 0.f));
+          htile_store32(htile, r, c0, pk);
         }
-        if (c0 + j == label) vl = x;
-        if (a.logits_out != nullptr && in_range) a.logits_out[(size_t)row * Q + c0 + j] = x;
+        acc_release(p);
+        fence_proxy_async_smem();
+        epi_bar_sync256();
+        if (elected) {
+          mbar_arrive(&h_ready[0]);
+          for (int kb = 0; kb < nkb2; ++kb) tma_store_2d(&map_h1, htile + kb * UA_BYTES, kb * UKB, (int)row0);
+          tma_store_commit();
+        }
       }
-    }
-    float sum = 0.f;
-    for (int c0 = 0; c0 < Q; c0 += 32) {  // pass 2: sum of exponentials
-      tmem_ld_32x32b_x32(acc0 + lane_sel + (uint32_t)c0, v);
-      tmem_ld_wait();
+      // ---- h2 = relu(h1 . POST1 + b1) ----
+      {
+        const uint32_t acc = acc_wait(p ^ 1);   // also: the contraction reading h1 from the tile has completed
+        if (elected) tma_store_wait_read<0>();  // the h1 store has finished reading the tile
+        epi_bar_sync256();
+        const int cb = half * (P / 2);
+        for (int c0 = cb; c0 < cb + P / 2; c0 += 32) {
+          tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+          tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = __uint_as_float(v[j]) + bias_s[512 + c0 + j];
-        sum += __expf(x - mx);
+          for (int j = 0; j < 16; ++j)
+            pk[j] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + bias_s[256 + c0 + 2 * j], 0.f),
+                                fmaxf(__uint_as_float(v[2 * j + 1]) + bias_s[256 + c0 + 2 * j + 1], 0.f));
+          htile_store32(htile, r, c0, pk);
+        }
+        acc_release(p ^ 1);
+        fence_proxy_async_smem();
+        epi_bar_sync256();
+        if (elected) {
+          mbar_arrive(&h_ready[1]);
+          for (int kb = 0; kb < nkb3; ++kb) tma_store_2d(&map_h2, htile + kb * UA_BYTES, kb * UKB, (int)row0);
+          tma_store_commit();
+        }
       }
-    }
-    const float inv = 1.f / sum;
-    if (elected) tma_store_wait_read<0>();  // the h2 store has finished reading the tile
-    epi_bar_sync();
-    for (int c0 = 0; c0 < Q; c0 += 32) {  // pass 3: dlogits = (softmax - onehot) * mask
-      tmem_ld_32x32b_x32(acc0 + lane_sel + (uint32_t)c0, v);
-      tmem_ld_wait();
+      // ---- logits, masked softmax cross entropy, dlogits ----
+      {
+        const uint32_t acc = acc_wait(p);
+        const bool in_range = row < a.rows;
+        const int b = in_range ? (int)(row / a.T) : 0, t = in_range ? (int)(row % a.T) : 0;
+        const bool has_next = in_range && (t + 1 < a.T);
+        const bool valid = has_next && (a.ids[(size_t)b * a.T + t + 1] != 0);  // tmodel.py:232
+        int label = has_next ? a.wav[(size_t)b * a.T + t + 1] : 0;              // tmodel.py:230
+        label = min(max(label, 0), Q - 1);
+        const int cb = half * (Q / 2);
+        // pass 1 (online softmax over this thread's column half): running max, sum of exp, argmax, label logit
+        float mx = -INFINITY, sum = 0.f, vl = 0.f;
+        int arg = 0;
+        for (int c0 = cb; c0 < cb + Q / 2; c0 += 32) {
+          tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+          tmem_ld_wait();
+          float cm = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float x0 = __uint_as_float(v[2 * j]) + bias_s[512 + c0 + 2 * j];
-        const float x1 = __uint_as_float(v[2 * j + 1]) + bias_s[512 + c0 + 2 * j + 1];
-        float g0 = __expf(x0 - mx) * inv - ((c0 + 2 * j) == label ? 1.f : 0.f);
-        float g1 = __expf(x1 - mx) * inv - ((c0 + 2 * j + 1) == label ? 1.f : 0.f);
-        pk[j] = valid ? pack_bf16x2(g0, g1) : 0u;
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(v[j]) + bias_s[512 + c0 + j];
+            v[j] = __float_as_uint(x);
+            if (x > mx && x > cm) arg = c0 + j;  // first maximum: strictly greater than everything before
+            cm = fmaxf(cm, x);
+            if (c0 + j == label) vl = x;
+            if (a.logits_out != nullptr && in_range) a.logits_out[(size_t)row * Q + c0 + j] = x;
+          }
+          const float nm = fmaxf(mx, cm);
+          float cs = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cs += __expf(__uint_as_float(v[j]) - nm);
+          sum = sum * __expf(mx - nm) + cs;
+          mx = nm;
+        }
+        // exchange the partials between the two column halves of the row
+        x_mx[half][r] = mx;
+        x_sum[half][r] = sum;
+        x_arg[half][r] = arg;
+        x_vl[half][r] = vl;
+        if (elected) tma_store_wait_read<0>();  // the h2 store has finished reading the tile
+        epi_bar_sync256();
+        const float om = x_mx[half ^ 1][r], os = x_sum[half ^ 1][r];
+        const float M = fmaxf(mx, om);
+        const float tot = sum * __expf(mx - M) + os * __expf(om - M);
+        const float inv = 1.f / tot;
+        for (int c0 = cb; c0 < cb + Q / 2; c0 += 32) {  // pass 2: dlogits = (softmax - onehot) * mask
+          tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x0 = __uint_as_float(v[2 * j]) + bias_s[512 + c0 + 2 * j];
+            const float x1 = __uint_as_float(v[2 * j + 1]) + bias_s[512 + c0 + 2 * j + 1];
+            const float g0 = __expf(x0 - M) * inv - ((c0 + 2 * j) == label ? 1.f : 0.f);
+            const float g1 = __expf(x1 - M) * inv - ((c0 + 2 * j + 1) == label ? 1.f : 0.f);
+            pk[j] = valid ? pack_bf16x2(g0, g1) : 0u;
+          }
+          htile_store32(htile, r, c0, pk);
+        }
+        acc_release(p);
+        fence_proxy_async_smem();
+        epi_bar_sync256();
+        if (elected) {
+          for (int kb = 0; kb < Q / UKB; ++kb) tma_store_2d(&map_dlog, htile + kb * UA_BYTES, kb * UKB, (int)row0);
+          tma_store_commit();
+        }
+        if (half == 0 && valid) {  // one thread per row owns the statistics
+          // argmax over the whole row: smallest index among equal maxima (tf.argmax)
+          const int garg = (x_mx[1][r] > x_mx[0][r]) ? x_arg[1][r] : x_arg[0][r];
+          const float gvl = label < Q / 2 ? x_vl[0][r] : x_vl[1][r];
+          acc_x += __logf(tot) + M - gvl;
+          acc_n += 1.f;
+          acc_d += fabsf((float)(label - garg));
+        }
       }
-      htile_store32(htile, r, c0, pk);
     }
-    fence_proxy_async_smem();
-    epi_bar_sync();
-    if (elected) {
-      for (int kb = 0; kb < Q / UKB; ++kb) tma_store_2d(&map_dlog, htile + kb * UA_BYTES, kb * UKB, (int)row0);
-      tma_store_commit();
-    }
-    // loss statistics: warp reduce, one fp64 atomic per warp and statistic
-    float sx = valid ? (__logf(sum) + mx - vl) : 0.f;
-    float sn = valid ? 1.f : 0.f;
-    float sd = valid ? fabsf((float)(label - arg)) : 0.f;
-    sx = warp_sum(sx);
-    sn = warp_sum(sn);
-    sd = warp_sum(sd);
-    if (lane == 0 && sn != 0.f) {
-      atomicAdd(a.stats + WN_STAT_XENT_SUM, (double)sx);
-      atomicAdd(a.stats + WN_STAT_N_VALID, (double)sn);
-      atomicAdd(a.stats + WN_STAT_DIFF_SUM, (double)sd);
+    acc_x = warp_sum(acc_x);
+    acc_n = warp_sum(acc_n);
+    acc_d = warp_sum(acc_d);
+    if (lane == 0 && acc_n != 0.f) {
+      atomicAdd(a.stats + WN_STAT_XENT_SUM, (double)acc_x);
+      atomicAdd(a.stats + WN_STAT_N_VALID, (double)acc_n);
+      atomicAdd(a.stats + WN_STAT_DIFF_SUM, (double)acc_d);
     }
     if (elected) tma_store_wait_all<0>();
   }
@@ -640,7 +673,10 @@ int launch_post_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws, 
   const size_t smem = (size_t)USTAGES * (UA_BYTES + UB_BYTES) + UH_BYTES + 1024;
   WN_CUDA_CHECK(cudaFuncSetAttribute(k_post_fwd_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps(PROF_POST_FWD, st);
-  k_post_fwd_umma<<<(unsigned)((rows + UM - 1) / UM), UPOST_THREADS, smem, st>>>(mz, mwsT, mw1T, mw2T, mh1, mh2, mdl, pa);
+  const int n_tiles = (int)((rows + UM - 1) / UM);
+  int grid = std::max(1, std::min(n_tiles, m->sm_count));
+  if (const char* e = getenv("WN_PERSIST_GRID")) if (atoi(e) > 0) grid = std::max(1, std::min(grid, atoi(e)));
+  k_post_fwd_umma<<<grid, UPOST_P_THREADS, smem, st>>>(mz, mwsT, mw1T, mw2T, mh1, mh2, mdl, pa);
   WN_LAUNCH_CHECK();
   return WN_OK;
 }

@@ -45,6 +45,7 @@ def _run_fwd(arch, B, T, seed, scale=1.0):
 @pytest.mark.parametrize("arch,B,T", [
     (util.TINY, 3, 96), (util.TINY, 2, 7), (util.TINY_GC, 2, 130), (util.TINY_ASYM, 2, 64),
     (util.TINY_NOBIAS, 2, 64), (util.WIDE, 1, 70), (util.CLASSIC, 2, 300), (util.CLASSIC_SHALLOW, 3, 200),
+    (util.C1, 2, 160), (util.CLASSIC_SHALLOW, 2, 1000),
 ])
 def test_forward_matches_oracle(lib, arch, B, T):
     a, p, wav, ids, eng, logits = _run_fwd(arch, B, T, 3)
@@ -57,8 +58,11 @@ def test_forward_matches_oracle(lib, arch, B, T):
     util.record("fwd_parity_R%d_S%d_L%d_B%d_T%d" % (arch["n_res"], arch["n_skip"], a.n_layers, B, T),
                 dict(maxabs_vs_emulated=float(np.abs(logits - lg_em).max()), rel_vs_emulated=util.rel_err(logits, lg_em),
                      rel_vs_fp64=util.rel_err(logits, lg_ex), logit_absmax=float(np.abs(lg_ex).max())))
-    assert np.abs(logits - lg_em).max() <= 0.05, np.abs(logits - lg_em).max()
-    assert util.rel_err(logits, lg_em) <= 1e-2
+    # deep stacks (30-50 layers): every 1-ulp bf16 flip of the residual stream is amplified layer by layer, so the
+    # kernel ends up as far from the same-rounding oracle as that oracle is from fp64 (measured 0.8-1.5 % rel-L2)
+    deep = a.n_layers >= 16
+    assert np.abs(logits - lg_em).max() <= (0.15 if deep else 0.05), np.abs(logits - lg_em).max()
+    assert util.rel_err(logits, lg_em) <= (3e-2 if deep else 1e-2)
     assert util.rel_err(logits, lg_ex) <= 3e-2
     # layer-0 input is a pure gather + bias: bit-exact against bf16(PRE[wav] + PRE_BIAS)
     x0 = eng.debug_read(0, 0).cpu().numpy()
@@ -103,7 +107,7 @@ def test_stagewise_equals_whole(lib):
 
 @pytest.mark.parametrize("arch,B,T", [(util.TINY, 3, 96), (util.TINY_GC, 2, 130), (util.TINY_ASYM, 2, 64),
                                       (util.WIDE, 1, 70), (util.CLASSIC, 2, 300), (util.CLASSIC_SHALLOW, 3, 200),
-                                      (util.TINY_NOBIAS, 2, 64)])
+                                      (util.TINY_NOBIAS, 2, 64), (util.C1, 2, 160), (util.CLASSIC_SHALLOW, 2, 1000)])
 def test_gradients_match_oracle(lib, arch, B, T):
     a, p, wav, ids, eng, logits = _run_fwd(arch, B, T, 11)
     eng.backward()
@@ -136,6 +140,37 @@ def test_gradients_match_oracle(lib, arch, B, T):
     assert not bad, ("vs emulated oracle", bad)
     bad = {k: v for k, v in vs_ex.items() if v > (0.35 if deep else 0.2)}
     assert not bad, ("vs fp64 oracle", bad)
+
+
+@pytest.mark.parametrize("cap", ["1", "3"])
+def test_persistent_kernels_many_tiles_per_cta(lib, cap, monkeypatch):
+    """The persistent layer kernels loop over tiles with multi-stage TMA rings and double-buffered TMEM; with the
+    grid capped to 1 / 3 CTAs one CTA walks 16 / 6 tiles (ring and mbarrier phases wrap several times).  Results
+    must equal the uncapped run bit for bit (forward) and to fp32-atomic noise (gradients)."""
+    arch, B, T = util.CLASSIC_SHALLOW, 2, 1000
+    a = util.oracle_arch(arch)
+    p = util.scaled_params(a, B, 31)
+    wav, ids = util.synth_batch(B, T, 3, 32)
+    dw, di = torch.as_tensor(wav).cuda(), torch.as_tensor(ids).cuda()
+
+    def run():
+        eng = _engine(arch, B)
+        eng.load_state(p)
+        lg = eng.forward(dw, di, want_logits=True)
+        eng.backward()
+        torch.cuda.synchronize()
+        return lg.cpu().numpy(), eng.grads.cpu().numpy(), eng.save.float().cpu().numpy()
+
+    monkeypatch.delenv("WN_PERSIST_GRID", raising=False)
+    lg0, g0, s0 = run()
+    monkeypatch.setenv("WN_PERSIST_GRID", cap)
+    lg1, g1, s1 = run()
+    assert np.array_equal(lg0, lg1) and np.array_equal(s0, s1)
+    assert np.abs(g0 - g1).max() <= 1e-3 * max(1.0, np.abs(g0).max())
+    pt, save, kinds = O.to_torch_params(a, p, B, torch.float64, requires_grad=False)
+    em = O.train_forward(a, pt, save, torch.as_tensor(wav).long(), torch.as_tensor(ids).long(), torch.float64,
+                         emulate_bf16=True)
+    assert np.abs(lg1 - em.logits.numpy()).max() <= 0.05
 
 
 def test_adam_step_matches_tf_formula(lib):
