@@ -191,6 +191,9 @@ int wn_selftest_umma_gemm_tn(const void* d_a, const void* d_b, float* d_c, int32
  * and clears the records. */
 #define WN_PROF_NCAT 16
 int wn_prof_enable(int32_t on);
+/* developer aid: d_buf = device buffer of 32 x 2048 int64 (or NULL to switch off); CTA 0 of the persistent layer
+ * kernels (layer `layer`, -1 = all) logs (event << 56 | tile << 40 | clock64) per role warp -- see tools/trace_layer.py */
+int wn_debug_trace(void* d_buf, int32_t layer);
 int wn_prof_collect(double* h_ms, int64_t* h_launches);
 
 /* number of kernels launched by this library since the last call (for bench.py's

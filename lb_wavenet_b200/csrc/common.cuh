@@ -47,6 +47,23 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// ---- optional in-kernel timeline (tools/trace_layer.py): CTA 0's role warps log (event, tile, clock64) ----
+extern int g_trace_layer;       // layer whose launches are traced (-1: all)
+extern long long* g_trace_buf;  // device buffer [32 warps][WN_TRACE_PER_WARP] or nullptr (set by wn_debug_trace)
+constexpr int WN_TRACE_PER_WARP = 2048;
+struct Tracer {
+  long long* p;
+  int n;
+  __device__ __forceinline__ void init(long long* base, int warp, bool on) {
+    p = (base != nullptr && on) ? base + (size_t)warp * WN_TRACE_PER_WARP : nullptr;
+    n = 0;
+  }
+  __device__ __forceinline__ void ev(int code, int tile) {
+    if (p != nullptr && n < WN_TRACE_PER_WARP)
+      p[n++] = ((long long)code << 56) | ((long long)(tile & 0xffff) << 40) | (clock64() & 0xffffffffffLL);
+  }
+};
+
 // ---- math ------------------------------------------------------------------------------
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;

@@ -61,6 +61,8 @@ const WorkspaceLayout& workspace_layout(wn_model* m, int32_t T) {
   w.dv = take(rows * 2 * D * 2);
   w.dx[0] = take(rows * R * 2);
   w.dx[1] = take(rows * R * 2);
+  w.p0[0] = take(rows * R * 2);
+  w.p0[1] = take(rows * R * 2);
   const int64_t gc_elems = a.n_gc_embed > 0 ? L * (int64_t)(a.n_gc_category + 1) * 2 * D : 0;
   w.gc_tbl = take(gc_elems * 4);
   w.dgc_tbl = take(gc_elems * 4);

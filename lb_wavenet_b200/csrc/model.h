@@ -40,9 +40,10 @@ struct WorkspaceLayout {
   int64_t h1, h2;     // [B*T][S], [B*T][P] bf16
   int64_t dlogits;    // [B*T][Q] bf16
   int64_t dp1, dskip; // [B*T][P], [B*T][S] bf16
-  int64_t dz;         // [B*T][L*D] bf16
+  int64_t dz;         // [L][B*T][D] bf16: per-layer planes (dense 64-byte rows for the layer backward)
   int64_t dv;         // [B*T][2D] bf16
-  int64_t dx[2];      // [B*T][R] bf16 ping/pong
+  int64_t dx[2];      // [B*T][R] bf16 ping/pong: data gradient (GC path) / its Y part (fused backward)
+  int64_t p0[2];      // [B*T][R] bf16 ping/pong: P0 part of the split data gradient dx[t] = Y[t] + P0[t+dil]
   int64_t gc_tbl;     // [L][C+1][2D] fp32 (GC projections incl. nothing else)
   int64_t dgc_tbl;    // same shape, gradient
   int64_t skip_bias;  // [S] fp32, sum over layers of SKIP_BIAS

@@ -15,6 +15,8 @@
 namespace wn {
 
 int64_t g_launches = 0;
+long long* g_trace_buf = nullptr;
+int g_trace_layer = -1;
 
 // ---- per-category event timing ------------------------------------------------------------
 struct ProfState {
@@ -54,9 +56,9 @@ int launch_prep_layer_umma(wn_model* m, const float* d_params, unsigned char* ws
 int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_ids, int T, int l,
                           cudaStream_t st);
 int launch_layer_bwd_dx_umma(wn_model* m, unsigned char* ws, int T, int l, cudaStream_t st);
-bool umma_gate_supported(const wn_model* m);
-int launch_layer_bwd_gate_umma(wn_model* m, const float* d_params, unsigned char* ws, int T, int l, float* d_grads,
-                               cudaStream_t st);
+bool umma_bwd_fused_supported(const wn_model* m);
+int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned char* ws, int T, int l, float* d_grads,
+                                cudaStream_t st);
 bool umma_wgrad_supported(const wn_model* m, int lda, int ldy, int N);
 int launch_wgrad_umma(wn_model* m, const bf16* A, int lda, int a_col0, int M_total, const bf16* Y, int ldy, int N,
                       int64_t rows, float* out, int ldo, int mode, float* grads, cudaStream_t st);
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(NT) k_post_bwd(PostArgs a) {
     for (int idx = threadIdx.x; idx < TM * nl * D; idx += NT) {
       const int r = idx / (nl * D), c = idx % (nl * D);
       const int64_t row = row0 + r;
-      if (row < a.rows) a.dz[(size_t)row * a.LD + l0 * D + c] = f2bf(C_s[r * ldc + c]);
+      if (row < a.rows) a.dz[((size_t)(l0 + c / D) * a.rows + row) * D + c % D] = f2bf(C_s[r * ldc + c]);  // [L][B*T][D]
     }
   }
 }
@@ -500,7 +502,7 @@ struct LayerBwdArgs {
   const bf16* xin;      // xfull_l
   const bf16* dx_next;  // [B*T][R] gradient wrt x_{l+1}, nullptr for the last layer
   bf16* dx_out;         // [B*T][R] gradient wrt x_l
-  const bf16* dz;       // [B*T][LD]
+  const bf16* dz;       // [L][B*T][D]
   bf16* dv;             // [B*T][2D]
   const float* gc_tbl;
   float* dgc_tbl;       // this layer's [C1][2D] gradient table
@@ -554,7 +556,7 @@ __global__ void __launch_bounds__(NT) k_layer_bwd_a(LayerBwdArgs a) {
         vg += g[D + d];
       }
       const float th = tanh_fast(vs), sg = sigmoid_fast(vg);
-      float dz = bf2f(a.dz[((size_t)b * T + t) * a.LD + a.l * D + d]);
+      float dz = bf2f(a.dz[(((size_t)a.l * a.B + b) * T + t) * D + d]);
       if (a.dx_next != nullptr) dz += C2_s[r * ldc2 + d];
       o_s = f2bf(dz * sg * (1.f - th * th));
       o_g = f2bf(dz * th * sg * (1.f - sg));
@@ -723,9 +725,12 @@ __global__ void __launch_bounds__(NT) k_wgrad(WgradArgs a) {
 // ======================================================================================
 // PRE gather backward (scatter-add) + PRE_BIAS
 // ======================================================================================
-__global__ void __launch_bounds__(NT) k_embed_bwd(const bf16* __restrict__ dx0, const int32_t* __restrict__ wav,
-                                                  float* grads, int64_t off_pre, int64_t off_pre_b,
-                                                  int64_t rows, int R, int Q, int64_t rows_per_cta) {
+// dx0 = gradient wrt the layer-0 input; with p0 != nullptr it arrives in split form dx0[t] = dx0[t] + p0[t + dil0]
+// (rows t + dil0 >= T contribute nothing: truncated at the stage boundary), see layer_umma.cu
+__global__ void __launch_bounds__(NT) k_embed_bwd(const bf16* __restrict__ dx0, const bf16* __restrict__ p0, int dil0,
+                                                  int T, const int32_t* __restrict__ wav, float* grads,
+                                                  int64_t off_pre, int64_t off_pre_b, int64_t rows, int R, int Q,
+                                                  int64_t rows_per_cta) {
   extern __shared__ float tbl[];  // [Q][R] + [R]
   float* bias = tbl + (size_t)Q * R;
   for (int i = threadIdx.x; i < Q * R + R; i += NT) tbl[i] = 0.f;
@@ -734,7 +739,8 @@ __global__ void __launch_bounds__(NT) k_embed_bwd(const bf16* __restrict__ dx0, 
   for (int64_t i = r0 * R + threadIdx.x; i < r1 * R; i += NT) {
     const int64_t row = i / R;
     const int r = (int)(i % R);
-    const float v = bf2f(dx0[i]);
+    float v = bf2f(dx0[i]);
+    if (p0 != nullptr && (int)(row % T) + dil0 < T) v += bf2f(p0[i + (int64_t)dil0 * R]);
     const int code = wav[row];
     if (code >= 0 && code < Q) atomicAdd(&tbl[code * R + r], v);
     atomicAdd(&bias[r], v);
@@ -815,14 +821,18 @@ __global__ void k_l2(const float* __restrict__ w, const uint8_t* __restrict__ ki
   }
 }
 
+// `add` (optional, same [rows][ld] geometry): dst += add[t + add_shift] for t + add_shift < slot_rows
 __global__ void k_debug_read(const bf16* __restrict__ src, float* __restrict__ dst, int64_t n_rows, int ncols,
-                             int64_t slot_rows, int64_t slot_pitch_rows, int row_off, int ld, int col0) {
+                             int64_t slot_rows, int64_t slot_pitch_rows, int row_off, int ld, int col0,
+                             const bf16* __restrict__ add, int add_shift) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows * ncols) return;
   const int64_t row = i / ncols;
   const int c = (int)(i % ncols);
   const int64_t b = row / slot_rows, t = row % slot_rows;
-  dst[i] = bf2f(src[(b * slot_pitch_rows + t + row_off) * ld + col0 + c]);
+  float v = bf2f(src[(b * slot_pitch_rows + t + row_off) * ld + col0 + c]);
+  if (add != nullptr && t + add_shift < slot_rows) v += bf2f(add[(b * slot_pitch_rows + t + add_shift) * ld + col0 + c]);
+  dst[i] = v;
 }
 
 // ======================================================================================
@@ -947,6 +957,12 @@ int wn_prof_collect(double* h_ms, int64_t* h_launches) {
   }
   g_prof.used = 0;
   g_prof.recs.clear();
+  return WN_OK;
+}
+
+int wn_debug_trace(void* d_buf, int32_t layer) {
+  g_trace_buf = reinterpret_cast<long long*>(d_buf);
+  g_trace_layer = layer;
   return WN_OK;
 }
 
@@ -1147,6 +1163,7 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
   if ((rc = set_smem(k_layer_bwd_b, sb))) return rc;
   bf16* dxbuf[2] = {reinterpret_cast<bf16*>(ws + wl.dx[0]), reinterpret_cast<bf16*>(ws + wl.dx[1])};
   bf16* dv = reinterpret_cast<bf16*>(ws + wl.dv);
+  const bool fused = umma_bwd_fused_supported(m);  // data gradient in split form dx[t] = Y[t] + P0[t + dil]
   for (int l = d.L - 1; l >= 0; --l) {
     const int phase = d.L - l;
     if (phase < phase_begin || phase >= phase_end) continue;
@@ -1163,10 +1180,11 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
     la.ids = d_ids; la.grads = d_grads;
     la.B = d.B; la.T = T; la.R = d.R; la.D = d.D; la.LD = d.LD; la.l = l; la.C1 = d.C1;
     const dim3 grid((T + TM - 1) / TM, d.B);
-    if (umma_gate_supported(m)) {
-      // gate backward, conv / residual weight + bias gradients in one persistent tcgen05 kernel
-      if ((rc = launch_layer_bwd_gate_umma(m, d_params, ws, T, l, d_grads, st))) return rc;
-    } else {
+    if (fused) {
+      // gate backward, conv / residual weight + bias gradients and the data gradient in one persistent tcgen05 kernel
+      if ((rc = launch_layer_bwd_fused_umma(m, d_params, ws, T, l, d_grads, st))) return rc;
+      continue;
+    }
     {
       ProfScope ps(PROF_LAYER_BWD_A, st);
       k_layer_bwd_a<<<grid, NT, sa, st>>>(la);
@@ -1184,7 +1202,6 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
         if ((rc = launch_wgrad(wa, m->sm_count, st))) return rc;
       }
     }
-    }
     if (umma_layer_supported(m)) {
       if ((rc = launch_layer_bwd_dx_umma(m, ws, T, l, st))) return rc;
     } else {
@@ -1201,7 +1218,9 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
     if ((rc = set_smem(k_embed_bwd, esm))) return rc;
     const int nblk = (int)std::min<int64_t>(m->sm_count * 2, (d.rows + 255) / 256);
     const int64_t rpc = (d.rows + nblk - 1) / nblk;
-    k_embed_bwd<<<nblk, NT, esm, st>>>(dx_next, d_wav, d_grads, m->off_pre, m->off_pre_b, d.rows, d.R, d.Q, rpc);
+    const bf16* p0 = fused ? reinterpret_cast<const bf16*>(ws + wl.p0[0]) : nullptr;
+    k_embed_bwd<<<nblk, NT, esm, st>>>(dx_next, p0, m->layers[0].dil, T, d_wav, d_grads, m->off_pre, m->off_pre_b,
+                                       d.rows, d.R, d.Q, rpc);
     WN_LAUNCH_CHECK();
   }
   if (gc) {
@@ -1259,7 +1278,8 @@ int wn_debug_read(wn_model* m, const void* d_ws, int32_t T, int32_t what, int32_
   const Dims d = make_dims(m, T);
   const unsigned char* ws = (const unsigned char*)d_ws;
   const bf16* src = nullptr;
-  int ncols = 0, ld = 0, col0 = 0, row_off = 0;
+  const bf16* add = nullptr;
+  int ncols = 0, ld = 0, col0 = 0, row_off = 0, add_shift = 0;
   int64_t slot_rows = T, slot_pitch_rows = T;
   switch (what) {
     case 0:
@@ -1274,12 +1294,18 @@ int wn_debug_read(wn_model* m, const void* d_ws, int32_t T, int32_t what, int32_
     case 2: src = reinterpret_cast<const bf16*>(ws + wl.h1); ncols = d.S; ld = d.S; break;
     case 3: src = reinterpret_cast<const bf16*>(ws + wl.h2); ncols = d.P; ld = d.P; break;
     case 4: src = reinterpret_cast<const bf16*>(ws + wl.dlogits); ncols = d.Q; ld = d.Q; break;
-    case 5: src = reinterpret_cast<const bf16*>(ws + wl.dx[0]); ncols = d.R; ld = d.R; break;
+    case 5:  // gradient wrt the layer-0 input; the fused backward keeps it as Y[t] + P0[t + dil_0]
+      src = reinterpret_cast<const bf16*>(ws + wl.dx[0]); ncols = d.R; ld = d.R;
+      if (umma_bwd_fused_supported(m)) {
+        add = reinterpret_cast<const bf16*>(ws + wl.p0[0]);
+        add_shift = m->layers[0].dil;
+      }
+      break;
     default: set_error("wn_debug_read: unknown tap %d", what); return WN_ERR_INVALID;
   }
   const int64_t n = d.rows * ncols;
   k_debug_read<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(src, d_out, d.rows, ncols, slot_rows,
-                                                                             slot_pitch_rows, row_off, ld, col0);
+                                                                             slot_pitch_rows, row_off, ld, col0, add, add_shift);
   WN_LAUNCH_CHECK();
   return WN_OK;
 }

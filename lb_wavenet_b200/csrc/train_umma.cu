@@ -388,7 +388,7 @@ struct PostBwdUmmaArgs {
   float* g_post2_b;   // or nullptr
   float* g_post1_b;
   float* g_skip_b0;   // SKIP_BIAS of layer 0 (broadcast to the other layers afterwards)
-  int S, P, Q, LD;
+  int S, P, Q, LD, D;
   int64_t rows;
 };
 
@@ -592,20 +592,30 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
       const uint32_t acc = acc_wait();
       if (elected) tma_store_wait_read<0>();  // previous stores (dp1 / dskip / previous chunk) done reading smem
       epi_bar_sync();
+      // dz is stored as per-layer planes [L][B*T][D] (dense rows for the layer backward): the staging tile is a row of
+      // per-layer panels [128][D] whose rows are one swizzle span (2*D bytes)
       const int ncols = min(256, LD - c * 256);
+      const int span = 2 * a.D, panel_bytes = UM * span;
       for (int c0 = 0; c0 < ncols; c0 += 32) {
         tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-        htile_store32(tile1, r, c0, pk);
+        for (int ch = 0; ch < 4; ++ch) {
+          const int col = c0 + 8 * ch;
+          unsigned char* dst = tile1 + (col / a.D) * panel_bytes + swizzled_offset((uint32_t)r, (uint32_t)((col % a.D) * 2), span);
+          *reinterpret_cast<uint4*>(dst) =
+              make_uint4(pack_bf16x2(__uint_as_float(v[8 * ch]), __uint_as_float(v[8 * ch + 1])),
+                         pack_bf16x2(__uint_as_float(v[8 * ch + 2]), __uint_as_float(v[8 * ch + 3])),
+                         pack_bf16x2(__uint_as_float(v[8 * ch + 4]), __uint_as_float(v[8 * ch + 5])),
+                         pack_bf16x2(__uint_as_float(v[8 * ch + 6]), __uint_as_float(v[8 * ch + 7])));
+        }
       }
       acc_release();
       fence_proxy_async_smem();
       epi_bar_sync();
       if (elected) {
-        for (int kb = 0; kb * UKB < ncols; ++kb)
-          tma_store_2d(&map_dz, tile1 + kb * UA_BYTES, c * 256 + kb * UKB, (int)row0);
+        for (int pn = 0; pn * a.D < ncols; ++pn)
+          tma_store_3d(&map_dz, tile1 + pn * panel_bytes, 0, (int)row0, (c * 256) / a.D + pn);
         tma_store_commit();
       }
     }
@@ -621,7 +631,7 @@ bool umma_post_supported(const wn_model* m) {
   static const bool disabled = getenv("WN_DISABLE_UMMA") != nullptr;
   const wn_arch& a = m->a;
   return !disabled && a.n_skip % 64 == 0 && a.n_post % 64 == 0 && a.n_skip <= 256 && a.n_post <= 256 &&
-         a.n_quant == 256 && (m->L * a.n_dil) % 8 == 0;
+         a.n_quant == 256 && (a.n_dil == 16 || a.n_dil == 32 || a.n_dil == 64);
 }
 
 static int map2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
@@ -706,7 +716,13 @@ int launch_post_bwd_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, 
   if ((rc = map2d(&mcat, ws + wl.wsCat, S, LD, UKB, 256))) return rc;              // wsCat [LD][S]: N = LD, K = S
   if ((rc = map2d(&mdp1, ws + wl.dp1, P, (uint64_t)rows, UKB, UM))) return rc;
   if ((rc = map2d(&mdsk, ws + wl.dskip, S, (uint64_t)rows, UKB, UM))) return rc;
-  if ((rc = map2d(&mdz, ws + wl.dz, LD, (uint64_t)rows, UKB, UM))) return rc;
+  {  // dz planes [L][B*T][D]: box = one layer's [128][D] panel
+    const uint64_t D = a.n_dil;
+    const uint64_t dims[3] = {D, (uint64_t)rows, (uint64_t)m->L};
+    const uint64_t strides[2] = {D * 2, (uint64_t)rows * D * 2};
+    const uint32_t box[3] = {(uint32_t)D, UM, 1};
+    if ((rc = make_tensor_map_bf16(&mdz, ws + wl.dz, 3, dims, strides, box, (int)D * 2))) return rc;
+  }
   PostBwdUmmaArgs pa;
   memset(&pa, 0, sizeof(pa));
   pa.h1 = reinterpret_cast<const bf16*>(ws + wl.h1);
@@ -716,7 +732,7 @@ int launch_post_bwd_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, 
     pa.g_post1_b = d_grads + m->off_post1_b;
     pa.g_skip_b0 = d_grads + m->layers[0].skip_b;
   }
-  pa.S = a.n_skip; pa.P = a.n_post; pa.Q = a.n_quant; pa.LD = (int)LD; pa.rows = rows;
+  pa.S = a.n_skip; pa.P = a.n_post; pa.Q = a.n_quant; pa.LD = (int)LD; pa.D = a.n_dil; pa.rows = rows;
   const size_t smem = (size_t)2 * UH_BYTES + (size_t)UBSTAGES * UB_BYTES + 1024;
   WN_CUDA_CHECK(cudaFuncSetAttribute(k_post_bwd_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {

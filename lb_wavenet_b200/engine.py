@@ -180,6 +180,13 @@ class TrainEngine:
         check(self.lib.wn_train_backward(self.reg.handle, ptr(self.params), ptr(wav), ptr(ids), T, ptr(self.ws),
                                          ptr(self.grads), _lib.cur_stream()), "wn_train_backward")
 
+    def backward_phases(self, begin: int, end: int):
+        """phases [begin, end) of the backward: 0 = post-net, p = layer L-p, L+1 = PRE / GC (wavenet_b200.h)."""
+        wav, ids, T = self._last
+        check(self.lib.wn_train_backward_phases(self.reg.handle, ptr(self.params), ptr(wav), ptr(ids), T, ptr(self.ws),
+                                                ptr(self.grads), int(begin), int(end), _lib.cur_stream()),
+              "wn_train_backward_phases")
+
     def adam(self, step: int, lr: float, l2_factor: float, n_valid=None, beta1=0.9, beta2=0.999, eps=1e-8):
         """n_valid: device float64 tensor with the GLOBAL valid count (default: this rank's)."""
         nv = self.stats[_lib.STAT_N_VALID:_lib.STAT_N_VALID + 1] if n_valid is None else n_valid

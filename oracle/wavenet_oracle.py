@@ -492,10 +492,13 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
             Ws, Wg = W("SIGNAL_" + sfx), W("GATE_" + sfx)
             cur_part = dvs @ Ws[1].T + dvg @ Wg[1].T
             old_part = dvs @ Ws[0].T + dvg @ Wg[0].T  # gradient for full[t] , t in [0,T)
-            dxl = dx + cur_part
+            # CUDA path rounding points: the data gradient is stored in split form
+            # dx_l[t] = Y_l[t] + P0_l[t+dil] with Y_l = bf16(dx_{l+1} + cur_part), P0_l = bf16(old_part)
+            # and the consuming layer merges the two into one bf16 tile: dx_l = bf16(Y_l[t] + P0_l[t+dil])
+            dxl = _maybe(dx + cur_part, em)
             if T > dil:
-                dxl[:, :T - dil, :] += old_part[:, dil:, :]
-            dx = _maybe(dxl, em)
+                dxl[:, :T - dil, :] += _maybe(old_part, em)[:, dil:, :]
+            dx = _maybe(dxl, em) if li > 0 else dxl  # layer 0's gradient feeds the PRE gather in split form
         # PRE gather backward
         g["PRE"] = torch.zeros_like(pd["PRE"])
         okay = ((wav >= 0) & (wav < a.n_quant)).reshape(-1)

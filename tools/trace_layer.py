@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""In-kernel timeline of the persistent layer kernels (developer aid, GPU box only).
+
+    python tools/trace_layer.py [fwd|bwd] [layer]
+
+Runs BASELINE configs[1] once with tracing off, then one forward (+ backward) with wn_debug_trace pointing at a
+device buffer during ONE layer launch, and prints per-role event timelines of CTA 0 (clock64 deltas in cycles).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lb_wavenet_b200 import _lib, config  # noqa: E402
+from lb_wavenet_b200.engine import TrainEngine  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "bwd"
+layer = int(sys.argv[2]) if len(sys.argv) > 2 else 15
+arch = config.load_arch(os.path.join(ROOT, "par", "arch_classic_3x10.json"))
+B, T = 32, 16384
+eng = TrainEngine(arch, B)
+rng = np.random.default_rng(0)
+wav = torch.as_tensor(rng.integers(0, 256, (B, T)).astype(np.int32)).cuda()
+ids = torch.ones(B, T, dtype=torch.int32).cuda()
+lib = _lib.load()
+for _ in range(2):
+    eng.forward(wav, ids)
+    eng.backward()
+torch.cuda.synchronize()
+buf = torch.zeros(32 * 2048, dtype=torch.int64, device="cuda")
+L = len(eng.reg.saves)
+if which == "fwd":
+    # tracing stays on for the whole forward: every layer overwrites the buffer, the LAST layer that logged wins;
+    # so run the forward with tracing and keep only the wanted layer via phases is not possible -> trace layer L-2
+    lib.wn_debug_trace(buf.data_ptr(), layer)
+    eng.forward(wav, ids)
+    torch.cuda.synchronize()
+    lib.wn_debug_trace(None, -1)
+else:
+    eng.forward(wav, ids)
+    torch.cuda.synchronize()
+    eng.backward_phases(0, L - layer)      # everything above `layer`
+    torch.cuda.synchronize()
+    lib.wn_debug_trace(buf.data_ptr(), layer)
+    eng.backward_phases(L - layer, L - layer + 1)
+    torch.cuda.synchronize()
+    lib.wn_debug_trace(None, -1)
+ev = buf.cpu().numpy().reshape(32, 2048)
+names = {1: "prod:wait_free", 2: "prod:got_free", 3: "mma:issueA", 4: "mma:issueB", 5: "e1:begin", 14: "e1:in_full",
+         6: "e1:v_full", 15: "e1:math_done", 7: "e1:pre_bar", 8: "e1:post_bar", 9: "e2:begin", 10: "e2:acc_full",
+         11: "e2:pre_bar", 12: "e2:post_bar", 13: "e2:stored",
+         16: "mma:doneA", 17: "mma:doneB", 18: "e0:begin", 19: "e0:in_full", 20: "e0:done"}
+rows = []
+for w in range(32):
+    for x in ev[w]:
+        if x == 0:
+            continue
+        rows.append((int(x) & 0xffffffffff, w, (int(x) >> 56) & 0xff, (int(x) >> 40) & 0xffff))
+rows.sort()
+if not rows:
+    print("no events")
+    sys.exit(0)
+t0 = rows[0][0]
+maxtile = int(os.environ.get("TRACE_TILES", "12"))
+lo = int(os.environ.get("TRACE_FROM", "6"))
+for t, w, c, tile in rows:
+    if lo <= tile < lo + maxtile:
+        print("%9d  w%-2d tile %3d  %s" % (t - t0, w, tile, names.get(c, str(c))))
+# per-event mean period
+last = {}
+per = {}
+for t, w, c, tile in rows:
+    k = (w, c)
+    if k in last:
+        per.setdefault(k, []).append(t - last[k])
+    last[k] = t
+print("mean period per (warp, event):")
+for k in sorted(per):
+    print("  w%-2d %-16s %8.0f cycles over %d" % (k[0], names.get(k[1], str(k[1])), np.mean(per[k]), len(per[k])))
+print("total span %d cycles, tiles %d" % (rows[-1][0] - t0, max(r[3] for r in rows) + 1))
