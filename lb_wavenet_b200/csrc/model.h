@@ -9,6 +9,8 @@
 
 namespace wn {
 
+constexpr int WN_EMBED_PARTS = 256;
+
 struct ParamEntry {
   std::string name;
   int64_t offset;  // element offset into the fp32 arena
@@ -47,6 +49,7 @@ struct WorkspaceLayout {
   int64_t gc_tbl;     // [L][C+1][2D] fp32 (GC projections incl. nothing else)
   int64_t dgc_tbl;    // same shape, gradient
   int64_t skip_bias;  // [S] fp32, sum over layers of SKIP_BIAS
+  int64_t embed_part; // [WN_EMBED_PARTS][Q + 1][R] fp32: per-CTA partial PRE gradients
   // transposed / concatenated bf16 weight copies for the tcgen05 kernels (B operands, N x K K-major)
   int64_t wsT;        // [S][L*D]   = SKIP_l[d][s] at [s][l*D+d]
   int64_t wsCat;      // [L*D][S]   = SKIP_l stacked over layers

@@ -726,31 +726,51 @@ __global__ void __launch_bounds__(NT) k_wgrad(WgradArgs a) {
 // PRE gather backward (scatter-add) + PRE_BIAS
 // ======================================================================================
 // dx0 = gradient wrt the layer-0 input; with p0 != nullptr it arrives in split form dx0[t] = dx0[t] + p0[t + dil0]
-// (rows t + dil0 >= T contribute nothing: truncated at the stage boundary), see layer_umma.cu
-__global__ void __launch_bounds__(NT) k_embed_bwd(const bf16* __restrict__ dx0, const bf16* __restrict__ p0, int dil0,
-                                                  int T, const int32_t* __restrict__ wav, float* grads,
-                                                  int64_t off_pre, int64_t off_pre_b, int64_t rows, int R, int Q,
-                                                  int64_t rows_per_cta) {
-  extern __shared__ float tbl[];  // [Q][R] + [R]
-  float* bias = tbl + (size_t)Q * R;
-  for (int i = threadIdx.x; i < Q * R + R; i += NT) tbl[i] = 0.f;
+// (rows t + dil0 >= T contribute nothing: truncated at the stage boundary), see layer_umma.cu.
+// One warp per row, lane <-> channel: the shared-memory atomics of a warp hit 32 different banks.  Rows whose code is
+// out of range (an all-zero one-hot row, tmodel.py:64) still feed PRE_BIAS: they go to table row Q, and PRE_BIAS's
+// gradient is the column sum of the whole table (no per-row atomic on 32 hot addresses).
+__global__ void __launch_bounds__(1024) k_embed_bwd(const bf16* __restrict__ dx0, const bf16* __restrict__ p0, int dil0,
+                                                    int T, const int32_t* __restrict__ wav, float* __restrict__ part,
+                                                    int64_t rows, int R, int Q, int64_t rows_per_cta) {
+  extern __shared__ float tbl[];  // [Q + 1][R]
+  const int nt = blockDim.x;
+  for (int i = threadIdx.x; i < (Q + 1) * R; i += nt) tbl[i] = 0.f;
   __syncthreads();
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
-  for (int64_t i = r0 * R + threadIdx.x; i < r1 * R; i += NT) {
-    const int64_t row = i / R;
-    const int r = (int)(i % R);
-    float v = bf2f(dx0[i]);
-    if (p0 != nullptr && (int)(row % T) + dil0 < T) v += bf2f(p0[i + (int64_t)dil0 * R]);
-    const int code = wav[row];
-    if (code >= 0 && code < Q) atomicAdd(&tbl[code * R + r], v);
-    atomicAdd(&bias[r], v);
+  if (R == 32) {
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    for (int64_t row = r0 + wrp; row < r1; row += nt / 32) {
+      float v = bf2f(dx0[row * 32 + lane]);
+      if (p0 != nullptr && (int)(row % T) + dil0 < T) v += bf2f(p0[(row + dil0) * 32 + lane]);
+      int code = wav[row];
+      if (code < 0 || code >= Q) code = Q;
+      atomicAdd(&tbl[code * 32 + lane], v);
+    }
+  } else {
+    for (int64_t i = r0 * R + threadIdx.x; i < r1 * R; i += nt) {
+      const int64_t row = i / R;
+      const int r = (int)(i % R);
+      float v = bf2f(dx0[i]);
+      if (p0 != nullptr && (int)(row % T) + dil0 < T) v += bf2f(p0[i + (int64_t)dil0 * R]);
+      int code = wav[row];
+      if (code < 0 || code >= Q) code = Q;
+      atomicAdd(&tbl[code * R + r], v);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < Q * R; i += NT)
-    if (tbl[i] != 0.f) atomicAdd(grads + off_pre + i, tbl[i]);
-  if (off_pre_b >= 0)
-    for (int i = threadIdx.x; i < R; i += NT)
-      if (bias[i] != 0.f) atomicAdd(grads + off_pre_b + i, bias[i]);
+  float* dst = part + (size_t)blockIdx.x * (Q + 1) * R;  // per-CTA partial table: no global atomics
+  for (int i = threadIdx.x; i < (Q + 1) * R; i += nt) dst[i] = tbl[i];
+}
+// grads[PRE] += sum over the partial tables (rows < Q); grads[PRE_BIAS] += column sums over all Q + 1 rows
+__global__ void k_embed_bwd_reduce(const float* __restrict__ part, int n_part, float* grads, int64_t off_pre,
+                                   int64_t off_pre_b, int R, int Q) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (Q + 1) * R) return;
+  float sum = 0.f;
+  for (int p = 0; p < n_part; ++p) sum += part[(size_t)p * (Q + 1) * R + i];
+  if (i < Q * R) grads[off_pre + i] += sum;
+  if (off_pre_b >= 0 && sum != 0.f) atomicAdd(grads + off_pre_b + i % R, sum);
 }
 
 // ======================================================================================
@@ -1214,13 +1234,15 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
   ProfScope ps_tail(PROF_EMBED_GC_BWD, st);
   {
     const bf16* dx_next = dxbuf[0];  // gradient wrt the layer-0 input
-    const size_t esm = ((size_t)d.Q * d.R + d.R) * sizeof(float);
+    const size_t esm = ((size_t)(d.Q + 1) * d.R) * sizeof(float);
     if ((rc = set_smem(k_embed_bwd, esm))) return rc;
-    const int nblk = (int)std::min<int64_t>(m->sm_count * 2, (d.rows + 255) / 256);
+    const int nblk = (int)std::min<int64_t>(std::min(m->sm_count, WN_EMBED_PARTS), (d.rows + 1023) / 1024);
     const int64_t rpc = (d.rows + nblk - 1) / nblk;
     const bf16* p0 = fused ? reinterpret_cast<const bf16*>(ws + wl.p0[0]) : nullptr;
-    k_embed_bwd<<<nblk, NT, esm, st>>>(dx_next, p0, m->layers[0].dil, T, d_wav, d_grads, m->off_pre, m->off_pre_b,
-                                       d.rows, d.R, d.Q, rpc);
+    float* part = reinterpret_cast<float*>(ws + wl.embed_part);
+    k_embed_bwd<<<nblk, 1024, esm, st>>>(dx_next, p0, m->layers[0].dil, T, d_wav, part, d.rows, d.R, d.Q, rpc);
+    WN_LAUNCH_CHECK();
+    k_embed_bwd_reduce<<<((d.Q + 1) * d.R + 255) / 256, 256, 0, st>>>(part, nblk, d_grads, m->off_pre, m->off_pre_b, d.R, d.Q);
     WN_LAUNCH_CHECK();
   }
   if (gc) {

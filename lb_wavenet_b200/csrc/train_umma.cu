@@ -380,7 +380,7 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
 // B operands are the weights in their natural [N][K] row-major layout (POST2 [P][Q], POST1 [S][P]) and the
 // layer-stacked SKIP matrix wsCat [L*D][S].
 // =====================================================================================================
-constexpr int UBSTAGES = 2;
+constexpr int UBSTAGES = 3;
 
 struct PostBwdUmmaArgs {
   const bf16* h1;
@@ -392,20 +392,22 @@ struct PostBwdUmmaArgs {
   int64_t rows;
 };
 
-// column sums of a [128 x ncols] K-major SW128 tile; thread j of the 128 epilogue threads owns columns 2j, 2j+1
-__device__ __forceinline__ void tile_colsum_atomic(const unsigned char* tile, int ncols, int j, float* dst,
-                                                   int rows_valid) {
-  if (dst == nullptr || 2 * j >= ncols) return;
+// partial column sums of a [128 x ncols] K-major SW128 tile: thread et of the 256 epilogue threads owns the column
+// pair et / 2 and the row half et % 2; accumulated in registers across all tiles of the CTA
+__device__ __forceinline__ void tile_colsum_acc(const unsigned char* tile, int ncols, int et, int rows_valid, float (&acc)[2]) {
+  const int j = et >> 1;
+  if (2 * j >= ncols) return;
   const unsigned char* blk = tile + ((2 * j) >> 6) * UA_BYTES;
   const uint32_t byte_in_row = (uint32_t)((2 * j) & 63) * 2;
+  const int rb = (et & 1) * 64, re = min(rows_valid, rb + 64);
   float s0 = 0.f, s1 = 0.f;
-  for (int r = 0; r < rows_valid; ++r) {
+  for (int r = rb; r < re; ++r) {
     const uint32_t w = *reinterpret_cast<const uint32_t*>(blk + swizzled_offset((uint32_t)r, byte_in_row, 128));
     s0 += __uint_as_float(w << 16);
     s1 += __uint_as_float(w & 0xffff0000u);
   }
-  if (s0 != 0.f) atomicAdd(dst + 2 * j, s0);
-  if (s1 != 0.f) atomicAdd(dst + 2 * j + 1, s1);
+  acc[0] += s0;
+  acc[1] += s1;
 }
 
 // relu mask from 32 stored activations (64 bytes of one row), applied while packing to bf16
@@ -425,7 +427,11 @@ __device__ __forceinline__ void mask_pack32(const uint32_t (&v)[32], const bf16*
   }
 }
 
-__global__ void __launch_bounds__(UPOST_THREADS, 1)
+// Persistent: one CTA per SM loops over 128-row tiles; warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
+// (thread <-> (row, column half)).  The weight stream (B operands) runs through a 3-stage ring that never drains
+// between tiles; the next tile's dlogits are fetched as soon as the last dz-chunk contraction has released tile0, so
+// its first contraction overlaps the tail epilogues of the current tile.
+__global__ void __launch_bounds__(UPOST_P_THREADS, 1)
 k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_constant__ CUtensorMap map_w2,
                 const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_wsCat,
                 const __grid_constant__ CUtensorMap map_dp1, const __grid_constant__ CUtensorMap map_dskip,
@@ -435,12 +441,13 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
   unsigned char* tile0 = smem;                          // 64 KB: dlogits, later dskip
   unsigned char* tile1 = smem + UH_BYTES;               // 64 KB: dp1, later dz staging
   unsigned char* stage_b = smem + 2 * UH_BYTES;         // UBSTAGES x 32 KB
-  __shared__ __align__(8) uint64_t full_bar[UBSTAGES], empty_bar[UBSTAGES], a_full, acc_full[2], acc_empty[2],
+  __shared__ __align__(8) uint64_t full_bar[UBSTAGES], empty_bar[UBSTAGES], a_full, t0_free, acc_full[2], acc_empty[2],
       t_ready[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = a.S, P = a.P, Q = a.Q, LD = a.LD;
-  const int64_t row0 = (int64_t)blockIdx.x * UM;
+  const int n_tiles = (int)((a.rows + UM - 1) / UM);
+  const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int nkb4 = Q / UKB, nkb5 = P / UKB, nkb6 = S / UKB;
   const int nchunk = (LD + 255) / 256;
 
@@ -450,9 +457,10 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(&a_full, 1);
+    mbar_init(&t0_free, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], 256);
       mbar_init(&t_ready[i], 1);
     }
     fence_mbar_init();
@@ -469,8 +477,6 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(&a_full, (uint32_t)(nkb4 * UA_BYTES));
-      for (int kb = 0; kb < nkb4; ++kb) tma_load_2d(tile0 + kb * UA_BYTES, &map_dlog, &a_full, kb * UKB, (int)row0);
       int it = 0;
       auto load_b = [&](const CUtensorMap* mp, int k0, int n0, uint32_t bytes) {
         const int st = it % UBSTAGES;
@@ -479,10 +485,16 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
         tma_load_2d(stage_b + st * UB_BYTES, mp, &full_bar[st], k0, n0);
         ++it;
       };
-      for (int kb = 0; kb < nkb4; ++kb) load_b(&map_w2, kb * UKB, 0, (uint32_t)(P * 128));
-      for (int kb = 0; kb < nkb5; ++kb) load_b(&map_w1, kb * UKB, 0, (uint32_t)(S * 128));
-      for (int c = 0; c < nchunk; ++c)
-        for (int kb = 0; kb < nkb6; ++kb) load_b(&map_wsCat, kb * UKB, c * 256, (uint32_t)UB_BYTES);
+      for (int i = 0; i < n_my; ++i) {
+        const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * UM;
+        if (i > 0) mbar_wait(&t0_free, (uint32_t)(i - 1) & 1u);  // the previous tile's dz contractions have released tile0
+        mbar_expect_tx(&a_full, (uint32_t)(nkb4 * UA_BYTES));
+        for (int kb = 0; kb < nkb4; ++kb) tma_load_2d(tile0 + kb * UA_BYTES, &map_dlog, &a_full, kb * UKB, row0);
+        for (int kb = 0; kb < nkb4; ++kb) load_b(&map_w2, kb * UKB, 0, (uint32_t)(P * 128));
+        for (int kb = 0; kb < nkb5; ++kb) load_b(&map_w1, kb * UKB, 0, (uint32_t)(S * 128));
+        for (int c = 0; c < nchunk; ++c)
+          for (int kb = 0; kb < nkb6; ++kb) load_b(&map_wsCat, kb * UKB, c * 256, (uint32_t)UB_BYTES);
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -505,25 +517,29 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
         mma_commit(&acc_full[buf]);
         ++use;
       };
-      mbar_wait(&a_full, 0);
-      gemm(tile0, nkb4, make_idesc_bf16(UM, P));          // dp1 pre-activation gradient
-      mbar_wait(&t_ready[1], 0);                           // dp1 tile written
-      gemm(tile1, nkb5, make_idesc_bf16(UM, S));          // dskip pre-mask
-      mbar_wait(&t_ready[0], 0);                           // dskip tile written
-      for (int c = 0; c < nchunk; ++c) gemm(tile0, nkb6, make_idesc_bf16(UM, 256));  // dz chunks
+      for (int i = 0; i < n_my; ++i) {
+        mbar_wait(&a_full, (uint32_t)i & 1u);
+        tc_fence_after_sync();
+        gemm(tile0, nkb4, make_idesc_bf16(UM, P));          // dp1 pre-activation gradient
+        mbar_wait(&t_ready[1], (uint32_t)i & 1u);            // dp1 tile written
+        tc_fence_after_sync();
+        gemm(tile1, nkb5, make_idesc_bf16(UM, S));          // dskip pre-mask
+        mbar_wait(&t_ready[0], (uint32_t)i & 1u);            // dskip tile written
+        tc_fence_after_sync();
+        for (int c = 0; c < nchunk; ++c) gemm(tile0, nkb6, make_idesc_bf16(UM, 256));  // dz chunks
+        mma_commit(&t0_free);
+      }
     }
   } else {
-    const int q4 = warp & 3;
+    const int e = warp - 2, q4 = warp & 3, half = e >> 2;
     const int r = q4 * 32 + lane;
-    const int et = (warp - 2) * 32 + lane;  // 0..127 index among the epilogue threads
-    const int64_t row = row0 + r;
-    const bool in_range = row < a.rows;
-    const int rows_valid = (int)min((int64_t)UM, a.rows - row0);
+    const int et = e * 32 + lane;  // 0..255 index among the epilogue threads
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
     const bool elected = (warp == 2 && lane == 0);
     uint32_t v[32];
     uint32_t pk[16];
     int use = 0;
+    float b2acc[2] = {0.f, 0.f}, b1acc[2] = {0.f, 0.f}, bsacc[2] = {0.f, 0.f};
     auto acc_wait = [&]() -> uint32_t {
       const int buf = use & 1, k_use = use >> 1;
       mbar_wait(&acc_full[buf], (uint32_t)k_use & 1u);
@@ -535,89 +551,113 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
       mbar_arrive(&acc_empty[use & 1]);
       ++use;
     };
-    // POST2_BIAS gradient from the dlogits tile while the first contraction runs
-    mbar_wait(&a_full, 0);
-    tile_colsum_atomic(tile0, Q, et, a.g_post2_b, rows_valid);
-
-    // ---- dp1 ----
-    {
-      const uint32_t acc = acc_wait();
-      for (int c0 = 0; c0 < P; c0 += 32) {
-        tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (in_range) {
-          mask_pack32(v, a.h2 + (size_t)row * P + c0, pk);
-        } else {
+    for (int i = 0; i < n_my; ++i) {
+      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * UM;
+      const int64_t row = row0 + r;
+      const bool in_range = row < a.rows;
+      const int rows_valid = (int)min((int64_t)UM, a.rows - row0);
+      // POST2_BIAS gradient from the dlogits tile while the first contraction runs
+      mbar_wait(&a_full, (uint32_t)i & 1u);
+      if (a.g_post2_b != nullptr) tile_colsum_acc(tile0, Q, et, rows_valid, b2acc);
+      // ---- dp1 ----
+      {
+        const uint32_t acc = acc_wait();
+        if (elected) tma_store_wait_read<0>();  // the previous tile's last dz store has finished reading tile1
+        epi_bar_sync256();
+        const int cb = half * (P / 2);
+        for (int c0 = cb; c0 < cb + P / 2; c0 += 32) {
+          tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (in_range) {
+            mask_pack32(v, a.h2 + (size_t)row * P + c0, pk);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+            for (int j = 0; j < 16; ++j) pk[j] = 0u;
+          }
+          htile_store32(tile1, r, c0, pk);
         }
-        htile_store32(tile1, r, c0, pk);
+        acc_release();
+        fence_proxy_async_smem();
+        epi_bar_sync256();
+        if (elected) {
+          for (int kb = 0; kb < nkb5; ++kb) tma_store_2d(&map_dp1, tile1 + kb * UA_BYTES, kb * UKB, (int)row0);
+          tma_store_commit();
+          mbar_arrive(&t_ready[1]);
+        }
+        if (a.g_post1_b != nullptr) tile_colsum_acc(tile1, P, et, rows_valid, b1acc);
       }
-      acc_release();
-      fence_proxy_async_smem();
-      epi_bar_sync();
-      if (elected) {
-        for (int kb = 0; kb < nkb5; ++kb) tma_store_2d(&map_dp1, tile1 + kb * UA_BYTES, kb * UKB, (int)row0);
-        tma_store_commit();
-        mbar_arrive(&t_ready[1]);
-      }
-      tile_colsum_atomic(tile1, P, et, a.g_post1_b, rows_valid);
-    }
-    // ---- dskip ----
-    {
-      const uint32_t acc = acc_wait();  // also: the first contraction (reading tile0) has completed
-      for (int c0 = 0; c0 < S; c0 += 32) {
-        tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (in_range) {
-          mask_pack32(v, a.h1 + (size_t)row * S + c0, pk);
-        } else {
+      // ---- dskip ----
+      {
+        const uint32_t acc = acc_wait();  // also: the first contraction (reading tile0) has completed
+        const int cb = half * (S / 2);
+        for (int c0 = cb; c0 < cb + S / 2; c0 += 32) {
+          tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (in_range) {
+            mask_pack32(v, a.h1 + (size_t)row * S + c0, pk);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+            for (int j = 0; j < 16; ++j) pk[j] = 0u;
+          }
+          htile_store32(tile0, r, c0, pk);
         }
-        htile_store32(tile0, r, c0, pk);
+        acc_release();
+        fence_proxy_async_smem();
+        epi_bar_sync256();
+        if (elected) {
+          for (int kb = 0; kb < nkb6; ++kb) tma_store_2d(&map_dskip, tile0 + kb * UA_BYTES, kb * UKB, (int)row0);
+          tma_store_commit();
+          mbar_arrive(&t_ready[0]);
+        }
+        if (a.g_skip_b0 != nullptr) tile_colsum_acc(tile0, S, et, rows_valid, bsacc);
       }
-      acc_release();
-      fence_proxy_async_smem();
-      epi_bar_sync();
-      if (elected) {
-        for (int kb = 0; kb < nkb6; ++kb) tma_store_2d(&map_dskip, tile0 + kb * UA_BYTES, kb * UKB, (int)row0);
-        tma_store_commit();
-        mbar_arrive(&t_ready[0]);
-      }
-      tile_colsum_atomic(tile0, S, et, a.g_skip_b0, rows_valid);
-    }
-    // ---- dz chunks: staging through tile1 (dp1 is dead: its contraction and its TMA store are complete) ----
-    for (int c = 0; c < nchunk; ++c) {
-      const uint32_t acc = acc_wait();
-      if (elected) tma_store_wait_read<0>();  // previous stores (dp1 / dskip / previous chunk) done reading smem
-      epi_bar_sync();
+      // ---- dz chunks: staging through tile1 (dp1 is dead: its contraction and its TMA store are complete) ----
       // dz is stored as per-layer planes [L][B*T][D] (dense rows for the layer backward): the staging tile is a row of
       // per-layer panels [128][D] whose rows are one swizzle span (2*D bytes)
-      const int ncols = min(256, LD - c * 256);
       const int span = 2 * a.D, panel_bytes = UM * span;
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
-        tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
-        tmem_ld_wait();
+      for (int c = 0; c < nchunk; ++c) {
+        const uint32_t acc = acc_wait();
+        if (elected) tma_store_wait_read<0>();  // previous stores (dp1 / dskip / previous chunk) done reading smem
+        epi_bar_sync256();
+        const int ncols = min(256, LD - c * 256);
+        const int cb = half * 128, ce = min(ncols, cb + 128);
+        for (int c0 = cb; c0 < ce; c0 += 32) {
+          tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const int col = c0 + 8 * ch;
-          unsigned char* dst = tile1 + (col / a.D) * panel_bytes + swizzled_offset((uint32_t)r, (uint32_t)((col % a.D) * 2), span);
-          *reinterpret_cast<uint4*>(dst) =
-              make_uint4(pack_bf16x2(__uint_as_float(v[8 * ch]), __uint_as_float(v[8 * ch + 1])),
-                         pack_bf16x2(__uint_as_float(v[8 * ch + 2]), __uint_as_float(v[8 * ch + 3])),
-                         pack_bf16x2(__uint_as_float(v[8 * ch + 4]), __uint_as_float(v[8 * ch + 5])),
-                         pack_bf16x2(__uint_as_float(v[8 * ch + 6]), __uint_as_float(v[8 * ch + 7])));
+          for (int ch = 0; ch < 4; ++ch) {
+            const int col = c0 + 8 * ch;
+            unsigned char* dst = tile1 + (col / a.D) * panel_bytes + swizzled_offset((uint32_t)r, (uint32_t)((col % a.D) * 2), span);
+            *reinterpret_cast<uint4*>(dst) =
+                make_uint4(pack_bf16x2(__uint_as_float(v[8 * ch]), __uint_as_float(v[8 * ch + 1])),
+                           pack_bf16x2(__uint_as_float(v[8 * ch + 2]), __uint_as_float(v[8 * ch + 3])),
+                           pack_bf16x2(__uint_as_float(v[8 * ch + 4]), __uint_as_float(v[8 * ch + 5])),
+                           pack_bf16x2(__uint_as_float(v[8 * ch + 6]), __uint_as_float(v[8 * ch + 7])));
+          }
+        }
+        acc_release();
+        fence_proxy_async_smem();
+        epi_bar_sync256();
+        if (elected) {
+          for (int pn = 0; pn * a.D < ncols; ++pn)
+            tma_store_3d(&map_dz, tile1 + pn * panel_bytes, 0, (int)row0, (c * 256) / a.D + pn);
+          tma_store_commit();
         }
       }
-      acc_release();
-      fence_proxy_async_smem();
-      epi_bar_sync();
-      if (elected) {
-        for (int pn = 0; pn * a.D < ncols; ++pn)
-          tma_store_3d(&map_dz, tile1 + pn * panel_bytes, 0, (int)row0, (c * 256) / a.D + pn);
-        tma_store_commit();
-      }
+    }
+    // bias gradients: one atomic per (thread, column) for the whole CTA
+    const int j = et >> 1;
+    if (a.g_post2_b != nullptr && 2 * j < Q) {
+      if (b2acc[0] != 0.f) atomicAdd(a.g_post2_b + 2 * j, b2acc[0]);
+      if (b2acc[1] != 0.f) atomicAdd(a.g_post2_b + 2 * j + 1, b2acc[1]);
+    }
+    if (a.g_post1_b != nullptr && 2 * j < P) {
+      if (b1acc[0] != 0.f) atomicAdd(a.g_post1_b + 2 * j, b1acc[0]);
+      if (b1acc[1] != 0.f) atomicAdd(a.g_post1_b + 2 * j + 1, b1acc[1]);
+    }
+    if (a.g_skip_b0 != nullptr && 2 * j < S) {
+      if (bsacc[0] != 0.f) atomicAdd(a.g_skip_b0 + 2 * j, bsacc[0]);
+      if (bsacc[1] != 0.f) atomicAdd(a.g_skip_b0 + 2 * j + 1, bsacc[1]);
     }
     if (elected) tma_store_wait_all<0>();
   }
@@ -737,7 +777,10 @@ int launch_post_bwd_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, 
   WN_CUDA_CHECK(cudaFuncSetAttribute(k_post_bwd_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     ProfScope ps(PROF_POST_BWD, st);
-    k_post_bwd_umma<<<(unsigned)((rows + UM - 1) / UM), UPOST_THREADS, smem, st>>>(mdl, mw2, mw1, mcat, mdp1, mdsk, mdz, pa);
+    const int n_tiles = (int)((rows + UM - 1) / UM);
+    int grid = std::max(1, std::min(n_tiles, m->sm_count));
+    if (const char* e = getenv("WN_PERSIST_GRID")) if (atoi(e) > 0) grid = std::max(1, std::min(grid, atoi(e)));
+    k_post_bwd_umma<<<grid, UPOST_P_THREADS, smem, st>>>(mdl, mw2, mw1, mcat, mdp1, mdsk, mdz, pa);
     WN_LAUNCH_CHECK();
   }
   if (a.use_bias && m->L > 1) {
