@@ -148,7 +148,7 @@ def cpu_reference_run(arch, steps, warmup, n_threads=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-gen", action="store_true", help="skip the generation leg")
@@ -239,7 +239,6 @@ def main():
     prof_n = (C.c_int64 * 16)()
     lib.wn_prof_collect(prof_ms, prof_n)
     lib.wn_prof_enable(0)
-    clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         import torch.distributed as dist
@@ -263,6 +262,7 @@ def main():
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / args.steps
+    clk = clocks.stop() if rank == 0 else None  # sampled over both timed regions
     e2e = {"value": B_total * (T - 1) / (e2e_ms * 1e-3), "unit": "timesteps/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(2 * args.slots * T * 4 * max(world, 1)),
            "d2h_bytes_per_step": int(8 * _lib.WN_NSTATS * max(world, 1)), "loss": loss}
@@ -274,7 +274,9 @@ def main():
         return 0
 
     # ---- roofline of the dominant kernel (category timing from CUDA events on the launch stream) ----
-    cats = ["prep_embed_save", "layer_fwd", "post_fwd_loss", "post_bwd", "layer_bwd_gate", "layer_bwd_data",
+    # "layer_bwd": the fused per-layer backward kernel (gate backward + weight gradients + data gradient);
+    # "layer_bwd_data" only exists on the global-conditioning path (separate data-gradient kernel)
+    cats = ["prep_embed_save", "layer_fwd", "post_fwd_loss", "post_bwd", "layer_bwd", "layer_bwd_data",
             "wgrad", "pre_gc_bwd", "adam", "gen"]
     shares = {c: {"ms_per_step": prof_ms[k] / args.steps, "launches_per_step": prof_n[k] / args.steps}
               for k, c in enumerate(cats) if prof_n[k] > 0}
@@ -301,13 +303,24 @@ def main():
                         "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
                         "peak_source": peaks["source"], "ms_per_step": dms}
         else:
+            # algorithmic HBM bytes per timestep and layer, bf16:
+            #   layer_fwd : read x_l (R), write z_l (D) and x_{l+1} (R)
+            #   layer_bwd : read x_l (R), dz_l (D), Y_{l+1} (R), P0_{l+1} (R); write Y_l (R), P0_l (R)
             L = arch["n_blocks"] * arch["n_block_layers"]
-            byts = {"layer_fwd": L * 3 * arch["n_res"] * 2, "layer_bwd_gate": L * (2 * arch["n_res"] + 4 * arch["n_dil"]) * 2,
-                    "layer_bwd_data": L * (4 * arch["n_dil"] + 2 * arch["n_res"]) * 2}.get(dom, 0) * rows
-            ach = byts / (dms * 1e-3) / 1e9
+            R_, D_ = arch["n_res"], arch["n_dil"]
+            per_row = {"layer_fwd": L * (2 * R_ + D_) * 2, "layer_bwd": L * (5 * R_ + D_) * 2,
+                       "layer_bwd_data": L * (4 * D_ + 2 * R_) * 2}.get(dom, 0)
+            n_launch = max(1.0, shares[dom]["launches_per_step"])
+            ach = per_row * rows / (dms * 1e-3) / 1e9
+            traffic = None  # measured DRAM bytes per launch of this kernel (one ncu --set full capture, profiles/)
+            tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.exists(tp):
+                with open(tp) as f:
+                    traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
             roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
-                        "ms_per_step": dms}
+                        "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
+                        "algorithmic_bytes_per_launch": per_row * rows / n_launch,
+                        "us_per_launch": dms * 1e3 / n_launch, "peak_source": peaks["source"], "ms_per_step": dms}
     whole = value * train_flop_per_timestep(arch) / 1e12
 
     line = dict(base)

@@ -36,7 +36,7 @@ extern int64_t g_launches;  // kernels launched by this library (bench.py gpu_la
 
 // ---- per-category kernel timing (CUDA events on the launch stream; bench.py's roofline) ------
 enum ProfCat {
-  PROF_PREP = 0, PROF_LAYER_FWD = 1, PROF_POST_FWD = 2, PROF_POST_BWD = 3, PROF_LAYER_BWD_A = 4,
+  PROF_PREP = 0, PROF_LAYER_FWD = 1, PROF_POST_FWD = 2, PROF_POST_BWD = 3, PROF_LAYER_BWD_A = 4,  // 4: fused layer backward (or gate backward on the GC path)
   PROF_LAYER_BWD_B = 5, PROF_WGRAD = 6, PROF_EMBED_GC_BWD = 7, PROF_ADAM = 8, PROF_GEN = 9, PROF_NCAT = 16
 };
 struct ProfScope {

@@ -4,9 +4,11 @@
 TAG=${1:-prof}
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 3 --no-gen --no-cpu"
-python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench exit $?"
+python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench exit $?"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1; echo "ncu list exit $?"
 ncu --set full --clock-control none --import-source on -k regex:"k_post_fwd_umma|k_post_bwd_umma|k_wgrad_umma" -s 5 -c 5 -o gpurun_out/${TAG}_post $CMD > gpurun_out/${TAG}_ncu2.log 2>&1; echo "ncu post exit $?"
-ncu --set full --clock-control none --import-source on -k regex:"k_layer_fwd_p_umma|k_layer_bwd_gate_umma|k_layer_bwd_dx_p_umma" -s 195 -c 9 -o gpurun_out/${TAG}_layer $CMD > gpurun_out/${TAG}_ncu3.log 2>&1; echo "ncu layer exit $?"
+# layer kernels: 30 forward + 30 backward launches per step; skip two steps, then 4 forward + 4 backward of the middle
+ncu --set full --clock-control none --import-source on -k regex:"k_layer_fwd_p_umma" -s 73 -c 3 -o gpurun_out/${TAG}_lfwd $CMD > gpurun_out/${TAG}_ncu3.log 2>&1; echo "ncu layer fwd exit $?"
+ncu --set full --clock-control none --import-source on -k regex:"k_layer_bwd_fused_umma" -s 73 -c 3 -o gpurun_out/${TAG}_lbwd $CMD > gpurun_out/${TAG}_ncu4.log 2>&1; echo "ncu layer bwd exit $?"
 ls -la gpurun_out/${TAG}_*
