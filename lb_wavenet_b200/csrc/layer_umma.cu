@@ -277,8 +277,9 @@ k_layer_fwd_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 }
 
 // =====================================================================================================
-// Persistent forward kernel.  Roles: warp 0 TMA producer (+ L2 prefetch), warp 1 MMA issuer, warps 2..9 epilogue
-// ((TMEM lane quarter) x (channel half)), warp 10 TMA-store issuer; two CTAs per SM fill each other's bubbles.
+// Persistent forward kernel.  Roles: warp 0 TMA producer (+ L2 prefetch), warp 1 MMA issuer, warps 2..17 epilogue
+// (two groups of 8 warps alternating tiles; (TMEM lane quarter) x (channel half)), warp 18 TMA-store issuer; two CTAs
+// per SM fill each other's bubbles.
 // Measured on B200 (tools/mma_cost.cu, tools/trace_layer.py): one tcgen05.mma (M = 128, K = 16, N <= 64) occupies the
 // tensor pipe for ~48 cycles and its single-thread issue costs about as much again, and an elected epilogue thread
 // that issues a TMA store stalls its whole group for ~450 cycles -- hence: as few MMA instructions as possible (6 per
@@ -290,11 +291,12 @@ struct LayerFwdPArgs {
   int64_t sig_b, gate_b, res_b;
   int T, dil, dil_next, l, last, n_tiles, tiles_per_slot;
   int z_col;  // first column of this layer's block in the z stash
+  int pf;     // L2 prefetch distance in tiles beyond the ring (0: off, the default: measured 3-5 % slower with it)
   long long* trace;
 };
 
 template <int R, int D>
-__global__ void __launch_bounds__(352, 2)
+__global__ void __launch_bounds__(608, 2)
 k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_xout,
                    const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_wc,
                    const __grid_constant__ CUtensorMap map_wr, LayerFwdPArgs a) {
@@ -306,21 +308,33 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
   constexpr uint32_t HI = desc_hi(XB);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* zt = smem + NST * STAGE;       // [2] z tiles
+  unsigned char* zt = smem + NST * STAGE;       // [2] z tiles, one per epilogue group
   unsigned char* wc0 = zt + 2 * PANEL;          // [2D rows][R] 4 KB (GATE half pre-scaled by 0.5)
   unsigned char* wc1 = wc0 + 2 * D * XB;
   unsigned char* wr = wc1 + 2 * D * XB;         // [R rows][D] 2 KB
   __shared__ __align__(8) uint64_t w_full, in_full[NST], stage_free[NST], v_full[2], r_full[2], v_free[2], r_free[2],
-      z_ready[2], zo_ready[2], xo_ready[2], zt_free[2];
+      z_ready[2], zo_ready[2], xo_ready[NST], zt_free[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[96];   // SIGNAL_BIAS | 0.5 * GATE_BIAS | RESIDUAL_BIAS
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  Tracer tr;
+  tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
+  tr.ev(30, 0);
+  if (a.trace != nullptr && tid == 0) {  // per-CTA wall-clock start / SM id (tools/trace_layer.py)
+    unsigned long long gt;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x] = (long long)gt;
+    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 2] = (long long)smid;
+  }
   if (tid == 0) {
     mbar_init(&w_full, 1);
     for (int i = 0; i < NST; ++i) {
       mbar_init(&in_full[i], 1);
       mbar_init(&stage_free[i], 1);
+      mbar_init(&xo_ready[i], 1);  // per ring stage: a group that runs ahead of the store warp cannot lap a phase
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&v_full[i], 1);
@@ -329,7 +343,6 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
       mbar_init(&r_free[i], 256);
       mbar_init(&z_ready[i], 1);
       mbar_init(&zo_ready[i], 1);
-      mbar_init(&xo_ready[i], 1);
       mbar_init(&zt_free[i], 1);
     }
     fence_mbar_init();
@@ -343,12 +356,11 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tm = tmem_base_s;  // buffer ab: acc_v at ab*128 (64 cols), acc_r at ab*128 + 64 (32 cols)
-  Tracer tr;
-  tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
+  tr.ev(31, 0);
 
   if (warp == 0) {
     if (lane == 0) {
-      constexpr int PF = NST + 2;  // L2 prefetch distance (tiles)
+      const int PF = NST + a.pf;  // L2 prefetch distance (tiles)
       mbar_expect_tx(&w_full, (uint32_t)(2 * 2 * D * XB + (a.last ? 0 : R * XB)));
       tma_load_2d(wc0, &map_wc, &w_full, 0, (a.l * 2 + 0) * 2 * D);
       tma_load_2d(wc1, &map_wc, &w_full, 0, (a.l * 2 + 1) * 2 * D);
@@ -364,7 +376,7 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
         const int s = i % NST;
-        if (i + PF < n_my) prefetch(i + PF);
+        if (a.pf > 0 && i + PF < n_my) prefetch(i + PF);
         tr.ev(1, i);
         mbar_wait(&stage_free[s], ((uint32_t)(i / NST) & 1u) ^ 1u);
         tr.ev(2, i);
@@ -417,93 +429,103 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (did) spins = 0; else if (++spins > (1u << 26)) __trap();
       }
     }
-  } else if (warp < 10) {
-    const int e = warp - 2, q4 = warp & 3, half = e >> 2;
-    const int r = q4 * 32 + lane, c0 = 16 * half;
+  } else if (warp < 18) {
+    // ===== epilogue: two groups of 8 warps that alternate tiles (group g owns tiles g, g+2, ... and with them the
+    // accumulator parity g and z tile g); one group's TMEM round trip / proxy fence / barrier / wait for the residual
+    // MMA overlaps the other group's arithmetic.  thread <-> (row r, channels [16*half, +16)), two passes of 8 =====
+    const int e = warp - 2;
+    const int g = e >> 3, half = (e >> 2) & 1, q4 = warp & 3;
+    const int r = q4 * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    const bool elected = (warp == 2 && lane == 0);
+    const bool elected = ((e & 7) == 0 && lane == 0);
     const uint32_t sw = ((uint32_t)r >> 1) & 3u;  // SW64: 16-byte chunk index ^= (row / 2) % 4
-    const uint32_t o0 = (uint32_t)r * 64u + ((((uint32_t)(2 * half)) ^ sw) << 4);
-    const uint32_t o1 = (uint32_t)r * 64u + ((((uint32_t)(2 * half + 1)) ^ sw) << 4);
-    const float4* bs4 = reinterpret_cast<const float4*>(bias_s + c0);
-    const float4* bg4 = reinterpret_cast<const float4*>(bias_s + 32 + c0);
-    const float4* br4 = reinterpret_cast<const float4*>(bias_s + 64 + c0);
-    auto ebar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-    auto e1 = [&](int i) {  // gate: z = tanh(v_s + b_s) * sigmoid(v_g + b_g)
-      const int s = i % NST, ab = i & 1;
-      unsigned char* ztile = zt + ab * PANEL;
-      uint32_t vs[16], vg[16], pk[8];
+    const uint32_t o[2] = {(uint32_t)r * 64u + ((((uint32_t)(2 * half)) ^ sw) << 4),
+                           (uint32_t)r * 64u + ((((uint32_t)(2 * half + 1)) ^ sw) << 4)};
+    const float4* bs4 = reinterpret_cast<const float4*>(bias_s + 16 * half);
+    const float4* bg4 = reinterpret_cast<const float4*>(bias_s + 32 + 16 * half);
+    const float4* br4 = reinterpret_cast<const float4*>(bias_s + 64 + 16 * half);
+    unsigned char* ztile = zt + g * PANEL;
+    const uint32_t tb = tm + g * 128 + lane_sel;
+    auto gbar = [&]() {
+      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
+    };
+    for (int i = g; i < n_my; i += 2) {
+      const int s = i % NST, ab = g;
+      // ---- gate: z = tanh(v_s + b_s) * sigmoid(v_g + b_g) ----
       tr.ev(5, i);
       mbar_wait(&v_full[ab], (uint32_t)(i >> 1) & 1u);
       tr.ev(6, i);
       tc_fence_after_sync();
-      tmem_ld_32x32b_x16(tm + ab * 128 + c0 + lane_sel, vs);
-      tmem_ld_32x32b_x16(tm + ab * 128 + 32 + c0 + lane_sel, vg);
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      mbar_arrive(&v_free[ab]);
+      if (i >= 2) mbar_wait(&zt_free[ab], (uint32_t)((i - 2) >> 1) & 1u);  // z(i-2)'s store has finished reading zt[g]
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 b_s = bs4[q], b_g = bg4[q];
-        const float z0 = tanh_fast(__uint_as_float(vs[4 * q]) + b_s.x) * fmaf(0.5f, tanh_fast(__uint_as_float(vg[4 * q]) + b_g.x), 0.5f);
-        const float z1 = tanh_fast(__uint_as_float(vs[4 * q + 1]) + b_s.y) * fmaf(0.5f, tanh_fast(__uint_as_float(vg[4 * q + 1]) + b_g.y), 0.5f);
-        const float z2 = tanh_fast(__uint_as_float(vs[4 * q + 2]) + b_s.z) * fmaf(0.5f, tanh_fast(__uint_as_float(vg[4 * q + 2]) + b_g.z), 0.5f);
-        const float z3 = tanh_fast(__uint_as_float(vs[4 * q + 3]) + b_s.w) * fmaf(0.5f, tanh_fast(__uint_as_float(vg[4 * q + 3]) + b_g.w), 0.5f);
-        pk[2 * q] = pack2(z0, z1);
-        pk[2 * q + 1] = pack2(z2, z3);
+      for (int p = 0; p < 2; ++p) {
+        uint32_t vs[8], vg[8], pk[4];
+        tmem_ld_32x32b_x8(tb + 16 * half + 8 * p, vs);
+        tmem_ld_32x32b_x8(tb + 32 + 16 * half + 8 * p, vg);
+        tmem_ld_wait();
+        if (p == 1) {
+          tc_fence_before_sync();
+          mbar_arrive(&v_free[ab]);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float4 b_s = bs4[2 * p + q], b_g = bg4[2 * p + q];
+          const float z0 = tanh_fast(__uint_as_float(vs[4 * q]) + b_s.x) * fmaf(0.5f, tanh_fast(__uint_as_float(vg[4 * q]) + b_g.x), 0.5f);
+          const float z1 = tanh_fast(__uint_as_float(vs[4 * q + 1]) + b_s.y) * fmaf(0.5f, tanh_fast(__uint_as_float(vg[4 * q + 1]) + b_g.y), 0.5f);
+          const float z2 = tanh_fast(__uint_as_float(vs[4 * q + 2]) + b_s.z) * fmaf(0.5f, tanh_fast(__uint_as_float(vg[4 * q + 2]) + b_g.z), 0.5f);
+          const float z3 = tanh_fast(__uint_as_float(vs[4 * q + 3]) + b_s.w) * fmaf(0.5f, tanh_fast(__uint_as_float(vg[4 * q + 3]) + b_g.w), 0.5f);
+          pk[2 * q] = pack2(z0, z1);
+          pk[2 * q + 1] = pack2(z2, z3);
+        }
+        *reinterpret_cast<uint4*>(ztile + o[p]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
-      if (i >= 2) mbar_wait(&zt_free[ab], (uint32_t)((i - 2) >> 1) & 1u);  // z(i-2)'s store has finished reading zt[ab]
-      *reinterpret_cast<uint4*>(ztile + o0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(ztile + o1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       fence_proxy_async_smem();
       tr.ev(7, i);
-      ebar();
+      gbar();
       tr.ev(8, i);
       if (elected) {
         if (!a.last) mbar_arrive(&z_ready[ab]);
         else mbar_arrive(&stage_free[s]);  // last layer: both x tiles were only read by the (completed) conv MMA
         mbar_arrive(&zo_ready[ab]);
       }
-    };
-    auto e2 = [&](int i) {  // x' = bf16(x[t] + z . RESIDUAL + bias), written over the dead x[t-dil] tile
-      const int s = i % NST, ab = i & 1;
+      if (a.last) continue;
+      // ---- x' = bf16(x[t] + z . RESIDUAL + bias), written over the dead x[t-dil] tile ----
       unsigned char* otile = smem + s * STAGE;
       const unsigned char* x1 = otile + PANEL;
-      uint32_t vr[16], pk[8];
       tr.ev(9, i);
       mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);  // x[t] tile (TMA) visible to this thread
       mbar_wait(&r_full[ab], (uint32_t)(i >> 1) & 1u);
       tr.ev(10, i);
       tc_fence_after_sync();
-      tmem_ld_32x32b_x16(tm + ab * 128 + 64 + c0 + lane_sel, vr);
-      const uint4 xa = *reinterpret_cast<const uint4*>(x1 + o0), xb = *reinterpret_cast<const uint4*>(x1 + o1);
-      const uint32_t xin[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      mbar_arrive(&r_free[ab]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 b_r = br4[q];
-        pk[2 * q] = pack2(__uint_as_float(vr[4 * q]) + __uint_as_float(xin[2 * q] << 16) + b_r.x,
-                          __uint_as_float(vr[4 * q + 1]) + __uint_as_float(xin[2 * q] & 0xffff0000u) + b_r.y);
-        pk[2 * q + 1] = pack2(__uint_as_float(vr[4 * q + 2]) + __uint_as_float(xin[2 * q + 1] << 16) + b_r.z,
-                              __uint_as_float(vr[4 * q + 3]) + __uint_as_float(xin[2 * q + 1] & 0xffff0000u) + b_r.w);
+      for (int p = 0; p < 2; ++p) {
+        uint32_t vr[8], pk[4];
+        tmem_ld_32x32b_x8(tb + 64 + 16 * half + 8 * p, vr);
+        const uint4 xa = *reinterpret_cast<const uint4*>(x1 + o[p]);
+        const uint32_t xin[4] = {xa.x, xa.y, xa.z, xa.w};
+        tmem_ld_wait();
+        if (p == 1) {
+          tc_fence_before_sync();
+          mbar_arrive(&r_free[ab]);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float4 b_r = br4[2 * p + q];
+          pk[2 * q] = pack2(__uint_as_float(vr[4 * q]) + __uint_as_float(xin[2 * q] << 16) + b_r.x,
+                            __uint_as_float(vr[4 * q + 1]) + __uint_as_float(xin[2 * q] & 0xffff0000u) + b_r.y);
+          pk[2 * q + 1] = pack2(__uint_as_float(vr[4 * q + 2]) + __uint_as_float(xin[2 * q + 1] << 16) + b_r.z,
+                                __uint_as_float(vr[4 * q + 3]) + __uint_as_float(xin[2 * q + 1] & 0xffff0000u) + b_r.w);
+        }
+        *reinterpret_cast<uint4*>(otile + o[p]) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
-      *reinterpret_cast<uint4*>(otile + o0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(otile + o1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       fence_proxy_async_smem();
       tr.ev(11, i);
-      ebar();
+      gbar();
       tr.ev(12, i);
-      if (elected) mbar_arrive(&xo_ready[ab]);
-    };
-    // e1 runs one tile ahead of e2: the residual MMA of tile i executes while tile i+1 is being gated
-    for (int i = 0; i <= n_my; ++i) {
-      if (i < n_my) e1(i);
-      if (!a.last && i > 0) e2(i - 1);
+      if (elected) mbar_arrive(&xo_ready[s]);
     }
-  } else if (warp == 10) {
-    // ===== TMA-store issuer: z(0) z(1) x'(0) z(2) x'(1) ... ; hands zt buffers and ring stages back =====
+  } else if (warp == 18) {
+    // ===== TMA-store issuer: serves the z and x' queues in whatever order they fill; hands zt buffers and ring stages back =====
     if (lane == 0) {
       int prev_kind = -1, prev_idx = 0;  // newest committed bulk group: 0 = z tile, 1 = x' tile
       auto release_prev = [&]() {
@@ -512,33 +534,43 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (prev_kind == 0) mbar_arrive(&zt_free[prev_idx & 1]);
         else mbar_arrive(&stage_free[prev_idx % NST]);
       };
-      for (int i = 0; i <= n_my; ++i) {
-        if (i < n_my) {
-          const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      int nz = 0, nx = a.last ? n_my : 0;
+      uint32_t spins = 0;
+      while (nz < n_my || nx < n_my) {
+        bool did = false;
+        if (nz < n_my && mbar_test_wait(&zo_ready[nz & 1], (uint32_t)(nz >> 1) & 1u)) {
+          const int tile = (int)blockIdx.x + nz * (int)gridDim.x;
           const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
-          mbar_wait(&zo_ready[i & 1], (uint32_t)(i >> 1) & 1u);
-          tma_store_3d(&map_z, zt + (i & 1) * PANEL, a.z_col, t0, b);
+          tma_store_3d(&map_z, zt + (nz & 1) * PANEL, a.z_col, t0, b);
           tma_store_commit();
           release_prev();
-          prev_kind = 0; prev_idx = i;
+          prev_kind = 0; prev_idx = nz++;
+          did = true;
         }
-        if (!a.last && i > 0) {
-          const int j = i - 1;
-          const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+        if (nx < n_my && nx < nz && mbar_test_wait(&xo_ready[nx % NST], (uint32_t)(nx / NST) & 1u)) {
+          const int tile = (int)blockIdx.x + nx * (int)gridDim.x;
           const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
-          mbar_wait(&xo_ready[j & 1], (uint32_t)(j >> 1) & 1u);
-          tma_store_3d(&map_xout, smem + (j % NST) * STAGE, 0, a.dil_next + t0, b);
+          tma_store_3d(&map_xout, smem + (nx % NST) * STAGE, 0, a.dil_next + t0, b);
           tma_store_commit();
-          tr.ev(13, j);
+          tr.ev(13, nx);
           release_prev();
-          prev_kind = 1; prev_idx = j;
+          prev_kind = 1; prev_idx = nx++;
+          did = true;
         }
+        if (did) spins = 0; else if (++spins > (1u << 26)) __trap();
       }
       tma_store_wait_all<0>();
     }
   }
+  tr.ev(32, 0);
   tc_fence_before_sync();
   __syncthreads();
+  tr.ev(33, 0);
+  if (a.trace != nullptr && tid == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 1] = (long long)gt;
+  }
   if (warp == 1) tmem_dealloc(tm, 256);
 }
 
@@ -694,6 +726,7 @@ struct LayerBwdFusedArgs {
   float* grads;
   int64_t sig, gate, res, sig_b, gate_b, res_b;
   int dil, dil_next, l, has_next, n_tiles, tiles_per_slot, z_plane0;
+  int pf;  // L2 prefetch distance in tiles beyond the ring (0: off)
   long long* trace;
 };
 
@@ -760,11 +793,19 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
   const uint32_t tm = tmem_base_s;
   Tracer tr;
   tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
+  if (a.trace != nullptr && tid == 0) {  // per-CTA wall-clock start / SM id (tools/trace_layer.py)
+    unsigned long long gt;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x] = (long long)gt;
+    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 2] = (long long)smid;
+  }
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      constexpr int PF = NST + 2;  // L2 prefetch distance in tiles
+      const int PF = NST + a.pf;  // L2 prefetch distance in tiles
       mbar_expect_tx(&w_full, (uint32_t)(2 * 2 * D * XB + D * XB));
       tma_load_2d(wc0, &map_wc, &w_full, 0, (a.l * 2 + 0) * 2 * D);
       tma_load_2d(wc1, &map_wc, &w_full, 0, (a.l * 2 + 1) * 2 * D);
@@ -786,7 +827,7 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
         const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
         const int s = i % NST;
         unsigned char* st = smem + s * STAGE;
-        if (i + PF < n_my) prefetch(i + PF);
+        if (a.pf > 0 && i + PF < n_my) prefetch(i + PF);
         tr.ev(1, i);
         mbar_wait(&stage_free[s], ((uint32_t)(i / NST) & 1u) ^ 1u);
         tr.ev(2, i);
@@ -1130,6 +1171,11 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (a.trace != nullptr && tid == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 1] = (long long)gt;
+  }
   if (warp == 1) tmem_dealloc(tm, 512);
 }
 
@@ -1155,6 +1201,11 @@ static int persist_grid(int want) {
   const char* e = getenv("WN_PERSIST_GRID");
   if (e != nullptr && atoi(e) > 0) return std::max(1, std::min(want, atoi(e)));
   return want;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e != nullptr ? atoi(e) : dflt;
 }
 
 struct LayerMaps {
@@ -1247,13 +1298,14 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
   pa.tiles_per_slot = (T + 127) / 128;
   pa.n_tiles = pa.tiles_per_slot * m->n_slots;
   pa.z_col = l * a.n_dil;
+  pa.pf = env_int("WN_PF_FWD", 0);
   pa.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
   // stages 5 x 16 KB | z tiles 2 x 8 KB | wc 2 x 4 KB | wr 2 KB
   const size_t smem = 5 * 2 * 8192 + 2 * 8192 + 2 * 4096 + 2048 + 1024;
   WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_fwd_p_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nblk = persist_grid(std::max(1, std::min(pa.n_tiles, 2 * m->sm_count)));
   ProfScope ps(PROF_LAYER_FWD, st);
-  k_layer_fwd_p_umma<32, 32><<<nblk, 352, smem, st>>>(mp->x[l], mxo, mp->z, mp->wc, mp->wr, pa);
+  k_layer_fwd_p_umma<32, 32><<<nblk, 608, smem, st>>>(mp->x[l], mxo, mp->z, mp->wc, mp->wr, pa);
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
@@ -1299,6 +1351,7 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
   ga.tiles_per_slot = (T + 127) / 128;
   ga.n_tiles = ga.tiles_per_slot * m->n_slots;
   ga.z_plane0 = l * m->n_slots;
+  ga.pf = env_int("WN_PF_BWD", 0);
   ga.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
   // ring 4 x 40 KB | work buffers 2 x 24 KB | wc 2 x 4 KB | RESIDUAL 2 KB
   const size_t smem = 4 * 5 * 8192 + 2 * 3 * 8192 + 2 * 4096 + 2048 + 1024;

@@ -30,7 +30,7 @@ for _ in range(2):
     eng.forward(wav, ids)
     eng.backward()
 torch.cuda.synchronize()
-buf = torch.zeros(32 * 2048, dtype=torch.int64, device="cuda")
+buf = torch.zeros(32 * 2048 + 4 * 1024, dtype=torch.int64, device="cuda")
 L = len(eng.reg.saves)
 if which == "fwd":
     # tracing stays on for the whole forward: every layer overwrites the buffer, the LAST layer that logged wins;
@@ -48,11 +48,21 @@ else:
     eng.backward_phases(L - layer, L - layer + 1)
     torch.cuda.synchronize()
     lib.wn_debug_trace(None, -1)
-ev = buf.cpu().numpy().reshape(32, 2048)
+allbuf = buf.cpu().numpy()
+ev = allbuf[:32 * 2048].reshape(32, 2048)
+cta = allbuf[32 * 2048:].reshape(1024, 4)
+cta = cta[cta[:, 0] > 0]
+if len(cta):
+    g0 = cta[:, 0].min()
+    print("per-CTA wall clock (ns since first CTA start): n=%d" % len(cta))
+    for k in range(0, len(cta), max(1, len(cta) // 40)):
+        print("  cta %4d sm %3d start %7d end %7d" % (k, cta[k, 2], cta[k, 0] - g0, cta[k, 1] - g0))
+    print("  last end %d ns" % (cta[:, 1].max() - g0))
 names = {1: "prod:wait_free", 2: "prod:got_free", 3: "mma:issueA", 4: "mma:issueB", 5: "e1:begin", 14: "e1:in_full",
          6: "e1:v_full", 15: "e1:math_done", 7: "e1:pre_bar", 8: "e1:post_bar", 9: "e2:begin", 10: "e2:acc_full",
          11: "e2:pre_bar", 12: "e2:post_bar", 13: "e2:stored",
-         16: "mma:doneA", 17: "mma:doneB", 18: "e0:begin", 19: "e0:in_full", 20: "e0:done"}
+         16: "mma:doneA", 17: "mma:doneB", 18: "e0:begin", 19: "e0:in_full", 20: "e0:done",
+         30: "k:entry", 31: "k:init_done", 32: "k:role_done", 33: "k:all_done"}
 rows = []
 for w in range(32):
     for x in ev[w]:
@@ -67,7 +77,7 @@ t0 = rows[0][0]
 maxtile = int(os.environ.get("TRACE_TILES", "12"))
 lo = int(os.environ.get("TRACE_FROM", "6"))
 for t, w, c, tile in rows:
-    if lo <= tile < lo + maxtile:
+    if lo <= tile < lo + maxtile or c >= 30:
         print("%9d  w%-2d tile %3d  %s" % (t - t0, w, tile, names.get(c, str(c))))
 # per-event mean period
 last = {}
