@@ -67,6 +67,11 @@ typedef struct wn_model wn_model; /* opaque */
 #define WN_NSTATS 4
 
 int32_t wn_abi_version(void);
+
+/* CRC-32C (Castagnoli) of a HOST buffer, running value in / out (0 to start): the checksum of TensorFlow's
+ * tensor-bundle checkpoint files written / read by lb_wavenet_b200/tfbundle.py (reference ckpt.py:41,54-62 ->
+ * tf.train.Saver) */
+uint32_t wn_crc32c(uint32_t crc, const void* h_data, uint64_t n_bytes);
 const char* wn_last_error(void);
 
 /* ---- model handle + variable registry -------------------------------------------------

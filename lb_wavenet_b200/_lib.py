@@ -32,6 +32,7 @@ _vp, _i32, _i64, _u64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_
 # name -> (restype, argtypes); must list every symbol declared in include/wavenet_b200.h
 SIGNATURES = {
     "wn_abi_version": (_i32, []),
+    "wn_crc32c": (C.c_uint32, [C.c_uint32, _vp, _u64]),
     "wn_last_error": (C.c_char_p, []),
     "wn_model_create": (C.c_int, [C.POINTER(WnArch), _i32, C.POINTER(_vp)]),
     "wn_model_destroy": (None, [_vp]),

@@ -5,11 +5,11 @@ Mirrors reference ckpt.py:13-81: a dict of saveable objects keyed by serial name
 ``n_keep_checkpoints`` (tf.train.Saver max_to_keep, ckpt.py:41-42), restored from
 ``<ckpt_path>-<resume_step>`` after checking that the three files are readable (ckpt.py:70-76).
 
-Container: ``.data-00000-of-00001`` holds the raw little-endian tensor bytes concatenated in
-key-sorted order -- the same payload layout TensorFlow's bundle writer produces; ``.index`` is a
-JSON table {key: dtype, shape, offset, size, crc32} instead of TF's SSTable and ``.meta`` is a
-small JSON stub instead of a MetaGraphDef (writing/reading the real SSTable is the first row of
-DESIGN.md's "next" list).
+Container: TensorFlow's own tensor-bundle format, written and read without TensorFlow by ``tfbundle.py``
+(``.index`` = SSTable of BundleHeaderProto / BundleEntryProto records, ``.data-00000-of-00001`` = raw little-endian
+tensor bytes in key order), so checkpoints interchange with reference-trained ones; ``.meta`` (a MetaGraphDef in the
+reference, of which only the presence is ever checked, ckpt.py:70-76) is a small stub.  Checkpoints written by
+earlier builds of this repository (JSON ``.index``) are still readable.
 """
 from __future__ import annotations
 
@@ -98,19 +98,10 @@ class Checkpoint(object):
         d = os.path.dirname(path_pfx)
         if d:
             os.makedirs(d, exist_ok=True)
-        index, off = {}, 0
-        with open(path_pfx + ".data-00000-of-00001.tmp", "wb") as f:
-            for key in sorted(values):
-                arr = values[key]
-                raw = arr.astype(arr.dtype.newbyteorder("<")).tobytes()
-                f.write(raw)
-                index[key] = dict(dtype=arr.dtype.name, shape=list(arr.shape), offset=off, size=len(raw),
-                                  crc32=zlib.crc32(raw) & 0xFFFFFFFF)
-                off += len(raw)
-        with open(path_pfx + ".index.tmp", "w") as f:
-            json.dump(dict(format="lb-wavenet-b200/1", tensors=index), f)
-        with open(path_pfx + ".meta.tmp", "w") as f:
-            json.dump(dict(format="lb-wavenet-b200/1", note="stub: no TF MetaGraphDef", keys=sorted(index)), f)
+        from . import tfbundle
+        tfbundle.write_bundle(path_pfx, values, suffix=".tmp")
+        with open(path_pfx + ".meta.tmp", "wb") as f:  # presence only (ckpt.py:70-76); not a real MetaGraphDef
+            f.write(b"\x0a\x1c\x0a\x1alb-wavenet-b200 (no graph)")
         for s in SUFFIXES:
             os.replace(path_pfx + "." + s + ".tmp", path_pfx + "." + s)
         # TF 'checkpoint' state file + max_to_keep pruning (ckpt.py:41-42)
@@ -149,7 +140,11 @@ class Checkpoint(object):
 
 
 def read_checkpoint(ckpt_file: str) -> Dict[str, np.ndarray]:
-    """All tensors of a checkpoint prefix, keyed by serial name."""
+    """All tensors of a checkpoint prefix, keyed by serial name (TF tensor bundle, or this repository's first JSON
+    container)."""
+    from . import tfbundle
+    if tfbundle.is_table_file(ckpt_file + ".index"):
+        return tfbundle.read_bundle(ckpt_file)
     with open(ckpt_file + ".index", "r") as f:
         idx = json.load(f)
     out = {}

@@ -89,6 +89,37 @@ extern "C" {
 
 int32_t wn_abi_version(void) { return WN_ABI_VERSION; }
 
+// CRC-32C (Castagnoli, reflected polynomial 0x82F63B78), slicing-by-8: the checksum of TensorFlow's tensor-bundle
+// checkpoint files (lb_wavenet_b200/tfbundle.py).  Host memory; `crc` is the running value (0 to start).
+uint32_t wn_crc32c(uint32_t crc, const void* h_data, uint64_t n) {
+  static uint32_t tbl[8][256];
+  static bool ready = false;
+  if (!ready) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      tbl[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) tbl[t][i] = (tbl[t - 1][i] >> 8) ^ tbl[0][tbl[t - 1][i] & 0xffu];
+    ready = true;
+  }
+  const unsigned char* p = static_cast<const unsigned char*>(h_data);
+  uint32_t c = ~crc;
+  while (n >= 8) {
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = tbl[7][lo & 0xffu] ^ tbl[6][(lo >> 8) & 0xffu] ^ tbl[5][(lo >> 16) & 0xffu] ^ tbl[4][lo >> 24] ^
+        tbl[3][hi & 0xffu] ^ tbl[2][(hi >> 8) & 0xffu] ^ tbl[1][(hi >> 16) & 0xffu] ^ tbl[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = (c >> 8) ^ tbl[0][(c ^ *p++) & 0xffu];
+  return ~c;
+}
+
 const char* wn_last_error(void) { return g_err; }
 
 int wn_model_create(const wn_arch* arch, int32_t n_slots, wn_model** out) {
