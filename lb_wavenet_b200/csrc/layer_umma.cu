@@ -95,13 +95,11 @@ __device__ __forceinline__ void fill_ones(unsigned char* tile, int bytes, int ti
 // ---- weight preparation: K-major B operands -------------------------------------------------------
 // wcT[l][tap][n][r] = (n < D ? SIGNAL : 0.5 * GATE)[tap][r][n % D]  ([2D rows][R], one block per tap)
 // wrT[l][r][d]      = RESIDUAL[d][r]                               ([R rows][D])
-// wdT[l][tap][r][n] = (n < D ? SIGNAL : GATE)[tap][r][n % D]      ([R rows][2D]: data-gradient B operand, GC path)
 // wr [l][d][r]      = RESIDUAL[d][r] (bf16 copy, [D rows][R]: B operand of dz = dx' . RESIDUAL^T)
 // The 0.5 on the GATE half implements sigmoid(g) = 0.5 tanh(0.5 g) + 0.5 without a multiply in the epilogue
 // (bf16(0.5 w) == 0.5 bf16(w)).
 __global__ void k_prep_layer_weights(const float* __restrict__ p, const LayerDesc* __restrict__ layers, int L, int R,
-                                     int D, bf16* __restrict__ wcT, bf16* __restrict__ wrT, bf16* __restrict__ wdT,
-                                     bf16* __restrict__ wr) {
+                                     int D, bf16* __restrict__ wcT, bf16* __restrict__ wrT, bf16* __restrict__ wr) {
   const int l = blockIdx.x;
   const LayerDesc ld = layers[l];
   const int n_wc = 2 * 2 * D * R, n_wr = R * D;
@@ -110,7 +108,6 @@ __global__ void k_prep_layer_weights(const float* __restrict__ p, const LayerDes
     const int n = rem / R, r = rem % R;
     const float v = p[(n < D ? ld.sig : ld.gate) + ((int64_t)tap * R + r) * D + (n % D)];
     wcT[(int64_t)l * n_wc + i] = f2bf(n < D ? v : 0.5f * v);
-    wdT[(int64_t)l * n_wc + ((int64_t)tap * R + r) * 2 * D + n] = f2bf(v);
   }
   for (int i = threadIdx.x; i < n_wr; i += blockDim.x) {
     const int r = i / D, d = i % D;
@@ -118,162 +115,6 @@ __global__ void k_prep_layer_weights(const float* __restrict__ p, const LayerDes
     wrT[(int64_t)l * n_wr + i] = f2bf(v);
     wr[(int64_t)l * n_wr + (int64_t)d * R + r] = f2bf(v);
   }
-}
-
-// =====================================================================================================
-// Global-conditioning forward variant: one CTA per 128-timestep tile (reads the per-id projection table in the
-// gate epilogue, reference tmodel.py:150-154).  The GATE accumulator holds 0.5 * (x . W_gate), see above.
-// =====================================================================================================
-struct LayerFwdUmmaArgs {
-  const float* params;
-  int64_t sig_b, gate_b, res_b;  // -1: no bias
-  const float* gc_tbl;            // this layer's [C1][2D] table or nullptr
-  const int32_t* ids;
-  int T, dil, dil_next, l, C1, last;
-};
-
-template <int R, int D>
-__global__ void __launch_bounds__(128)
-k_layer_fwd_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_xout,
-                 const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_wc,
-                 const __grid_constant__ CUtensorMap map_wr, LayerFwdUmmaArgs a) {
-  constexpr int XB = R * 2, ZB = D * 2;            // bytes per row == swizzle span
-  constexpr int X_TILE = 128 * XB, Z_TILE = 128 * ZB;
-  constexpr int WC_TILE = 2 * D * XB, WR_TILE = R * ZB;
-  static_assert(XB <= 128 && ZB <= 128, "one row must fit one swizzle span");
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* x0 = smem;
-  unsigned char* x1 = x0 + X_TILE;
-  unsigned char* ztile = x1 + X_TILE;
-  unsigned char* otile = x0;  // x[t-dil] is only read by the first MMA, complete before the output tile is written
-  unsigned char* wc0 = ztile + Z_TILE;
-  unsigned char* wc1 = wc0 + WC_TILE;
-  unsigned char* wr = wc1 + WC_TILE;
-  __shared__ __align__(8) uint64_t bar_in, bar_v, bar_r;
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int b = blockIdx.y, t0 = blockIdx.x * 128;
-  constexpr uint32_t NCOL = 2 * D <= 64 ? 64 : (2 * D <= 128 ? 128 : 256);  // acc_r reuses acc_v's columns
-
-  if (tid == 0) {
-    mbar_init(&bar_in, 1);
-    mbar_init(&bar_v, 1);
-    mbar_init(&bar_r, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc(&tmem_base_s, NCOL);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t acc_v = tmem_base_s, acc_r = tmem_base_s;  // second MMA is issued after every thread drained acc_v
-
-  if (tid == 0) {
-    mbar_expect_tx(&bar_in, (uint32_t)(2 * X_TILE + 2 * WC_TILE + (a.last ? 0 : WR_TILE)));
-    tma_load_3d(x0, &map_x, &bar_in, 0, t0, b);                 // x[t - dil]
-    tma_load_3d(x1, &map_x, &bar_in, 0, t0 + a.dil, b);         // x[t]
-    tma_load_2d(wc0, &map_wc, &bar_in, 0, (a.l * 2 + 0) * 2 * D);
-    tma_load_2d(wc1, &map_wc, &bar_in, 0, (a.l * 2 + 1) * 2 * D);
-    if (!a.last) tma_load_2d(wr, &map_wr, &bar_in, 0, a.l * R);
-    mbar_wait(&bar_in, 0);
-    tc_fence_after_sync();
-    const uint32_t idesc = make_idesc_bf16(128, 2 * D);
-#pragma unroll
-    for (int k = 0; k < R / 16; ++k)
-      mma_bf16_ss(acc_v, make_kmajor_desc(smem_u32(x0), XB, k * 32), make_kmajor_desc(smem_u32(wc0), XB, k * 32), idesc, k != 0);
-#pragma unroll
-    for (int k = 0; k < R / 16; ++k)
-      mma_bf16_ss(acc_v, make_kmajor_desc(smem_u32(x1), XB, k * 32), make_kmajor_desc(smem_u32(wc1), XB, k * 32), idesc, true);
-    mma_commit(&bar_v);
-  }
-  // ---- gate: thread <-> row ----
-  const int r = tid, t = t0 + r;
-  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-  const float* gct = nullptr;
-  if (a.gc_tbl != nullptr && t < a.T) {
-    int id = a.ids[(size_t)b * a.T + t];
-    id = min(max(id, 0), a.C1 - 1);
-    gct = a.gc_tbl + (size_t)id * 2 * D;
-  }
-  mbar_wait(&bar_v, 0);
-  tc_fence_after_sync();
-  {
-    uint32_t vs[32], vg[32], pk[16];
-#pragma unroll
-    for (int c0 = 0; c0 < D; c0 += 32) {
-      tmem_ld_32x32b_x32(acc_v + lane_sel + (uint32_t)c0, vs);
-      tmem_ld_32x32b_x32(acc_v + lane_sel + (uint32_t)(D + c0), vg);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float z[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int d = c0 + 2 * j + e;
-          float s = __uint_as_float(vs[2 * j + e]), g = 2.f * __uint_as_float(vg[2 * j + e]);
-          if (a.sig_b >= 0) {
-            s += __ldg(a.params + a.sig_b + d);
-            g += __ldg(a.params + a.gate_b + d);
-          }
-          if (gct != nullptr) {
-            s += __ldg(gct + d);
-            g += __ldg(gct + D + d);
-          }
-          z[e] = tanh_fast(s) * sigmoid_fast(g);
-        }
-        pk[j] = pack2(z[0], z[1]);
-      }
-      row_store<ZB, 64>(ztile, r, c0 * 2, pk);
-    }
-  }
-  fence_proxy_async_smem();
-  tc_fence_before_sync();
-  __syncthreads();
-  if (tid == 0) {
-    tc_fence_after_sync();
-    if (!a.last) {
-      const uint32_t idesc = make_idesc_bf16(128, R);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k)
-        mma_bf16_ss(acc_r, make_kmajor_desc(smem_u32(ztile), ZB, k * 32), make_kmajor_desc(smem_u32(wr), ZB, k * 32), idesc, k != 0);
-      mma_commit(&bar_r);
-    }
-    tma_store_3d(&map_z, ztile, a.l * D, t0, b);
-    tma_store_commit();
-  }
-  if (!a.last) {
-    mbar_wait(&bar_in, 0);  // the TMA-written x[t] tile is visible to this thread's generic loads
-    mbar_wait(&bar_r, 0);
-    tc_fence_after_sync();
-    uint32_t vr[32], xin[16], pk[16];
-#pragma unroll
-    for (int c0 = 0; c0 < R; c0 += 32) {
-      tmem_ld_32x32b_x32(acc_r + lane_sel + (uint32_t)c0, vr);
-      row_load<XB, 64>(x1, r, c0 * 2, xin);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float o0 = __uint_as_float(vr[2 * j]) + __uint_as_float(xin[j] << 16);
-        float o1 = __uint_as_float(vr[2 * j + 1]) + __uint_as_float(xin[j] & 0xffff0000u);
-        if (a.res_b >= 0) {
-          o0 += __ldg(a.params + a.res_b + c0 + 2 * j);
-          o1 += __ldg(a.params + a.res_b + c0 + 2 * j + 1);
-        }
-        pk[j] = pack2(o0, o1);
-      }
-      row_store<XB, 64>(otile, r, c0 * 2, pk);
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tma_store_3d(&map_xout, otile, 0, a.dil_next + t0, b);
-      tma_store_commit();
-    }
-  }
-  if (tid == 0) tma_store_wait_all<0>();
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base_s, NCOL);
 }
 
 // =====================================================================================================
@@ -292,10 +133,13 @@ struct LayerFwdPArgs {
   int T, dil, dil_next, l, last, n_tiles, tiles_per_slot;
   int z_col;  // first column of this layer's block in the z stash
   int pf;     // L2 prefetch distance in tiles beyond the ring (0: off, the default: measured 3-5 % slower with it)
+  const float* gc_tbl;  // global conditioning: this layer's [C1][2D] projection table (tmodel.py:150-154), else nullptr
+  const int32_t* ids;   // [B][T] voice ids
+  int C1;
   long long* trace;
 };
 
-template <int R, int D>
+template <int R, int D, bool GC>
 __global__ void __launch_bounds__(608, 2)
 k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_xout,
                    const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_wc,
@@ -452,6 +296,13 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
     for (int i = g; i < n_my; i += 2) {
       const int s = i % NST, ab = g;
       // ---- gate: z = tanh(v_s + b_s) * sigmoid(v_g + b_g) ----
+      const float* gct = nullptr;  // this row's global-conditioning projections (signal [D] | gate [D])
+      if constexpr (GC) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int b = tile / a.tiles_per_slot, t = (tile % a.tiles_per_slot) * 128 + r;
+        const int id = t < a.T ? min(max(__ldg(a.ids + (size_t)b * a.T + t), 0), a.C1 - 1) : 0;
+        gct = a.gc_tbl + (size_t)id * 2 * D + 16 * half;
+      }
       tr.ev(5, i);
       mbar_wait(&v_full[ab], (uint32_t)(i >> 1) & 1u);
       tr.ev(6, i);
@@ -469,7 +320,14 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const float4 b_s = bs4[2 * p + q], b_g = bg4[2 * p + q];
+          float4 b_s = bs4[2 * p + q], b_g = bg4[2 * p + q];
+          if constexpr (GC) {  // the accumulator's GATE half holds 0.5 * pre-activation: the table's gate half is halved too
+            const float4 c_s = __ldg(reinterpret_cast<const float4*>(gct) + 2 * p + q);
+            const float4 c_g = __ldg(reinterpret_cast<const float4*>(gct + D) + 2 * p + q);
+            b_s.x += c_s.x; b_s.y += c_s.y; b_s.z += c_s.z; b_s.w += c_s.w;
+            b_g.x = fmaf(0.5f, c_g.x, b_g.x); b_g.y = fmaf(0.5f, c_g.y, b_g.y);
+            b_g.z = fmaf(0.5f, c_g.z, b_g.z); b_g.w = fmaf(0.5f, c_g.w, b_g.w);
+          }
           const float z0 = tanh_fast(__uint_as_float(vs[4 * q]) + b_s.x) * fmaf(0.5f, tanh_fast(__uint_as_float(vg[4 * q]) + b_g.x), 0.5f);
           const float z1 = tanh_fast(__uint_as_float(vs[4 * q + 1]) + b_s.y) * fmaf(0.5f, tanh_fast(__uint_as_float(vg[4 * q + 1]) + b_g.y), 0.5f);
           const float z2 = tanh_fast(__uint_as_float(vs[4 * q + 2]) + b_s.z) * fmaf(0.5f, tanh_fast(__uint_as_float(vg[4 * q + 2]) + b_g.z), 0.5f);
@@ -575,132 +433,6 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
 }
 
 // =====================================================================================================
-// Data-gradient kernel of the global-conditioning path (dv comes from the generation-1 gate kernel):
-//   dx_l[t] = dx_{l+1}[t] + dv[t] . W[1]^T + dv[t+dil] . W[0]^T
-// =====================================================================================================
-struct LayerDxPArgs {
-  int dil, l, has_next, n_tiles, tiles_per_slot;
-};
-
-template <int R, int D>
-__global__ void __launch_bounds__(320, 1)
-k_layer_bwd_dx_p_umma(const __grid_constant__ CUtensorMap map_dv, const __grid_constant__ CUtensorMap map_wd,
-                      const __grid_constant__ CUtensorMap map_dxn, const __grid_constant__ CUtensorMap map_dxo,
-                      LayerDxPArgs a) {
-  static_assert(R == 32 && D == 32, "64-byte activation rows");
-  constexpr int XB = 64, VB = 128;
-  constexpr int PANEL = 128 * XB, VT = 128 * VB;
-  constexpr int STAGE = 2 * VT + PANEL;  // dv[t] | dv[t+dil] | dx'
-  constexpr int NST = 4;
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* ot = smem + NST * STAGE;  // [3] output tiles (a store may still be reading two tiles back)
-  unsigned char* wd0 = ot + 3 * PANEL;
-  unsigned char* wd1 = wd0 + R * VB;
-  __shared__ __align__(8) uint64_t w_full, in_full[NST], stage_free[NST], a_full[2], acc_free[2];
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  if (tid == 0) {
-    mbar_init(&w_full, 1);
-    for (int i = 0; i < NST; ++i) {
-      mbar_init(&in_full[i], 1);
-      mbar_init(&stage_free[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 1);
-      mbar_init(&acc_free[i], 256);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc(&tmem_base_s, 64);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tm = tmem_base_s;  // buffer ab at ab*32
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(&w_full, (uint32_t)(2 * R * VB));
-      tma_load_2d(wd0, &map_wd, &w_full, 0, (a.l * 2 + 0) * R);
-      tma_load_2d(wd1, &map_wd, &w_full, 0, (a.l * 2 + 1) * R);
-      for (int i = 0; i < n_my; ++i) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
-        const int s = i % NST;
-        unsigned char* st = smem + s * STAGE;
-        mbar_wait(&stage_free[s], ((uint32_t)(i / NST) & 1u) ^ 1u);
-        mbar_expect_tx(&in_full[s], (uint32_t)(2 * VT + (a.has_next ? PANEL : 0)));
-        tma_load_3d(st, &map_dv, &in_full[s], 0, t0, b);
-        tma_load_3d(st + VT, &map_dv, &in_full[s], 0, t0 + a.dil, b);  // rows >= T: zero fill == truncated gradient
-        if (a.has_next) tma_load_3d(st + 2 * VT, &map_dxn, &in_full[s], 0, t0, b);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(&w_full, 0);
-      const uint32_t idesc = make_idesc_bf16(128, R);
-      for (int i = 0; i < n_my; ++i) {
-        const int s = i % NST, ab = i & 1;
-        const uint32_t st = smem_u32(smem + s * STAGE);
-        mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);
-        mbar_wait(&acc_free[ab], ((uint32_t)(i >> 1) & 1u) ^ 1u);
-        tc_fence_after_sync();
-#pragma unroll
-        for (int k = 0; k < 2 * D / 16; ++k)  // dv[t] . W[1]^T
-          mma_bf16_ss(tm + ab * 32, make_kmajor_desc(st, VB, k * 32), make_kmajor_desc(smem_u32(wd1), VB, k * 32), idesc, k != 0);
-#pragma unroll
-        for (int k = 0; k < 2 * D / 16; ++k)  // dv[t+dil] . W[0]^T
-          mma_bf16_ss(tm + ab * 32, make_kmajor_desc(st + VT, VB, k * 32), make_kmajor_desc(smem_u32(wd0), VB, k * 32), idesc, true);
-        mma_commit(&a_full[ab]);
-      }
-    }
-  } else {
-    const int e = warp - 2, q4 = warp & 3, half = e >> 2;
-    const int r = q4 * 32 + lane, c0 = 16 * half;
-    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    const bool elected = (warp == 2 && lane == 0);
-    auto ebar = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-    for (int i = 0; i < n_my; ++i) {
-      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-      const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
-      const int s = i % NST, ab = i & 1;
-      unsigned char* otile = ot + (i % 3) * PANEL;
-      uint32_t vr[16], xin[8], pk[8];
-      mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);
-      mbar_wait(&a_full[ab], (uint32_t)(i >> 1) & 1u);
-      tc_fence_after_sync();
-      tmem_ld_32x32b_x16(tm + ab * 32 + c0 + lane_sel, vr);
-      if (a.has_next) {
-        row_load<XB, 32>(smem + s * STAGE + 2 * VT, r, 32 * half, xin);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) xin[j] = 0u;
-      }
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      mbar_arrive(&acc_free[ab]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        pk[j] = pack2(__uint_as_float(vr[2 * j]) + __uint_as_float(xin[j] << 16),
-                      __uint_as_float(vr[2 * j + 1]) + __uint_as_float(xin[j] & 0xffff0000u));
-      row_store<XB, 32>(otile, r, 32 * half, pk);
-      fence_proxy_async_smem();
-      if (elected) tma_store_wait_read<1>();  // all stores but the previous tile's have drained: buffer (i+1)%3 is free
-      ebar();
-      if (elected) {
-        tma_store_3d(&map_dxo, otile, 0, t0, b);
-        tma_store_commit();
-        mbar_arrive(&stage_free[s]);
-      }
-    }
-    if (elected) tma_store_wait_all<0>();
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tm, 64);
-}
-
-// =====================================================================================================
 // k_layer_bwd_fused_umma (see the file header).  One CTA per SM, 27 warps:
 //   warp 0        TMA producer (+ L2 prefetch)                  warp 1        MMA issuer
 //   warps 2..17   gate epilogue E1, two alternating groups      warps 18..25  row warps: E0 (dx = Y + P0 merge) and E2 (outputs)
@@ -727,10 +459,14 @@ struct LayerBwdFusedArgs {
   int64_t sig, gate, res, sig_b, gate_b, res_b;
   int dil, dil_next, l, has_next, n_tiles, tiles_per_slot, z_plane0;
   int pf;  // L2 prefetch distance in tiles beyond the ring (0: off)
+  const float* gc_tbl;  // global conditioning: this layer's [C1][2D] projection table, else nullptr
+  float* dgc_tbl;       // its gradient (fp32 atomics)
+  const int32_t* ids;   // [B][T] voice ids
+  int C1, T;
   long long* trace;
 };
 
-template <int R, int D>
+template <int R, int D, bool GC>
 __global__ void __launch_bounds__(864, 1)
 k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz,
                        const __grid_constant__ CUtensorMap map_yn, const __grid_constant__ CUtensorMap map_pn,
@@ -929,6 +665,12 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
       const unsigned char* dzp = smem + s * STAGE + P_DZ * PANEL;
       unsigned char* wbuf = wb + ab * WBUF;
       const uint32_t tb = tm + ab * ACC_STRIDE + lane_sel;
+      int gid = 0;  // this row's voice id (global conditioning)
+      if constexpr (GC) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int b = tile / a.tiles_per_slot, t = (tile % a.tiles_per_slot) * 128 + r;
+        gid = t < a.T ? min(max(__ldg(a.ids + (size_t)b * a.T + t), 0), a.C1 - 1) : 0;
+      }
       tr.ev(5, i);
       mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);  // dz tile (TMA) visible to this thread
       tr.ev(14, i);
@@ -958,7 +700,15 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          const float4 b_s = bs4[2 * p + q], b_g = bg4[2 * p + q];
+          float4 b_s = bs4[2 * p + q], b_g = bg4[2 * p + q];
+          if constexpr (GC) {  // the accumulator's GATE half holds 0.5 * pre-activation: the table's gate half is halved too
+            const float* gct = a.gc_tbl + (size_t)gid * 2 * D + c0;
+            const float4 c_s = __ldg(reinterpret_cast<const float4*>(gct) + q);
+            const float4 c_g = __ldg(reinterpret_cast<const float4*>(gct + D) + q);
+            b_s.x += c_s.x; b_s.y += c_s.y; b_s.z += c_s.z; b_s.w += c_s.w;
+            b_g.x = fmaf(0.5f, c_g.x, b_g.x); b_g.y = fmaf(0.5f, c_g.y, b_g.y);
+            b_g.z = fmaf(0.5f, c_g.z, b_g.z); b_g.w = fmaf(0.5f, c_g.w, b_g.w);
+          }
           const float bsv[4] = {b_s.x, b_s.y, b_s.z, b_s.w}, bgv[4] = {b_g.x, b_g.y, b_g.z, b_g.w};
           float zz[4], ds[4], dg[4];
 #pragma unroll
@@ -976,6 +726,25 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
           pz[2 * q] = pack2(zz[0], zz[1]);  pz[2 * q + 1] = pack2(zz[2], zz[3]);
           pvs[2 * q] = pack2(ds[0], ds[1]); pvs[2 * q + 1] = pack2(ds[2], ds[3]);
           pvg[2 * q] = pack2(dg[0], dg[1]); pvg[2 * q + 1] = pack2(dg[2], dg[3]);
+          if constexpr (GC) {
+            // table gradient: dTbl[id][n] += dv[n] (gate half: dv carries 2x).  A warp is 32 consecutive timesteps of
+            // one slot, ids change only at file junctions: reduce over the warp when it is uniform, else per row
+            const int id0 = __shfl_sync(0xffffffffu, gid, 0);
+            const bool uni = __all_sync(0xffffffffu, gid == id0);
+            float* drow = a.dgc_tbl + (size_t)(uni ? id0 : gid) * 2 * D + c0 + 4 * q;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float vs_ = ds[k], vg_ = 0.5f * dg[k];
+              if (uni) {
+                vs_ = warp_sum(vs_);
+                vg_ = warp_sum(vg_);
+              }
+              if (!uni || lane == 0) {
+                if (vs_ != 0.f) atomicAdd(drow + k, vs_);
+                if (vg_ != 0.f) atomicAdd(drow + D + k, vg_);
+              }
+            }
+          }
         }
         *reinterpret_cast<uint4*>(wbuf + W_Z * PANEL + o[p]) = make_uint4(pz[0], pz[1], pz[2], pz[3]);
         *reinterpret_cast<uint4*>(wbuf + W_DVS * PANEL + o[p]) = make_uint4(pvs[0], pvs[1], pvs[2], pvs[3]);
@@ -1213,7 +982,7 @@ struct LayerMaps {
   const void* model = nullptr;
   int T = -1;
   std::vector<CUtensorMap> x;  // per layer: xfull_l [B][dil+T][R]
-  CUtensorMap z, wc, wr, wd, dv, dx[2], p0[2], dz, wrn;
+  CUtensorMap z, wc, wr, dx[2], p0[2], dz, wrn;
 };
 
 bool umma_layer_supported(const wn_model* m) {
@@ -1237,8 +1006,6 @@ static LayerMaps* get_maps(wn_model* m, unsigned char* ws, int T, int* rc) {
   if ((*rc = map3d(&cache.z, ws + wl.z, LD, (uint64_t)T, B, (uint32_t)D, 128, (int)D * 2))) return nullptr;
   if ((*rc = map2ds(&cache.wc, ws + wl.wcT, R, (uint64_t)m->L * 2 * 2 * D, (uint32_t)R, (uint32_t)(2 * D), (int)R * 2))) return nullptr;
   if ((*rc = map2ds(&cache.wr, ws + wl.wrT, D, (uint64_t)m->L * R, (uint32_t)D, (uint32_t)R, (int)D * 2))) return nullptr;
-  if ((*rc = map2ds(&cache.wd, ws + wl.wdT, 2 * D, (uint64_t)m->L * 2 * R, (uint32_t)(2 * D), (uint32_t)R, (int)D * 4))) return nullptr;
-  if ((*rc = map3d(&cache.dv, ws + wl.dv, 2 * D, (uint64_t)T, B, (uint32_t)(2 * D), 128, (int)D * 4))) return nullptr;
   for (int i = 0; i < 2; ++i) {
     if ((*rc = map3d(&cache.dx[i], ws + wl.dx[i], R, (uint64_t)T, B, (uint32_t)R, 128, (int)R * 2))) return nullptr;
     if ((*rc = map3d(&cache.p0[i], ws + wl.p0[i], R, (uint64_t)T, B, (uint32_t)R, 128, (int)R * 2))) return nullptr;
@@ -1256,7 +1023,7 @@ int launch_prep_layer_umma(wn_model* m, const float* d_params, unsigned char* ws
   const WorkspaceLayout& wl = m->wl;
   k_prep_layer_weights<<<m->L, 256, 0, st>>>(d_params, m->d_layers, m->L, m->a.n_res, m->a.n_dil,
                                              reinterpret_cast<bf16*>(ws + wl.wcT), reinterpret_cast<bf16*>(ws + wl.wrT),
-                                             reinterpret_cast<bf16*>(ws + wl.wdT), reinterpret_cast<bf16*>(ws + wl.wrN));
+                                             reinterpret_cast<bf16*>(ws + wl.wrN));
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
@@ -1272,23 +1039,6 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
   const int C1 = a.n_gc_category + 1;
   const bool last = (l + 1 == m->L);
   const CUtensorMap& mxo = last ? mp->x[l] : mp->x[l + 1];
-  const dim3 grid((T + 127) / 128, m->n_slots);
-  if (a.n_gc_embed > 0) {  // global conditioning: per-tile variant (reads the per-id projection table)
-    LayerFwdUmmaArgs fa;
-    memset(&fa, 0, sizeof(fa));
-    fa.params = d_params;
-    fa.sig_b = ld.sig_b; fa.gate_b = ld.gate_b; fa.res_b = ld.res_b;
-    fa.gc_tbl = reinterpret_cast<const float*>(ws + wl.gc_tbl) + (size_t)l * C1 * 2 * a.n_dil;
-    fa.ids = d_ids;
-    fa.T = T; fa.dil = ld.dil; fa.l = l; fa.C1 = C1;
-    fa.last = last;
-    fa.dil_next = last ? 0 : m->layers[l + 1].dil;
-    const size_t smem = 3 * 128 * 64 + 2 * 64 * 64 + 32 * 64 + 1024;
-    ProfScope ps(PROF_LAYER_FWD, st);
-    k_layer_fwd_umma<32, 32><<<grid, 128, smem, st>>>(mp->x[l], mxo, mp->z, mp->wc, mp->wr, fa);
-    WN_LAUNCH_CHECK();
-    return WN_OK;
-  }
   LayerFwdPArgs pa;
   memset(&pa, 0, sizeof(pa));
   pa.params = d_params;
@@ -1302,39 +1052,27 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
   pa.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
   // stages 5 x 16 KB | z tiles 2 x 8 KB | wc 2 x 4 KB | wr 2 KB
   const size_t smem = 5 * 2 * 8192 + 2 * 8192 + 2 * 4096 + 2048 + 1024;
-  WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_fwd_p_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nblk = persist_grid(std::max(1, std::min(pa.n_tiles, 2 * m->sm_count)));
   ProfScope ps(PROF_LAYER_FWD, st);
-  k_layer_fwd_p_umma<32, 32><<<nblk, 608, smem, st>>>(mp->x[l], mxo, mp->z, mp->wc, mp->wr, pa);
+  if (a.n_gc_embed > 0) {
+    pa.gc_tbl = reinterpret_cast<const float*>(ws + wl.gc_tbl) + (size_t)l * C1 * 2 * a.n_dil;
+    pa.ids = d_ids;
+    pa.C1 = C1;
+    WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_fwd_p_umma<32, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_layer_fwd_p_umma<32, 32, true><<<nblk, 608, smem, st>>>(mp->x[l], mxo, mp->z, mp->wc, mp->wr, pa);
+  } else {
+    WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_fwd_p_umma<32, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_layer_fwd_p_umma<32, 32, false><<<nblk, 608, smem, st>>>(mp->x[l], mxo, mp->z, mp->wc, mp->wr, pa);
+  }
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
 
-// global-conditioning path: dx_out = dxbuf[l & 1], dx_next = dxbuf[(l + 1) & 1]
-int launch_layer_bwd_dx_umma(wn_model* m, unsigned char* ws, int T, int l, cudaStream_t st) {
-  int rc;
-  LayerMaps* mp = get_maps(m, ws, T, &rc);
-  if (!mp) return rc;
-  LayerDxPArgs da;
-  da.dil = m->layers[l].dil;
-  da.l = l;
-  da.has_next = (l + 1 < m->L);
-  da.tiles_per_slot = (T + 127) / 128;
-  da.n_tiles = da.tiles_per_slot * m->n_slots;
-  const size_t smem = 4 * (2 * 16384 + 8192) + 3 * 8192 + 2 * 32 * 128 + 1024;
-  WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_dx_p_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int nblk = persist_grid(std::max(1, std::min(da.n_tiles, m->sm_count)));
-  ProfScope ps(PROF_LAYER_BWD_B, st);
-  k_layer_bwd_dx_p_umma<32, 32><<<nblk, 320, smem, st>>>(mp->dv, mp->wd, mp->dx[(l + 1) & 1], mp->dx[l & 1], da);
-  WN_LAUNCH_CHECK();
-  return WN_OK;
-}
-
-bool umma_bwd_fused_supported(const wn_model* m) { return umma_layer_supported(m) && m->a.n_gc_embed == 0; }
+bool umma_bwd_fused_supported(const wn_model* m) { return umma_layer_supported(m); }
 
 // whole backward of layer l: reads (Y, P0)[(l+1) & 1], writes (Y, P0)[l & 1]; Y lives in dxbuf, P0 in p0buf
-int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned char* ws, int T, int l, float* d_grads,
-                                cudaStream_t st) {
+int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_ids, int T, int l,
+                                float* d_grads, cudaStream_t st) {
   int rc;
   LayerMaps* mp = get_maps(m, ws, T, &rc);
   if (!mp) return rc;
@@ -1355,12 +1093,24 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
   ga.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
   // ring 4 x 40 KB | work buffers 2 x 24 KB | wc 2 x 4 KB | RESIDUAL 2 KB
   const size_t smem = 4 * 5 * 8192 + 2 * 3 * 8192 + 2 * 4096 + 2048 + 1024;
-  WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_umma<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = persist_grid(std::max(1, std::min(ga.n_tiles, m->sm_count)));
   const int nx = (l + 1) & 1, cu = l & 1;
   ProfScope ps(PROF_LAYER_BWD_A, st);
-  k_layer_bwd_fused_umma<32, 32><<<grid, 864, smem, st>>>(mp->x[l], mp->dz, mp->dx[nx], mp->p0[nx], mp->dx[cu], mp->p0[cu],
-                                                         mp->wc, mp->wrn, ga);
+  if (m->a.n_gc_embed > 0) {
+    const int C1 = m->a.n_gc_category + 1;
+    ga.gc_tbl = reinterpret_cast<const float*>(ws + m->wl.gc_tbl) + (size_t)l * C1 * 2 * m->a.n_dil;
+    ga.dgc_tbl = reinterpret_cast<float*>(ws + m->wl.dgc_tbl) + (size_t)l * C1 * 2 * m->a.n_dil;
+    ga.ids = d_ids;
+    ga.C1 = C1;
+    ga.T = T;
+    WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_umma<32, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_layer_bwd_fused_umma<32, 32, true><<<grid, 864, smem, st>>>(mp->x[l], mp->dz, mp->dx[nx], mp->p0[nx], mp->dx[cu],
+                                                                 mp->p0[cu], mp->wc, mp->wrn, ga);
+  } else {
+    WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_umma<32, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_layer_bwd_fused_umma<32, 32, false><<<grid, 864, smem, st>>>(mp->x[l], mp->dz, mp->dx[nx], mp->p0[nx], mp->dx[cu],
+                                                                  mp->p0[cu], mp->wc, mp->wrn, ga);
+  }
   WN_LAUNCH_CHECK();
   return WN_OK;
 }

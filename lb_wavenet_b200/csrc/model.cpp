@@ -74,7 +74,6 @@ const WorkspaceLayout& workspace_layout(wn_model* m, int32_t T) {
   w.w2T = take(Q * P * 2);
   w.wcT = take(L * 2 * 2 * D * R * 2);
   w.wrT = take(L * R * D * 2);
-  w.wdT = take(L * 2 * R * 2 * D * 2);
   w.wrN = take(L * D * R * 2);
   w.total = off;
   m->wl = w;

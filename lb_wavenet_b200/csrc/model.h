@@ -55,7 +55,7 @@ struct WorkspaceLayout {
   int64_t wsCat;      // [L*D][S]   = SKIP_l stacked over layers
   int64_t w1T;        // [P][S]     = POST1^T
   int64_t w2T;        // [Q][P]     = POST2^T
-  int64_t wcT, wrT, wdT, wrN;  // per-layer conv / residual operands of the tcgen05 layer kernels (layer_umma.cu)
+  int64_t wcT, wrT, wrN;     // per-layer conv / residual operands of the tcgen05 layer kernels (layer_umma.cu)
   int64_t total;
   std::vector<int64_t> xfull;  // per layer: [B][dil+T][R] bf16
 };

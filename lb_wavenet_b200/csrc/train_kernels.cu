@@ -55,10 +55,9 @@ bool umma_layer_supported(const wn_model* m);
 int launch_prep_layer_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st);
 int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_ids, int T, int l,
                           cudaStream_t st);
-int launch_layer_bwd_dx_umma(wn_model* m, unsigned char* ws, int T, int l, cudaStream_t st);
 bool umma_bwd_fused_supported(const wn_model* m);
-int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned char* ws, int T, int l, float* d_grads,
-                                cudaStream_t st);
+int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_ids, int T, int l,
+                                float* d_grads, cudaStream_t st);
 bool umma_wgrad_supported(const wn_model* m, int lda, int ldy, int N);
 int launch_wgrad_umma(wn_model* m, const bf16* A, int lda, int a_col0, int M_total, const bf16* Y, int ldy, int N,
                       int64_t rows, float* out, int ldo, int mode, float* grads, cudaStream_t st);
@@ -1202,7 +1201,7 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
     const dim3 grid((T + TM - 1) / TM, d.B);
     if (fused) {
       // gate backward, conv / residual weight + bias gradients and the data gradient in one persistent tcgen05 kernel
-      if ((rc = launch_layer_bwd_fused_umma(m, d_params, ws, T, l, d_grads, st))) return rc;
+      if ((rc = launch_layer_bwd_fused_umma(m, d_params, ws, d_ids, T, l, d_grads, st))) return rc;
       continue;
     }
     {
@@ -1222,9 +1221,7 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
         if ((rc = launch_wgrad(wa, m->sm_count, st))) return rc;
       }
     }
-    if (umma_layer_supported(m)) {
-      if ((rc = launch_layer_bwd_dx_umma(m, ws, T, l, st))) return rc;
-    } else {
+    {
       ProfScope ps(PROF_LAYER_BWD_B, st);
       k_layer_bwd_b<<<grid, NT, sb, st>>>(la);
       WN_LAUNCH_CHECK();

@@ -60,15 +60,11 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
-      printf("mbar_wait timeout: smem barrier 0x%x parity %u block %d thread %d\n", smem_u32(bar), parity, (int)blockIdx.x,
-             (int)threadIdx.x);
-      __trap();
-    }
+    if (++spins > (1u << 24)) __trap();  // (no printf here: its stack frame costs registers in every kernel; see mbar_wait_tag)
   }
 }
 
-// same with a caller tag in the timeout message (which role / which loop index was stuck)
+// debugging variant: same wait with a caller tag in the timeout message (which role / which loop index was stuck)
 __device__ __forceinline__ void mbar_wait_tag(uint64_t* bar, uint32_t parity, const char* tag, int idx) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
