@@ -9,7 +9,7 @@
 
 namespace wn {
 
-constexpr int WN_EMBED_PARTS = 256;
+constexpr int WN_EMBED_PARTS = 512;
 
 struct ParamEntry {
   std::string name;

@@ -109,18 +109,34 @@ __global__ void k_gc_table(const float* __restrict__ p, int64_t off_embed,
 // ======================================================================================
 // PRE gather (one_hot @ PRE == row gather; tmodel.py:53-66,96-100) and SAVE prefix handling
 // ======================================================================================
+// one thread per 8 channels (one 16-byte store); R % 8 == 0 (the registry enforces R % 16 == 0)
 __global__ void k_embed(const float* __restrict__ p, int64_t off_pre, int64_t off_pre_b,
                         const int32_t* __restrict__ wav, bf16* __restrict__ x0, int B, int T, int R,
                         int dil0, int Q) {
+  const int R8 = R >> 3;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)B * T * R) return;
-  const int r = (int)(i % R);
-  const int64_t bt = i / R;
+  if (i >= (int64_t)B * T * R8) return;
+  const int r = (int)(i % R8) * 8;
+  const int64_t bt = i / R8;
   const int t = (int)(bt % T), b = (int)(bt / T);
-  const int code = wav[bt];
-  float v = (code >= 0 && code < Q) ? p[off_pre + (int64_t)code * R + r] : 0.f;  // tf.one_hot OOR -> 0
-  if (off_pre_b >= 0) v += p[off_pre_b + r];
-  x0[((int64_t)b * (dil0 + T) + dil0 + t) * R + r] = f2bf(v);
+  const int code = __ldg(wav + bt);
+  float v[8];
+  if (code >= 0 && code < Q) {  // tf.one_hot: an out-of-range index gives an all-zero row
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + off_pre + (int64_t)code * R + r));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(p + off_pre + (int64_t)code * R + r) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+  }
+  if (off_pre_b >= 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] += __ldg(p + off_pre_b + r + k);
+  }
+  __nv_bfloat162 o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+  *reinterpret_cast<uint4*>(x0 + ((int64_t)b * (dil0 + T) + dil0 + t) * R + r) = *reinterpret_cast<uint4*>(o);
 }
 
 // xfull_l[b][j][:] = SAVE_l[b][j][:]  for j < dil     (the concat of tmodel.py:127)
@@ -731,20 +747,23 @@ __global__ void __launch_bounds__(NT) k_wgrad(WgradArgs a) {
 // gradient is the column sum of the whole table (no per-row atomic on 32 hot addresses).
 __global__ void __launch_bounds__(1024) k_embed_bwd(const bf16* __restrict__ dx0, const bf16* __restrict__ p0, int dil0,
                                                     int T, const int32_t* __restrict__ wav, float* __restrict__ part,
-                                                    int64_t rows, int R, int Q, int64_t rows_per_cta) {
-  extern __shared__ float tbl[];  // [Q + 1][R]
+                                                    int64_t rows, int R, int Q, int64_t rows_per_cta, int ncopy) {
+  extern __shared__ float tbl[];  // [ncopy][Q + 1][R]
   const int nt = blockDim.x;
-  for (int i = threadIdx.x; i < (Q + 1) * R; i += nt) tbl[i] = 0.f;
+  for (int i = threadIdx.x; i < ncopy * (Q + 1) * R; i += nt) tbl[i] = 0.f;
   __syncthreads();
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
   if (R == 32) {
+    // audio codes cluster around mid-scale, so many warps hit the same table rows: NCOPY private copies of the
+    // table (warp w uses copy w % NCOPY) cut the same-address serialisation of the shared-memory atomics
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    float* mine = tbl + (size_t)(wrp % ncopy) * (Q + 1) * 32;
     for (int64_t row = r0 + wrp; row < r1; row += nt / 32) {
       float v = bf2f(dx0[row * 32 + lane]);
       if (p0 != nullptr && (int)(row % T) + dil0 < T) v += bf2f(p0[(row + dil0) * 32 + lane]);
-      int code = wav[row];
+      int code = __ldg(wav + row);
       if (code < 0 || code >= Q) code = Q;
-      atomicAdd(&tbl[code * 32 + lane], v);
+      atomicAdd(&mine[code * 32 + lane], v);
     }
   } else {
     for (int64_t i = r0 * R + threadIdx.x; i < r1 * R; i += nt) {
@@ -759,7 +778,11 @@ __global__ void __launch_bounds__(1024) k_embed_bwd(const bf16* __restrict__ dx0
   }
   __syncthreads();
   float* dst = part + (size_t)blockIdx.x * (Q + 1) * R;  // per-CTA partial table: no global atomics
-  for (int i = threadIdx.x; i < (Q + 1) * R; i += nt) dst[i] = tbl[i];
+  for (int i = threadIdx.x; i < (Q + 1) * R; i += nt) {
+    float sum = 0.f;
+    for (int c = 0; c < ncopy; ++c) sum += tbl[(size_t)c * (Q + 1) * R + i];
+    dst[i] = sum;
+  }
 }
 // grads[PRE] += sum over the partial tables (rows < Q); grads[PRE_BIAS] += column sums over all Q + 1 rows
 __global__ void k_embed_bwd_reduce(const float* __restrict__ part, int n_part, float* grads, int64_t off_pre,
@@ -1029,7 +1052,7 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
   k_save_load<<<dim3(64, d.L), 256, 0, st>>>(reinterpret_cast<const bf16*>(d_save), ws, m->d_layers, d.B, T, d.R);
   WN_LAUNCH_CHECK();
   {
-    const int64_t n = d.rows * d.R;
+    const int64_t n = d.rows * (d.R / 8);
     k_embed<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_params, m->off_pre, m->off_pre_b, d_wav,
                                                          reinterpret_cast<bf16*>(ws + wl.xfull[0]), d.B, T, d.R,
                                                          m->layers[0].dil, d.Q);
@@ -1231,13 +1254,16 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
   ProfScope ps_tail(PROF_EMBED_GC_BWD, st);
   {
     const bf16* dx_next = dxbuf[0];  // gradient wrt the layer-0 input
-    const size_t esm = ((size_t)(d.Q + 1) * d.R) * sizeof(float);
+    const int ncopy = 1;  // (private table copies did not pay: the kernel is load-latency bound, not atomic bound)
+    const size_t esm = (size_t)ncopy * (d.Q + 1) * d.R * sizeof(float);
     if ((rc = set_smem(k_embed_bwd, esm))) return rc;
-    const int nblk = (int)std::min<int64_t>(std::min(m->sm_count, WN_EMBED_PARTS), (d.rows + 1023) / 1024);
+    // two 1024-thread CTAs per SM when the table is small enough: twice the loads in flight
+    const int per_sm = esm <= 96 * 1024 ? 2 : 1;
+    const int nblk = (int)std::min<int64_t>(std::min(per_sm * m->sm_count, WN_EMBED_PARTS), (d.rows + 1023) / 1024);
     const int64_t rpc = (d.rows + nblk - 1) / nblk;
     const bf16* p0 = fused ? reinterpret_cast<const bf16*>(ws + wl.p0[0]) : nullptr;
     float* part = reinterpret_cast<float*>(ws + wl.embed_part);
-    k_embed_bwd<<<nblk, 1024, esm, st>>>(dx_next, p0, m->layers[0].dil, T, d_wav, part, d.rows, d.R, d.Q, rpc);
+    k_embed_bwd<<<nblk, 1024, esm, st>>>(dx_next, p0, m->layers[0].dil, T, d_wav, part, d.rows, d.R, d.Q, rpc, ncopy);
     WN_LAUNCH_CHECK();
     k_embed_bwd_reduce<<<((d.Q + 1) * d.R + 255) / 256, 256, 0, st>>>(part, nblk, d_grads, m->off_pre, m->off_pre_b, d.R, d.Q);
     WN_LAUNCH_CHECK();
