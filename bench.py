@@ -8,6 +8,11 @@ forward + backward + gradient all-reduce + Adam), BASELINE.json configs[1]: clas
 R=D=32, S=P=256, 32 slots per GPU, slice_sz 16384, bf16 operands.  N>1 (torchrun): the B=32*N
 slots are sharded 32 per GPU (weak scaling, BASELINE.json configs[2] at N=8).
 Extra keys: `gen` = batched incremental generation audio samples/s on 1 GPU (256 streams).
+
+Timing: W warm-up steps; 3 untimed steps with CUDA events around EVERY kernel launch (`kernel_shares`); then exactly K
+timed steps bracketed by barrier + synchronize, with live CUDA events only around the launches of the dominant kernel
+(`roofline.achieved`; an event pair costs ~1 us of stream time per launch, ~0.15 ms per step if every launch is timed);
+then K end-to-end steps through WaveNetTrain.train_step with pinned host inputs and the loss read back (`e2e`).
 """
 from __future__ import annotations
 
@@ -148,7 +153,7 @@ def cpu_reference_run(arch, steps, warmup, n_threads=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-gen", action="store_true", help="skip the generation leg")
@@ -216,15 +221,35 @@ def main():
         ctx.barrier()
 
     # ---- device-resident timing: `value` ---------------------------------------------------
+    import ctypes as C
+    cats = ["prep_embed_save", "layer_fwd", "post_fwd_loss", "post_bwd", "layer_bwd", "layer_bwd_data",
+            "wgrad", "pre_gc_bwd", "adam", "gen"]
     for s in range(args.warmup):
         w, i = dev_batches[s % n_batches]
         net.train_step(w, i, opt, want_loss=False)
+    sync_all()
+    # kernel_shares: per-category CUDA-event timing of every launch over 3 extra UNTIMED steps (an event pair costs
+    # ~1 us of stream time per launch, ~0.15 ms per step with ~90 launches: too much to leave inside `value`)
+    n_prof = 3
+    lib.wn_prof_enable(1)
+    for s in range(n_prof):
+        w, i = dev_batches[s % n_batches]
+        net.train_step(w, i, opt, want_loss=False)
+    prof_ms = (C.c_double * 16)()
+    prof_n = (C.c_int64 * 16)()
+    lib.wn_prof_collect(prof_ms, prof_n)
+    lib.wn_prof_enable(0)
+    shares = {c: {"ms_per_step": prof_ms[k] / n_prof, "launches_per_step": prof_n[k] / n_prof}
+              for k, c in enumerate(cats) if prof_n[k] > 0}
+    dom = max(shares, key=lambda c: shares[c]["ms_per_step"]) if shares else None
     sync_all()
     clocks = ClockSampler(ctx.local_rank)
     if rank == 0:
         clocks.start()
     lib.wn_launch_count_reset()
-    lib.wn_prof_enable(1)
+    # the timed region keeps live CUDA events around the launches of the DOMINANT kernel only (roofline.achieved)
+    if dom is not None:
+        lib.wn_prof_enable(1 << (cats.index(dom) + 1))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(args.steps):
@@ -234,10 +259,9 @@ def main():
     sync_all()
     ms_total = e0.elapsed_time(e1)
     launches = int(lib.wn_launch_count_reset())
-    import ctypes as C
-    prof_ms = (C.c_double * 16)()
-    prof_n = (C.c_int64 * 16)()
-    lib.wn_prof_collect(prof_ms, prof_n)
+    dom_ms = (C.c_double * 16)()
+    dom_n = (C.c_int64 * 16)()
+    lib.wn_prof_collect(dom_ms, dom_n)
     lib.wn_prof_enable(0)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -273,13 +297,11 @@ def main():
         dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (category timing from CUDA events on the launch stream) ----
-    # "layer_bwd": the fused per-layer backward kernel (gate backward + weight gradients + data gradient);
-    # "layer_bwd_data" only exists on the global-conditioning path (separate data-gradient kernel)
-    cats = ["prep_embed_save", "layer_fwd", "post_fwd_loss", "post_bwd", "layer_bwd", "layer_bwd_data",
-            "wgrad", "pre_gc_bwd", "adam", "gen"]
-    shares = {c: {"ms_per_step": prof_ms[k] / args.steps, "launches_per_step": prof_n[k] / args.steps}
-              for k, c in enumerate(cats) if prof_n[k] > 0}
+    # ---- roofline of the dominant kernel (its launches were timed live, inside the timed region) ----
+    if dom is not None and dom_n[cats.index(dom)] > 0:
+        k = cats.index(dom)
+        shares[dom] = {"ms_per_step": dom_ms[k] / args.steps, "launches_per_step": dom_n[k] / args.steps,
+                       "timed_in": "timed region (the other categories: %d untimed profiling steps)" % n_prof}
     peaks = {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
@@ -287,7 +309,6 @@ def main():
             mp = json.load(f)
         peaks = {"bf16_tflops": mp.get("bf16_tflops_sustained", mp["bf16_tflops"]), "hbm_gbs": mp["hbm_gbs"],
                  "source": "MEASURED_PEAKS.json (sustained bf16: kernel timed inside a long step)"}
-    dom = max(shares, key=lambda c: shares[c]["ms_per_step"]) if shares else None
     rows = args.slots * T
     flop_by_cat = {
         "post_fwd_loss": post_fwd_flop_per_timestep(arch) * rows,

@@ -190,8 +190,10 @@ int wn_selftest_umma_gemm_tn(const void* d_a, const void* d_b, float* d_c, int32
 
 /* Per-category kernel timing with CUDA events recorded on the launch stream around every kernel
  * launch (bench.py's roofline figures).  Categories: 0 prep/embed/SAVE, 1 layer forward, 2 post-net
- * forward + loss, 3 post-net backward, 4 layer backward (gate), 5 layer backward (data), 6 weight
- * gradients, 7 PRE/GC backward, 8 Adam, 9 generator.  wn_prof_collect synchronises the device,
+ * forward + loss, 3 post-net backward, 4 layer backward (fused kernel; gate backward on the HMMA path), 5 layer
+ * backward data gradient (HMMA path only), 6 weight gradients, 7 PRE/GC backward, 8 Adam, 9 generator.
+ * wn_prof_enable(0) switches the timing off, (1) times every category, (1 << (c + 1)) | ... only the selected
+ * categories (an event pair costs ~1 us of stream time per launch).  wn_prof_collect synchronises the device,
  * writes the summed milliseconds and launch counts of the WN_PROF_NCAT categories to HOST arrays
  * and clears the records. */
 #define WN_PROF_NCAT 16

@@ -132,7 +132,7 @@ struct LayerFwdPArgs {
   int64_t sig_b, gate_b, res_b;
   int T, dil, dil_next, l, last, n_tiles, tiles_per_slot;
   int z_col;  // first column of this layer's block in the z stash
-  int pf;     // L2 prefetch distance in tiles beyond the ring (0: off, the default: measured 3-5 % slower with it)
+  int* tile_ctr;  // [2] dynamic tile scheduler: next-tile counter, finished-CTA counter (zero on entry, reset on exit)
   const float* gc_tbl;  // global conditioning: this layer's [C1][2D] projection table (tmodel.py:150-154), else nullptr
   const int32_t* ids;   // [B][T] voice ids
   int C1;
@@ -160,8 +160,15 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
       z_ready[2], zo_ready[2], xo_ready[NST], zt_free[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[96];   // SIGNAL_BIAS | 0.5 * GATE_BIAS | RESIDUAL_BIAS
+  // Dynamic tile scheduler: the first tile of a CTA is blockIdx.x, further ones come from a global counter (SMs do not
+  // run at the same speed and the second CTA of an SM starts ~1.4 us late: a static split leaves a 4-8 us tail).
+  // tile_s[stage] = tile held by that ring stage, -1 = no more tiles.  The MMA issuer reads it after in_full[stage];
+  // the epilogue groups after v_full (for a sentinel the issuer commits v_full without any MMA); the store warp gets
+  // the tile with the z / x' hand-over and the final count from n_done_s.
+  __shared__ int tile_s[NST], zo_tile[2], xo_tile[NST];
+  __shared__ volatile int n_done_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (tid == 0) n_done_s = 0x7fffffff;
   Tracer tr;
   tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
   tr.ev(30, 0);
@@ -204,29 +211,30 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      const int PF = NST + a.pf;  // L2 prefetch distance (tiles)
       mbar_expect_tx(&w_full, (uint32_t)(2 * 2 * D * XB + (a.last ? 0 : R * XB)));
       tma_load_2d(wc0, &map_wc, &w_full, 0, (a.l * 2 + 0) * 2 * D);
       tma_load_2d(wc1, &map_wc, &w_full, 0, (a.l * 2 + 1) * 2 * D);
       if (!a.last) tma_load_2d(wr, &map_wr, &w_full, 0, a.l * R);
-      auto prefetch = [&](int j) {
-        const int tile = (int)blockIdx.x + j * (int)gridDim.x;
-        const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
-        tma_prefetch_l2_3d(&map_x, 0, t0, b);
-        tma_prefetch_l2_3d(&map_x, 0, t0 + a.dil, b);
-      };
-      for (int j = NST; j < PF && j < n_my; ++j) prefetch(j);
-      for (int i = 0; i < n_my; ++i) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
+      int tile = (int)blockIdx.x, i = 0;
+      for (;; ++i) {
         const int s = i % NST;
-        if (a.pf > 0 && i + PF < n_my) prefetch(i + PF);
         tr.ev(1, i);
         mbar_wait(&stage_free[s], ((uint32_t)(i / NST) & 1u) ^ 1u);
         tr.ev(2, i);
+        if (tile >= a.n_tiles) break;
+        const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
+        tile_s[s] = tile;
         mbar_expect_tx(&in_full[s], (uint32_t)STAGE);
         tma_load_3d(smem + s * STAGE, &map_x, &in_full[s], 0, t0, b);
         tma_load_3d(smem + s * STAGE + PANEL, &map_x, &in_full[s], 0, t0 + a.dil, b);
+        tile = (int)gridDim.x + atomicAdd(a.tile_ctr, 1);  // the next one, fetched while these loads fly
+      }
+      n_done_s = i;
+      for (int k = 0; k < 2; ++k) {  // one sentinel per epilogue group (they alternate tiles)
+        const int j = i + k, s = j % NST;
+        if (k > 0) mbar_wait(&stage_free[s], ((uint32_t)(j / NST) & 1u) ^ 1u);
+        tile_s[s] = -1;
+        mbar_arrive(&in_full[s]);
       }
     }
   } else if (warp == 1) {
@@ -252,22 +260,29 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
         mma_commit(&r_full[ab]);
       };
       // two queues served in whatever order their inputs become ready
-      int n1 = 0, n2 = a.last ? n_my : 0;
+      int n1 = 0, n2 = 0, n_end = 1 << 30;  // n_end: index of the first sentinel
       uint32_t spins = 0;
-      while (n1 < n_my || n2 < n_my) {
+      while (n1 < n_end + 2 || n2 < n_end) {
         bool did = false;
-        if (n2 < n1 && mbar_test_wait(&z_ready[n2 & 1], (uint32_t)(n2 >> 1) & 1u) &&
+        if (a.last) n2 = min(n1, n_end);
+        if (n2 < min(n1, n_end) && mbar_test_wait(&z_ready[n2 & 1], (uint32_t)(n2 >> 1) & 1u) &&
             mbar_test_wait(&r_free[n2 & 1], ((uint32_t)(n2 >> 1) & 1u) ^ 1u)) {
           tc_fence_after_sync();
           tr.ev(4, n2);
           mma2(n2++);
           did = true;
         }
-        if (n1 < n_my && mbar_test_wait(&in_full[n1 % NST], (uint32_t)(n1 / NST) & 1u) &&
+        if (n1 < n_end + 2 && mbar_test_wait(&in_full[n1 % NST], (uint32_t)(n1 / NST) & 1u) &&
             mbar_test_wait(&v_free[n1 & 1], ((uint32_t)(n1 >> 1) & 1u) ^ 1u)) {
           tc_fence_after_sync();
-          tr.ev(3, n1);
-          mma1(n1++);
+          if (tile_s[n1 % NST] < 0) {  // sentinel: wake the owning epilogue group without any MMA
+            if (n_end == (1 << 30)) n_end = n1;
+            mma_commit(&v_full[n1 & 1]);
+            ++n1;
+          } else {
+            tr.ev(3, n1);
+            mma1(n1++);
+          }
           did = true;
         }
         if (did) spins = 0; else if (++spins > (1u << 26)) __trap();
@@ -293,20 +308,21 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
     auto gbar = [&]() {
       if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 2, 256;" ::: "memory");
     };
-    for (int i = g; i < n_my; i += 2) {
+    for (int i = g;; i += 2) {
       const int s = i % NST, ab = g;
       // ---- gate: z = tanh(v_s + b_s) * sigmoid(v_g + b_g) ----
+      tr.ev(5, i);
+      mbar_wait(&v_full[ab], (uint32_t)(i >> 1) & 1u);
+      tr.ev(6, i);
+      const int tile = tile_s[s];  // written before the loads the conv MMA (or the sentinel commit) waited for
+      if (tile < 0) break;
+      tc_fence_after_sync();
       const float* gct = nullptr;  // this row's global-conditioning projections (signal [D] | gate [D])
       if constexpr (GC) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         const int b = tile / a.tiles_per_slot, t = (tile % a.tiles_per_slot) * 128 + r;
         const int id = t < a.T ? min(max(__ldg(a.ids + (size_t)b * a.T + t), 0), a.C1 - 1) : 0;
         gct = a.gc_tbl + (size_t)id * 2 * D + 16 * half;
       }
-      tr.ev(5, i);
-      mbar_wait(&v_full[ab], (uint32_t)(i >> 1) & 1u);
-      tr.ev(6, i);
-      tc_fence_after_sync();
       if (i >= 2) mbar_wait(&zt_free[ab], (uint32_t)((i - 2) >> 1) & 1u);  // z(i-2)'s store has finished reading zt[g]
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
@@ -342,6 +358,8 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
       gbar();
       tr.ev(8, i);
       if (elected) {
+        zo_tile[ab] = tile;  // (the ring stage may have been recycled by the time the store warp gets here: last layer)
+        xo_tile[s] = tile;
         if (!a.last) mbar_arrive(&z_ready[ab]);
         else mbar_arrive(&stage_free[s]);  // last layer: both x tiles were only read by the (completed) conv MMA
         mbar_arrive(&zo_ready[ab]);
@@ -392,12 +410,12 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (prev_kind == 0) mbar_arrive(&zt_free[prev_idx & 1]);
         else mbar_arrive(&stage_free[prev_idx % NST]);
       };
-      int nz = 0, nx = a.last ? n_my : 0;
+      int nz = 0, nx = 0;
       uint32_t spins = 0;
-      while (nz < n_my || nx < n_my) {
+      while (nz < n_done_s || (!a.last && nx < n_done_s)) {  // n_done_s: INT_MAX until the producer has run out of tiles
         bool did = false;
-        if (nz < n_my && mbar_test_wait(&zo_ready[nz & 1], (uint32_t)(nz >> 1) & 1u)) {
-          const int tile = (int)blockIdx.x + nz * (int)gridDim.x;
+        if (nz < n_done_s && mbar_test_wait(&zo_ready[nz & 1], (uint32_t)(nz >> 1) & 1u)) {
+          const int tile = zo_tile[nz & 1];
           const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
           tma_store_3d(&map_z, zt + (nz & 1) * PANEL, a.z_col, t0, b);
           tma_store_commit();
@@ -405,8 +423,10 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
           prev_kind = 0; prev_idx = nz++;
           did = true;
         }
-        if (nx < n_my && nx < nz && mbar_test_wait(&xo_ready[nx % NST], (uint32_t)(nx / NST) & 1u)) {
-          const int tile = (int)blockIdx.x + nx * (int)gridDim.x;
+        // (last layer: no x' tiles at all -- xo_ready never completes a phase, and a parity test on a barrier one is not
+        // following phase by phase gives false positives)
+        if (!a.last && nx < nz && mbar_test_wait(&xo_ready[nx % NST], (uint32_t)(nx / NST) & 1u)) {
+          const int tile = xo_tile[nx % NST];
           const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
           tma_store_3d(&map_xout, smem + (nx % NST) * STAGE, 0, a.dil_next + t0, b);
           tma_store_commit();
@@ -424,6 +444,10 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
   tc_fence_before_sync();
   __syncthreads();
   tr.ev(33, 0);
+  if (tid == 0 && atomicAdd(a.tile_ctr + 1, 1) == (int)gridDim.x - 1) {  // last CTA out re-arms the scheduler
+    a.tile_ctr[0] = 0;
+    a.tile_ctr[1] = 0;
+  }
   if (a.trace != nullptr && tid == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
@@ -1048,7 +1072,7 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
   pa.tiles_per_slot = (T + 127) / 128;
   pa.n_tiles = pa.tiles_per_slot * m->n_slots;
   pa.z_col = l * a.n_dil;
-  pa.pf = env_int("WN_PF_FWD", 0);
+  pa.tile_ctr = reinterpret_cast<int*>(ws + wl.tile_ctr) + 4 * l;
   pa.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
   // stages 5 x 16 KB | z tiles 2 x 8 KB | wc 2 x 4 KB | wr 2 KB
   const size_t smem = 5 * 2 * 8192 + 2 * 8192 + 2 * 4096 + 2048 + 1024;

@@ -67,6 +67,7 @@ const WorkspaceLayout& workspace_layout(wn_model* m, int32_t T) {
   w.gc_tbl = take(gc_elems * 4);
   w.dgc_tbl = take(gc_elems * 4);
   w.skip_bias = take(S * 4);
+  w.tile_ctr = take(L * 4 * 4);
   w.embed_part = take((int64_t)WN_EMBED_PARTS * (Q + 1) * R * 4);
   w.wsT = take(S * L * D * 2);
   w.wsCat = take(L * D * S * 2);

@@ -49,6 +49,7 @@ struct WorkspaceLayout {
   int64_t gc_tbl;     // [L][C+1][2D] fp32 (GC projections incl. nothing else)
   int64_t dgc_tbl;    // same shape, gradient
   int64_t skip_bias;  // [S] fp32, sum over layers of SKIP_BIAS
+  int64_t tile_ctr;   // [L][4] int32: dynamic tile-scheduler counters of the persistent layer kernels (fwd: 0,1; bwd: 2,3)
   int64_t embed_part; // [WN_EMBED_PARTS][Q + 1][R] fp32: per-CTA partial PRE gradients
   // transposed / concatenated bf16 weight copies for the tcgen05 kernels (B operands, N x K K-major)
   int64_t wsT;        // [S][L*D]   = SKIP_l[d][s] at [s][l*D+d]

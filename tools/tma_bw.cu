@@ -4,6 +4,7 @@
 // mode 1: TMA 2-D box {64 x 64 rows} of the same bytes viewed as [rows/2][64], SWIZZLE_128B
 // mode 2: cp.async.bulk (1-D, 8 KB contiguous, no swizzle)
 // mode 3: TMA 3-D box {32 x 256 rows}, SWIZZLE_64B (16 KB per request)
+// mode 4: mode 0 loads plus two 8 KB TMA stores per loaded tile (the forward layer kernel's 1 : 2 read : write mix)
 // Each CTA: one producer thread keeps `nst` tiles in flight, one consumer thread recycles them immediately.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(64) k_stream(const __grid_constant__ CUtensorM
       mbar_wait(&empty[s], ((i / nst) & 1) ^ 1);
       mbar_expect(&full[s], tile_bytes);
       unsigned char* dst = smem + (size_t)s * tile_bytes;
-      if (MODE == 0) {
+      if (MODE == 0 || MODE == 4) {
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(s32(dst)), "l"((uint64_t)&map), "r"(s32(&full[s])), "r"(0), "r"(tile * 128), "r"(0) : "memory");
       } else if (MODE == 3) {
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(s32(dst)), "l"((uint64_t)&map), "r"(s32(&full[s])), "r"(0), "r"(tile * 256), "r"(0) : "memory");
@@ -54,6 +55,14 @@ __global__ void __launch_bounds__(64) k_stream(const __grid_constant__ CUtensorM
     for (int i = 0; i < n_my; ++i) {
       const int s = i % nst;
       mbar_wait(&full[s], (i / nst) & 1);
+      if (MODE == 4) {  // write the tile back twice (second half of the buffer), then recycle the stage
+        const int tile = blockIdx.x + i * gridDim.x;
+        unsigned char* src = smem + (size_t)s * tile_bytes;
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)&map), "r"(s32(src)), "r"(0), "r"((n_tiles + 2 * tile) * 128), "r"(0) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)&map), "r"(s32(src)), "r"(0), "r"((n_tiles + 2 * tile + 1) * 128), "r"(0) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
       mbar_arrive(&empty[s]);
     }
   }
@@ -91,9 +100,11 @@ int main() {
   CK(cudaFuncSetAttribute(k_stream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_stream<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  for (int mode = 0; mode < 4; ++mode) {
+  CK(cudaFuncSetAttribute(k_stream<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  for (int mode = 0; mode < 5; ++mode) {
+    if (mode == 1 || mode == 2 || mode == 3) continue;  // (box shape / bulk-copy variants: no difference, see gpurun_out/tma_bw.txt)
     const int tile_bytes = mode == 3 ? 16384 : 8192;
-    const int n_tiles = (int)(bytes / tile_bytes);
+    const int n_tiles = (int)(bytes / tile_bytes) / (mode == 4 ? 3 : 1);  // mode 4: first third read, rest written
     for (int ctas_per_sm = 1; ctas_per_sm <= 2; ++ctas_per_sm) {
       for (int kb_in_flight : {32, 64, 96, 160}) {
         const int nst = kb_in_flight * 1024 / tile_bytes / ctas_per_sm;
@@ -107,6 +118,7 @@ int main() {
           if (mode == 1) k_stream<1><<<grid, 64, smem>>>(m1, d, n_tiles, nst, tile_bytes);
           if (mode == 2) k_stream<2><<<grid, 64, smem>>>(m0, d, n_tiles, nst, tile_bytes);
           if (mode == 3) k_stream<3><<<grid, 64, smem>>>(m3, d, n_tiles, nst, tile_bytes);
+          if (mode == 4) k_stream<4><<<grid, 64, smem>>>(m0, d, n_tiles, nst, tile_bytes);
           CK(cudaEventRecord(e1));
           CK(cudaEventSynchronize(e1));
           CK(cudaGetLastError());
@@ -114,7 +126,8 @@ int main() {
           CK(cudaEventElapsedTime(&ms, e0, e1));
           if (ms < best) best = ms;
         }
-        printf("mode %d  ctas/sm %d  in-flight %3d KB/SM (nst %2d)  %7.1f GB/s\n", mode, ctas_per_sm, kb_in_flight, nst, bytes / best * 1e-6);
+        printf("mode %d  ctas/sm %d  in-flight %3d KB/SM (nst %2d)  %7.1f GB/s (read + written)\n", mode, ctas_per_sm, kb_in_flight, nst,
+               (mode == 4 ? (double)n_tiles * tile_bytes * 3 : (double)bytes) / best * 1e-6);
       }
     }
   }
