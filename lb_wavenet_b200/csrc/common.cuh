@@ -47,6 +47,22 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// One event pair around a run of launches of the same category (the per-layer loops): events between the launches
+// would serialise them and defeat programmatic dependent launch.  ProfScope(cat) inside the group is a no-op.
+struct ProfGroup {
+  int cat;
+  cudaStream_t st;
+  bool on;
+  ProfGroup(int cat, cudaStream_t st, bool enable = true);
+  ~ProfGroup();
+};
+
+// ---- programmatic dependent launch (sm_90+): the next kernel of the stream may be scheduled while this one drains ----
+// pdl_launch_dependents(): "my dependents may be scheduled now" (they still block in pdl_wait()).
+// pdl_wait(): every prerequisite grid has completed and its memory is visible.  No-ops without the launch attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- optional in-kernel timeline (tools/trace_layer.py): CTA 0's role warps log (event, tile, clock64) ----
 extern int g_trace_layer;       // layer whose launches are traced (-1: all)
 extern long long* g_trace_buf;  // device buffer [32 warps][WN_TRACE_PER_WARP] or nullptr (set by wn_debug_trace)

@@ -132,6 +132,7 @@ struct LayerFwdPArgs {
   int64_t sig_b, gate_b, res_b;
   int T, dil, dil_next, l, last, n_tiles, tiles_per_slot;
   int z_col;  // first column of this layer's block in the z stash
+  int z_plane0, z_skip;  // experiment knobs (WN_EXP_Z)
   int* tile_ctr;  // [2] dynamic tile scheduler: next-tile counter, finished-CTA counter (zero on entry, reset on exit)
   const float* gc_tbl;  // global conditioning: this layer's [C1][2D] projection table (tmodel.py:150-154), else nullptr
   const int32_t* ids;   // [B][T] voice ids
@@ -168,6 +169,7 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
   __shared__ int tile_s[NST], zo_tile[2], xo_tile[NST];
   __shared__ volatile int n_done_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();  // the next layer's CTAs may take this SM's resources as soon as they are released
   if (tid == 0) n_done_s = 0x7fffffff;
   Tracer tr;
   tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
@@ -207,6 +209,9 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tm = tmem_base_s;  // buffer ab: acc_v at ab*128 (64 cols), acc_r at ab*128 + 64 (32 cols)
+  // Programmatic dependent launch: everything above touched only parameters and on-chip state; the previous layer's
+  // activations (and the buffers this kernel overwrites) are safe to use once the prerequisite grid has completed.
+  pdl_wait();
   tr.ev(31, 0);
 
   if (warp == 0) {
@@ -417,7 +422,7 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (nz < n_done_s && mbar_test_wait(&zo_ready[nz & 1], (uint32_t)(nz >> 1) & 1u)) {
           const int tile = zo_tile[nz & 1];
           const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
-          tma_store_3d(&map_z, zt + (nz & 1) * PANEL, a.z_col, t0, b);
+          if (!a.z_skip) tma_store_3d(&map_z, zt + (nz & 1) * PANEL, a.z_col, t0, a.z_plane0 + b);
           tma_store_commit();
           release_prev();
           prev_kind = 0; prev_idx = nz++;
@@ -487,6 +492,7 @@ struct LayerBwdFusedArgs {
   float* dgc_tbl;       // its gradient (fp32 atomics)
   const int32_t* ids;   // [B][T] voice ids
   int C1, T;
+  int seq;  // launch sequence number while tracing (tools/trace_layer.py gaps)
   long long* trace;
 };
 
@@ -522,6 +528,13 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
   __shared__ float red_s[32];                 // RESIDUAL_BIAS gradient partials
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  pdl_launch_dependents();
+  if (a.trace != nullptr && tid == 0) {  // kernel entry (before barrier init / TMEM allocation)
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 3] = (long long)gt;
+    atomicMin(reinterpret_cast<unsigned long long*>(a.trace) + 32 * WN_TRACE_PER_WARP + 4096 + 2 * (a.seq & 63), gt);
+  }
 
   if (tid == 0) {
     mbar_init(&w_full, 1);
@@ -551,6 +564,7 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tm = tmem_base_s;
+  pdl_wait();  // the layer above has finished writing (Y, P0) and reading the buffers this layer overwrites
   Tracer tr;
   tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
   if (a.trace != nullptr && tid == 0) {  // per-CTA wall-clock start / SM id (tools/trace_layer.py)
@@ -817,6 +831,7 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
         }
       }
       asm volatile("bar.sync 5, 512;" ::: "memory");
+      if (a.pf != -1) {
       // dWc row m = tap*R + rr, column n: n < D -> SIGNAL[tap][rr][n], else GATE[tap][rr][n-D]
       for (int idx = et; idx < 64 * 64; idx += NE1) {
         const int m = idx >> 6, n = idx & 63;
@@ -835,6 +850,7 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
           const float val = red_s[et];
           if (val != 0.f) atomicAdd(a.grads + a.res_b + et, val);
         }
+      }
       }
     }
   } else if (warp < 26) {
@@ -968,11 +984,33 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 1] = (long long)gt;
+    atomicMax(reinterpret_cast<unsigned long long*>(a.trace) + 32 * WN_TRACE_PER_WARP + 4096 + 2 * (a.seq & 63) + 1, gt);
   }
   if (warp == 1) tmem_dealloc(tm, 512);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
+// Launch with programmatic stream serialisation: the kernel may be scheduled before its predecessor in the stream has
+// drained (it blocks in pdl_wait()), which hides the ~4 us launch gap between the 60 per-layer launches of a step.
+static bool pdl_enabled() {
+  static const bool on = getenv("WN_DISABLE_PDL") == nullptr;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
 static int map3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
                  int swizzle) {
   const uint64_t dims[3] = {d0, d1, d2};
@@ -1072,6 +1110,10 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
   pa.tiles_per_slot = (T + 127) / 128;
   pa.n_tiles = pa.tiles_per_slot * m->n_slots;
   pa.z_col = l * a.n_dil;
+  const int exp_z = env_int("WN_EXP_Z", 0);
+  pa.z_skip = exp_z == 1;
+  if (exp_z == 2) { pa.z_col = 0; pa.z_plane0 = l * m->n_slots; }
+  const CUtensorMap& mz = exp_z == 2 ? mp->dz : mp->z;
   pa.tile_ctr = reinterpret_cast<int*>(ws + wl.tile_ctr) + 4 * l;
   pa.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
   // stages 5 x 16 KB | z tiles 2 x 8 KB | wc 2 x 4 KB | wr 2 KB
@@ -1083,10 +1125,10 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
     pa.ids = d_ids;
     pa.C1 = C1;
     WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_fwd_p_umma<32, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_layer_fwd_p_umma<32, 32, true><<<nblk, 608, smem, st>>>(mp->x[l], mxo, mp->z, mp->wc, mp->wr, pa);
+    WN_CUDA_CHECK(launch_pdl(k_layer_fwd_p_umma<32, 32, true>, nblk, 608, smem, st, mp->x[l], mxo, mz, mp->wc, mp->wr, pa));
   } else {
     WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_fwd_p_umma<32, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_layer_fwd_p_umma<32, 32, false><<<nblk, 608, smem, st>>>(mp->x[l], mxo, mp->z, mp->wc, mp->wr, pa);
+    WN_CUDA_CHECK(launch_pdl(k_layer_fwd_p_umma<32, 32, false>, nblk, 608, smem, st, mp->x[l], mxo, mz, mp->wc, mp->wr, pa));
   }
   WN_LAUNCH_CHECK();
   return WN_OK;
@@ -1115,6 +1157,8 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
   ga.z_plane0 = l * m->n_slots;
   ga.pf = env_int("WN_PF_BWD", 0);
   ga.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
+  static int trace_seq = 0;
+  if (ga.trace != nullptr) ga.seq = trace_seq++;
   // ring 4 x 40 KB | work buffers 2 x 24 KB | wc 2 x 4 KB | RESIDUAL 2 KB
   const size_t smem = 4 * 5 * 8192 + 2 * 3 * 8192 + 2 * 4096 + 2048 + 1024;
   const int grid = persist_grid(std::max(1, std::min(ga.n_tiles, m->sm_count)));
@@ -1128,12 +1172,12 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
     ga.C1 = C1;
     ga.T = T;
     WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_umma<32, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_layer_bwd_fused_umma<32, 32, true><<<grid, 864, smem, st>>>(mp->x[l], mp->dz, mp->dx[nx], mp->p0[nx], mp->dx[cu],
-                                                                 mp->p0[cu], mp->wc, mp->wrn, ga);
+    WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_umma<32, 32, true>, grid, 864, smem, st, mp->x[l], mp->dz, mp->dx[nx],
+                             mp->p0[nx], mp->dx[cu], mp->p0[cu], mp->wc, mp->wrn, ga));
   } else {
     WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_umma<32, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_layer_bwd_fused_umma<32, 32, false><<<grid, 864, smem, st>>>(mp->x[l], mp->dz, mp->dx[nx], mp->p0[nx], mp->dx[cu],
-                                                                  mp->p0[cu], mp->wc, mp->wrn, ga);
+    WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_umma<32, 32, false>, grid, 864, smem, st, mp->x[l], mp->dz, mp->dx[nx],
+                             mp->p0[nx], mp->dx[cu], mp->p0[cu], mp->wc, mp->wrn, ga));
   }
   WN_LAUNCH_CHECK();
   return WN_OK;

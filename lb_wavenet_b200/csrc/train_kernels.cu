@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "common.cuh"
@@ -38,8 +39,29 @@ static size_t prof_event(cudaStream_t st) {
   return g_prof.used++;
 }
 
-ProfScope::ProfScope(int cat_, cudaStream_t st_) : cat(cat_), st(st_), on((g_prof.mask >> cat_) & 1u) {
+static int g_prof_group_cat = -1;  // category of the open ProfGroup, -1: none
+
+ProfScope::ProfScope(int cat_, cudaStream_t st_)
+    : cat(cat_), st(st_), on(((g_prof.mask >> cat_) & 1u) && g_prof_group_cat != cat_) {
   if (on) g_prof.recs.push_back({cat, prof_event(st), 0, g_launches});
+}
+ProfGroup::ProfGroup(int cat_, cudaStream_t st_, bool enable)
+    : cat(cat_), st(st_), on(enable && ((g_prof.mask >> cat_) & 1u) && g_prof_group_cat < 0) {
+  if (on) {
+    g_prof.recs.push_back({cat, prof_event(st), 0, g_launches});
+    g_prof_group_cat = cat;
+  }
+}
+ProfGroup::~ProfGroup() {
+  if (on) {
+    g_prof_group_cat = -1;
+    for (size_t i = g_prof.recs.size(); i-- > 0;)
+      if (g_prof.recs[i].cat == cat && g_prof.recs[i].e1 == 0) {  // the group's own record (inner scopes of other categories follow it)
+        g_prof.recs[i].e1 = prof_event(st);
+        g_prof.recs[i].launches = g_launches - g_prof.recs[i].launches;
+        break;
+      }
+  }
 }
 ProfScope::~ProfScope() {
   if (on) {
@@ -1065,6 +1087,7 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
   const size_t lsm = layer_fwd_smem(d.R, d.D);
   rc = set_smem(k_layer_fwd, lsm);
   if (rc) return rc;
+  std::unique_ptr<ProfGroup> pg_fwd(new ProfGroup(PROF_LAYER_FWD, st, umma_layer));
   for (int l = 0; l < d.L; ++l) {
     if (umma_layer) {
       if ((rc = launch_layer_fwd_umma(m, d_params, ws, d_ids, T, l, st))) return rc;
@@ -1083,6 +1106,7 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
     k_layer_fwd<<<dim3((T + TM - 1) / TM, d.B), NT, lsm, st>>>(la);
     WN_LAUNCH_CHECK();
   }
+  pg_fwd.reset();
   {
     ProfScope ps(PROF_PREP, st);
     k_save_store<<<dim3(64, d.L), 256, 0, st>>>(reinterpret_cast<bf16*>(d_save), ws, m->d_layers, d.B, T, d.R);
@@ -1209,6 +1233,7 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
   bf16* dxbuf[2] = {reinterpret_cast<bf16*>(ws + wl.dx[0]), reinterpret_cast<bf16*>(ws + wl.dx[1])};
   bf16* dv = reinterpret_cast<bf16*>(ws + wl.dv);
   const bool fused = umma_bwd_fused_supported(m);  // data gradient in split form dx[t] = Y[t] + P0[t + dil]
+  std::unique_ptr<ProfGroup> pg_bwd(new ProfGroup(PROF_LAYER_BWD_A, st, fused));
   for (int l = d.L - 1; l >= 0; --l) {
     const int phase = d.L - l;
     if (phase < phase_begin || phase >= phase_end) continue;
@@ -1253,6 +1278,7 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
       WN_LAUNCH_CHECK();
     }
   }
+  pg_bwd.reset();
   if (phase_end < d.L + 2) return WN_OK;
   ProfScope ps_tail(PROF_EMBED_GC_BWD, st);
   {

@@ -30,7 +30,8 @@ for _ in range(2):
     eng.forward(wav, ids)
     eng.backward()
 torch.cuda.synchronize()
-buf = torch.zeros(32 * 2048 + 4 * 1024, dtype=torch.int64, device="cuda")
+buf = torch.zeros(32 * 2048 + 4 * 1024 + 128, dtype=torch.int64, device="cuda")
+buf[32 * 2048 + 4096::2] = 2 ** 62
 L = len(eng.reg.saves)
 if which == "fwd":
     # tracing stays on for the whole forward: every layer overwrites the buffer, the LAST layer that logged wins;
@@ -45,12 +46,41 @@ else:
     eng.backward_phases(0, L - layer)      # everything above `layer`
     torch.cuda.synchronize()
     lib.wn_debug_trace(buf.data_ptr(), layer)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     eng.backward_phases(L - layer, L - layer + 1)
+    e1.record()
+    torch.cuda.synchronize()
+    print("traced launch, CUDA events: %.1f us" % (1e3 * e0.elapsed_time(e1)))
+    lib.wn_debug_trace(None, -1)
+    # the same layer launched three times back to back without tracing
+    eng.forward(wav, ids)
+    eng.backward_phases(0, L - layer)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    for k in range(3):
+        eng.backward_phases(L - layer, L - layer + 1)
+        ev[k + 1].record()
+    torch.cuda.synchronize()
+    print("untraced x3, CUDA events:", ["%.1f us" % (1e3 * ev[k].elapsed_time(ev[k + 1])) for k in range(3)])
+    # gaps between back-to-back launches (no events in between): whole backward with every layer traced
+    buf2 = torch.zeros_like(buf)
+    buf2[32 * 2048 + 4096::2] = 2 ** 62
+    eng.forward(wav, ids)
+    torch.cuda.synchronize()
+    lib.wn_debug_trace(buf2.data_ptr(), -1)
+    eng.backward()
     torch.cuda.synchronize()
     lib.wn_debug_trace(None, -1)
+    se = buf2[32 * 2048 + 4096:].cpu().numpy().reshape(64, 2)
+    se = se[(se[:, 1] > 0) & (se[:, 0] < 2 ** 62)]
+    se = se[np.argsort(se[:, 0])]
+    print("back-to-back layer launches: body us", np.round((se[:, 1] - se[:, 0]) / 1e3, 1).tolist())
+    print("gap (last CTA end -> next kernel first entry) us", np.round((se[1:, 0] - se[:-1, 1]) / 1e3, 1).tolist())
 allbuf = buf.cpu().numpy()
 ev = allbuf[:32 * 2048].reshape(32, 2048)
-cta = allbuf[32 * 2048:].reshape(1024, 4)
+cta = allbuf[32 * 2048:32 * 2048 + 4096].reshape(1024, 4)
 cta = cta[cta[:, 0] > 0]
 if len(cta):
     g0 = cta[:, 0].min()
@@ -58,6 +88,9 @@ if len(cta):
     for k in range(0, len(cta), max(1, len(cta) // 40)):
         print("  cta %4d sm %3d start %7d end %7d" % (k, cta[k, 2], cta[k, 0] - g0, cta[k, 1] - g0))
     print("  last end %d ns" % (cta[:, 1].max() - g0))
+    if (cta[:, 3] > 0).all():
+        print("  kernel entry -> init done: min %d max %d ns; first entry -> first start %d ns; entry spread %d ns" % (
+            (cta[:, 0] - cta[:, 3]).min(), (cta[:, 0] - cta[:, 3]).max(), g0 - cta[:, 3].min(), cta[:, 3].max() - cta[:, 3].min()))
 names = {1: "prod:wait_free", 2: "prod:got_free", 3: "mma:issueA", 4: "mma:issueB", 5: "e1:begin", 14: "e1:in_full",
          6: "e1:v_full", 15: "e1:math_done", 7: "e1:pre_bar", 8: "e1:post_bar", 9: "e2:begin", 10: "e2:acc_full",
          11: "e2:pre_bar", 12: "e2:post_bar", 13: "e2:stored",
