@@ -55,9 +55,16 @@ def synth_slots(n_slots, T, n_batches, seed, recep_field):
     """Synthetic 16 kHz audio per slot: 3 sinusoids + noise, mu-law encoded by the loader's own
     dealer from in-memory 'files' of length U[2F, 8F], ids from the real slot dealer."""
     from lb_wavenet_b200.data import SlotDealer
+    files = synth_files(max(8, n_slots), seed, recep_field)
+    d = SlotDealer(files, n_slots, T, recep_field, 1, seed, 0, quiet=True)
+    return [d.next_batch()[1:] for _ in range(n_batches)]
+
+
+def synth_files(n_files, seed, recep_field):
+    """In-memory synthetic 'files' (voice id, mu-law codes): lengths U[2F, 8F], 3 sinusoids + noise."""
     rng = np.random.default_rng(seed)
     files = []
-    for i in range(max(8, n_slots)):
+    for i in range(n_files):
         n = int(rng.integers(2 * recep_field, 8 * recep_field))
         t = np.arange(n)
         f = rng.uniform(100, 4000, 3) / 16000.0
@@ -65,8 +72,7 @@ def synth_slots(n_slots, T, n_batches, seed, recep_field):
         x = np.clip(x, -1, 1)
         q = (np.sign(x) * np.log1p(255 * np.abs(x)) / np.log1p(255) + 1) * 0.5 * 255 + 0.5  # mu-law codes
         files.append((int(rng.integers(1, 100)), q.astype(np.int32)))
-    d = SlotDealer(files, n_slots, T, recep_field, 1, seed, 0, quiet=True)
-    return [d.next_batch()[1:] for _ in range(n_batches)]
+    return files
 
 
 class ClockSampler:
@@ -206,10 +212,19 @@ def main():
     net = WaveNetTrain(**arch, batch_sz=B_total, l2_factor=1e-3, add_summary=False, n_keep_checkpoints=1,
                        ckpt_path="/tmp/bench.net", resume_step=0, n_valid_total=1, print_interval=0, dist=ctx,
                        init_seed=0, device=str(dev))
-    net.build()
+    # the reference-facing loop (train.py:133-186,216-240): dataset -> get_op() -> net.build(*ops) -> sess.run stand-in
+    from lb_wavenet_b200 import data as wdata
+    F = net.get_recep_field_sz()
+    dset = wdata.MaskedSliceWav(None, None, 16000, T, 2, 0, 1, B_total, 1, "/tmp/bench.dset", 0,
+                                dist=ctx if world > 1 else None, device=str(dev), random_seed=99)
+    dset.init_sample_catalog(entries=synth_files(max(8, B_total), 4321, F))  # same catalog on every rank
+    dset.set_receptive_field_size(F)
+    dset.build()
+    _, *data_ops = dset.get_op()
+    gv_op, loss_op = net.build(*data_ops)
     net.init_vars()
     opt = AdamOptimizer(1e-3)
-    F = net.get_recep_field_sz()
+    apply_op = opt.apply_gradients(gv_op)
     n_batches = 2
     host_batches = synth_slots(args.slots, T, n_batches, 1234 + rank, F)
     pinned = [(torch.as_tensor(w).pin_memory(), torch.as_tensor(i).pin_memory()) for w, i in host_batches]
@@ -285,11 +300,34 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    direct_ms = float(t.item()) / args.steps
+    # (b) the reference's own loop: net.run([apply_grads_op, loss_op]) pulling from MaskedSliceWav -- the loader thread
+    # deals windows into pinned buffers and copies them on its own stream (double buffered), so the H2D copy of step
+    # i+1 overlaps step i; the loss is still read back (and the host blocked) every step
+    dset.init_vars()  # start the loader thread
+    for s in range(3):
+        net.run([apply_op, loss_op])
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        _, loss = net.run([apply_op, loss_op])
+    e1.record()
+    sync_all()
+    dset._shutdown()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / args.steps
-    clk = clocks.stop() if rank == 0 else None  # sampled over both timed regions
+    clk = clocks.stop() if rank == 0 else None  # sampled over all timed regions
     e2e = {"value": B_total * (T - 1) / (e2e_ms * 1e-3), "unit": "timesteps/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(2 * args.slots * T * 4 * max(world, 1)),
-           "d2h_bytes_per_step": int(8 * _lib.WN_NSTATS * max(world, 1)), "loss": loss}
+           "d2h_bytes_per_step": int(8 * _lib.WN_NSTATS * max(world, 1)), "loss": loss,
+           "api": "MaskedSliceWav.get_op() -> WaveNetTrain.build(*ops) -> net.run([apply_grads_op, loss_op]) (reference "
+                  "train.py:182-240); inputs dealt on the host into pinned buffers, H2D on the loader's copy stream",
+           "direct_train_step_ms": direct_ms,
+           "direct_note": "WaveNetTrain.train_step(pinned host tensors): the same step with the H2D copy serialised on "
+                          "the compute stream"}
 
     if rank != 0:
         ctx.barrier()

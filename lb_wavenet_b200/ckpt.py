@@ -35,9 +35,12 @@ class Variable:
     (a view of the device arena, a host scalar, ...)."""
 
     def __init__(self, name: str, shape, dtype, get: Callable[[], np.ndarray],
-                 set: Callable[[np.ndarray], None], trainable: bool = True):
+                 set: Callable[[np.ndarray], None], trainable: bool = True, optional: bool = False):
         self.name, self.shape, self.dtype = name, tuple(shape), np.dtype(dtype)
         self._get, self._set, self.trainable = get, set, trainable
+        # optional: an extra key beyond the reference's layout (optimiser slots, exact loader state).  Written always,
+        # and simply skipped on restore when a checkpoint (e.g. one trained by the reference) does not have it.
+        self.optional = optional
 
     def numpy(self) -> np.ndarray:
         # (np.ascontiguousarray would turn a 0-d scalar into shape (1,))
@@ -132,11 +135,15 @@ class Checkpoint(object):
                 print("Couldn't find checkpoint file {}".format(fn), file=stderr)
                 raise SystemExit(1)
         tensors = read_checkpoint(ckpt_file)
-        missing = [k for k in self.saveable_objects if k not in tensors]
+        missing = [k for k, v in self.saveable_objects.items() if k not in tensors and not v.optional]
         if missing:
             raise KeyError("checkpoint {} lacks keys: {}".format(ckpt_file, ", ".join(missing[:8])))
+        self.restored_optional = []
         for k, var in self.saveable_objects.items():
-            var.assign(tensors[k])
+            if k in tensors:
+                var.assign(tensors[k])
+                if var.optional:
+                    self.restored_optional.append(k)
 
 
 def read_checkpoint(ckpt_file: str) -> Dict[str, np.ndarray]:

@@ -132,7 +132,6 @@ struct LayerFwdPArgs {
   int64_t sig_b, gate_b, res_b;
   int T, dil, dil_next, l, last, n_tiles, tiles_per_slot;
   int z_col;  // first column of this layer's block in the z stash
-  int z_plane0, z_skip;  // experiment knobs (WN_EXP_Z)
   int* tile_ctr;  // [2] dynamic tile scheduler: next-tile counter, finished-CTA counter (zero on entry, reset on exit)
   const float* gc_tbl;  // global conditioning: this layer's [C1][2D] projection table (tmodel.py:150-154), else nullptr
   const int32_t* ids;   // [B][T] voice ids
@@ -422,7 +421,7 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (nz < n_done_s && mbar_test_wait(&zo_ready[nz & 1], (uint32_t)(nz >> 1) & 1u)) {
           const int tile = zo_tile[nz & 1];
           const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
-          if (!a.z_skip) tma_store_3d(&map_z, zt + (nz & 1) * PANEL, a.z_col, t0, a.z_plane0 + b);
+          tma_store_3d(&map_z, zt + (nz & 1) * PANEL, a.z_col, t0, b);
           tma_store_commit();
           release_prev();
           prev_kind = 0; prev_idx = nz++;
@@ -831,7 +830,6 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
         }
       }
       asm volatile("bar.sync 5, 512;" ::: "memory");
-      if (a.pf != -1) {
       // dWc row m = tap*R + rr, column n: n < D -> SIGNAL[tap][rr][n], else GATE[tap][rr][n-D]
       for (int idx = et; idx < 64 * 64; idx += NE1) {
         const int m = idx >> 6, n = idx & 63;
@@ -850,7 +848,6 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
           const float val = red_s[et];
           if (val != 0.f) atomicAdd(a.grads + a.res_b + et, val);
         }
-      }
       }
     }
   } else if (warp < 26) {
@@ -1110,10 +1107,6 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
   pa.tiles_per_slot = (T + 127) / 128;
   pa.n_tiles = pa.tiles_per_slot * m->n_slots;
   pa.z_col = l * a.n_dil;
-  const int exp_z = env_int("WN_EXP_Z", 0);
-  pa.z_skip = exp_z == 1;
-  if (exp_z == 2) { pa.z_col = 0; pa.z_plane0 = l * m->n_slots; }
-  const CUtensorMap& mz = exp_z == 2 ? mp->dz : mp->z;
   pa.tile_ctr = reinterpret_cast<int*>(ws + wl.tile_ctr) + 4 * l;
   pa.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
   // stages 5 x 16 KB | z tiles 2 x 8 KB | wc 2 x 4 KB | wr 2 KB
@@ -1125,10 +1118,10 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
     pa.ids = d_ids;
     pa.C1 = C1;
     WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_fwd_p_umma<32, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WN_CUDA_CHECK(launch_pdl(k_layer_fwd_p_umma<32, 32, true>, nblk, 608, smem, st, mp->x[l], mxo, mz, mp->wc, mp->wr, pa));
+    WN_CUDA_CHECK(launch_pdl(k_layer_fwd_p_umma<32, 32, true>, nblk, 608, smem, st, mp->x[l], mxo, mp->z, mp->wc, mp->wr, pa));
   } else {
     WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_fwd_p_umma<32, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WN_CUDA_CHECK(launch_pdl(k_layer_fwd_p_umma<32, 32, false>, nblk, 608, smem, st, mp->x[l], mxo, mz, mp->wc, mp->wr, pa));
+    WN_CUDA_CHECK(launch_pdl(k_layer_fwd_p_umma<32, 32, false>, nblk, 608, smem, st, mp->x[l], mxo, mp->z, mp->wc, mp->wr, pa));
   }
   WN_LAUNCH_CHECK();
   return WN_OK;

@@ -109,6 +109,29 @@ class SlotDealer:
                 self._cur_data[slot] = np.asarray(_npy_load(self.catalog[idx][1]))[:n]
             return
 
+    # ---- exact resume (beyond the reference, whose (seed, position) restart re-deals every slot from a fresh file:
+    # data.py:249-250,280-286) -------------------------------------------------------------------------------------
+    def state(self) -> dict:
+        """Everything that determines all future batches, as small int64 arrays: the shared stream's position and, per
+        slot, the current file (catalog index, -1 = none yet), the cursor into it and its pull count."""
+        return {"stream_position": np.array(self._datum_count, np.int64),
+                "slot_file": np.array(self._cur_file, np.int64), "slot_pos": np.array(self._cur_pos, np.int64),
+                "slot_count": np.array(self._slot_count, np.int64)}
+
+    def load_state(self, st: dict, seed: int) -> None:
+        if len(st["slot_file"]) != self.batch_sz:
+            raise ValueError("loader state is for batch_sz {}, not {}".format(len(st["slot_file"]), self.batch_sz))
+        self._datum_count = int(st["stream_position"])
+        self._order = shuffled_repeat_order(len(self.catalog), seed, self._datum_count)
+        for slot in range(self.batch_sz):
+            idx = int(st["slot_file"][slot])
+            self._cur_file[slot], self._cur_pos[slot] = idx, int(st["slot_pos"][slot])
+            self._slot_count[slot] = int(st["slot_count"][slot])
+            self._cur_len[slot] = self._usable_len(idx) if idx >= 0 else 0
+            self._cur_data[slot] = None
+            if idx >= 0 and self.slot_lo <= slot < self.slot_hi:
+                self._cur_data[slot] = np.asarray(_npy_load(self.catalog[idx][1]))[:self._cur_len[slot]]
+
     def next_batch(self, wav_out: Optional[np.ndarray] = None, ids_out: Optional[np.ndarray] = None):
         """Returns (latest_file_read_count, wav[int32 n_local x T], ids[int32 n_local x T])."""
         T, nl = self.slice_sz, self.slot_hi - self.slot_lo
@@ -143,6 +166,7 @@ class Batch:
     wav: object  # int32 [n_local_slots, T] (device tensor when CUDA is present, else numpy)
     ids: object
     mel: object = None
+    state: object = None  # SlotDealer.state() right after this batch was dealt (exact resume)
 
 
 class BatchField:
@@ -217,6 +241,31 @@ class MaskedSliceWav(ckpt.Checkpoint):
                                            lambda: np.array(self.ckpt_position, np.int64),
                                            lambda v: setattr(self, "ckpt_position", int(v)), trainable=False),
         })
+        # optional extra keys: the dealer's exact state after the last CONSUMED batch (the reference's two scalars
+        # restart every slot on a fresh file).  Absent from reference-written checkpoints -> approximate restart.
+        self._exact_state = None
+        n = self.batch_sz
+
+        def getter(key, shape):
+            def get():
+                st = self._exact_state
+                if st is None:  # nothing consumed yet: "no current file" for every slot, stream at ckpt_position
+                    st = {"stream_position": np.array(self.ckpt_position, np.int64),
+                          "slot_file": np.full(n, -1, np.int64), "slot_pos": np.zeros(n, np.int64),
+                          "slot_count": np.full(n, self.ckpt_position, np.int64)}
+                return np.asarray(st[key], np.int64).reshape(shape)
+            return get
+
+        def setter(key):
+            def set_(v):
+                if self._exact_state is None:
+                    self._exact_state = {}
+                self._exact_state[key] = np.array(v, np.int64)
+            return set_
+
+        self.add_saveable_objects({
+            key: ckpt.Variable(key, shape, np.int64, getter(key, shape), setter(key), trainable=False, optional=True)
+            for key, shape in (("stream_position", ()), ("slot_file", (n,)), ("slot_pos", (n,)), ("slot_count", (n,)))})
         self.add_initializable_ops([self._start])
 
     def _start(self):
@@ -226,6 +275,10 @@ class MaskedSliceWav(ckpt.Checkpoint):
         lo, hi = (0, self.batch_sz) if self.dist is None else self.dist.slot_range(self.batch_sz)
         self._dealer = SlotDealer([(e[0], e[1]) for e in self.sample_catalog], self.batch_sz, self.slice_sz,
                                   self.recep_field_sz, self.mel_hop_sz, self.random_seed, self.ckpt_position, lo, hi)
+        st = getattr(self, "_resume_state", None)
+        if st is not None:  # exact resume: restore() found the optional keys
+            self._dealer.load_state(st, self.random_seed)
+            self._resume_state = None
         self._n_local = hi - lo
         self._use_cuda = False
         if self.device is None or str(self.device).startswith("cuda"):
@@ -273,17 +326,18 @@ class MaskedSliceWav(ckpt.Checkpoint):
                     torch = self._torch
                     pw, pi = self._pin[k]
                     cnt, _, _ = self._dealer.next_batch(pw.numpy(), pi.numpy())
+                    st = self._dealer.state()
                     dw, di = self._devbuf[k]
                     with torch.cuda.stream(self._copy_stream):
                         dw.copy_(pw, non_blocking=True)
                         di.copy_(pi, non_blocking=True)
                         ev = torch.cuda.Event()
                         ev.record(self._copy_stream)
-                    self._q.put((cnt, k, ev))
+                    self._q.put((cnt, k, ev, st))
                 else:
                     hw, hi = self._hostbuf[k]
                     cnt, _, _ = self._dealer.next_batch(hw, hi)
-                    self._q.put((cnt, k, None))
+                    self._q.put((cnt, k, None, self._dealer.state()))
         except Exception as e:  # surface loader failures in the consumer
             self._q.put(e)
 
@@ -294,7 +348,8 @@ class MaskedSliceWav(ckpt.Checkpoint):
         item = self._q.get()
         if isinstance(item, Exception):
             raise item
-        cnt, k, ev = item
+        cnt, k, ev, st = item
+        self._exact_state = st
         if self._use_cuda:
             torch = self._torch
             cur = torch.cuda.current_stream(self._dev)
@@ -305,12 +360,12 @@ class MaskedSliceWav(ckpt.Checkpoint):
             cur.wait_event(ev)  # this batch's H2D copy
             self._last_k = k
             dw, di = self._devbuf[k]
-            return Batch(cnt, dw, di)
+            return Batch(cnt, dw, di, None, st)
         if self._last_k is not None:
             self._free.put((self._last_k, None))
         self._last_k = k
         hw, hi = self._hostbuf[k]
-        return Batch(cnt, hw, hi)
+        return Batch(cnt, hw, hi, None, st)
 
     def _shutdown(self):
         if self._worker is not None:
@@ -351,6 +406,12 @@ class MaskedSliceWav(ckpt.Checkpoint):
         return super().save(step)
 
     def restore(self, ckpt_file=None):
+        self._exact_state = None
         super().restore(ckpt_file)
+        keys = ("stream_position", "slot_file", "slot_pos", "slot_count")
+        exact = self._exact_state is not None and all(k in self._exact_state for k in keys)
+        self._resume_state = dict(self._exact_state) if exact else None
+        if not exact:
+            self._exact_state = None
         if self._q is not None:
-            self._start()  # re-initialise the iterators from the restored seed / position
+            self._start()  # re-initialise the iterators from the restored seed / position (or the exact state)

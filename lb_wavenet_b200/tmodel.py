@@ -21,14 +21,19 @@ INT32_MAX = 2 ** 31 - 1
 
 class AdamOptimizer:
     """tf.train.AdamOptimizer(learning_rate) stand-in (reference train.py:178,186): TF defaults
-    beta1=0.9, beta2=0.999, epsilon=1e-8, epsilon-hat update (wn_adam_step).  Slots are not part of
-    the checkpoint, as in the reference (ckpt.py:41 saves only the model's dict)."""
+    beta1=0.9, beta2=0.999, epsilon=1e-8, epsilon-hat update (wn_adam_step).  The reference does not checkpoint the
+    slots (ckpt.py:41 saves only the model's dict) and a resumed run restarts Adam from zero; here they travel as OPTIONAL
+    extra keys with TensorFlow's slot names ('<var>/Adam', '<var>/Adam_1') plus 'optimizer_step', which a
+    reference-trained checkpoint simply lacks."""
 
     def __init__(self, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8):
         self.learning_rate, self.beta1, self.beta2, self.epsilon = learning_rate, beta1, beta2, epsilon
         self.t = 0
 
     def apply_gradients(self, grads_and_vars):
+        net = getattr(grads_and_vars, "net", None)
+        if net is not None:
+            net.bind_optimizer(self)
         return ApplyGradsOp(self, grads_and_vars)
 
 
@@ -124,6 +129,23 @@ class WaveNetTrain(ar.WaveNetArch):
         return ckpt.Variable(name, shape, np.float32,
                              lambda: eng.view(name).detach().cpu().numpy(),
                              lambda v: eng.view(name).copy_(torch.as_tensor(v).to(eng.device)), trainable=True)
+
+    def bind_optimizer(self, opt: "AdamOptimizer"):
+        """Adds the optimiser state to the checkpoint as optional keys (a checkpoint without them restores with zero
+        slots and t = 0, which is what the reference does on every resume)."""
+        eng = self._ensure_engine()
+        torch = eng.torch
+        self._optimizer = opt
+        extra = {}
+        for name, info in eng.reg.params.items():
+            for arena, suffix in ((eng.m, "/Adam"), (eng.v, "/Adam_1")):
+                view = arena[info.offset:info.offset + info.numel].view(info.shape)
+                extra[name + suffix] = ckpt.Variable(
+                    name + suffix, info.shape, np.float32, (lambda v=view: v.detach().cpu().numpy()),
+                    (lambda x, v=view: v.copy_(torch.as_tensor(x).to(eng.device))), trainable=False, optional=True)
+        extra["optimizer_step"] = ckpt.Variable("optimizer_step", (), np.int64, lambda: np.array(opt.t, np.int64),
+                                                lambda x: setattr(opt, "t", int(x)), trainable=False, optional=True)
+        self.add_saveable_objects(extra)
 
     def _register_variables(self):
         """Same get_variable call sequence as the reference graph construction (tmodel.py:292-328)."""
@@ -250,6 +272,8 @@ class WaveNetTrain(ar.WaveNetArch):
         """One optimiser step on a [batch_sz or local slots, slice_sz] batch (host or device tensors).
         Returns the total loss of tmodel.py:261 as a Python float (one 32-byte device->host read)."""
         eng = self._ensure_engine()
+        if getattr(self, "_optimizer", None) is not optimizer:
+            self.bind_optimizer(optimizer)  # its slots become (optional) checkpoint keys
         self.forward_backward(wav, ids)
         optimizer.t += 1
         eng.adam(optimizer.t, optimizer.learning_rate, self.l2_factor, n_valid=self._gstats[1:2],

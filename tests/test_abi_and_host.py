@@ -242,13 +242,60 @@ def test_loader_surface_resume_and_alignment(tmp_path):
     ds2.init_vars()
     ds2.restore()
     assert ds2.random_seed == 5 and ds2.ckpt_position == cnt
-    # resume is approximate by design (data.py:249-250): the file stream restarts at skip(ckpt_position)
+    # our own checkpoints carry the dealer's exact state as optional extra keys: the resumed
+    # stream continues exactly where the consumed one stopped -- every slot mid-file, same file-to-slot dealing
+    assert sorted(ds2.restored_optional) == ["slot_count", "slot_file", "slot_pos", "stream_position"]
+    for _ in range(5):
+        b = ds2.next_batch()
+        rc, rw, ri = next(ref)
+        assert b.file_read_count == rc and np.array_equal(b.wav, rw) and np.array_equal(b.ids, ri)
+    # a checkpoint with only the reference's two scalars (data.py:273-276): the reference's approximate resume, i.e.
+    # the file stream restarts at skip(ckpt_position) and every slot starts a fresh file (data.py:249-250)
+    from lb_wavenet_b200 import tfbundle
+    tfbundle.write_bundle(str(tmp_path / "r.dset-41"), {"random_seed": np.array(5, np.int64),
+                                                         "ckpt_position": np.array(cnt, np.int64)})
+    (tmp_path / "r.dset-41.meta").write_bytes(b"")
+    ds3 = data.MaskedSliceWav(None, str(tmp_path / "cat.tsv"), 16000, 132, 2, 2, 4, 3, 5, str(tmp_path / "r.dset"), 41,
+                              device="cpu")
+    ds3.init_sample_catalog()
+    ds3.set_receptive_field_size(30)
+    ds3.build()
+    ds3.restore()      # before init_vars(), as train.py may do: the start-up honours the restored position
+    ds3.init_vars()
+    assert ds3.restored_optional == []
     ref2 = _ref_batches(cat, 3, 132, 30, 4, 5, cnt)
-    b = ds2.next_batch()
+    b = ds3.next_batch()
     rc, rw, ri = next(ref2)
     assert b.file_read_count == rc and np.array_equal(b.wav, rw)
-    ds._shutdown()
-    ds2._shutdown()
+    for d in (ds, ds2, ds3):
+        d._shutdown()
+
+
+def test_checkpoint_optional_keys(tmp_path):
+    """Optional variables are written, restored when present and skipped (not an error) when a checkpoint lacks them;
+    a missing mandatory key is still an error (reference ckpt.py:65-81 restores exactly its own dict)."""
+    from lb_wavenet_b200 import ckpt
+    store = {"W": np.arange(6, dtype=np.float32).reshape(2, 3), "W/Adam": np.ones((2, 3), np.float32)}
+
+    def var(name, optional):
+        return ckpt.Variable(name, (2, 3), np.float32, lambda: store[name], lambda v: store.__setitem__(name, v.copy()),
+                             optional=optional)
+    c = ckpt.Checkpoint(str(tmp_path / "a.net"), 2, 7)
+    c.add_saveable_objects({"W": var("W", False)})
+    c.save(7)                                    # a "reference" checkpoint: no slot keys
+    c.add_saveable_objects({"W/Adam": var("W/Adam", True)})
+    store["W"] = np.zeros((2, 3), np.float32)
+    c.restore()
+    assert c.restored_optional == [] and store["W"][1, 2] == 5 and store["W/Adam"][0, 0] == 1
+    store["W/Adam"] = np.full((2, 3), 3, np.float32)
+    c.save(8)
+    store["W/Adam"] = np.zeros((2, 3), np.float32)
+    c.restore(str(tmp_path / "a.net-8"))
+    assert c.restored_optional == ["W/Adam"] and store["W/Adam"][1, 1] == 3
+    c2 = ckpt.Checkpoint(str(tmp_path / "a.net"), 2, 8)
+    c2.add_saveable_objects({"W": var("W", False), "V": var("W", False)})
+    with pytest.raises(KeyError):
+        c2.restore()
 
 
 def test_slice_data_cli(tmp_path):

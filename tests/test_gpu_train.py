@@ -199,3 +199,52 @@ def test_adam_step_matches_tf_formula(lib):
     st = eng.read_stats()
     ref_l2 = 0.5 * float((eng.params.double() ** 2 * kindmask.double()).sum())
     assert abs(st["l2"] - ref_l2) <= 1e-6 * max(1.0, ref_l2)
+
+
+@pytest.mark.gpu
+def test_checkpoint_carries_adam_slots_as_optional_keys(lib, tmp_path):
+    """'<var>/Adam', '<var>/Adam_1' and 'optimizer_step' ride along as optional keys; a checkpoint
+    without them (what the reference writes, ckpt.py:41) restores with zero slots, as the reference resumes."""
+    import torch
+    from lb_wavenet_b200 import ckpt, config
+    from lb_wavenet_b200.tmodel import AdamOptimizer, WaveNetTrain
+    import os
+    arch = config.load_arch(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "par",
+                                         "arch_tiny_2x4.json"))
+    B, T = 2, 96
+    rng = np.random.default_rng(3)
+    wav = torch.as_tensor(rng.integers(0, 256, (B, T)).astype(np.int32))
+    ids = torch.ones(B, T, dtype=torch.int32)
+
+    def make(resume):
+        net = WaveNetTrain(**arch, batch_sz=B, l2_factor=0.0, add_summary=False, n_keep_checkpoints=3,
+                           ckpt_path=str(tmp_path / "s.net"), resume_step=resume, n_valid_total=1, print_interval=0,
+                           init_seed=1)
+        gv, _ = net.build()
+        opt = AdamOptimizer(1e-3)
+        opt.apply_gradients(gv)
+        net.init_vars()
+        return net, opt
+    a, oa = make(0)
+    for _ in range(2):
+        a.train_step(wav, ids, oa)
+    a.save(2)
+    keys = ckpt.read_checkpoint(str(tmp_path / "s.net-2"))
+    assert "PRE/Adam" in keys and "PRE/Adam_1" in keys and int(keys["optimizer_step"]) == 2
+    b, ob = make(2)
+    b.restore()
+    assert ob.t == 2 and "optimizer_step" in b.restored_optional
+    assert torch.equal(a.engine.m, b.engine.m) and torch.equal(a.engine.v, b.engine.v)
+    assert torch.equal(a.engine.params, b.engine.params)
+    la, lb = a.train_step(wav, ids, oa), b.train_step(wav, ids, ob)
+    assert abs(la - lb) < 1e-5 * max(1.0, abs(la))
+    # resumed == uninterrupted, up to the run-to-run rounding of the split-K gradient atomics
+    assert torch.allclose(a.engine.params, b.engine.params, rtol=0, atol=2e-5)
+    # a reference-style checkpoint: same tensors minus the optional keys -> slots stay zero, t = 0
+    from lb_wavenet_b200 import tfbundle
+    ref_keys = {k: v for k, v in keys.items() if "/Adam" not in k and k != "optimizer_step"}
+    tfbundle.write_bundle(str(tmp_path / "s.net-5"), ref_keys)
+    (tmp_path / "s.net-5.meta").write_bytes(b"")
+    c, oc = make(5)
+    c.restore()
+    assert oc.t == 0 and c.restored_optional == [] and float(c.engine.m.abs().max()) == 0.0
