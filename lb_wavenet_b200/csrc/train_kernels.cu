@@ -72,6 +72,12 @@ ProfScope::~ProfScope() {
 
 // tcgen05 generation (train_umma.cu)
 bool umma_post_supported(const wn_model* m);
+bool umma_post_chain_supported(const wn_model* m);  // GEMM-chain post-net (n_skip / n_post up to 512)
+int launch_post_fwd_chain_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_wav,
+                               const int32_t* d_ids, int T, double* d_stats, float* d_logits, cudaStream_t st);
+int launch_post_bwd_chain_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, cudaStream_t st);
+int launch_wgrad_umma_cols(wn_model* m, const bf16* A, int lda, int M_total, const bf16* Y, int N_total, int64_t rows,
+                           float* out, int mode, float* grads, cudaStream_t st);
 int launch_prep_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st);
 bool umma_layer_supported(const wn_model* m);
 int launch_prep_layer_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st);
@@ -1055,6 +1061,7 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
   const bool gc = d.G > 0;
 
   const bool umma_post = umma_post_supported(m);
+  const bool umma_chain = !umma_post && umma_post_chain_supported(m);
   const bool umma_layer = umma_layer_supported(m);
   {
   ProfScope ps_prep(PROF_PREP, st);
@@ -1070,7 +1077,7 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
                                                     reinterpret_cast<float*>(ws + wl.gc_tbl));
     WN_LAUNCH_CHECK();
   }
-  if (umma_post && (rc = launch_prep_umma(m, d_params, ws, st))) return rc;
+  if ((umma_post || umma_chain) && (rc = launch_prep_umma(m, d_params, ws, st))) return rc;
   if (umma_layer && (rc = launch_prep_layer_umma(m, d_params, ws, st))) return rc;
   WN_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(double) * 3, st));
   WN_CUDA_CHECK(cudaMemsetAsync(ws + wl.tile_ctr, 0, sizeof(int) * 4 * d.L, st));  // tile schedulers (they also re-arm themselves)
@@ -1113,6 +1120,7 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
     WN_LAUNCH_CHECK();
   }
   if (umma_post) return launch_post_fwd_umma(m, d_params, ws, d_wav, d_ids, T, d_stats, d_logits, st);
+  if (umma_chain) return launch_post_fwd_chain_umma(m, d_params, ws, d_wav, d_ids, T, d_stats, d_logits, st);
   PostArgs pa = make_post_args(m, d, wl, ws, d_params);
   pa.logits_out = d_logits; pa.wav = d_wav; pa.ids = d_ids; pa.stats = d_stats;
   const size_t psm = post_smem(pa.AW, pa.CW);
@@ -1183,6 +1191,8 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
       WN_CUDA_CHECK(cudaMemsetAsync(ws + wl.dgc_tbl, 0, sizeof(float) * (size_t)d.L * d.C1 * 2 * d.D, st));
     if (umma_post_supported(m)) {
       if ((rc = launch_post_bwd_umma(m, ws, T, d_grads, st))) return rc;
+    } else if (umma_post_chain_supported(m)) {
+      if ((rc = launch_post_bwd_chain_umma(m, ws, T, d_grads, st))) return rc;
     } else {
       const size_t psm = post_smem(pa.AW, pa.CW);
       rc = set_smem(k_post_bwd, psm);
@@ -1219,6 +1229,12 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
                                   d_grads, st))) return rc;
       if ((rc = launch_wgrad_umma(m, pa.z, d.LD, 0, d.LD, pa.dskip, d.S, d.S, d.rows, nullptr, d.S, 1, d_grads, st)))
         return rc;
+    } else if (umma_post_chain_supported(m)) {
+      if ((rc = launch_wgrad_umma_cols(m, pa.h2, d.P, d.P, pa.dlogits, d.Q, d.rows, d_grads + m->off_post2, 0, d_grads, st)))
+        return rc;
+      if ((rc = launch_wgrad_umma_cols(m, pa.h1, d.S, d.S, pa.dp1, d.P, d.rows, d_grads + m->off_post1, 0, d_grads, st)))
+        return rc;
+      if ((rc = launch_wgrad_umma_cols(m, pa.z, d.LD, d.LD, pa.dskip, d.S, d.rows, nullptr, 1, d_grads, st))) return rc;
     } else {
       if ((rc = flat(pa.h2, d.P, 0, d.P, pa.dlogits, d.Q, 0, d.Q, d_grads + m->off_post2, d.Q))) return rc;
       if ((rc = flat(pa.h1, d.S, 0, d.S, pa.dp1, d.P, 0, d.P, d_grads + m->off_post1, d.P))) return rc;

@@ -793,6 +793,394 @@ int launch_post_bwd_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, 
 }  // namespace wn
 
 // =====================================================================================================
+// k_gemm_umma: the post-net as a chain of plain tcgen05 GEMMs, for the shapes the fused kernels above do not hold in
+// shared memory / tensor memory at once (n_skip or n_post = 512: the reference's own par/arch*.json all use 512).
+//     out[rows x N] = epilogue( A[rows x K] . B[N x K]^T ),  N processed in chunks of <= 256 columns
+// Persistent, one CTA per SM; work items = (128-row tile, N chunk), chunks innermost so the A tile's re-read hits L2.
+// warp 0 TMA producer (3-stage ring of A [128 x 64] + B [<=256 x 64] K blocks), warp 1 MMA issuer, 8 epilogue warps
+// (thread <-> (row, column half)); two 256-column TMEM accumulators alternate between items, so item j+1's
+// contraction overlaps item j's epilogue.  Epilogues (mode):
+//   0  bf16(relu(acc + bias))                      -> staging tile -> TMA store        (h1, h2: tmodel.py:187-215)
+//   1  bf16(acc * (H > 0))                         -> staging tile -> TMA store        (dp1, dskip)
+//   2  bf16(acc) as per-layer [128 x D] panels     -> TMA stores into the dz planes
+//   3  logits = acc + bias; masked softmax cross entropy, statistics, dlogits          (tmodel.py:228-249)
+// =====================================================================================================
+namespace wn {
+
+constexpr int GEMM_STAGES = 3;
+
+struct GemmUmmaArgs {
+  int64_t rows;
+  int K, N, mode, D;
+  const float* bias;   // modes 0, 3: [N] fp32 or nullptr
+  const bf16* H;       // mode 1: [rows][N] relu outputs (the mask)
+  const int32_t* wav;  // mode 3
+  const int32_t* ids;
+  double* stats;
+  float* logits_out;
+  int T;
+};
+
+__global__ void __launch_bounds__(UPOST_P_THREADS, 1)
+k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+            const __grid_constant__ CUtensorMap map_out, GemmUmmaArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* stage_a = smem;                                   // GEMM_STAGES x 16 KB
+  unsigned char* stage_b = smem + GEMM_STAGES * UA_BYTES;          // GEMM_STAGES x 32 KB
+  unsigned char* otile = stage_b + GEMM_STAGES * UB_BYTES;         // 64 KB staging tile
+  __shared__ __align__(8) uint64_t full_bar[GEMM_STAGES], empty_bar[GEMM_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[512];
+  __shared__ float x_mx[2][128], x_sum[2][128], x_vl[2][128];
+  __shared__ int x_arg[2][128];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = (int)((a.rows + UM - 1) / UM);
+  const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int nchunk = (a.N + 255) / 256, nkb = a.K / UKB;
+  const int box_n = min(256, a.N);  // rows of B one TMA box brings (a partial last chunk is zero filled)
+  for (int i = tid; i < 512; i += UPOST_P_THREADS) bias_s[i] = (a.bias != nullptr && i < a.N) ? a.bias[i] : 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < GEMM_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 256);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_out);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int i = 0; i < n_my; ++i) {
+        const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * UM;
+        for (int c = 0; c < nchunk; ++c)
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int st = it % GEMM_STAGES;
+            mbar_wait(&empty_bar[st], ((uint32_t)(it / GEMM_STAGES) & 1u) ^ 1u);
+            mbar_expect_tx(&full_bar[st], (uint32_t)(UA_BYTES + box_n * 128));
+            tma_load_2d(stage_a + st * UA_BYTES, &map_a, &full_bar[st], kb * UKB, row0);
+            tma_load_2d(stage_b + st * UB_BYTES, &map_b, &full_bar[st], kb * UKB, c * 256);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int it = 0, item = 0;
+      for (int i = 0; i < n_my; ++i)
+        for (int c = 0; c < nchunk; ++c, ++item) {
+          const int buf = item & 1;
+          const int w = min(256, a.N - c * 256);
+          const uint32_t idesc = make_idesc_bf16(UM, (w + 15) & ~15);
+          mbar_wait(&acc_empty[buf], ((uint32_t)(item >> 1) & 1u) ^ 1u);
+          tc_fence_after_sync();
+          const uint32_t acc = tmem_base + (uint32_t)buf * 256;
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int st = it % GEMM_STAGES;
+            mbar_wait(&full_bar[st], (uint32_t)(it / GEMM_STAGES) & 1u);
+            tc_fence_after_sync();
+            const uint32_t sa = smem_u32(stage_a + st * UA_BYTES), sb = smem_u32(stage_b + st * UB_BYTES);
+#pragma unroll
+            for (int k = 0; k < UKB / 16; ++k)
+              mma_bf16_ss(acc, make_kmajor_desc(sa, 128, k * 32), make_kmajor_desc(sb, 128, k * 32), idesc, (kb | k) != 0);
+            mma_commit(&empty_bar[st]);
+          }
+          mma_commit(&acc_full[buf]);
+        }
+    }
+  } else {
+    const int e = warp - 2, q4 = warp & 3, half = e >> 2;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    const bool elected = (warp == 2 && lane == 0);
+    uint32_t v[32];
+    uint32_t pk[16];
+    float acc_x = 0.f, acc_n = 0.f, acc_d = 0.f;
+    int item = 0;
+    for (int i = 0; i < n_my; ++i) {
+      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * UM;
+      const int64_t row = row0 + r;
+      const bool in_range = row < a.rows;
+      for (int c = 0; c < nchunk; ++c, ++item) {
+        const int buf = item & 1;
+        const int n0 = c * 256, w = min(256, a.N - n0);
+        mbar_wait(&acc_full[buf], (uint32_t)(item >> 1) & 1u);
+        tc_fence_after_sync();
+        const uint32_t acc = tmem_base + (uint32_t)buf * 256 + lane_sel;
+        if (a.mode != 3) {
+          if (elected) tma_store_wait_read<0>();  // the previous item's stores have finished reading the staging tile
+          epi_bar_sync256();
+        }
+        if (a.mode == 0 || a.mode == 1) {
+          const int cb = half * (w / 2);
+          for (int c0 = cb; c0 < cb + w / 2; c0 += 32) {
+            tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (a.mode == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                pk[j] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + bias_s[n0 + c0 + 2 * j], 0.f),
+                                    fmaxf(__uint_as_float(v[2 * j + 1]) + bias_s[n0 + c0 + 2 * j + 1], 0.f));
+            } else if (in_range) {
+              mask_pack32(v, a.H + (size_t)row * a.N + n0 + c0, pk);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = 0u;
+            }
+            htile_store32(otile, r, c0, pk);
+          }
+          tc_fence_before_sync();
+          mbar_arrive(&acc_empty[buf]);
+          fence_proxy_async_smem();
+          epi_bar_sync256();
+          if (elected) {
+            for (int kb = 0; kb < w / UKB; ++kb) tma_store_2d(&map_out, otile + kb * UA_BYTES, n0 + kb * UKB, (int)row0);
+            tma_store_commit();
+          }
+        } else if (a.mode == 2) {
+          const int span = 2 * a.D, panel_bytes = UM * span;
+          const int cb = half * 128, ce = min(w, cb + 128);
+          for (int c0 = cb; c0 < ce; c0 += 32) {
+            tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const int col = c0 + 8 * ch;
+              unsigned char* dst = otile + (col / a.D) * panel_bytes + swizzled_offset((uint32_t)r, (uint32_t)((col % a.D) * 2), span);
+              *reinterpret_cast<uint4*>(dst) =
+                  make_uint4(pack_bf16x2(__uint_as_float(v[8 * ch]), __uint_as_float(v[8 * ch + 1])),
+                             pack_bf16x2(__uint_as_float(v[8 * ch + 2]), __uint_as_float(v[8 * ch + 3])),
+                             pack_bf16x2(__uint_as_float(v[8 * ch + 4]), __uint_as_float(v[8 * ch + 5])),
+                             pack_bf16x2(__uint_as_float(v[8 * ch + 6]), __uint_as_float(v[8 * ch + 7])));
+            }
+          }
+          tc_fence_before_sync();
+          mbar_arrive(&acc_empty[buf]);
+          fence_proxy_async_smem();
+          epi_bar_sync256();
+          if (elected) {
+            for (int pn = 0; pn * a.D < w; ++pn)
+              tma_store_3d(&map_out, otile + pn * panel_bytes, 0, (int)row0, n0 / a.D + pn);
+            tma_store_commit();
+          }
+        } else {
+          // ---- mode 3: logits, masked softmax cross entropy, dlogits (N == 256, one chunk per tile) ----
+          const int Q = a.N;
+          const int b = in_range ? (int)(row / a.T) : 0, t = in_range ? (int)(row % a.T) : 0;
+          const bool has_next = in_range && (t + 1 < a.T);
+          const bool valid = has_next && (a.ids[(size_t)b * a.T + t + 1] != 0);  // tmodel.py:232
+          int label = has_next ? a.wav[(size_t)b * a.T + t + 1] : 0;              // tmodel.py:230
+          label = min(max(label, 0), Q - 1);
+          const int cb = half * (Q / 2);
+          float mx = -INFINITY, sum = 0.f, vl = 0.f;
+          int arg = 0;
+          for (int c0 = cb; c0 < cb + Q / 2; c0 += 32) {
+            tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+            tmem_ld_wait();
+            float cm = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = __uint_as_float(v[j]) + bias_s[c0 + j];
+              v[j] = __float_as_uint(x);
+              if (x > mx && x > cm) arg = c0 + j;
+              cm = fmaxf(cm, x);
+              if (c0 + j == label) vl = x;
+              if (a.logits_out != nullptr && in_range) a.logits_out[(size_t)row * Q + c0 + j] = x;
+            }
+            const float nm = fmaxf(mx, cm);
+            float cs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cs += __expf(__uint_as_float(v[j]) - nm);
+            sum = sum * __expf(mx - nm) + cs;
+            mx = nm;
+          }
+          x_mx[half][r] = mx;
+          x_sum[half][r] = sum;
+          x_arg[half][r] = arg;
+          x_vl[half][r] = vl;
+          if (elected) tma_store_wait_read<0>();
+          epi_bar_sync256();
+          const float om = x_mx[half ^ 1][r], os = x_sum[half ^ 1][r];
+          const float M = fmaxf(mx, om);
+          const float tot = sum * __expf(mx - M) + os * __expf(om - M);
+          const float inv = 1.f / tot;
+          for (int c0 = cb; c0 < cb + Q / 2; c0 += 32) {
+            tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float x0 = __uint_as_float(v[2 * j]) + bias_s[c0 + 2 * j];
+              const float x1 = __uint_as_float(v[2 * j + 1]) + bias_s[c0 + 2 * j + 1];
+              const float g0 = __expf(x0 - M) * inv - ((c0 + 2 * j) == label ? 1.f : 0.f);
+              const float g1 = __expf(x1 - M) * inv - ((c0 + 2 * j + 1) == label ? 1.f : 0.f);
+              pk[j] = valid ? pack_bf16x2(g0, g1) : 0u;
+            }
+            htile_store32(otile, r, c0, pk);
+          }
+          tc_fence_before_sync();
+          mbar_arrive(&acc_empty[buf]);
+          fence_proxy_async_smem();
+          epi_bar_sync256();
+          if (elected) {
+            for (int kb = 0; kb < Q / UKB; ++kb) tma_store_2d(&map_out, otile + kb * UA_BYTES, kb * UKB, (int)row0);
+            tma_store_commit();
+          }
+          if (half == 0 && valid) {
+            const int garg = (x_mx[1][r] > x_mx[0][r]) ? x_arg[1][r] : x_arg[0][r];
+            const float gvl = label < Q / 2 ? x_vl[0][r] : x_vl[1][r];
+            acc_x += __logf(tot) + M - gvl;
+            acc_n += 1.f;
+            acc_d += fabsf((float)(label - garg));
+          }
+          epi_bar_sync256();  // the partials of this tile are consumed before the next tile overwrites them
+        }
+      }
+    }
+    if (a.mode == 3) {
+      acc_x = warp_sum(acc_x);
+      acc_n = warp_sum(acc_n);
+      acc_d = warp_sum(acc_d);
+      if (lane == 0 && acc_n != 0.f) {
+        atomicAdd(a.stats + WN_STAT_XENT_SUM, (double)acc_x);
+        atomicAdd(a.stats + WN_STAT_N_VALID, (double)acc_n);
+        atomicAdd(a.stats + WN_STAT_DIFF_SUM, (double)acc_d);
+      }
+    }
+    if (elected) tma_store_wait_all<0>();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// column sums of a bf16 [rows x N] matrix, added to out[N] (bias gradients on the GEMM-chain path)
+__global__ void k_colsum_bf16(const bf16* __restrict__ x, int64_t rows, int N, float* __restrict__ out) {
+  const int c2 = blockIdx.x * blockDim.x + threadIdx.x;  // column pair
+  if (2 * c2 >= N) return;
+  const int64_t r0 = (int64_t)blockIdx.y * ((rows + gridDim.y - 1) / gridDim.y);
+  const int64_t r1 = min(rows, r0 + (rows + gridDim.y - 1) / gridDim.y);
+  float s0 = 0.f, s1 = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    const uint32_t wv = *reinterpret_cast<const uint32_t*>(x + r * N + 2 * c2);
+    s0 += __uint_as_float(wv << 16);
+    s1 += __uint_as_float(wv & 0xffff0000u);
+  }
+  if (s0 != 0.f) atomicAdd(out + 2 * c2, s0);
+  if (s1 != 0.f) atomicAdd(out + 2 * c2 + 1, s1);
+}
+
+// shapes the GEMM chain covers when the fused kernels do not
+bool umma_post_chain_supported(const wn_model* m) {
+  static const bool disabled = getenv("WN_DISABLE_UMMA") != nullptr || getenv("WN_DISABLE_UMMA_CHAIN") != nullptr;
+  const wn_arch& a = m->a;
+  auto ok = [](int n) { return n % 64 == 0 && (n <= 256 || n % 256 == 0) && n <= 512; };
+  return !disabled && ok(a.n_skip) && ok(a.n_post) && a.n_quant == 256 && ((int64_t)m->L * a.n_dil) % 64 == 0 &&
+         (a.n_dil == 16 || a.n_dil == 32 || a.n_dil == 64);
+}
+
+static int launch_gemm_umma(wn_model* m, const void* A, int K, const void* B, int N, void* out, int64_t rows,
+                            GemmUmmaArgs ga, cudaStream_t st) {
+  CUtensorMap ma, mb, mo;
+  int rc;
+  if ((rc = map2d(&ma, A, (uint64_t)K, (uint64_t)rows, UKB, UM))) return rc;
+  if ((rc = map2d(&mb, B, (uint64_t)K, (uint64_t)N, UKB, (uint32_t)std::min(256, N)))) return rc;
+  if (ga.mode == 2) {
+    const uint64_t D = ga.D;
+    const uint64_t dims[3] = {D, (uint64_t)rows, (uint64_t)(N / ga.D)};
+    const uint64_t strides[2] = {D * 2, (uint64_t)rows * D * 2};
+    const uint32_t box[3] = {(uint32_t)D, UM, 1};
+    if ((rc = make_tensor_map_bf16(&mo, out, 3, dims, strides, box, (int)D * 2))) return rc;
+  } else {
+    if ((rc = map2d(&mo, out, (uint64_t)N, (uint64_t)rows, UKB, UM))) return rc;
+  }
+  ga.rows = rows; ga.K = K; ga.N = N;
+  const size_t smem = (size_t)GEMM_STAGES * (UA_BYTES + UB_BYTES) + UH_BYTES + 1024;
+  WN_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_tiles = (int)((rows + UM - 1) / UM);
+  int grid = std::max(1, std::min(n_tiles, m->sm_count));
+  if (const char* e = getenv("WN_PERSIST_GRID")) if (atoi(e) > 0) grid = std::max(1, std::min(grid, atoi(e)));
+  k_gemm_umma<<<grid, UPOST_P_THREADS, smem, st>>>(ma, mb, mo, ga);
+  WN_LAUNCH_CHECK();
+  return WN_OK;
+}
+
+// skip sum + post-net + loss as three GEMMs (h1, h2 are stashed for the backward exactly as the fused kernel does)
+int launch_post_fwd_chain_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_wav,
+                               const int32_t* d_ids, int T, double* d_stats, float* d_logits, cudaStream_t st) {
+  const WorkspaceLayout& wl = m->wl;
+  const wn_arch& a = m->a;
+  const int64_t rows = (int64_t)m->n_slots * T;
+  const int LD = m->L * a.n_dil, S = a.n_skip, P = a.n_post, Q = a.n_quant;
+  ProfScope ps(PROF_POST_FWD, st);
+  GemmUmmaArgs ga;
+  int rc;
+  memset(&ga, 0, sizeof(ga));
+  ga.mode = 0;
+  ga.bias = a.use_bias ? reinterpret_cast<const float*>(ws + wl.skip_bias) : nullptr;
+  if ((rc = launch_gemm_umma(m, ws + wl.z, LD, ws + wl.wsT, S, ws + wl.h1, rows, ga, st))) return rc;
+  ga.bias = a.use_bias ? d_params + m->off_post1_b : nullptr;
+  if ((rc = launch_gemm_umma(m, ws + wl.h1, S, ws + wl.w1T, P, ws + wl.h2, rows, ga, st))) return rc;
+  ga.mode = 3;
+  ga.bias = a.use_bias ? d_params + m->off_post2_b : nullptr;
+  ga.wav = d_wav; ga.ids = d_ids; ga.stats = d_stats; ga.logits_out = d_logits; ga.T = T;
+  return launch_gemm_umma(m, ws + wl.h2, P, ws + wl.w2T, Q, ws + wl.dlogits, rows, ga, st);
+}
+
+// dlogits -> dp1 -> dskip -> dz planes, and the three bias gradients as column sums
+int launch_post_bwd_chain_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, cudaStream_t st) {
+  const WorkspaceLayout& wl = m->wl;
+  const wn_arch& a = m->a;
+  const int64_t rows = (int64_t)m->n_slots * T;
+  const int LD = m->L * a.n_dil, S = a.n_skip, P = a.n_post, Q = a.n_quant;
+  const bf16* wbf = reinterpret_cast<const bf16*>(ws + wl.wbf);
+  int rc;
+  {
+    ProfScope ps(PROF_POST_BWD, st);
+    GemmUmmaArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.mode = 1;
+    ga.H = reinterpret_cast<const bf16*>(ws + wl.h2);
+    if ((rc = launch_gemm_umma(m, ws + wl.dlogits, Q, wbf + m->off_post2, P, ws + wl.dp1, rows, ga, st))) return rc;
+    ga.H = reinterpret_cast<const bf16*>(ws + wl.h1);
+    if ((rc = launch_gemm_umma(m, ws + wl.dp1, P, wbf + m->off_post1, S, ws + wl.dskip, rows, ga, st))) return rc;
+    ga.mode = 2;
+    ga.H = nullptr;
+    ga.D = a.n_dil;
+    if ((rc = launch_gemm_umma(m, ws + wl.dskip, S, ws + wl.wsCat, LD, ws + wl.dz, rows, ga, st))) return rc;
+    if (a.use_bias) {
+      const int ny = (int)std::max<int64_t>(1, std::min<int64_t>(rows / 256, 4 * m->sm_count));
+      auto colsum = [&](const void* x, int N, float* out) {
+        k_colsum_bf16<<<dim3((N / 2 + 127) / 128, ny), 128, 0, st>>>(reinterpret_cast<const bf16*>(x), rows, N, out);
+      };
+      colsum(ws + wl.dlogits, Q, d_grads + m->off_post2_b);
+      WN_LAUNCH_CHECK();
+      colsum(ws + wl.dp1, P, d_grads + m->off_post1_b);
+      WN_LAUNCH_CHECK();
+      colsum(ws + wl.dskip, S, d_grads + m->layers[0].skip_b);
+      WN_LAUNCH_CHECK();
+    }
+  }
+  if (a.use_bias && m->L > 1) {
+    k_bcast_skip_bias_umma<<<(a.n_skip + 127) / 128, 128, 0, st>>>(d_grads, m->d_layers, m->L, a.n_skip);
+    WN_LAUNCH_CHECK();
+  }
+  return WN_OK;
+}
+
+}  // namespace wn
+
+// =====================================================================================================
 // k_wgrad_umma: dW[m][n] += sum_rows A[row][a_col0 + m] * Y[row][n]      (weight gradients, split-K)
 // Both operands are MN-major for the tensor core (the contraction index -- time -- is the slow one in
 // memory), staged by TMA as 64-column SW128 panels.  One CTA owns a 128 x N output tile (N <= 256) in TMEM
@@ -813,6 +1201,7 @@ struct WgradUmmaArgs {
   int mode, D, ldo;
   int M_total, N;
   int a_col0;
+  int out_col0;  // mode 1: first output column (N chunks of a wider gradient)
   int64_t kblocks_total, kblocks_per_cta;
 };
 
@@ -903,7 +1292,7 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         if (m < a.M_total) {
           const float val = stg[rr * lds + c];
           float* dst = a.mode == 0 ? a.out + (size_t)m * a.ldo + c
-                                   : a.grads + a.layers[m / a.D].skip + (size_t)(m % a.D) * a.ldo + c;
+                                   : a.grads + a.layers[m / a.D].skip + (size_t)(m % a.D) * a.ldo + a.out_col0 + c;
           if (val != 0.f) atomicAdd(dst, val);
         }
       }
@@ -915,8 +1304,29 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 }
 
 // A: [rows][lda] bf16 (columns a_col0 .. a_col0 + M_total), Y: [rows][N] bf16 (row pitch ldy)
+static int launch_wgrad_umma_at(wn_model* m, const bf16* A, int lda, int a_col0, int M_total, const bf16* Y, int ldy,
+                                int N, int64_t rows, float* out, int ldo, int mode, float* grads, int out_col0,
+                                cudaStream_t st);
+
 int launch_wgrad_umma(wn_model* m, const bf16* A, int lda, int a_col0, int M_total, const bf16* Y, int ldy, int N,
                       int64_t rows, float* out, int ldo, int mode, float* grads, cudaStream_t st) {
+  return launch_wgrad_umma_at(m, A, lda, a_col0, M_total, Y, ldy, N, rows, out, ldo, mode, grads, 0, st);
+}
+
+// the same for N > 256: one launch per chunk of 256 output columns (Y and the output advance by the chunk)
+int launch_wgrad_umma_cols(wn_model* m, const bf16* A, int lda, int M_total, const bf16* Y, int N_total, int64_t rows,
+                           float* out, int mode, float* grads, cudaStream_t st) {
+  for (int n0 = 0; n0 < N_total; n0 += 256) {
+    const int rc = launch_wgrad_umma_at(m, A, lda, 0, M_total, Y + n0, N_total, std::min(256, N_total - n0), rows,
+                                        out != nullptr ? out + n0 : nullptr, N_total, mode, grads, n0, st);
+    if (rc) return rc;
+  }
+  return WN_OK;
+}
+
+static int launch_wgrad_umma_at(wn_model* m, const bf16* A, int lda, int a_col0, int M_total, const bf16* Y, int ldy,
+                                int N, int64_t rows, float* out, int ldo, int mode, float* grads, int out_col0,
+                                cudaStream_t st) {
   CUtensorMap ma, my;
   int rc;
   if ((rc = map2d(&ma, A, (uint64_t)lda, (uint64_t)rows, 64, WG_BK))) return rc;
@@ -924,7 +1334,7 @@ int launch_wgrad_umma(wn_model* m, const bf16* A, int lda, int a_col0, int M_tot
   WgradUmmaArgs wa;
   memset(&wa, 0, sizeof(wa));
   wa.out = out; wa.layers = m->d_layers; wa.grads = grads; wa.mode = mode; wa.D = m->a.n_dil; wa.ldo = ldo;
-  wa.M_total = M_total; wa.N = N; wa.a_col0 = a_col0;
+  wa.M_total = M_total; wa.N = N; wa.a_col0 = a_col0; wa.out_col0 = out_col0;
   wa.kblocks_total = (rows + WG_BK - 1) / WG_BK;
   const int m_tiles = (M_total + 127) / 128;
   const int sms = std::max(1, m->sm_count);

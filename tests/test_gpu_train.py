@@ -142,12 +142,18 @@ def test_gradients_match_oracle(lib, arch, B, T):
     assert not bad, ("vs fp64 oracle", bad)
 
 
+# CLASSIC_SHALLOW: the fused post-net kernels (n_skip = n_post = 256); SKIP512: the tcgen05 GEMM-chain post-net the
+# reference's own 512-wide architectures take (N chunks of 256, a partial last dz chunk, partial last row tile)
+SKIP512 = dict(util.CLASSIC_SHALLOW, n_block_layers=6, n_skip=512, n_post=512)
+
+
+@pytest.mark.parametrize("arch", [util.CLASSIC_SHALLOW, SKIP512], ids=["fused256", "chain512"])
 @pytest.mark.parametrize("cap", ["1", "3"])
-def test_persistent_kernels_many_tiles_per_cta(lib, cap, monkeypatch):
-    """The persistent layer kernels loop over tiles with multi-stage TMA rings and double-buffered TMEM; with the
+def test_persistent_kernels_many_tiles_per_cta(lib, cap, arch, monkeypatch):
+    """The persistent kernels loop over tiles with multi-stage TMA rings and double-buffered TMEM; with the
     grid capped to 1 / 3 CTAs one CTA walks 16 / 6 tiles (ring and mbarrier phases wrap several times).  Results
     must equal the uncapped run bit for bit (forward) and to fp32-atomic noise (gradients)."""
-    arch, B, T = util.CLASSIC_SHALLOW, 2, 1000
+    B, T = 2, 1000
     a = util.oracle_arch(arch)
     p = util.scaled_params(a, B, 31)
     wav, ids = util.synth_batch(B, T, 3, 32)

@@ -12,12 +12,15 @@ sys.path.insert(0, ROOT)
 from lb_wavenet_b200 import config  # noqa: E402
 from lb_wavenet_b200.engine import TrainEngine  # noqa: E402
 
-arch = config.load_arch(os.path.join(ROOT, "par", "arch_classic_3x10.json"))
-B, T = 32, 16384
+# usage: host_overhead.py [arch.json] [slots] [slice_sz]
+arch = config.load_arch(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "par", "arch_classic_3x10.json"))
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+T = int(sys.argv[3]) if len(sys.argv) > 3 else 16384
 eng = TrainEngine(arch, B)
 rng = np.random.default_rng(0)
 wav = torch.as_tensor(rng.integers(0, 256, (B, T)).astype(np.int32)).cuda()
-ids = torch.ones(B, T, dtype=torch.int32).cuda()
+ids = torch.as_tensor(rng.integers(1, max(2, arch["n_gc_category"]), (B, 1)).astype(np.int32)).cuda().expand(B, T).contiguous()
+print("arch", os.path.basename(sys.argv[1]) if len(sys.argv) > 1 else "classic_3x10", "slots", B, "slice_sz", T)
 for _ in range(3):
     eng.forward(wav, ids)
     eng.backward()
@@ -40,3 +43,6 @@ for rep in range(3):
     print("host enqueue ms: fwd %.3f bwd %.3f adam %.3f | device ms (from idle): fwd %.3f bwd %.3f adam %.3f" % (
         1e3 * (t[1] - t[0]), 1e3 * (t[2] - t[1]), 1e3 * (t[3] - t[2]),
         ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])))
+    if rep == 2:
+        tot = ev[0].elapsed_time(ev[3])
+        print("step %.3f ms -> %.2f M output timesteps/s" % (tot, B * (T - 1) / tot / 1e3))
