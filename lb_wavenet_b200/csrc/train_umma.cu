@@ -668,7 +668,7 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
 
 // ---- host side --------------------------------------------------------------------------------------
 bool umma_post_supported(const wn_model* m) {
-  static const bool disabled = getenv("WN_DISABLE_UMMA") != nullptr;
+  static const bool disabled = getenv("WN_DISABLE_UMMA") != nullptr || getenv("WN_PREFER_CHAIN") != nullptr;
   const wn_arch& a = m->a;
   return !disabled && a.n_skip % 64 == 0 && a.n_post % 64 == 0 && a.n_skip <= 256 && a.n_post <= 256 &&
          a.n_quant == 256 && (a.n_dil == 16 || a.n_dil == 32 || a.n_dil == 64);
@@ -949,7 +949,8 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             tma_store_commit();
           }
         } else if (a.mode == 2) {
-          const int span = 2 * a.D, panel_bytes = UM * span;
+          // panels of PW = min(D, 64) columns (one swizzle span per row); a plane wider than 64 columns is two panels
+          const int PW = min(a.D, 64), span = 2 * PW, panel_bytes = UM * span;
           const int cb = half * 128, ce = min(w, cb + 128);
           for (int c0 = cb; c0 < ce; c0 += 32) {
             tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
@@ -957,7 +958,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
               const int col = c0 + 8 * ch;
-              unsigned char* dst = otile + (col / a.D) * panel_bytes + swizzled_offset((uint32_t)r, (uint32_t)((col % a.D) * 2), span);
+              unsigned char* dst = otile + (col / PW) * panel_bytes + swizzled_offset((uint32_t)r, (uint32_t)((col % PW) * 2), span);
               *reinterpret_cast<uint4*>(dst) =
                   make_uint4(pack_bf16x2(__uint_as_float(v[8 * ch]), __uint_as_float(v[8 * ch + 1])),
                              pack_bf16x2(__uint_as_float(v[8 * ch + 2]), __uint_as_float(v[8 * ch + 3])),
@@ -970,8 +971,10 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           fence_proxy_async_smem();
           epi_bar_sync256();
           if (elected) {
-            for (int pn = 0; pn * a.D < w; ++pn)
-              tma_store_3d(&map_out, otile + pn * panel_bytes, 0, (int)row0, n0 / a.D + pn);
+            for (int pn = 0; pn * PW < w; ++pn) {
+              const int col = n0 + pn * PW;
+              tma_store_3d(&map_out, otile + pn * panel_bytes, col % a.D, (int)row0, col / a.D);
+            }
             tma_store_commit();
           }
         } else {
@@ -1086,7 +1089,7 @@ bool umma_post_chain_supported(const wn_model* m) {
   const wn_arch& a = m->a;
   auto ok = [](int n) { return n % 64 == 0 && (n <= 256 || n % 256 == 0) && n <= 512; };
   return !disabled && ok(a.n_skip) && ok(a.n_post) && a.n_quant == 256 && ((int64_t)m->L * a.n_dil) % 64 == 0 &&
-         (a.n_dil == 16 || a.n_dil == 32 || a.n_dil == 64);
+         (a.n_dil == 16 || a.n_dil == 32 || a.n_dil == 64 || a.n_dil == 128);
 }
 
 static int launch_gemm_umma(wn_model* m, const void* A, int K, const void* B, int N, void* out, int64_t rows,
@@ -1096,11 +1099,11 @@ static int launch_gemm_umma(wn_model* m, const void* A, int K, const void* B, in
   if ((rc = map2d(&ma, A, (uint64_t)K, (uint64_t)rows, UKB, UM))) return rc;
   if ((rc = map2d(&mb, B, (uint64_t)K, (uint64_t)N, UKB, (uint32_t)std::min(256, N)))) return rc;
   if (ga.mode == 2) {
-    const uint64_t D = ga.D;
+    const uint64_t D = ga.D, PW = std::min<uint64_t>(D, 64);
     const uint64_t dims[3] = {D, (uint64_t)rows, (uint64_t)(N / ga.D)};
     const uint64_t strides[2] = {D * 2, (uint64_t)rows * D * 2};
-    const uint32_t box[3] = {(uint32_t)D, UM, 1};
-    if ((rc = make_tensor_map_bf16(&mo, out, 3, dims, strides, box, (int)D * 2))) return rc;
+    const uint32_t box[3] = {(uint32_t)PW, UM, 1};
+    if ((rc = make_tensor_map_bf16(&mo, out, 3, dims, strides, box, (int)PW * 2))) return rc;
   } else {
     if ((rc = map2d(&mo, out, (uint64_t)N, (uint64_t)rows, UKB, UM))) return rc;
   }
