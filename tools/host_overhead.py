@@ -46,3 +46,19 @@ for rep in range(3):
     if rep == 2:
         tot = ev[0].elapsed_time(ev[3])
         print("step %.3f ms -> %.2f M output timesteps/s" % (tot, B * (T - 1) / tot / 1e3))
+
+# per-category CUDA-event timing of one more step (ms)
+import ctypes as C
+from lb_wavenet_b200 import _lib
+lib = _lib.load()
+cats = ["prep_embed_save", "layer_fwd", "post_fwd_loss", "post_bwd", "layer_bwd", "layer_bwd_data", "wgrad", "pre_gc_bwd",
+        "adam", "gen"]
+lib.wn_prof_enable(1)
+eng.forward(wav, ids)
+eng.backward()
+eng.adam(1, 1e-3, 0.0)
+ms = (C.c_double * 16)()
+n = (C.c_int64 * 16)()
+lib.wn_prof_collect(ms, n)
+lib.wn_prof_enable(0)
+print("category ms:", {c: round(ms[k], 3) for k, c in enumerate(cats) if n[k] > 0})
