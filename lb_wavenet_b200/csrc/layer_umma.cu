@@ -199,13 +199,17 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
     }
     fence_mbar_init();
   }
+  tr.ev(34, 0);
   if (tid < 96)
     bias_s[tid] = tid < 32 ? (a.sig_b >= 0 ? a.params[a.sig_b + tid] : 0.f)
                 : tid < 64 ? (a.gate_b >= 0 ? 0.5f * a.params[a.gate_b + tid - 32] : 0.f)
                            : (a.res_b >= 0 ? a.params[a.res_b + tid - 64] : 0.f);
+  tr.ev(35, 0);
   if (warp == 1) tmem_alloc(&tmem_base_s, 256);
+  tr.ev(36, 0);
   tc_fence_before_sync();
   __syncthreads();
+  tr.ev(37, 0);
   tc_fence_after_sync();
   const uint32_t tm = tmem_base_s;  // buffer ab: acc_v at ab*128 (64 cols), acc_r at ab*128 + 64 (32 cols)
   // Programmatic dependent launch: everything above touched only parameters and on-chip state; the previous layer's
@@ -768,17 +772,38 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
             // one slot, ids change only at file junctions: reduce over the warp when it is uniform, else per row
             const int id0 = __shfl_sync(0xffffffffu, gid, 0);
             const bool uni = __all_sync(0xffffffffu, gid == id0);
-            float* drow = a.dgc_tbl + (size_t)(uni ? id0 : gid) * 2 * D + c0 + 4 * q;
+            if (uni) {
+              // transpose-reduce: 8 values x 32 lanes -> lane L ends up with the warp total of value (L >> 2) & 7
+              // (9 shuffles instead of 8 full warp sums = 40)
+              float w[8] = {ds[0], ds[1], ds[2], ds[3], 0.5f * dg[0], 0.5f * dg[1], 0.5f * dg[2], 0.5f * dg[3]};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float vs_ = ds[k], vg_ = 0.5f * dg[k];
-              if (uni) {
-                vs_ = warp_sum(vs_);
-                vg_ = warp_sum(vg_);
+              for (int i = 0; i < 4; ++i) {
+                const bool hi = (lane & 16) != 0;
+                const float send = hi ? w[i] : w[i + 4], keep = hi ? w[i + 4] : w[i];
+                w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
               }
-              if (!uni || lane == 0) {
-                if (vs_ != 0.f) atomicAdd(drow + k, vs_);
-                if (vg_ != 0.f) atomicAdd(drow + D + k, vg_);
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const bool hi = (lane & 8) != 0;
+                const float send = hi ? w[i] : w[i + 2], keep = hi ? w[i + 2] : w[i];
+                w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+              {
+                const bool hi = (lane & 4) != 0;
+                const float send = hi ? w[0] : w[1], keep = hi ? w[1] : w[0];
+                w[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+              w[0] += __shfl_xor_sync(0xffffffffu, w[0], 2);
+              w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
+              const int idx = (lane >> 2) & 7;
+              if ((lane & 3) == 0 && w[0] != 0.f)
+                atomicAdd(a.dgc_tbl + (size_t)id0 * 2 * D + (idx < 4 ? 0 : D) + c0 + 4 * q + (idx & 3), w[0]);
+            } else {
+              float* drow = a.dgc_tbl + (size_t)gid * 2 * D + c0 + 4 * q;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (ds[k] != 0.f) atomicAdd(drow + k, ds[k]);
+                if (dg[k] != 0.f) atomicAdd(drow + D + k, 0.5f * dg[k]);
               }
             }
           }

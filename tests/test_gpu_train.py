@@ -254,3 +254,64 @@ def test_checkpoint_carries_adam_slots_as_optional_keys(lib, tmp_path):
     c, oc = make(5)
     c.restore()
     assert oc.t == 0 and c.restored_optional == [] and float(c.engine.m.abs().max()) == 0.0
+
+
+def test_all_invalid_batch_and_out_of_range_codes(lib):
+    """Edge cases of the reference's loss and one-hot (tmodel.py:53-66, 232, 244-249): a batch whose id mask is all
+    zero has n_valid == 0 -> mean loss 0 and NO gradient (Adam leaves every weight untouched, nothing becomes
+    NaN); mu-law codes outside [0, 256) one-hot to an all-zero row, i.e. the layer-0 input is the PRE bias alone."""
+    arch, B, T = util.TINY, 2, 200
+    a = util.oracle_arch(arch)
+    p = util.scaled_params(a, B, 5)
+    wav, _ = util.synth_batch(B, T, 3, 6)
+    wav = wav.copy()
+    wav[0, 10], wav[1, 20], wav[1, 21] = 256, -1, 100000   # out of range on purpose
+    eng = _engine(arch, B)
+    eng.load_state(p)
+    dw = torch.as_tensor(wav).cuda()
+    zero_ids = torch.zeros(B, T, dtype=torch.int32).cuda()
+    before = eng.params.clone()
+    eng.forward(dw, zero_ids)
+    eng.backward()
+    st = eng.read_stats()
+    assert st["n_valid"] == 0 and st["xent_sum"] == 0.0 and st["diff_sum"] == 0
+    eng.adam(1, 1e-3, 0.0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(eng.params).all() and torch.equal(eng.params, before)
+    assert float(eng.grads.abs().max()) == 0.0
+    # out-of-range codes against the oracle (same rounding points), valid ids
+    ids = np.ones((B, T), np.int32)
+    eng2 = _engine(arch, B)
+    eng2.load_state(p)
+    logits = eng2.forward(dw, torch.as_tensor(ids).cuda(), want_logits=True).cpu().numpy()
+    x0 = eng2.debug_read(0, 0).cpu().numpy()
+    pt, save, kinds = O.to_torch_params(a, p, B, torch.float64, requires_grad=False)
+    em = O.train_forward(a, pt, save, torch.as_tensor(wav).long(), torch.as_tensor(ids).long(), torch.float64,
+                         emulate_bf16=True)
+    bias = torch.as_tensor(p["PRE_BIAS"]).to(torch.bfloat16).float().numpy()
+    for b, t in ((0, 10), (1, 20), (1, 21)):
+        assert np.array_equal(x0[b, t], bias)          # zero one-hot row -> bias only, bit exact
+    assert np.abs(logits - em.logits.numpy()).max() <= 0.05
+
+
+@pytest.mark.parametrize("B,T", [(1, 2), (1, 129), (5, 128)])
+def test_minimal_and_tile_boundary_shapes(lib, B, T):
+    """T = 2 is the smallest stage with one output timestep (tmodel.py:230-231); 128 / 129 sit on the kernels' tile edge."""
+    arch = util.TINY
+    a = util.oracle_arch(arch)
+    p = util.scaled_params(a, B, 9)
+    wav, ids = util.synth_batch(B, T, 3, 10, invalid_frac=0.0)
+    eng = _engine(arch, B)
+    eng.load_state(p)
+    lg = eng.forward(torch.as_tensor(wav).cuda(), torch.as_tensor(ids).cuda(), want_logits=True).cpu().numpy()
+    eng.backward()
+    torch.cuda.synchronize()
+    pt, save, kinds = O.to_torch_params(a, p, B, torch.float64, requires_grad=False)
+    w, i = torch.as_tensor(wav).long(), torch.as_tensor(ids).long()
+    em = O.train_forward(a, pt, save, w, i, torch.float64, emulate_bf16=True)
+    L = O.loss_fn(a, em.logits, w, i, pt, kinds, 0.0)
+    st = eng.read_stats()
+    assert st["n_valid"] == L.n_valid
+    assert np.abs(lg - em.logits.numpy()).max() <= 0.05
+    assert abs(st["xent_sum"] - float(L.xent_sum)) <= 2e-3 * max(1.0, abs(float(L.xent_sum)))
+    assert torch.isfinite(eng.grads).all()

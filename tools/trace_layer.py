@@ -95,7 +95,8 @@ names = {1: "prod:wait_free", 2: "prod:got_free", 3: "mma:issueA", 4: "mma:issue
          6: "e1:v_full", 15: "e1:math_done", 7: "e1:pre_bar", 8: "e1:post_bar", 9: "e2:begin", 10: "e2:acc_full",
          11: "e2:pre_bar", 12: "e2:post_bar", 13: "e2:stored",
          16: "mma:doneA", 17: "mma:doneB", 18: "e0:begin", 19: "e0:in_full", 20: "e0:done",
-         30: "k:entry", 31: "k:init_done", 32: "k:role_done", 33: "k:all_done"}
+         30: "k:entry", 31: "k:init_done", 32: "k:role_done", 33: "k:all_done", 34: "k:bar_init", 35: "k:bias",
+         36: "k:tmem_alloc", 37: "k:synced"}
 rows = []
 for w in range(32):
     for x in ev[w]:
