@@ -76,6 +76,9 @@ bool umma_post_chain_supported(const wn_model* m);  // GEMM-chain post-net (n_sk
 int launch_post_fwd_chain_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_wav,
                                const int32_t* d_ids, int T, double* d_stats, float* d_logits, cudaStream_t st);
 int launch_post_bwd_chain_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, cudaStream_t st);
+bool umma_wgrad_x_supported(const wn_model* m, int T);
+int launch_wgrad_umma_x(wn_model* m, const bf16* xfull, int dil, int T, int tap, const bf16* Y, int ldy, int N,
+                        float* out, int ldo, cudaStream_t st);
 int launch_wgrad_umma_cols(wn_model* m, const bf16* A, int lda, int M_total, const bf16* Y, int N_total, int64_t rows,
                            float* out, int mode, float* grads, cudaStream_t st);
 int launch_prep_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st);
@@ -1277,10 +1280,23 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
       WN_LAUNCH_CHECK();
     }
     // weight gradients of this layer
-    if (dx_next != nullptr)  // RESIDUAL_l [D][R] = z_l^T dx_{l+1}  (the last layer's output is unused)
-      if ((rc = flat(pa.z, d.LD, l * d.D, d.D, dx_next, d.R, 0, d.R, d_grads + m->layers[l].res, d.R))) return rc;
+    const bool wg_umma = umma_wgrad_x_supported(m, T);  // tcgen05 split-K kernel (MN-major operands)
+    if (dx_next != nullptr) {  // RESIDUAL_l [D][R] = z_l^T dx_{l+1}  (the last layer's output is unused)
+      if (wg_umma) {
+        if ((rc = launch_wgrad_umma(m, pa.z, d.LD, l * d.D, d.D, dx_next, d.R, d.R, d.rows, d_grads + m->layers[l].res,
+                                    d.R, 0, d_grads, st))) return rc;
+      } else if ((rc = flat(pa.z, d.LD, l * d.D, d.D, dx_next, d.R, 0, d.R, d_grads + m->layers[l].res, d.R))) {
+        return rc;
+      }
+    }
     for (int tap = 0; tap < 2; ++tap) {
       for (int sg = 0; sg < 2; ++sg) {
+        if (wg_umma) {
+          if ((rc = launch_wgrad_umma_x(m, la.xin, la.ld.dil, T, tap, dv + sg * d.D, 2 * d.D, d.D,
+                                        d_grads + (sg ? la.ld.gate : la.ld.sig) + (int64_t)tap * d.R * d.D, d.D, st)))
+            return rc;
+          continue;
+        }
         wa.A = la.xin; wa.a_slot_pitch = (int64_t)(la.ld.dil + T) * d.R; wa.a_row_off = tap ? la.ld.dil : 0;
         wa.lda = d.R; wa.a_col0 = 0; wa.Ka = d.R;
         wa.Y = dv; wa.y_slot_pitch = (int64_t)T * 2 * d.D; wa.ldy = 2 * d.D; wa.y_col0 = sg * d.D; wa.N = d.D;

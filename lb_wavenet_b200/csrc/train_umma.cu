@@ -1205,6 +1205,8 @@ struct WgradUmmaArgs {
   int M_total, N;
   int a_col0;
   int out_col0;  // mode 1: first output column (N chunks of a wider gradient)
+  int a_T, a_row_off;  // a_T > 0: A is a layer input in the prefix layout [slot][dil + T][R] (3-D map): flat row r is
+                       // (slot r / a_T, row r % a_T + a_row_off); a_T % 64 == 0 keeps a K block inside one slot
   int64_t kblocks_total, kblocks_per_cta;
 };
 
@@ -1249,8 +1251,13 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           mbar_wait(&empty_bar[st], ((uint32_t)(it / WG_STAGES) & 1u) ^ 1u);
           mbar_expect_tx(&full_bar[st], (uint32_t)((2 + npan) * WG_PANEL));
           const int row = (int)((kb0 + it) * WG_BK);
-          for (int c = 0; c < 2; ++c)
-            tma_load_2d(stage_a + st * WG_A_BYTES + c * WG_PANEL, &map_a, &full_bar[st], a.a_col0 + m0 + c * 64, row);
+          for (int c = 0; c < 2; ++c) {
+            if (a.a_T > 0)
+              tma_load_3d(stage_a + st * WG_A_BYTES + c * WG_PANEL, &map_a, &full_bar[st], a.a_col0 + m0 + c * 64,
+                          row % a.a_T + a.a_row_off, row / a.a_T);
+            else
+              tma_load_2d(stage_a + st * WG_A_BYTES + c * WG_PANEL, &map_a, &full_bar[st], a.a_col0 + m0 + c * 64, row);
+          }
           for (int c = 0; c < npan; ++c)
             tma_load_2d(stage_b + st * WG_B_BYTES + c * WG_PANEL, &map_y, &full_bar[st], c * 64, row);
         }
@@ -1340,6 +1347,45 @@ static int launch_wgrad_umma_at(wn_model* m, const bf16* A, int lda, int a_col0,
   wa.M_total = M_total; wa.N = N; wa.a_col0 = a_col0; wa.out_col0 = out_col0;
   wa.kblocks_total = (rows + WG_BK - 1) / WG_BK;
   const int m_tiles = (M_total + 127) / 128;
+  const int sms = std::max(1, m->sm_count);
+  int64_t splits = std::max<int64_t>(1, std::min<int64_t>(wa.kblocks_total, sms / m_tiles));
+  wa.kblocks_per_cta = (wa.kblocks_total + splits - 1) / splits;
+  splits = (wa.kblocks_total + wa.kblocks_per_cta - 1) / wa.kblocks_per_cta;
+  const size_t smem = (size_t)WG_STAGES * (WG_A_BYTES + WG_B_BYTES) + 1024;
+  WN_CUDA_CHECK(cudaFuncSetAttribute(k_wgrad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps(PROF_WGRAD, st);
+  k_wgrad_umma<<<dim3(m_tiles, (unsigned)splits), UPOST_THREADS, smem, st>>>(ma, my, wa);
+  WN_LAUNCH_CHECK();
+  return WN_OK;
+}
+
+// Weight gradients of one conv tap on the layers the fused tcgen05 backward does not cover (R, D multiples of 64):
+// dW[r][n] = sum_t x_tap[t][r] * dv[t][y_col0 + n], x read straight from the prefix layout xfull_l
+bool umma_wgrad_x_supported(const wn_model* m, int T) {
+  static const bool disabled = getenv("WN_DISABLE_UMMA") != nullptr;
+  const wn_arch& a = m->a;
+  return !disabled && a.n_res % 64 == 0 && a.n_dil % 64 == 0 && a.n_res <= 256 && a.n_dil <= 256 && T % 64 == 0;
+}
+
+int launch_wgrad_umma_x(wn_model* m, const bf16* xfull, int dil, int T, int tap, const bf16* Y, int ldy, int N,
+                        float* out, int ldo, cudaStream_t st) {
+  const int R = m->a.n_res;
+  const int64_t rows = (int64_t)m->n_slots * T;
+  CUtensorMap ma, my;
+  int rc;
+  {
+    const uint64_t dims[3] = {(uint64_t)R, (uint64_t)(dil + T), (uint64_t)m->n_slots};
+    const uint64_t strides[2] = {(uint64_t)R * 2, (uint64_t)(dil + T) * R * 2};
+    const uint32_t box[3] = {64, WG_BK, 1};
+    if ((rc = make_tensor_map_bf16(&ma, xfull, 3, dims, strides, box, 128))) return rc;
+  }
+  if ((rc = map2d(&my, Y, (uint64_t)ldy, (uint64_t)rows, 64, WG_BK))) return rc;
+  WgradUmmaArgs wa;
+  memset(&wa, 0, sizeof(wa));
+  wa.out = out; wa.layers = m->d_layers; wa.mode = 0; wa.D = m->a.n_dil; wa.ldo = ldo;
+  wa.M_total = R; wa.N = N; wa.a_T = T; wa.a_row_off = tap ? dil : 0;
+  wa.kblocks_total = (rows + WG_BK - 1) / WG_BK;
+  const int m_tiles = (R + 127) / 128;
   const int sms = std::max(1, m->sm_count);
   int64_t splits = std::max<int64_t>(1, std::min<int64_t>(wa.kblocks_total, sms / m_tiles));
   wa.kblocks_per_cta = (wa.kblocks_total + splits - 1) / splits;

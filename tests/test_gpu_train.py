@@ -106,7 +106,8 @@ def test_stagewise_equals_whole(lib):
 
 
 @pytest.mark.parametrize("arch,B,T", [(util.TINY, 3, 96), (util.TINY_GC, 2, 130), (util.TINY_ASYM, 2, 64),
-                                      (util.WIDE, 1, 70), (util.CLASSIC, 2, 300), (util.CLASSIC_SHALLOW, 3, 200),
+                                      (util.WIDE, 1, 70), (util.WIDE, 2, 128), (util.CLASSIC, 2, 300),
+                                      (util.CLASSIC_SHALLOW, 3, 200),
                                       (util.TINY_NOBIAS, 2, 64), (util.C1, 2, 160), (util.CLASSIC_SHALLOW, 2, 1000)])
 def test_gradients_match_oracle(lib, arch, B, T):
     a, p, wav, ids, eng, logits = _run_fwd(arch, B, T, 11)
