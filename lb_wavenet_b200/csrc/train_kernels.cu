@@ -76,6 +76,9 @@ bool umma_post_chain_supported(const wn_model* m);  // GEMM-chain post-net (n_sk
 int launch_post_fwd_chain_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_wav,
                                const int32_t* d_ids, int T, double* d_stats, float* d_logits, cudaStream_t st);
 int launch_post_bwd_chain_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, cudaStream_t st);
+bool umma_wide_layer_supported(const wn_model* m);  // layers with R, D multiples of 64 through the GEMM kernel
+int launch_prep_wide_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st);
+int launch_layer_fwd_wide_umma(wn_model* m, const float* d_params, unsigned char* ws, int T, int l, cudaStream_t st);
 bool umma_wgrad_x_supported(const wn_model* m, int T);
 int launch_wgrad_umma_x(wn_model* m, const bf16* xfull, int dil, int T, int tap, const bf16* Y, int ldy, int N,
                         float* out, int ldo, cudaStream_t st);
@@ -1066,6 +1069,7 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
   const bool umma_post = umma_post_supported(m);
   const bool umma_chain = !umma_post && umma_post_chain_supported(m);
   const bool umma_layer = umma_layer_supported(m);
+  const bool umma_wide = !umma_layer && umma_wide_layer_supported(m);
   {
   ProfScope ps_prep(PROF_PREP, st);
   k_cast_params<<<(unsigned)((m->n_param_elems + 255) / 256), 256, 0, st>>>(d_params, wbf, m->n_param_elems);
@@ -1082,6 +1086,7 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
   }
   if ((umma_post || umma_chain) && (rc = launch_prep_umma(m, d_params, ws, st))) return rc;
   if (umma_layer && (rc = launch_prep_layer_umma(m, d_params, ws, st))) return rc;
+  if (umma_wide && (rc = launch_prep_wide_umma(m, d_params, ws, st))) return rc;
   WN_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(double) * 3, st));
   WN_CUDA_CHECK(cudaMemsetAsync(ws + wl.tile_ctr, 0, sizeof(int) * 4 * d.L, st));  // tile schedulers (they also re-arm themselves)
   k_save_load<<<dim3(64, d.L), 256, 0, st>>>(reinterpret_cast<const bf16*>(d_save), ws, m->d_layers, d.B, T, d.R);
@@ -1101,6 +1106,10 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
   for (int l = 0; l < d.L; ++l) {
     if (umma_layer) {
       if ((rc = launch_layer_fwd_umma(m, d_params, ws, d_ids, T, l, st))) return rc;
+      continue;
+    }
+    if (umma_wide) {
+      if ((rc = launch_layer_fwd_wide_umma(m, d_params, ws, T, l, st))) return rc;
       continue;
     }
     ProfScope ps(PROF_LAYER_FWD, st);

@@ -819,6 +819,15 @@ struct GemmUmmaArgs {
   double* stats;
   float* logits_out;
   int T;
+  // ---- per-layer use (modes 4, 5): tiles are (slot, 128 timesteps); A and the output are 3-D maps [cols][rows][slot]
+  int tps;            // tiles per slot (0: flat rows, 2-D maps)
+  int a_col0;         // first A column (the z stash holds every layer side by side)
+  int a_k_split;      // K elements that come from A rows t0 + ...; the rest from rows t0 + a_row_off2 (second conv tap)
+  int a_row_off2;
+  int out_col0, out_row_off;
+  const float* bias2; // mode 4: GATE bias (bias = SIGNAL bias); both [D]
+  const bf16* X;      // mode 5: the layer input x[t] for the residual add: X[(slot * x_slot_rows + x_row_off + t) * N + c]
+  int x_slot_rows, x_row_off;
 };
 
 __global__ void __launch_bounds__(UPOST_P_THREADS, 1)
@@ -835,11 +844,18 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   __shared__ float x_mx[2][128], x_sum[2][128], x_vl[2][128];
   __shared__ int x_arg[2][128];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tiles = (int)((a.rows + UM - 1) / UM);
+  const int n_tiles = a.tps > 0 ? a.tps * (int)(a.rows / a.T) : (int)((a.rows + UM - 1) / UM);
   const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int nchunk = (a.N + 255) / 256, nkb = a.K / UKB;
   const int box_n = min(256, a.N);  // rows of B one TMA box brings (a partial last chunk is zero filled)
-  for (int i = tid; i < 512; i += UPOST_P_THREADS) bias_s[i] = (a.bias != nullptr && i < a.N) ? a.bias[i] : 0.f;
+  if (a.mode == 4) {  // SIGNAL_BIAS | 0.5 * GATE_BIAS (the GATE filter copy is pre-scaled by 0.5: sigmoid via tanh)
+    const int Dh = a.N / 2;
+    for (int i = tid; i < 512; i += UPOST_P_THREADS)
+      bias_s[i] = i < Dh ? (a.bias != nullptr ? a.bias[i] : 0.f)
+                : i < 2 * Dh ? (a.bias2 != nullptr ? 0.5f * a.bias2[i - Dh] : 0.f) : 0.f;
+  } else {
+    for (int i = tid; i < 512; i += UPOST_P_THREADS) bias_s[i] = (a.bias != nullptr && i < a.N) ? a.bias[i] : 0.f;
+  }
   if (tid == 0) {
     for (int i = 0; i < GEMM_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -864,13 +880,21 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if (lane == 0) {
       int it = 0;
       for (int i = 0; i < n_my; ++i) {
-        const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * UM;
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int row0 = tile * UM;
+        const int sb = a.tps > 0 ? tile / a.tps : 0, t0 = a.tps > 0 ? (tile % a.tps) * UM : 0;
         for (int c = 0; c < nchunk; ++c)
           for (int kb = 0; kb < nkb; ++kb, ++it) {
             const int st = it % GEMM_STAGES;
             mbar_wait(&empty_bar[st], ((uint32_t)(it / GEMM_STAGES) & 1u) ^ 1u);
             mbar_expect_tx(&full_bar[st], (uint32_t)(UA_BYTES + box_n * 128));
-            tma_load_2d(stage_a + st * UA_BYTES, &map_a, &full_bar[st], kb * UKB, row0);
+            if (a.tps > 0) {
+              int k0 = kb * UKB, roff = 0;
+              if (a.a_k_split > 0 && k0 >= a.a_k_split) { k0 -= a.a_k_split; roff = a.a_row_off2; }
+              tma_load_3d(stage_a + st * UA_BYTES, &map_a, &full_bar[st], a.a_col0 + k0, t0 + roff, sb);
+            } else {
+              tma_load_2d(stage_a + st * UA_BYTES, &map_a, &full_bar[st], kb * UKB, row0);
+            }
             tma_load_2d(stage_b + st * UB_BYTES, &map_b, &full_bar[st], kb * UKB, c * 256);
           }
       }
@@ -909,9 +933,11 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     float acc_x = 0.f, acc_n = 0.f, acc_d = 0.f;
     int item = 0;
     for (int i = 0; i < n_my; ++i) {
-      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * UM;
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const int64_t row0 = (int64_t)tile * UM;
       const int64_t row = row0 + r;
       const bool in_range = row < a.rows;
+      const int sb = a.tps > 0 ? tile / a.tps : 0, t0 = a.tps > 0 ? (tile % a.tps) * UM : 0;
       for (int c = 0; c < nchunk; ++c, ++item) {
         const int buf = item & 1;
         const int n0 = c * 256, w = min(256, a.N - n0);
@@ -946,6 +972,70 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           epi_bar_sync256();
           if (elected) {
             for (int kb = 0; kb < w / UKB; ++kb) tma_store_2d(&map_out, otile + kb * UA_BYTES, n0 + kb * UKB, (int)row0);
+            tma_store_commit();
+          }
+        } else if (a.mode == 4) {
+          // gate: columns [h*D, h*D + D/2) = SIGNAL channels [h*D/2, ...), [h*D + D/2, (h+1)*D) = the same GATE channels
+          // (weight rows permuted by k_prep_wide_weights); z = tanh(s) * (0.5 tanh(g/2) + 0.5)   (tmodel.py:167)
+          const int Dn = a.N / 2, Dh = Dn / 2;  // z channels, channels per column half
+          uint32_t g[32];
+          for (int c0 = 0; c0 < Dh; c0 += 32) {
+            tmem_ld_32x32b_x32(acc + (uint32_t)(half * Dn + c0), v);
+            tmem_ld_32x32b_x32(acc + (uint32_t)(half * Dn + Dh + c0), g);
+            tmem_ld_wait();
+            const int ch = half * Dh + c0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float z0 = tanh_fast(__uint_as_float(v[2 * j]) + bias_s[ch + 2 * j]) *
+                               fmaf(0.5f, tanh_fast(__uint_as_float(g[2 * j]) + bias_s[Dn + ch + 2 * j]), 0.5f);
+              const float z1 = tanh_fast(__uint_as_float(v[2 * j + 1]) + bias_s[ch + 2 * j + 1]) *
+                               fmaf(0.5f, tanh_fast(__uint_as_float(g[2 * j + 1]) + bias_s[Dn + ch + 2 * j + 1]), 0.5f);
+              pk[j] = pack_bf16x2(z0, z1);
+            }
+            htile_store32(otile, r, ch, pk);
+          }
+          tc_fence_before_sync();
+          mbar_arrive(&acc_empty[buf]);
+          fence_proxy_async_smem();
+          epi_bar_sync256();
+          if (elected) {
+            for (int kb = 0; kb < Dn / UKB; ++kb)
+              tma_store_3d(&map_out, otile + kb * UA_BYTES, a.out_col0 + kb * UKB, a.out_row_off + t0, sb);
+            tma_store_commit();
+          }
+        } else if (a.mode == 5) {
+          // residual: x' = bf16(x[t] + z . RESIDUAL + bias) written into the next layer's input  (tmodel.py:325)
+          const bool row_ok = t0 + r < a.T;
+          const bf16* xrow = a.X + ((size_t)sb * a.x_slot_rows + a.x_row_off + t0 + r) * a.N;
+          const int cb = half * (w / 2);
+          for (int c0 = cb; c0 < cb + w / 2; c0 += 32) {
+            tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
+            tmem_ld_wait();
+            uint32_t xw[16];
+            if (row_ok) {
+              const uint4* x4 = reinterpret_cast<const uint4*>(xrow + c0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 t4 = __ldg(x4 + q);
+                xw[4 * q] = t4.x; xw[4 * q + 1] = t4.y; xw[4 * q + 2] = t4.z; xw[4 * q + 3] = t4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) xw[j] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]) + __uint_as_float(xw[j] << 16) + bias_s[c0 + 2 * j],
+                                  __uint_as_float(v[2 * j + 1]) + __uint_as_float(xw[j] & 0xffff0000u) + bias_s[c0 + 2 * j + 1]);
+            htile_store32(otile, r, c0, pk);
+          }
+          tc_fence_before_sync();
+          mbar_arrive(&acc_empty[buf]);
+          fence_proxy_async_smem();
+          epi_bar_sync256();
+          if (elected) {
+            for (int kb = 0; kb < w / UKB; ++kb)
+              tma_store_3d(&map_out, otile + kb * UA_BYTES, a.out_col0 + kb * UKB, a.out_row_off + t0, sb);
             tma_store_commit();
           }
         } else if (a.mode == 2) {
@@ -1179,6 +1269,108 @@ int launch_post_bwd_chain_umma(wn_model* m, unsigned char* ws, int T, float* d_g
     WN_LAUNCH_CHECK();
   }
   return WN_OK;
+}
+
+}  // namespace wn
+
+// =====================================================================================================
+// Wide layers (R, D multiples of 64; BASELINE configs[4] has R = D = 128) through k_gemm_umma: forward as two GEMMs
+//   v = [x(t-dil) | x(t)] . Wc  -> gate epilogue -> z (stash)          (tmodel.py:117-168)
+//   x' = x + z . RESIDUAL + b    -> next layer's input (prefix layout)   (tmodel.py:171-184, :325)
+// =====================================================================================================
+namespace wn {
+
+// wcP[l][n][k] (K-major B operand, N = 2D rows, K = 2R): row n = h*D + j: j < D/2 -> SIGNAL channel h*D/2 + j,
+// else 0.5 * GATE channel h*D/2 + (j - D/2); k < R -> tap 0 (x[t-dil]), else tap 1 (x[t]).  wrT[l][r][d] = RESIDUAL[d][r].
+__global__ void k_prep_wide_weights(const float* __restrict__ p, const LayerDesc* __restrict__ layers, int R, int D,
+                                    bf16* __restrict__ wcP, bf16* __restrict__ wrT) {
+  const int l = blockIdx.x;
+  const LayerDesc ld = layers[l];
+  const int n_wc = 2 * D * 2 * R, n_wr = R * D, Dh = D / 2;
+  for (int i = threadIdx.x; i < n_wc; i += blockDim.x) {
+    const int n = i / (2 * R), k = i % (2 * R);
+    const int h = n / D, j = n % D;
+    const bool gate = j >= Dh;
+    const int ch = h * Dh + (gate ? j - Dh : j);
+    const int tap = k >= R, r = k % R;
+    const float v = p[(gate ? ld.gate : ld.sig) + ((int64_t)tap * R + r) * D + ch];
+    wcP[(int64_t)l * n_wc + i] = f2bf(gate ? 0.5f * v : v);
+  }
+  for (int i = threadIdx.x; i < n_wr; i += blockDim.x) {
+    const int r = i / D, d = i % D;
+    wrT[(int64_t)l * n_wr + i] = f2bf(p[ld.res + (int64_t)d * R + r]);
+  }
+}
+
+bool umma_wide_layer_supported(const wn_model* m) {
+  static const bool disabled = getenv("WN_DISABLE_UMMA") != nullptr || getenv("WN_DISABLE_UMMA_WIDE") != nullptr;
+  const wn_arch& a = m->a;
+  return !disabled && a.n_res % 64 == 0 && a.n_dil % 64 == 0 && a.n_res <= 256 && a.n_dil <= 128 && a.n_gc_embed == 0;
+}
+
+int launch_prep_wide_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st) {
+  const WorkspaceLayout& wl = m->wl;
+  k_prep_wide_weights<<<m->L, 256, 0, st>>>(d_params, m->d_layers, m->a.n_res, m->a.n_dil,
+                                            reinterpret_cast<bf16*>(ws + wl.wcT), reinterpret_cast<bf16*>(ws + wl.wrT));
+  WN_LAUNCH_CHECK();
+  return WN_OK;
+}
+
+static int map3(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t slots) {
+  const uint64_t dims[3] = {cols, rows, slots};
+  const uint64_t strides[2] = {cols * 2, cols * rows * 2};
+  const uint32_t box[3] = {UKB, UM, 1};
+  return make_tensor_map_bf16(out, base, 3, dims, strides, box, 128);
+}
+
+static int launch_gemm_umma_layer(wn_model* m, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
+                                  GemmUmmaArgs ga, int T, cudaStream_t st) {
+  ga.rows = (int64_t)m->n_slots * T;
+  ga.T = T;
+  ga.tps = (T + UM - 1) / UM;
+  const size_t smem = (size_t)GEMM_STAGES * (UA_BYTES + UB_BYTES) + UH_BYTES + 1024;
+  WN_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int n_tiles = ga.tps * m->n_slots;
+  int grid = std::max(1, std::min(n_tiles, m->sm_count));
+  if (const char* e = getenv("WN_PERSIST_GRID")) if (atoi(e) > 0) grid = std::max(1, std::min(grid, atoi(e)));
+  k_gemm_umma<<<grid, UPOST_P_THREADS, smem, st>>>(ma, mb, mo, ga);
+  WN_LAUNCH_CHECK();
+  return WN_OK;
+}
+
+int launch_layer_fwd_wide_umma(wn_model* m, const float* d_params, unsigned char* ws, int T, int l, cudaStream_t st) {
+  const WorkspaceLayout& wl = m->wl;
+  const wn_arch& a = m->a;
+  const LayerDesc& ld = m->layers[l];
+  const int R = a.n_res, D = a.n_dil, LD = m->L * D;
+  const bool last = (l + 1 == m->L);
+  CUtensorMap mx, mz, mwc, mwr, mxo;
+  int rc;
+  if ((rc = map3(&mx, ws + wl.xfull[l], R, (uint64_t)ld.dil + T, m->n_slots))) return rc;
+  if ((rc = map3(&mz, ws + wl.z, LD, T, m->n_slots))) return rc;
+  if ((rc = map2d(&mwc, reinterpret_cast<const bf16*>(ws + wl.wcT) + (size_t)l * 2 * D * 2 * R, 2 * R, 2 * D, UKB,
+                  (uint32_t)(2 * D)))) return rc;
+  ProfScope ps(PROF_LAYER_FWD, st);
+  GemmUmmaArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.mode = 4; ga.K = 2 * R; ga.N = 2 * D;
+  ga.a_k_split = R; ga.a_row_off2 = ld.dil;
+  ga.out_col0 = l * D; ga.out_row_off = 0;
+  ga.bias = ld.sig_b >= 0 ? d_params + ld.sig_b : nullptr;
+  ga.bias2 = ld.gate_b >= 0 ? d_params + ld.gate_b : nullptr;
+  if ((rc = launch_gemm_umma_layer(m, mx, mwc, mz, ga, T, st))) return rc;
+  if (last) return WN_OK;  // the last layer's residual output is unused (tmodel.py:313-325)
+  const int dil_next = m->layers[l + 1].dil;
+  if ((rc = map2d(&mwr, reinterpret_cast<const bf16*>(ws + wl.wrT) + (size_t)l * R * D, D, R, UKB, (uint32_t)R))) return rc;
+  if ((rc = map3(&mxo, ws + wl.xfull[l + 1], R, (uint64_t)dil_next + T, m->n_slots))) return rc;
+  memset(&ga, 0, sizeof(ga));
+  ga.mode = 5; ga.K = D; ga.N = R;
+  ga.a_col0 = l * D;
+  ga.out_col0 = 0; ga.out_row_off = dil_next;
+  ga.bias = ld.res_b >= 0 ? d_params + ld.res_b : nullptr;
+  ga.X = reinterpret_cast<const bf16*>(ws + wl.xfull[l]);
+  ga.x_slot_rows = ld.dil + T; ga.x_row_off = ld.dil;
+  return launch_gemm_umma_layer(m, mz, mwr, mxo, ga, T, st);
 }
 
 }  // namespace wn
