@@ -76,6 +76,7 @@ const WorkspaceLayout& workspace_layout(wn_model* m, int32_t T) {
   w.wcT = take(L * 2 * 2 * D * R * 2);
   w.wrT = take(L * R * D * 2);
   w.wrN = take(L * D * R * 2);
+  w.wdP = take(L * R * 4 * D * 2);
   w.total = off;
   m->wl = w;
   return m->wl;

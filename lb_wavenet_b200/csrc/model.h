@@ -57,6 +57,7 @@ struct WorkspaceLayout {
   int64_t w1T;        // [P][S]     = POST1^T
   int64_t w2T;        // [Q][P]     = POST2^T
   int64_t wcT, wrT, wrN;     // per-layer conv / residual operands of the tcgen05 layer kernels (layer_umma.cu)
+  int64_t wdP;               // [L][R][4D]: B operand of the wide layers' data gradient (train_umma.cu)
   int64_t total;
   std::vector<int64_t> xfull;  // per layer: [B][dil+T][R] bf16
 };

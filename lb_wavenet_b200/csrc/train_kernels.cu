@@ -79,6 +79,8 @@ int launch_post_bwd_chain_umma(wn_model* m, unsigned char* ws, int T, float* d_g
 bool umma_wide_layer_supported(const wn_model* m);  // layers with R, D multiples of 64 through the GEMM kernel
 int launch_prep_wide_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st);
 int launch_layer_fwd_wide_umma(wn_model* m, const float* d_params, unsigned char* ws, int T, int l, cudaStream_t st);
+int launch_layer_bwd_wide_umma(wn_model* m, const float* d_params, unsigned char* ws, int T, int l, float* d_grads,
+                               cudaStream_t st);
 bool umma_wgrad_x_supported(const wn_model* m, int T);
 int launch_wgrad_umma_x(wn_model* m, const bf16* xfull, int dil, int T, int tap, const bf16* Y, int ldy, int N,
                         float* out, int ldo, cudaStream_t st);
@@ -1283,7 +1285,10 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
       if ((rc = launch_layer_bwd_fused_umma(m, d_params, ws, d_ids, T, l, d_grads, st))) return rc;
       continue;
     }
-    {
+    const bool wide = umma_wide_layer_supported(m) && umma_wgrad_x_supported(m, T);
+    if (wide) {
+      if ((rc = launch_layer_bwd_wide_umma(m, d_params, ws, T, l, d_grads, st))) return rc;
+    } else {
       ProfScope ps(PROF_LAYER_BWD_A, st);
       k_layer_bwd_a<<<grid, NT, sa, st>>>(la);
       WN_LAUNCH_CHECK();
@@ -1313,7 +1318,7 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
         if ((rc = launch_wgrad(wa, m->sm_count, st))) return rc;
       }
     }
-    {
+    if (!wide) {
       ProfScope ps(PROF_LAYER_BWD_B, st);
       k_layer_bwd_b<<<grid, NT, sb, st>>>(la);
       WN_LAUNCH_CHECK();

@@ -848,7 +848,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int nchunk = (a.N + 255) / 256, nkb = a.K / UKB;
   const int box_n = min(256, a.N);  // rows of B one TMA box brings (a partial last chunk is zero filled)
-  if (a.mode == 4) {  // SIGNAL_BIAS | 0.5 * GATE_BIAS (the GATE filter copy is pre-scaled by 0.5: sigmoid via tanh)
+  if (a.mode == 4 || a.mode == 6) {  // SIGNAL_BIAS | 0.5 * GATE_BIAS (the GATE filter copy is pre-scaled by 0.5: sigmoid via tanh)
     const int Dh = a.N / 2;
     for (int i = tid; i < 512; i += UPOST_P_THREADS)
       bias_s[i] = i < Dh ? (a.bias != nullptr ? a.bias[i] : 0.f)
@@ -1005,8 +1005,9 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           }
         } else if (a.mode == 5) {
           // residual: x' = bf16(x[t] + z . RESIDUAL + bias) written into the next layer's input  (tmodel.py:325)
-          const bool row_ok = t0 + r < a.T;
-          const bf16* xrow = a.X + ((size_t)sb * a.x_slot_rows + a.x_row_off + t0 + r) * a.N;
+          const bool row_ok = a.X != nullptr && (a.tps > 0 ? t0 + r < a.T : in_range);
+          const bf16* xrow = a.tps > 0 ? a.X + ((size_t)sb * a.x_slot_rows + a.x_row_off + t0 + r) * a.N
+                                       : a.X + (size_t)row * a.N;
           const int cb = half * (w / 2);
           for (int c0 = cb; c0 < cb + w / 2; c0 += 32) {
             tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
@@ -1034,8 +1035,61 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           fence_proxy_async_smem();
           epi_bar_sync256();
           if (elected) {
-            for (int kb = 0; kb < w / UKB; ++kb)
-              tma_store_3d(&map_out, otile + kb * UA_BYTES, a.out_col0 + kb * UKB, a.out_row_off + t0, sb);
+            for (int kb = 0; kb < w / UKB; ++kb) {
+              if (a.tps > 0) tma_store_3d(&map_out, otile + kb * UA_BYTES, a.out_col0 + kb * UKB, a.out_row_off + t0, sb);
+              else tma_store_2d(&map_out, otile + kb * UA_BYTES, a.out_col0 + kb * UKB, (int)row0);
+            }
+            tma_store_commit();
+          }
+        } else if (a.mode == 6) {
+          // gate backward: recompute th, sg from the pre-activations; dz (skip + residual part) from the dz plane;
+          // dv_s = dz sg (1 - th^2), dv_g = dz th sg (1 - sg) -> dv [.. x 2D] (SIGNAL | GATE)
+          const int Dn = a.N / 2, Dh = Dn / 2;
+          const bool row_ok = t0 + r < a.T;
+          const bf16* dzrow = a.X + ((size_t)sb * a.T + t0 + r) * Dn;
+          uint32_t g[32], pg[16];
+          for (int c0 = 0; c0 < Dh; c0 += 32) {
+            tmem_ld_32x32b_x32(acc + (uint32_t)(half * Dn + c0), v);
+            tmem_ld_32x32b_x32(acc + (uint32_t)(half * Dn + Dh + c0), g);
+            const int ch = half * Dh + c0;
+            uint32_t dzw[16];
+            if (row_ok) {
+              const uint4* d4 = reinterpret_cast<const uint4*>(dzrow + ch);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 t4 = __ldg(d4 + q);
+                dzw[4 * q] = t4.x; dzw[4 * q + 1] = t4.y; dzw[4 * q + 2] = t4.z; dzw[4 * q + 3] = t4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) dzw[j] = 0u;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float ds[2], dg[2];
+#pragma unroll
+              for (int e2 = 0; e2 < 2; ++e2) {
+                const float th = tanh_fast(__uint_as_float(v[2 * j + e2]) + bias_s[ch + 2 * j + e2]);
+                const float u = tanh_fast(__uint_as_float(g[2 * j + e2]) + bias_s[Dn + ch + 2 * j + e2]);
+                const float sg = fmaf(0.5f, u, 0.5f);
+                const float dz = e2 == 0 ? __uint_as_float(dzw[j] << 16) : __uint_as_float(dzw[j] & 0xffff0000u);
+                ds[e2] = (dz * sg) * fmaf(-th, th, 1.f);
+                dg[e2] = (dz * th) * (sg * (1.f - sg));
+              }
+              pk[j] = pack_bf16x2(ds[0], ds[1]);
+              pg[j] = pack_bf16x2(dg[0], dg[1]);
+            }
+            htile_store32(otile, r, ch, pk);
+            htile_store32(otile, r, Dn + ch, pg);
+          }
+          tc_fence_before_sync();
+          mbar_arrive(&acc_empty[buf]);
+          fence_proxy_async_smem();
+          epi_bar_sync256();
+          if (elected) {
+            for (int kb = 0; kb < a.N / UKB; ++kb)
+              tma_store_3d(&map_out, otile + kb * UA_BYTES, kb * UKB, t0, sb);
             tma_store_commit();
           }
         } else if (a.mode == 2) {
@@ -1158,14 +1212,14 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 }
 
 // column sums of a bf16 [rows x N] matrix, added to out[N] (bias gradients on the GEMM-chain path)
-__global__ void k_colsum_bf16(const bf16* __restrict__ x, int64_t rows, int N, float* __restrict__ out) {
+__global__ void k_colsum_bf16(const bf16* __restrict__ x, int64_t rows, int ld, int N, float* __restrict__ out) {
   const int c2 = blockIdx.x * blockDim.x + threadIdx.x;  // column pair
   if (2 * c2 >= N) return;
   const int64_t r0 = (int64_t)blockIdx.y * ((rows + gridDim.y - 1) / gridDim.y);
   const int64_t r1 = min(rows, r0 + (rows + gridDim.y - 1) / gridDim.y);
   float s0 = 0.f, s1 = 0.f;
   for (int64_t r = r0; r < r1; ++r) {
-    const uint32_t wv = *reinterpret_cast<const uint32_t*>(x + r * N + 2 * c2);
+    const uint32_t wv = *reinterpret_cast<const uint32_t*>(x + r * ld + 2 * c2);
     s0 += __uint_as_float(wv << 16);
     s1 += __uint_as_float(wv & 0xffff0000u);
   }
@@ -1254,7 +1308,7 @@ int launch_post_bwd_chain_umma(wn_model* m, unsigned char* ws, int T, float* d_g
     if (a.use_bias) {
       const int ny = (int)std::max<int64_t>(1, std::min<int64_t>(rows / 256, 4 * m->sm_count));
       auto colsum = [&](const void* x, int N, float* out) {
-        k_colsum_bf16<<<dim3((N / 2 + 127) / 128, ny), 128, 0, st>>>(reinterpret_cast<const bf16*>(x), rows, N, out);
+        k_colsum_bf16<<<dim3((N / 2 + 127) / 128, ny), 128, 0, st>>>(reinterpret_cast<const bf16*>(x), rows, N, N, out);
       };
       colsum(ws + wl.dlogits, Q, d_grads + m->off_post2_b);
       WN_LAUNCH_CHECK();
@@ -1283,7 +1337,7 @@ namespace wn {
 // wcP[l][n][k] (K-major B operand, N = 2D rows, K = 2R): row n = h*D + j: j < D/2 -> SIGNAL channel h*D/2 + j,
 // else 0.5 * GATE channel h*D/2 + (j - D/2); k < R -> tap 0 (x[t-dil]), else tap 1 (x[t]).  wrT[l][r][d] = RESIDUAL[d][r].
 __global__ void k_prep_wide_weights(const float* __restrict__ p, const LayerDesc* __restrict__ layers, int R, int D,
-                                    bf16* __restrict__ wcP, bf16* __restrict__ wrT) {
+                                    bf16* __restrict__ wcP, bf16* __restrict__ wrT, bf16* __restrict__ wdP) {
   const int l = blockIdx.x;
   const LayerDesc ld = layers[l];
   const int n_wc = 2 * D * 2 * R, n_wr = R * D, Dh = D / 2;
@@ -1300,6 +1354,15 @@ __global__ void k_prep_wide_weights(const float* __restrict__ p, const LayerDesc
     const int r = i / D, d = i % D;
     wrT[(int64_t)l * n_wr + i] = f2bf(p[ld.res + (int64_t)d * R + r]);
   }
+  // wdP[l][r][k] (N = R rows, K = 4D): k < 2D -> tap 1 (contracted with dv[t]), else tap 0 (with dv[t + dil]);
+  // inside a tap: k % 2D < D -> SIGNAL[tap][r][.], else GATE[tap][r][.]
+  const int n_wd = R * 4 * D;
+  for (int i = threadIdx.x; i < n_wd; i += blockDim.x) {
+    const int r = i / (4 * D), k = i % (4 * D);
+    const int tap = k < 2 * D ? 1 : 0, kk = k % (2 * D);
+    const float v = p[(kk < D ? ld.sig : ld.gate) + ((int64_t)tap * R + r) * D + (kk % D)];
+    wdP[(int64_t)l * n_wd + i] = f2bf(v);
+  }
 }
 
 bool umma_wide_layer_supported(const wn_model* m) {
@@ -1311,7 +1374,8 @@ bool umma_wide_layer_supported(const wn_model* m) {
 int launch_prep_wide_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st) {
   const WorkspaceLayout& wl = m->wl;
   k_prep_wide_weights<<<m->L, 256, 0, st>>>(d_params, m->d_layers, m->a.n_res, m->a.n_dil,
-                                            reinterpret_cast<bf16*>(ws + wl.wcT), reinterpret_cast<bf16*>(ws + wl.wrT));
+                                            reinterpret_cast<bf16*>(ws + wl.wcT), reinterpret_cast<bf16*>(ws + wl.wrT),
+                                            reinterpret_cast<bf16*>(ws + wl.wdP));
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
@@ -1371,6 +1435,79 @@ int launch_layer_fwd_wide_umma(wn_model* m, const float* d_params, unsigned char
   ga.X = reinterpret_cast<const bf16*>(ws + wl.xfull[l]);
   ga.x_slot_rows = ld.dil + T; ga.x_row_off = ld.dil;
   return launch_gemm_umma_layer(m, mz, mwr, mxo, ga, T, st);
+}
+
+}  // namespace wn
+
+namespace wn {
+
+// Backward of one wide layer as three GEMMs (the data gradient in its plain form, as the generation-1 kernels keep it):
+//   dz_l      += dx_{l+1} . RESIDUAL^T                      (in place on the layer's dz plane; one extra bf16 rounding)
+//   dv         = gate'(v) * dz_l, v recomputed from x        -> dv [B*T][2D]
+//   dx_l[t]    = dx_{l+1}[t] + dv[t] . W[1]^T + dv[t + dil] . W[0]^T   (rows t + dil >= T: TMA zero fill = truncated BPTT)
+// and the bias gradients as column sums.  The weight gradients follow from k_wgrad_umma (launch_wgrad_umma_x).
+int launch_layer_bwd_wide_umma(wn_model* m, const float* d_params, unsigned char* ws, int T, int l, float* d_grads,
+                               cudaStream_t st) {
+  const WorkspaceLayout& wl = m->wl;
+  const wn_arch& a = m->a;
+  const LayerDesc& ld = m->layers[l];
+  const int R = a.n_res, D = a.n_dil;
+  const int64_t rows = (int64_t)m->n_slots * T;
+  const bool has_next = (l + 1 < m->L);
+  const bf16* wbf = reinterpret_cast<const bf16*>(ws + wl.wbf);
+  bf16* dz_plane = reinterpret_cast<bf16*>(ws + wl.dz) + (size_t)l * rows * D;
+  bf16* dv = reinterpret_cast<bf16*>(ws + wl.dv);
+  bf16* dx_next = has_next ? reinterpret_cast<bf16*>(ws + wl.dx[(l + 1) & 1]) : nullptr;
+  bf16* dx_out = reinterpret_cast<bf16*>(ws + wl.dx[l & 1]);
+  int rc;
+  GemmUmmaArgs ga;
+  {
+    ProfScope ps(PROF_LAYER_BWD_A, st);
+    if (has_next) {  // dz_l += dx_{l+1} . RESIDUAL^T   (RESIDUAL [D][R]: N = D rows, K = R)
+      memset(&ga, 0, sizeof(ga));
+      ga.mode = 5;
+      ga.X = dz_plane;
+      if ((rc = launch_gemm_umma(m, dx_next, R, wbf + ld.res, D, dz_plane, rows, ga, st))) return rc;
+    }
+    CUtensorMap mx, mwc, mdv;
+    if ((rc = map3(&mx, ws + wl.xfull[l], R, (uint64_t)ld.dil + T, m->n_slots))) return rc;
+    if ((rc = map2d(&mwc, reinterpret_cast<const bf16*>(ws + wl.wcT) + (size_t)l * 2 * D * 2 * R, 2 * R, 2 * D, UKB,
+                    (uint32_t)(2 * D)))) return rc;
+    if ((rc = map3(&mdv, dv, 2 * D, T, m->n_slots))) return rc;
+    memset(&ga, 0, sizeof(ga));
+    ga.mode = 6; ga.K = 2 * R; ga.N = 2 * D;
+    ga.a_k_split = R; ga.a_row_off2 = ld.dil;
+    ga.bias = ld.sig_b >= 0 ? d_params + ld.sig_b : nullptr;
+    ga.bias2 = ld.gate_b >= 0 ? d_params + ld.gate_b : nullptr;
+    ga.X = dz_plane;
+    if ((rc = launch_gemm_umma_layer(m, mx, mwc, mdv, ga, T, st))) return rc;
+    if (a.use_bias) {
+      const int ny = (int)std::max<int64_t>(1, std::min<int64_t>(rows / 256, 4 * m->sm_count));
+      k_colsum_bf16<<<dim3((D / 2 + 127) / 128, ny), 128, 0, st>>>(dv, rows, 2 * D, D, d_grads + ld.sig_b);
+      WN_LAUNCH_CHECK();
+      k_colsum_bf16<<<dim3((D / 2 + 127) / 128, ny), 128, 0, st>>>(dv + D, rows, 2 * D, D, d_grads + ld.gate_b);
+      WN_LAUNCH_CHECK();
+      if (has_next) {
+        k_colsum_bf16<<<dim3((R / 2 + 127) / 128, ny), 128, 0, st>>>(dx_next, rows, R, R, d_grads + ld.res_b);
+        WN_LAUNCH_CHECK();
+      }
+    }
+  }
+  {
+    ProfScope ps(PROF_LAYER_BWD_B, st);
+    CUtensorMap mdv, mwd, mdx;
+    if ((rc = map3(&mdv, dv, 2 * D, T, m->n_slots))) return rc;
+    if ((rc = map2d(&mwd, reinterpret_cast<const bf16*>(ws + wl.wdP) + (size_t)l * R * 4 * D, 4 * D, R, UKB, (uint32_t)R)))
+      return rc;
+    if ((rc = map3(&mdx, dx_out, R, T, m->n_slots))) return rc;
+    memset(&ga, 0, sizeof(ga));
+    ga.mode = 5; ga.K = 4 * D; ga.N = R;
+    ga.a_k_split = 2 * D; ga.a_row_off2 = ld.dil;
+    ga.X = dx_next;
+    ga.x_slot_rows = T; ga.x_row_off = 0;
+    if ((rc = launch_gemm_umma_layer(m, mdv, mwd, mdx, ga, T, st))) return rc;
+  }
+  return WN_OK;
 }
 
 }  // namespace wn
