@@ -83,7 +83,7 @@ int launch_layer_bwd_wide_umma(wn_model* m, const float* d_params, unsigned char
                                cudaStream_t st);
 bool umma_wgrad_x_supported(const wn_model* m, int T);
 int launch_wgrad_umma_x(wn_model* m, const bf16* xfull, int dil, int T, int tap, const bf16* Y, int ldy, int N,
-                        float* out, int ldo, cudaStream_t st);
+                        float* out, float* out2, int n_split, int ldo, int64_t tap_out_stride, cudaStream_t st);
 int launch_wgrad_umma_cols(wn_model* m, const bf16* A, int lda, int M_total, const bf16* Y, int N_total, int64_t rows,
                            float* out, int mode, float* grads, cudaStream_t st);
 int launch_prep_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st);
@@ -1303,11 +1303,18 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
         return rc;
       }
     }
+    if (wg_umma && 2 * d.D <= 256) {
+      // SIGNAL and GATE gradients of both taps in one launch (N = 2D with a split output, tap = blockIdx.x / m_tiles)
+      if ((rc = launch_wgrad_umma_x(m, la.xin, la.ld.dil, T, -1, dv, 2 * d.D, 2 * d.D, d_grads + la.ld.sig,
+                                    d_grads + la.ld.gate, d.D, d.D, (int64_t)d.R * d.D, st)))
+        return rc;
+    } else
     for (int tap = 0; tap < 2; ++tap) {
       for (int sg = 0; sg < 2; ++sg) {
         if (wg_umma) {
           if ((rc = launch_wgrad_umma_x(m, la.xin, la.ld.dil, T, tap, dv + sg * d.D, 2 * d.D, d.D,
-                                        d_grads + (sg ? la.ld.gate : la.ld.sig) + (int64_t)tap * d.R * d.D, d.D, st)))
+                                        d_grads + (sg ? la.ld.gate : la.ld.sig) + (int64_t)tap * d.R * d.D, nullptr, 0,
+                                        d.D, 0, st)))
             return rc;
           continue;
         }

@@ -828,6 +828,11 @@ struct GemmUmmaArgs {
   const float* bias2; // mode 4: GATE bias (bias = SIGNAL bias); both [D]
   const bf16* X;      // mode 5: the layer input x[t] for the residual add: X[(slot * x_slot_rows + x_row_off + t) * N + c]
   int x_slot_rows, x_row_off;
+  // modes 5 (3-D), 6: column sums of the OUTPUT tile, accumulated over the CTA's tiles (bias gradients): columns
+  // [0, colsum_split) -> colsum_out, the rest -> colsum_out2
+  float* colsum_out;
+  float* colsum_out2;
+  int colsum_split;
 };
 
 __global__ void __launch_bounds__(UPOST_P_THREADS, 1)
@@ -931,6 +936,8 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     uint32_t v[32];
     uint32_t pk[16];
     float acc_x = 0.f, acc_n = 0.f, acc_d = 0.f;
+    float cs_acc[2] = {0.f, 0.f};
+    const int et = e * 32 + lane;  // 0..255
     int item = 0;
     for (int i = 0; i < n_my; ++i) {
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
@@ -1041,6 +1048,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             }
             tma_store_commit();
           }
+          if (a.colsum_out != nullptr && a.tps > 0) tile_colsum_acc(otile, w, et, min(UM, a.T - t0), cs_acc);
         } else if (a.mode == 6) {
           // gate backward: recompute th, sg from the pre-activations; dz (skip + residual part) from the dz plane;
           // dv_s = dz sg (1 - th^2), dv_g = dz th sg (1 - sg) -> dv [.. x 2D] (SIGNAL | GATE)
@@ -1092,6 +1100,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               tma_store_3d(&map_out, otile + kb * UA_BYTES, kb * UKB, t0, sb);
             tma_store_commit();
           }
+          if (a.colsum_out != nullptr) tile_colsum_acc(otile, a.N, et, min(UM, a.T - t0), cs_acc);
         } else if (a.mode == 2) {
           // panels of PW = min(D, 64) columns (one swizzle span per row); a plane wider than 64 columns is two panels
           const int PW = min(a.D, 64), span = 2 * PW, panel_bytes = UM * span;
@@ -1192,6 +1201,14 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           }
           epi_bar_sync256();  // the partials of this tile are consumed before the next tile overwrites them
         }
+      }
+    }
+    if (a.colsum_out != nullptr && (a.mode == 6 || a.mode == 5) && 2 * (et >> 1) < a.N) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int col = 2 * (et >> 1) + q;
+        float* dst = col < a.colsum_split ? a.colsum_out + col : a.colsum_out2 + (col - a.colsum_split);
+        if (cs_acc[q] != 0.f) atomicAdd(dst, cs_acc[q]);
       }
     }
     if (a.mode == 3) {
@@ -1480,18 +1497,12 @@ int launch_layer_bwd_wide_umma(wn_model* m, const float* d_params, unsigned char
     ga.bias = ld.sig_b >= 0 ? d_params + ld.sig_b : nullptr;
     ga.bias2 = ld.gate_b >= 0 ? d_params + ld.gate_b : nullptr;
     ga.X = dz_plane;
-    if ((rc = launch_gemm_umma_layer(m, mx, mwc, mdv, ga, T, st))) return rc;
-    if (a.use_bias) {
-      const int ny = (int)std::max<int64_t>(1, std::min<int64_t>(rows / 256, 4 * m->sm_count));
-      k_colsum_bf16<<<dim3((D / 2 + 127) / 128, ny), 128, 0, st>>>(dv, rows, 2 * D, D, d_grads + ld.sig_b);
-      WN_LAUNCH_CHECK();
-      k_colsum_bf16<<<dim3((D / 2 + 127) / 128, ny), 128, 0, st>>>(dv + D, rows, 2 * D, D, d_grads + ld.gate_b);
-      WN_LAUNCH_CHECK();
-      if (has_next) {
-        k_colsum_bf16<<<dim3((R / 2 + 127) / 128, ny), 128, 0, st>>>(dx_next, rows, R, R, d_grads + ld.res_b);
-        WN_LAUNCH_CHECK();
-      }
+    if (a.use_bias) {  // SIGNAL_BIAS / GATE_BIAS gradients = column sums of dv, taken from the staged output tiles
+      ga.colsum_out = d_grads + ld.sig_b;
+      ga.colsum_out2 = d_grads + ld.gate_b;
+      ga.colsum_split = D;
     }
+    if ((rc = launch_gemm_umma_layer(m, mx, mwc, mdv, ga, T, st))) return rc;
   }
   {
     ProfScope ps(PROF_LAYER_BWD_B, st);
@@ -1505,6 +1516,11 @@ int launch_layer_bwd_wide_umma(wn_model* m, const float* d_params, unsigned char
     ga.a_k_split = 2 * D; ga.a_row_off2 = ld.dil;
     ga.X = dx_next;
     ga.x_slot_rows = T; ga.x_row_off = 0;
+    if (a.use_bias && l > 0) {  // RESIDUAL_BIAS gradient of the layer below = column sums of the dx_l produced here
+      ga.colsum_out = d_grads + m->layers[l - 1].res_b;
+      ga.colsum_out2 = ga.colsum_out;
+      ga.colsum_split = R;
+    }
     if ((rc = launch_gemm_umma_layer(m, mdv, mwd, mdx, ga, T, st))) return rc;
   }
   return WN_OK;
@@ -1534,10 +1550,20 @@ struct WgradUmmaArgs {
   int M_total, N;
   int a_col0;
   int out_col0;  // mode 1: first output column (N chunks of a wider gradient)
+  int n_taps, m_tiles;  // n_taps == 2: blockIdx.x / m_tiles is the conv tap: A rows shifted by tap * a_tap_row_off,
+  int a_tap_row_off;    // outputs by tap * tap_out_stride (both taps of a layer share Y = dv: one launch, half the splits)
+  int64_t tap_out_stride;
+  float* out2;         // mode 0 with n_split > 0: columns >= n_split go to out2[m * ldo + (n - n_split)]
+  int n_split;
   int a_T, a_row_off;  // a_T > 0: A is a layer input in the prefix layout [slot][dil + T][R] (3-D map): flat row r is
                        // (slot r / a_T, row r % a_T + a_row_off); a_T % 64 == 0 keeps a K block inside one slot
   int64_t kblocks_total, kblocks_per_cta;
 };
+
+// 16-byte vector reduction into global memory (sm_90+): one L2 operation for four fp32 adds
+__device__ __forceinline__ void red_add_v4(float* dst, float v0, float v1, float v2, float v3) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+}
 
 __global__ void __launch_bounds__(UPOST_THREADS, 1)
 k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_y, WgradUmmaArgs a) {
@@ -1548,7 +1574,11 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   __shared__ __align__(8) uint64_t full_bar[WG_STAGES], empty_bar[WG_STAGES], acc_full;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * 128;
+  const int tap = a.n_taps == 2 ? (int)blockIdx.x / a.m_tiles : 0;
+  const int m0 = (a.n_taps == 2 ? (int)blockIdx.x % a.m_tiles : (int)blockIdx.x) * 128;
+  const int a_row_off = a.a_row_off + tap * a.a_tap_row_off;
+  float* const out = a.out + tap * a.tap_out_stride;
+  float* const out2 = a.out2 != nullptr ? a.out2 + tap * a.tap_out_stride : nullptr;
   const int64_t kb0 = (int64_t)blockIdx.y * a.kblocks_per_cta;
   const int64_t kb1 = min(a.kblocks_total, kb0 + a.kblocks_per_cta);
   const int nkb = (int)max((int64_t)0, kb1 - kb0);
@@ -1583,7 +1613,7 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           for (int c = 0; c < 2; ++c) {
             if (a.a_T > 0)
               tma_load_3d(stage_a + st * WG_A_BYTES + c * WG_PANEL, &map_a, &full_bar[st], a.a_col0 + m0 + c * 64,
-                          row % a.a_T + a.a_row_off, row / a.a_T);
+                          row % a.a_T + a_row_off, row / a.a_T);
             else
               tma_load_2d(stage_a + st * WG_A_BYTES + c * WG_PANEL, &map_a, &full_bar[st], a.a_col0 + m0 + c * 64, row);
           }
@@ -1625,14 +1655,31 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           if (c0 + j < N) stg[r * lds + c0 + j] = __uint_as_float(v[j]);
       }
       epi_bar_sync();
-      for (int idx = et; idx < 128 * N; idx += 128) {
-        const int rr = idx / N, c = idx % N;
+      // four consecutive columns per thread: one 16-byte vector reduction when the destination allows it (a quarter of
+      // the L2 atomic operations: with 148 splits per output tile the kernel is bound by them, not by the GEMM)
+      for (int idx = et * 4; idx < 128 * N; idx += 128 * 4) {
+        const int rr = idx / N, c = idx % N;  // N % 16 == 0: the four columns stay inside the row
         const int m = m0 + rr;
         if (m < a.M_total) {
-          const float val = stg[rr * lds + c];
-          float* dst = a.mode == 0 ? a.out + (size_t)m * a.ldo + c
+          const float* sp = stg + rr * lds + c;
+          const float v0 = sp[0], v1 = sp[1], v2 = sp[2], v3 = sp[3];
+          const bool second = a.mode == 0 && a.n_split > 0 && c >= a.n_split;
+          float* dst = a.mode == 0 ? (second ? out2 + (size_t)m * a.ldo + (c - a.n_split) : out + (size_t)m * a.ldo + c)
                                    : a.grads + a.layers[m / a.D].skip + (size_t)(m % a.D) * a.ldo + a.out_col0 + c;
-          if (val != 0.f) atomicAdd(dst, val);
+          const bool same_dst = a.mode != 0 || a.n_split <= 0 || second || c + 3 < a.n_split;
+          if (same_dst && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            if (v0 != 0.f || v1 != 0.f || v2 != 0.f || v3 != 0.f) red_add_v4(dst, v0, v1, v2, v3);
+          } else {
+            const float vv[4] = {v0, v1, v2, v3};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int cj = c + j;
+              float* dj = a.mode == 0 && a.n_split > 0 && cj >= a.n_split ? out2 + (size_t)m * a.ldo + (cj - a.n_split)
+                          : a.mode == 0                                   ? out + (size_t)m * a.ldo + cj
+                                                                          : dst + j;
+              if (vv[j] != 0.f) atomicAdd(dj, vv[j]);
+            }
+          }
         }
       }
     }
@@ -1689,7 +1736,8 @@ static int launch_wgrad_umma_at(wn_model* m, const bf16* A, int lda, int a_col0,
 }
 
 // Weight gradients of one conv tap on the layers the fused tcgen05 backward does not cover (R, D multiples of 64):
-// dW[r][n] = sum_t x_tap[t][r] * dv[t][y_col0 + n], x read straight from the prefix layout xfull_l
+// dW[r][n] = sum_t x_tap[t][r] * dv[t][y_col0 + n], x read straight from the prefix layout xfull_l; tap < 0: both taps
+// in one launch (outputs of tap 1 at out + tap_out_stride)
 bool umma_wgrad_x_supported(const wn_model* m, int T) {
   static const bool disabled = getenv("WN_DISABLE_UMMA") != nullptr;
   const wn_arch& a = m->a;
@@ -1697,7 +1745,7 @@ bool umma_wgrad_x_supported(const wn_model* m, int T) {
 }
 
 int launch_wgrad_umma_x(wn_model* m, const bf16* xfull, int dil, int T, int tap, const bf16* Y, int ldy, int N,
-                        float* out, int ldo, cudaStream_t st) {
+                        float* out, float* out2, int n_split, int ldo, int64_t tap_out_stride, cudaStream_t st) {
   const int R = m->a.n_res;
   const int64_t rows = (int64_t)m->n_slots * T;
   CUtensorMap ma, my;
@@ -1712,9 +1760,12 @@ int launch_wgrad_umma_x(wn_model* m, const bf16* xfull, int dil, int T, int tap,
   WgradUmmaArgs wa;
   memset(&wa, 0, sizeof(wa));
   wa.out = out; wa.layers = m->d_layers; wa.mode = 0; wa.D = m->a.n_dil; wa.ldo = ldo;
-  wa.M_total = R; wa.N = N; wa.a_T = T; wa.a_row_off = tap ? dil : 0;
+  wa.M_total = R; wa.N = N; wa.a_T = T; wa.a_row_off = tap > 0 ? dil : 0;
+  wa.out2 = out2; wa.n_split = n_split;
   wa.kblocks_total = (rows + WG_BK - 1) / WG_BK;
-  const int m_tiles = (R + 127) / 128;
+  const int n_taps = tap < 0 ? 2 : 1;
+  const int m_tiles = (R + 127) / 128 * n_taps;
+  wa.n_taps = n_taps; wa.m_tiles = m_tiles / n_taps; wa.a_tap_row_off = dil; wa.tap_out_stride = tap_out_stride;
   const int sms = std::max(1, m->sm_count);
   int64_t splits = std::max<int64_t>(1, std::min<int64_t>(wa.kblocks_total, sms / m_tiles));
   wa.kblocks_per_cta = (wa.kblocks_total + splits - 1) / splits;
