@@ -164,9 +164,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-gen", action="store_true", help="skip the generation leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--slots", type=int, default=SLOTS_PER_GPU)
-    ap.add_argument("--slice", type=int, default=SLICE_SZ)
+    ap.add_argument("--slots", type=int, default=None)
+    ap.add_argument("--slice", type=int, default=None)
+    ap.add_argument("--workload", default="classic", choices=["classic", "wide"],
+                    help="classic = BASELINE.json configs[1] (the metric's configuration); wide = configs[4] "
+                         "(4x10, R=D=128, S=P=512, 8 slots/GPU x 32768): a second, non-headline line")
     args = ap.parse_args()
+    global ARCH_FILE
+    wide = args.workload == "wide"
+    if wide:
+        ARCH_FILE = os.path.join(ROOT, "par", "arch_wide_4x10.json")
+    args.slots = args.slots or (8 if wide else SLOTS_PER_GPU)
+    args.slice = args.slice or (32768 if wide else SLICE_SZ)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
     from lb_wavenet_b200 import config
@@ -178,9 +187,11 @@ def main():
         "metric": "train output timesteps/s", "unit": "timesteps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[1]: classic 3x10 (R=D=32,S=P=256), %d slots/GPU x slice_sz %d, "
-                               "one stage-wise training step (fwd+bwd+allreduce+Adam)" % (args.slots, args.slice),
-                   "arch_file": "par/arch_classic_3x10.json", "slots_per_gpu": args.slots, "slice_sz": args.slice,
+        "config": {"workload": ("BASELINE.json configs[4]: wide 4x10 (R=D=128,S=P=512)" if wide else
+                                "BASELINE.json configs[1]: classic 3x10 (R=D=32,S=P=256)") +
+                               ", %d slots/GPU x slice_sz %d, one stage-wise training step (fwd+bwd+allreduce+Adam), "
+                               "consecutive stages with carried SAVE state" % (args.slots, args.slice),
+                   "arch_file": "par/" + os.path.basename(ARCH_FILE), "slots_per_gpu": args.slots, "slice_sz": args.slice,
                    "global_slots": args.slots * args.gpus, "parallelism": "dp%d over slots" % args.gpus,
                    "l2_flush": "inputs and activation stash (>4 GB/step) far exceed the 126 MB L2"},
     }
@@ -353,6 +364,11 @@ def main():
         "post_bwd": post_fwd_flop_per_timestep(arch) * rows,       # dgrad chain: same contractions transposed
         "wgrad": train_flop_per_timestep(arch) / 3.0 * rows,          # every contraction once more
     }
+    if arch["n_res"] >= 64:  # wide layers run as plain tcgen05 GEMMs: tensor-bound (SURVEY 8d formula per contraction)
+        L_, R_, D_ = arch["n_blocks"] * arch["n_block_layers"], arch["n_res"], arch["n_dil"]
+        flop_by_cat.update({"layer_fwd": L_ * (8 * R_ * D_ + 2 * D_ * R_) * rows,        # conv taps + residual
+                            "layer_bwd": L_ * (8 * R_ * D_ + 2 * D_ * R_) * rows,        # recomputed conv + dz = dx.RESIDUAL^T
+                            "layer_bwd_data": L_ * (8 * R_ * D_) * rows})                # dx = dv.[W0^T|W1^T]
     roofline = None
     if dom is not None:
         dms = shares[dom]["ms_per_step"]

@@ -63,6 +63,28 @@ struct ProfGroup {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Launch with programmatic stream serialisation: the kernel may be scheduled before its predecessor in the stream has
+// drained (it blocks in pdl_wait()), which hides the ~4 us launch gap between the 60 per-layer launches of a step.
+inline bool pdl_enabled() {
+  static const bool on = getenv("WN_DISABLE_PDL") == nullptr;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
 // ---- optional in-kernel timeline (tools/trace_layer.py): CTA 0's role warps log (event, tile, clock64) ----
 extern int g_trace_layer;       // layer whose launches are traced (-1: all)
 extern long long* g_trace_buf;  // device buffer [32 warps][WN_TRACE_PER_WARP] or nullptr (set by wn_debug_trace)

@@ -1012,27 +1012,6 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
-// Launch with programmatic stream serialisation: the kernel may be scheduled before its predecessor in the stream has
-// drained (it blocks in pdl_wait()), which hides the ~4 us launch gap between the 60 per-layer launches of a step.
-static bool pdl_enabled() {
-  static const bool on = getenv("WN_DISABLE_PDL") == nullptr;
-  return on;
-}
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)block);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
-}
 static int map3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
                  int swizzle) {
   const uint64_t dims[3] = {d0, d1, d2};

@@ -833,17 +833,24 @@ struct GemmUmmaArgs {
   float* colsum_out;
   float* colsum_out2;
   int colsum_split;
+  // b_resident: the whole B operand (N <= 256, K * N * 2 bytes) is loaded into shared memory once per CTA and only A
+  // goes through the ring (a_stages deep).  Re-streaming B from L2 for every 128-row tile is what bounds the ring
+  // version when B is larger than the A tile (wide layers: 128 KB of conv weights against a 64 KB activation tile).
+  int b_resident, a_stages;
 };
+constexpr int GEMM_MAX_STAGES = 8;
 
 __global__ void __launch_bounds__(UPOST_P_THREADS, 1)
 k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_out, GemmUmmaArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* stage_a = smem;                                   // GEMM_STAGES x 16 KB
-  unsigned char* stage_b = smem + GEMM_STAGES * UA_BYTES;          // GEMM_STAGES x 32 KB
-  unsigned char* otile = stage_b + GEMM_STAGES * UB_BYTES;         // 64 KB staging tile
-  __shared__ __align__(8) uint64_t full_bar[GEMM_STAGES], empty_bar[GEMM_STAGES], acc_full[2], acc_empty[2];
+  const int nst = a.b_resident ? a.a_stages : GEMM_STAGES;
+  const int b_blk = a.b_resident ? min(256, a.N) * 128 : UB_BYTES;  // bytes of one K block of B
+  unsigned char* stage_a = smem;                                   // nst x 16 KB
+  unsigned char* stage_b = smem + nst * UA_BYTES;                  // ring: GEMM_STAGES x 32 KB; resident: K / 64 blocks
+  unsigned char* otile = stage_b + (a.b_resident ? (a.K / UKB) * b_blk : GEMM_STAGES * UB_BYTES);  // staging tile
+  __shared__ __align__(8) uint64_t full_bar[GEMM_MAX_STAGES], empty_bar[GEMM_MAX_STAGES], acc_full[2], acc_empty[2], b_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[512];
   __shared__ float x_mx[2][128], x_sum[2][128], x_vl[2][128];
@@ -853,6 +860,24 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int nchunk = (a.N + 255) / 256, nkb = a.K / UKB;
   const int box_n = min(256, a.N);  // rows of B one TMA box brings (a partial last chunk is zero filled)
+  pdl_launch_dependents();  // the next launch of the chain may set up as soon as this CTA releases its resources
+  if (tid == 0) {
+    for (int i = 0; i < GEMM_MAX_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 256);
+    }
+    mbar_init(&b_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_out);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  pdl_wait();  // everything below reads or writes global memory the previous kernels of the stream own
   if (a.mode == 4 || a.mode == 6) {  // SIGNAL_BIAS | 0.5 * GATE_BIAS (the GATE filter copy is pre-scaled by 0.5: sigmoid via tanh)
     const int Dh = a.N / 2;
     for (int i = tid; i < 512; i += UPOST_P_THREADS)
@@ -861,21 +886,6 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   } else {
     for (int i = tid; i < 512; i += UPOST_P_THREADS) bias_s[i] = (a.bias != nullptr && i < a.N) ? a.bias[i] : 0.f;
   }
-  if (tid == 0) {
-    for (int i = 0; i < GEMM_STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 256);
-    }
-    fence_mbar_init();
-    tma_prefetch_desc(&map_a);
-    tma_prefetch_desc(&map_b);
-    tma_prefetch_desc(&map_out);
-  }
-  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -883,16 +893,20 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   if (warp == 0) {
     if (lane == 0) {
-      int it = 0;
+      if (a.b_resident && n_my > 0) {  // the weights do not depend on the previous kernel's output: no need to order
+        mbar_expect_tx(&b_full, (uint32_t)(nkb * b_blk));
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(stage_b + kb * b_blk, &map_b, &b_full, kb * UKB, 0);
+      }
+      int st = 0;
+      uint32_t ph = 1;
       for (int i = 0; i < n_my; ++i) {
         const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         const int row0 = tile * UM;
         const int sb = a.tps > 0 ? tile / a.tps : 0, t0 = a.tps > 0 ? (tile % a.tps) * UM : 0;
         for (int c = 0; c < nchunk; ++c)
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const int st = it % GEMM_STAGES;
-            mbar_wait(&empty_bar[st], ((uint32_t)(it / GEMM_STAGES) & 1u) ^ 1u);
-            mbar_expect_tx(&full_bar[st], (uint32_t)(UA_BYTES + box_n * 128));
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty_bar[st], ph);
+            mbar_expect_tx(&full_bar[st], (uint32_t)(UA_BYTES + (a.b_resident ? 0 : box_n * 128)));
             if (a.tps > 0) {
               int k0 = kb * UKB, roff = 0;
               if (a.a_k_split > 0 && k0 >= a.a_k_split) { k0 -= a.a_k_split; roff = a.a_row_off2; }
@@ -900,13 +914,16 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             } else {
               tma_load_2d(stage_a + st * UA_BYTES, &map_a, &full_bar[st], kb * UKB, row0);
             }
-            tma_load_2d(stage_b + st * UB_BYTES, &map_b, &full_bar[st], kb * UKB, c * 256);
+            if (!a.b_resident) tma_load_2d(stage_b + st * UB_BYTES, &map_b, &full_bar[st], kb * UKB, c * 256);
+            if (++st == nst) { st = 0; ph ^= 1u; }
           }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      int it = 0, item = 0;
+      int item = 0, st = 0;
+      uint32_t ph = 0;
+      if (a.b_resident && n_my > 0) mbar_wait(&b_full, 0);
       for (int i = 0; i < n_my; ++i)
         for (int c = 0; c < nchunk; ++c, ++item) {
           const int buf = item & 1;
@@ -915,15 +932,16 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           mbar_wait(&acc_empty[buf], ((uint32_t)(item >> 1) & 1u) ^ 1u);
           tc_fence_after_sync();
           const uint32_t acc = tmem_base + (uint32_t)buf * 256;
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const int st = it % GEMM_STAGES;
-            mbar_wait(&full_bar[st], (uint32_t)(it / GEMM_STAGES) & 1u);
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full_bar[st], ph);
             tc_fence_after_sync();
-            const uint32_t sa = smem_u32(stage_a + st * UA_BYTES), sb = smem_u32(stage_b + st * UB_BYTES);
+            const uint32_t sa = smem_u32(stage_a + st * UA_BYTES),
+                           sb = smem_u32(a.b_resident ? stage_b + kb * b_blk : stage_b + st * UB_BYTES);
 #pragma unroll
             for (int k = 0; k < UKB / 16; ++k)
               mma_bf16_ss(acc, make_kmajor_desc(sa, 128, k * 32), make_kmajor_desc(sb, 128, k * 32), idesc, (kb | k) != 0);
             mma_commit(&empty_bar[st]);
+            if (++st == nst) { st = 0; ph ^= 1u; }
           }
           mma_commit(&acc_full[buf]);
         }
@@ -1253,6 +1271,24 @@ bool umma_post_chain_supported(const wn_model* m) {
          (a.n_dil == 16 || a.n_dil == 32 || a.n_dil == 64 || a.n_dil == 128);
 }
 
+// shared-memory plan of k_gemm_umma: resident B when it, the staging tile and >= 3 A stages fit (WN_GEMM_NO_RESIDENT=1:
+// always the ring)
+static size_t gemm_smem_plan(GemmUmmaArgs& ga) {
+  static const bool off = getenv("WN_GEMM_NO_RESIDENT") != nullptr;
+  ga.b_resident = 0;
+  ga.a_stages = GEMM_STAGES;
+  const size_t ring = (size_t)GEMM_STAGES * (UA_BYTES + UB_BYTES) + UH_BYTES + 1024;
+  if (off || ga.N > 256 || ga.K % UKB != 0) return ring;
+  const size_t b_bytes = (size_t)(ga.K / UKB) * std::min(256, ga.N) * 128;
+  const size_t o_bytes = (size_t)UM * (ga.mode == 4 ? ga.N / 2 : ga.N) * 2;
+  const size_t budget = 220 * 1024;
+  if (1024 + b_bytes + o_bytes + 3 * (size_t)UA_BYTES > budget) return ring;
+  const int stages = (int)std::min<size_t>(GEMM_MAX_STAGES, (budget - 1024 - b_bytes - o_bytes) / UA_BYTES);
+  ga.b_resident = 1;
+  ga.a_stages = stages;
+  return 1024 + (size_t)stages * UA_BYTES + b_bytes + o_bytes;
+}
+
 static int launch_gemm_umma(wn_model* m, const void* A, int K, const void* B, int N, void* out, int64_t rows,
                             GemmUmmaArgs ga, cudaStream_t st) {
   CUtensorMap ma, mb, mo;
@@ -1269,12 +1305,12 @@ static int launch_gemm_umma(wn_model* m, const void* A, int K, const void* B, in
     if ((rc = map2d(&mo, out, (uint64_t)N, (uint64_t)rows, UKB, UM))) return rc;
   }
   ga.rows = rows; ga.K = K; ga.N = N;
-  const size_t smem = (size_t)GEMM_STAGES * (UA_BYTES + UB_BYTES) + UH_BYTES + 1024;
-  WN_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = gemm_smem_plan(ga);
+  WN_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   const int n_tiles = (int)((rows + UM - 1) / UM);
   int grid = std::max(1, std::min(n_tiles, m->sm_count));
   if (const char* e = getenv("WN_PERSIST_GRID")) if (atoi(e) > 0) grid = std::max(1, std::min(grid, atoi(e)));
-  k_gemm_umma<<<grid, UPOST_P_THREADS, smem, st>>>(ma, mb, mo, ga);
+  WN_CUDA_CHECK(launch_pdl(k_gemm_umma, grid, UPOST_P_THREADS, smem, st, ma, mb, mo, ga));
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
@@ -1409,12 +1445,12 @@ static int launch_gemm_umma_layer(wn_model* m, const CUtensorMap& ma, const CUte
   ga.rows = (int64_t)m->n_slots * T;
   ga.T = T;
   ga.tps = (T + UM - 1) / UM;
-  const size_t smem = (size_t)GEMM_STAGES * (UA_BYTES + UB_BYTES) + UH_BYTES + 1024;
-  WN_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = gemm_smem_plan(ga);
+  WN_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   const int n_tiles = ga.tps * m->n_slots;
   int grid = std::max(1, std::min(n_tiles, m->sm_count));
   if (const char* e = getenv("WN_PERSIST_GRID")) if (atoi(e) > 0) grid = std::max(1, std::min(grid, atoi(e)));
-  k_gemm_umma<<<grid, UPOST_P_THREADS, smem, st>>>(ma, mb, mo, ga);
+  WN_CUDA_CHECK(launch_pdl(k_gemm_umma, grid, UPOST_P_THREADS, smem, st, ma, mb, mo, ga));
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
@@ -1586,6 +1622,7 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   uint32_t ncols = 32;
   while (ncols < (uint32_t)N) ncols <<= 1;
 
+  pdl_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < WG_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -1597,6 +1634,7 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     tma_prefetch_desc(&map_y);
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+  pdl_wait();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -1730,7 +1768,7 @@ static int launch_wgrad_umma_at(wn_model* m, const bf16* A, int lda, int a_col0,
   const size_t smem = (size_t)WG_STAGES * (WG_A_BYTES + WG_B_BYTES) + 1024;
   WN_CUDA_CHECK(cudaFuncSetAttribute(k_wgrad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps(PROF_WGRAD, st);
-  k_wgrad_umma<<<dim3(m_tiles, (unsigned)splits), UPOST_THREADS, smem, st>>>(ma, my, wa);
+  WN_CUDA_CHECK(launch_pdl(k_wgrad_umma, dim3(m_tiles, (unsigned)splits), UPOST_THREADS, smem, st, ma, my, wa));
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
@@ -1773,7 +1811,7 @@ int launch_wgrad_umma_x(wn_model* m, const bf16* xfull, int dil, int T, int tap,
   const size_t smem = (size_t)WG_STAGES * (WG_A_BYTES + WG_B_BYTES) + 1024;
   WN_CUDA_CHECK(cudaFuncSetAttribute(k_wgrad_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps(PROF_WGRAD, st);
-  k_wgrad_umma<<<dim3(m_tiles, (unsigned)splits), UPOST_THREADS, smem, st>>>(ma, my, wa);
+  WN_CUDA_CHECK(launch_pdl(k_wgrad_umma, dim3(m_tiles, (unsigned)splits), UPOST_THREADS, smem, st, ma, my, wa));
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
