@@ -837,6 +837,7 @@ struct GemmUmmaArgs {
   // goes through the ring (a_stages deep).  Re-streaming B from L2 for every 128-row tile is what bounds the ring
   // version when B is larger than the A tile (wide layers: 128 KB of conv weights against a 64 KB activation tile).
   int b_resident, a_stages;
+  int l2_prefetch;  // producer prefetches the next tile's A blocks into L2 (3-D maps only)
 };
 constexpr int GEMM_MAX_STAGES = 8;
 
@@ -899,10 +900,24 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       }
       int st = 0;
       uint32_t ph = 1;
+      // L2 prefetch of the next tile's A blocks (per-layer launches): with B resident only a_stages x 16 KB of A are in
+      // flight per SM, too little to cover DRAM latency; the ring then reads at L2 latency
+      auto prefetch_tile = [&](int i_tile) {
+        const int tile2 = (int)blockIdx.x + i_tile * (int)gridDim.x;
+        const int sb2 = tile2 / a.tps, t02 = (tile2 % a.tps) * UM;
+        for (int kb = 0; kb < nkb; ++kb) {
+          int k0 = kb * UKB, roff = 0;
+          if (a.a_k_split > 0 && k0 >= a.a_k_split) { k0 -= a.a_k_split; roff = a.a_row_off2; }
+          tma_prefetch_l2_3d(&map_a, a.a_col0 + k0, t02 + roff, sb2);
+        }
+      };
+      const bool pf = a.l2_prefetch && a.tps > 0;
+      if (pf && n_my > 1) prefetch_tile(1);
       for (int i = 0; i < n_my; ++i) {
         const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         const int row0 = tile * UM;
         const int sb = a.tps > 0 ? tile / a.tps : 0, t0 = a.tps > 0 ? (tile % a.tps) * UM : 0;
+        if (pf && i >= 1 && i + 1 < n_my) prefetch_tile(i + 1);
         for (int c = 0; c < nchunk; ++c)
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&empty_bar[st], ph);
@@ -956,6 +971,42 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     float acc_x = 0.f, acc_n = 0.f, acc_d = 0.f;
     float cs_acc[2] = {0.f, 0.f};
     const int et = e * 32 + lane;  // 0..255
+    // Modes 5 and 6 add a per-row global operand (x[t] / the dz plane) in the epilogue.  Loading it after the accumulator
+    // is ready exposes one DRAM latency per 32-column step (ncu: the 128 x 128 residual GEMM took longer than the
+    // 128 x 256 x 256 conv GEMM).  When this thread's slice of the row is <= 64 columns it is prefetched into xq one
+    // tile ahead: the loads of tile i + 1 are issued right after tile i's TMEM reads and fly during its store phase.
+    const int x_span = a.mode == 5 ? a.N / 2 : a.mode == 6 ? a.N / 4 : 0;  // columns of the row this thread consumes
+    const bool x_pre = a.X != nullptr && nchunk == 1 && x_span > 0 && x_span <= 64;
+    uint32_t xq[32];
+    auto load_xq = [&](int i_tile) {
+      const int tile2 = (int)blockIdx.x + i_tile * (int)gridDim.x;
+      const int sb2 = a.tps > 0 ? tile2 / a.tps : 0, t02 = a.tps > 0 ? (tile2 % a.tps) * UM : 0;
+      const bf16* src;
+      bool ok;
+      if (a.mode == 5) {
+        ok = a.tps > 0 ? t02 + r < a.T : (int64_t)tile2 * UM + r < a.rows;
+        src = (a.tps > 0 ? a.X + ((size_t)sb2 * a.x_slot_rows + a.x_row_off + t02 + r) * a.N
+                         : a.X + ((size_t)tile2 * UM + r) * a.N) + half * x_span;
+      } else {
+        ok = t02 + r < a.T;
+        src = a.X + ((size_t)sb2 * a.T + t02 + r) * (a.N / 2) + half * x_span;
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (ok && u * 32 < x_span) {
+          const uint4* x4 = reinterpret_cast<const uint4*>(src + u * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 t4 = __ldg(x4 + q);
+            xq[16 * u + 4 * q] = t4.x; xq[16 * u + 4 * q + 1] = t4.y; xq[16 * u + 4 * q + 2] = t4.z; xq[16 * u + 4 * q + 3] = t4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xq[16 * u + j] = 0u;
+        }
+      }
+    };
+    if (x_pre && n_my > 0) load_xq(0);
     int item = 0;
     for (int i = 0; i < n_my; ++i) {
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
@@ -1038,7 +1089,11 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
             tmem_ld_wait();
             uint32_t xw[16];
-            if (row_ok) {
+            if (x_pre) {
+              const bool second = c0 != cb;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) xw[j] = second ? xq[16 + j] : xq[j];
+            } else if (row_ok) {
               const uint4* x4 = reinterpret_cast<const uint4*>(xrow + c0);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -1055,6 +1110,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                                   __uint_as_float(v[2 * j + 1]) + __uint_as_float(xw[j] & 0xffff0000u) + bias_s[c0 + 2 * j + 1]);
             htile_store32(otile, r, c0, pk);
           }
+          if (x_pre && i + 1 < n_my) load_xq(i + 1);
           tc_fence_before_sync();
           mbar_arrive(&acc_empty[buf]);
           fence_proxy_async_smem();
@@ -1079,7 +1135,11 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             tmem_ld_32x32b_x32(acc + (uint32_t)(half * Dn + Dh + c0), g);
             const int ch = half * Dh + c0;
             uint32_t dzw[16];
-            if (row_ok) {
+            if (x_pre) {
+              const bool second = c0 != 0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) dzw[j] = second ? xq[16 + j] : xq[j];
+            } else if (row_ok) {
               const uint4* d4 = reinterpret_cast<const uint4*>(dzrow + ch);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -1109,6 +1169,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             htile_store32(otile, r, ch, pk);
             htile_store32(otile, r, Dn + ch, pg);
           }
+          if (x_pre && i + 1 < n_my) load_xq(i + 1);
           tc_fence_before_sync();
           mbar_arrive(&acc_empty[buf]);
           fence_proxy_async_smem();
@@ -1284,8 +1345,10 @@ static size_t gemm_smem_plan(GemmUmmaArgs& ga) {
   const size_t budget = 220 * 1024;
   if (1024 + b_bytes + o_bytes + 3 * (size_t)UA_BYTES > budget) return ring;
   const int stages = (int)std::min<size_t>(GEMM_MAX_STAGES, (budget - 1024 - b_bytes - o_bytes) / UA_BYTES);
+  static const bool no_pf = getenv("WN_GEMM_NO_PREFETCH") != nullptr;
   ga.b_resident = 1;
   ga.a_stages = stages;
+  ga.l2_prefetch = !no_pf && stages < 6;
   return 1024 + (size_t)stages * UA_BYTES + b_bytes + o_bytes;
 }
 

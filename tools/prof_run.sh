@@ -5,6 +5,8 @@ TAG=${1:-prof}
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 3 --no-gen --no-cpu"
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench exit $?"
+python bench.py --workload wide --steps 20 --no-gen --no-cpu > gpurun_out/${TAG}_bench_wide.json 2> gpurun_out/${TAG}_bench_wide.err; echo "bench wide exit $?"
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; echo "bench reference exit $?"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1; echo "ncu list exit $?"
 ncu --set full --clock-control none --import-source on -k regex:"k_post_fwd_umma|k_post_bwd_umma|k_wgrad_umma" -s 5 -c 5 -o gpurun_out/${TAG}_post $CMD > gpurun_out/${TAG}_ncu2.log 2>&1; echo "ncu post exit $?"
