@@ -45,7 +45,7 @@ def _run_fwd(arch, B, T, seed, scale=1.0):
 @pytest.mark.parametrize("arch,B,T", [
     (util.TINY, 3, 96), (util.TINY, 2, 7), (util.TINY_GC, 2, 130), (util.TINY_ASYM, 2, 64),
     (util.TINY_NOBIAS, 2, 64), (util.WIDE, 1, 70), (util.CLASSIC, 2, 300), (util.CLASSIC_SHALLOW, 3, 200),
-    (util.C1, 2, 160), (util.CLASSIC_SHALLOW, 2, 1000),
+    (util.C1, 2, 160), (util.CLASSIC_SHALLOW, 2, 1000), (util.WIDE_DEEP, 1, 1088),
 ])
 def test_forward_matches_oracle(lib, arch, B, T):
     a, p, wav, ids, eng, logits = _run_fwd(arch, B, T, 3)
@@ -108,7 +108,8 @@ def test_stagewise_equals_whole(lib):
 @pytest.mark.parametrize("arch,B,T", [(util.TINY, 3, 96), (util.TINY_GC, 2, 130), (util.TINY_ASYM, 2, 64),
                                       (util.WIDE, 1, 70), (util.WIDE, 2, 128), (util.CLASSIC, 2, 300),
                                       (util.CLASSIC_SHALLOW, 3, 200),
-                                      (util.TINY_NOBIAS, 2, 64), (util.C1, 2, 160), (util.CLASSIC_SHALLOW, 2, 1000)])
+                                      (util.TINY_NOBIAS, 2, 64), (util.C1, 2, 160), (util.CLASSIC_SHALLOW, 2, 1000),
+                                      (util.WIDE_DEEP, 1, 1088)])
 def test_gradients_match_oracle(lib, arch, B, T):
     a, p, wav, ids, eng, logits = _run_fwd(arch, B, T, 11)
     eng.backward()
@@ -316,3 +317,64 @@ def test_minimal_and_tile_boundary_shapes(lib, B, T):
     assert np.abs(lg - em.logits.numpy()).max() <= 0.05
     assert abs(st["xent_sum"] - float(L.xent_sum)) <= 2e-3 * max(1.0, abs(float(L.xent_sum)))
     assert torch.isfinite(eng.grads).all()
+
+
+FULL_CLASSIC = dict(util.CLASSIC)                                  # BASELINE configs[1]: 3x10, 32 slots x 16384
+FULL_WIDE = dict(util.WIDE, n_blocks=4, n_block_layers=10)          # BASELINE configs[4]: 4x10, R = D = 128 (8 slots x 8192 here)
+
+
+@pytest.mark.parametrize("arch,B,T", [(FULL_CLASSIC, 32, 16384), (FULL_WIDE, 8, 8192)], ids=["configs1", "configs4"])
+def test_full_size_properties(lib, arch, B, T):
+    """BASELINE.json's full sizes, where the CPU oracle would take hours: size-independent properties instead.
+    (1) reference README.md:16-21: two half stages from the saved D-separation state == one whole stage (logits to
+        1e-4 -- the same bf16 arithmetic, tiles only shifted -- and the SAVE rows bit for bit);
+    (2) the mask rule is per position: n_valid and the cross-entropy sum add up over the two stages;
+    (3) slots are independent: the unnormalised gradient of the batch == the sum of the gradients of its
+        two halves (this is what the multi-GPU slot sharding relies on), to fp32 summation-order noise."""
+    a = util.oracle_arch(arch)
+    p = util.scaled_params(a, B, 41)
+    wav, ids = util.synth_batch(B, T, 3, 42)
+    dw, di = torch.as_tensor(wav).cuda(), torch.as_tensor(ids).cuda()
+    eng = _engine(arch, B)
+    eng.load_state(p)
+    whole = eng.forward(dw, di, want_logits=True).clone()
+    st_whole = eng.read_stats()
+    eng.backward()
+    g_whole = eng.grads.clone()
+    assert torch.isfinite(whole).all() and torch.isfinite(g_whole).all() and st_whole["n_valid"] > 0
+
+    eng2 = _engine(arch, B)
+    eng2.load_state(p)
+    h = T // 2
+    n_valid, xent = 0, 0.0
+    for t0 in (0, h):
+        lg = eng2.forward(dw[:, t0:t0 + h].contiguous(), di[:, t0:t0 + h].contiguous(), want_logits=True)
+        assert float((lg - whole[:, t0:t0 + h]).abs().max()) <= 1e-4
+        st = eng2.read_stats()
+        n_valid += st["n_valid"]
+        xent += st["xent_sum"]
+    for l in range(len(eng.reg.saves)):
+        assert torch.equal(eng.save_view(l), eng2.save_view(l))
+    # the whole stage has no target for its first position only; the second half stage additionally has none for ITS
+    # first position (tmodel.py:230-231), which is valid or not by the same mask rule
+    assert 0 <= st_whole["n_valid"] - n_valid <= B
+    assert abs(st_whole["xent_sum"] - xent) <= 1e-3 * st_whole["xent_sum"] + 8.0 * B
+    del eng2, whole
+
+    g_sum = torch.zeros_like(g_whole)
+    hb = B // 2
+    for b0 in (0, hb):
+        e = _engine(arch, hb)
+        sub = {k: (v[b0:b0 + hb] if k.startswith("SAVE") or "save" in k.lower() else v) for k, v in p.items()}
+        e.load_state(sub)
+        e.forward(dw[b0:b0 + hb].contiguous(), di[b0:b0 + hb].contiguous())
+        e.backward()
+        g_sum += e.grads
+        del e
+    for name in eng.reg.params:
+        gw, gs = eng.view(name, g_whole), eng.view(name, g_sum)
+        scale = float(gw.abs().max())
+        if scale == 0:
+            assert float(gs.abs().max()) == 0, name
+            continue
+        assert float((gw - gs).abs().max()) <= 2e-3 * scale, (name, float((gw - gs).abs().max()), scale)

@@ -12,6 +12,7 @@ TINY_ASYM = dict(n_blocks=1, n_block_layers=5, n_quant=256, n_res=16, n_dil=48, 
 TINY_NOBIAS = dict(TINY, use_bias=0)
 WIDE = dict(n_blocks=1, n_block_layers=3, n_quant=256, n_res=128, n_dil=128, n_skip=512, n_post=512,
             n_gc_embed=0, n_gc_category=0, use_bias=1)
+WIDE_DEEP = dict(WIDE, n_block_layers=10)  # dilations 1..512 through the wide-layer GEMM kernels
 CLASSIC = dict(n_blocks=3, n_block_layers=10, n_quant=256, n_res=32, n_dil=32, n_skip=256, n_post=256,
                n_gc_embed=0, n_gc_category=0, use_bias=1)
 CLASSIC_SHALLOW = dict(CLASSIC, n_blocks=1, n_block_layers=4)
