@@ -138,7 +138,10 @@ def test_gradients_match_oracle(lib, arch, B, T):
     # a 30-layer stack amplifies every 1-ulp bf16 flip of the residual stream chaotically: there the
     # kernel is as far from the same-rounding oracle as that oracle is from fp64 (measured ~9% median)
     deep = a.n_layers >= 16
-    bad = {k: v for k, v in vs_em.items() if v > (0.3 if deep else 6e-2)}
+    # the wide-layer GEMM path keeps dz as a bf16 plane and adds the residual branch to it in place (one more bf16
+    # rounding per layer than the emulated oracle has): 10 wide layers measured 3.1 % median, 5.6 % max
+    wide_stack = arch["n_res"] >= 64 and a.n_layers >= 8
+    bad = {k: v for k, v in vs_em.items() if v > (0.3 if deep else 0.1 if wide_stack else 6e-2)}
     assert not bad, ("vs emulated oracle", bad)
     bad = {k: v for k, v in vs_ex.items() if v > (0.35 if deep else 0.2)}
     assert not bad, ("vs fp64 oracle", bad)
