@@ -1345,10 +1345,10 @@ static size_t gemm_smem_plan(GemmUmmaArgs& ga) {
   const size_t budget = 220 * 1024;
   if (1024 + b_bytes + o_bytes + 3 * (size_t)UA_BYTES > budget) return ring;
   const int stages = (int)std::min<size_t>(GEMM_MAX_STAGES, (budget - 1024 - b_bytes - o_bytes) / UA_BYTES);
-  static const bool no_pf = getenv("WN_GEMM_NO_PREFETCH") != nullptr;
+  static const bool pf = getenv("WN_GEMM_PREFETCH") != nullptr;  // measured: no gain (7.58 vs 7.53 ms wide step), off by default
   ga.b_resident = 1;
   ga.a_stages = stages;
-  ga.l2_prefetch = !no_pf && stages < 6;
+  ga.l2_prefetch = pf && stages < 6;
   return 1024 + (size_t)stages * UA_BYTES + b_bytes + o_bytes;
 }
 
