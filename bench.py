@@ -426,6 +426,18 @@ def main():
                            "steps": GEN_STEPS, "us_per_step": gms * 1e3 / GEN_STEPS,
                            "realtime_multiple_per_stream": sps / GEN_STREAMS / 16000.0,
                            "ring_gbs": sps * ring_bytes / 1e9, "gpu_launches": int(lib.wn_launch_count_reset())}
+            # the step time is set by one SM streaming the stack's weights: more streams only
+            # occupy more SMs, so throughput grows with the batch until all 148 are busy
+            del g
+            g4 = GenEngine(net._arch_dict, 4 * GEN_STREAMS, str(dev))
+            g4.load_params(net.engine.params)
+            g4.run(20, seed=0)
+            torch.cuda.synchronize()
+            e0.record()
+            g4.run(GEN_STEPS // 2, seed=0)
+            e1.record()
+            torch.cuda.synchronize()
+            line["gen"]["at_%d_streams" % (4 * GEN_STREAMS)] = 4 * GEN_STREAMS * (GEN_STEPS // 2) / (e0.elapsed_time(e1) * 1e-3)
         except Exception as e:  # the training line must survive a generator failure
             line["gen"] = {"error": repr(e)}
 

@@ -1072,6 +1072,16 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
   const bool umma_chain = !umma_post && umma_post_chain_supported(m);
   const bool umma_layer = umma_layer_supported(m);
   const bool umma_wide = !umma_layer && umma_wide_layer_supported(m);
+  if (!(umma_layer || umma_wide) || !(umma_post || umma_chain) || (umma_wide && !umma_wgrad_x_supported(m, T))) {
+    // still the device path, but 10-20x slower than the tcgen05 kernels: say so once instead of silently
+    static bool noted = false;
+    if (!noted && getenv("WN_DISABLE_UMMA") == nullptr) {
+      noted = true;
+      fprintf(stderr, "libwavenet_b200: n_res=%d n_dil=%d n_skip=%d n_post=%d slice_sz=%d runs (partly) on the generation-1 "
+                      "HMMA kernels; the tcgen05 kernels cover n_res = n_dil = 32 or multiples of 64 (then slice_sz %% 64 == 0), "
+                      "n_skip / n_post multiples of 64 up to 512\n", d.R, d.D, d.S, d.P, T);
+    }
+  }
   {
   ProfScope ps_prep(PROF_PREP, st);
   k_cast_params<<<(unsigned)((m->n_param_elems + 255) / 256), 256, 0, st>>>(d_params, wbf, m->n_param_elems);
