@@ -29,8 +29,10 @@ constexpr int GS = 16;            // streams per CTA
 constexpr int R = 32, D = 32, S = 256, P = 256, Q = 256;
 constexpr int NCW = 8;            // compute warps
 constexpr int THREADS = (NCW + 1) * 32;
-constexpr int SLOT = 16384;       // weight ring slot
+constexpr int SLOT = 27 * 1024;    // weight ring slot: one layer item (conv | residual | biases | SKIP_l) or one post-net chunk
 constexpr int NSLOT = 5;
+constexpr int OLD_W = 8;           // rolling window of prefetched x[t-dil] tiles (one per layer position)
+constexpr int OLD_LA = 6;          // ... issued this many layer positions ahead
 // fragment-ready block: [n-tile][k-step][lane][2 x u32]  (256 B per (n-tile, k-step))
 constexpr int CONV_BYTES = 8 * 4 * 256;   // N = 64 (signal | gate), K = 64 (x[t-dil] | x[t])
 constexpr int RES_BYTES = 4 * 2 * 256;    // N = 32, K = 32
@@ -169,6 +171,18 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending_dyn(int n) {  // at most n (0..5) most recent groups still pending
+  switch (n) {
+    case 0: cp_async_wait_pending<0>(); break;
+    case 1: cp_async_wait_pending<1>(); break;
+    case 2: cp_async_wait_pending<2>(); break;
+    case 3: cp_async_wait_pending<3>(); break;
+    case 4: cp_async_wait_pending<4>(); break;
+    default: cp_async_wait_pending<5>(); break;
+  }
+}
 
 struct Gen2Args {
   const unsigned char* blob;
@@ -183,21 +197,24 @@ struct Gen2Args {
   int64_t t0;
   uint64_t seed;
   int n_streams, n_steps, n_teacher, L;
+  long long* trace;  // wn_debug_trace buffer: CTA 0's warps log (event, layer, clock64) during the last step
 };
 
 __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
   using namespace g2;
   extern __shared__ __align__(1024) unsigned char sm[];
-  unsigned char* wring = sm;                                         // NSLOT x 16 KB
+  unsigned char* wring = sm;                                         // NSLOT x 27 KB
   bf16* x0tab = reinterpret_cast<bf16*>(sm + NSLOT * SLOT);          // [257][32]
   bf16* xbuf = x0tab + 257 * 32;                                     // [2][GS][XP]   current layer input (ping-pong)
   bf16* zbuf = xbuf + 2 * GS * XP;                                   // [GS][XP]
   bf16* hbuf = zbuf + GS * XP;                                       // [2][GS][HP]   h1 / h2
   float* lgbuf = reinterpret_cast<float*>(hbuf + 2 * GS * HP);       // [GS][Q]
-  bf16* oldbuf = reinterpret_cast<bf16*>(lgbuf + GS * Q);            // [2][L][GS][XP] prefetched x[t-dil]
-  float* bias3 = reinterpret_cast<float*>(oldbuf + 2 * a.L * GS * XP);  // [768]
+  bf16* oldbuf = reinterpret_cast<bf16*>(lgbuf + GS * Q);            // [OLD_W][GS][XP] prefetched x[t-dil] tiles
+  float* bias3 = reinterpret_cast<float*>(oldbuf + OLD_W * GS * XP);  // [768]
   __shared__ __align__(8) uint64_t full[NSLOT], empty[NSLOT];
   __shared__ int code_s[GS];
+  __shared__ int dil_s[64];
+  __shared__ int64_t roff_s[64];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s0 = blockIdx.x * GS;
   const int L = a.L;
@@ -213,30 +230,35 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
     reinterpret_cast<uint4*>(x0tab)[i] = reinterpret_cast<const uint4*>(a.blob + a.g.x0tab)[i];
   for (int i = tid; i < 768; i += THREADS) bias3[i] = reinterpret_cast<const float*>(a.blob + a.g.biases)[i];
   if (tid < GS) code_s[tid] = (s0 + tid < a.n_streams) ? a.codes[s0 + tid] : -1;
+  if (tid < L) {
+    dil_s[tid] = a.layers[tid].dil;
+    roff_s[tid] = a.ring_off[tid];
+  }
   __syncthreads();
 
-  const int items_per_step = 2 * L + 16;
+  const int items_per_step = L + 16;
   if (warp == NCW) {
     // ===== weight producer: same item sequence every timestep =====
+    // One item per layer (conv | residual | biases, then SKIP_l: two bulk copies into one slot) and 16 post-net chunks.
+    // (The in-kernel timeline showed ~290 cycles per wait / release pair on the per-sample chain: one pair per layer.)
     if (lane == 0) {
-      int64_t it = 0;
+      int slot = 0;
+      uint32_t ph = 1;
       for (int step = 0; step < a.n_steps; ++step) {
-        for (int j = 0; j < items_per_step; ++j, ++it) {
-          const int slot = (int)(it % NSLOT);
-          mbar_wait(&empty[slot], ((uint32_t)(it / NSLOT) & 1u) ^ 1u);
-          const unsigned char* src;
-          uint32_t bytes;
-          if (j < 2 * L) {
-            const int l = j >> 1;
-            if ((j & 1) == 0) { src = a.blob + a.g.layer_a + (size_t)l * LAYER_A_BYTES; bytes = LAYER_A_BYTES; }
-            else { src = a.blob + a.g.skip + (size_t)l * CHUNK_BYTES; bytes = CHUNK_BYTES; }
-          } else if (j < 2 * L + 8) {
-            src = a.blob + a.g.post1 + (size_t)(j - 2 * L) * CHUNK_BYTES; bytes = CHUNK_BYTES;
+        for (int j = 0; j < items_per_step; ++j) {
+          mbar_wait(&empty[slot], ph);
+          unsigned char* dst = wring + slot * SLOT;
+          if (j < L) {
+            mbar_expect_tx(&full[slot], LAYER_A_BYTES + CHUNK_BYTES);
+            bulk_g2s(dst, a.blob + a.g.layer_a + (size_t)j * LAYER_A_BYTES, LAYER_A_BYTES, &full[slot]);
+            bulk_g2s(dst + LAYER_A_BYTES, a.blob + a.g.skip + (size_t)j * CHUNK_BYTES, CHUNK_BYTES, &full[slot]);
           } else {
-            src = a.blob + a.g.post2 + (size_t)(j - 2 * L - 8) * CHUNK_BYTES; bytes = CHUNK_BYTES;
+            const unsigned char* src = j < L + 8 ? a.blob + a.g.post1 + (size_t)(j - L) * CHUNK_BYTES
+                                                 : a.blob + a.g.post2 + (size_t)(j - L - 8) * CHUNK_BYTES;
+            mbar_expect_tx(&full[slot], CHUNK_BYTES);
+            bulk_g2s(dst, src, CHUNK_BYTES, &full[slot]);
           }
-          mbar_expect_tx(&full[slot], bytes);
-          bulk_g2s(wring + slot * SLOT, src, bytes, &full[slot]);
+          if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
         }
       }
     }
@@ -244,47 +266,54 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
   }
 
   // ===== compute warps =====
+  Tracer tr;
+  tr.init(nullptr, warp, false);
   const int g = lane >> 2, t4 = lane & 3;
-  int64_t it = 0;  // weight-ring consumer position (same sequence as the producer)
+  int c_slot = 0;  // weight-ring consumer position (same sequence as the producer)
+  uint32_t c_ph = 0;
   auto slot_wait = [&]() -> const unsigned char* {
-    const int slot = (int)(it % NSLOT);
-    mbar_wait(&full[slot], (uint32_t)(it / NSLOT) & 1u);
-    return wring + slot * SLOT;
+    mbar_wait(&full[c_slot], c_ph);
+    return wring + c_slot * SLOT;
   };
   auto slot_release = [&]() {
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[(int)(it % NSLOT)]);
-    ++it;
+    if (lane == 0) mbar_arrive(&empty[c_slot]);
+    if (++c_slot == NSLOT) { c_slot = 0; c_ph ^= 1u; }
   };
-  // prefetch of x[t-dil] for timestep `ts` into oldbuf[pb]: layers with dil >= 2 read the HBM ring (the slot was
-  // written >= 1 timestep ago), dil == 1 layers are served from `prevx` kept in oldbuf by the layer itself
-  auto prefetch_old = [&](int64_t ts, int pb) {
-    for (int i = tid; i < L * GS * 4; i += NCW * 32) {  // 16-byte chunks: 4 per (layer, stream) row
-      const int ch = i & 3, s = (i >> 2) % GS, l = (i >> 2) / GS;
-      const int dil = a.layers[l].dil;
-      if (dil < 2 || s0 + s >= a.n_streams) continue;
-      const bf16* src = a.rings + a.ring_off[l] + ((int64_t)(s0 + s) * dil + (ts % dil)) * R + ch * 8;
-      cp_async16(oldbuf + ((size_t)(pb * L + l) * GS + s) * XP + ch * 8, src);
+  // x[t-dil] of every layer comes from its HBM ring buffer (length dil, slot t mod dil; dil = 2^k, dil == 1 included:
+  // the slot then holds the previous step's input).  Warps 4..7 prefetch it with cp.async `la` layer positions ahead
+  // (position p = step * L + l; the addresses depend on p only) into a rolling window of OLD_W tiles.  x_l[t] is
+  // stored at position (t, l) and read for (t + dil, l), whose prefetch is issued at (t + dil, l) - la > (t, l)
+  // because la = min(OLD_LA, L - 1) < L.  (A whole step ahead, as before, cost 77 KB of shared memory.)
+  const int la = max(1, min(OLD_LA, L - 1));
+  int pf_l = 0, pf_buf = 0;
+  int64_t pf_t = a.t0, pf_left = (int64_t)a.n_steps * L;
+  auto prefetch_next = [&]() {  // warps 4..7 only
+    if (pf_left > 0) {
+      const int q = tid - 4 * 32;
+      if (q < GS * 4) {
+        const int s = q >> 2, ch = q & 3, dil = dil_s[pf_l];
+        if (s0 + s < a.n_streams)
+          cp_async16(oldbuf + ((size_t)pf_buf * GS + s) * XP + ch * 8,
+                     a.rings + roff_s[pf_l] + ((int64_t)(s0 + s) * dil + (pf_t & (int64_t)(dil - 1))) * R + ch * 8);
+      }
+      if (++pf_l == L) { pf_l = 0; ++pf_t; }
+      pf_buf = (pf_buf + 1) & (OLD_W - 1);
+      --pf_left;
     }
     cp_async_commit();
   };
-  // initial state: previous inputs of dil == 1 layers come from their length-1 rings; first prefetch
-  for (int i = tid; i < L * GS * R; i += NCW * 32) {
-    const int r = i % R, s = (i / R) % GS, l = i / (R * GS);
-    if (a.layers[l].dil == 1) {
-      const bf16 v = (s0 + s < a.n_streams) ? a.rings[a.ring_off[l] + (int64_t)(s0 + s) * R + r] : f2bf(0.f);
-      oldbuf[((size_t)(0 * L + l) * GS + s) * XP + r] = v;
-    }
+  if (warp >= 4) {
+    for (int k = 0; k < la; ++k) prefetch_next();
+    cp_async_wait_pending_dyn(la - 1);  // position 0 has landed
   }
-  prefetch_old(a.t0, 0);
-  cp_async_wait_all();
   cbar();
+  int cur_buf = 0;  // window tile of the current layer position
 
   for (int step = 0; step < a.n_steps; ++step) {
     const int64_t t = a.t0 + step;
-    const int pb = step & 1;
-    // next step's ring reads are issued now (addresses depend on t only)
-    if (step + 1 < a.n_steps) prefetch_old(t + 1, pb ^ 1);
+    if (step == a.n_steps - 1) tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
+    tr.ev(20, 0);
     // input embedding (imodel.py:66-74): table row of the pending code; -1 -> all-zero vector -> bias only
     for (int i = tid; i < GS * 4; i += NCW * 32) {
       const int s = i >> 2, ch = i & 3;
@@ -300,11 +329,13 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
     cbar();
     int xb = 0;
     for (int l = 0; l < L; ++l) {
-      const int dil = a.layers[l].dil;
+      const int dil = dil_s[l];
       const bf16* xin = xbuf + xb * GS * XP;
       bf16* xout = xbuf + (xb ^ 1) * GS * XP;
-      const bf16* oldx = oldbuf + ((size_t)(pb * L + l) * GS) * XP;
+      const bf16* oldx = oldbuf + cur_buf * (GS * XP);
+      tr.ev(0, l);
       const unsigned char* wa = slot_wait();
+      tr.ev(1, l);
       const float* bias = reinterpret_cast<const float*>(wa + CONV_BYTES + RES_BYTES);
       if (warp < 4) {
         // conv + gate: this warp owns channels [8w, 8w+8): signal n-tile w, gate n-tile w + 4
@@ -317,6 +348,7 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
           mma16816(cs, af, bs.x, bs.y);
           mma16816(cg, af, bg.x, bg.y);
         }
+        tr.ev(2, l);
         const int c = warp * 8 + 2 * t4;
         const float bs0 = bias[c], bs1 = bias[c + 1], bg0 = bias[32 + c], bg1 = bias[32 + c + 1];
         const float z00 = tanh_fast(cs[0] + bs0) * sigmoid_fast(cg[0] + bg0);
@@ -326,20 +358,20 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
         *reinterpret_cast<uint32_t*>(zbuf + g * XP + c) = frag_pack(z00, z01);
         *reinterpret_cast<uint32_t*>(zbuf + (g + 8) * XP + c) = frag_pack(z10, z11);
       } else {
-        // meanwhile: ring <- x[t] (imodel.py:97).  dil >= 2: HBM ring slot t mod dil; dil == 1: next step's "old"
-        const int i = (warp - 4) * 32 + lane;  // 128 threads: 16 streams x 4 chunks of 16 B ... two passes
-        for (int q = i; q < GS * 4; q += 128) {
-          const int s = q >> 2, ch = q & 3;
+        // meanwhile: ring <- x[t] (imodel.py:97), slot t mod dil; then the read of a later position
+        const int i = (warp - 4) * 32 + lane;  // 128 threads: 16 streams x 4 chunks of 16 B
+        if (i < GS * 4) {
+          const int s = i >> 2, ch = i & 3;
           const uint4 v = *reinterpret_cast<const uint4*>(xin + s * XP + ch * 8);
-          if (dil >= 2) {
-            if (s0 + s < a.n_streams)
-              *reinterpret_cast<uint4*>(a.rings + a.ring_off[l] + ((int64_t)(s0 + s) * dil + (t % dil)) * R + ch * 8) = v;
-          } else {
-            *reinterpret_cast<uint4*>(oldbuf + ((size_t)((pb ^ 1) * L + l) * GS + s) * XP + ch * 8) = v;
-          }
+          if (s0 + s < a.n_streams)
+            *reinterpret_cast<uint4*>(a.rings + roff_s[l] + ((int64_t)(s0 + s) * dil + (t & (int64_t)(dil - 1))) * R + ch * 8) = v;
         }
+        prefetch_next();
+        cp_async_wait_pending_dyn(la - 1);  // the next position's tile has landed (visible after the barriers below)
       }
+      tr.ev(3, l);
       cbar();
+      tr.ev(4, l);
       {
         // residual (warps 0..3: n-tile w) and skip (every warp: n-tiles 4w..4w+3), A = z
         const unsigned char* wsk = nullptr;
@@ -362,8 +394,8 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
           *reinterpret_cast<uint32_t*>(xout + (g + 8) * XP + c) =
               frag_pack(__low2float(x_hi) + cr[2] + br0, __high2float(x_hi) + cr[3] + br1);
         }
-        slot_release();  // layer item A
-        wsk = slot_wait();
+        tr.ev(5, l);
+        wsk = wa + LAYER_A_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -372,11 +404,15 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
             mma16816(skip[j], af[ks], b.x, b.y);  // imodel.py:247 (bias added once, below)
           }
         }
+        tr.ev(7, l);
         slot_release();
       }
       cbar();
+      tr.ev(8, l);
       xb ^= 1;
+      cur_buf = (cur_buf + 1) & (OLD_W - 1);
     }
+    tr.ev(9, 0);
     // ---- post-net (imodel.py:140-164) ----
     bf16* h1 = hbuf;
     bf16* h2 = hbuf + GS * HP;
@@ -419,8 +455,10 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
       *reinterpret_cast<uint32_t*>(h2 + (g + 8) * HP + c) =
           frag_pack(fmaxf(acc[j][2] + bias3[256 + c], 0.f), fmaxf(acc[j][3] + bias3[256 + c + 1], 0.f));
     }
+    tr.ev(10, 0);
     cbar();
     dense256(h2);
+    tr.ev(11, 0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = (warp * 4 + j) * 8 + 2 * t4;
@@ -446,17 +484,12 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
         }
       }
     }
-    cp_async_wait_all();  // next step's x[t-dil] rows have landed
+    tr.ev(12, 0);
     cbar();
+    tr.ev(13, 0);
   }
-  // persist the state a later launch continues from: pending codes, previous inputs of the dil == 1 layers
+  // persist the state a later launch continues from: the pending codes (the rings already hold every x[t-dil])
   if (tid < GS && s0 + tid < a.n_streams) a.codes[s0 + tid] = code_s[tid];
-  const int pbn = a.n_steps & 1;
-  for (int i = tid; i < L * GS * R; i += NCW * 32) {
-    const int r = i % R, s = (i / R) % GS, l = i / (R * GS);
-    if (a.layers[l].dil == 1 && s0 + s < a.n_streams)
-      a.rings[a.ring_off[l] + (int64_t)(s0 + s) * R + r] = oldbuf[((size_t)(pbn * L + l) * GS + s) * XP + r];
-  }
 }
 
 // ---- host ------------------------------------------------------------------------------------------------
@@ -464,7 +497,7 @@ bool gen2_supported(const wn_model* m) {
   static const bool disabled = getenv("WN_DISABLE_GEN2") != nullptr;
   const wn_arch& a = m->a;
   return !disabled && a.n_res == 32 && a.n_dil == 32 && a.n_skip == 256 && a.n_post == 256 && a.n_quant == 256 &&
-         a.n_gc_embed == 0 && m->L <= 64;
+         a.n_gc_embed == 0 && m->L >= 2 && m->L <= 64;
 }
 int64_t gen2_blob_bytes(const wn_model* m) { return gen2_layout(m->L).total; }
 
@@ -484,9 +517,10 @@ int gen2_run(wn_model* m, const unsigned char* blob, const int64_t* ring_off, bf
   memset(&a, 0, sizeof(a));
   a.blob = blob; a.g = gen2_layout(m->L); a.layers = m->d_layers; a.ring_off = ring_off; a.rings = rings;
   a.codes = codes; a.teacher = teacher; a.n_teacher = teacher ? n_teacher : 0; a.out = out; a.logits_out = logits;
+  a.trace = g_trace_buf;
   a.t0 = t0; a.seed = seed; a.n_streams = n_streams; a.n_steps = n_steps; a.L = m->L;
   const size_t smem = (size_t)NSLOT * SLOT + 257 * 32 * 2 + (size_t)(2 * GS * XP + GS * XP + 2 * GS * HP) * 2 +
-                      (size_t)GS * Q * 4 + (size_t)2 * m->L * GS * XP * 2 + 768 * 4 + 1024;
+                      (size_t)GS * Q * 4 + (size_t)OLD_W * GS * XP * 2 + 768 * 4 + 1024;
   if (smem > 227 * 1024) {
     set_error("gen2_run: %zu bytes of shared memory needed", smem);
     return WN_ERR_UNSUPPORTED;
