@@ -269,16 +269,20 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
   Tracer tr;
   tr.init(nullptr, warp, false);
   const int g = lane >> 2, t4 = lane & 3;
-  int c_slot = 0;  // weight-ring consumer position (same sequence as the producer)
-  uint32_t c_ph = 0;
+  // weight-ring consumer positions (same item sequence as the producer).  Waits and releases advance separately:
+  // a layer's slot is held until its skip MMAs have run, which is during the NEXT layer (below)
+  int w_slot = 0, r_slot = 0;
+  uint32_t w_ph = 0;
   auto slot_wait = [&]() -> const unsigned char* {
-    mbar_wait(&full[c_slot], c_ph);
-    return wring + c_slot * SLOT;
+    mbar_wait(&full[w_slot], w_ph);
+    const unsigned char* p = wring + w_slot * SLOT;
+    if (++w_slot == NSLOT) { w_slot = 0; w_ph ^= 1u; }
+    return p;
   };
   auto slot_release = [&]() {
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[c_slot]);
-    if (++c_slot == NSLOT) { c_slot = 0; c_ph ^= 1u; }
+    if (lane == 0) mbar_arrive(&empty[r_slot]);
+    if (++r_slot == NSLOT) r_slot = 0;
   };
   // x[t-dil] of every layer comes from its HBM ring buffer (length dil, slot t mod dil; dil = 2^k, dil == 1 included:
   // the slot then holds the previous step's input).  Warps 4..7 prefetch it with cp.async `la` layer positions ahead
@@ -326,6 +330,21 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) skip[i][j] = 0.f;
+    // The skip MMAs of layer l (A = z_l, off the per-sample chain) are deferred into layer l + 1, where they fill the
+    // latency bubbles of the conv chain instead of sitting between the residual and the second barrier
+    uint32_t zf[2][4];                         // A fragments of the previous layer's z
+    const unsigned char* wsk_prev = nullptr;   // its SKIP weights (slot still held)
+    auto skip_mma = [&]() {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint2 b = ldb_frag(wsk_prev, warp * 4 + j, ks, 2, lane);
+          mma16816(skip[j], zf[ks], b.x, b.y);  // imodel.py:247 (bias added once, below)
+        }
+      }
+      slot_release();
+    };
     cbar();
     int xb = 0;
     for (int l = 0; l < L; ++l) {
@@ -339,22 +358,30 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
       const float* bias = reinterpret_cast<const float*>(wa + CONV_BYTES + RES_BYTES);
       if (warp < 4) {
         // conv + gate: this warp owns channels [8w, 8w+8): signal n-tile w, gate n-tile w + 4
+        // (the x[t-dil] and x[t] halves of K accumulate separately: two dependent MMAs deep instead of four)
         float cs[4] = {0.f, 0.f, 0.f, 0.f}, cg[4] = {0.f, 0.f, 0.f, 0.f};
+        float ds[4] = {0.f, 0.f, 0.f, 0.f}, dg[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t af[4];
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           lda_frag(af, ks < 2 ? oldx : xin, XP, (ks & 1) * 16, lane);
           const uint2 bs = ldb_frag(wa, warp, ks, 4, lane), bg = ldb_frag(wa, warp + 4, ks, 4, lane);
-          mma16816(cs, af, bs.x, bs.y);
-          mma16816(cg, af, bg.x, bg.y);
+          if (ks < 2) {
+            mma16816(cs, af, bs.x, bs.y);
+            mma16816(cg, af, bg.x, bg.y);
+          } else {
+            mma16816(ds, af, bs.x, bs.y);
+            mma16816(dg, af, bg.x, bg.y);
+          }
         }
+        if (l > 0) skip_mma();  // the previous layer's skip contribution, in the shadow of the conv chain
         tr.ev(2, l);
         const int c = warp * 8 + 2 * t4;
         const float bs0 = bias[c], bs1 = bias[c + 1], bg0 = bias[32 + c], bg1 = bias[32 + c + 1];
-        const float z00 = tanh_fast(cs[0] + bs0) * sigmoid_fast(cg[0] + bg0);
-        const float z01 = tanh_fast(cs[1] + bs1) * sigmoid_fast(cg[1] + bg1);
-        const float z10 = tanh_fast(cs[2] + bs0) * sigmoid_fast(cg[2] + bg0);
-        const float z11 = tanh_fast(cs[3] + bs1) * sigmoid_fast(cg[3] + bg1);
+        const float z00 = tanh_fast(cs[0] + ds[0] + bs0) * sigmoid_fast(cg[0] + dg[0] + bg0);
+        const float z01 = tanh_fast(cs[1] + ds[1] + bs1) * sigmoid_fast(cg[1] + dg[1] + bg1);
+        const float z10 = tanh_fast(cs[2] + ds[2] + bs0) * sigmoid_fast(cg[2] + dg[2] + bg0);
+        const float z11 = tanh_fast(cs[3] + ds[3] + bs1) * sigmoid_fast(cg[3] + dg[3] + bg1);
         *reinterpret_cast<uint32_t*>(zbuf + g * XP + c) = frag_pack(z00, z01);
         *reinterpret_cast<uint32_t*>(zbuf + (g + 8) * XP + c) = frag_pack(z10, z11);
       } else {
@@ -367,23 +394,22 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
             *reinterpret_cast<uint4*>(a.rings + roff_s[l] + ((int64_t)(s0 + s) * dil + (t & (int64_t)(dil - 1))) * R + ch * 8) = v;
         }
         prefetch_next();
+        if (l > 0) skip_mma();
         cp_async_wait_pending_dyn(la - 1);  // the next position's tile has landed (visible after the barriers below)
       }
       tr.ev(3, l);
       cbar();
       tr.ev(4, l);
       {
-        // residual (warps 0..3: n-tile w) and skip (every warp: n-tiles 4w..4w+3), A = z
-        const unsigned char* wsk = nullptr;
-        uint32_t af[2][4];
-        lda_frag(af[0], zbuf, XP, 0, lane);
-        lda_frag(af[1], zbuf, XP, 16, lane);
+        // residual (warps 0..3: n-tile w), A = z; the z fragments stay in registers for the deferred skip MMAs
+        lda_frag(zf[0], zbuf, XP, 0, lane);
+        lda_frag(zf[1], zbuf, XP, 16, lane);
         if (warp < 4 && l + 1 < L) {
           float cr[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
             const uint2 b = ldb_frag(wa + CONV_BYTES, warp, ks, 2, lane);
-            mma16816(cr, af[ks], b.x, b.y);
+            mma16816(cr, zf[ks], b.x, b.y);
           }
           const int c = warp * 8 + 2 * t4;
           const float br0 = bias[64 + c], br1 = bias[64 + c + 1];
@@ -395,23 +421,14 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
               frag_pack(__low2float(x_hi) + cr[2] + br0, __high2float(x_hi) + cr[3] + br1);
         }
         tr.ev(5, l);
-        wsk = wa + LAYER_A_BYTES;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint2 b = ldb_frag(wsk, warp * 4 + j, ks, 2, lane);
-            mma16816(skip[j], af[ks], b.x, b.y);  // imodel.py:247 (bias added once, below)
-          }
-        }
-        tr.ev(7, l);
-        slot_release();
+        wsk_prev = wa + LAYER_A_BYTES;
       }
       cbar();
       tr.ev(8, l);
       xb ^= 1;
       cur_buf = (cur_buf + 1) & (OLD_W - 1);
     }
+    skip_mma();  // the last layer's skip contribution
     tr.ev(9, 0);
     // ---- post-net (imodel.py:140-164) ----
     bf16* h1 = hbuf;
