@@ -485,17 +485,23 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
       lgbuf[(g + 8) * Q + c + 1] = acc[j][3] + bias3[512 + c + 1];
     }
     cbar();
-    // ---- sampling (imodel.py:167-187) + teacher forcing (imodel.py:260-267): warp w -> streams 2w, 2w+1 ----
+    // ---- sampling (imodel.py:167-187) + teacher forcing (imodel.py:260-267): warp w -> streams 2w, 2w+1, in lock step ----
+    {
+      const int sa = warp * 2, sb = warp * 2 + 1;
+      if (a.logits_out != nullptr) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int s = warp * 2 + k;
-      if (s0 + s < a.n_streams) {
-        if (a.logits_out != nullptr)
-          for (int q = lane; q < Q; q += 32)
-            a.logits_out[((int64_t)(s0 + s) * a.n_steps + step) * Q + q] = lgbuf[s * Q + q];
-        const float u = sampler_uniform(a.seed, (uint64_t)t, (uint32_t)(s0 + s));
-        const int samp = warp_sample(lgbuf + s * Q, u);
-        if (lane == 0) {
+        for (int k = 0; k < 2; ++k)
+          if (s0 + sa + k < a.n_streams)
+            for (int q = lane; q < Q; q += 32)
+              a.logits_out[((int64_t)(s0 + sa + k) * a.n_steps + step) * Q + q] = lgbuf[(sa + k) * Q + q];
+      }
+      const float ua = sampler_uniform(a.seed, (uint64_t)t, (uint32_t)(s0 + sa));
+      const float ub = sampler_uniform(a.seed, (uint64_t)t, (uint32_t)(s0 + sb));
+      int ra, rb;
+      warp_sample2(lgbuf + sa * Q, lgbuf + sb * Q, ua, ub, ra, rb);
+      if (lane < 2) {
+        const int s = sa + lane, samp = lane == 0 ? ra : rb;
+        if (s0 + s < a.n_streams) {
           a.out[(int64_t)(s0 + s) * a.n_steps + step] = samp;
           code_s[s] = (t < a.n_teacher) ? a.teacher[t] : samp;
         }

@@ -76,5 +76,71 @@ __device__ __forceinline__ int warp_sample(const float* lg, float u) {
   return min(cnt, 255);
 }
 
+// two rows in lock step (the generator's warps own two streams each): the same arithmetic per row, so the result is
+// bit-identical to two warp_sample calls; the two dependency chains (running sums, scans, shuffles) overlap
+__device__ __forceinline__ void warp_sample2(const float* lg0, const float* lg1, float u0, float u1, int& r0, int& r1) {
+  const int lane = threadIdx.x & 31;
+  const float* lg[2] = {lg0, lg1};
+  const float u[2] = {u0, u1};
+  float v[2][8], mx[2], s[2][8], incl[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(lg[k] + lane * 8);
+    const float4 b = *reinterpret_cast<const float4*>(lg[k] + lane * 8 + 4);
+    v[k][0] = a.x; v[k][1] = a.y; v[k][2] = a.z; v[k][3] = a.w;
+    v[k][4] = b.x; v[k][5] = b.y; v[k][6] = b.z; v[k][7] = b.w;
+    mx[k] = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx[k] = fmaxf(mx[k], v[k][j]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx[0] = fmaxf(mx[0], __shfl_xor_sync(0xffffffffu, mx[0], o));
+    mx[1] = fmaxf(mx[1], __shfl_xor_sync(0xffffffffu, mx[1], o));
+  }
+  float e[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    e[0][j] = det_exp(__fsub_rn(v[0][j], mx[0]));
+    e[1][j] = det_exp(__fsub_rn(v[1][j], mx[1]));
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    float run = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      run = __fadd_rn(run, e[k][j]);
+      s[k][j] = run;
+    }
+    incl[k] = run;
+  }
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float o0 = __shfl_up_sync(0xffffffffu, incl[0], d);
+    const float o1 = __shfl_up_sync(0xffffffffu, incl[1], d);
+    if (lane >= d) {
+      incl[0] = __fadd_rn(incl[0], o0);
+      incl[1] = __fadd_rn(incl[1], o1);
+    }
+  }
+  int cnt[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    float excl = __shfl_up_sync(0xffffffffu, incl[k], 1);
+    if (lane == 0) excl = 0.f;
+    const float total = __shfl_sync(0xffffffffu, incl[k], 31);
+    const float thr = __fmul_rn(u[k], total);
+    cnt[k] = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cnt[k] += (__fadd_rn(excl, s[k][j]) <= thr) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt[0] += __shfl_xor_sync(0xffffffffu, cnt[0], o);
+    cnt[1] += __shfl_xor_sync(0xffffffffu, cnt[1], o);
+  }
+  r0 = min(cnt[0], 255);
+  r1 = min(cnt[1], 255);
+}
 
 }  // namespace wn
