@@ -500,7 +500,7 @@ struct LayerBwdFusedArgs {
 };
 
 template <int R, int D, bool GC>
-__global__ void __launch_bounds__(864, 1)
+__global__ void __launch_bounds__(896, 1)
 k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz,
                        const __grid_constant__ CUtensorMap map_yn, const __grid_constant__ CUtensorMap map_pn,
                        const __grid_constant__ CUtensorMap map_yo, const __grid_constant__ CUtensorMap map_po,
@@ -618,8 +618,11 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 1 || warp == 27) {
+    // ===== MMA issuers: warp 1 serves queue A, warp 27 queue B.  One thread spends ~100 cycles per tcgen05.mma it issues
+    // (descriptor arithmetic, the instruction itself, polling) against ~50 cycles of tensor-pipe time: a single issuer was
+    // busy 2400 of the 3150 cycles a tile takes.  tcgen05.commit tracks the issuing thread's own MMAs, and the two queues
+    // write disjoint accumulators, so they only meet through the mbarriers they already used. =====
     if (lane == 0) {
       mbar_wait(&w_full, 0);
       const uint32_t idv = make_idesc_bf16(128, 2 * D), idd = make_idesc_bf16(128, D);
@@ -660,31 +663,33 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
           mma_bf16_ss2(tm + ACC_W, sm + k * 64, HI, wm + k * 64, HI, idw, (i | k) != 0);
         mma_commit(&p_full[ab]);
       };
-      // two queues served in whatever order their inputs become ready; B first: its completion returns stages
-      int na = 0, nb = 0;
       uint32_t spins = 0;
-      while (nb < n_my) {
-        bool did = false;
-        if (nb < na && mbar_test_wait(&dv_ready[nb & 1], (uint32_t)(nb >> 1) & 1u) &&
-            mbar_test_wait(&acc2_free[nb & 1], ((uint32_t)(nb >> 1) & 1u) ^ 1u)) {
-          tc_fence_after_sync();
-          tr.ev(4, nb);
-          issue_b(nb++);
-          tr.ev(17, nb - 1);
-          did = true;
+      if (warp == 27) {
+        for (int nb = 0; nb < n_my;) {
+          // tile nb's dv tile is written after its v_full, i.e. after queue A issued tile nb
+          if (mbar_test_wait(&dv_ready[nb & 1], (uint32_t)(nb >> 1) & 1u) &&
+              mbar_test_wait(&acc2_free[nb & 1], ((uint32_t)(nb >> 1) & 1u) ^ 1u)) {
+            tc_fence_after_sync();
+            tr.ev(4, nb);
+            issue_b(nb++);
+            tr.ev(17, nb - 1);
+            spins = 0;
+          } else if (++spins > (1u << 26)) __trap();
         }
-        if (na < n_my && mbar_test_wait(&in_full[na % NST], (uint32_t)(na / NST) & 1u) &&
-            mbar_test_wait(&dx_ready[na % NST], (uint32_t)(na / NST) & 1u) &&
-            mbar_test_wait(&acc1_free[na & 1], ((uint32_t)(na >> 1) & 1u) ^ 1u)) {
-          tc_fence_after_sync();
-          tr.ev(3, na);
-          issue_a(na++);
-          tr.ev(16, na - 1);
-          did = true;
+        mma_commit(&g_full);
+      } else {
+        for (int na = 0; na < n_my;) {
+          if (mbar_test_wait(&in_full[na % NST], (uint32_t)(na / NST) & 1u) &&
+              mbar_test_wait(&dx_ready[na % NST], (uint32_t)(na / NST) & 1u) &&
+              mbar_test_wait(&acc1_free[na & 1], ((uint32_t)(na >> 1) & 1u) ^ 1u)) {
+            tc_fence_after_sync();
+            tr.ev(3, na);
+            issue_a(na++);
+            tr.ev(16, na - 1);
+            spins = 0;
+          } else if (++spins > (1u << 26)) __trap();
         }
-        if (did) spins = 0; else if (++spins > (1u << 26)) __trap();
       }
-      mma_commit(&g_full);
     }
   } else if (warp < 18) {
     // ===== E1: gate backward, two groups of 8 warps that alternate tiles (group g owns tiles g, g+2, ... and with them
@@ -1169,11 +1174,11 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
     ga.C1 = C1;
     ga.T = T;
     WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_umma<32, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_umma<32, 32, true>, grid, 864, smem, st, mp->x[l], mp->dz, mp->dx[nx],
+    WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_umma<32, 32, true>, grid, 896, smem, st, mp->x[l], mp->dz, mp->dx[nx],
                              mp->p0[nx], mp->dx[cu], mp->p0[cu], mp->wc, mp->wrn, ga));
   } else {
     WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_umma<32, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_umma<32, 32, false>, grid, 864, smem, st, mp->x[l], mp->dz, mp->dx[nx],
+    WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_umma<32, 32, false>, grid, 896, smem, st, mp->x[l], mp->dz, mp->dx[nx],
                              mp->p0[nx], mp->dx[cu], mp->p0[cu], mp->wc, mp->wrn, ga));
   }
   WN_LAUNCH_CHECK();
