@@ -103,6 +103,12 @@ class WaveNetTrain(ar.WaveNetArch):
             torch = self.engine.torch
             self._comm_stream = torch.cuda.Stream() if self.dist.world > 1 else None
             self._gstats = torch.zeros(_lib.WN_NSTATS, dtype=torch.float64, device=self.engine.device)
+            # the step's statistics are final right after the loss kernel (+ their all-reduce): they are copied to
+            # pinned host memory on a side stream while the backward runs, so the blocking loss read of
+            # sess.run([apply_grads_op, loss_op]) does not leave the GPU idle between steps
+            self._host_stats = torch.zeros(_lib.WN_NSTATS, dtype=torch.float64).pin_memory()
+            self._rb_stream = self._comm_stream if self._comm_stream is not None else torch.cuda.Stream()
+            self._rb_event = torch.cuda.Event()
         return self.engine
 
     def _make_variable(self, name, shape, arch, trainable):
@@ -233,24 +239,36 @@ class WaveNetTrain(ar.WaveNetArch):
             wav = codes
         return wav.to(torch.int32), ids.to(torch.int32)
 
-    def forward_backward(self, wav, ids):
+    def forward_backward(self, wav, ids, want_loss: bool = False):
         """Forward + backward (+ data-parallel reduction).  Leaves the global statistics in
-        self._gstats and the summed unnormalised gradients in engine.grads."""
+        self._gstats and the summed unnormalised gradients in engine.grads.  want_loss: also evaluate the L2 term (on the
+        weights the loss is computed with, as tmodel.py:250-261 does) and start the device -> host copy of the
+        statistics as soon as they are final; _finish_step waits for it."""
         eng = self._ensure_engine()
         torch = eng.torch
         wav, ids = self._prepare_inputs(wav, ids)
         eng.forward(wav, ids)
+        if want_loss:
+            eng.l2_loss()
         self._gstats.copy_(eng.stats)
         L = eng.reg.n_layers
-        if self.dist.world == 1:
-            eng.backward()
-            return
         cur = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(cur)
+        if self.dist.world == 1:
+            if want_loss:
+                with torch.cuda.stream(self._rb_stream):
+                    self._rb_stream.wait_event(ev)
+                    self._host_stats.copy_(self._gstats, non_blocking=True)
+                    self._rb_event.record(self._rb_stream)
+            eng.backward()
+            return
         with torch.cuda.stream(self._comm_stream):
             self._comm_stream.wait_event(ev)
             self.dist.all_reduce_sum_(self._gstats[:3])  # xent_sum, n_valid, diff_sum (tmodel.py:244-249)
+            if want_loss:
+                self._host_stats.copy_(self._gstats, non_blocking=True)
+                self._rb_event.record(self._comm_stream)
         phase = 0
         for phase_end, ranges in self._plan:
             _lib.check(eng.lib.wn_train_backward_phases(
@@ -274,7 +292,7 @@ class WaveNetTrain(ar.WaveNetArch):
         eng = self._ensure_engine()
         if getattr(self, "_optimizer", None) is not optimizer:
             self.bind_optimizer(optimizer)  # its slots become (optional) checkpoint keys
-        self.forward_backward(wav, ids)
+        self.forward_backward(wav, ids, want_loss)
         optimizer.t += 1
         eng.adam(optimizer.t, optimizer.learning_rate, self.l2_factor, n_valid=self._gstats[1:2],
                  beta1=optimizer.beta1, beta2=optimizer.beta2, eps=optimizer.epsilon)
@@ -284,14 +302,8 @@ class WaveNetTrain(ar.WaveNetArch):
         return self._finish_step(wav)
 
     def _finish_step(self, wav):
-        eng = self.engine
-        need_l2 = True
-        if need_l2:
-            # the reference evaluates the L2 term on the weights the loss was computed with; the
-            # optimiser has already moved them, so this is the post-update value (log line only)
-            eng.l2_loss()
-            self._gstats[3:4].copy_(eng.stats[3:4])
-        s = self._gstats.cpu().numpy()  # device -> host read of the step's result
+        self._rb_event.synchronize()  # device -> host read of the step's result (copy enqueued by forward_backward)
+        s = self._host_stats.numpy().copy()
         xent_sum, n_valid, diff_sum, l2 = float(s[0]), int(round(s[1])), int(round(s[2])), float(s[3])
         mean_xent = xent_sum / n_valid if n_valid != 0 else 0.0  # tmodel.py:246-249
         total = mean_xent + self.l2_factor * l2  # tmodel.py:261
