@@ -138,9 +138,18 @@ class SlotDealer:
         wav = np.empty((nl, T), np.int32) if wav_out is None else wav_out
         ids = np.empty((nl, T), np.int32) if ids_out is None else ids_out
         bound = self.F - 1  # data.py:133
+        cur_file, cur_pos, cur_len = self._cur_file, self._cur_pos, self._cur_len
         for slot in range(self.batch_sz):
             local = self.slot_lo <= slot < self.slot_hi
             filled = 0
+            if not local:  # another rank's slot: replay the cursor arithmetic only
+                while filled < T:
+                    if cur_file[slot] < 0 or cur_pos[slot] >= cur_len[slot]:
+                        self._pull(slot)
+                    take = min(T - filled, cur_len[slot] - cur_pos[slot])
+                    cur_pos[slot] += take
+                    filled += take
+                continue
             while filled < T:
                 if self._cur_file[slot] < 0 or self._cur_pos[slot] >= self._cur_len[slot]:
                     self._pull(slot)
@@ -310,6 +319,12 @@ class MaskedSliceWav(ckpt.Checkpoint):
         else:
             self._hostbuf = [(np.empty((self._n_local, self.slice_sz), np.int32),
                               np.empty((self._n_local, self.slice_sz), np.int32)) for _ in range(n)]
+        # The dealer replays the shared file stream for ALL global slots in Python (only lengths for the slots of other
+        # ranks), ~2 ms of interpreter time per batch at 256 slots.  With CPython's default 5 ms switch interval the
+        # training thread can wait that long for the GIL while the GPU runs dry; 0.2 ms bounds the wait.
+        import sys
+        if sys.getswitchinterval() > 2e-4:
+            sys.setswitchinterval(2e-4)
         self._worker = threading.Thread(target=self._produce, name="wav-loader", daemon=True)
         self._worker.start()
 
