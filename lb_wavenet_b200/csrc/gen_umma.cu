@@ -40,6 +40,7 @@ constexpr int LAYER_A_BYTES = CONV_BYTES + RES_BYTES + 512;  // + biases: sig[32
 constexpr int CHUNK_BYTES = 32 * 2 * 256; // N = 256, two k-steps (K = 32): SKIP_l, or a K-slice of POST1 / POST2
 constexpr int XP = 40;            // padded row (bf16 elements) of the 32-wide activation tiles
 constexpr int HP = 264;           // padded row of the 256-wide activation tiles
+constexpr int LP = 264;           // padded row (floats) of the logits tile: rows g, g + 1 land in different banks
 }  // namespace g2
 
 struct Gen2Layout {  // byte offsets inside the generation-2 weight blob (device memory)
@@ -208,8 +209,8 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
   bf16* xbuf = x0tab + 257 * 32;                                     // [2][GS][XP]   current layer input (ping-pong)
   bf16* zbuf = xbuf + 2 * GS * XP;                                   // [GS][XP]
   bf16* hbuf = zbuf + GS * XP;                                       // [2][GS][HP]   h1 / h2
-  float* lgbuf = reinterpret_cast<float*>(hbuf + 2 * GS * HP);       // [GS][Q]
-  bf16* oldbuf = reinterpret_cast<bf16*>(lgbuf + GS * Q);            // [OLD_W][GS][XP] prefetched x[t-dil] tiles
+  float* lgbuf = reinterpret_cast<float*>(hbuf + 2 * GS * HP);       // [GS][LP]
+  bf16* oldbuf = reinterpret_cast<bf16*>(lgbuf + GS * LP);            // [OLD_W][GS][XP] prefetched x[t-dil] tiles
   float* bias3 = reinterpret_cast<float*>(oldbuf + OLD_W * GS * XP);  // [768]
   __shared__ __align__(8) uint64_t full[NSLOT], empty[NSLOT];
   __shared__ int code_s[GS];
@@ -318,6 +319,9 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
     const int64_t t = a.t0 + step;
     if (step == a.n_steps - 1) tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
     tr.ev(20, 0);
+    // the sampler's uniforms depend on (seed, t, stream) only: computed here, off the tail of the step
+    const float ua = sampler_uniform(a.seed, (uint64_t)t, (uint32_t)(s0 + warp * 2));
+    const float ub = sampler_uniform(a.seed, (uint64_t)t, (uint32_t)(s0 + warp * 2 + 1));
     // input embedding (imodel.py:66-74): table row of the pending code; -1 -> all-zero vector -> bias only
     for (int i = tid; i < GS * 4; i += NCW * 32) {
       const int s = i >> 2, ch = i & 3;
@@ -479,10 +483,8 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = (warp * 4 + j) * 8 + 2 * t4;
-      lgbuf[g * Q + c] = acc[j][0] + bias3[512 + c];
-      lgbuf[g * Q + c + 1] = acc[j][1] + bias3[512 + c + 1];
-      lgbuf[(g + 8) * Q + c] = acc[j][2] + bias3[512 + c];
-      lgbuf[(g + 8) * Q + c + 1] = acc[j][3] + bias3[512 + c + 1];
+      *reinterpret_cast<float2*>(lgbuf + g * LP + c) = make_float2(acc[j][0] + bias3[512 + c], acc[j][1] + bias3[512 + c + 1]);
+      *reinterpret_cast<float2*>(lgbuf + (g + 8) * LP + c) = make_float2(acc[j][2] + bias3[512 + c], acc[j][3] + bias3[512 + c + 1]);
     }
     cbar();
     // ---- sampling (imodel.py:167-187) + teacher forcing (imodel.py:260-267): warp w -> streams 2w, 2w+1, in lock step ----
@@ -493,12 +495,10 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
         for (int k = 0; k < 2; ++k)
           if (s0 + sa + k < a.n_streams)
             for (int q = lane; q < Q; q += 32)
-              a.logits_out[((int64_t)(s0 + sa + k) * a.n_steps + step) * Q + q] = lgbuf[(sa + k) * Q + q];
+              a.logits_out[((int64_t)(s0 + sa + k) * a.n_steps + step) * Q + q] = lgbuf[(sa + k) * LP + q];
       }
-      const float ua = sampler_uniform(a.seed, (uint64_t)t, (uint32_t)(s0 + sa));
-      const float ub = sampler_uniform(a.seed, (uint64_t)t, (uint32_t)(s0 + sb));
       int ra, rb;
-      warp_sample2(lgbuf + sa * Q, lgbuf + sb * Q, ua, ub, ra, rb);
+      warp_sample2(lgbuf + sa * LP, lgbuf + sb * LP, ua, ub, ra, rb);
       if (lane < 2) {
         const int s = sa + lane, samp = lane == 0 ? ra : rb;
         if (s0 + s < a.n_streams) {
@@ -543,7 +543,7 @@ int gen2_run(wn_model* m, const unsigned char* blob, const int64_t* ring_off, bf
   a.trace = g_trace_buf;
   a.t0 = t0; a.seed = seed; a.n_streams = n_streams; a.n_steps = n_steps; a.L = m->L;
   const size_t smem = (size_t)NSLOT * SLOT + 257 * 32 * 2 + (size_t)(2 * GS * XP + GS * XP + 2 * GS * HP) * 2 +
-                      (size_t)GS * Q * 4 + (size_t)OLD_W * GS * XP * 2 + 768 * 4 + 1024;
+                      (size_t)GS * LP * 4 + (size_t)OLD_W * GS * XP * 2 + 768 * 4 + 1024;
   if (smem > 227 * 1024) {
     set_error("gen2_run: %zu bytes of shared memory needed", smem);
     return WN_ERR_UNSUPPORTED;
