@@ -33,7 +33,7 @@ ARCH_FILE = os.path.join(ROOT, "par", "arch_classic_3x10.json")
 SLOTS_PER_GPU = 32
 SLICE_SZ = 16384
 GEN_STREAMS = 256
-GEN_STEPS = 1000
+GEN_STEPS = 160000   # BASELINE configs[3]: 10 s at 16 kHz per stream
 
 
 def train_flop_per_timestep(a) -> float:
@@ -156,6 +156,107 @@ def cpu_reference_run(arch, steps, warmup, n_threads=None):
                        "(TensorFlow 1.x not installable)" % (B, T, steps), B=B, T=T)
 
 
+def gen_leg(arch, params, n_streams, n_steps, dev, lib, workload, gc_ids=None, e2e=True):
+    """Batched incremental generation: `value` = streams x steps / device time of ONE persistent launch (CUDA events);
+    `e2e` = the same through the host call including the device -> host copy of the sampled codes (wall clock around
+    run + .cpu()).  Roofline per SURVEY 8(d): ring-buffer bytes per stream-step = L * 2 * R * 2 (read x[t-dil], write
+    x[t], bf16) against the measured HBM copy peak -- the path is latency-bound (L dependent layer hops per sample), so
+    us_per_step is the figure that matters."""
+    import torch
+    from lb_wavenet_b200.engine import GenEngine
+    g = GenEngine(arch, n_streams, dev)
+    g.load_params(params, gc_ids)
+    g.run(50, seed=0)
+    torch.cuda.synchronize()
+    lib.wn_launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    codes = g.run(n_steps, seed=0)
+    e1.record()
+    torch.cuda.synchronize()
+    gms = e0.elapsed_time(e1)
+    launches = int(lib.wn_launch_count_reset())
+    sps = n_streams * n_steps / (gms * 1e-3)
+    L = arch["n_blocks"] * arch["n_block_layers"]
+    ring_bytes = L * 2 * arch["n_res"] * 2
+    hbm_peak = 6650.0
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        with open(pk) as f:
+            hbm_peak = json.load(f)["hbm_gbs"]
+    out = {"metric": "batched gen audio samples/s", "value": sps, "unit": "samples/s", "streams": n_streams,
+           "steps": n_steps, "us_per_step": gms * 1e3 / n_steps, "realtime_multiple_per_stream": sps / n_streams / 16000.0,
+           "gpu_launches": launches, "workload": workload,
+           "roofline": {"bound": "hbm", "achieved": sps * ring_bytes / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": sps * ring_bytes / 1e9 / hbm_peak, "traffic": None,
+                        "algorithmic_bytes_per_stream_step": ring_bytes,
+                        "note": "latency-bound chain of L dependent layer steps per sample, not a bandwidth limit"}}
+    if e2e:
+        del codes
+        g.reset()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        host_codes = g.run(n_steps, seed=0).cpu()
+        dt = time.perf_counter() - t0
+        out["e2e"] = {"value": n_streams * n_steps / dt, "unit": "samples/s", "h2d_bytes_per_step": 0,
+                      "d2h_bytes_per_step": int(host_codes.numel() * host_codes.element_size()),
+                      "note": "one step = the whole %d-step run: GenEngine.run + device -> host copy of the int32 codes, "
+                              "host wall clock" % n_steps}
+    del g
+    return out
+
+
+def configs0_leg(dev, lib):
+    """BASELINE.json configs[0]: par/arch1.json + par/par1.json of the reference (5x10 stack, R = D = 32, S = P = 512,
+    global conditioning 17 x 377; batch 10, slice 512, l2 = lr = 1e-3) -- one stage-wise training step and 1 s
+    (16 000 steps) of incremental generation for the 10 streams.  A launch-latency-sized workload (5 120 timesteps per
+    step): reported beside the headline, not as it."""
+    import torch
+    from lb_wavenet_b200 import config
+    from lb_wavenet_b200.tmodel import AdamOptimizer, WaveNetTrain
+    arch = config.load_arch(os.path.join(ROOT, "par", "arch_c1_5x10_gc.json"))
+    par = config.load_par(os.path.join(ROOT, "par", "par_c1.json"))
+    B, T = par["batch_sz"], par["slice_sz"]
+    net = WaveNetTrain(**arch, batch_sz=B, l2_factor=par["l2_factor"], add_summary=False, n_keep_checkpoints=1,
+                       ckpt_path="/tmp/bench0.net", resume_step=0, n_valid_total=1, print_interval=0, init_seed=0,
+                       device=dev)
+    net.build()
+    net.init_vars()
+    opt = AdamOptimizer(par["learning_rate"])
+    F = net.get_recep_field_sz()
+    files = synth_files(16, 777, F)
+    files = [(1 + (v % arch["n_gc_category"]), q) for v, q in files]
+    from lb_wavenet_b200.data import SlotDealer
+    d = SlotDealer(files, B, T, F, 1, 5, 0, quiet=True)
+    batches = [d.next_batch()[1:] for _ in range(4)]
+    pinned = [(torch.as_tensor(w).pin_memory(), torch.as_tensor(i).pin_memory()) for w, i in batches]
+    devb = [(w.to(dev), i.to(dev)) for w, i in pinned]
+    K = 50
+    for s_ in range(5):
+        net.train_step(*devb[s_ % 4], opt, want_loss=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s_ in range(K):
+        net.train_step(*devb[s_ % 4], opt, want_loss=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    t0 = time.perf_counter()
+    for s_ in range(K):
+        loss = net.train_step(*pinned[s_ % 4], opt, want_loss=True)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / K
+    out = {"workload": "BASELINE.json configs[0]: reference par/arch1.json (normalised: par/arch_c1_5x10_gc.json) + "
+                       "par/par1.json, batch 10 x slice 512, one stage-wise training step; 16 000 generation steps x 10 streams",
+           "train": {"value": B * (T - 1) / (ms * 1e-3), "unit": "timesteps/s", "ms_per_step": ms,
+                     "e2e": {"value": B * (T - 1) / (e2e_ms * 1e-3), "ms_per_step": e2e_ms, "loss": loss,
+                             "h2d_bytes_per_step": 8 * B * T, "d2h_bytes_per_step": 32}}}
+    gc_ids = np.arange(1, 11, dtype=np.int32)
+    out["gen"] = gen_leg(net._arch_dict, net.engine.params, 10, 16000, dev, lib, "10 streams x 16 000 steps (1 s)", gc_ids)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +265,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-gen", action="store_true", help="skip the generation leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs0", action="store_true", help="skip the BASELINE configs[0] (arch1 + par1) leg")
+    ap.add_argument("--gen-steps", type=int, default=GEN_STEPS, help="generation steps per stream (configs[3]: 160000 = 10 s)")
     ap.add_argument("--slots", type=int, default=None)
     ap.add_argument("--slice", type=int, default=None)
     ap.add_argument("--workload", default="classic", choices=["classic", "wide"],
@@ -201,6 +304,13 @@ def main():
             return 0
         r = cpu_reference_run(arch, args.steps, args.warmup)
         line = dict(base)
+        line["config"] = dict(base["config"])
+        line["config"]["workload"] += (" -- REFERENCE ARM: CPU port of the reference graph (torch fp32; TensorFlow 1.x is "
+                                       "not installable), timed on a BOUNDED SAMPLE of this workload: %d slots x %d "
+                                       "timesteps per step, every position valid (throughput is ~linear in slots x "
+                                       "timesteps)" % (r["B"], r["T"]))
+        line["config"]["reference_sample"] = {"slots": r["B"], "slice_sz": r["T"], "dtype": "f32",
+                                              "same_shape_as_gpu_arm": False}
         line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"],
                      "dtype": "f32", "gpu_launches": 0,
                      "cpu_baseline": {"value": r["value"], "unit": "timesteps/s", "cores": r["cores"], "kind": "port",
@@ -325,6 +435,7 @@ def main():
         _, loss = net.run([apply_op, loss_op])
     e1.record()
     sync_all()
+    loader = dset.loader_stats()
     dset._shutdown()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -332,11 +443,15 @@ def main():
     e2e_ms = float(t.item()) / args.steps
     clk = clocks.stop() if rank == 0 else None  # sampled over all timed regions
     e2e = {"value": B_total * (T - 1) / (e2e_ms * 1e-3), "unit": "timesteps/s", "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(2 * args.slots * T * 4 * max(world, 1)),
+           # uint8 mu-law code + int32 id per timestep, counted from the pinned tensors the loader copies
+           "h2d_bytes_per_step": int(loader.get("h2d_bytes_per_batch", 5 * args.slots * T) * max(world, 1)),
            "d2h_bytes_per_step": int(8 * _lib.WN_NSTATS * max(world, 1)), "loss": loss,
            "api": "MaskedSliceWav.get_op() -> WaveNetTrain.build(*ops) -> net.run([apply_grads_op, loss_op]) (reference "
                   "train.py:182-240); inputs dealt on the host into pinned buffers, H2D on the loader's copy stream",
            "direct_train_step_ms": direct_ms,
+           "loader": dict(loader, note="h2d_gbs: CUDA events on the loader's copy stream around the two H2D copies of a "
+                                       "batch (pinned -> device); deal_ms_per_batch: host time of the C slot dealer "
+                                       "(all global slots replayed, local slots materialised)"),
            "direct_note": "WaveNetTrain.train_step(pinned host tensors): the same step with the H2D copy serialised on "
                           "the compute stream"}
 
@@ -351,95 +466,93 @@ def main():
         k = cats.index(dom)
         shares[dom] = {"ms_per_step": dom_ms[k] / args.steps, "launches_per_step": dom_n[k] / args.steps,
                        "timed_in": "timed region (the other categories: %d untimed profiling steps)" % n_prof}
-    peaks = {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+    peaks = {"bf16_sustained": 1590.0, "bf16_burst": 1590.0, "hbm_gbs": 6650.0,
+             "source": "fallback figures of B200_PROFILING.md (MEASURED_PEAKS.json absent)"}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         with open(pk) as f:
             mp = json.load(f)
-        peaks = {"bf16_tflops": mp.get("bf16_tflops_sustained", mp["bf16_tflops"]), "hbm_gbs": mp["hbm_gbs"],
-                 "source": "MEASURED_PEAKS.json (sustained bf16: kernel timed inside a long step)"}
+        peaks = {"bf16_sustained": mp.get("bf16_tflops_sustained", mp["bf16_tflops"]), "bf16_burst": mp["bf16_tflops"],
+                 "hbm_gbs": mp["hbm_gbs"], "source": "MEASURED_PEAKS.json"}
     rows = args.slots * T
+    L_, R_, D_ = arch["n_blocks"] * arch["n_block_layers"], arch["n_res"], arch["n_dil"]
     flop_by_cat = {
         "post_fwd_loss": post_fwd_flop_per_timestep(arch) * rows,
         "post_bwd": post_fwd_flop_per_timestep(arch) * rows,       # dgrad chain: same contractions transposed
         "wgrad": train_flop_per_timestep(arch) / 3.0 * rows,          # every contraction once more
+        "layer_fwd": L_ * (8 * R_ * D_ + 2 * D_ * R_) * rows,         # conv taps + residual (SURVEY 8d formula)
+        # fused R = 32 backward: data + weight gradients of conv and residual in one kernel; wide path: the recomputed
+        # conv + dz = dx.RESIDUAL^T here, the data gradient under layer_bwd_data, weight gradients under wgrad
+        "layer_bwd": L_ * (8 * R_ * D_ + 2 * D_ * R_) * rows * (2 if R_ < 64 else 1),
+        "layer_bwd_data": L_ * (8 * R_ * D_) * rows,
     }
-    if arch["n_res"] >= 64:  # wide layers run as plain tcgen05 GEMMs: tensor-bound (SURVEY 8d formula per contraction)
-        L_, R_, D_ = arch["n_blocks"] * arch["n_block_layers"], arch["n_res"], arch["n_dil"]
-        flop_by_cat.update({"layer_fwd": L_ * (8 * R_ * D_ + 2 * D_ * R_) * rows,        # conv taps + residual
-                            "layer_bwd": L_ * (8 * R_ * D_ + 2 * D_ * R_) * rows,        # recomputed conv + dz = dx.RESIDUAL^T
-                            "layer_bwd_data": L_ * (8 * R_ * D_) * rows})                # dx = dv.[W0^T|W1^T]
+    # ALGORITHMIC HBM bytes per timestep (bf16), independent of how the kernel stores its intermediates:
+    #   layer_fwd : read x_l (R), write z_l (D) and x_{l+1} (R)                      = 192 B per layer at R = D = 32
+    #   layer_bwd : read x_l (R), dz_l (D), dx_{l+1} (R), write dx_l (R)             = 256 B per layer
+    # (the fused backward's split form dx = Y + P0 moves 384 B: reported as implementation_bytes_per_launch)
+    hbm_by_cat = {"layer_fwd": L_ * (2 * R_ + D_) * 2, "layer_bwd": L_ * (3 * R_ + D_) * 2,
+                  "layer_bwd_data": L_ * (4 * D_ + 2 * R_) * 2}
+    impl_by_cat = {"layer_bwd": L_ * (5 * R_ + D_) * 2} if R_ < 64 else {}
+    tensor_bound = ("post_fwd_loss", "post_bwd", "wgrad") + (("layer_fwd", "layer_bwd", "layer_bwd_data") if R_ >= 64 else ())
     roofline = None
     if dom is not None:
         dms = shares[dom]["ms_per_step"]
-        if dom in flop_by_cat:
-            ach = flop_by_cat[dom] / (dms * 1e-3) / 1e12
-            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"],
-                        "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
-                        "peak_source": peaks["source"], "ms_per_step": dms}
+        n_launch = max(1.0, shares[dom]["launches_per_step"])
+        tf_ach = flop_by_cat[dom] / (dms * 1e-3) / 1e12 if dom in flop_by_cat else None
+        gb_ach = hbm_by_cat[dom] * rows / (dms * 1e-3) / 1e9 if dom in hbm_by_cat else None
+        traffic = None  # measured DRAM bytes per launch of this kernel (one ncu --set full capture, profiles/)
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
+        if dom in tensor_bound or gb_ach is None:
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": tf_ach, "peak": peaks["bf16_sustained"],
+                        "unit": "TFLOP/s", "frac": tf_ach / peaks["bf16_sustained"], "traffic": traffic,
+                        "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"}
         else:
-            # algorithmic HBM bytes per timestep and layer, bf16:
-            #   layer_fwd : read x_l (R), write z_l (D) and x_{l+1} (R)
-            #   layer_bwd : read x_l (R), dz_l (D), Y_{l+1} (R), P0_{l+1} (R); write Y_l (R), P0_l (R)
-            L = arch["n_blocks"] * arch["n_block_layers"]
-            R_, D_ = arch["n_res"], arch["n_dil"]
-            per_row = {"layer_fwd": L * (2 * R_ + D_) * 2, "layer_bwd": L * (5 * R_ + D_) * 2,
-                       "layer_bwd_data": L * (4 * D_ + 2 * R_) * 2}.get(dom, 0)
-            n_launch = max(1.0, shares[dom]["launches_per_step"])
-            ach = per_row * rows / (dms * 1e-3) / 1e9
-            traffic = None  # measured DRAM bytes per launch of this kernel (one ncu --set full capture, profiles/)
-            tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-            if os.path.exists(tp):
-                with open(tp) as f:
-                    traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
-            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
-                        "algorithmic_bytes_per_launch": per_row * rows / n_launch,
-                        "us_per_launch": dms * 1e3 / n_launch, "peak_source": peaks["source"], "ms_per_step": dms}
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": gb_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": gb_ach / peaks["hbm_gbs"], "traffic": traffic,
+                        "algorithmic_bytes_per_launch": hbm_by_cat[dom] * rows / n_launch,
+                        "peak_source": peaks["source"] + " hbm_gbs (measured copy bandwidth)"}
+            if dom in impl_by_cat:
+                roofline["implementation_bytes_per_launch"] = impl_by_cat[dom] * rows / n_launch
+        roofline.update({"us_per_launch": dms * 1e3 / n_launch, "ms_per_step": dms})
+        # both fractions of the dominant kernel, whichever bound is reported above (tensor: against the BURST peak,
+        # BASELINE.md section 3)
+        if tf_ach is not None:
+            roofline["tensor"] = {"achieved_tflops": tf_ach, "peak_burst": peaks["bf16_burst"],
+                                  "frac_of_burst": tf_ach / peaks["bf16_burst"]}
+        if gb_ach is not None:
+            roofline["hbm"] = {"achieved_gbs": gb_ach, "peak": peaks["hbm_gbs"], "frac": gb_ach / peaks["hbm_gbs"]}
     whole = value * train_flop_per_timestep(arch) / 1e12
 
     line = dict(base)
     line.update({"value": value, "ms_per_step": ms_per_step, "e2e": e2e, "gpu_launches": launches,
                  "clocks": clk, "roofline": roofline,
-                 "whole_step_tflops": whole, "whole_step_frac_of_bf16_peak": whole / peaks["bf16_tflops"] / max(world, 1),
+                 "whole_step_tflops": whole,
+                 "whole_step_frac_of_bf16_peak": whole / peaks["bf16_burst"] / max(world, 1),   # burst peak, BASELINE.md 3
+                 "whole_step_frac_of_bf16_sustained": whole / peaks["bf16_sustained"] / max(world, 1),
                  "kernel_shares": shares})
 
-    # ---- generation leg (1 GPU, rank 0): batched incremental generation samples/s --------------------
+    # ---- generation legs (1 GPU, rank 0): batched incremental generation samples/s ---------------------
     if not args.no_gen and world == 1:
         try:
-            from lb_wavenet_b200.engine import GenEngine
-            g = GenEngine(net._arch_dict, GEN_STREAMS, str(dev))
-            g.load_params(net.engine.params)
-            g.run(50, seed=0)
-            torch.cuda.synchronize()
-            lib.wn_launch_count_reset()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            g.run(GEN_STEPS, seed=0)
-            e1.record()
-            torch.cuda.synchronize()
-            gms = e0.elapsed_time(e1)
-            sps = GEN_STREAMS * GEN_STEPS / (gms * 1e-3)
-            L = arch["n_blocks"] * arch["n_block_layers"]
-            ring_bytes = L * 2 * arch["n_res"] * 2
-            line["gen"] = {"metric": "batched gen audio samples/s", "value": sps, "streams": GEN_STREAMS,
-                           "steps": GEN_STEPS, "us_per_step": gms * 1e3 / GEN_STEPS,
-                           "realtime_multiple_per_stream": sps / GEN_STREAMS / 16000.0,
-                           "ring_gbs": sps * ring_bytes / 1e9, "gpu_launches": int(lib.wn_launch_count_reset())}
-            # the step time is set by one SM streaming the stack's weights: more streams only
-            # occupy more SMs, so throughput grows with the batch until all 148 are busy
-            del g
-            g4 = GenEngine(net._arch_dict, 4 * GEN_STREAMS, str(dev))
-            g4.load_params(net.engine.params)
-            g4.run(20, seed=0)
-            torch.cuda.synchronize()
-            e0.record()
-            g4.run(GEN_STEPS // 2, seed=0)
-            e1.record()
-            torch.cuda.synchronize()
-            line["gen"]["at_%d_streams" % (4 * GEN_STREAMS)] = 4 * GEN_STREAMS * (GEN_STEPS // 2) / (e0.elapsed_time(e1) * 1e-3)
+            # BASELINE configs[3]: 256 independent streams x 160 000 steps (10 s each) from the 3x10 stack
+            line["gen"] = gen_leg(net._arch_dict, net.engine.params, GEN_STREAMS, args.gen_steps, str(dev), lib,
+                                  "BASELINE.json configs[3]: %d streams x %d steps, 3x10 stack, ring buffers in HBM"
+                                  % (GEN_STREAMS, args.gen_steps))
+            # throughput grows with the batch until all 148 SMs hold a stream group (one CTA per 16 streams)
+            g4 = gen_leg(net._arch_dict, net.engine.params, 4 * GEN_STREAMS, 2000, str(dev), lib, "", e2e=False)
+            line["gen"]["at_%d_streams" % (4 * GEN_STREAMS)] = g4["value"]
         except Exception as e:  # the training line must survive a generator failure
             line["gen"] = {"error": repr(e)}
+    del net, dset
+    torch.cuda.empty_cache()
+    if not args.no_configs0 and world == 1 and not wide:
+        try:
+            line["configs0"] = configs0_leg(str(dev), lib)
+        except Exception as e:
+            line["configs0"] = {"error": repr(e)}
 
     # ---- CPU baseline beside it (bounded sample) ------------------------------------------------------
     if not args.no_cpu and world == 1:

@@ -142,7 +142,9 @@ int wn_l2_loss(wn_model* m, const float* d_params, double* d_stats, void* stream
 /* test/debug taps into the stash written by the last wn_train_forward / backward:
  * what: 0 = x_l (layer input, [n_slots, T, n_res]), 1 = z_l ([n_slots, T, n_dil]),
  *       2 = h1 ([n_slots,T,n_skip]), 3 = h2 ([n_slots,T,n_post]), 4 = dlogits [.,.,n_quant],
- *       5 = dx_0 (gradient wrt layer-0 input) ; converted to fp32 into d_out */
+ *       5 = dx_0 (gradient wrt layer-0 input), 6 = dz plane of `layer` [., ., n_dil], 7 / 8 = the raw data-gradient
+ *       buffers of parity layer & 1 (Y_l / P0_l of the fused backward: dx_l[t] = Y_l[t] + P0_l[t + dil_l]; dx_l itself in
+ *       buffer 7 on the other paths) -- readable between wn_train_backward_phases calls ; converted to fp32 into d_out */
 int wn_debug_read(wn_model* m, const void* d_ws, int32_t slice_sz, int32_t what, int32_t layer,
                   float* d_out, void* stream);
 
@@ -176,6 +178,31 @@ int wn_mu_decode(const int32_t* d_q, float* d_x, int64_t n, void* stream);
  * counter (step, stream = i).  Replaces tf.multinomial (reference imodel.py:179). */
 int wn_sample_logits(const float* d_logits, int32_t n_rows, uint64_t seed, int64_t step,
                      int32_t* d_out, void* stream);
+
+/* ---- window loader (HOST functions: no GPU, no handle) --------------------------------------
+ * The slot dealer of MaskedSliceWav (reference data.py:110-227: _gen_concat_slice_factory / _gen_slice_batch) as plain
+ * cursor arithmetic.  Called through ctypes without the GIL from the loader thread.
+ * wn_deal_plan advances ALL batch_sz global slots by one slice_sz window: a slot whose file is used up pulls the next
+ * entry of h_order (catalog indices of the shared shuffled stream, data.py:246-250) in slot order, skipping files whose
+ * usable length is below recep_field (data.py:150-154).  State arrays (int64[batch_sz]) and *h_datum_count are updated in
+ * place.  Output: rows of 5 int64 in h_seg -- (local_slot, dst_off, file_idx, src_off, len) for slots in
+ * [slot_lo, slot_hi), or (-1, slot, file_idx, 0, usable_len) as a notice that a short file was skipped.
+ * Returns 0, or 1 = h_order exhausted / 2 = h_seg too small (then NOTHING was changed: extend and call again). */
+int wn_deal_plan(int32_t batch_sz, int32_t slice_sz, int32_t slot_lo, int32_t slot_hi, int32_t recep_field,
+                 int64_t* h_cur_file, int64_t* h_cur_pos, int64_t* h_cur_len, int64_t* h_slot_count,
+                 int64_t* h_datum_count, const int32_t* h_order, int64_t n_order, int64_t* h_order_used,
+                 const int64_t* h_usable_len, int64_t n_files, int64_t* h_seg, int64_t seg_cap, int64_t* h_n_seg);
+/* wn_deal_fill executes the segments into one batch buffer [n_local, slice_sz]: h_file_ptr[i] = host address of file
+ * i's samples (0 = not loaded), h_file_dtype[i] in {0 u8, 1 i16, 2 i32, 3 i64, 4 f32, 5 f64}; out_dtype 0 = uint8
+ * mu-law codes (error if a code is outside [0, 255]), 2 = int32 codes, 4 = float32 raw audio (wav_input_type 'raw',
+ * tmodel.py:59-62).  h_ids_out gets the voice id, or 0 for the first recep_field - 1 samples of every file
+ * (data.py:133,156-159). */
+int wn_deal_fill(const int64_t* h_seg, int64_t n_seg, const uint64_t* h_file_ptr, const int32_t* h_file_dtype,
+                 const int32_t* h_voice_id, int64_t n_files, int32_t recep_field, int32_t slice_sz, int32_t out_dtype,
+                 void* h_wav_out, int32_t* h_ids_out);
+/* device: widen the uint8 codes the loader ships (5 bytes per timestep with the id) to the int32 [n] the training
+ * kernels index with */
+int wn_codes_u8_to_i32(const uint8_t* d_u8, int32_t* d_i32, int64_t n, void* stream);
 
 /* ---- self tests (device) ---------------------------------------------------------------
  * C[M,N] fp32 = A[M,K] bf16 (row-major) x B[N,K]^T bf16 (row-major) through the

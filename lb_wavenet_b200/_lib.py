@@ -58,6 +58,10 @@ SIGNATURES = {
     "wn_mu_encode": (C.c_int, [_vp, _vp, _i64, _vp]),
     "wn_mu_decode": (C.c_int, [_vp, _vp, _i64, _vp]),
     "wn_sample_logits": (C.c_int, [_vp, _i32, _u64, _i64, _vp, _vp]),
+    "wn_deal_plan": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64,
+                               _vp]),
+    "wn_deal_fill": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "wn_codes_u8_to_i32": (C.c_int, [_vp, _vp, _i64, _vp]),
     "wn_selftest_umma_gemm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "wn_selftest_umma_gemm_tn": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "wn_prof_enable": (C.c_int, [_i32]),

@@ -417,12 +417,14 @@ __global__ void __launch_bounds__(NT) k_post_fwd(PostArgs a) {
     }
     sum = warp_sum(sum);
     const bool valid = (t + 1 < T) && (a.ids[(size_t)b * T + t + 1] != 0);  // tmodel.py:232
-    int label = (t + 1 < T) ? a.wav[(size_t)b * T + t + 1] : 0;              // tmodel.py:230
-    label = min(max(label, 0), Q - 1);
-    const float vl = __shfl_sync(0xffffffffu, v[label & 7], label >> 3);
+    const int label_raw = (t + 1 < T) ? a.wav[(size_t)b * T + t + 1] : 0;    // tmodel.py:230
+    const bool label_ok = label_raw >= 0 && label_raw < Q;                   // out of range: all-zero one-hot row (tmodel.py:64)
+    const int label = label_ok ? label_raw : -1;
+    const int lsel = label_ok ? label : 0;
+    const float vl = __shfl_sync(0xffffffffu, v[lsel & 7], lsel >> 3);
     // NB: v[label&7] with a lane-varying index would be needed if label differed per lane; it is
     // warp-uniform here, so every lane evaluates the same register select.
-    const float xent = __logf(sum) + mx - vl;
+    const float xent = label_ok ? __logf(sum) + mx - vl : 0.f;
     const float inv = 1.f / sum;
     __align__(16) bf16 dl[8];
 #pragma unroll
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(NT) k_post_fwd(PostArgs a) {
     if (valid) {
       acc_x += xent;
       acc_n += 1.f;
-      acc_d += fabsf((float)(label - arg));
+      acc_d += fabsf((float)(lsel - arg));
     }
   }
   if (lane == 0) {
@@ -900,6 +902,25 @@ __global__ void k_l2(const float* __restrict__ w, const uint8_t* __restrict__ ki
 }
 
 // `add` (optional, same [rows][ld] geometry): dst += add[t + add_shift] for t + add_shift < slot_rows
+// loader: mu-law codes travel host -> device as uint8 (5 bytes per timestep with the int32 id) and are
+// widened here to the int32 the kernels index with (data.py:262-265 dtypes).  16 codes per thread, grid-stride.
+__global__ void k_widen_u8(const uint8_t* __restrict__ src, int32_t* __restrict__ dst, int64_t n) {
+  const int64_t n16 = n / 16;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n + 15) / 16; i += (int64_t)gridDim.x * blockDim.x) {
+    if (aligned && i < n16) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      int4* o = reinterpret_cast<int4*>(dst) + 4 * i;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        o[k] = make_int4(w[k] & 0xff, (w[k] >> 8) & 0xff, (w[k] >> 16) & 0xff, w[k] >> 24);
+    } else {
+      for (int64_t j = 16 * i; j < n && j < 16 * i + 16; ++j) dst[j] = src[j];
+    }
+  }
+}
+
 __global__ void k_debug_read(const bf16* __restrict__ src, float* __restrict__ dst, int64_t n_rows, int ncols,
                              int64_t slot_rows, int64_t slot_pitch_rows, int row_off, int ld, int col0,
                              const bf16* __restrict__ add, int add_shift) {
@@ -1405,6 +1426,18 @@ int wn_l2_loss(wn_model* m, const float* d_params, double* d_stats, void* stream
   return WN_OK;
 }
 
+int wn_codes_u8_to_i32(const uint8_t* d_u8, int32_t* d_i32, int64_t n, void* stream_) {
+  if (!d_u8 || !d_i32 || n < 0) {
+    set_error("wn_codes_u8_to_i32: invalid argument");
+    return WN_ERR_INVALID;
+  }
+  if (n == 0) return WN_OK;
+  const int64_t n16 = (n + 15) / 16;
+  k_widen_u8<<<(unsigned)std::min<int64_t>((n16 + 255) / 256, 148 * 16), 256, 0, (cudaStream_t)stream_>>>(d_u8, d_i32, n);
+  WN_LAUNCH_CHECK();
+  return WN_OK;
+}
+
 int wn_debug_read(wn_model* m, const void* d_ws, int32_t T, int32_t what, int32_t layer, float* d_out,
                   void* stream_) {
   if (!m || !d_ws || !d_out) {
@@ -1437,6 +1470,17 @@ int wn_debug_read(wn_model* m, const void* d_ws, int32_t T, int32_t what, int32_
         add = reinterpret_cast<const bf16*>(ws + wl.p0[0]);
         add_shift = m->layers[0].dil;
       }
+      break;
+    case 6:  // dz plane of `layer` ([L][B*T][D]): the skip-path gradient after phase 0 (the wide-layer backward adds the
+             // residual part in place while it differentiates that layer)
+      if (layer < 0 || layer >= d.L) { set_error("wn_debug_read: bad layer"); return WN_ERR_INVALID; }
+      src = reinterpret_cast<const bf16*>(ws + wl.dz) + (size_t)layer * d.rows * d.D; ncols = d.D; ld = d.D;
+      break;
+    case 7:  // raw data-gradient buffer of parity `layer` & 1: Y_l of the fused backward, dx_l on the other paths
+      src = reinterpret_cast<const bf16*>(ws + wl.dx[layer & 1]); ncols = d.R; ld = d.R;
+      break;
+    case 8:  // raw P0 buffer of parity `layer` & 1 (fused backward: dx_l[t] = Y_l[t] + P0_l[t + dil_l])
+      src = reinterpret_cast<const bf16*>(ws + wl.p0[layer & 1]); ncols = d.R; ld = d.R;
       break;
     default: set_error("wn_debug_read: unknown tap %d", what); return WN_ERR_INVALID;
   }

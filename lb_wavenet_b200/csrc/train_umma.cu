@@ -290,8 +290,11 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
         const int b = in_range ? (int)(row / a.T) : 0, t = in_range ? (int)(row % a.T) : 0;
         const bool has_next = in_range && (t + 1 < a.T);
         const bool valid = has_next && (a.ids[(size_t)b * a.T + t + 1] != 0);  // tmodel.py:232
-        int label = has_next ? a.wav[(size_t)b * a.T + t + 1] : 0;              // tmodel.py:230
-        label = min(max(label, 0), Q - 1);
+        // tmodel.py:230 + :64: tf.one_hot of an out-of-range code is an all-zero row, so the cross entropy of that
+        // position is 0, dlogits = softmax - 0 (TF's fused xent kernel returns softmax - labels) and argmax(label) = 0
+        const int label_raw = has_next ? a.wav[(size_t)b * a.T + t + 1] : 0;
+        const bool label_ok = label_raw >= 0 && label_raw < Q;
+        const int label = label_ok ? label_raw : -1;
         const int cb = half * (Q / 2);
         // pass 1 (online softmax over this thread's column half): running max, sum of exp, argmax, label logit
         float mx = -INFINITY, sum = 0.f, vl = 0.f;
@@ -351,9 +354,9 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
           // argmax over the whole row: smallest index among equal maxima (tf.argmax)
           const int garg = (x_mx[1][r] > x_mx[0][r]) ? x_arg[1][r] : x_arg[0][r];
           const float gvl = label < Q / 2 ? x_vl[0][r] : x_vl[1][r];
-          acc_x += __logf(tot) + M - gvl;
+          acc_x += label_ok ? __logf(tot) + M - gvl : 0.f;
           acc_n += 1.f;
-          acc_d += fabsf((float)(label - garg));
+          acc_d += fabsf((float)((label_ok ? label : 0) - garg));
         }
       }
     }
@@ -1215,8 +1218,9 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           const int b = in_range ? (int)(row / a.T) : 0, t = in_range ? (int)(row % a.T) : 0;
           const bool has_next = in_range && (t + 1 < a.T);
           const bool valid = has_next && (a.ids[(size_t)b * a.T + t + 1] != 0);  // tmodel.py:232
-          int label = has_next ? a.wav[(size_t)b * a.T + t + 1] : 0;              // tmodel.py:230
-          label = min(max(label, 0), Q - 1);
+          const int label_raw = has_next ? a.wav[(size_t)b * a.T + t + 1] : 0;    // tmodel.py:230
+          const bool label_ok = label_raw >= 0 && label_raw < Q;                  // out of range: all-zero one-hot row
+          const int label = label_ok ? label_raw : -1;
           const int cb = half * (Q / 2);
           float mx = -INFINITY, sum = 0.f, vl = 0.f;
           int arg = 0;
@@ -1274,9 +1278,9 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           if (half == 0 && valid) {
             const int garg = (x_mx[1][r] > x_mx[0][r]) ? x_arg[1][r] : x_arg[0][r];
             const float gvl = label < Q / 2 ? x_vl[0][r] : x_vl[1][r];
-            acc_x += __logf(tot) + M - gvl;
+            acc_x += label_ok ? __logf(tot) + M - gvl : 0.f;
             acc_n += 1.f;
-            acc_d += fabsf((float)(label - garg));
+            acc_d += fabsf((float)((label_ok ? label : 0) - garg));
           }
           epi_bar_sync256();  // the partials of this tile are consumed before the next tile overwrites them
         }

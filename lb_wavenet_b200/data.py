@@ -14,6 +14,7 @@ from the .npy headers) and materialise just their own slots.
 """
 from __future__ import annotations
 
+import itertools
 import queue
 import threading
 from dataclasses import dataclass
@@ -55,59 +56,88 @@ def _npy_load(src: WavSource) -> np.ndarray:
     return src if isinstance(src, np.ndarray) else np.load(src)
 
 
+_NP_DTYPE_CODE = {np.dtype(np.uint8): 0, np.dtype(np.int16): 1, np.dtype(np.int32): 2, np.dtype(np.int64): 3,
+                  np.dtype(np.float32): 4, np.dtype(np.float64): 5}
+_WAV_DTYPES = {"u8": (np.uint8, 0), "i32": (np.int32, 2), "f32": (np.float32, 4)}
+
+
 class SlotDealer:
     """Deterministic replay of reference data.py:110-227 for slots [slot_lo, slot_hi) of batch_sz.
 
     Files are pulled lazily from ONE shared stream in slot order, exactly when a slot's generator
     would call next(wav_gen) (data.py:140): which slot receives which file therefore matches the
     reference for any mix of file lengths.
+
+    The cursor arithmetic over all global slots and the copies into the batch buffer are two C calls
+    (wn_deal_plan / wn_deal_fill, csrc/dealer.cpp) made through ctypes, i.e. WITHOUT the GIL: the loader thread no
+    longer competes with the training thread for the interpreter.  This class keeps the file stream (numpy PCG64
+    shuffle buffer), the .npy loading of the local slots' current files and the state for exact resume.
+
+    wav_dtype: 'i32' (mu-law codes as int32, data.py:262-265), 'u8' (the same codes in one byte: what the loader ships
+    to the device) or 'f32' (raw float audio for wav_input_type == 'raw', tmodel.py:59-62).
     """
 
     def __init__(self, catalog: Sequence[Tuple[int, WavSource]], batch_sz: int, slice_sz: int,
                  recep_field_sz: int, mel_hop_sz: int = 1, seed: int = 0, position: int = 0,
-                 slot_lo: int = 0, slot_hi: Optional[int] = None, quiet: bool = False):
+                 slot_lo: int = 0, slot_hi: Optional[int] = None, quiet: bool = False, wav_dtype: str = "i32"):
         if not catalog:
             raise ValueError("empty sample catalog")
+        from . import _lib
+        self._lib = _lib.load()
+        self._check = _lib.check
         self.catalog = list(catalog)
         self.batch_sz, self.slice_sz = int(batch_sz), int(slice_sz)
         self.F, self.hop = int(recep_field_sz), int(mel_hop_sz)
         self.slot_lo, self.slot_hi = slot_lo, batch_sz if slot_hi is None else slot_hi
         self.quiet = quiet
+        self.wav_dtype = wav_dtype
+        self._np_wav, self._out_code = _WAV_DTYPES[wav_dtype]
         self._order = shuffled_repeat_order(len(self.catalog), seed, position)
-        self._datum_count = int(position)  # data.py:79
-        self._len_cache = {}
-        n = self.batch_sz
-        self._cur_file = [-1] * n      # catalog index of the slot's current file
-        self._cur_pos = [0] * n        # cursor into it
-        self._cur_len = [0] * n        # usable (hop-trimmed) length
-        self._cur_data = [None] * n    # loaded array (local slots only)
-        self._slot_count = [self._datum_count] * n  # datum_count of the slot's latest pull
-        usable = [self._usable_len(i) for i in range(len(self.catalog))]
-        if max(usable) < self.F:
+        self._order_buf = np.empty(0, np.int32)   # upcoming entries of the shared file stream, not yet consumed
+        n, nf = self.batch_sz, len(self.catalog)
+        self._datum = np.array([int(position)], np.int64)   # data.py:79
+        self._cur_file = np.full(n, -1, np.int64)            # catalog index of the slot's current file
+        self._cur_pos = np.zeros(n, np.int64)                # cursor into it
+        self._cur_len = np.zeros(n, np.int64)                # usable (hop-trimmed) length
+        self._slot_count = np.full(n, int(position), np.int64)  # datum_count of the slot's latest pull
+        self._usable = np.empty(nf, np.int64)
+        for i in range(nf):
+            ln = _npy_len(self.catalog[i][1])
+            self._usable[i] = ln - (ln % self.hop)            # data.py:141-142
+        if int(self._usable.max()) < self.F:
             raise ValueError("every file is shorter than the receptive field {}".format(self.F))
+        self._voice = np.array([int(c[0]) for c in self.catalog], np.int32)
+        self._file_ptr = np.zeros(nf, np.uint64)
+        self._file_dtype = np.zeros(nf, np.int32)
+        self._loaded = {}                                     # catalog index -> contiguous array (local slots' files)
+        self._seg = np.empty((max(64, 8 * n), 5), np.int64)
+        self._n_seg = np.zeros(1, np.int64)
+        self._used = np.zeros(1, np.int64)
+
+    @property
+    def _datum_count(self) -> int:
+        return int(self._datum[0])
 
     def _usable_len(self, idx: int) -> int:
-        if idx not in self._len_cache:
-            n = _npy_len(self.catalog[idx][1])
-            self._len_cache[idx] = n - (n % self.hop)  # data.py:141-142
-        return self._len_cache[idx]
+        return int(self._usable[idx])
 
-    def _pull(self, slot: int) -> None:
-        """next(wav_gen) + the length filter (data.py:140-154)."""
-        while True:
-            idx = next(self._order)
-            self._datum_count += 1  # data.py:82
-            n = self._usable_len(idx)
-            if n < self.F:
-                if not self.quiet:
-                    print("Warning: skipping length {} wav file (voice id {}).  Shorter than receptive "
-                          "field size of {}".format(n, self.catalog[idx][0], self.F), file=stderr)
-                continue
-            self._cur_file[slot], self._cur_pos[slot], self._cur_len[slot] = idx, 0, n
-            self._slot_count[slot] = self._datum_count
-            if self.slot_lo <= slot < self.slot_hi:
-                self._cur_data[slot] = np.asarray(_npy_load(self.catalog[idx][1]))[:n]
+    def _load(self, idx: int) -> None:
+        if idx in self._loaded:
             return
+        arr = np.ascontiguousarray(np.asarray(_npy_load(self.catalog[idx][1])))
+        code = _NP_DTYPE_CODE.get(arr.dtype)
+        if code is None:
+            arr = np.ascontiguousarray(arr.astype(np.float32 if arr.dtype.kind == "f" else np.int64))
+            code = _NP_DTYPE_CODE[arr.dtype]
+        self._loaded[idx] = arr
+        self._file_ptr[idx] = arr.ctypes.data
+        self._file_dtype[idx] = code
+
+    def _evict(self) -> None:
+        live = set(int(f) for f in self._cur_file[self.slot_lo:self.slot_hi] if f >= 0)
+        for idx in [i for i in self._loaded if i not in live]:
+            del self._loaded[idx]
+            self._file_ptr[idx] = 0
 
     # ---- exact resume (beyond the reference, whose (seed, position) restart re-deals every slot from a fresh file:
     # data.py:249-250,280-286) -------------------------------------------------------------------------------------
@@ -115,58 +145,61 @@ class SlotDealer:
         """Everything that determines all future batches, as small int64 arrays: the shared stream's position and, per
         slot, the current file (catalog index, -1 = none yet), the cursor into it and its pull count."""
         return {"stream_position": np.array(self._datum_count, np.int64),
-                "slot_file": np.array(self._cur_file, np.int64), "slot_pos": np.array(self._cur_pos, np.int64),
-                "slot_count": np.array(self._slot_count, np.int64)}
+                "slot_file": self._cur_file.copy(), "slot_pos": self._cur_pos.copy(),
+                "slot_count": self._slot_count.copy()}
 
     def load_state(self, st: dict, seed: int) -> None:
         if len(st["slot_file"]) != self.batch_sz:
             raise ValueError("loader state is for batch_sz {}, not {}".format(len(st["slot_file"]), self.batch_sz))
-        self._datum_count = int(st["stream_position"])
+        self._datum[0] = int(st["stream_position"])
         self._order = shuffled_repeat_order(len(self.catalog), seed, self._datum_count)
+        self._order_buf = np.empty(0, np.int32)
+        self._cur_file[:] = np.asarray(st["slot_file"], np.int64)
+        self._cur_pos[:] = np.asarray(st["slot_pos"], np.int64)
+        self._slot_count[:] = np.asarray(st["slot_count"], np.int64)
         for slot in range(self.batch_sz):
-            idx = int(st["slot_file"][slot])
-            self._cur_file[slot], self._cur_pos[slot] = idx, int(st["slot_pos"][slot])
-            self._slot_count[slot] = int(st["slot_count"][slot])
+            idx = int(self._cur_file[slot])
             self._cur_len[slot] = self._usable_len(idx) if idx >= 0 else 0
-            self._cur_data[slot] = None
-            if idx >= 0 and self.slot_lo <= slot < self.slot_hi:
-                self._cur_data[slot] = np.asarray(_npy_load(self.catalog[idx][1]))[:self._cur_len[slot]]
+        self._loaded.clear()
+        self._file_ptr[:] = 0
 
     def next_batch(self, wav_out: Optional[np.ndarray] = None, ids_out: Optional[np.ndarray] = None):
-        """Returns (latest_file_read_count, wav[int32 n_local x T], ids[int32 n_local x T])."""
+        """Returns (latest_file_read_count, wav[n_local x T], ids[int32 n_local x T])."""
         T, nl = self.slice_sz, self.slot_hi - self.slot_lo
-        wav = np.empty((nl, T), np.int32) if wav_out is None else wav_out
+        wav = np.empty((nl, T), self._np_wav) if wav_out is None else wav_out
         ids = np.empty((nl, T), np.int32) if ids_out is None else ids_out
-        bound = self.F - 1  # data.py:133
-        cur_file, cur_pos, cur_len = self._cur_file, self._cur_pos, self._cur_len
-        for slot in range(self.batch_sz):
-            local = self.slot_lo <= slot < self.slot_hi
-            filled = 0
-            if not local:  # another rank's slot: replay the cursor arithmetic only
-                while filled < T:
-                    if cur_file[slot] < 0 or cur_pos[slot] >= cur_len[slot]:
-                        self._pull(slot)
-                    take = min(T - filled, cur_len[slot] - cur_pos[slot])
-                    cur_pos[slot] += take
-                    filled += take
+        if wav.dtype != self._np_wav or ids.dtype != np.int32 or not (wav.flags.c_contiguous and ids.flags.c_contiguous):
+            raise ValueError("batch buffers must be C-contiguous {} / int32".format(np.dtype(self._np_wav).name))
+        lib = self._lib
+        while True:
+            rc = lib.wn_deal_plan(self.batch_sz, T, self.slot_lo, self.slot_hi, self.F, self._cur_file.ctypes.data,
+                                  self._cur_pos.ctypes.data, self._cur_len.ctypes.data, self._slot_count.ctypes.data,
+                                  self._datum.ctypes.data, self._order_buf.ctypes.data, len(self._order_buf),
+                                  self._used.ctypes.data, self._usable.ctypes.data, len(self.catalog),
+                                  self._seg.ctypes.data, len(self._seg), self._n_seg.ctypes.data)
+            if rc == 1:  # the file stream buffer ran dry: draw more of the shuffled order (numpy PCG64, see above)
+                more = np.fromiter(itertools.islice(self._order, 2 * self.batch_sz + 64), np.int32)
+                self._order_buf = np.concatenate([self._order_buf, more])
                 continue
-            while filled < T:
-                if self._cur_file[slot] < 0 or self._cur_pos[slot] >= self._cur_len[slot]:
-                    self._pull(slot)
-                pos = self._cur_pos[slot]
-                take = min(T - filled, self._cur_len[slot] - pos)
-                if local:
-                    r = slot - self.slot_lo
-                    wav[r, filled:filled + take] = self._cur_data[slot][pos:pos + take]
-                    vid = self.catalog[self._cur_file[slot]][0]
-                    seg = ids[r, filled:filled + take]
-                    seg[:] = vid
-                    nz = bound - pos  # positions < F-1 of the file are invalid (data.py:156-159)
-                    if nz > 0:
-                        seg[:min(nz, take)] = 0
-                self._cur_pos[slot] = pos + take
-                filled += take
-        return self._slot_count[self.batch_sz - 1], wav, ids  # data.py:220
+            if rc == 2:
+                self._seg = np.empty((2 * len(self._seg), 5), np.int64)
+                continue
+            self._check(rc, "wn_deal_plan")
+            break
+        self._order_buf = self._order_buf[int(self._used[0]):].copy()
+        seg = self._seg[:int(self._n_seg[0])]
+        for row in seg:
+            if row[0] < 0:
+                if not self.quiet:
+                    print("Warning: skipping length {} wav file (voice id {}).  Shorter than receptive "
+                          "field size of {}".format(int(row[4]), self.catalog[int(row[2])][0], self.F), file=stderr)
+            else:
+                self._load(int(row[2]))
+        self._check(lib.wn_deal_fill(seg.ctypes.data, len(seg), self._file_ptr.ctypes.data, self._file_dtype.ctypes.data,
+                                     self._voice.ctypes.data, len(self.catalog), self.F, T, self._out_code,
+                                     wav.ctypes.data, ids.ctypes.data), "wn_deal_fill")
+        self._evict()
+        return int(self._slot_count[self.batch_sz - 1]), wav, ids  # data.py:220
 
 
 @dataclass
@@ -190,7 +223,7 @@ class MaskedSliceWav(ckpt.Checkpoint):
 
     def __init__(self, sess, sam_file, sample_rate, slice_sz, prefetch_sz, mel_spectrum_sz, mel_hop_sz,
                  batch_sz, n_keep_checkpoints, ckpt_path, resume_step, dist=None, device: Optional[str] = None,
-                 random_seed: Optional[int] = None):
+                 random_seed: Optional[int] = None, wav_input_type: str = "mu_law_quant"):
         super().__init__(ckpt_path, n_keep_checkpoints, resume_step, sess)
         self.sam_file = sam_file
         self.sample_rate = sample_rate
@@ -208,6 +241,9 @@ class MaskedSliceWav(ckpt.Checkpoint):
         self.ckpt_position = 0  # data.py:41
         self.dist = dist
         self.device = device
+        # 'mu_law_quant': .npy files hold mu-law codes, shipped as uint8 and widened on the device; 'raw': float audio in
+        # [-1, 1], shipped as float32 and mu-law encoded on the device by the model (tmodel.py:59-62)
+        self.wav_input_type = wav_input_type
         self.sample_catalog: List[list] = []
         self.recep_field_sz = None
         self._worker = None
@@ -282,12 +318,6 @@ class MaskedSliceWav(ckpt.Checkpoint):
         data.py:254,270."""
         self._shutdown()
         lo, hi = (0, self.batch_sz) if self.dist is None else self.dist.slot_range(self.batch_sz)
-        self._dealer = SlotDealer([(e[0], e[1]) for e in self.sample_catalog], self.batch_sz, self.slice_sz,
-                                  self.recep_field_sz, self.mel_hop_sz, self.random_seed, self.ckpt_position, lo, hi)
-        st = getattr(self, "_resume_state", None)
-        if st is not None:  # exact resume: restore() found the optional keys
-            self._dealer.load_state(st, self.random_seed)
-            self._resume_state = None
         self._n_local = hi - lo
         self._use_cuda = False
         if self.device is None or str(self.device).startswith("cuda"):
@@ -296,6 +326,17 @@ class MaskedSliceWav(ckpt.Checkpoint):
                 self._use_cuda = torch.cuda.is_available()
             except ImportError:
                 self._use_cuda = False
+        raw = self.wav_input_type == "raw"
+        # device path: codes travel as uint8 (5 bytes per timestep with the int32 id) and are widened to
+        # int32 on the copy stream; host path (no CUDA: CPU tests, tools): int32 codes as data.py:262-265
+        wav_dtype = "f32" if raw else ("u8" if self._use_cuda else "i32")
+        self._dealer = SlotDealer([(e[0], e[1]) for e in self.sample_catalog], self.batch_sz, self.slice_sz,
+                                  self.recep_field_sz, self.mel_hop_sz, self.random_seed, self.ckpt_position, lo, hi,
+                                  wav_dtype=wav_dtype)
+        st = getattr(self, "_resume_state", None)
+        if st is not None:  # exact resume: restore() found the optional keys
+            self._dealer.load_state(st, self.random_seed)
+            self._resume_state = None
         self._stop = threading.Event()
         self._q = queue.Queue()
         # ring of prefetch_sz + 2 buffers: one being consumed, prefetch_sz ready, one being filled.
@@ -306,55 +347,93 @@ class MaskedSliceWav(ckpt.Checkpoint):
         for k in range(n):
             self._free.put((k, None))
         self._last_k = None
+        self._copy_events = []   # (start, end, bytes) of the newest H2D copies: loader_stats()
+        self._deal_seconds, self._deal_batches = 0.0, 0
+        shape = (self._n_local, self.slice_sz)
         if self._use_cuda:
             import torch
             self._torch = torch
             self._dev = torch.device(self.device or "cuda")
-            shape = (self._n_local, self.slice_sz)
-            self._pin = [(torch.empty(shape, dtype=torch.int32).pin_memory(),
+            wt = torch.float32 if raw else torch.uint8
+            self._pin = [(torch.empty(shape, dtype=wt).pin_memory(),
                           torch.empty(shape, dtype=torch.int32).pin_memory()) for _ in range(n)]
-            self._devbuf = [(torch.empty(shape, dtype=torch.int32, device=self._dev),
-                             torch.empty(shape, dtype=torch.int32, device=self._dev)) for _ in range(n)]
+            # staging copy of the pinned pair + the int32 codes the kernels index with (raw audio: float32, encoded by
+            # the model)
+            self._stage = [torch.empty(shape, dtype=wt, device=self._dev) for _ in range(n)]
+            self._devbuf = [(self._stage[k] if raw else torch.empty(shape, dtype=torch.int32, device=self._dev),
+                             torch.empty(shape, dtype=torch.int32, device=self._dev)) for k in range(n)]
             self._copy_stream = torch.cuda.Stream(device=self._dev)
         else:
-            self._hostbuf = [(np.empty((self._n_local, self.slice_sz), np.int32),
-                              np.empty((self._n_local, self.slice_sz), np.int32)) for _ in range(n)]
-        # The dealer replays the shared file stream for ALL global slots in Python (only lengths for the slots of other
-        # ranks), ~2 ms of interpreter time per batch at 256 slots.  With CPython's default 5 ms switch interval the
-        # training thread can wait that long for the GIL while the GPU runs dry; 0.2 ms bounds the wait.
-        import sys
-        if sys.getswitchinterval() > 2e-4:
-            sys.setswitchinterval(2e-4)
-        self._worker = threading.Thread(target=self._produce, name="wav-loader", daemon=True)
+            self._hostbuf = [(np.empty(shape, np.float32 if raw else np.int32), np.empty(shape, np.int32))
+                             for _ in range(n)]
+        self._worker = threading.Thread(target=self._produce, name="wav-loader", daemon=True,
+                                        args=(self._stop, self._q, self._free, self._dealer))
         self._worker.start()
 
-    def _produce(self):
+    def _produce(self, stop, q, free, dealer):
+        """Loader thread.  Its queues / stop flag / dealer are arguments, not attributes: a restart (_start) replaces the
+        attributes, and a worker that is still finishing a batch must not touch the new ones."""
+        import time
         try:
-            while not self._stop.is_set():
+            while not stop.is_set():
                 try:
-                    k, released = self._free.get(timeout=0.1)
+                    k, released = free.get(timeout=0.1)
                 except queue.Empty:
                     continue
                 if released is not None:
                     released.synchronize()  # the step that read this buffer has finished
+                t0 = time.perf_counter()
                 if self._use_cuda:
                     torch = self._torch
                     pw, pi = self._pin[k]
-                    cnt, _, _ = self._dealer.next_batch(pw.numpy(), pi.numpy())
-                    st = self._dealer.state()
+                    cnt, _, _ = dealer.next_batch(pw.numpy(), pi.numpy())
+                    st = dealer.state()
+                    self._deal_seconds += time.perf_counter() - t0
+                    self._deal_batches += 1
                     dw, di = self._devbuf[k]
                     with torch.cuda.stream(self._copy_stream):
-                        dw.copy_(pw, non_blocking=True)
+                        e0 = torch.cuda.Event(enable_timing=True)
+                        e1 = torch.cuda.Event(enable_timing=True)
+                        e0.record(self._copy_stream)
+                        self._stage[k].copy_(pw, non_blocking=True)
                         di.copy_(pi, non_blocking=True)
+                        e1.record(self._copy_stream)
+                        if dw is not self._stage[k]:
+                            from . import _lib
+                            _lib.check(_lib.load().wn_codes_u8_to_i32(self._stage[k].data_ptr(), dw.data_ptr(), dw.numel(),
+                                                                      self._copy_stream.cuda_stream), "wn_codes_u8_to_i32")
                         ev = torch.cuda.Event()
                         ev.record(self._copy_stream)
-                    self._q.put((cnt, k, ev, st))
+                    self._copy_events.append((e0, e1, pw.numel() * pw.element_size() + pi.numel() * 4))
+                    del self._copy_events[:-64]
+                    q.put((cnt, k, ev, st))
                 else:
                     hw, hi = self._hostbuf[k]
-                    cnt, _, _ = self._dealer.next_batch(hw, hi)
-                    self._q.put((cnt, k, None, self._dealer.state()))
+                    cnt, _, _ = dealer.next_batch(hw, hi)
+                    self._deal_seconds += time.perf_counter() - t0
+                    self._deal_batches += 1
+                    q.put((cnt, k, None, dealer.state()))
         except Exception as e:  # surface loader failures in the consumer
-            self._q.put(e)
+            q.put(e)
+
+    def loader_stats(self) -> dict:
+        """Measured figures of the loader path: host -> device bytes per batch and per timestep, achieved copy
+        bandwidth (CUDA events on the copy stream around the two H2D copies of the newest batches) and the host time
+        the dealer needs per batch."""
+        out = {"batches": self._deal_batches,
+               "deal_ms_per_batch": 1e3 * self._deal_seconds / max(1, self._deal_batches)}
+        if self._use_cuda and self._copy_events:
+            ms, nbytes = 0.0, 0
+            for e0, e1, b in list(self._copy_events):
+                if e1.query():
+                    ms += e0.elapsed_time(e1)
+                    nbytes += b
+            if ms > 0:
+                per_batch = self._copy_events[-1][2]
+                out.update(h2d_bytes_per_batch=per_batch,
+                           h2d_bytes_per_timestep=per_batch / float(self._n_local * self.slice_sz),
+                           h2d_gbs=nbytes / (ms * 1e-3) / 1e9)
+        return out
 
     def next_batch(self) -> Batch:
         """The next [n_local_slots, slice_sz] batch.  Valid until the following next_batch() call."""
@@ -390,7 +469,9 @@ class MaskedSliceWav(ckpt.Checkpoint):
                     self._q.get_nowait()
             except queue.Empty:
                 pass
-            self._worker.join(timeout=5)
+            self._worker.join(timeout=30)
+            if self._worker.is_alive():
+                raise RuntimeError("the wav-loader thread did not stop within 30 s")
             self._worker = None
 
     def __del__(self):

@@ -362,8 +362,16 @@ def loss_fn(a: Arch, logits: torch.Tensor, wav: torch.Tensor, ids: torch.Tensor,
     mask = mask_i.to(logits.dtype)
     lse = torch.logsumexp(lg, dim=2)
     picked = lg.gather(2, labels.clamp(0, a.n_quant - 1).unsqueeze(-1)).squeeze(-1)
-    xent = (lse - picked) * mask  # tmodel.py:235-237
-    diffs = (labels - lg.argmax(dim=2)).abs() * mask_i  # tmodel.py:240-241 (int32 in TF)
+    # tmodel.py:64: tf.one_hot of an out-of-range code is an ALL-ZERO row, so softmax_cross_entropy_with_logits_v2
+    # (tmodel.py:235) returns -sum(0 * log_softmax) = 0 there, argmax(label) (tmodel.py:240) is 0, and the op's
+    # registered gradient is grad_loss * (softmax - labels) = softmax (TF's fused kernel hands back softmax - labels
+    # whatever the labels sum to).  The zero-valued second term carries exactly that gradient through autograd.
+    lab_ok = (labels >= 0) & (labels < a.n_quant)
+    sm = torch.softmax(lg, dim=2).detach()
+    xent_bad = (sm * (lg - lg.detach())).sum(dim=2)
+    xent = torch.where(lab_ok, lse - picked, xent_bad) * mask  # tmodel.py:235-237
+    lab_arg = torch.where(lab_ok, labels, torch.zeros_like(labels))
+    diffs = (lab_arg - lg.argmax(dim=2)).abs() * mask_i  # tmodel.py:240-241 (int32 in TF)
     diff_sum = int(diffs.sum().item())
     avg_diff = diff_sum // diffs.numel() if diffs.numel() else 0  # tmodel.py:242 integer reduce_mean
     n_valid = int(mask_i.sum().item())  # tmodel.py:244
@@ -437,7 +445,9 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
         labels = torch.zeros(B, T, dtype=torch.int64)
         labels[:, :-1] = wav[:, 1:]
         sm = torch.softmax(logits, dim=2)
+        lab_ok = ((labels >= 0) & (labels < a.n_quant))
         onehot = torch.nn.functional.one_hot(labels.clamp(0, a.n_quant - 1), a.n_quant).to(dtype)
+        onehot = onehot * lab_ok.unsqueeze(-1).to(dtype)  # out-of-range code: all-zero one-hot row (tmodel.py:64)
         dlog = _maybe((sm - onehot) * mask.unsqueeze(-1), em)
         g: Dict[str, torch.Tensor] = {}
         flat = lambda t: t.reshape(-1, t.shape[-1])
@@ -508,8 +518,72 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
         n_valid = int((ids[:, 1:] != 0).sum().item())
         lse = torch.logsumexp(logits[:, :-1], dim=2)
         picked = logits[:, :-1].gather(2, wav[:, 1:].clamp(0, a.n_quant - 1).unsqueeze(-1)).squeeze(-1)
-        xent_sum = ((lse - picked) * mask[:, :-1]).sum()
+        xent_sum = ((lse - picked) * lab_ok[:, :-1].to(dtype) * mask[:, :-1]).sum()
     return g, dict(n_valid=n_valid, xent_sum=float(xent_sum), fwd=fwd)
+
+
+# --------------------------------------------------------------------------------------
+# ONE layer in isolation (tests feed it the CUDA path's own stash for layer l, so a defect in a single deep layer is
+# not hidden behind the rounding noise of the 30-50 layers around it).  Same statements as train_forward /
+# train_backward_manual above: reference tmodel.py:117-168 (_dilated_conv), :171-184 (_chan_reduce), :325 (residual add).
+# --------------------------------------------------------------------------------------
+
+
+def layer_single(a: Arch, p: Dict[str, torch.Tensor], li: int, x_full: torch.Tensor, ids: Optional[torch.Tensor] = None,
+                 dz_skip: Optional[torch.Tensor] = None, dx_next: Optional[torch.Tensor] = None,
+                 round_weights: bool = True) -> Dict[str, torch.Tensor]:
+    """x_full [B, dil+T, R] = [SAVE ; x_l] (tmodel.py:127).  Forward: z_l, x_{l+1}.  With dz_skip [B,T,D] (gradient wrt
+    z_l through the skip branch) and dx_next [B,T,R] (gradient wrt x_{l+1}; zeros after the last layer) also the
+    unnormalised backward of the layer: filter / bias gradients, and the data gradient in the split form the CUDA path
+    stores, dx_l[t] = Y[t] + P0[t + dil]  (Y = dx_next + dv . W[1]^T, P0 = dv . W[0]^T; rows t + dil >= T get no P0:
+    the gradient stops at the stage boundary, SAVE is a variable, tmodel.py:123-124,165)."""
+    (b, bl), dil = a.layer_ids()[li], a.dilations()[li]
+    sfx = "{}_{}".format(b, bl)
+    dt = x_full.dtype
+    T = x_full.shape[1] - dil
+
+    def W(name):
+        w = p[name].to(dt)
+        return bf16_round(w) if round_weights else w
+
+    xa, xb = x_full[:, :T, :], x_full[:, dil:dil + T, :]  # x[t-dil], x[t]  (tmodel.py:143-144)
+    v = {}
+    gathered = p["GC_EMBED"].to(dt)[ids] if a.has_gc() else None
+    for nm in ("SIGNAL", "GATE"):
+        filt = W("{}_{}".format(nm, sfx))
+        vv = xa @ filt[0] + xb @ filt[1]
+        if a.use_bias:
+            vv = vv + p["{}_BIAS_{}".format(nm, sfx)].to(dt)
+        if a.has_gc():
+            vv = vv + gathered @ p["GC_{}_{}".format(nm, sfx)].to(dt)
+        v[nm] = vv
+    th, sg = torch.tanh(v["SIGNAL"]), torch.sigmoid(v["GATE"])
+    z = th * sg
+    sig = z @ W("RESIDUAL_" + sfx)
+    if a.use_bias:
+        sig = sig + p["RESIDUAL_BIAS_" + sfx].to(dt)
+    out = dict(z=z, x_next=xb + sig)
+    if dz_skip is None:
+        return out
+    flat = lambda t: t.reshape(-1, t.shape[-1])
+    dz = dz_skip + dx_next @ W("RESIDUAL_" + sfx).T
+    dvs = dz * sg * (1 - th * th)
+    dvg = dz * th * sg * (1 - sg)
+    out["RESIDUAL_" + sfx] = flat(z).T @ flat(dx_next)
+    if a.use_bias:
+        out["RESIDUAL_BIAS_" + sfx] = flat(dx_next).sum(0)
+    for nm, dv in (("SIGNAL", dvs), ("GATE", dvg)):
+        out["{}_{}".format(nm, sfx)] = torch.stack([flat(xa).T @ flat(dv), flat(xb).T @ flat(dv)])
+        if a.use_bias:
+            out["{}_BIAS_{}".format(nm, sfx)] = flat(dv).sum(0)
+    Ws, Wg = W("SIGNAL_" + sfx), W("GATE_" + sfx)
+    out["Y"] = dx_next + dvs @ Ws[1].T + dvg @ Wg[1].T
+    out["P0"] = dvs @ Ws[0].T + dvg @ Wg[0].T
+    dx = out["Y"].clone()
+    if T > dil:
+        dx[:, :T - dil, :] += out["P0"][:, dil:, :]
+    out["dx"] = dx
+    return out
 
 
 # --------------------------------------------------------------------------------------
@@ -656,6 +730,7 @@ class GenOracle:
         self.p = {k: torch.tensor(np.asarray(v), dtype=dtype) for k, v in p_np.items()
                   if np.asarray(v).dtype.kind == "f" and not k.startswith("SAVE")}
         self.rings = [torch.zeros(n_streams, d, a.n_res, dtype=dtype) for d in a.dilations()]
+        self._w: Dict[str, torch.Tensor] = {}
         self.t = 0
         self.cur_code = np.full(n_streams, -1, np.int64)  # -1 == all-zero input vector
         self.gc = None
@@ -664,7 +739,10 @@ class GenOracle:
             self.gc = self.p["GC_EMBED"][torch.as_tensor(g)]  # imodel.py:53-56
 
     def W(self, name):
-        return _maybe(self.p[name], self.em)
+        w = self._w.get(name)
+        if w is None:  # the weights never change during a run: round them once
+            w = self._w[name] = _maybe(self.p[name], self.em)
+        return w
 
     def step_logits(self) -> torch.Tensor:
         """Consume self.cur_code, advance all rings one timestep, return logits [B, Q]."""

@@ -1,0 +1,190 @@
+"""GPU tests of the host-side paths around the kernels: the loader's pinned-buffer / copy-stream / event-recycling
+path (reference data.py:230-293 surface), a 2-rank NCCL step against the 1-rank step, and
+train.py -> checkpoint -> generate.py end to end (reference train.py:216-252, generate.py:32-117)."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wavenet_oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _catalog(n_files, seed, lo=150, hi=900, dtype=np.int32):
+    rng = np.random.default_rng(seed)
+    return [(int(rng.integers(1, 11)), rng.integers(0, 256, int(rng.integers(lo, hi))).astype(dtype))
+            for _ in range(n_files)]
+
+
+@pytest.mark.parametrize("file_dtype", [np.int32, np.uint8, np.int64])
+def test_masked_slice_wav_device_batches_equal_the_dealer(lib, file_dtype):
+    """Every batch MaskedSliceWav hands out on the device (uint8 codes + int32 ids copied from pinned buffers on the
+    copy stream, codes widened by wn_codes_u8_to_i32) equals, bit for bit, what the slot dealer -- itself bit-exact
+    against the oracle's restatement of data.py:110-227 (tests/test_abi_and_host.py) -- deals for the same seed, across
+    several recyclings of the 4-buffer ring and with a consumer that lags behind the producer."""
+    from lb_wavenet_b200 import data as wdata
+    B, T, F = 6, 1000, 120
+    cat = _catalog(9, 3, dtype=file_dtype)
+    ds = wdata.MaskedSliceWav(None, None, 16000, T, 2, 0, 1, B, 1, "/tmp/t.dset", 0, device="cuda", random_seed=17)
+    ds.init_sample_catalog(entries=cat)
+    ds.set_receptive_field_size(F)
+    ds.build()
+    ds.init_vars()
+    ref = wdata.SlotDealer(cat, B, T, F, 1, 17, 0, quiet=True)
+    junk = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    for n in range(14):
+        b = ds.next_batch()
+        cnt, w, i = ref.next_batch()
+        assert b.wav.dtype == torch.int32 and b.ids.dtype == torch.int32 and b.wav.is_cuda
+        if n % 3 == 0:
+            junk.zero_()  # keep the compute stream busy: the buffer must not be recycled under the consumer
+        got_w, got_i = b.wav.cpu().numpy(), b.ids.cpu().numpy()
+        assert b.file_read_count == cnt
+        assert np.array_equal(got_w, w), n
+        assert np.array_equal(got_i, i), n
+    st = ds.loader_stats()
+    assert st["h2d_bytes_per_timestep"] == 5.0   # uint8 code + int32 id
+    ds._shutdown()
+
+
+def test_masked_slice_wav_raw_float_input(lib):
+    """wav_input_type == 'raw' (reference tmodel.py:59-62): float audio travels as float32 and is mu-law encoded on
+    the device by the model; integer transport of such files is refused instead of silently truncating to 0."""
+    from lb_wavenet_b200 import data as wdata
+    from lb_wavenet_b200._lib import WaveNetLibError
+    B, T, F = 3, 400, 50
+    rng = np.random.default_rng(5)
+    cat = [(int(rng.integers(1, 5)), rng.uniform(-1, 1, int(rng.integers(100, 600))).astype(np.float32)) for _ in range(7)]
+    ds = wdata.MaskedSliceWav(None, None, 16000, T, 2, 0, 1, B, 1, "/tmp/t2.dset", 0, device="cuda", random_seed=1,
+                              wav_input_type="raw")
+    ds.init_sample_catalog(entries=cat)
+    ds.set_receptive_field_size(F)
+    ds.build()
+    ds.init_vars()
+    ref = wdata.SlotDealer(cat, B, T, F, 1, 1, 0, quiet=True, wav_dtype="f32")
+    for n in range(6):
+        b = ds.next_batch()
+        _, w, i = ref.next_batch()
+        assert b.wav.dtype == torch.float32
+        assert np.array_equal(b.wav.cpu().numpy(), w) and np.array_equal(b.ids.cpu().numpy(), i)
+    ds._shutdown()
+    with pytest.raises(WaveNetLibError):
+        wdata.SlotDealer(cat, B, T, F, 1, 1, 0, quiet=True, wav_dtype="u8").next_batch()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+_RANK_SCRIPT = r'''
+import os, sys, json, numpy as np, torch
+sys.path.insert(0, %(root)r)
+from lb_wavenet_b200.dist import DistContext
+from lb_wavenet_b200.tmodel import WaveNetTrain, AdamOptimizer
+from lb_wavenet_b200.data import SlotDealer
+from tests import util
+arch = dict(util.CLASSIC_SHALLOW, n_lc_in=0, n_lc_out=0, lc_upsample=[], wav_input_type="mu_law_quant")
+B, T = 4, 512
+ctx = DistContext.from_env("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
+torch.cuda.set_device(ctx.local_rank)
+net = WaveNetTrain(**arch, batch_sz=B, l2_factor=1e-3, add_summary=False, n_keep_checkpoints=1, ckpt_path="/tmp/nccl.net",
+                   resume_step=0, n_valid_total=1, print_interval=0, dist=ctx, init_seed=5, device="cuda:%%d" %% ctx.local_rank)
+net.build()
+net.init_vars()
+opt = AdamOptimizer(1e-3)
+rng = np.random.default_rng(0)
+cat = [(int(rng.integers(1, 11)), rng.integers(0, 256, int(rng.integers(300, 900))).astype(np.int32)) for _ in range(9)]
+lo, hi = ctx.slot_range(B)
+deal = SlotDealer(cat, B, T, net.get_recep_field_sz(), 1, 5, 0, lo, hi, quiet=True)
+losses = []
+for step in range(3):
+    _, w, i = deal.next_batch()
+    losses.append(net.train_step(torch.as_tensor(w), torch.as_tensor(i), opt))
+torch.cuda.synchronize()
+if ctx.rank == 0:
+    st = {k: v.tolist() for k, v in net.engine.export_state().items() if not k.startswith("SAVE")}
+    json.dump(dict(losses=losses, state=st, mode=net._allreduce_mode() if ctx.world > 1 else "none"), open(sys.argv[1], "w"))
+ctx.barrier()
+if ctx.world > 1:
+    torch.distributed.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("mode", ["single", "buckets"])
+def test_two_rank_nccl_step_equals_one_rank_step(lib, tmp_path, mode):
+    """3 optimiser steps with the 4 slots sharded over 2 GPUs (NCCL all-reduce of statistics + gradient arena, both
+    all-reduce schedules) == the same 3 steps on one GPU: losses to 1e-5 relative, weights to the fp32 atomics'
+    summation-order noise."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "rank.py"
+    script.write_text(_RANK_SCRIPT % dict(root=ROOT))
+    env = dict(os.environ, WN_ALLREDUCE=mode)
+    env.pop("RANK", None); env.pop("WORLD_SIZE", None); env.pop("LOCAL_RANK", None)
+    one, two = str(tmp_path / "one.json"), str(tmp_path / "two.json")
+    subprocess.run([sys.executable, str(script), one], check=True, env=env, cwd=ROOT, timeout=600)
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                    "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script), two],
+                   check=True, env=env, cwd=ROOT, timeout=600)
+    a, b = json.load(open(one)), json.load(open(two))
+    assert b["mode"] == mode
+    for la, lb in zip(a["losses"], b["losses"]):
+        assert abs(la - lb) <= 1e-5 * abs(la), (a["losses"], b["losses"])
+    for k in a["state"]:
+        x, y = np.asarray(a["state"][k]), np.asarray(b["state"][k])
+        # 3 Adam steps of <= 1e-3 each; a gradient element near zero may flip its (sign-like) first steps
+        assert np.abs(x - y).max() <= 2.5e-3, k
+        assert util.rel_err(y - 0, x - 0) <= 2e-3, k
+
+
+def test_train_cli_checkpoint_then_generate_cli(lib, tmp_path):
+    """train.py -> checkpoint -> generate.py with the reference's own command lines (train.py:12-65,
+    generate.py:5-29): a catalog TSV of .npy mu-law files, 6 optimiser steps with a save at step 4, then 0.02 s (320 samples)
+    for 3 streams written as gen.i{n}.wav (generate.py:114)."""
+    rng = np.random.default_rng(0)
+    d = tmp_path
+    lines = []
+    for n in range(6):
+        t = np.arange(int(rng.integers(3000, 6000)))
+        x = 0.5 * np.sin(t * 0.05 * (n + 1)) + 0.05 * rng.normal(size=t.shape)
+        np.save(d / ("f%d.npy" % n), O.mu_encode_np(np.clip(x, -1, 1).astype(np.float32)).astype(np.int32))
+        lines.append("%d\t%s\t%s" % (n % 3 + 1, d / ("f%d.npy" % n), "none"))
+    (d / "samples.tsv").write_text("\n".join(lines) + "\n")
+    arch = dict(n_blocks=2, n_block_layers=5, n_quant=256, n_res=32, n_dil=32, n_skip=256, n_post=256, n_gc_embed=16,
+                n_gc_category=3, n_lc_in=0, n_lc_out=0, lc_upsample=[], use_bias=True, wav_input_type="mu_law_quant")
+    par = dict(batch_sz=4, sample_rate=16000, slice_sz=1024, l2_factor=1e-3, learning_rate=1e-3, prefetch_sz=2,
+               add_summary=False, n_keep_checkpoints=3, n_valid_total=100000)
+    (d / "arch.json").write_text(json.dumps(arch))
+    (d / "par.json").write_text(json.dumps(par))
+    pfx = str(d / "ck")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "train.py"), "-ms", "7", "-si", "4", "-pi", "1", pfx,
+                        str(d / "arch.json"), str(d / "par.json"), str(d / "samples.tsv")],
+                       capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert os.path.exists(pfx + ".net-4.index") and os.path.exists(pfx + ".net-4.data-00000-of-00001"), os.listdir(d)
+    rows = [l.split("\t") for l in r.stderr.splitlines() if l.strip() and l.split("\t")[0].strip().isdigit()]
+    assert len(rows) >= 5
+    losses = [float(x[1]) for x in rows]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]   # it learns
+    out = d / "gen"
+    out.mkdir()
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "generate.py"), "-g", "0.02", "-s", "16000", "-b", "3",
+                        "-c", "100", "--seed", "3", str(d / "arch.json"), pfx + ".net-4", str(out)],
+                       capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import wave
+    for n in range(3):
+        with wave.open(str(out / ("gen.i%d.wav" % n))) as wf:
+            assert wf.getnframes() == 320 and wf.getframerate() == 16000

@@ -105,10 +105,13 @@ def test_stagewise_equals_whole(lib):
         assert torch.equal(eng.save_view(l), eng2.save_view(l))
 
 
+# The deep stacks (3x10, arch1's 5x10) are compared at the benchmark's stage length in tests/test_gpu_full.py, where
+# the per-tensor bound is 8 %, plus layer by layer in isolation (1e-2): at a few hundred positions the bf16 gradient
+# floor of a 30-50 layer stack (~1/sqrt(positions)) would force a tolerance that proves nothing.
 @pytest.mark.parametrize("arch,B,T", [(util.TINY, 3, 96), (util.TINY_GC, 2, 130), (util.TINY_ASYM, 2, 64),
-                                      (util.WIDE, 1, 70), (util.WIDE, 2, 128), (util.CLASSIC, 2, 300),
+                                      (util.WIDE, 1, 70), (util.WIDE, 2, 128),
                                       (util.CLASSIC_SHALLOW, 3, 200),
-                                      (util.TINY_NOBIAS, 2, 64), (util.C1, 2, 160), (util.CLASSIC_SHALLOW, 2, 1000),
+                                      (util.TINY_NOBIAS, 2, 64), (util.CLASSIC_SHALLOW, 2, 1000),
                                       (util.WIDE_DEEP, 1, 1088)])
 def test_gradients_match_oracle(lib, arch, B, T):
     a, p, wav, ids, eng, logits = _run_fwd(arch, B, T, 11)
@@ -133,17 +136,14 @@ def test_gradients_match_oracle(lib, arch, B, T):
     util.record("grad_parity_R%d_S%d_L%d_B%d_T%d" % (arch["n_res"], arch["n_skip"], a.n_layers, B, T),
                 dict(max_vs_emulated=max(vs_em.values()), median_vs_emulated=float(np.median(list(vs_em.values()))),
                      max_vs_fp64=max(vs_ex.values()), median_vs_fp64=float(np.median(list(vs_ex.values())))))
-    # same rounding points -> tight; fp64 -> loose (the bf16 FORWARD dominates: near-cancelling
-    # random-init gradients amplify the ~1% logit error, see DESIGN.md "Numerics")
-    # a 30-layer stack amplifies every 1-ulp bf16 flip of the residual stream chaotically: there the
-    # kernel is as far from the same-rounding oracle as that oracle is from fp64 (measured ~9% median)
-    deep = a.n_layers >= 16
+    # same rounding points -> tight; fp64 -> loose (the bf16 FORWARD dominates: at a few hundred positions the random-init
+    # gradients nearly cancel and amplify the ~0.5 % logit error, see DESIGN.md "Numerics")
     # the wide-layer GEMM path keeps dz as a bf16 plane and adds the residual branch to it in place (one more bf16
     # rounding per layer than the emulated oracle has): 10 wide layers measured 3.1 % median, 5.6 % max
     wide_stack = arch["n_res"] >= 64 and a.n_layers >= 8
-    bad = {k: v for k, v in vs_em.items() if v > (0.3 if deep else 0.1 if wide_stack else 6e-2)}
+    bad = {k: v for k, v in vs_em.items() if v > (0.08 if wide_stack else 6e-2)}
     assert not bad, ("vs emulated oracle", bad)
-    bad = {k: v for k, v in vs_ex.items() if v > (0.35 if deep else 0.2)}
+    bad = {k: v for k, v in vs_ex.items() if v > 0.2}
     assert not bad, ("vs fp64 oracle", bad)
 
 
@@ -297,6 +297,22 @@ def test_all_invalid_batch_and_out_of_range_codes(lib):
     for b, t in ((0, 10), (1, 20), (1, 21)):
         assert np.array_equal(x0[b, t], bias)          # zero one-hot row -> bias only, bit exact
     assert np.abs(logits - em.logits.numpy()).max() <= 0.05
+    # an out-of-range LABEL is an all-zero one-hot row too (tmodel.py:64,230,235): its cross entropy is 0, argmax(label)
+    # is 0 and dlogits = softmax (TF's fused kernel: softmax - labels) -- statistics and dlogits against the oracle
+    w, i = torch.as_tensor(wav).long(), torch.as_tensor(ids).long()
+    st = eng2.read_stats()
+    Lk = O.loss_fn(a, torch.as_tensor(logits, dtype=torch.float64), w, i, pt, kinds, 0.0)
+    assert st["n_valid"] == Lk.n_valid and st["diff_sum"] == Lk.diff_sum
+    assert abs(st["xent_sum"] - float(Lk.xent_sum)) <= 1e-4 * float(Lk.xent_sum)
+    eng2.backward()
+    dl = eng2.debug_read(4, 0).cpu().numpy()
+    sm = torch.softmax(torch.as_tensor(logits, dtype=torch.float64), dim=2).numpy()
+    for b, t in ((0, 9), (1, 19), (1, 20)):   # logits[t] is scored against wav[t + 1]
+        assert np.abs(dl[b, t] - sm[b, t]).max() <= 4e-3, (b, t)      # no "-1" anywhere in the row
+        assert abs(dl[b, t].sum() - 1.0) <= 2e-2
+    gm, _ = O.train_backward_manual(a, pt, save, w, i, torch.float64, emulate_bf16=True)
+    for name in ("POST2_BIAS", "POST1", "SKIP_0_1", "PRE"):
+        assert util.rel_err(eng2.view(name, eng2.grads).cpu().numpy(), gm[name].numpy()) <= 6e-2, name
 
 
 @pytest.mark.parametrize("B,T", [(1, 2), (1, 129), (5, 128)])

@@ -303,3 +303,86 @@ def test_bf16_gradient_error_floor():
                                     torch.float64, emulate_bf16=True)
     errs = [util.rel_err(gm[k].numpy() / L.n_valid, grads[k]) for k in grads if np.abs(grads[k]).max() > 0]
     assert 0.01 < np.median(errs) < 0.08 and max(errs) < 0.2
+
+
+def test_out_of_range_code_is_an_all_zero_one_hot_row():
+    """reference tmodel.py:64 (tf.one_hot) + :230-236: an out-of-range mu-law code is an all-zero one-hot row both as an
+    INPUT (PRE contributes only its bias) and as a LABEL: softmax_cross_entropy_with_logits_v2 then returns
+    -sum(0 * log_softmax) = 0, tf.argmax of the zero row is 0, and the op's registered gradient is
+    grad_loss * (softmax - labels) = softmax.  Both backward statements of the oracle carry exactly that."""
+    arch = util.TINY
+    a = util.oracle_arch(arch)
+    B, T = 2, 40
+    p = util.scaled_params(a, B, 3)
+    wav, _ = util.synth_batch(B, T, 3, 4)
+    wav = wav.copy()
+    wav[0, 10], wav[1, 20] = 256, -7
+    ids = np.ones((B, T), np.int32)
+    pt, save, kinds = O.to_torch_params(a, p, B, torch.float64, requires_grad=False)
+    w, i = torch.as_tensor(wav).long(), torch.as_tensor(ids).long()
+    fwd = O.train_forward(a, pt, save, w, i, torch.float64, keep=True)
+    bias = pt["PRE_BIAS"]
+    assert torch.equal(fwd.xs[0][0, 10], bias) and torch.equal(fwd.xs[0][1, 20], bias)
+    L = O.loss_fn(a, fwd.logits, w, i, pt, kinds, 0.0)
+    # the same batch with in-range labels at those two positions differs by exactly their two cross entropies
+    wav2 = wav.copy()
+    wav2[0, 10], wav2[1, 20] = 5, 9
+    lg = fwd.logits
+    lse = torch.logsumexp(lg, dim=2)
+    extra = (lse[0, 9] - lg[0, 9, 5]) + (lse[1, 19] - lg[1, 19, 9])
+    L2 = O.loss_fn(a, lg, torch.as_tensor(wav2).long(), i, pt, kinds, 0.0)
+    assert L.n_valid == L2.n_valid == B * (T - 1)
+    assert abs(float(L2.xent_sum - L.xent_sum - extra)) < 1e-9
+    am = lg.argmax(dim=2)
+    assert L.diff_sum - L2.diff_sum == int(am[0, 9] + am[1, 19]) - int(abs(5 - am[0, 9]) + abs(9 - am[1, 19]))
+    # gradient wrt the logits of such a row is softmax / n_valid (autograd statement) ...
+    lgr = lg.clone().requires_grad_(True)
+    O.loss_fn(a, lgr, w, i, pt, kinds, 0.0).total.backward()
+    sm = torch.softmax(lg, dim=2)
+    assert torch.allclose(lgr.grad[0, 9] * L.n_valid, sm[0, 9], atol=1e-12)
+    assert torch.allclose(lgr.grad[1, 19] * L.n_valid, sm[1, 19], atol=1e-12)
+    # ... and the two full backward statements agree on every parameter
+    grads, La, _ = O.train_step_autograd(a, p, wav, ids, 0.0, torch.float64)
+    gman, info = O.train_backward_manual(a, pt, save, w, i, torch.float64)
+    assert abs(info["xent_sum"] - float(La.xent_sum)) < 1e-9
+    for k in grads:
+        assert np.allclose(grads[k] * La.n_valid, gman[k].numpy(), rtol=1e-9, atol=1e-10), k
+
+
+def test_single_layer_statement_composes_to_the_stack():
+    """oracle.layer_single (one layer of tmodel.py:117-184,325 in isolation, used by the per-layer GPU tests) chained
+    over the layers reproduces train_forward, and its backward reproduces the hand-written whole-stack backward."""
+    arch = util.TINY_GC
+    a = util.oracle_arch(arch)
+    B, T = 2, 50
+    p = util.scaled_params(a, B, 13)
+    wav, ids = util.synth_batch(B, T, arch["n_gc_category"], 14)
+    pt, save, kinds = O.to_torch_params(a, p, B, torch.float64, requires_grad=False)
+    w, i = torch.as_tensor(wav).long(), torch.as_tensor(ids).long()
+    fwd = O.train_forward(a, pt, save, w, i, torch.float64, keep=True)
+    x = fwd.xs[0]
+    for l in range(a.n_layers):
+        o = O.layer_single(a, pt, l, torch.cat([save[l], x], dim=1), i, round_weights=False)
+        assert torch.allclose(o["z"], fwd.zs[l], atol=1e-12)
+        x = o["x_next"]
+    assert torch.allclose(x, fwd.x_out, atol=1e-12)
+    # backward: rebuild every layer's gradient from layer_single, walking down from the post-net
+    gman, _ = O.train_backward_manual(a, pt, save, w, i, torch.float64)
+    lg = fwd.logits
+    mask = torch.zeros(B, T, dtype=torch.float64)
+    mask[:, :-1] = (i[:, 1:] != 0).double()
+    labels = torch.zeros(B, T, dtype=torch.int64)
+    labels[:, :-1] = w[:, 1:]
+    dlog = (torch.softmax(lg, 2) - torch.nn.functional.one_hot(labels, a.n_quant).double()) * mask.unsqueeze(-1)
+    h1 = torch.relu(fwd.skip_sum)
+    h2 = torch.relu(h1 @ pt["POST1"] + pt["POST1_BIAS"])
+    dskip = ((dlog @ pt["POST2"].T) * (h2 > 0) @ pt["POST1"].T) * (h1 > 0)
+    dx = torch.zeros(B, T, a.n_res, dtype=torch.float64)
+    for l in reversed(range(a.n_layers)):
+        sfx = "%d_%d" % a.layer_ids()[l]
+        o = O.layer_single(a, pt, l, torch.cat([save[l], fwd.xs[l]], dim=1), i, dskip @ pt["SKIP_" + sfx].T, dx,
+                           round_weights=False)
+        for nm in ("SIGNAL", "GATE", "RESIDUAL", "SIGNAL_BIAS", "GATE_BIAS", "RESIDUAL_BIAS"):
+            assert torch.allclose(o["%s_%s" % (nm, sfx)], gman["%s_%s" % (nm, sfx)], rtol=1e-9, atol=1e-11), (nm, l)
+        dx = o["dx"]
+    assert torch.allclose(dx.reshape(-1, a.n_res).sum(0), gman["PRE_BIAS"], rtol=1e-9, atol=1e-11)

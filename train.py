@@ -93,7 +93,8 @@ def main(argv=None):
     dset_ckpt = "{}.dset".format(args.ckpt_path)
     dset = data.MaskedSliceWav(None, args.sam_file, par["sample_rate"], par["slice_sz"], par["prefetch_sz"],
                                arch_n["n_lc_in"], mel_hop_sz, par["batch_sz"], par["n_keep_checkpoints"], dset_ckpt,
-                               args.resume_step or 0, dist=ctx, random_seed=seed)
+                               args.resume_step or 0, dist=ctx, random_seed=seed,
+                               wav_input_type=arch_n.get("wav_input_type", "mu_law_quant"))
     dset.init_sample_catalog()
 
     if args.num_global_cond is not None:  # train.py:140-146
