@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libwavenet_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["model.cpp", "dealer.cpp", "train_kernels.cu", "train_umma.cu", "layer_umma.cu", "gen_kernels.cu", "gen_umma.cu", "selftest.cu"]
+SOURCES = ["model.cpp", "dealer.cpp", "train_kernels.cu", "train_umma.cu", "layer_umma.cu", "gen_kernels.cu", "gen_mma.cu", "selftest.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -17,13 +17,13 @@
 
 namespace wn {
 
-// generation 2 (gen_umma.cu)
+// generation 2 (gen_mma.cu)
 bool gen2_supported(const wn_model* m);
 int64_t gen2_blob_bytes(const wn_model* m);
 int gen2_prepare(wn_model* m, const float* d_params, unsigned char* blob, cudaStream_t st);
 int gen2_run(wn_model* m, const unsigned char* blob, const int64_t* ring_off, bf16* rings, int32_t* codes,
              int n_streams, int64_t t0, int n_steps, uint64_t seed, const int32_t* teacher, int n_teacher, int32_t* out,
-             float* logits, cudaStream_t st);
+             float* logits, const float* gcproj, cudaStream_t st);
 
 __constant__ uint32_t c_mu_thr[255];
 __constant__ uint32_t c_mu_dec[256];
@@ -81,7 +81,7 @@ struct GenLayout {
   int64_t wbf;       // bf16 mirror of the parameter arena
   int64_t pf32;      // fp32 copy of the arena (PRE table, biases)
   int64_t gcproj;    // fp32 [n_streams][L][2D]
-  int64_t blob2;     // generation-2 fragment-ready weight blob (gen_umma.cu)
+  int64_t blob2;     // generation-2 fragment-ready weight blob (gen_mma.cu)
   int64_t rings;     // bf16, layer l: [n_streams][dil][R]
   int64_t ring_elems;
   int64_t total;
@@ -385,7 +385,8 @@ int wn_gen_run(wn_model* m, void* d_gws, int32_t n_streams, int64_t t0, int32_t 
   if (gen2_supported(m))
     return gen2_run(m, ws + g.blob2, reinterpret_cast<const int64_t*>(ws + g.ring_off),
                     reinterpret_cast<bf16*>(ws + g.rings), reinterpret_cast<int32_t*>(ws + g.codes), n_streams, t0,
-                    n_steps, seed, d_teacher, d_teacher ? n_teacher : 0, d_out, d_logits, st);
+                    n_steps, seed, d_teacher, d_teacher ? n_teacher : 0, d_out, d_logits,
+                    m->a.n_gc_embed > 0 ? reinterpret_cast<const float*>(ws + g.gcproj) : nullptr, st);
   GenArgs a;
   memset(&a, 0, sizeof(a));
   a.wbf = reinterpret_cast<const bf16*>(ws + g.wbf);

@@ -11,9 +11,14 @@
 //   * skip accumulators stay in registers across the 30 layers (each warp owns 32 skip channels);
 //   * the input embedding bf16(PRE[code] + bias) is a 16 KB shared-memory table.
 // 8 compute warps + 1 producer warp.  Two named barriers per layer.
-// Shapes: R = D = 32, S = P = 256, Q = 256, no global conditioning (others: generation-1 kernel k_gen).
+// Shapes: R = D = 32, Q = 256, S and P in {256, 512}, with or without global conditioning -- i.e. the classic 3x10
+// stack that is benchmarked AND every R = D = 32 architecture the reference ships (par/arch1.json, arch3.json:
+// S = P = 512, arch1 with a 17-wide voice embedding).  Global conditioning (imodel.py:53-56,113-118) is a per-stream,
+// per-layer constant: the projections gc_embed[id] . GC_SIGNAL|GATE_l are computed once per launch sequence
+// (wn_gen_load_params) and read as a per-row bias in the gate, prefetched one layer ahead.  Other shapes: k_gen.
 #include <algorithm>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -26,43 +31,45 @@ using namespace umma;
 
 namespace g2 {
 constexpr int GS = 16;            // streams per CTA
-constexpr int R = 32, D = 32, S = 256, P = 256, Q = 256;
+constexpr int R = 32, D = 32, Q = 256;   // S, P: template parameters of k_gen2 (256 or 512)
 constexpr int NCW = 8;            // compute warps
 constexpr int THREADS = (NCW + 1) * 32;
-constexpr int SLOT = 27 * 1024;    // weight ring slot: one layer item (conv | residual | biases | SKIP_l) or one post-net chunk
-constexpr int NSLOT = 5;
+// weight ring slot: one layer item (conv | residual | biases | SKIP_l) or one post-net K slice; S = 256: 5 slots of
+// 27 KB, S or P = 512: 3 slots of 43 KB (the 512-wide activation tiles need the rest of the 227 KB)
+constexpr int slot_bytes(int S, int P) { return ((10752 + (S > P ? S : P) * 64 + 1023) / 1024) * 1024; }
+constexpr int n_slots(int S, int P) { return (S > 256 || P > 256) ? 3 : 5; }
 constexpr int OLD_W = 8;           // rolling window of prefetched x[t-dil] tiles (one per layer position)
 constexpr int OLD_LA = 6;          // ... issued this many layer positions ahead
 // fragment-ready block: [n-tile][k-step][lane][2 x u32]  (256 B per (n-tile, k-step))
 constexpr int CONV_BYTES = 8 * 4 * 256;   // N = 64 (signal | gate), K = 64 (x[t-dil] | x[t])
 constexpr int RES_BYTES = 4 * 2 * 256;    // N = 32, K = 32
 constexpr int LAYER_A_BYTES = CONV_BYTES + RES_BYTES + 512;  // + biases: sig[32] gate[32] res[32] fp32 (pad to 512)
-constexpr int CHUNK_BYTES = 32 * 2 * 256; // N = 256, two k-steps (K = 32): SKIP_l, or a K-slice of POST1 / POST2
+constexpr int chunk_bytes(int N) { return (N / 8) * 2 * 256; }  // [N / 8 n-tiles][2 k-steps (K = 32)]: SKIP_l, or a K slice of POST1 / POST2
 constexpr int XP = 40;            // padded row (bf16 elements) of the 32-wide activation tiles
-constexpr int HP = 264;           // padded row of the 256-wide activation tiles
+constexpr int hp(int S, int P) { return (S > P ? S : P) + 8; }   // padded row of the S / P-wide activation tiles
 constexpr int LP = 264;           // padded row (floats) of the logits tile: rows g, g + 1 land in different banks
 }  // namespace g2
 
 struct Gen2Layout {  // byte offsets inside the generation-2 weight blob (device memory)
   int64_t layer_a;   // L x LAYER_A_BYTES
-  int64_t skip;      // L x CHUNK_BYTES
-  int64_t post1;     // 8 x CHUNK_BYTES
-  int64_t post2;     // 8 x CHUNK_BYTES
+  int64_t skip;      // L x chunk_bytes(S)
+  int64_t post1;     // S / 32 x chunk_bytes(P)
+  int64_t post2;     // P / 32 x chunk_bytes(Q)
   int64_t x0tab;     // bf16 [257][32]: bf16(PRE[code] + bias), row 256 = all-zero input
-  int64_t biases;    // fp32: skip-bias sum [256] | POST1_BIAS [256] | POST2_BIAS [256]
+  int64_t biases;    // fp32: skip-bias sum [S] | POST1_BIAS [P] | POST2_BIAS [Q]
   int64_t total;
 };
 
-static Gen2Layout gen2_layout(int L) {
+static Gen2Layout gen2_layout(int L, int S, int P) {
   Gen2Layout g;
   int64_t off = 0;
   auto take = [&](int64_t b) { int64_t o = off; off = align_up(off + b, 1024); return o; };
   g.layer_a = take((int64_t)L * g2::LAYER_A_BYTES);
-  g.skip = take((int64_t)L * g2::CHUNK_BYTES);
-  g.post1 = take(8 * g2::CHUNK_BYTES);
-  g.post2 = take(8 * g2::CHUNK_BYTES);
+  g.skip = take((int64_t)L * g2::chunk_bytes(S));
+  g.post1 = take((int64_t)(S / 32) * g2::chunk_bytes(P));
+  g.post2 = take((int64_t)(P / 32) * g2::chunk_bytes(g2::Q));
   g.x0tab = take(257 * 32 * 2);
-  g.biases = take(3 * 256 * 4);
+  g.biases = take((int64_t)(S + P + g2::Q) * 4);
   g.total = off;
   return g;
 }
@@ -76,7 +83,7 @@ __device__ __forceinline__ uint32_t frag_pack(float lo, float hi) {
 // Builds the fragment-ready blob from the fp32 arena.  One block per (kind, index).
 __global__ void k_gen2_prep(const float* __restrict__ p, const LayerDesc* __restrict__ layers, int L, int64_t off_pre,
                             int64_t off_pre_b, int64_t off_post1, int64_t off_post1_b, int64_t off_post2,
-                            int64_t off_post2_b, unsigned char* __restrict__ blob, Gen2Layout g) {
+                            int64_t off_post2_b, unsigned char* __restrict__ blob, Gen2Layout g, int S, int P) {
   using namespace g2;
   const int bid = blockIdx.x, tid = threadIdx.x;
   auto frag_store = [&](uint32_t* dst, int nt, int ks, int nks, auto Bfun) {
@@ -107,15 +114,15 @@ __global__ void k_gen2_prep(const float* __restrict__ p, const LayerDesc* __rest
       else if (i >= 64 && i < 96 && ld.res_b >= 0) v = p[ld.res_b + i - 64];
       bias[i] = v;
     }
-    frag_store(reinterpret_cast<uint32_t*>(blob + g.skip + (size_t)bid * CHUNK_BYTES), 32, 0, 2,
+    frag_store(reinterpret_cast<uint32_t*>(blob + g.skip + (size_t)bid * chunk_bytes(S)), S / 8, 0, 2,
                [&](int k, int n) { return p[ld.skip + (int64_t)k * S + n]; });
-  } else if (bid < L + 8) {
+  } else if (bid < L + S / 32) {
     const int c = bid - L;  // K slice [32c, 32c+32) of POST1 [S][P]
-    frag_store(reinterpret_cast<uint32_t*>(blob + g.post1 + (size_t)c * CHUNK_BYTES), 32, 0, 2,
+    frag_store(reinterpret_cast<uint32_t*>(blob + g.post1 + (size_t)c * chunk_bytes(P)), P / 8, 0, 2,
                [&](int k, int n) { return p[off_post1 + (int64_t)(c * 32 + k) * P + n]; });
-  } else if (bid < L + 16) {
-    const int c = bid - L - 8;
-    frag_store(reinterpret_cast<uint32_t*>(blob + g.post2 + (size_t)c * CHUNK_BYTES), 32, 0, 2,
+  } else if (bid < L + S / 32 + P / 32) {
+    const int c = bid - L - S / 32;
+    frag_store(reinterpret_cast<uint32_t*>(blob + g.post2 + (size_t)c * chunk_bytes(Q)), Q / 8, 0, 2,
                [&](int k, int n) { return p[off_post2 + (int64_t)(c * 32 + k) * Q + n]; });
   } else {
     bf16* tab = reinterpret_cast<bf16*>(blob + g.x0tab);
@@ -126,9 +133,9 @@ __global__ void k_gen2_prep(const float* __restrict__ p, const LayerDesc* __rest
       tab[i] = f2bf(v);
     }
     float* b = reinterpret_cast<float*>(blob + g.biases);
-    for (int i = tid; i < 768; i += blockDim.x) {
+    for (int i = tid; i < S + P + Q; i += blockDim.x) {
       float v = 0.f;
-      const int which = i >> 8, c = i & 255;
+      const int which = i < S ? 0 : i < S + P ? 1 : 2, c = i < S ? i : i < S + P ? i - S : i - S - P;
       if (which == 0) {
         for (int l = 0; l < L; ++l)
           if (layers[l].skip_b >= 0) v += p[layers[l].skip_b + c];
@@ -198,11 +205,16 @@ struct Gen2Args {
   int64_t t0;
   uint64_t seed;
   int n_streams, n_steps, n_teacher, L;
+  const float* gcproj;  // global conditioning: fp32 [n_streams][L][2D] per-stream projections (k_gen_gcproj), else nullptr
   long long* trace;  // wn_debug_trace buffer: CTA 0's warps log (event, layer, clock64) during the last step
 };
 
+template <int S, int P, bool GC>
 __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
   using namespace g2;
+  constexpr int SLOT = slot_bytes(S, P), NSLOT = n_slots(S, P), HP = hp(S, P);
+  constexpr int NHS = S / 256, NHP = P / 256;   // 256-column halves: warp w owns n-tiles h * 32 + 4w .. 4w + 3 of every half
+  constexpr int SKIP_BYTES = chunk_bytes(S), P1_BYTES = chunk_bytes(P), P2_BYTES = chunk_bytes(Q);
   extern __shared__ __align__(1024) unsigned char sm[];
   unsigned char* wring = sm;                                         // NSLOT x 27 KB
   bf16* x0tab = reinterpret_cast<bf16*>(sm + NSLOT * SLOT);          // [257][32]
@@ -211,7 +223,7 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
   bf16* hbuf = zbuf + GS * XP;                                       // [2][GS][HP]   h1 / h2
   float* lgbuf = reinterpret_cast<float*>(hbuf + 2 * GS * HP);       // [GS][LP]
   bf16* oldbuf = reinterpret_cast<bf16*>(lgbuf + GS * LP);            // [OLD_W][GS][XP] prefetched x[t-dil] tiles
-  float* bias3 = reinterpret_cast<float*>(oldbuf + OLD_W * GS * XP);  // [768]
+  float* bias3 = reinterpret_cast<float*>(oldbuf + OLD_W * GS * XP);  // [S + P + Q]
   __shared__ __align__(8) uint64_t full[NSLOT], empty[NSLOT];
   __shared__ int code_s[GS];
   __shared__ int dil_s[64];
@@ -229,7 +241,7 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
   }
   for (int i = tid; i < 257 * 32 / 8; i += THREADS)
     reinterpret_cast<uint4*>(x0tab)[i] = reinterpret_cast<const uint4*>(a.blob + a.g.x0tab)[i];
-  for (int i = tid; i < 768; i += THREADS) bias3[i] = reinterpret_cast<const float*>(a.blob + a.g.biases)[i];
+  for (int i = tid; i < S + P + Q; i += THREADS) bias3[i] = reinterpret_cast<const float*>(a.blob + a.g.biases)[i];
   if (tid < GS) code_s[tid] = (s0 + tid < a.n_streams) ? a.codes[s0 + tid] : -1;
   if (tid < L) {
     dil_s[tid] = a.layers[tid].dil;
@@ -237,7 +249,7 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
   }
   __syncthreads();
 
-  const int items_per_step = L + 16;
+  const int items_per_step = L + S / 32 + P / 32;
   if (warp == NCW) {
     // ===== weight producer: same item sequence every timestep =====
     // One item per layer (conv | residual | biases, then SKIP_l: two bulk copies into one slot) and 16 post-net chunks.
@@ -250,14 +262,15 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
           mbar_wait(&empty[slot], ph);
           unsigned char* dst = wring + slot * SLOT;
           if (j < L) {
-            mbar_expect_tx(&full[slot], LAYER_A_BYTES + CHUNK_BYTES);
+            mbar_expect_tx(&full[slot], LAYER_A_BYTES + SKIP_BYTES);
             bulk_g2s(dst, a.blob + a.g.layer_a + (size_t)j * LAYER_A_BYTES, LAYER_A_BYTES, &full[slot]);
-            bulk_g2s(dst + LAYER_A_BYTES, a.blob + a.g.skip + (size_t)j * CHUNK_BYTES, CHUNK_BYTES, &full[slot]);
+            bulk_g2s(dst + LAYER_A_BYTES, a.blob + a.g.skip + (size_t)j * SKIP_BYTES, SKIP_BYTES, &full[slot]);
+          } else if (j < L + S / 32) {
+            mbar_expect_tx(&full[slot], P1_BYTES);
+            bulk_g2s(dst, a.blob + a.g.post1 + (size_t)(j - L) * P1_BYTES, P1_BYTES, &full[slot]);
           } else {
-            const unsigned char* src = j < L + 8 ? a.blob + a.g.post1 + (size_t)(j - L) * CHUNK_BYTES
-                                                 : a.blob + a.g.post2 + (size_t)(j - L - 8) * CHUNK_BYTES;
-            mbar_expect_tx(&full[slot], CHUNK_BYTES);
-            bulk_g2s(dst, src, CHUNK_BYTES, &full[slot]);
+            mbar_expect_tx(&full[slot], P2_BYTES);
+            bulk_g2s(dst, a.blob + a.g.post2 + (size_t)(j - L - S / 32) * P2_BYTES, P2_BYTES, &full[slot]);
           }
           if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
         }
@@ -329,9 +342,9 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
       const int row = (c >= 0 && c < 256) ? c : 256;
       *reinterpret_cast<uint4*>(xbuf + s * XP + ch * 8) = *reinterpret_cast<const uint4*>(x0tab + row * 32 + ch * 8);
     }
-    float skip[4][4];
+    float skip[NHS * 4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < NHS * 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) skip[i][j] = 0.f;
     // The skip MMAs of layer l (A = z_l, off the per-sample chain) are deferred into layer l + 1, where they fill the
@@ -340,15 +353,37 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
     const unsigned char* wsk_prev = nullptr;   // its SKIP weights (slot still held)
     auto skip_mma = [&]() {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int h = 0; h < NHS; ++h) {
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint2 b = ldb_frag(wsk_prev, warp * 4 + j, ks, 2, lane);
-          mma16816(skip[j], zf[ks], b.x, b.y);  // imodel.py:247 (bias added once, below)
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint2 b = ldb_frag(wsk_prev, h * 32 + warp * 4 + j, ks, 2, lane);
+            mma16816(skip[h * 4 + j], zf[ks], b.x, b.y);  // imodel.py:247 (bias added once, below)
+          }
         }
       }
       slot_release();
     };
+    // global conditioning: this lane's per-stream projections of the CURRENT layer (rows g, g + 8; channels c, c + 1 of
+    // the signal and the gate half), loaded one layer ahead -- they depend on (stream, layer) only
+    float2 gcs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, gcg[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    float2 ngs[2], ngg[2];
+    auto gc_load = [&](int l) {
+      if constexpr (GC) {
+        if (warp < 4) {
+          const int c = warp * 8 + 2 * (lane & 3);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int sidx = min(s0 + (lane >> 2) + 8 * k, a.n_streams - 1);
+            const float* q = a.gcproj + ((size_t)sidx * L + l) * (2 * D) + c;
+            ngs[k] = __ldg(reinterpret_cast<const float2*>(q));
+            ngg[k] = __ldg(reinterpret_cast<const float2*>(q + D));
+          }
+        }
+      }
+    };
+    gc_load(0);
     cbar();
     int xb = 0;
     for (int l = 0; l < L; ++l) {
@@ -357,6 +392,10 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
       bf16* xout = xbuf + (xb ^ 1) * GS * XP;
       const bf16* oldx = oldbuf + cur_buf * (GS * XP);
       tr.ev(0, l);
+      if constexpr (GC) {
+        gcs[0] = ngs[0]; gcs[1] = ngs[1]; gcg[0] = ngg[0]; gcg[1] = ngg[1];
+        if (l + 1 < L) gc_load(l + 1);
+      }
       const unsigned char* wa = slot_wait();
       tr.ev(1, l);
       const float* bias = reinterpret_cast<const float*>(wa + CONV_BYTES + RES_BYTES);
@@ -382,10 +421,11 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
         tr.ev(2, l);
         const int c = warp * 8 + 2 * t4;
         const float bs0 = bias[c], bs1 = bias[c + 1], bg0 = bias[32 + c], bg1 = bias[32 + c + 1];
-        const float z00 = tanh_fast(cs[0] + ds[0] + bs0) * sigmoid_fast(cg[0] + dg[0] + bg0);
-        const float z01 = tanh_fast(cs[1] + ds[1] + bs1) * sigmoid_fast(cg[1] + dg[1] + bg1);
-        const float z10 = tanh_fast(cs[2] + ds[2] + bs0) * sigmoid_fast(cg[2] + dg[2] + bg0);
-        const float z11 = tanh_fast(cs[3] + ds[3] + bs1) * sigmoid_fast(cg[3] + dg[3] + bg1);
+        // (+ the stream's global-conditioning projections, imodel.py:113-118; zero without GC)
+        const float z00 = tanh_fast(cs[0] + ds[0] + bs0 + gcs[0].x) * sigmoid_fast(cg[0] + dg[0] + bg0 + gcg[0].x);
+        const float z01 = tanh_fast(cs[1] + ds[1] + bs1 + gcs[0].y) * sigmoid_fast(cg[1] + dg[1] + bg1 + gcg[0].y);
+        const float z10 = tanh_fast(cs[2] + ds[2] + bs0 + gcs[1].x) * sigmoid_fast(cg[2] + dg[2] + bg0 + gcg[1].x);
+        const float z11 = tanh_fast(cs[3] + ds[3] + bs1 + gcs[1].y) * sigmoid_fast(cg[3] + dg[3] + bg1 + gcg[1].y);
         *reinterpret_cast<uint32_t*>(zbuf + g * XP + c) = frag_pack(z00, z01);
         *reinterpret_cast<uint32_t*>(zbuf + (g + 8) * XP + c) = frag_pack(z10, z11);
       } else {
@@ -438,53 +478,58 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
     bf16* h1 = hbuf;
     bf16* h2 = hbuf + GS * HP;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = (warp * 4 + j) * 8 + 2 * t4;
+    for (int hj = 0; hj < NHS * 4; ++hj) {
+      const int c = ((hj >> 2) * 32 + warp * 4 + (hj & 3)) * 8 + 2 * t4;
       *reinterpret_cast<uint32_t*>(h1 + g * HP + c) =
-          frag_pack(fmaxf(skip[j][0] + bias3[c], 0.f), fmaxf(skip[j][1] + bias3[c + 1], 0.f));
+          frag_pack(fmaxf(skip[hj][0] + bias3[c], 0.f), fmaxf(skip[hj][1] + bias3[c + 1], 0.f));
       *reinterpret_cast<uint32_t*>(h1 + (g + 8) * HP + c) =
-          frag_pack(fmaxf(skip[j][2] + bias3[c], 0.f), fmaxf(skip[j][3] + bias3[c + 1], 0.f));
+          frag_pack(fmaxf(skip[hj][2] + bias3[c], 0.f), fmaxf(skip[hj][3] + bias3[c + 1], 0.f));
     }
     cbar();
-    float acc[4][4];
-    auto dense256 = [&](const bf16* A) {  // acc[j] = A[16 x 256] . W[256 x (n-tiles 4w..4w+3)], W streamed in 8 K slices
+    // acc[h * 4 + j] = A[16 x K] . W[K x (n-tiles h * 32 + 4w .. 4w + 3)], W streamed in K / 32 slices of [32 x N]
+    float acc[(NHP > 1 ? NHP : 1) * 4][4];
+    auto dense = [&](const bf16* A, auto kc, auto nh) {
+      constexpr int KC = decltype(kc)::value, NH = decltype(nh)::value;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < NH * 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-      for (int c8 = 0; c8 < 8; ++c8) {
+      for (int c8 = 0; c8 < KC; ++c8) {
         const unsigned char* w = slot_wait();
         uint32_t af[4];
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
           lda_frag(af, A, HP, c8 * 32 + ks * 16, lane);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint2 b = ldb_frag(w, warp * 4 + j, ks, 2, lane);
-            mma16816(acc[j], af, b.x, b.y);
+          for (int h = 0; h < NH; ++h) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint2 b = ldb_frag(w, h * 32 + warp * 4 + j, ks, 2, lane);
+              mma16816(acc[h * 4 + j], af, b.x, b.y);
+            }
           }
         }
         slot_release();
       }
     };
-    dense256(h1);
+    dense(h1, std::integral_constant<int, S / 32>{}, std::integral_constant<int, NHP>{});
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = (warp * 4 + j) * 8 + 2 * t4;
+    for (int hj = 0; hj < NHP * 4; ++hj) {
+      const int c = ((hj >> 2) * 32 + warp * 4 + (hj & 3)) * 8 + 2 * t4;
       *reinterpret_cast<uint32_t*>(h2 + g * HP + c) =
-          frag_pack(fmaxf(acc[j][0] + bias3[256 + c], 0.f), fmaxf(acc[j][1] + bias3[256 + c + 1], 0.f));
+          frag_pack(fmaxf(acc[hj][0] + bias3[S + c], 0.f), fmaxf(acc[hj][1] + bias3[S + c + 1], 0.f));
       *reinterpret_cast<uint32_t*>(h2 + (g + 8) * HP + c) =
-          frag_pack(fmaxf(acc[j][2] + bias3[256 + c], 0.f), fmaxf(acc[j][3] + bias3[256 + c + 1], 0.f));
+          frag_pack(fmaxf(acc[hj][2] + bias3[S + c], 0.f), fmaxf(acc[hj][3] + bias3[S + c + 1], 0.f));
     }
     tr.ev(10, 0);
     cbar();
-    dense256(h2);
+    dense(h2, std::integral_constant<int, P / 32>{}, std::integral_constant<int, 1>{});
     tr.ev(11, 0);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c = (warp * 4 + j) * 8 + 2 * t4;
-      *reinterpret_cast<float2*>(lgbuf + g * LP + c) = make_float2(acc[j][0] + bias3[512 + c], acc[j][1] + bias3[512 + c + 1]);
-      *reinterpret_cast<float2*>(lgbuf + (g + 8) * LP + c) = make_float2(acc[j][2] + bias3[512 + c], acc[j][3] + bias3[512 + c + 1]);
+      *reinterpret_cast<float2*>(lgbuf + g * LP + c) = make_float2(acc[j][0] + bias3[S + P + c], acc[j][1] + bias3[S + P + c + 1]);
+      *reinterpret_cast<float2*>(lgbuf + (g + 8) * LP + c) = make_float2(acc[j][2] + bias3[S + P + c], acc[j][3] + bias3[S + P + c + 1]);
     }
     cbar();
     // ---- sampling (imodel.py:167-187) + teacher forcing (imodel.py:260-267): warp w -> streams 2w, 2w+1, in lock step ----
@@ -519,40 +564,57 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
 bool gen2_supported(const wn_model* m) {
   static const bool disabled = getenv("WN_DISABLE_GEN2") != nullptr;
   const wn_arch& a = m->a;
-  return !disabled && a.n_res == 32 && a.n_dil == 32 && a.n_skip == 256 && a.n_post == 256 && a.n_quant == 256 &&
-         a.n_gc_embed == 0 && m->L >= 2 && m->L <= 64;
+  return !disabled && a.n_res == 32 && a.n_dil == 32 && (a.n_skip == 256 || a.n_skip == 512) &&
+         (a.n_post == 256 || a.n_post == 512) && a.n_quant == 256 && m->L >= 2 && m->L <= 64;
 }
-int64_t gen2_blob_bytes(const wn_model* m) { return gen2_layout(m->L).total; }
+int64_t gen2_blob_bytes(const wn_model* m) { return gen2_layout(m->L, m->a.n_skip, m->a.n_post).total; }
 
 int gen2_prepare(wn_model* m, const float* d_params, unsigned char* blob, cudaStream_t st) {
-  const Gen2Layout g = gen2_layout(m->L);
-  k_gen2_prep<<<m->L + 17, 256, 0, st>>>(d_params, m->d_layers, m->L, m->off_pre, m->off_pre_b, m->off_post1,
-                                         m->off_post1_b, m->off_post2, m->off_post2_b, blob, g);
+  const int S = m->a.n_skip, P = m->a.n_post;
+  const Gen2Layout g = gen2_layout(m->L, S, P);
+  k_gen2_prep<<<m->L + S / 32 + P / 32 + 1, 256, 0, st>>>(d_params, m->d_layers, m->L, m->off_pre, m->off_pre_b,
+                                                           m->off_post1, m->off_post1_b, m->off_post2, m->off_post2_b,
+                                                           blob, g, S, P);
+  WN_LAUNCH_CHECK();
+  return WN_OK;
+}
+
+template <int S, int P, bool GC>
+static int gen2_launch(const Gen2Args& a, int n_streams, cudaStream_t st) {
+  using namespace g2;
+  constexpr size_t smem = (size_t)n_slots(S, P) * slot_bytes(S, P) + 257 * 32 * 2 +
+                          (size_t)(2 * GS * XP + GS * XP + 2 * GS * hp(S, P)) * 2 + (size_t)GS * LP * 4 +
+                          (size_t)OLD_W * GS * XP * 2 + (size_t)(S + P + Q) * 4 + 1024;
+  static_assert(smem <= 226 * 1024, "generator shared memory");
+  WN_CUDA_CHECK(cudaFuncSetAttribute(k_gen2<S, P, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps(PROF_GEN, st);
+  k_gen2<S, P, GC><<<(n_streams + GS - 1) / GS, THREADS, smem, st>>>(a);
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
 
 int gen2_run(wn_model* m, const unsigned char* blob, const int64_t* ring_off, bf16* rings, int32_t* codes,
              int n_streams, int64_t t0, int n_steps, uint64_t seed, const int32_t* teacher, int n_teacher, int32_t* out,
-             float* logits, cudaStream_t st) {
-  using namespace g2;
+             float* logits, const float* gcproj, cudaStream_t st) {
+  const int S = m->a.n_skip, P = m->a.n_post;
   Gen2Args a;
   memset(&a, 0, sizeof(a));
-  a.blob = blob; a.g = gen2_layout(m->L); a.layers = m->d_layers; a.ring_off = ring_off; a.rings = rings;
+  a.blob = blob; a.g = gen2_layout(m->L, S, P); a.layers = m->d_layers; a.ring_off = ring_off; a.rings = rings;
   a.codes = codes; a.teacher = teacher; a.n_teacher = teacher ? n_teacher : 0; a.out = out; a.logits_out = logits;
   a.trace = g_trace_buf;
   a.t0 = t0; a.seed = seed; a.n_streams = n_streams; a.n_steps = n_steps; a.L = m->L;
-  const size_t smem = (size_t)NSLOT * SLOT + 257 * 32 * 2 + (size_t)(2 * GS * XP + GS * XP + 2 * GS * HP) * 2 +
-                      (size_t)GS * LP * 4 + (size_t)OLD_W * GS * XP * 2 + 768 * 4 + 1024;
-  if (smem > 227 * 1024) {
-    set_error("gen2_run: %zu bytes of shared memory needed", smem);
-    return WN_ERR_UNSUPPORTED;
-  }
-  WN_CUDA_CHECK(cudaFuncSetAttribute(k_gen2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ProfScope ps(PROF_GEN, st);
-  k_gen2<<<(n_streams + GS - 1) / GS, THREADS, smem, st>>>(a);
-  WN_LAUNCH_CHECK();
-  return WN_OK;
+  a.gcproj = gcproj;
+  const bool gc = gcproj != nullptr;
+#define WN_GEN2(S_, P_)                                                              \
+  if (S == S_ && P == P_)                                                            \
+    return gc ? gen2_launch<S_, P_, true>(a, n_streams, st) : gen2_launch<S_, P_, false>(a, n_streams, st);
+  WN_GEN2(256, 256)
+  WN_GEN2(512, 512)
+  WN_GEN2(256, 512)
+  WN_GEN2(512, 256)
+#undef WN_GEN2
+  set_error("gen2_run: unsupported n_skip / n_post %d / %d", S, P);
+  return WN_ERR_UNSUPPORTED;
 }
 
 }  // namespace wn

@@ -28,7 +28,10 @@ def _engine(arch, B):
     return TrainEngine(arch, B)
 
 
-@pytest.mark.parametrize("arch,B,T", [(util.CLASSIC, 4, 16384), (util.C1, 4, 8192), (WIDE4, 1, 8192)],
+# sizes: >= 30 000 valid positions each, so that the statistical bf16 floor of the worst tensor (PRE: a row of the
+# embedding table only sees the positions that carry its code) stays under the bound -- measured on B200 at 4 x 8192
+# (21 881 valid): arch1 8.3 %, at 1 x 8192 wide (5 596 valid): 11.9 %, at 4 x 16384 3x10 (43 608 valid): 4.6 %
+@pytest.mark.parametrize("arch,B,T", [(util.CLASSIC, 4, 16384), (util.C1, 8, 8192), (WIDE4, 6, 8192)],
                          ids=["configs1_3x10_T16384", "configs0_arch1_T8192", "configs4_wide_T8192"])
 def test_full_stage_length_vs_oracle(lib, arch, B, T):
     """Logits, loss statistics and EVERY gradient tensor against the fp64 oracle (autograd) and the same-rounding

@@ -29,11 +29,18 @@ def _mk(arch, n_streams, seed, gc_ids=None):
     return a, p, eng
 
 
+ARCH3 = dict(util.C1, n_gc_embed=0, n_gc_category=0)                     # reference par/arch3.json: 5x10, S = P = 512
+MIX_A = dict(util.CLASSIC_SHALLOW, n_skip=512, n_gc_embed=8, n_gc_category=11)   # S = 512, P = 256, GC
+MIX_B = dict(util.CLASSIC_SHALLOW, n_post=512)                                    # S = 256, P = 512
+
+
 @pytest.mark.parametrize("arch,gc,n_streams", [(util.TINY, False, 5), (util.TINY_GC, True, 5), (util.TINY_ASYM, False, 5),
-                                               (util.CLASSIC_SHALLOW, False, 20), (util.CLASSIC, False, 3)])
+                                               (util.CLASSIC_SHALLOW, False, 20), (util.CLASSIC, False, 3),
+                                               (util.C1, True, 5), (ARCH3, False, 20), (MIX_A, True, 5), (MIX_B, False, 5)])
 def test_teacher_forced_logits(lib, arch, gc, n_streams):
-    """TINY*: generation-1 kernel; CLASSIC*: generation-2 kernel (mma.sync, streamed weights; 20 streams = one full
-    and one partial 16-stream CTA)."""
+    """TINY*: generation-1 kernel; everything with R = D = 32 and S, P in {256, 512}: generation-2 kernel (mma.sync,
+    streamed weights; 20 streams = one full and one partial 16-stream CTA) -- the classic 3x10 stack, the reference's
+    par/arch1.json (C1: S = P = 512 + global conditioning) and par/arch3.json shapes, and the mixed widths."""
     n = 80
     gc_ids = np.array([1, 3, 5, 7, 2], np.int32) if gc else None
     a, p, eng = _mk(arch, n_streams, 4, gc_ids)
@@ -86,15 +93,18 @@ def test_free_running_fixed_seed(lib, arch, n_streams):
 # the teacher-forced GenOracle (reference tests.py:1,7-11 intent): trainer input [all-zero vector, seq[0], seq[1], ...]
 # with zero SAVE state == generator fed seq (imodel.py:66-70,88-95).
 
-def _trainer_logits(a, p, fed):
+def _trainer_logits(a, p, fed, gc_ids=None):
     """logits the training forward gives for the generator's inputs: step i consumes fed[i-1] (step 0: the all-zero
-    vector == an out-of-range code, tmodel.py:64)."""
+    vector == an out-of-range code, tmodel.py:64); gc_ids: one voice id per row (the trainer's id mask, constant in
+    time, selects the same GC_EMBED row the generator is given, imodel.py:53-56)."""
     n = fed.shape[1] + 1
     wav = np.concatenate([np.full((fed.shape[0], 1), -1, np.int64), fed.astype(np.int64)], axis=1)[:, :n]
     pt = {k: torch.tensor(np.asarray(v), dtype=torch.float64) for k, v in p.items()
           if np.asarray(v).dtype.kind == "f" and not k.startswith("SAVE")}
     save = [torch.zeros(wav.shape[0], d, a.n_res, dtype=torch.float64) for d in a.dilations()]
     ids = torch.ones(wav.shape, dtype=torch.int64)
+    if gc_ids is not None:
+        ids = ids * torch.as_tensor(np.asarray(gc_ids, np.int64))[:, None]
     return O.train_forward(a, pt, save, torch.as_tensor(wav), ids, torch.float64, emulate_bf16=True).logits.numpy()
 
 
@@ -148,3 +158,25 @@ def test_classic_stack_free_running_full_horizon(lib):
     eng.reset()
     again = eng.run(HORIZON, seed=77).cpu().numpy()
     assert np.array_equal(again, codes)
+
+
+def test_arch1_stack_full_horizon_with_global_conditioning(lib):
+    """The reference's own par/arch1.json (BASELINE configs[0]: 5x10, S = P = 512, 17-wide voice embedding over 377
+    voices) through k_gen2<512, 512, GC>: 10 streams with different voices, free-running for 5 300 steps > F + 1 = 5 116
+    (every ring wraps: dil = 512 ten times).  Sampled indices bit-exact against the oracle sampler on the kernel's
+    logits at every step; the same-rounding oracle fed the kernel's own output reproduces the logits."""
+    arch, n_streams, n = util.C1, 10, 5300
+    gc_ids = np.array([5, 6, 1, 377, 200, 17, 3, 99, 250, 42], np.int32)
+    a, p, eng = _mk(arch, n_streams, 8, gc_ids)
+    codes, logits = eng.run(n, seed=5, want_logits=True)
+    codes, logits = codes.cpu().numpy(), logits.cpu().numpy()
+    _check_sampler_all_steps(codes, logits, 5)
+    ref = _trainer_logits(a, p, codes[:, :n - 1], gc_ids)
+    err = np.abs(ref - logits).max(axis=(0, 2))
+    util.record("gen_free_running_arch1_gc", dict(horizon=n, maxabs=float(err.max()), maxabs_after_F=float(err[5116:].max())))
+    # 50 layers, 53 000 rows: the bound of the deep-stack training forward test (0.15 max-abs, logit range +-4)
+    assert err.max() <= 0.15 and float(np.sqrt((ref - logits) ** 2).mean()) <= 0.02, (int(err.argmax()), float(err.max()))
+    # a different voice changes the stream (the conditioning is really applied)
+    eng2 = _mk(arch, n_streams, 8, gc_ids[::-1].copy())[2]
+    other = eng2.run(300, seed=5, want_logits=True)[1].cpu().numpy()
+    assert np.abs(other[:, :300] - logits[:, :300]).max() > 0.05
