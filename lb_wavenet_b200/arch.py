@@ -42,6 +42,37 @@ def serial_name(arch: ArchCat, *var_indices, get_bias: bool = False) -> str:
     return "_".join(map(str, [name, *var_indices]))
 
 
+def parse_serial_name(name: str):
+    """Inverse of serial_name: 'SIGNAL_BIAS_0_3' -> (ArchCat.SIGNAL, (0, 3), True)."""
+    for cat in sorted(ArchCat, key=lambda c: -len(c.name)):
+        if name == cat.name or name.startswith(cat.name + "_"):
+            rest = [x for x in name[len(cat.name):].split("_") if x]
+            bias = bool(rest) and rest[0] == "BIAS"
+            if bias:
+                rest = rest[1:]
+            if all(x.isdigit() for x in rest):
+                return cat, tuple(int(x) for x in rest), bias
+    raise KeyError("not a serial variable name: {}".format(name))
+
+
+def padded_accessors(view_fn, shape):
+    """(get, set) for a variable of logical `shape` stored zero-extended in a (possibly larger) device tensor returned
+    by view_fn(): reads the logical slice, writes it and zeroes the padding (config.engine_arch)."""
+    sl = tuple(slice(0, int(d)) for d in shape)
+
+    def get():
+        return view_fn()[sl].detach().float().cpu().numpy()
+
+    def set_(v):
+        import torch
+        t = view_fn()
+        if tuple(t.shape) != tuple(shape):
+            t.zero_()
+        t[sl].copy_(torch.as_tensor(np.asarray(v, np.float32)).to(t.device))
+
+    return get, set_
+
+
 def xavier_uniform(shape, rng: np.random.Generator) -> np.ndarray:
     """tf.contrib.layers.xavier_initializer_conv2d (reference arch.py:63): U(+-sqrt(6/(fan_in+fan_out)))
     with fan_in = shape[-2]*prod(shape[:-2]), fan_out = shape[-1]*prod(shape[:-2])."""

@@ -81,13 +81,29 @@ def mel_hop_sz(arch: dict) -> int:
     return hop
 
 
-def engine_arch(arch: dict) -> dict:
-    """The subset of keys the C ABI's wn_arch carries."""
-    if arch.get("n_lc_out", 0) > 0:
-        raise NotImplementedError(
-            "local conditioning (n_lc_out > 0, reference tmodel.py:68-83,156-160) is not built yet; "
-            "see DESIGN.md 'next' rows")
-    return dict(n_blocks=arch["n_blocks"], n_block_layers=arch["n_block_layers"], n_quant=arch["n_quant"],
-                n_res=arch["n_res"], n_dil=arch["n_dil"], n_skip=arch["n_skip"], n_post=arch["n_post"],
-                n_gc_embed=arch["n_gc_embed"], n_gc_category=arch["n_gc_category"],
-                use_bias=1 if arch["use_bias"] else 0)
+def _pad_res_dil(n: int) -> int:
+    """The tcgen05 layer kernels take n_res = n_dil = 32 (fused per-layer kernels) or multiples of 64 (GEMM chain)."""
+    return 32 if n <= 32 else 64 if n <= 64 else (n + 63) // 64 * 64
+
+
+def _pad_skip_post(n: int) -> int:
+    return max(64, (n + 63) // 64 * 64)
+
+
+def engine_arch(arch: dict, pad: bool = True) -> dict:
+    """The keys the C ABI's wn_arch carries.  Channel counts the kernels do not tile (the reference's par/arch2.json has
+    n_res = 3, n_dil = 4, n_skip = 8, n_post = 6) are PADDED here: the device arena holds zero-extended tensors, the
+    host mirror (tmodel / imodel) reads and writes the logical slices, so checkpoints keep the reference's shapes.  Zero
+    padding is closed under the whole training step: a padded input channel is 0, a padded output channel gets
+    tanh(0) * sigmoid(0) = 0 / relu(0) = 0, every gradient into a padded row or column is a product with one of those
+    zeros, and Adam / L2 leave an exactly-zero weight with an exactly-zero gradient at zero."""
+    out = dict(n_blocks=arch["n_blocks"], n_block_layers=arch["n_block_layers"], n_quant=arch["n_quant"],
+               n_res=arch["n_res"], n_dil=arch["n_dil"], n_skip=arch["n_skip"], n_post=arch["n_post"],
+               n_gc_embed=arch["n_gc_embed"], n_gc_category=arch["n_gc_category"],
+               use_bias=1 if arch["use_bias"] else 0)
+    if pad:
+        out["n_res"], out["n_dil"] = _pad_res_dil(out["n_res"]), _pad_res_dil(out["n_dil"])
+        if out["n_res"] != out["n_dil"] and max(out["n_res"], out["n_dil"]) <= 64:
+            out["n_res"] = out["n_dil"] = max(out["n_res"], out["n_dil"])   # the fused kernels want n_res == n_dil
+        out["n_skip"], out["n_post"] = _pad_skip_post(out["n_skip"]), _pad_skip_post(out["n_post"])
+    return out

@@ -44,9 +44,10 @@ class WaveNetGen(ar.WaveNetArch):
         self.engine = None
         self.gen_sz = Placeholder("gen_sz")
         self.gc_ids = Placeholder("gc_ids") if self.use_gc else None
-        self._arch_dict = dict(n_blocks=n_blocks, n_block_layers=n_block_layers, n_quant=n_quant, n_res=n_res,
-                               n_dil=n_dil, n_skip=n_skip, n_post=n_post1, n_gc_embed=n_gc_embed,
-                               n_gc_category=n_gc_category, use_bias=1 if use_bias else 0)
+        from . import config
+        self._arch_dict = config.engine_arch(dict(
+            n_blocks=n_blocks, n_block_layers=n_block_layers, n_quant=n_quant, n_res=n_res, n_dil=n_dil, n_skip=n_skip,
+            n_post=n_post1, n_gc_embed=n_gc_embed, n_gc_category=n_gc_category, use_bias=use_bias))
         # independent streams shard across GPUs with no collective
         self.dist = dist
         self.stream_lo, self.stream_hi = (0, batch_sz) if dist is None else dist.slot_range(batch_sz)
@@ -62,15 +63,16 @@ class WaveNetGen(ar.WaveNetArch):
     def _make_variable(self, name, shape, arch, trainable):
         eng = self._ensure_engine()
         torch = eng.torch
-        return ckpt.Variable(name, shape, np.float32, lambda: eng.view(name).detach().cpu().numpy(),
-                             lambda v: eng.view(name).copy_(torch.as_tensor(v).to(eng.device)), trainable)
+        get, set_ = ar.padded_accessors(lambda: eng.view(name), shape)
+        return ckpt.Variable(name, shape, np.float32, get, set_, trainable)
 
     def build_graph(self):
         """reference imodel.py:279-303.  Registers the trainable variables (same serial names as the
         trainer, so a trainer checkpoint restores into the generator) and encodes the teacher."""
         eng = self._ensure_engine()
         for name, info in eng.reg.params.items():
-            self.vars[name] = self._make_variable(name, info.shape, None, True)
+            cat, idx, bias = ar.parse_serial_name(name)   # logical (checkpoint) shape; the arena may be zero-extended
+            self.vars[name] = self._make_variable(name, self.var_shape(cat, *idx, get_bias=bias), cat, True)
         self.add_saveable_objects(self.vars)
         if self.teacher_vec is not None:  # imodel.py:44-48: ops.mu_encode(teacher_vec) on the device
             from . import ops

@@ -117,12 +117,17 @@ class WaveNetTrain(ar.WaveNetArch):
         if arch == ar.ArchCat.SAVE:
             layer = next(i for i, s in enumerate(eng.reg.saves) if s.name == name)
 
+            R = self.n_res  # logical width; the arena may hold zero-extended rows (config.engine_arch)
+
             def get_save():
-                full = self.dist.all_gather_cat(eng.save_view(layer).float(), dim=0)  # [B, dil, R]
+                full = self.dist.all_gather_cat(eng.save_view(layer)[:, :, :R].float().contiguous(), dim=0)  # [B, dil, R]
                 return full.cpu().numpy()
 
             def set_save(v):
-                eng.save_view(layer).copy_(torch.as_tensor(v[self.slot_lo:self.slot_hi]).to(eng.device))
+                sv = eng.save_view(layer)
+                if sv.shape[2] != R:
+                    sv.zero_()
+                sv[:, :, :R].copy_(torch.as_tensor(v[self.slot_lo:self.slot_hi]).to(eng.device))
 
             return ckpt.Variable(name, shape, np.float32, get_save, set_save, trainable=False)
         if arch in (ar.ArchCat.GLOBAL_STEP, ar.ArchCat.VALID_SAMPLES):
@@ -132,9 +137,8 @@ class WaveNetTrain(ar.WaveNetArch):
                                  lambda v: setattr(self, attr, int(v)), trainable=False)
         if name not in eng.reg.params:
             raise KeyError("variable {} is not part of this architecture".format(name))
-        return ckpt.Variable(name, shape, np.float32,
-                             lambda: eng.view(name).detach().cpu().numpy(),
-                             lambda v: eng.view(name).copy_(torch.as_tensor(v).to(eng.device)), trainable=True)
+        get, set_ = ar.padded_accessors(lambda: eng.view(name), shape)
+        return ckpt.Variable(name, shape, np.float32, get, set_, trainable=True)
 
     def bind_optimizer(self, opt: "AdamOptimizer"):
         """Adds the optimiser state to the checkpoint as optional keys (a checkpoint without them restores with zero
@@ -144,11 +148,13 @@ class WaveNetTrain(ar.WaveNetArch):
         self._optimizer = opt
         extra = {}
         for name, info in eng.reg.params.items():
+            cat, idx, bias = ar.parse_serial_name(name)
+            shape = tuple(self.var_shape(cat, *idx, get_bias=bias))   # logical (checkpoint) shape
             for arena, suffix in ((eng.m, "/Adam"), (eng.v, "/Adam_1")):
                 view = arena[info.offset:info.offset + info.numel].view(info.shape)
-                extra[name + suffix] = ckpt.Variable(
-                    name + suffix, info.shape, np.float32, (lambda v=view: v.detach().cpu().numpy()),
-                    (lambda x, v=view: v.copy_(torch.as_tensor(x).to(eng.device))), trainable=False, optional=True)
+                get, set_ = ar.padded_accessors(lambda v=view: v, shape)
+                extra[name + suffix] = ckpt.Variable(name + suffix, shape, np.float32, get, set_, trainable=False,
+                                                     optional=True)
         extra["optimizer_step"] = ckpt.Variable("optimizer_step", (), np.int64, lambda: np.array(opt.t, np.int64),
                                                 lambda x: setattr(opt, "t", int(x)), trainable=False, optional=True)
         self.add_saveable_objects(extra)
@@ -205,14 +211,17 @@ class WaveNetTrain(ar.WaveNetArch):
         rng = np.random.default_rng(seed)  # identical on every rank when init_seed is given
         if self.dist.world > 1 and self.init_seed is None:
             raise ValueError("data-parallel training needs an explicit init_seed so that replicas agree")
+        eng.params.zero_()
+        eng.save.zero_()
         for name, info in eng.reg.params.items():
-            if info.kind == _lib.KIND_FILTER:
-                eng.view(name).copy_(torch.as_tensor(ar.xavier_uniform(info.shape, rng)).to(eng.device))
-            else:
-                eng.view(name).zero_()
+            if info.kind == _lib.KIND_FILTER:   # Xavier bounds from the LOGICAL shape; padding stays zero
+                cat, idx, bias = ar.parse_serial_name(name)
+                shape = tuple(self.var_shape(cat, *idx, get_bias=bias))
+                sl = tuple(slice(0, d) for d in shape)
+                eng.view(name)[sl].copy_(torch.as_tensor(ar.xavier_uniform(shape, rng)).to(eng.device))
         for l, s in enumerate(eng.reg.saves):
             full = ar.xavier_uniform((self.batch_sz, s.dil, self.n_res), rng)
-            eng.save_view(l).copy_(torch.as_tensor(full[self.slot_lo:self.slot_hi]).to(eng.device))
+            eng.save_view(l)[:, :, :self.n_res].copy_(torch.as_tensor(full[self.slot_lo:self.slot_hi]).to(eng.device))
         eng.m.zero_()
         eng.v.zero_()
         self.global_step = 0

@@ -188,3 +188,70 @@ def test_train_cli_checkpoint_then_generate_cli(lib, tmp_path):
     for n in range(3):
         with wave.open(str(out / ("gen.i%d.wav" % n))) as wf:
             assert wf.getnframes() == 320 and wf.getframerate() == 16000
+
+
+def test_small_channel_counts_are_zero_padded(lib, tmp_path):
+    """reference par/arch2.json has n_res = 3, n_dil = 4, n_skip = 8, n_post = 6: the host mirror zero-extends such
+    tensors to what the kernels tile (config.engine_arch) while every checkpoint key keeps the reference's shape.
+    The padded model computes exactly the unpadded function: logits and gradients against the oracle on the LOGICAL
+    architecture, and the padding is still exactly zero after optimiser steps (L2 + Adam included)."""
+    from lb_wavenet_b200 import ckpt
+    from lb_wavenet_b200.tmodel import AdamOptimizer, WaveNetTrain
+    arch = dict(n_blocks=2, n_block_layers=4, n_quant=256, n_res=3, n_dil=4, n_skip=8, n_post=6, n_gc_embed=16,
+                n_gc_category=5, n_lc_in=80, n_lc_out=0, lc_upsample=[4, 4, 4, 4], use_bias=True,
+                wav_input_type="mu_law_quant")
+    B, T = 3, 256
+    net = WaveNetTrain(**arch, batch_sz=B, l2_factor=1e-3, add_summary=False, n_keep_checkpoints=2,
+                       ckpt_path=str(tmp_path / "small.net"), resume_step=0, n_valid_total=1000, print_interval=0,
+                       init_seed=3)
+    net.build()
+    net.init_vars()
+    eng = net.engine
+    assert eng.reg.arch["n_res"] == 32 and eng.reg.arch["n_skip"] == 64
+    a = O.Arch(2, 4, 256, 3, 4, 8, 6, 16, 5, True)
+    shapes = O.param_shapes(a, B)
+    state = {k: net.vars[k].numpy() for k in net.vars}
+    for k, (shp, kind) in shapes.items():
+        assert tuple(state[k].shape) == tuple(shp), k       # checkpoint keys keep the reference's shapes
+    # non-zero biases so that every path is observable
+    rng = np.random.default_rng(1)
+    for k, (shp, kind) in shapes.items():
+        if kind == "bias":
+            state[k] = (0.2 * rng.uniform(-1, 1, shp)).astype(np.float32)
+            net.vars[k].assign(state[k])
+        if kind == "save":
+            state[k] = torch.tensor(state[k]).to(torch.bfloat16).float().numpy()
+    wav, ids = util.synth_batch(B, T, 5, 9)
+    dw, di = torch.as_tensor(wav).cuda(), torch.as_tensor(ids).cuda()
+    logits = eng.forward(dw, di, want_logits=True).cpu().numpy()
+    eng.backward()
+    torch.cuda.synchronize()
+    pt, save, kinds = O.to_torch_params(a, state, B, torch.float64, requires_grad=False)
+    gem, info = O.train_backward_manual(a, pt, save, torch.as_tensor(wav).long(), torch.as_tensor(ids).long(),
+                                        torch.float64, emulate_bf16=True)
+    assert np.abs(logits - info["fwd"].logits.numpy()).max() <= 0.05
+    assert eng.read_stats()["n_valid"] == info["n_valid"]
+
+    def pad_is_zero(arena):
+        for name, pi in eng.reg.params.items():
+            full = eng.view(name, arena)
+            mask = torch.ones_like(full, dtype=torch.bool)
+            mask[tuple(slice(0, d) for d in state[name].shape)] = False
+            if bool(mask.any()):
+                assert float(full[mask].abs().max()) == 0.0, name
+
+    pad_is_zero(eng.grads)
+    for name in ("SIGNAL_0_1", "GATE_1_2", "RESIDUAL_0_0", "SKIP_1_3", "POST1", "POST2", "PRE", "GC_SIGNAL_0_2",
+                 "SIGNAL_BIAS_1_0", "POST1_BIAS"):
+        g = eng.view(name, eng.grads)[tuple(slice(0, d) for d in state[name].shape)].cpu().numpy()
+        assert util.rel_err(g, gem[name].numpy()) <= 6e-2, (name, util.rel_err(g, gem[name].numpy()))
+    opt = AdamOptimizer(1e-3)
+    for _ in range(3):
+        net.train_step(dw, di, opt)
+    pad_is_zero(eng.params)
+    pad_is_zero(eng.m)
+    path = net.save(3)
+    tensors = ckpt.read_checkpoint(path)
+    for k, (shp, kind) in shapes.items():
+        assert tuple(tensors[k].shape) == tuple(shp), k
+    assert tuple(tensors["SIGNAL_0_1/Adam"].shape) == (2, 3, 4)
