@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WN_ABI_VERSION 1
+#define WN_ABI_VERSION 2
 
 typedef enum wn_status {
   WN_OK = 0,
@@ -51,6 +51,14 @@ typedef struct wn_arch {
   int32_t n_gc_embed;     /* 0 == no global conditioning */
   int32_t n_gc_category;
   int32_t use_bias;
+  /* local conditioning (reference tmodel.py:68-83,156-160; arch.py:75-80,96-97): mel frames [.., n_lc_in] are upsampled
+   * by a chain of n_lc_layers transposed convolutions (width == stride == lc_upsample[i]) to one n_lc_out vector per
+   * timestep, which every layer projects onto its SIGNAL / GATE pre-activations.  n_lc_out == 0: none.
+   * Limits: n_lc_in, n_lc_out <= 128, n_lc_layers <= 8, n_res == n_dil == 32. */
+  int32_t n_lc_in;
+  int32_t n_lc_out;
+  int32_t n_lc_layers;
+  int32_t lc_upsample[8];
 } wn_arch;
 
 typedef struct wn_model wn_model; /* opaque */
@@ -103,11 +111,13 @@ int64_t wn_workspace_bytes(const wn_model* m, int32_t slice_sz);
  *   d_save     bf16 SAVE arena (wn_save_elems), read AND updated in place
  *   d_wav      int32 [n_slots, slice_sz] mu-law codes   (data.py:262-265 dtypes)
  *   d_ids      int32 [n_slots, slice_sz] voice id or 0 == invalid
+ *   d_mel      fp32 [n_slots, slice_sz / hop, n_lc_in] mel frames of the window, hop = prod(lc_upsample) (data.py:170-171,
+ *              222); NULL without local conditioning
  *   d_ws       workspace (wn_workspace_bytes), keeps the stash for wn_train_backward
  *   d_stats    double[WN_NSTATS]; XENT_SUM, N_VALID, DIFF_SUM are OVERWRITTEN
  *   d_logits   optional fp32 [n_slots, slice_sz, n_quant] (NULL: logits never leave the chip) */
 int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int32_t* d_wav,
-                     const int32_t* d_ids, int32_t slice_sz, void* d_ws, double* d_stats,
+                     const int32_t* d_ids, const float* d_mel, int32_t slice_sz, void* d_ws, double* d_stats,
                      float* d_logits, void* stream);
 
 /* wn_train_backward replaces Optimizer.compute_gradients (reference tmodel.py:354-358).
@@ -121,7 +131,7 @@ int wn_train_backward(wn_model* m, const float* d_params, const int32_t* d_wav,
 
 /* The same computation issued in phases so that data-parallel ranks can overlap the gradient
  * all-reduce with the rest of backward: phase 0 = post-net (+ every SKIP weight gradient);
- * phase p in [1, L] = layer L-p; phase L+1 = PRE gather + global-conditioning gradients.
+ * phase p in [1, L] = layer L-p; phase L+1 = PRE gather + global- and local-conditioning gradients.
  * Phases must be issued in ascending order on one stream; [0, L+2) == wn_train_backward. */
 int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* d_wav,
                              const int32_t* d_ids, int32_t slice_sz, void* d_ws, float* d_grads,

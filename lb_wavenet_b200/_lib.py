@@ -18,9 +18,21 @@ KIND_FILTER, KIND_BIAS = 0, 1
 
 
 class WnArch(C.Structure):
+    """struct wn_arch (include/wavenet_b200.h, ABI version 2)"""
     _fields_ = [(n, C.c_int32) for n in (
         "n_blocks", "n_block_layers", "n_quant", "n_res", "n_dil", "n_skip", "n_post",
-        "n_gc_embed", "n_gc_category", "use_bias")]
+        "n_gc_embed", "n_gc_category", "use_bias", "n_lc_in", "n_lc_out", "n_lc_layers")] + [("lc_upsample", C.c_int32 * 8)]
+
+    @staticmethod
+    def from_dict(d: dict) -> "WnArch":
+        up = [int(x) for x in (d.get("lc_upsample") or [])]
+        lc = int(d.get("n_lc_out", 0) or 0) > 0
+        if len(up) > 8:
+            raise ValueError("lc_upsample holds more than 8 strides")
+        return WnArch(int(d["n_blocks"]), int(d["n_block_layers"]), int(d["n_quant"]), int(d["n_res"]), int(d["n_dil"]),
+                      int(d["n_skip"]), int(d["n_post"]), int(d["n_gc_embed"]), int(d["n_gc_category"]),
+                      int(d["use_bias"]), int(d.get("n_lc_in", 0) or 0) if lc else 0,
+                      int(d.get("n_lc_out", 0) or 0), len(up) if lc else 0, (C.c_int32 * 8)(*(up if lc else [])))
 
 
 class WaveNetLibError(RuntimeError):
@@ -45,7 +57,7 @@ SIGNATURES = {
     "wn_save_elems": (_i64, [_vp]),
     "wn_save_info": (C.c_int, [_vp, _i32, C.POINTER(_i64), C.POINTER(_i32)]),
     "wn_workspace_bytes": (_i64, [_vp, _i32]),
-    "wn_train_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "wn_train_forward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "wn_train_backward": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "wn_train_backward_phases": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp]),
     "wn_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _vp]),

@@ -101,6 +101,9 @@ def engine_arch(arch: dict, pad: bool = True) -> dict:
                n_res=arch["n_res"], n_dil=arch["n_dil"], n_skip=arch["n_skip"], n_post=arch["n_post"],
                n_gc_embed=arch["n_gc_embed"], n_gc_category=arch["n_gc_category"],
                use_bias=1 if arch["use_bias"] else 0)
+    if arch.get("n_lc_out", 0):  # local conditioning (tmodel.py:15-17): mel channels, conditioning channels, strides
+        out.update(n_lc_in=int(arch["n_lc_in"]), n_lc_out=int(arch["n_lc_out"]),
+                   lc_upsample=[int(x) for x in arch["lc_upsample"]])
     if pad:
         out["n_res"], out["n_dil"] = _pad_res_dil(out["n_res"]), _pad_res_dil(out["n_dil"])
         if out["n_res"] != out["n_dil"] and max(out["n_res"], out["n_dil"]) <= 64:

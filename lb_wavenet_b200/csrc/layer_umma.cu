@@ -136,10 +136,18 @@ struct LayerFwdPArgs {
   const float* gc_tbl;  // global conditioning: this layer's [C1][2D] projection table (tmodel.py:150-154), else nullptr
   const int32_t* ids;   // [B][T] voice ids
   int C1;
+  // local conditioning (tmodel.py:156-160): this layer's plane [B*T][2D] bf16 = lc_upsampled . [LC_SIGNAL | LC_GATE],
+  // added to the pre-activations row by row in the gate epilogue
+  const bf16* cond;
   long long* trace;
 };
+// 4 bf16 (two packed words) added onto a float4 of pre-activation biases, scaled (GATE half: 0.5, see the file header)
+__device__ __forceinline__ void add_bf16x4(float4& b, uint32_t w0, uint32_t w1, float sc) {
+  b.x = fmaf(sc, __uint_as_float(w0 << 16), b.x); b.y = fmaf(sc, __uint_as_float(w0 & 0xffff0000u), b.y);
+  b.z = fmaf(sc, __uint_as_float(w1 << 16), b.z); b.w = fmaf(sc, __uint_as_float(w1 & 0xffff0000u), b.w);
+}
 
-template <int R, int D, bool GC>
+template <int R, int D, bool GC, bool LC>
 __global__ void __launch_bounds__(608, 2)
 k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_xout,
                    const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_wc,
@@ -320,6 +328,22 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const int s = i % NST, ab = g;
       // ---- gate: z = tanh(v_s + b_s) * sigmoid(v_g + b_g) ----
       tr.ev(5, i);
+      uint4 lcs[2], lcg[2];  // this row's local-conditioning projections (signal / gate channels of the two passes)
+      if constexpr (LC) {
+        // the tile id is published before the stage's loads are issued: visible once in_full[s] has completed (the stage
+        // cannot be recycled before this tile's epilogue has run).  The plane row is fetched while the conv MMA runs.
+        mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);
+        const int tl = tile_s[s];
+        lcs[0] = lcs[1] = lcg[0] = lcg[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (tl >= 0) {
+          const int b = tl / a.tiles_per_slot, t = (tl % a.tiles_per_slot) * 128 + r;
+          if (t < a.T) {
+            const uint4* row = reinterpret_cast<const uint4*>(a.cond + ((size_t)b * a.T + t) * (2 * D) + 16 * half);
+            lcs[0] = __ldg(row); lcs[1] = __ldg(row + 1);
+            lcg[0] = __ldg(row + D / 8); lcg[1] = __ldg(row + D / 8 + 1);
+          }
+        }
+      }
       mbar_wait(&v_full[ab], (uint32_t)(i >> 1) & 1u);
       tr.ev(6, i);
       const int tile = tile_s[s];  // written before the loads the conv MMA (or the sentinel commit) waited for
@@ -351,6 +375,12 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
             b_s.x += c_s.x; b_s.y += c_s.y; b_s.z += c_s.z; b_s.w += c_s.w;
             b_g.x = fmaf(0.5f, c_g.x, b_g.x); b_g.y = fmaf(0.5f, c_g.y, b_g.y);
             b_g.z = fmaf(0.5f, c_g.z, b_g.z); b_g.w = fmaf(0.5f, c_g.w, b_g.w);
+          }
+          if constexpr (LC) {
+            const uint32_t ws0 = q == 0 ? lcs[p].x : lcs[p].z, ws1 = q == 0 ? lcs[p].y : lcs[p].w;
+            const uint32_t wg0 = q == 0 ? lcg[p].x : lcg[p].z, wg1 = q == 0 ? lcg[p].y : lcg[p].w;
+            add_bf16x4(b_s, ws0, ws1, 1.f);
+            add_bf16x4(b_g, wg0, wg1, 0.5f);
           }
           const float z0 = tanh_fast(__uint_as_float(vs[4 * q]) + b_s.x) * fmaf(0.5f, tanh_fast(__uint_as_float(vg[4 * q]) + b_g.x), 0.5f);
           const float z1 = tanh_fast(__uint_as_float(vs[4 * q + 1]) + b_s.y) * fmaf(0.5f, tanh_fast(__uint_as_float(vg[4 * q + 1]) + b_g.y), 0.5f);
@@ -495,11 +525,15 @@ struct LayerBwdFusedArgs {
   float* dgc_tbl;       // its gradient (fp32 atomics)
   const int32_t* ids;   // [B][T] voice ids
   int C1, T;
+  // local conditioning: this layer's plane [B*T][2D] bf16, read as the conditioning term of the recomputed
+  // pre-activations and OVERWRITTEN in place with dv = [dv_s | dv_g] (each thread writes exactly the bytes it read):
+  // the gradient wrt the plane, consumed by the LC weight / data gradients of phase L + 1
+  bf16* cond;
   int seq;  // launch sequence number while tracing (tools/trace_layer.py gaps)
   long long* trace;
 };
 
-template <int R, int D, bool GC>
+template <int R, int D, bool GC, bool LC>
 __global__ void __launch_bounds__(896, 1)
 k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz,
                        const __grid_constant__ CUtensorMap map_yn, const __grid_constant__ CUtensorMap map_pn,
@@ -717,6 +751,18 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
         const int b = tile / a.tiles_per_slot, t = (tile % a.tiles_per_slot) * 128 + r;
         gid = t < a.T ? min(max(__ldg(a.ids + (size_t)b * a.T + t), 0), a.C1 - 1) : 0;
       }
+      uint4 lcs[2], lcg[2];
+      uint4* lcrow = nullptr;
+      if constexpr (LC) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int b = tile / a.tiles_per_slot, t = (tile % a.tiles_per_slot) * 128 + r;
+        lcs[0] = lcs[1] = lcg[0] = lcg[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (t < a.T) {
+          lcrow = reinterpret_cast<uint4*>(a.cond + ((size_t)b * a.T + t) * (2 * D) + 16 * half);
+          lcs[0] = lcrow[0]; lcs[1] = lcrow[1];
+          lcg[0] = lcrow[D / 8]; lcg[1] = lcrow[D / 8 + 1];
+        }
+      }
       tr.ev(5, i);
       mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);  // dz tile (TMA) visible to this thread
       tr.ev(14, i);
@@ -755,6 +801,12 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
             b_g.x = fmaf(0.5f, c_g.x, b_g.x); b_g.y = fmaf(0.5f, c_g.y, b_g.y);
             b_g.z = fmaf(0.5f, c_g.z, b_g.z); b_g.w = fmaf(0.5f, c_g.w, b_g.w);
           }
+          if constexpr (LC) {
+            const uint32_t ws0 = q == 0 ? lcs[p].x : lcs[p].z, ws1 = q == 0 ? lcs[p].y : lcs[p].w;
+            const uint32_t wg0 = q == 0 ? lcg[p].x : lcg[p].z, wg1 = q == 0 ? lcg[p].y : lcg[p].w;
+            add_bf16x4(b_s, ws0, ws1, 1.f);
+            add_bf16x4(b_g, wg0, wg1, 0.5f);
+          }
           const float bsv[4] = {b_s.x, b_s.y, b_s.z, b_s.w}, bgv[4] = {b_g.x, b_g.y, b_g.z, b_g.w};
           float zz[4], ds[4], dg[4];
 #pragma unroll
@@ -772,6 +824,10 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
           pz[2 * q] = pack2(zz[0], zz[1]);  pz[2 * q + 1] = pack2(zz[2], zz[3]);
           pvs[2 * q] = pack2(ds[0], ds[1]); pvs[2 * q + 1] = pack2(ds[2], ds[3]);
           pvg[2 * q] = pack2(dg[0], dg[1]); pvg[2 * q + 1] = pack2(dg[2], dg[3]);
+          if constexpr (LC) {  // gradient wrt the conditioning plane: the true dv_g is half of what pairs with the 0.5-scaled filter
+            if (q == 0) { lcg[p].x = pack2(0.5f * dg[0], 0.5f * dg[1]); lcg[p].y = pack2(0.5f * dg[2], 0.5f * dg[3]); }
+            else        { lcg[p].z = pack2(0.5f * dg[0], 0.5f * dg[1]); lcg[p].w = pack2(0.5f * dg[2], 0.5f * dg[3]); }
+          }
           if constexpr (GC) {
             // table gradient: dTbl[id][n] += dv[n] (gate half: dv carries 2x).  A warp is 32 consecutive timesteps of
             // one slot, ids change only at file junctions: reduce over the warp when it is uniform, else per row
@@ -816,6 +872,12 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
         *reinterpret_cast<uint4*>(wbuf + W_Z * PANEL + o[p]) = make_uint4(pz[0], pz[1], pz[2], pz[3]);
         *reinterpret_cast<uint4*>(wbuf + W_DVS * PANEL + o[p]) = make_uint4(pvs[0], pvs[1], pvs[2], pvs[3]);
         *reinterpret_cast<uint4*>(wbuf + W_DVG * PANEL + o[p]) = make_uint4(pvg[0], pvg[1], pvg[2], pvg[3]);
+        if constexpr (LC) {
+          if (lcrow != nullptr) {
+            lcrow[p] = make_uint4(pvs[0], pvs[1], pvs[2], pvs[3]);
+            lcrow[D / 8 + p] = lcg[p];
+          }
+        }
       }
       tr.ev(15, i);
       fence_proxy_async_smem();
@@ -1122,16 +1184,25 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
   const size_t smem = 5 * 2 * 8192 + 2 * 8192 + 2 * 4096 + 2048 + 1024;
   const int nblk = persist_grid(std::max(1, std::min(pa.n_tiles, 2 * m->sm_count)));
   ProfScope ps(PROF_LAYER_FWD, st);
-  if (a.n_gc_embed > 0) {
+  const bool gc = a.n_gc_embed > 0, lc = a.n_lc_out > 0;
+  if (gc) {
     pa.gc_tbl = reinterpret_cast<const float*>(ws + wl.gc_tbl) + (size_t)l * C1 * 2 * a.n_dil;
     pa.ids = d_ids;
     pa.C1 = C1;
-    WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_fwd_p_umma<32, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WN_CUDA_CHECK(launch_pdl(k_layer_fwd_p_umma<32, 32, true>, nblk, 608, smem, st, mp->x[l], mxo, mp->z, mp->wc, mp->wr, pa));
-  } else {
-    WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_fwd_p_umma<32, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WN_CUDA_CHECK(launch_pdl(k_layer_fwd_p_umma<32, 32, false>, nblk, 608, smem, st, mp->x[l], mxo, mp->z, mp->wc, mp->wr, pa));
   }
+  if (lc) pa.cond = reinterpret_cast<const bf16*>(ws + wl.cond) + (size_t)l * m->n_slots * T * 2 * a.n_dil;
+#define WN_FWD(GC_, LC_)                                                                                                  \
+  {                                                                                                                       \
+    WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_fwd_p_umma<32, 32, GC_, LC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem));                                                                       \
+    WN_CUDA_CHECK(launch_pdl(k_layer_fwd_p_umma<32, 32, GC_, LC_>, nblk, 608, smem, st, mp->x[l], mxo, mp->z, mp->wc,     \
+                             mp->wr, pa));                                                                                \
+  }
+  if (gc && lc) WN_FWD(true, true)
+  else if (gc) WN_FWD(true, false)
+  else if (lc) WN_FWD(false, true)
+  else WN_FWD(false, false)
+#undef WN_FWD
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
@@ -1166,21 +1237,28 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
   const int grid = persist_grid(std::max(1, std::min(ga.n_tiles, m->sm_count)));
   const int nx = (l + 1) & 1, cu = l & 1;
   ProfScope ps(PROF_LAYER_BWD_A, st);
-  if (m->a.n_gc_embed > 0) {
+  const bool gc = m->a.n_gc_embed > 0, lc = m->a.n_lc_out > 0;
+  ga.T = T;
+  if (gc) {
     const int C1 = m->a.n_gc_category + 1;
     ga.gc_tbl = reinterpret_cast<const float*>(ws + m->wl.gc_tbl) + (size_t)l * C1 * 2 * m->a.n_dil;
     ga.dgc_tbl = reinterpret_cast<float*>(ws + m->wl.dgc_tbl) + (size_t)l * C1 * 2 * m->a.n_dil;
     ga.ids = d_ids;
     ga.C1 = C1;
-    ga.T = T;
-    WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_umma<32, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_umma<32, 32, true>, grid, 896, smem, st, mp->x[l], mp->dz, mp->dx[nx],
-                             mp->p0[nx], mp->dx[cu], mp->p0[cu], mp->wc, mp->wrn, ga));
-  } else {
-    WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_umma<32, 32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_umma<32, 32, false>, grid, 896, smem, st, mp->x[l], mp->dz, mp->dx[nx],
-                             mp->p0[nx], mp->dx[cu], mp->p0[cu], mp->wc, mp->wrn, ga));
   }
+  if (lc) ga.cond = reinterpret_cast<bf16*>(ws + m->wl.cond) + (size_t)l * m->n_slots * T * 2 * m->a.n_dil;
+#define WN_BWD(GC_, LC_)                                                                                                  \
+  {                                                                                                                       \
+    WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_umma<32, 32, GC_, LC_>,                                          \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
+    WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_umma<32, 32, GC_, LC_>, grid, 896, smem, st, mp->x[l], mp->dz, mp->dx[nx], \
+                             mp->p0[nx], mp->dx[cu], mp->p0[cu], mp->wc, mp->wrn, ga));                                   \
+  }
+  if (gc && lc) WN_BWD(true, true)
+  else if (gc) WN_BWD(true, false)
+  else if (lc) WN_BWD(false, true)
+  else WN_BWD(false, false)
+#undef WN_BWD
   WN_LAUNCH_CHECK();
   return WN_OK;
 }

@@ -77,6 +77,27 @@ const WorkspaceLayout& workspace_layout(wn_model* m, int32_t T) {
   w.wrT = take(L * R * D * 2);
   w.wrN = take(L * D * R * 2);
   w.wdP = take(L * R * 4 * D * 2);
+  for (int i = 0; i < 9; ++i) w.lc_x[i] = w.lc_dx[i] = 0;
+  for (int i = 0; i < 8; ++i) w.lc_wup[i] = w.lc_wupT[i] = 0;
+  w.cond = w.lc_wcat = w.lc_wcatT = w.lc_gtmp = 0;
+  if (a.n_lc_out > 0) {
+    const int64_t LCP = 128;
+    int64_t r = rows / m->lc_hop, gt = L * LCP * 2 * D;
+    for (int i = 0; i <= a.n_lc_layers; ++i) {
+      w.lc_x[i] = take(align_up(r, 128) * LCP * 2);
+      if (i > 0) w.lc_dx[i] = take(align_up(r, 128) * LCP * 2);
+      if (i < a.n_lc_layers) {
+        w.lc_wup[i] = take((int64_t)a.lc_upsample[i] * LCP * LCP * 2);
+        w.lc_wupT[i] = take((int64_t)a.lc_upsample[i] * LCP * LCP * 2);
+        gt += LCP * a.lc_upsample[i] * LCP;
+        r *= a.lc_upsample[i];
+      }
+    }
+    w.cond = take(L * rows * 2 * D * 2);
+    w.lc_wcat = take(L * 2 * D * LCP * 2);
+    w.lc_wcatT = take(L * 2 * D * LCP * 2);
+    w.lc_gtmp = take(gt * 4);
+  }
   w.total = off;
   m->wl = w;
   return m->wl;
@@ -142,6 +163,18 @@ int wn_model_create(const wn_arch* arch, int32_t n_slots, wn_model** out) {
   if (a.n_gc_embed < 0 || a.n_gc_embed > 64) return bad("n_gc_embed must be in [0,64]");
   if (a.n_gc_embed > 0 && a.n_gc_category < 1) return bad("n_gc_category must be >= 1 with global conditioning");
   if (n_slots < 1) return bad("n_slots must be >= 1");
+  if (a.n_lc_out < 0 || a.n_lc_out > 128 || a.n_lc_in < 0 || a.n_lc_in > 128) return bad("n_lc_in / n_lc_out must be in [0,128]");
+  int64_t hop = 1;
+  if (a.n_lc_out > 0) {
+    if (a.n_lc_in < 1) return bad("local conditioning needs n_lc_in >= 1");
+    if (a.n_lc_layers < 1 || a.n_lc_layers > 8) return bad("lc_upsample must hold 1..8 strides");
+    for (int i = 0; i < a.n_lc_layers; ++i) {
+      if (a.lc_upsample[i] < 1 || a.lc_upsample[i] > 16) return bad("lc_upsample strides must be in [1,16]");
+      hop *= a.lc_upsample[i];
+    }
+    if (hop > 65536) return bad("prod(lc_upsample) too large");
+    if (a.n_res != 32 || a.n_dil != 32) return bad("local conditioning is built for n_res == n_dil == 32 (the fused layer kernels)");
+  }
 
   wn_model* m = new wn_model();
   m->a = a;
@@ -155,6 +188,15 @@ int wn_model_create(const wn_arch* arch, int32_t n_slots, wn_model** out) {
   m->off_gc_embed = gc ? add_param(m, "GC_EMBED", {a.n_gc_category + 1, G}, WN_KIND_FILTER) : -1;
   m->off_pre = add_param(m, "PRE", {Q, R}, WN_KIND_FILTER);
   m->off_pre_b = ub ? add_param(m, "PRE_BIAS", {R}, WN_KIND_BIAS) : -1;
+  const bool lc = a.n_lc_out > 0;
+  m->lc_hop = (int32_t)hop;
+  for (int i = 0; i < 8; ++i) m->off_lc_up[i] = -1;
+  if (lc)  // tmodel.py:68-83 (_preprocess_lc runs right after _preprocess, tmodel.py:307-311); shape arch.py:75-80
+    for (int i = 0; i < a.n_lc_layers; ++i) {
+      char nm[32];
+      snprintf(nm, sizeof(nm), "LC_UPSAMPLE_%d", i);
+      m->off_lc_up[i] = add_param(m, nm, {(int64_t)a.lc_upsample[i], (int64_t)a.n_lc_out, (int64_t)(i == 0 ? a.n_lc_in : a.n_lc_out)}, WN_KIND_FILTER);
+    }
   for (int b = 0; b < a.n_blocks; ++b) {
     for (int bl = 0; bl < a.n_block_layers; ++bl) {
       char sfx[32];
@@ -170,6 +212,8 @@ int wn_model_create(const wn_arch* arch, int32_t n_slots, wn_model** out) {
       d.gate_b = ub ? add_param(m, std::string("GATE_BIAS") + sfx, {D}, WN_KIND_BIAS) : -1;
       d.gc_sig = gc ? add_param(m, std::string("GC_SIGNAL") + sfx, {G, D}, WN_KIND_FILTER) : -1;
       d.gc_gate = gc ? add_param(m, std::string("GC_GATE") + sfx, {G, D}, WN_KIND_FILTER) : -1;
+      d.lc_sig = lc ? add_param(m, std::string("LC_SIGNAL") + sfx, {(int64_t)a.n_lc_out, D}, WN_KIND_FILTER) : -1;  // tmodel.py:156-160
+      d.lc_gate = lc ? add_param(m, std::string("LC_GATE") + sfx, {(int64_t)a.n_lc_out, D}, WN_KIND_FILTER) : -1;
       d.res = add_param(m, std::string("RESIDUAL") + sfx, {D, R}, WN_KIND_FILTER);
       d.res_b = ub ? add_param(m, std::string("RESIDUAL_BIAS") + sfx, {R}, WN_KIND_BIAS) : -1;
       d.skip = add_param(m, std::string("SKIP") + sfx, {D, S}, WN_KIND_FILTER);
@@ -233,6 +277,10 @@ int wn_save_info(const wn_model* m, int32_t layer, int64_t* offset, int32_t* dil
 int64_t wn_workspace_bytes(const wn_model* m, int32_t slice_sz) {
   if (slice_sz < 2) {
     set_error("wn_workspace_bytes: slice_sz must be >= 2");
+    return WN_ERR_INVALID;
+  }
+  if (m->a.n_lc_out > 0 && slice_sz % m->lc_hop != 0) {
+    set_error("wn_workspace_bytes: slice_sz %d must be a multiple of prod(lc_upsample) = %d (data.py:32-37)", slice_sz, m->lc_hop);
     return WN_ERR_INVALID;
   }
   return workspace_layout(const_cast<wn_model*>(m), slice_sz).total;

@@ -28,6 +28,7 @@ struct ParamEntry {
 // and also uploaded as a device table.  -1 == tensor absent (no bias / no GC).
 struct LayerDesc {
   int64_t sig, sig_b, gate, gate_b, gc_sig, gc_gate, res, res_b, skip, skip_b;
+  int64_t lc_sig, lc_gate;  // LC_SIGNAL / LC_GATE [n_lc_out][D] (reference tmodel.py:156-160), -1 without local conditioning
   int64_t save_off;   // element offset into the bf16 SAVE arena, layout [n_slots][dil][R]
   int64_t xfull_off;  // byte offset of xfull_l in the workspace (filled per slice_sz)
   int32_t dil;
@@ -58,6 +59,16 @@ struct WorkspaceLayout {
   int64_t w2T;        // [Q][P]     = POST2^T
   int64_t wcT, wrT, wrN;     // per-layer conv / residual operands of the tcgen05 layer kernels (layer_umma.cu)
   int64_t wdP;               // [L][R][4D]: B operand of the wide layers' data gradient (train_umma.cu)
+  // ---- local conditioning (train_umma.cu "local conditioning"): every activation row is 128 bf16 wide (LCP), channels
+  // beyond n_lc_in / n_lc_out are zero.  lc_x[0] = mel frames, lc_x[i + 1] = output of upsampling level i.
+  int64_t lc_x[9];           // [B * T_i][128] bf16, T_i = T / hop * prod(s_0 .. s_{i-1})
+  int64_t lc_dx[9];          // gradients of the same (index 0 unused)
+  int64_t cond;              // [L][B*T][2D] bf16: lc_up . [LC_SIGNAL_l | LC_GATE_l]; the layer backward overwrites it with dv
+  int64_t lc_wup[8];         // [s_i * 128][128] bf16: B operand of level i  (row k * 128 + o, column c) = LC_UPSAMPLE_i[k][o][c]
+  int64_t lc_wupT[8];        // [128][s_i * 128] bf16: its transpose, B operand of the level's data gradient
+  int64_t lc_wcat;           // [L * 2D][128] bf16: row l * 2D + n = (LC_SIGNAL_l | LC_GATE_l)[c][n]
+  int64_t lc_wcatT;          // [128][L * 2D] bf16
+  int64_t lc_gtmp;           // fp32 scratch for the weight gradients: [L][128][2D] | per level [128][s_i * 128]
   int64_t total;
   std::vector<int64_t> xfull;  // per layer: [B][dil+T][R] bf16
 };
@@ -71,6 +82,8 @@ struct wn_model {
   std::vector<wn::ParamEntry> params;
   int64_t n_param_elems;
   int64_t off_pre, off_pre_b, off_gc_embed, off_post1, off_post1_b, off_post2, off_post2_b;
+  int64_t off_lc_up[8];  // LC_UPSAMPLE_i [s_i][n_lc_out][n_lc_in | n_lc_out]
+  int32_t lc_hop;        // prod(lc_upsample), 1 without local conditioning
   std::vector<wn::LayerDesc> layers;
   int64_t save_elems;
   wn::WorkspaceLayout wl;  // cached for the last slice_sz

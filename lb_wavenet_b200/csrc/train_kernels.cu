@@ -98,6 +98,8 @@ bool umma_wgrad_supported(const wn_model* m, int lda, int ldy, int N);
 int launch_wgrad_umma(wn_model* m, const bf16* A, int lda, int a_col0, int M_total, const bf16* Y, int ldy, int N,
                       int64_t rows, float* out, int ldo, int mode, float* grads, cudaStream_t st);
 int launch_post_bwd_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, cudaStream_t st);
+int launch_lc_fwd(wn_model* m, const float* d_params, const float* d_mel, unsigned char* ws, int T, cudaStream_t st);
+int launch_lc_bwd(wn_model* m, unsigned char* ws, int T, float* d_grads, cudaStream_t st);
 int launch_post_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_wav,
                          const int32_t* d_ids, int T, double* d_stats, float* d_logits, cudaStream_t st);
 
@@ -1074,10 +1076,15 @@ int64_t wn_launch_count_reset(void) {
 }
 
 int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int32_t* d_wav,
-                     const int32_t* d_ids, int32_t T, void* d_ws, double* d_stats, float* d_logits,
+                     const int32_t* d_ids, const float* d_mel, int32_t T, void* d_ws, double* d_stats, float* d_logits,
                      void* stream_) {
   if (!m || !d_params || !d_save || !d_wav || !d_ids || !d_ws || !d_stats || T < 2) {
     set_error("wn_train_forward: invalid argument");
+    return WN_ERR_INVALID;
+  }
+  const bool lc = m->a.n_lc_out > 0;
+  if (lc && (!d_mel || T % m->lc_hop != 0)) {
+    set_error("wn_train_forward: local conditioning needs d_mel and slice_sz %% prod(lc_upsample) == 0");
     return WN_ERR_INVALID;
   }
   cudaStream_t st = (cudaStream_t)stream_;
@@ -1093,6 +1100,10 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
   const bool umma_chain = !umma_post && umma_post_chain_supported(m);
   const bool umma_layer = umma_layer_supported(m);
   const bool umma_wide = !umma_layer && umma_wide_layer_supported(m);
+  if (lc && !umma_layer) {
+    set_error("wn_train_forward: local conditioning runs on the fused tcgen05 layer kernels only (n_res == n_dil == 32)");
+    return WN_ERR_UNSUPPORTED;
+  }
   if (!(umma_layer || umma_wide) || !(umma_post || umma_chain) || (umma_wide && !umma_wgrad_x_supported(m, T))) {
     // still the device path, but 10-20x slower than the tcgen05 kernels: say so once instead of silently
     static bool noted = false;
@@ -1132,6 +1143,7 @@ int wn_train_forward(wn_model* m, const float* d_params, void* d_save, const int
     WN_LAUNCH_CHECK();
   }
   }
+  if (lc && (rc = launch_lc_fwd(m, d_params, d_mel, ws, T, st))) return rc;
   const size_t lsm = layer_fwd_smem(d.R, d.D);
   rc = set_smem(k_layer_fwd, lsm);
   if (rc) return rc;
@@ -1381,6 +1393,7 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
     k_embed_bwd_reduce<<<((d.Q + 1) * d.R + 255) / 256, 256, 0, st>>>(part, nblk, d_grads, m->off_pre, m->off_pre_b, d.R, d.Q);
     WN_LAUNCH_CHECK();
   }
+  if (m->a.n_lc_out > 0 && (rc = launch_lc_bwd(m, ws, T, d_grads, st))) return rc;
   if (gc) {
     const float* dtbl = reinterpret_cast<const float*>(ws + wl.dgc_tbl);
     k_gc_bwd_embed<<<d.C1, 64, 0, st>>>(d_params, dtbl, m->d_layers, d_grads, m->off_gc_embed, d.L, d.C1, d.G, d.D);

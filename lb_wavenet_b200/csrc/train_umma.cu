@@ -807,6 +807,7 @@ int launch_post_bwd_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, 
 //   1  bf16(acc * (H > 0))                         -> staging tile -> TMA store        (dp1, dskip)
 //   2  bf16(acc) as per-layer [128 x D] panels     -> TMA stores into the dz planes
 //   3  logits = acc + bias; masked softmax cross entropy, statistics, dlogits          (tmodel.py:228-249)
+//   7  bf16(acc)                                   -> staging tile -> TMA store        (local-conditioning chain)
 // =====================================================================================================
 namespace wn {
 
@@ -841,6 +842,9 @@ struct GemmUmmaArgs {
   // version when B is larger than the A tile (wide layers: 128 KB of conv weights against a 64 KB activation tile).
   int b_resident, a_stages;
   int l2_prefetch;  // producer prefetches the next tile's A blocks into L2 (3-D maps only)
+  // a_planes: A is a stack of K / 64 planes [plane][rows][64] (the per-layer dcond planes): K block kb of a row tile is
+  // the 3-D box (0, row0, kb) of map_a
+  int a_planes;
 };
 constexpr int GEMM_MAX_STAGES = 8;
 
@@ -929,6 +933,8 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               int k0 = kb * UKB, roff = 0;
               if (a.a_k_split > 0 && k0 >= a.a_k_split) { k0 -= a.a_k_split; roff = a.a_row_off2; }
               tma_load_3d(stage_a + st * UA_BYTES, &map_a, &full_bar[st], a.a_col0 + k0, t0 + roff, sb);
+            } else if (a.a_planes) {
+              tma_load_3d(stage_a + st * UA_BYTES, &map_a, &full_bar[st], 0, row0, kb);
             } else {
               tma_load_2d(stage_a + st * UA_BYTES, &map_a, &full_bar[st], kb * UKB, row0);
             }
@@ -1027,7 +1033,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           if (elected) tma_store_wait_read<0>();  // the previous item's stores have finished reading the staging tile
           epi_bar_sync256();
         }
-        if (a.mode == 0 || a.mode == 1) {
+        if (a.mode == 0 || a.mode == 1 || a.mode == 7) {
           const int cb = half * (w / 2);
           for (int c0 = cb; c0 < cb + w / 2; c0 += 32) {
             tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
@@ -1037,6 +1043,9 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
               for (int j = 0; j < 16; ++j)
                 pk[j] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + bias_s[n0 + c0 + 2 * j], 0.f),
                                     fmaxf(__uint_as_float(v[2 * j + 1]) + bias_s[n0 + c0 + 2 * j + 1], 0.f));
+            } else if (a.mode == 7) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
             } else if (in_range) {
               mask_pack32(v, a.H + (size_t)row * a.N + n0 + c0, pk);
             } else {
@@ -1360,7 +1369,14 @@ static int launch_gemm_umma(wn_model* m, const void* A, int K, const void* B, in
                             GemmUmmaArgs ga, cudaStream_t st) {
   CUtensorMap ma, mb, mo;
   int rc;
-  if ((rc = map2d(&ma, A, (uint64_t)K, (uint64_t)rows, UKB, UM))) return rc;
+  if (ga.a_planes) {
+    const uint64_t dims[3] = {UKB, (uint64_t)rows, (uint64_t)(K / UKB)};
+    const uint64_t strides[2] = {UKB * 2, (uint64_t)rows * UKB * 2};
+    const uint32_t box[3] = {UKB, UM, 1};
+    if ((rc = make_tensor_map_bf16(&ma, A, 3, dims, strides, box, 128))) return rc;
+  } else if ((rc = map2d(&ma, A, (uint64_t)K, (uint64_t)rows, UKB, UM))) {
+    return rc;
+  }
   if ((rc = map2d(&mb, B, (uint64_t)K, (uint64_t)N, UKB, (uint32_t)std::min(256, N)))) return rc;
   if (ga.mode == 2) {
     const uint64_t D = ga.D, PW = std::min<uint64_t>(D, 64);
@@ -1885,6 +1901,177 @@ int launch_wgrad_umma_x(wn_model* m, const bf16* xfull, int dil, int T, int tap,
 
 bool umma_wgrad_supported(const wn_model* m, int lda, int ldy, int N) {
   return umma_post_supported(m) && N % 16 == 0 && N <= 256 && lda % 8 == 0 && ldy % 8 == 0;
+}
+
+// =====================================================================================================
+// Local conditioning (reference tmodel.py:68-83 _preprocess_lc, :156-160 the per-layer LC projections; arch.py:75-80).
+// A transposed convolution whose width equals its stride is a plain GEMM: level i maps [B*T_i x n_in] onto
+// [B*T_i x s_i*n_out], which IS [B*T_i*s_i x n_out] row-major (out[b, t*s + k, o] = sum_c in[b, t, c] W_i[k][o][c]).
+// All LC activations use 128-column rows (LCP; channels beyond n_lc_in / n_lc_out are zero), so every level is
+// k_gemm_umma with K = 128, N = s_i * 128; the per-layer projections of ALL layers are one more GEMM
+// lc_up[rows x 128] . [LC_SIGNAL_l | LC_GATE_l]_l (N = L * 2D) whose epilogue writes per-layer planes cond[l][rows][2D]
+// -- the operand the fused layer kernels add in their gate epilogues.  Backward: the layer kernels leave dv in those
+// planes; LC_SIGNAL / LC_GATE gradients = lc_up^T . dcond_l (split-K k_wgrad_umma), d lc_up = sum_l dcond_l . Wlc_l^T
+// (one GEMM whose K blocks are the planes), then the upsampling chain in reverse.
+// =====================================================================================================
+constexpr int LCP = 128;
+
+struct LcPrepArgs {
+  int n_levels, L, D, n_in, n_out;
+  int s[8];
+  int64_t off_up[8];
+  bf16* wup[8];
+  bf16* wupT[8];
+  bf16* wcat;
+  bf16* wcatT;
+};
+
+// blocks [0, n_levels): level i ; blocks [n_levels, n_levels + L): layer l
+__global__ void k_lc_prep(const float* __restrict__ p, const LayerDesc* __restrict__ layers, LcPrepArgs a) {
+  const int bid = blockIdx.x;
+  if (bid < a.n_levels) {
+    const int i = bid, s = a.s[i], nin = i == 0 ? a.n_in : a.n_out;
+    const float* w = p + a.off_up[i];  // [s][n_out][nin]
+    for (int e = threadIdx.x; e < s * LCP * LCP; e += blockDim.x) {
+      const int n = e / LCP, c = e % LCP;  // n = k * 128 + o
+      const int k = n / LCP, o = n % LCP;
+      const float v = (o < a.n_out && c < nin) ? w[((int64_t)k * a.n_out + o) * nin + c] : 0.f;
+      a.wup[i][e] = f2bf(v);
+      a.wupT[i][(int64_t)c * (s * LCP) + n] = f2bf(v);
+    }
+  } else {
+    const int l = bid - a.n_levels, D = a.D;
+    const LayerDesc ld = layers[l];
+    const int64_t LD2 = (int64_t)a.L * 2 * D;
+    for (int e = threadIdx.x; e < 2 * D * LCP; e += blockDim.x) {
+      const int n = e / LCP, c = e % LCP;
+      const float v = c < a.n_out ? p[(n < D ? ld.lc_sig : ld.lc_gate) + (int64_t)c * D + (n % D)] : 0.f;
+      a.wcat[((int64_t)l * 2 * D + n) * LCP + c] = f2bf(v);
+      a.wcatT[(int64_t)c * LD2 + (int64_t)l * 2 * D + n] = f2bf(v);
+    }
+  }
+}
+
+__global__ void k_lc_mel(const float* __restrict__ mel, bf16* __restrict__ out, int64_t rows0, int n_in) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows0 * LCP) return;
+  const int64_t r = i / LCP;
+  const int c = (int)(i % LCP);
+  out[i] = f2bf(c < n_in ? mel[r * n_in + c] : 0.f);
+}
+
+// grads <- the fp32 scratch the split-K kernels accumulated into
+__global__ void k_lc_scatter(const float* __restrict__ gtmp, const LayerDesc* __restrict__ layers, float* __restrict__ grads,
+                             LcPrepArgs a, int64_t up_off0) {
+  const int bid = blockIdx.x;
+  if (bid < a.L) {
+    const LayerDesc ld = layers[bid];
+    const float* g = gtmp + (int64_t)bid * LCP * 2 * a.D;  // [128][2D]
+    for (int e = threadIdx.x; e < a.n_out * 2 * a.D; e += blockDim.x) {
+      const int c = e / (2 * a.D), n = e % (2 * a.D);
+      grads[(n < a.D ? ld.lc_sig : ld.lc_gate) + (int64_t)c * a.D + (n % a.D)] = g[(int64_t)c * 2 * a.D + n];
+    }
+  } else {
+    const int i = bid - a.L, s = a.s[i], nin = i == 0 ? a.n_in : a.n_out;
+    int64_t off = up_off0;
+    for (int j = 0; j < i; ++j) off += (int64_t)LCP * a.s[j] * LCP;
+    const float* g = gtmp + off;  // [128 (c)][s * 128 (k * 128 + o)]
+    for (int e = threadIdx.x; e < s * a.n_out * nin; e += blockDim.x) {
+      const int k = e / (a.n_out * nin), o = (e / nin) % a.n_out, c = e % nin;
+      grads[a.off_up[i] + e] = g[(int64_t)c * (s * LCP) + k * LCP + o];
+    }
+  }
+}
+
+static LcPrepArgs lc_args(wn_model* m, unsigned char* ws) {
+  const WorkspaceLayout& wl = m->wl;
+  LcPrepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_levels = m->a.n_lc_layers; a.L = m->L; a.D = m->a.n_dil; a.n_in = m->a.n_lc_in; a.n_out = m->a.n_lc_out;
+  for (int i = 0; i < a.n_levels; ++i) {
+    a.s[i] = m->a.lc_upsample[i];
+    a.off_up[i] = m->off_lc_up[i];
+    a.wup[i] = reinterpret_cast<bf16*>(ws + wl.lc_wup[i]);
+    a.wupT[i] = reinterpret_cast<bf16*>(ws + wl.lc_wupT[i]);
+  }
+  a.wcat = reinterpret_cast<bf16*>(ws + wl.lc_wcat);
+  a.wcatT = reinterpret_cast<bf16*>(ws + wl.lc_wcatT);
+  return a;
+}
+
+// mel frames -> upsampled conditioning -> per-layer planes cond[l][rows][2D]  (runs before the layer loop)
+int launch_lc_fwd(wn_model* m, const float* d_params, const float* d_mel, unsigned char* ws, int T, cudaStream_t st) {
+  const WorkspaceLayout& wl = m->wl;
+  const wn_arch& a = m->a;
+  const int64_t rows = (int64_t)m->n_slots * T;
+  const int n = a.n_lc_layers;
+  int rc;
+  ProfScope ps(PROF_PREP, st);
+  const LcPrepArgs pa = lc_args(m, ws);
+  k_lc_prep<<<n + m->L, 256, 0, st>>>(d_params, m->d_layers, pa);
+  WN_LAUNCH_CHECK();
+  int64_t r = rows / m->lc_hop;
+  k_lc_mel<<<(unsigned)((r * LCP + 255) / 256), 256, 0, st>>>(d_mel, reinterpret_cast<bf16*>(ws + wl.lc_x[0]), r, a.n_lc_in);
+  WN_LAUNCH_CHECK();
+  GemmUmmaArgs ga;
+  for (int i = 0; i < n; ++i) {
+    memset(&ga, 0, sizeof(ga));
+    ga.mode = 7;
+    if ((rc = launch_gemm_umma(m, ws + wl.lc_x[i], LCP, ws + wl.lc_wup[i], a.lc_upsample[i] * LCP, ws + wl.lc_x[i + 1], r, ga, st)))
+      return rc;
+    r *= a.lc_upsample[i];
+  }
+  memset(&ga, 0, sizeof(ga));
+  ga.mode = 2;
+  ga.D = 2 * a.n_dil;
+  return launch_gemm_umma(m, ws + wl.lc_x[n], LCP, ws + wl.lc_wcat, m->L * 2 * a.n_dil, ws + wl.cond, rows, ga, st);
+}
+
+// after every layer's backward has left dv in its plane: LC_SIGNAL / LC_GATE / LC_UPSAMPLE gradients
+int launch_lc_bwd(wn_model* m, unsigned char* ws, int T, float* d_grads, cudaStream_t st) {
+  const WorkspaceLayout& wl = m->wl;
+  const wn_arch& a = m->a;
+  const int64_t rows = (int64_t)m->n_slots * T;
+  const int n = a.n_lc_layers, D2 = 2 * a.n_dil;
+  int rc;
+  int64_t gt = (int64_t)m->L * LCP * D2;
+  const int64_t up_off0 = gt;
+  for (int i = 0; i < n; ++i) gt += (int64_t)LCP * a.lc_upsample[i] * LCP;
+  float* gtmp = reinterpret_cast<float*>(ws + wl.lc_gtmp);
+  WN_CUDA_CHECK(cudaMemsetAsync(gtmp, 0, sizeof(float) * gt, st));
+  const bf16* lc_up = reinterpret_cast<const bf16*>(ws + wl.lc_x[n]);
+  const bf16* cond = reinterpret_cast<const bf16*>(ws + wl.cond);
+  for (int l = 0; l < m->L; ++l)
+    if ((rc = launch_wgrad_umma(m, lc_up, LCP, 0, LCP, cond + (size_t)l * rows * D2, D2, D2, rows,
+                                gtmp + (size_t)l * LCP * D2, D2, 0, nullptr, st)))
+      return rc;
+  GemmUmmaArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.mode = 7;
+  ga.a_planes = 1;
+  if ((rc = launch_gemm_umma(m, ws + wl.cond, m->L * D2, ws + wl.lc_wcatT, LCP, ws + wl.lc_dx[n], rows, ga, st))) return rc;
+  std::vector<int64_t> rws(n + 1);
+  rws[0] = rows / m->lc_hop;
+  for (int i = 0; i < n; ++i) rws[i + 1] = rws[i] * a.lc_upsample[i];
+  int64_t up_off = up_off0;
+  std::vector<int64_t> up_offs(n);
+  for (int i = 0; i < n; ++i) { up_offs[i] = up_off; up_off += (int64_t)LCP * a.lc_upsample[i] * LCP; }
+  for (int i = n - 1; i >= 0; --i) {
+    const int N = a.lc_upsample[i] * LCP;
+    if ((rc = launch_wgrad_umma_cols(m, reinterpret_cast<const bf16*>(ws + wl.lc_x[i]), LCP, LCP,
+                                     reinterpret_cast<const bf16*>(ws + wl.lc_dx[i + 1]), N, rws[i], gtmp + up_offs[i], 0,
+                                     nullptr, st)))
+      return rc;
+    if (i > 0) {
+      memset(&ga, 0, sizeof(ga));
+      ga.mode = 7;
+      if ((rc = launch_gemm_umma(m, ws + wl.lc_dx[i + 1], N, ws + wl.lc_wupT[i], LCP, ws + wl.lc_dx[i], rws[i], ga, st))) return rc;
+    }
+  }
+  const LcPrepArgs pa = lc_args(m, ws);
+  k_lc_scatter<<<m->L + n, 256, 0, st>>>(gtmp, m->d_layers, d_grads, pa, up_off0);
+  WN_LAUNCH_CHECK();
+  return WN_OK;
 }
 
 }  // namespace wn

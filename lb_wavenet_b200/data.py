@@ -15,6 +15,7 @@ from the .npy headers) and materialise just their own slots.
 from __future__ import annotations
 
 import itertools
+import os
 import queue
 import threading
 from dataclasses import dataclass
@@ -79,7 +80,10 @@ class SlotDealer:
 
     def __init__(self, catalog: Sequence[Tuple[int, WavSource]], batch_sz: int, slice_sz: int,
                  recep_field_sz: int, mel_hop_sz: int = 1, seed: int = 0, position: int = 0,
-                 slot_lo: int = 0, slot_hi: Optional[int] = None, quiet: bool = False, wav_dtype: str = "i32"):
+                 slot_lo: int = 0, slot_hi: Optional[int] = None, quiet: bool = False, wav_dtype: str = "i32",
+                 mel_channels: int = 0):
+        """catalog entries: (voice_id, wav) or (voice_id, wav, mel); mel_channels > 0: also deal the mel frames
+        [len / hop, mel_channels] of every window (reference data.py:121,170-171,187,222)."""
         if not catalog:
             raise ValueError("empty sample catalog")
         from . import _lib
@@ -110,6 +114,10 @@ class SlotDealer:
         self._file_ptr = np.zeros(nf, np.uint64)
         self._file_dtype = np.zeros(nf, np.int32)
         self._loaded = {}                                     # catalog index -> contiguous array (local slots' files)
+        self.mel_channels = int(mel_channels)
+        self._mel_loaded = {}
+        if self.mel_channels > 0 and any(len(c) < 3 or c[2] is None for c in self.catalog):
+            raise ValueError("local conditioning needs a mel.npy for every catalog entry (data.py:43-48)")
         self._seg = np.empty((max(64, 8 * n), 5), np.int64)
         self._n_seg = np.zeros(1, np.int64)
         self._used = np.zeros(1, np.int64)
@@ -132,11 +140,19 @@ class SlotDealer:
         self._loaded[idx] = arr
         self._file_ptr[idx] = arr.ctypes.data
         self._file_dtype[idx] = code
+        if self.mel_channels > 0:
+            mel = np.asarray(_npy_load(self.catalog[idx][2]), np.float32)
+            if mel.ndim != 2 or mel.shape[1] != self.mel_channels or mel.shape[0] * self.hop != int(self._usable[idx]):
+                # data.py:143-146
+                raise ValueError("Error: len(wav) = {}, len(mel) * mel_hop_sz = {} (mel shape {}, expected {} channels)"
+                                 .format(int(self._usable[idx]), mel.shape[0] * self.hop, mel.shape, self.mel_channels))
+            self._mel_loaded[idx] = mel
 
     def _evict(self) -> None:
         live = set(int(f) for f in self._cur_file[self.slot_lo:self.slot_hi] if f >= 0)
         for idx in [i for i in self._loaded if i not in live]:
             del self._loaded[idx]
+            self._mel_loaded.pop(idx, None)
             self._file_ptr[idx] = 0
 
     # ---- exact resume (beyond the reference, whose (seed, position) restart re-deals every slot from a fresh file:
@@ -161,10 +177,13 @@ class SlotDealer:
             idx = int(self._cur_file[slot])
             self._cur_len[slot] = self._usable_len(idx) if idx >= 0 else 0
         self._loaded.clear()
+        self._mel_loaded.clear()
         self._file_ptr[:] = 0
 
-    def next_batch(self, wav_out: Optional[np.ndarray] = None, ids_out: Optional[np.ndarray] = None):
-        """Returns (latest_file_read_count, wav[n_local x T], ids[int32 n_local x T])."""
+    def next_batch(self, wav_out: Optional[np.ndarray] = None, ids_out: Optional[np.ndarray] = None,
+                   mel_out: Optional[np.ndarray] = None):
+        """Returns (latest_file_read_count, wav[n_local x T], ids[int32 n_local x T]); with mel_channels > 0 the mel
+        frames float32 [n_local, T / hop, mel_channels] are written into mel_out (kept in self.last_mel)."""
         T, nl = self.slice_sz, self.slot_hi - self.slot_lo
         wav = np.empty((nl, T), self._np_wav) if wav_out is None else wav_out
         ids = np.empty((nl, T), np.int32) if ids_out is None else ids_out
@@ -198,6 +217,14 @@ class SlotDealer:
         self._check(lib.wn_deal_fill(seg.ctypes.data, len(seg), self._file_ptr.ctypes.data, self._file_dtype.ctypes.data,
                                      self._voice.ctypes.data, len(self.catalog), self.F, T, self._out_code,
                                      wav.ctypes.data, ids.ctypes.data), "wn_deal_fill")
+        if self.mel_channels > 0:
+            hop = self.hop
+            mel = np.empty((nl, T // hop, self.mel_channels), np.float32) if mel_out is None else mel_out
+            for row in seg:  # windows, files and cursors are all multiples of hop (data.py:32-37,141-142)
+                if row[0] >= 0:
+                    r, d0, idx, s0, n = (int(x) for x in row)
+                    mel[r, d0 // hop:(d0 + n) // hop] = self._mel_loaded[idx][s0 // hop:(s0 + n) // hop]
+            self.last_mel = mel
         self._evict()
         return int(self._slot_count[self.batch_sz - 1]), wav, ids  # data.py:220
 
@@ -255,8 +282,8 @@ class MaskedSliceWav(ckpt.Checkpoint):
         """reference data.py:43-48; ``entries`` lets synthetic in-memory 'files' stand in for a TSV."""
         self.sample_catalog = []
         if entries is not None:
-            for vid, wav in entries:
-                self.sample_catalog.append([int(vid), wav, None])
+            for e in entries:
+                self.sample_catalog.append([int(e[0]), e[1], e[2] if len(e) > 2 else None])
             return
         with open(self.sam_file) as sam_fh:
             for s in sam_fh.readlines():
@@ -330,9 +357,13 @@ class MaskedSliceWav(ckpt.Checkpoint):
         # device path: codes travel as uint8 (5 bytes per timestep with the int32 id) and are widened to
         # int32 on the copy stream; host path (no CUDA: CPU tests, tools): int32 codes as data.py:262-265
         wav_dtype = "f32" if raw else ("u8" if self._use_cuda else "i32")
-        self._dealer = SlotDealer([(e[0], e[1]) for e in self.sample_catalog], self.batch_sz, self.slice_sz,
-                                  self.recep_field_sz, self.mel_hop_sz, self.random_seed, self.ckpt_position, lo, hi,
-                                  wav_dtype=wav_dtype)
+        # mel frames travel with the windows when the catalog has them and the model consumes them (mel_spectrum_sz > 0)
+        self._mel_ch = int(self.mel_spectrum_sz or 0) if all(
+            len(e) > 2 and e[2] is not None and (not isinstance(e[2], str) or os.path.exists(e[2]))
+            for e in self.sample_catalog) else 0
+        self._dealer = SlotDealer([(e[0], e[1], e[2] if len(e) > 2 else None) for e in self.sample_catalog], self.batch_sz,
+                                  self.slice_sz, self.recep_field_sz, self.mel_hop_sz, self.random_seed,
+                                  self.ckpt_position, lo, hi, wav_dtype=wav_dtype, mel_channels=self._mel_ch)
         st = getattr(self, "_resume_state", None)
         if st is not None:  # exact resume: restore() found the optional keys
             self._dealer.load_state(st, self.random_seed)
@@ -350,6 +381,7 @@ class MaskedSliceWav(ckpt.Checkpoint):
         self._copy_events = []   # (start, end, bytes) of the newest H2D copies: loader_stats()
         self._deal_seconds, self._deal_batches = 0.0, 0
         shape = (self._n_local, self.slice_sz)
+        mshape = (self._n_local, self.slice_sz // self.mel_hop_sz, max(1, self._mel_ch))
         if self._use_cuda:
             import torch
             self._torch = torch
@@ -363,9 +395,14 @@ class MaskedSliceWav(ckpt.Checkpoint):
             self._devbuf = [(self._stage[k] if raw else torch.empty(shape, dtype=torch.int32, device=self._dev),
                              torch.empty(shape, dtype=torch.int32, device=self._dev)) for k in range(n)]
             self._copy_stream = torch.cuda.Stream(device=self._dev)
+            if self._mel_ch:
+                self._pin_mel = [torch.empty(mshape, dtype=torch.float32).pin_memory() for _ in range(n)]
+                self._dev_mel = [torch.empty(mshape, dtype=torch.float32, device=self._dev) for _ in range(n)]
         else:
             self._hostbuf = [(np.empty(shape, np.float32 if raw else np.int32), np.empty(shape, np.int32))
                              for _ in range(n)]
+            if self._mel_ch:
+                self._host_mel = [np.empty(mshape, np.float32) for _ in range(n)]
         self._worker = threading.Thread(target=self._produce, name="wav-loader", daemon=True,
                                         args=(self._stop, self._q, self._free, self._dealer))
         self._worker.start()
@@ -386,7 +423,7 @@ class MaskedSliceWav(ckpt.Checkpoint):
                 if self._use_cuda:
                     torch = self._torch
                     pw, pi = self._pin[k]
-                    cnt, _, _ = dealer.next_batch(pw.numpy(), pi.numpy())
+                    cnt, _, _ = dealer.next_batch(pw.numpy(), pi.numpy(), self._pin_mel[k].numpy() if self._mel_ch else None)
                     st = dealer.state()
                     self._deal_seconds += time.perf_counter() - t0
                     self._deal_batches += 1
@@ -397,6 +434,8 @@ class MaskedSliceWav(ckpt.Checkpoint):
                         e0.record(self._copy_stream)
                         self._stage[k].copy_(pw, non_blocking=True)
                         di.copy_(pi, non_blocking=True)
+                        if self._mel_ch:
+                            self._dev_mel[k].copy_(self._pin_mel[k], non_blocking=True)
                         e1.record(self._copy_stream)
                         if dw is not self._stage[k]:
                             from . import _lib
@@ -404,12 +443,13 @@ class MaskedSliceWav(ckpt.Checkpoint):
                                                                       self._copy_stream.cuda_stream), "wn_codes_u8_to_i32")
                         ev = torch.cuda.Event()
                         ev.record(self._copy_stream)
-                    self._copy_events.append((e0, e1, pw.numel() * pw.element_size() + pi.numel() * 4))
+                    self._copy_events.append((e0, e1, pw.numel() * pw.element_size() + pi.numel() * 4 +
+                                              (self._pin_mel[k].numel() * 4 if self._mel_ch else 0)))
                     del self._copy_events[:-64]
                     q.put((cnt, k, ev, st))
                 else:
                     hw, hi = self._hostbuf[k]
-                    cnt, _, _ = dealer.next_batch(hw, hi)
+                    cnt, _, _ = dealer.next_batch(hw, hi, self._host_mel[k] if self._mel_ch else None)
                     self._deal_seconds += time.perf_counter() - t0
                     self._deal_batches += 1
                     q.put((cnt, k, None, dealer.state()))
@@ -454,12 +494,12 @@ class MaskedSliceWav(ckpt.Checkpoint):
             cur.wait_event(ev)  # this batch's H2D copy
             self._last_k = k
             dw, di = self._devbuf[k]
-            return Batch(cnt, dw, di, None, st)
+            return Batch(cnt, dw, di, self._dev_mel[k] if self._mel_ch else None, st)
         if self._last_k is not None:
             self._free.put((self._last_k, None))
         self._last_k = k
         hw, hi = self._hostbuf[k]
-        return Batch(cnt, hw, hi, None, st)
+        return Batch(cnt, hw, hi, self._host_mel[k] if self._mel_ch else None, st)
 
     def _shutdown(self):
         if self._worker is not None:

@@ -17,6 +17,7 @@ from ._lib import WnArch, check, ptr
 
 ARCH_KEYS = ("n_blocks", "n_block_layers", "n_quant", "n_res", "n_dil", "n_skip", "n_post",
              "n_gc_embed", "n_gc_category", "use_bias")
+LC_KEYS = ("n_lc_in", "n_lc_out")  # + lc_upsample (list of strides); absent / 0 == no local conditioning
 
 
 @dataclass
@@ -49,8 +50,14 @@ class Registry:
     def __init__(self, arch: dict, n_slots: int):
         lib = _lib.load()
         self.arch = {k: int(arch[k]) for k in ARCH_KEYS}
+        for k in LC_KEYS:
+            self.arch[k] = int(arch.get(k, 0) or 0)
+        self.arch["lc_upsample"] = [int(x) for x in (arch.get("lc_upsample") or [])] if self.arch["n_lc_out"] > 0 else []
+        if self.arch["n_lc_out"] == 0:
+            self.arch["n_lc_in"] = 0
+        self.lc_hop = int(np.prod(self.arch["lc_upsample"])) if self.arch["lc_upsample"] else 1
         self.n_slots = int(n_slots)
-        wa = WnArch(**self.arch)
+        wa = WnArch.from_dict(self.arch)
         h = C.c_void_p()
         check(lib.wn_model_create(C.byref(wa), self.n_slots, C.byref(h)), "wn_model_create")
         self.handle = h
@@ -158,21 +165,33 @@ class TrainEngine:
             self.ws = self.torch.empty(nbytes, dtype=self.torch.uint8, device=self.device)
             self.ws_T = T
 
-    def forward(self, wav, ids, want_logits: bool = False):
-        """wav, ids: int32 device tensors [n_slots, T].  Updates SAVE and stats in place."""
+    def forward(self, wav, ids, want_logits: bool = False, mel=None):
+        """wav, ids: int32 device tensors [n_slots, T]; mel: float32 device tensor [n_slots, T / hop, n_lc_in] when the
+        architecture has local conditioning.  Updates SAVE and stats in place."""
         torch = self.torch
         assert wav.dtype == torch.int32 and ids.dtype == torch.int32 and wav.is_cuda and ids.is_cuda
         assert wav.shape == ids.shape and wav.shape[0] == self.reg.n_slots
         wav, ids = wav.contiguous(), ids.contiguous()
         T = int(wav.shape[1])
+        if self.reg.arch["n_lc_out"] > 0:
+            if mel is None:
+                raise ValueError("this architecture has local conditioning: forward() needs the mel frames")
+            want = (self.reg.n_slots, T // self.reg.lc_hop, self.reg.arch["n_lc_in"])
+            if T % self.reg.lc_hop or tuple(mel.shape) != want or mel.dtype != torch.float32 or not mel.is_cuda:
+                raise ValueError("mel must be a float32 device tensor of shape {} (slice_sz {} / hop {}), got {} {}".format(
+                    want, T, self.reg.lc_hop, tuple(mel.shape), mel.dtype))
+            mel = mel.contiguous()
+        else:
+            mel = None
         self._ensure_ws(T)
         logits = None
         if want_logits:
             logits = torch.empty(self.reg.n_slots, T, self.reg.arch["n_quant"], dtype=torch.float32, device=self.device)
-        check(self.lib.wn_train_forward(self.reg.handle, ptr(self.params), ptr(self.save), ptr(wav), ptr(ids), T,
-                                        ptr(self.ws), ptr(self.stats), ptr(logits), _lib.cur_stream()),
+        check(self.lib.wn_train_forward(self.reg.handle, ptr(self.params), ptr(self.save), ptr(wav), ptr(ids), ptr(mel),
+                                        T, ptr(self.ws), ptr(self.stats), ptr(logits), _lib.cur_stream()),
               "wn_train_forward")
         self._last = (wav, ids, T)
+        self._last_mel = mel  # keep the buffer alive until the backward has consumed the conditioning planes
         return logits
 
     def backward(self):

@@ -83,7 +83,7 @@ class WaveNetTrain(ar.WaveNetArch):
         self._arch_dict = config.engine_arch(dict(
             n_blocks=n_blocks, n_block_layers=n_block_layers, n_quant=n_quant, n_res=n_res, n_dil=n_dil,
             n_skip=n_skip, n_post=n_post, n_gc_embed=n_gc_embed, n_gc_category=n_gc_category,
-            n_lc_out=n_lc_out, use_bias=use_bias))
+            n_lc_in=n_lc_in, n_lc_out=n_lc_out, lc_upsample=lc_upsample, use_bias=use_bias))
         self.engine = None
         self._source = None
         self.global_step = 0      # GLOBAL_STEP   (tmodel.py:223-224)
@@ -166,6 +166,9 @@ class WaveNetTrain(ar.WaveNetArch):
         self.get_variable(ar.ArchCat.PRE)
         if self.use_bias:
             self.get_variable(ar.ArchCat.PRE, get_bias=True)
+        if self.use_lc_input():  # tmodel.py:68-83 (_preprocess_lc, called right after _preprocess: tmodel.py:307-311)
+            for i in range(len(self.lc_upsample)):
+                self.get_variable(ar.ArchCat.LC_UPSAMPLE, i)
         for b in range(self.n_blocks):
             for bl in range(self.n_block_layers):
                 dil = 2 ** bl
@@ -177,6 +180,9 @@ class WaveNetTrain(ar.WaveNetArch):
                 if self.has_global_cond():
                     self.get_variable(ar.ArchCat.GC_SIGNAL, b, bl)
                     self.get_variable(ar.ArchCat.GC_GATE, b, bl)
+                if self.use_lc_input():  # tmodel.py:156-160
+                    self.get_variable(ar.ArchCat.LC_SIGNAL, b, bl)
+                    self.get_variable(ar.ArchCat.LC_GATE, b, bl)
                 for a in (ar.ArchCat.RESIDUAL, ar.ArchCat.SKIP):
                     self.get_variable(a, b, bl)
                     if self.use_bias:
@@ -191,8 +197,6 @@ class WaveNetTrain(ar.WaveNetArch):
     def build(self, wav_input=None, lc_input=None, id_mask=None):
         """Registers the model's variables, binds the data source and returns (grads_vars, loss)
         op handles (reference tmodel.py:292-340)."""
-        if self.use_lc_input():
-            raise NotImplementedError("local conditioning is not built yet (DESIGN.md 'next')")
         self._source = getattr(wav_input, "dataset", None)
         self._register_variables()
         self.add_saveable_objects(self.vars)  # tmodel.py:330
@@ -242,6 +246,20 @@ class WaveNetTrain(ar.WaveNetArch):
         return mode
 
     # ---- one training step ------------------------------------------------------------------
+    def _prepare_mel(self, mel):
+        """mel frames [batch_sz or local slots, slice_sz / hop, n_lc_in] -> float32 device tensor of the local slots"""
+        if not self.use_lc_input():
+            return None
+        if mel is None:
+            raise ValueError("this architecture has local conditioning (n_lc_out > 0): the step needs the mel frames")
+        eng = self.engine
+        torch = eng.torch
+        if not torch.is_tensor(mel):
+            mel = torch.as_tensor(np.asarray(mel, np.float32))
+        if mel.shape[0] == self.batch_sz and self.batch_sz != self.n_local_slots:
+            mel = mel[self.slot_lo:self.slot_hi]
+        return mel.to(eng.device, dtype=torch.float32, non_blocking=True)
+
     def _prepare_inputs(self, wav, ids):
         eng = self.engine
         torch = eng.torch
@@ -262,7 +280,7 @@ class WaveNetTrain(ar.WaveNetArch):
             wav = codes
         return wav.to(torch.int32), ids.to(torch.int32)
 
-    def forward_backward(self, wav, ids, want_loss: bool = False):
+    def forward_backward(self, wav, ids, want_loss: bool = False, mel=None):
         """Forward + backward (+ data-parallel reduction).  Leaves the global statistics in
         self._gstats and the summed unnormalised gradients in engine.grads.  want_loss: also evaluate the L2 term (on the
         weights the loss is computed with, as tmodel.py:250-261 does) and start the device -> host copy of the
@@ -270,7 +288,7 @@ class WaveNetTrain(ar.WaveNetArch):
         eng = self._ensure_engine()
         torch = eng.torch
         wav, ids = self._prepare_inputs(wav, ids)
-        eng.forward(wav, ids)
+        eng.forward(wav, ids, mel=self._prepare_mel(mel))
         if want_loss:
             eng.l2_loss()
         self._gstats.copy_(eng.stats)
@@ -323,13 +341,13 @@ class WaveNetTrain(ar.WaveNetArch):
         assert phase == L + 2
         cur.wait_stream(self._comm_stream)
 
-    def train_step(self, wav, ids, optimizer: AdamOptimizer, want_loss: bool = True):
+    def train_step(self, wav, ids, optimizer: AdamOptimizer, want_loss: bool = True, mel=None):
         """One optimiser step on a [batch_sz or local slots, slice_sz] batch (host or device tensors).
         Returns the total loss of tmodel.py:261 as a Python float (one 32-byte device->host read)."""
         eng = self._ensure_engine()
         if getattr(self, "_optimizer", None) is not optimizer:
             self.bind_optimizer(optimizer)  # its slots become (optional) checkpoint keys
-        self.forward_backward(wav, ids, want_loss)
+        self.forward_backward(wav, ids, want_loss, mel=mel)
         optimizer.t += 1
         eng.adam(optimizer.t, optimizer.learning_rate, self.l2_factor, n_valid=self._gstats[1:2],
                  beta1=optimizer.beta1, beta2=optimizer.beta2, eps=optimizer.epsilon)
@@ -366,5 +384,5 @@ class WaveNetTrain(ar.WaveNetArch):
             raise ValueError("run() needs the op returned by optimizer.apply_gradients")
         batch = self._source.next_batch()
         self.file_read_count = batch.file_read_count
-        loss = self.train_step(batch.wav, batch.ids, apply_op.opt)
+        loss = self.train_step(batch.wav, batch.ids, apply_op.opt, mel=batch.mel)
         return [None if isinstance(f, ApplyGradsOp) else loss for f in fetches]

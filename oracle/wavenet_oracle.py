@@ -47,6 +47,21 @@ class Arch:
     n_gc_embed: int = 0
     n_gc_category: int = 0
     use_bias: bool = True
+    # local conditioning (reference tmodel.py:15-17, arch.py:75-80): mel channels, conditioning channels, strides
+    n_lc_in: int = 0
+    n_lc_out: int = 0
+    lc_upsample: Tuple[int, ...] = ()
+
+    def has_lc(self) -> bool:
+        # reference arch.py:108-109 use_lc_input
+        return self.n_lc_out > 0
+
+    def lc_hop(self) -> int:
+        # reference train.py:129-130
+        h = 1
+        for s_ in self.lc_upsample:
+            h *= int(s_)
+        return h if self.has_lc() else 1
 
     @property
     def n_layers(self) -> int:
@@ -87,6 +102,9 @@ def param_shapes(a: Arch, batch_sz: int) -> "OrderedDict[str, Tuple[Tuple[int, .
     add("PRE", (Q, R), "filter")  # tmodel.py:96
     if a.use_bias:
         add("PRE_BIAS", (R,), "bias")  # tmodel.py:98-100
+    if a.has_lc():  # tmodel.py:68-83 (called from build right after _preprocess, tmodel.py:307-311); shape arch.py:75-80
+        for i, s_ in enumerate(a.lc_upsample):
+            add("LC_UPSAMPLE_{}".format(i), (int(s_), a.n_lc_out, a.n_lc_in if i == 0 else a.n_lc_out), "filter")
     for (b, bl), dil in zip(a.layer_ids(), a.dilations()):
         sfx = "{}_{}".format(b, bl)
         add("SAVE_{}_{}".format(dil, sfx), (batch_sz, dil, R), "save")  # tmodel.py:123-124
@@ -97,6 +115,9 @@ def param_shapes(a: Arch, batch_sz: int) -> "OrderedDict[str, Tuple[Tuple[int, .
         if a.has_gc():  # tmodel.py:150-154
             add("GC_SIGNAL_{}".format(sfx), (G, D), "filter")
             add("GC_GATE_{}".format(sfx), (G, D), "filter")
+        if a.has_lc():  # tmodel.py:156-160; shape arch.py:96-97
+            add("LC_SIGNAL_{}".format(sfx), (a.n_lc_out, D), "filter")
+            add("LC_GATE_{}".format(sfx), (a.n_lc_out, D), "filter")
         add("RESIDUAL_{}".format(sfx), (D, R), "filter")  # tmodel.py:171-181
         if a.use_bias:
             add("RESIDUAL_BIAS_{}".format(sfx), (R,), "bias")
@@ -255,10 +276,33 @@ def _t(p, name, dtype):
     return torch.as_tensor(np.asarray(v), dtype=dtype)
 
 
+def lc_upsample(a: Arch, p: Dict[str, torch.Tensor], mel: torch.Tensor, emulate_bf16: bool = False,
+                impl: str = "gemm", keep: Optional[list] = None) -> torch.Tensor:
+    """reference tmodel.py:68-83 _preprocess_lc: a chain of tf.contrib.nn.conv1d_transpose(lc, filt, out_shape, stride)
+    with filt [width, out_channels, in_channels] (arch.py:75-80) and width == stride == lc_upsample[i], no bias, no
+    non-linearity: out[b, t*s + k, o] = sum_c in[b, t, c] * filt[k, o, c]  ('SAME' and 'VALID' agree when width == stride).
+    impl 'gemm' = that formula as one matmul per level; 'conv_transpose' = torch.nn.functional.conv_transpose1d, a
+    structurally different statement of the same op.  emulate_bf16: the CUDA path's rounding points (mel, every level's
+    output and the filters are bf16 operands).  keep: list that receives every level's input (for the backward)."""
+    lc = _maybe(mel, emulate_bf16)
+    for i, s_ in enumerate(a.lc_upsample):
+        filt = _maybe(p["LC_UPSAMPLE_{}".format(i)], emulate_bf16)  # [s, n_out, n_in]
+        if keep is not None:
+            keep.append(lc)
+        B, Ti, _ = lc.shape
+        if impl == "gemm":
+            out = torch.einsum("btc,koc->btko", lc, filt).reshape(B, Ti * int(s_), filt.shape[1])
+        else:
+            w = filt.permute(2, 1, 0)  # conv_transpose1d weight: [in_channels, out_channels, width]
+            out = torch.nn.functional.conv_transpose1d(lc.transpose(1, 2), w, stride=int(s_)).transpose(1, 2)
+        lc = _maybe(out, emulate_bf16)
+    return lc
+
+
 def train_forward(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.Tensor],
                   wav: torch.Tensor, ids: torch.Tensor, dtype=torch.float64,
                   emulate_bf16: bool = False, conv_impl: str = "taps",
-                  keep: bool = False) -> FwdResult:
+                  keep: bool = False, mel: Optional[torch.Tensor] = None) -> FwdResult:
     """Forward of WaveNetTrain.build (reference tmodel.py:292-328).
 
     p: name -> tensor already in ``dtype`` (requires_grad as the caller wishes).
@@ -285,6 +329,10 @@ def train_forward(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.Tensor],
 
     if a.has_gc():
         gathered = p["GC_EMBED"][ids]  # tmodel.py:112  [B,T,G]
+    lc_up = None
+    if a.has_lc():  # tmodel.py:307-311; mel [B, T / hop, n_lc_in]
+        lc_up = lc_upsample(a, p, mel.to(dtype), em)
+        assert lc_up.shape[1] == T, (lc_up.shape, T)
 
     new_save, xs, zs = [], [], []
     skp_sum = None
@@ -303,6 +351,8 @@ def train_forward(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.Tensor],
                 vv = vv + p["{}_BIAS_{}".format(nm, sfx)]  # tmodel.py:145-148
             if a.has_gc():  # tmodel.py:150-154 (fp32 table in the CUDA path, no bf16 rounding)
                 vv = vv + gathered @ p["GC_{}_{}".format(nm, sfx)]
+            if a.has_lc():  # tmodel.py:156-160 (the CUDA path stores the projection as a bf16 plane)
+                vv = vv + _maybe(lc_up @ W("LC_{}_{}".format(nm, sfx)), em)
             v[nm] = vv
         new_save.append(full[:, full.shape[1] - dil:, :].detach())  # tmodel.py:165
         z = torch.tanh(v["SIGNAL"]) * torch.sigmoid(v["GATE"])  # tmodel.py:167
@@ -399,14 +449,15 @@ def to_torch_params(a: Arch, p_np: Dict[str, np.ndarray], batch_sz: int, dtype=t
 
 
 def train_step_autograd(a: Arch, p_np: Dict[str, np.ndarray], wav: np.ndarray, ids: np.ndarray,
-                        l2_factor: float, dtype=torch.float64, emulate_bf16: bool = False):
+                        l2_factor: float, dtype=torch.float64, emulate_bf16: bool = False, mel=None):
     """One forward+backward through torch autograd (the oracle for tmodel.grad_var,
     reference tmodel.py:354-358).  Returns (grads dict name->np, LossResult, FwdResult)."""
     B = wav.shape[0]
     p, save, kinds = to_torch_params(a, p_np, B, dtype)
     w = torch.as_tensor(np.asarray(wav), dtype=torch.int64)
     i = torch.as_tensor(np.asarray(ids), dtype=torch.int64)
-    fwd = train_forward(a, p, save, w, i, dtype, emulate_bf16, keep=True)
+    mt = None if mel is None else torch.as_tensor(np.asarray(mel), dtype=dtype)
+    fwd = train_forward(a, p, save, w, i, dtype, emulate_bf16, keep=True, mel=mt)
     L = loss_fn(a, fwd.logits, w, i, p, kinds, l2_factor)
     L.total.backward()
     grads = {k: (v.grad.detach().numpy().copy() if v.grad is not None else np.zeros(tuple(v.shape)))
@@ -424,7 +475,7 @@ def train_step_autograd(a: Arch, p_np: Dict[str, np.ndarray], wav: np.ndarray, i
 
 def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.Tensor],
                           wav: torch.Tensor, ids: torch.Tensor, dtype=torch.float64,
-                          emulate_bf16: bool = False):
+                          emulate_bf16: bool = False, mel: Optional[torch.Tensor] = None):
     em = emulate_bf16
     B, T = wav.shape
     with torch.no_grad():
@@ -433,7 +484,12 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
         def W(name):
             return _maybe(pd[name], em)
 
-        fwd = train_forward(a, pd, save, wav, ids, dtype, em, keep=True)
+        fwd = train_forward(a, pd, save, wav, ids, dtype, em, keep=True, mel=mel)
+        lc_in: list = []
+        lc_up, dlc_up = None, None
+        if a.has_lc():
+            lc_up = lc_upsample(a, pd, mel.to(dtype), em, keep=lc_in)
+            dlc_up = torch.zeros_like(lc_up)
         # recompute post-net intermediates
         h1 = _maybe(torch.relu(fwd.skip_sum), em)
         d1 = h1 @ W("POST1") + (pd["POST1_BIAS"] if a.use_bias else 0)
@@ -477,6 +533,8 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
                     vv = vv + pd["{}_BIAS_{}".format(nm, sfx)]
                 if a.has_gc():
                     vv = vv + gathered @ pd["GC_{}_{}".format(nm, sfx)]
+                if a.has_lc():
+                    vv = vv + _maybe(lc_up @ W("LC_{}_{}".format(nm, sfx)), em)
                 v[nm] = vv
             th, sg = torch.tanh(v["SIGNAL"]), torch.sigmoid(v["GATE"])
             g["SKIP_" + sfx] = flat(z).T @ flat(dskip)
@@ -497,6 +555,9 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
                     g["GC_{}_{}".format(nm, sfx)] = flat(gathered).T @ flat(dv)
                     dgath = dv @ pd["GC_{}_{}".format(nm, sfx)].T  # [B,T,G]
                     g["GC_EMBED"].index_add_(0, ids.reshape(-1), flat(dgath))
+                if a.has_lc():  # dv (already a bf16 tile in the CUDA path) is the gradient wrt the conditioning plane
+                    g["LC_{}_{}".format(nm, sfx)] = flat(lc_up).T @ flat(dv)
+                    dlc_up += dv @ W("LC_{}_{}".format(nm, sfx)).T
             # data gradient: x_l[t] feeds v[t] through W[1] and v[t+dil] through W[0];
             # rows that fall in the SAVE prefix receive none (truncated at the stage boundary)
             Ws, Wg = W("SIGNAL_" + sfx), W("GATE_" + sfx)
@@ -509,6 +570,16 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
             if T > dil:
                 dxl[:, :T - dil, :] += _maybe(old_part, em)[:, dil:, :]
             dx = _maybe(dxl, em) if li > 0 else dxl  # layer 0's gradient feeds the PRE gather in split form
+        if a.has_lc():  # the upsampling chain in reverse (tmodel.py:68-83)
+            d = _maybe(dlc_up, em)
+            for i in reversed(range(len(a.lc_upsample))):
+                s_ = int(a.lc_upsample[i])
+                filt = W("LC_UPSAMPLE_{}".format(i))  # [s, n_out, n_in]
+                xin = lc_in[i]  # [B, Ti, n_in]
+                dv_ = d.reshape(xin.shape[0], xin.shape[1], s_, filt.shape[1])  # [B, Ti, k, o]
+                g["LC_UPSAMPLE_{}".format(i)] = torch.einsum("btko,btc->koc", dv_, xin)
+                if i > 0:
+                    d = _maybe(torch.einsum("btko,koc->btc", dv_, filt), em)
         # PRE gather backward
         g["PRE"] = torch.zeros_like(pd["PRE"])
         okay = ((wav >= 0) & (wav < a.n_quant)).reshape(-1)
@@ -531,7 +602,7 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
 
 def layer_single(a: Arch, p: Dict[str, torch.Tensor], li: int, x_full: torch.Tensor, ids: Optional[torch.Tensor] = None,
                  dz_skip: Optional[torch.Tensor] = None, dx_next: Optional[torch.Tensor] = None,
-                 round_weights: bool = True) -> Dict[str, torch.Tensor]:
+                 round_weights: bool = True, lc_up: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """x_full [B, dil+T, R] = [SAVE ; x_l] (tmodel.py:127).  Forward: z_l, x_{l+1}.  With dz_skip [B,T,D] (gradient wrt
     z_l through the skip branch) and dx_next [B,T,R] (gradient wrt x_{l+1}; zeros after the last layer) also the
     unnormalised backward of the layer: filter / bias gradients, and the data gradient in the split form the CUDA path
@@ -556,6 +627,8 @@ def layer_single(a: Arch, p: Dict[str, torch.Tensor], li: int, x_full: torch.Ten
             vv = vv + p["{}_BIAS_{}".format(nm, sfx)].to(dt)
         if a.has_gc():
             vv = vv + gathered @ p["GC_{}_{}".format(nm, sfx)].to(dt)
+        if lc_up is not None:  # tmodel.py:156-160; lc_up [B, T, n_lc_out]
+            vv = vv + lc_up.to(dt) @ W("LC_{}_{}".format(nm, sfx))
         v[nm] = vv
     th, sg = torch.tanh(v["SIGNAL"]), torch.sigmoid(v["GATE"])
     z = th * sg

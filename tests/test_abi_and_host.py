@@ -48,13 +48,14 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), "symbol %s declared in the header but not exported" % name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.wn_abi_version() == 1
+    assert lib.wn_abi_version() == 2
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (wn_[a-z0-9_]+)", out))
     assert declared <= exported
 
 
-@pytest.mark.parametrize("arch", [util.TINY, util.TINY_GC, util.TINY_NOBIAS, util.WIDE, util.CLASSIC, util.C1])
+@pytest.mark.parametrize("arch", [util.TINY, util.TINY_GC, util.TINY_NOBIAS, util.WIDE, util.CLASSIC, util.C1,
+                                  util.TINY_LC, util.TINY_GC_LC, util.ARCH5])
 def test_registry_matches_reference_names_and_shapes(lib, arch):
     """arch.py:85-103,126,142 + tmodel.py:292-328: serial names, shapes, construction order."""
     from lb_wavenet_b200.engine import Registry
@@ -74,7 +75,8 @@ def test_registry_matches_reference_names_and_shapes(lib, arch):
     assert all(b0 >= a1 for (_, a1), (b0, _) in zip(spans, spans[1:])) and spans[-1][1] <= reg.n_param_elems
     assert all(o % 64 == 0 for o, _ in spans)
     assert reg.save_elems == sum(int(np.prod(s)) for _, s in saves)
-    assert reg.workspace_bytes(64) < reg.workspace_bytes(128)
+    hop = reg.lc_hop  # with local conditioning the stage length is a multiple of prod(lc_upsample) (data.py:32-37)
+    assert reg.workspace_bytes(64 * hop) < reg.workspace_bytes(128 * hop)
 
 
 def test_unsupported_architectures_are_rejected_with_a_message(lib):
@@ -116,8 +118,10 @@ def test_arch_schema_drift_is_normalised():
     assert a2["n_gc_category"] == 12 and config.mel_hop_sz(a2) == 256
     a4 = config.normalize_arch(REF_ARCH["arch4"], num_global_cond=5, warn=False)
     assert "lc_hop_sz" not in a4
-    with pytest.raises(NotImplementedError):
-        config.engine_arch(a4)  # local conditioning is a 'next' row
+    e4 = config.engine_arch(a4)  # local conditioning: the upsampling strides and channel counts reach the C ABI
+    assert e4["n_lc_in"] == 80 and e4["n_lc_out"] == 80 and e4["lc_upsample"] == [4, 4, 4, 4]
+    e2 = config.engine_arch(a2)  # arch2: n_lc_out == 0 -> no LC; tiny channel counts are zero-padded
+    assert "n_lc_out" not in e2 and (e2["n_res"], e2["n_dil"], e2["n_skip"], e2["n_post"]) == (32, 32, 64, 64)
     a3 = config.normalize_arch(REF_ARCH["arch3"], warn=False)
     # the normalised dict is exactly what WaveNetTrain.__init__ consumes (tmodel.py:8-24)
     assert set(a3) == {"n_blocks", "n_block_layers", "n_quant", "n_res", "n_dil", "n_skip", "n_post", "n_gc_embed",

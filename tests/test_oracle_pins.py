@@ -386,3 +386,44 @@ def test_single_layer_statement_composes_to_the_stack():
             assert torch.allclose(o["%s_%s" % (nm, sfx)], gman["%s_%s" % (nm, sfx)], rtol=1e-9, atol=1e-11), (nm, l)
         dx = o["dx"]
     assert torch.allclose(dx.reshape(-1, a.n_res).sum(0), gman["PRE_BIAS"], rtol=1e-9, atol=1e-11)
+
+
+def test_local_conditioning_statements_agree():
+    """reference tmodel.py:68-83 (_preprocess_lc) and :156-160: (1) the transposed convolution with width == stride as
+    one matmul per level == torch's conv_transpose1d; (2) every output frame t*s + k of a level depends on input frame
+    t only (hand case); (3) autograd == the hand-written backward on every LC tensor (LC_UPSAMPLE_i, LC_SIGNAL, LC_GATE)
+    == fp64 finite differences of the loss."""
+    arch = util.TINY_GC_LC
+    a = util.oracle_arch(dict(arch, n_res=8, n_dil=8, n_skip=16, n_post=16))
+    B, T = 2, 32
+    p = util.scaled_params(a, B, 7)
+    wav, ids = util.synth_batch(B, T, arch["n_gc_category"], 8)
+    mel = util.synth_mel(B, T, a, 9)
+    pt, save, kinds = O.to_torch_params(a, p, B, torch.float64, requires_grad=False)
+    m = torch.as_tensor(mel, dtype=torch.float64)
+    u1, u2 = O.lc_upsample(a, pt, m, impl="gemm"), O.lc_upsample(a, pt, m, impl="conv_transpose")
+    assert u1.shape == (B, T, a.n_lc_out) and torch.allclose(u1, u2, atol=1e-12)
+    m2 = m.clone()
+    m2[0, 3] += 1.0   # frame 3 -> output rows [3 * hop, 4 * hop) of slot 0 only
+    d = (O.lc_upsample(a, pt, m2) - u1).abs().sum(dim=2)
+    hop = a.lc_hop()
+    assert float(d[0, 3 * hop:4 * hop].min()) > 0 and float(d.sum() - d[0, 3 * hop:4 * hop].sum()) == 0.0
+    grads, L, _ = O.train_step_autograd(a, p, wav, ids, 0.0, torch.float64, mel=mel)
+    gm, _ = O.train_backward_manual(a, pt, save, torch.as_tensor(wav).long(), torch.as_tensor(ids).long(),
+                                    torch.float64, mel=m)
+    for k in grads:
+        assert np.allclose(grads[k] * L.n_valid, gm[k].numpy(), rtol=1e-9, atol=1e-11), k
+    # finite differences on one element of each LC tensor
+    def loss_of(pp):
+        q, sv, kd = O.to_torch_params(a, pp, B, torch.float64, requires_grad=False)
+        f = O.train_forward(a, q, sv, torch.as_tensor(wav).long(), torch.as_tensor(ids).long(), torch.float64, mel=m)
+        return float(O.loss_fn(a, f.logits, torch.as_tensor(wav).long(), torch.as_tensor(ids).long(), q, kd, 0.0).total)
+    for name, idx in (("LC_UPSAMPLE_0", (1, 2, 3)), ("LC_SIGNAL_0_1", (2, 1)), ("LC_GATE_1_0", (0, 3))):
+        eps = 1e-5
+        pp = {k: np.array(v, np.float64) for k, v in p.items()}
+        pp[name][idx] += eps
+        up = loss_of(pp)
+        pp[name][idx] -= 2 * eps
+        dn = loss_of(pp)
+        fd = (up - dn) / (2 * eps)
+        assert abs(fd - grads[name][idx]) <= 1e-6 * max(1.0, abs(fd)) + 1e-9, (name, fd, grads[name][idx])

@@ -20,9 +20,27 @@ C1 = dict(n_blocks=5, n_block_layers=10, n_quant=256, n_res=32, n_dil=32, n_skip
           n_gc_embed=17, n_gc_category=377, use_bias=1)
 
 
+# local conditioning (reference tmodel.py:68-83,156-160): small strides / channel counts, and the reference's own
+# par/arch5.json -- the one shipped architecture that satisfies train.py as written
+TINY_LC = dict(TINY, n_lc_in=20, n_lc_out=24, lc_upsample=[2, 4])
+TINY_GC_LC = dict(TINY_GC, n_lc_in=12, n_lc_out=16, lc_upsample=[4])
+ARCH5 = dict(n_blocks=5, n_block_layers=10, n_quant=256, n_res=32, n_dil=32, n_skip=512, n_post=512,
+             n_gc_embed=16, n_gc_category=376, use_bias=1, n_lc_in=80, n_lc_out=80, lc_upsample=[4, 4, 4, 4])
+
+
 def oracle_arch(d):
     return O.Arch(d["n_blocks"], d["n_block_layers"], d["n_quant"], d["n_res"], d["n_dil"], d["n_skip"],
-                  d["n_post"], d["n_gc_embed"], d["n_gc_category"], bool(d["use_bias"]))
+                  d["n_post"], d["n_gc_embed"], d["n_gc_category"], bool(d["use_bias"]),
+                  n_lc_in=d.get("n_lc_in", 0), n_lc_out=d.get("n_lc_out", 0),
+                  lc_upsample=tuple(d.get("lc_upsample", ())))
+
+
+def synth_mel(B, T, a, seed):
+    """mel frames [B, T / hop, n_lc_in] for an architecture with local conditioning (None otherwise)"""
+    if not a.has_lc():
+        return None
+    rng = np.random.default_rng(seed)
+    return rng.normal(0, 1.0, (B, T // a.lc_hop(), a.n_lc_in)).astype(np.float32)
 
 
 def synth_batch(B, T, n_cat, seed, invalid_frac=0.3):
