@@ -43,6 +43,7 @@ struct ProfScope {
   int cat;
   cudaStream_t st;
   bool on;
+  size_t rec = 0;  // index of this scope's record (scopes may nest: the LC backward runs inside the PRE / GC scope)
   ProfScope(int cat, cudaStream_t st);
   ~ProfScope();
 };

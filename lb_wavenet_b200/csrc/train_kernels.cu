@@ -43,7 +43,10 @@ static int g_prof_group_cat = -1;  // category of the open ProfGroup, -1: none
 
 ProfScope::ProfScope(int cat_, cudaStream_t st_)
     : cat(cat_), st(st_), on(((g_prof.mask >> cat_) & 1u) && g_prof_group_cat != cat_) {
-  if (on) g_prof.recs.push_back({cat, prof_event(st), 0, g_launches});
+  if (on) {
+    rec = g_prof.recs.size();
+    g_prof.recs.push_back({cat, prof_event(st), 0, g_launches});
+  }
 }
 ProfGroup::ProfGroup(int cat_, cudaStream_t st_, bool enable)
     : cat(cat_), st(st_), on(enable && ((g_prof.mask >> cat_) & 1u) && g_prof_group_cat < 0) {
@@ -64,9 +67,9 @@ ProfGroup::~ProfGroup() {
   }
 }
 ProfScope::~ProfScope() {
-  if (on) {
-    g_prof.recs.back().e1 = prof_event(st);
-    g_prof.recs.back().launches = g_launches - g_prof.recs.back().launches;
+  if (on && rec < g_prof.recs.size()) {
+    g_prof.recs[rec].e1 = prof_event(st);
+    g_prof.recs[rec].launches = g_launches - g_prof.recs[rec].launches;
   }
 }
 
@@ -1494,6 +1497,14 @@ int wn_debug_read(wn_model* m, const void* d_ws, int32_t T, int32_t what, int32_
       break;
     case 8:  // raw P0 buffer of parity `layer` & 1 (fused backward: dx_l[t] = Y_l[t] + P0_l[t + dil_l])
       src = reinterpret_cast<const bf16*>(ws + wl.p0[layer & 1]); ncols = d.R; ld = d.R;
+      break;
+    case 9:  // local-conditioning plane of `layer` [., ., 2 n_dil]: the projections after the forward, dv after that layer's backward
+      if (layer < 0 || layer >= d.L || m->a.n_lc_out == 0) { set_error("wn_debug_read: bad layer / no local conditioning"); return WN_ERR_INVALID; }
+      src = reinterpret_cast<const bf16*>(ws + wl.cond) + (size_t)layer * d.rows * 2 * d.D; ncols = 2 * d.D; ld = 2 * d.D;
+      break;
+    case 10:  // upsampled local conditioning [., ., 128] (channels >= n_lc_out are zero)
+      if (m->a.n_lc_out == 0) { set_error("wn_debug_read: no local conditioning"); return WN_ERR_INVALID; }
+      src = reinterpret_cast<const bf16*>(ws + wl.lc_x[m->a.n_lc_layers]); ncols = 128; ld = 128;
       break;
     default: set_error("wn_debug_read: unknown tap %d", what); return WN_ERR_INVALID;
   }

@@ -642,6 +642,10 @@ def layer_single(a: Arch, p: Dict[str, torch.Tensor], li: int, x_full: torch.Ten
     dz = dz_skip + dx_next @ W("RESIDUAL_" + sfx).T
     dvs = dz * sg * (1 - th * th)
     dvg = dz * th * sg * (1 - sg)
+    out["dv"] = torch.cat([dvs, dvg], dim=2)  # gradient wrt the pre-activations == wrt the conditioning terms added to them
+    if lc_up is not None:
+        out["LC_SIGNAL_" + sfx] = flat(lc_up.to(dt)).T @ flat(dvs)
+        out["LC_GATE_" + sfx] = flat(lc_up.to(dt)).T @ flat(dvg)
     out["RESIDUAL_" + sfx] = flat(z).T @ flat(dx_next)
     if a.use_bias:
         out["RESIDUAL_BIAS_" + sfx] = flat(dx_next).sum(0)

@@ -68,10 +68,10 @@ def test_local_conditioning_forward_and_gradients(lib, arch, B, T):
         bad = {k: v for k, v in errs.items() if v > 6e-2}
         assert not bad, bad
     else:
-        # the LC tensors of the LAST block see few layers above them: tight even on the 50-layer stack
-        tail = {k: v for k, v in lc.items() if k.endswith("_4_8") or k.endswith("_4_9")}
-        assert tail and max(tail.values()) <= 6e-2, tail
-        assert float(np.median(list(errs.values()))) <= 0.15
+        # 50 layers at 1 000 - 2 000 positions: the bf16 gradient floor (~1/sqrt(positions), tests/test_gpu_full.py) is
+        # 15-20 % for every tensor, LC or not.  Here: sanity only; the gradients of this stack are checked at 4 x 8192 in
+        # test_gpu_full.py (8 %) and layer by layer in isolation below (1e-2)
+        assert float(np.median(list(errs.values()))) <= 0.25 and max(errs.values()) <= 0.5
 
 
 def test_every_layer_in_isolation_with_local_conditioning(lib):
@@ -92,17 +92,77 @@ def test_every_layer_in_isolation_with_local_conditioning(lib):
     it = torch.as_tensor(ids).long()
     lc_up = O.lc_upsample(a, pt, torch.as_tensor(mel, dtype=torch.float64), emulate_bf16=True)
     rd = lambda what, l: eng.debug_read(what, l).double().cpu()
-    worst = 0.0
-    for l in range(a.n_layers):
-        x = rd(0, l)
-        full = torch.cat([torch.tensor(p[eng.reg.saves[l].name], dtype=torch.float64), x], dim=1)
-        o = O.layer_single(a, pt, l, full, it, lc_up=lc_up)
+    # the kernel's own upsampled conditioning == the oracle's chain (bf16 rounding points), to 1-ulp flips
+    got_up = rd(10, 0)
+    assert float(got_up[:, :, a.n_lc_out:].abs().max()) == 0.0
+    assert util.rel_err(got_up[:, :, :a.n_lc_out].numpy(), lc_up.numpy()) <= 4e-3
+    lc_k = got_up[:, :, :a.n_lc_out]
+    worst = dict(z=0.0, cond=0.0, dcond=0.0, lc_w=0.0)
+    L = a.n_layers
+    x = [rd(0, l) for l in range(L)]
+    full = [torch.cat([torch.tensor(p[eng.reg.saves[l].name], dtype=torch.float64), x[l]], dim=1) for l in range(L)]
+    for l in range(L):
+        sfx = "%d_%d" % a.layer_ids()[l]
+        o = O.layer_single(a, pt, l, full[l], it, lc_up=lc_k)
         e = util.rel_err(rd(1, l).numpy(), o["z"].numpy())
-        worst = max(worst, e)
+        worst["z"] = max(worst["z"], e)
         assert e <= 1e-2, (l, e)
-        if l + 1 < a.n_layers:
-            assert util.rel_err(rd(0, l + 1).numpy(), o["x_next"].numpy()) <= 1e-2, l
-    util.record("lc_layer_isolation_arch5", dict(z_worst=worst))
+        if l + 1 < L:
+            assert util.rel_err(x[l + 1].numpy(), o["x_next"].numpy()) <= 1e-2, l
+        # the conditioning plane itself: lc_up . [LC_SIGNAL | LC_GATE] (bf16 weights)
+        wl = torch.cat([O.bf16_round(pt["LC_SIGNAL_" + sfx]), O.bf16_round(pt["LC_GATE_" + sfx])], dim=1)
+        e = util.rel_err(rd(9, l).numpy(), (lc_k @ wl).numpy())
+        worst["cond"] = max(worst["cond"], e)
+        assert e <= 6e-3, (l, e)
+    # backward, phase by phase: the plane of layer l then holds dv_l; LC_SIGNAL / LC_GATE come last (phase L + 1)
+    eng.backward_phases(0, 1)
+    dz_skip = [rd(6, l) for l in range(L)]
+    dx_next = torch.zeros(B, T, arch["n_res"], dtype=torch.float64)
+    dconds = [None] * L
+    for l in reversed(range(L)):
+        eng.backward_phases(L - l, L - l + 1)
+        o = O.layer_single(a, pt, l, full[l], it, dz_skip[l], dx_next, lc_up=lc_k)
+        dconds[l] = rd(9, l)
+        e = util.rel_err(dconds[l].numpy(), o["dv"].numpy())
+        worst["dcond"] = max(worst["dcond"], e)
+        assert e <= 1e-2, (l, e)
+        Y, P0 = rd(7, l), rd(8, l)
+        dx = Y.clone()
+        d = a.dilations()[l]
+        if T > d:
+            dx[:, :T - d] += P0[:, d:]
+        dx_next = dx.float().to(torch.bfloat16).double() if l > 0 else dx
+    eng.backward_phases(L + 1, L + 2)
+    torch.cuda.synchronize()
+    flat = lambda t: t.reshape(-1, t.shape[-1])
+    for l in range(L):
+        sfx = "%d_%d" % a.layer_ids()[l]
+        for nm, sl in (("LC_SIGNAL_", slice(0, 32)), ("LC_GATE_", slice(32, 64))):
+            ref = flat(lc_k).T @ flat(dconds[l][:, :, sl])   # from the kernel's OWN planes: isolates the split-K contraction
+            e = util.rel_err(eng.view(nm + sfx, eng.grads).double().cpu().numpy(), ref.numpy())
+            worst["lc_w"] = max(worst["lc_w"], e)
+            assert e <= 2e-3, (nm + sfx, e)
+    # d lc_up = sum_l dcond_l . [LC_SIGNAL_l | LC_GATE_l]^T, then the chain in reverse: LC_UPSAMPLE_i from the kernel's planes
+    dup = torch.zeros(B, T, a.n_lc_out, dtype=torch.float64)
+    for l in range(L):
+        sfx = "%d_%d" % a.layer_ids()[l]
+        wl = torch.cat([O.bf16_round(pt["LC_SIGNAL_" + sfx]), O.bf16_round(pt["LC_GATE_" + sfx])], dim=1)
+        dup += dconds[l] @ wl.T
+    lc_in = []
+    O.lc_upsample(a, pt, torch.as_tensor(mel, dtype=torch.float64), emulate_bf16=True, keep=lc_in)
+    dcur = O.bf16_round(dup)
+    for i in reversed(range(len(a.lc_upsample))):
+        s_ = int(a.lc_upsample[i])
+        filt = O.bf16_round(pt["LC_UPSAMPLE_%d" % i])
+        xin = lc_in[i]
+        dv_ = dcur.reshape(xin.shape[0], xin.shape[1], s_, filt.shape[1])
+        ref = torch.einsum("btko,btc->koc", dv_, xin)
+        e = util.rel_err(eng.view("LC_UPSAMPLE_%d" % i, eng.grads).double().cpu().numpy(), ref.numpy())
+        worst["up%d" % i] = e
+        assert e <= 1e-2, (i, e)
+        if i > 0:
+            dcur = O.bf16_round(torch.einsum("btko,koc->btc", dv_, filt))
+    util.record("lc_layer_isolation_arch5", worst)
 
 
 def test_arch5_trains_from_the_reference_files_layout(lib, tmp_path):
