@@ -40,7 +40,7 @@ def test_full_stage_length_vs_oracle(lib, arch, B, T):
     a = util.oracle_arch(arch)
     p = util.scaled_params(a, B, 21)
     wav, ids = util.synth_batch(B, T, max(arch["n_gc_category"], 3), 22)
-    mel = util.synth_mel(B, T, a, 23)   # None unless the architecture has local conditioning (reference par/arch5.json)
+    mel = util.synth_mel(B, T, a, 23, wav)   # None unless the architecture has local conditioning (reference par/arch5.json)
     eng = _engine(arch, B)
     eng.load_state(p)
     logits = eng.forward(torch.as_tensor(wav).cuda(), torch.as_tensor(ids).cuda(), want_logits=True,

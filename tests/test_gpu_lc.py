@@ -29,7 +29,7 @@ def test_local_conditioning_forward_and_gradients(lib, arch, B, T):
     a = util.oracle_arch(arch)
     p = util.scaled_params(a, B, 61)
     wav, ids = util.synth_batch(B, T, max(arch["n_gc_category"], 3), 62)
-    mel = util.synth_mel(B, T, a, 63)
+    mel = util.synth_mel(B, T, a, 63, wav)
     eng = _engine(arch, B)
     eng.load_state(p)
     dm = torch.as_tensor(mel).cuda()
@@ -82,7 +82,7 @@ def test_every_layer_in_isolation_with_local_conditioning(lib):
     a = util.oracle_arch(arch)
     p = util.scaled_params(a, B, 71)
     wav, ids = util.synth_batch(B, T, arch["n_gc_category"], 72)
-    mel = util.synth_mel(B, T, a, 73)
+    mel = util.synth_mel(B, T, a, 73, wav)
     eng = _engine(arch, B)
     eng.load_state(p)
     eng.forward(torch.as_tensor(wav).cuda(), torch.as_tensor(ids).cuda(), mel=torch.as_tensor(mel).cuda())

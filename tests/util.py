@@ -35,12 +35,23 @@ def oracle_arch(d):
                   lc_upsample=tuple(d.get("lc_upsample", ())))
 
 
-def synth_mel(B, T, a, seed):
-    """mel frames [B, T / hop, n_lc_in] for an architecture with local conditioning (None otherwise)"""
+def synth_mel(B, T, a, seed, wav=None):
+    """mel frames [B, T / hop, n_lc_in] for an architecture with local conditioning (None otherwise).  With `wav`
+    (mu-law codes [B, T]) the frames are a cosine-transform spectrum of the very samples they condition, plus a little
+    noise -- like the real data, where mel.npy is computed from wav.npy.  That matters for gradient tests: with mel
+    independent of the audio the LC gradients have no coherent part, they are a random sum whose relative rounding error
+    equals the per-element error of dv and does not fall with the number of positions (measured with the CPU oracle,
+    8 192 positions: 6.7 % with random mel, 2.7 % with correlated mel, other tensors 2.1-2.4 % either way)."""
     if not a.has_lc():
         return None
     rng = np.random.default_rng(seed)
-    return rng.normal(0, 1.0, (B, T // a.lc_hop(), a.n_lc_in)).astype(np.float32)
+    hop, n = a.lc_hop(), a.n_lc_in
+    if wav is None:
+        return rng.normal(0, 1.0, (B, T // hop, n)).astype(np.float32)
+    x = O.mu_decode_np(np.asarray(wav, np.int64).clip(0, 255)).reshape(B, T // hop, hop).astype(np.float64)
+    t = np.arange(hop) + 0.5
+    basis = np.cos(np.pi * (np.arange(n)[:, None] + 0.5) * t[None, :] / hop)
+    return (4.0 * x @ basis.T / np.sqrt(hop) + 0.1 * rng.normal(size=(B, T // hop, n))).astype(np.float32)
 
 
 def synth_batch(B, T, n_cat, seed, invalid_frac=0.3):
