@@ -120,7 +120,8 @@ def encode_entry(dtype: np.dtype, shape: Iterable[int], offset: int, size: int, 
         out += b"\x20" + put_varint(offset)
     if size:
         out += b"\x28" + put_varint(size)
-    out += b"\x35" + struct.pack("<I", masked_crc)
+    if masked_crc:  # proto3: a zero fixed32 is not emitted either (1 in 2^32 for a masked crc)
+        out += b"\x35" + struct.pack("<I", masked_crc)
     return out
 
 

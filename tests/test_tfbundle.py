@@ -158,3 +158,83 @@ def test_checkpoint_class_writes_tf_bundles_and_reads_legacy_json(lib, tmp_path)
         json.dump(dict(format="lb-wavenet-b200/1", tensors={"PRE": dict(dtype="float32", shape=[3, 4], offset=0,
                   size=len(raw), crc32=zlib.crc32(raw) & 0xFFFFFFFF)}), f)
     assert np.array_equal(ckpt.read_checkpoint(leg)["PRE"], saved["PRE"])
+
+
+# ---- independent statements of the pieces, written by the TensorFlow team ---------------------------------------------
+# TensorFlow itself cannot be installed here (Python 3.12, no network), but TensorBoard -- which is -- ships Google's own
+# copies of the TensorFlow protos (tensor_shape.proto, types.proto, versions.proto) and a pure-Python twin of TF's
+# crc32c / masked crc (tensorboard/compat/tensorflow_stub/pywrap_tensorflow.py).  tensor_bundle.proto is not among
+# them, so BundleHeaderProto / BundleEntryProto are declared below from the published .proto and compiled by Google's
+# protobuf runtime; what is pinned is (a) the wire encoding of this file's hand-rolled protobuf writer, byte for byte,
+# against that runtime, (b) the nested messages and enums against TensorBoard's generated classes, (c) the checksum.
+# What this does NOT prove: that a file written by tf.train.Saver parses (the SSTable container has no second
+# implementation in this image); INTEGRATION.md says so.
+
+def _bundle_proto_classes():
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    from tensorboard.compat.proto import tensor_shape_pb2, types_pb2, versions_pb2  # noqa: F401  (register dependencies)
+    pool = descriptor_pool.Default()
+    name = "lbw_test/tensor_bundle.proto"
+    try:
+        fd = pool.FindFileByName(name)
+    except KeyError:
+        f = descriptor_pb2.FileDescriptorProto(name=name, package="lbw_test", syntax="proto3")
+        f.dependency.extend(["tensorboard/compat/proto/tensor_shape.proto", "tensorboard/compat/proto/types.proto",
+                             "tensorboard/compat/proto/versions.proto"])
+        F = descriptor_pb2.FieldDescriptorProto
+        h = f.message_type.add(name="BundleHeaderProto")
+        e_ = h.enum_type.add(name="Endianness")
+        e_.value.add(name="LITTLE", number=0)
+        e_.value.add(name="BIG", number=1)
+        h.field.add(name="num_shards", number=1, type=F.TYPE_INT32, label=F.LABEL_OPTIONAL)
+        h.field.add(name="endianness", number=2, type=F.TYPE_ENUM, label=F.LABEL_OPTIONAL,
+                    type_name=".lbw_test.BundleHeaderProto.Endianness")
+        h.field.add(name="version", number=3, type=F.TYPE_MESSAGE, label=F.LABEL_OPTIONAL, type_name=".tensorboard.VersionDef")
+        e = f.message_type.add(name="BundleEntryProto")
+        e.field.add(name="dtype", number=1, type=F.TYPE_ENUM, label=F.LABEL_OPTIONAL, type_name=".tensorboard.DataType")
+        e.field.add(name="shape", number=2, type=F.TYPE_MESSAGE, label=F.LABEL_OPTIONAL,
+                    type_name=".tensorboard.TensorShapeProto")
+        e.field.add(name="shard_id", number=3, type=F.TYPE_INT32, label=F.LABEL_OPTIONAL)
+        e.field.add(name="offset", number=4, type=F.TYPE_INT64, label=F.LABEL_OPTIONAL)
+        e.field.add(name="size", number=5, type=F.TYPE_INT64, label=F.LABEL_OPTIONAL)
+        e.field.add(name="crc32c", number=6, type=F.TYPE_FIXED32, label=F.LABEL_OPTIONAL)
+        fd = pool.Add(f)
+    return (message_factory.GetMessageClass(fd.message_types_by_name["BundleHeaderProto"]),
+            message_factory.GetMessageClass(fd.message_types_by_name["BundleEntryProto"]))
+
+
+def test_proto_wire_format_against_googles_runtime_and_tensorboards_tf_protos():
+    pytest.importorskip("tensorboard")
+    from tensorboard.compat.proto import types_pb2
+    Header, Entry = _bundle_proto_classes()
+    # enum values this file hard-codes (types.proto)
+    assert tb.DT_OF[np.dtype(np.float32)] == types_pb2.DT_FLOAT and tb.DT_OF[np.dtype(np.int32)] == types_pb2.DT_INT32
+    assert tb.DT_OF[np.dtype(np.int64)] == types_pb2.DT_INT64
+    h = Header.FromString(tb.encode_header(1))
+    assert h.num_shards == 1 and h.endianness == 0 and h.version.producer == 1
+    ref = Header(num_shards=1)
+    ref.version.producer = 1
+    assert ref.SerializeToString(deterministic=True) == tb.encode_header(1)
+    for dtype, shape, off, size, crc, shard in ((np.float32, (2, 32, 32), 4096, 8192, 0xdeadbeef, 0),
+                                                (np.int32, (), 0, 4, 1, 0), (np.int64, (10,), 123456789012, 80, 0, 0),
+                                                (np.float32, (377, 17), 1 << 33, 25636, 0xffffffff, 0)):
+        mine = tb.encode_entry(np.dtype(dtype), shape, off, size, crc, shard)
+        e = Entry.FromString(mine)
+        assert e.dtype == tb.DT_OF[np.dtype(dtype)] and [d.size for d in e.shape.dim] == list(shape)
+        assert (e.offset, e.size, e.crc32c, e.shard_id) == (off, size, crc, shard)
+        ref = Entry(dtype=tb.DT_OF[np.dtype(dtype)], offset=off, size=size, crc32c=crc, shard_id=shard)
+        ref.shape.SetInParent()   # TF calls mutable_shape(): the (possibly empty) message is always present
+        for n in shape:
+            ref.shape.dim.add(size=n)
+        assert ref.SerializeToString(deterministic=True) == mine, (dtype, shape)
+        assert tb.decode_entry(ref.SerializeToString())["shape"] == list(shape)
+
+
+def test_crc32c_and_mask_against_tensorboards_twin_of_tfs_checksum():
+    pw = pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 8, 9, 63, 64, 1000, 4097):
+        buf = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert tb.crc32c(buf) == pw.crc32c(buf), n
+        assert tb.crc_mask(tb.crc32c(buf)) == pw.masked_crc32c(buf), n
+        assert tb.crc_unmask(pw.masked_crc32c(buf)) == pw.crc32c(buf)
