@@ -83,15 +83,29 @@ def test_full_stage_length_vs_oracle(lib, arch, B, T):
                max_vs_fp64=vs_ex[worst_ex], worst_vs_fp64=worst_ex, median_vs_fp64=float(np.median(list(vs_ex.values()))),
                n_tensors=len(vs_ex), n_valid=L.n_valid)
     util.record("full_T_parity_R%d_S%d_L%d_B%d_T%d" % (arch["n_res"], arch["n_skip"], a.n_layers, B, T), rec)
-    # 30- and 40-layer stacks: every tensor within GRAD_TOL.  The 50-layer arch1 stack has ONE tensor whose bf16 floor
-    # sits above it whatever the amount of data: PRE, whose gradient crosses all 50 layers -- the CPU oracle evaluated
-    # with the same rounding points is itself 8.9 % (8 x 8192) / 7.7 % (16 x 8192) away from fp64 on PRE (median 1.7 %;
-    # DESIGN.md section 4).  There: at most 3 of the 505 tensors above GRAD_TOL, none above 0.12, median <= 0.03.
-    cap = 0.12 if a.n_layers >= 50 else GRAD_TOL
-    for which, errs in (("vs emulated oracle", vs_em), ("vs fp64 oracle", vs_ex)):
-        over = {k: v for k, v in errs.items() if v > GRAD_TOL}
-        assert len(over) <= (3 if a.n_layers >= 50 else 0) and all(v <= cap for v in over.values()), (which, over)
-        assert float(np.median(list(errs.values()))) <= 0.03, which
+    # 30- and 40-layer stacks: every tensor within GRAD_TOL.  The 50-layer stacks (arch1, arch5) have tensors whose bf16
+    # FLOOR sits above it whatever the amount of data -- the CPU oracle evaluated with the same rounding points is itself
+    # that far from fp64: PRE, whose gradient crosses all 50 layers (8.9 % at 8 x 8192, 7.7 % at
+    # 16 x 8192), and at random initialisation every local-conditioning tensor (15.6 % median: the mel frames explain
+    # nothing yet, the LC gradient is an incoherent sum, so its relative error IS the per-element error of dv and does not
+    # average out over positions).  For a tensor above GRAD_TOL the bound is therefore the floor itself: the kernel may be
+    # no further from fp64 than 1.3 x what the CPU evaluation of the same numerics contract is (+ 1 %), and no further from
+    # that evaluation than two independent realisations of the same rounding noise are (1.5 x).  The LC arithmetic itself
+    # is checked layer by layer at 1e-2 in tests/test_gpu_lc.py.
+    floor = {k: util.rel_err(gem[k].numpy(), grads[k] * L.n_valid) for k in vs_ex}
+    deep50 = a.n_layers >= 50
+    bad = {k: (v, floor[k]) for k, v in vs_ex.items()
+           if v > GRAD_TOL and not (deep50 and v <= 1.3 * floor[k] + 0.01)}
+    assert not bad, ("vs fp64 oracle (error, floor of the bf16 contract)", bad)
+    bad = {k: (v, floor[k]) for k, v in vs_em.items()
+           if v > GRAD_TOL and not (deep50 and v <= 1.5 * floor[k] + 0.01)}
+    assert not bad, ("vs emulated oracle (error, floor of the bf16 contract)", bad)
+    non_lc = [v for k, v in vs_ex.items() if not k.startswith("LC_")]
+    assert float(np.median(non_lc)) <= 0.03
+    rec["n_above_tol"] = sum(v > GRAD_TOL for v in vs_ex.values())
+    util.record("full_T_floor_R%d_S%d_L%d_B%d_T%d" % (arch["n_res"], arch["n_skip"], a.n_layers, B, T),
+                dict(n_above_tol=rec["n_above_tol"], floor_median=float(np.median(list(floor.values()))),
+                     floor_max=max(floor.values()), floor_worst=max(floor, key=floor.get)))
 
 
 @pytest.mark.parametrize("arch,B,T", [(util.CLASSIC, 2, 640), (util.C1, 2, 384), (util.WIDE_DEEP, 1, 1088),
