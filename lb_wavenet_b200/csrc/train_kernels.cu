@@ -799,14 +799,41 @@ __global__ void __launch_bounds__(1024) k_embed_bwd(const bf16* __restrict__ dx0
   if (R == 32) {
     // audio codes cluster around mid-scale, so many warps hit the same table rows: NCOPY private copies of the
     // table (warp w uses copy w % NCOPY) cut the same-address serialisation of the shared-memory atomics
-    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    // A lane owns 8 channels (16 bytes) of a row: a warp covers 8 rows per load instruction and keeps UNR of them in
+    // flight -- 2 x UNR x 512 bytes per warp.  (One 2-byte element per lane, as before, left ~8 KB in flight per SM and
+    // the kernel bound by DRAM latency: 93 us for 64 MB.)
+    constexpr int UNR = 4;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nw = nt / 32;
+    const int sub = lane >> 2, ch = lane & 3;  // row within the group of 8, 16-byte chunk of the row
     float* mine = tbl + (size_t)(wrp % ncopy) * (Q + 1) * 32;
-    for (int64_t row = r0 + wrp; row < r1; row += nt / 32) {
-      float v = bf2f(dx0[row * 32 + lane]);
-      if (p0 != nullptr && (int)(row % T) + dil0 < T) v += bf2f(p0[(row + dil0) * 32 + lane]);
-      int code = __ldg(wav + row);
-      if (code < 0 || code >= Q) code = Q;
-      atomicAdd(&mine[code * 32 + lane], v);
+    for (int64_t g0 = r0 + (int64_t)wrp * 8 * UNR; g0 < r1; g0 += (int64_t)nw * 8 * UNR) {
+      uint4 a[UNR], b[UNR];
+      int code[UNR];
+      bool ok[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int64_t row = g0 + u * 8 + sub;
+        a[u] = b[u] = make_uint4(0u, 0u, 0u, 0u);
+        code[u] = 0;
+        ok[u] = row < r1;
+        if (ok[u]) {
+          a[u] = __ldg(reinterpret_cast<const uint4*>(dx0 + row * 32) + ch);
+          if (p0 != nullptr && (int)(row % T) + dil0 < T) b[u] = __ldg(reinterpret_cast<const uint4*>(p0 + (row + dil0) * 32) + ch);
+          code[u] = __ldg(wav + row);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (!ok[u]) continue;
+        const int c = (code[u] < 0 || code[u] >= Q) ? Q : code[u];
+        float* dst = mine + c * 32 + ch * 8;
+        const uint32_t wa[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, wb[4] = {b[u].x, b[u].y, b[u].z, b[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          atomicAdd(dst + 2 * j, __uint_as_float(wa[j] << 16) + __uint_as_float(wb[j] << 16));
+          atomicAdd(dst + 2 * j + 1, __uint_as_float(wa[j] & 0xffff0000u) + __uint_as_float(wb[j] & 0xffff0000u));
+        }
+      }
     }
   } else {
     for (int64_t i = r0 * R + threadIdx.x; i < r1 * R; i += nt) {
