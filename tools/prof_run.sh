@@ -13,4 +13,6 @@ ncu --set full --clock-control none --import-source on -k regex:"k_post_fwd_umma
 # layer kernels: 30 forward + 30 backward launches per step; skip two steps, then 4 forward + 4 backward of the middle
 ncu --set full --clock-control none --import-source on -k regex:"k_layer_fwd_p_umma" -s 73 -c 3 -o gpurun_out/${TAG}_lfwd $CMD > gpurun_out/${TAG}_ncu3.log 2>&1; echo "ncu layer fwd exit $?"
 ncu --set full --clock-control none --import-source on -k regex:"k_layer_bwd_fused_umma" -s 73 -c 3 -o gpurun_out/${TAG}_lbwd $CMD > gpurun_out/${TAG}_ncu4.log 2>&1; echo "ncu layer bwd exit $?"
+# generator: the benchmarked kernel (3x10, 256 streams) and the reference's own arch1 shape (S = P = 512 + GC, 10 streams)
+ncu --set full --clock-control none --import-source on -k regex:"k_gen2" -s 1 -c 1 -o gpurun_out/${TAG}_gen python tools/gen_time.py 256 400 > gpurun_out/${TAG}_ncu5.log 2>&1; echo "ncu gen exit $?"
 ls -la gpurun_out/${TAG}_*
