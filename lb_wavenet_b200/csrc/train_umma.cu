@@ -829,8 +829,6 @@ struct GemmUmmaArgs {
   int a_k_split;      // K elements that come from A rows t0 + ...; the rest from rows t0 + a_row_off2 (second conv tap)
   int a_row_off2;
   int out_col0, out_row_off;
-  int out_col1;       // mode 6: first output column of the GATE half of dv (the SIGNAL half starts at out_col0)
-  int x_col0, x_ld;   // mode 6: the dz row is X[row * x_ld + x_col0 ..] (x_ld == 0: dense rows of N / 2 columns)
   const float* bias2; // mode 4: GATE bias (bias = SIGNAL bias); both [D]
   const bf16* X;      // mode 5: the layer input x[t] for the residual add: X[(slot * x_slot_rows + x_row_off + t) * N + c]
   int x_slot_rows, x_row_off;
@@ -1000,7 +998,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                          : a.X + ((size_t)tile2 * UM + r) * a.N) + half * x_span;
       } else {
         ok = t02 + r < a.T;
-        src = a.X + ((size_t)sb2 * a.T + t02 + r) * (a.x_ld > 0 ? a.x_ld : a.N / 2) + a.x_col0 + half * x_span;
+        src = a.X + ((size_t)sb2 * a.T + t02 + r) * (a.N / 2) + half * x_span;
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -1142,7 +1140,7 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           // dv_s = dz sg (1 - th^2), dv_g = dz th sg (1 - sg) -> dv [.. x 2D] (SIGNAL | GATE)
           const int Dn = a.N / 2, Dh = Dn / 2;
           const bool row_ok = t0 + r < a.T;
-          const bf16* dzrow = a.X + ((size_t)sb * a.T + t0 + r) * (a.x_ld > 0 ? a.x_ld : Dn) + a.x_col0;
+          const bf16* dzrow = a.X + ((size_t)sb * a.T + t0 + r) * Dn;
           uint32_t g[32], pg[16];
           for (int c0 = 0; c0 < Dh; c0 += 32) {
             tmem_ld_32x32b_x32(acc + (uint32_t)(half * Dn + c0), v);
@@ -1189,9 +1187,8 @@ k_gemm_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           fence_proxy_async_smem();
           epi_bar_sync256();
           if (elected) {
-            const int nb = Dn / UKB, oc1 = a.out_col1 > 0 ? a.out_col1 : Dn;  // dv = [dv_s | dv_g]: two column ranges
             for (int kb = 0; kb < a.N / UKB; ++kb)
-              tma_store_3d(&map_out, otile + kb * UA_BYTES, kb < nb ? a.out_col0 + kb * UKB : oc1 + (kb - nb) * UKB, t0, sb);
+              tma_store_3d(&map_out, otile + kb * UA_BYTES, kb * UKB, t0, sb);
             tma_store_commit();
           }
           if (a.colsum_out != nullptr) tile_colsum_acc(otile, a.N, et, min(UM, a.T - t0), cs_acc);
@@ -1473,18 +1470,16 @@ int launch_post_bwd_chain_umma(wn_model* m, unsigned char* ws, int T, float* d_g
 // =====================================================================================================
 namespace wn {
 
-// wcP[l][n][k] (K-major B operand, N = 2D rows, K = 2R): row n = h*Db + j: j < Db/2 -> SIGNAL channel h*Db/2 + j,
-// else 0.5 * GATE channel h*Db/2 + (j - Db/2); k < R -> tap 0 (x[t-dil]), else tap 1 (x[t]).  Db = the number of B rows
-// one conv launch contracts with divided by two (its epilogue's two column halves): D when the conv GEMM runs as one
-// N = 2D launch, D / 2 when it runs as two N = D launches (wide_conv_split).  wrT[l][r][d] = RESIDUAL[d][r].
-__global__ void k_prep_wide_weights(const float* __restrict__ p, const LayerDesc* __restrict__ layers, int R, int D, int Db,
+// wcP[l][n][k] (K-major B operand, N = 2D rows, K = 2R): row n = h*D + j: j < D/2 -> SIGNAL channel h*D/2 + j,
+// else 0.5 * GATE channel h*D/2 + (j - D/2); k < R -> tap 0 (x[t-dil]), else tap 1 (x[t]).  wrT[l][r][d] = RESIDUAL[d][r].
+__global__ void k_prep_wide_weights(const float* __restrict__ p, const LayerDesc* __restrict__ layers, int R, int D,
                                     bf16* __restrict__ wcP, bf16* __restrict__ wrT, bf16* __restrict__ wdP) {
   const int l = blockIdx.x;
   const LayerDesc ld = layers[l];
-  const int n_wc = 2 * D * 2 * R, n_wr = R * D, Dh = Db / 2;
+  const int n_wc = 2 * D * 2 * R, n_wr = R * D, Dh = D / 2;
   for (int i = threadIdx.x; i < n_wc; i += blockDim.x) {
     const int n = i / (2 * R), k = i % (2 * R);
-    const int h = n / Db, j = n % Db;
+    const int h = n / D, j = n % D;
     const bool gate = j >= Dh;
     const int ch = h * Dh + (gate ? j - Dh : j);
     const int tap = k >= R, r = k % R;
@@ -1512,20 +1507,9 @@ bool umma_wide_layer_supported(const wn_model* m) {
   return !disabled && a.n_res % 64 == 0 && a.n_dil % 64 == 0 && a.n_res <= 256 && a.n_dil <= 128 && a.n_gc_embed == 0;
 }
 
-// The conv GEMM of a D = 128 layer (K = 2R = 256, N = 2D = 256) keeps its whole 128 KB B operand resident, which leaves
-// room for only three 16 KB A stages -- less than ONE 128 x 256 A tile in flight per SM, so every tile pays a full DRAM
-// latency (ncu r1: tensor pipe 22 % active, DRAM 1.7 TB/s).  Run as two N = D launches instead (SIGNAL | GATE of 64
-// channels each, weight rows permuted accordingly): B is 64 KB, the A ring 8 stages = two tiles in flight; the second
-// launch re-reads the activations from L2.  WN_WIDE_NOSPLIT=1 restores the single launch.
-static bool wide_conv_split(const wn_model* m) {
-  static const bool off = getenv("WN_WIDE_NOSPLIT") != nullptr;
-  return !off && m->a.n_dil == 128;
-}
-
 int launch_prep_wide_umma(wn_model* m, const float* d_params, unsigned char* ws, cudaStream_t st) {
   const WorkspaceLayout& wl = m->wl;
   k_prep_wide_weights<<<m->L, 256, 0, st>>>(d_params, m->d_layers, m->a.n_res, m->a.n_dil,
-                                            wide_conv_split(m) ? m->a.n_dil / 2 : m->a.n_dil,
                                             reinterpret_cast<bf16*>(ws + wl.wcT), reinterpret_cast<bf16*>(ws + wl.wrT),
                                             reinterpret_cast<bf16*>(ws + wl.wdP));
   WN_LAUNCH_CHECK();
@@ -1568,20 +1552,13 @@ int launch_layer_fwd_wide_umma(wn_model* m, const float* d_params, unsigned char
                   (uint32_t)(2 * D)))) return rc;
   ProfScope ps(PROF_LAYER_FWD, st);
   GemmUmmaArgs ga;
-  const int nsplit = wide_conv_split(m) ? 2 : 1, Dn = D / nsplit;  // z channels per launch
-  for (int h = 0; h < nsplit; ++h) {
-    if (nsplit > 1 &&
-        (rc = map2d(&mwc, reinterpret_cast<const bf16*>(ws + wl.wcT) + ((size_t)l * 2 * D + (size_t)h * 2 * Dn) * 2 * R, 2 * R,
-                    2 * Dn, UKB, (uint32_t)(2 * Dn))))
-      return rc;
-    memset(&ga, 0, sizeof(ga));
-    ga.mode = 4; ga.K = 2 * R; ga.N = 2 * Dn;
-    ga.a_k_split = R; ga.a_row_off2 = ld.dil;
-    ga.out_col0 = l * D + h * Dn; ga.out_row_off = 0;
-    ga.bias = ld.sig_b >= 0 ? d_params + ld.sig_b + h * Dn : nullptr;
-    ga.bias2 = ld.gate_b >= 0 ? d_params + ld.gate_b + h * Dn : nullptr;
-    if ((rc = launch_gemm_umma_layer(m, mx, mwc, mz, ga, T, st))) return rc;
-  }
+  memset(&ga, 0, sizeof(ga));
+  ga.mode = 4; ga.K = 2 * R; ga.N = 2 * D;
+  ga.a_k_split = R; ga.a_row_off2 = ld.dil;
+  ga.out_col0 = l * D; ga.out_row_off = 0;
+  ga.bias = ld.sig_b >= 0 ? d_params + ld.sig_b : nullptr;
+  ga.bias2 = ld.gate_b >= 0 ? d_params + ld.gate_b : nullptr;
+  if ((rc = launch_gemm_umma_layer(m, mx, mwc, mz, ga, T, st))) return rc;
   if (last) return WN_OK;  // the last layer's residual output is unused (tmodel.py:313-325)
   const int dil_next = m->layers[l + 1].dil;
   if ((rc = map2d(&mwr, reinterpret_cast<const bf16*>(ws + wl.wrT) + (size_t)l * R * D, D, R, UKB, (uint32_t)R))) return rc;
@@ -1633,27 +1610,18 @@ int launch_layer_bwd_wide_umma(wn_model* m, const float* d_params, unsigned char
     if ((rc = map2d(&mwc, reinterpret_cast<const bf16*>(ws + wl.wcT) + (size_t)l * 2 * D * 2 * R, 2 * R, 2 * D, UKB,
                     (uint32_t)(2 * D)))) return rc;
     if ((rc = map3(&mdv, dv, 2 * D, T, m->n_slots))) return rc;
-    const int nsplit = wide_conv_split(m) ? 2 : 1, Dn = D / nsplit;  // channels per launch: dv columns [h Dn, +Dn) and D + the same
-    for (int h = 0; h < nsplit; ++h) {
-      if (nsplit > 1 &&
-          (rc = map2d(&mwc, reinterpret_cast<const bf16*>(ws + wl.wcT) + ((size_t)l * 2 * D + (size_t)h * 2 * Dn) * 2 * R,
-                      2 * R, 2 * Dn, UKB, (uint32_t)(2 * Dn))))
-        return rc;
-      memset(&ga, 0, sizeof(ga));
-      ga.mode = 6; ga.K = 2 * R; ga.N = 2 * Dn;
-      ga.a_k_split = R; ga.a_row_off2 = ld.dil;
-      ga.bias = ld.sig_b >= 0 ? d_params + ld.sig_b + h * Dn : nullptr;
-      ga.bias2 = ld.gate_b >= 0 ? d_params + ld.gate_b + h * Dn : nullptr;
-      ga.X = dz_plane;
-      ga.x_col0 = h * Dn; ga.x_ld = D;            // this launch's slice of the dz row
-      ga.out_col0 = h * Dn; ga.out_col1 = D + h * Dn;  // dv = [dv_s (D) | dv_g (D)]
-      if (a.use_bias) {  // SIGNAL_BIAS / GATE_BIAS gradients = column sums of dv, taken from the staged output tiles
-        ga.colsum_out = d_grads + ld.sig_b + h * Dn;
-        ga.colsum_out2 = d_grads + ld.gate_b + h * Dn;
-        ga.colsum_split = Dn;
-      }
-      if ((rc = launch_gemm_umma_layer(m, mx, mwc, mdv, ga, T, st))) return rc;
+    memset(&ga, 0, sizeof(ga));
+    ga.mode = 6; ga.K = 2 * R; ga.N = 2 * D;
+    ga.a_k_split = R; ga.a_row_off2 = ld.dil;
+    ga.bias = ld.sig_b >= 0 ? d_params + ld.sig_b : nullptr;
+    ga.bias2 = ld.gate_b >= 0 ? d_params + ld.gate_b : nullptr;
+    ga.X = dz_plane;
+    if (a.use_bias) {  // SIGNAL_BIAS / GATE_BIAS gradients = column sums of dv, taken from the staged output tiles
+      ga.colsum_out = d_grads + ld.sig_b;
+      ga.colsum_out2 = d_grads + ld.gate_b;
+      ga.colsum_split = D;
     }
+    if ((rc = launch_gemm_umma_layer(m, mx, mwc, mdv, ga, T, st))) return rc;
   }
   {
     ProfScope ps(PROF_LAYER_BWD_B, st);
