@@ -7,12 +7,17 @@ Metric: training output timesteps/s (= B*(T-1) loss positions per optimiser step
 forward + backward + gradient all-reduce + Adam), BASELINE.json configs[1]: classic 3x10 stack,
 R=D=32, S=P=256, 32 slots per GPU, slice_sz 16384, bf16 operands.  N>1 (torchrun): the B=32*N
 slots are sharded 32 per GPU (weak scaling, BASELINE.json configs[2] at N=8).
-Extra keys: `gen` = batched incremental generation audio samples/s on 1 GPU (256 streams).
+Extra keys: `gen` = BASELINE configs[3], batched incremental generation audio samples/s on 1 GPU (256 streams x 160 000
+steps, its own `roofline` and `e2e`); `configs0` = BASELINE configs[0] (reference par/arch1.json + par/par1.json: one
+10 x 512 training step and 16 000 generation steps x 10 streams); `e2e.loader` = H2D bytes per timestep, achieved copy
+GB/s and the dealer's host time; `roofline.hbm` / `roofline.tensor` = BOTH fractions of the dominant kernel.
+`--impl reference` times the CPU port of the reference graph on a bounded sample and says so in `config`.
 
 Timing: W warm-up steps; 3 untimed steps with CUDA events around EVERY kernel launch (`kernel_shares`); then exactly K
 timed steps bracketed by barrier + synchronize, with live CUDA events only around the launches of the dominant kernel
 (`roofline.achieved`; an event pair costs ~1 us of stream time per launch, ~0.15 ms per step if every launch is timed);
-then K end-to-end steps through WaveNetTrain.train_step with pinned host inputs and the loss read back (`e2e`).
+then K end-to-end steps through WaveNetTrain.train_step with pinned host inputs and the loss read back, and K through the
+reference's own loop (MaskedSliceWav -> net.run), which is what `e2e` reports.
 """
 from __future__ import annotations
 
