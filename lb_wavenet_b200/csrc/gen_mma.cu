@@ -560,6 +560,419 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen2(Gen2Args a) {
   if (tid < GS && s0 + tid < a.n_streams) a.codes[s0 + tid] = code_s[tid];
 }
 
+// =====================================================================================================
+// Generation 3: the per-sample chain on ONE warp, no CTA barrier inside the layer loop.
+//
+// k_gen2 spreads a layer over 8 warps and pays for it on the dependency chain: two 256-thread barriers per layer plus
+// the shared-memory round trips of z and x (~700 of ~1400 cycles per layer, in-kernel timeline of round 1).  Here warp 0
+// computes a whole layer for its 16 streams by itself -- 32 mma.sync for the conv (all 64 SIGNAL | GATE columns), the
+// gate, 8 mma.sync for the residual -- and hands x from layer to layer IN REGISTERS: the accumulator fragment of an
+// m16n8k16 (rows g, g+8; columns 2t, 2t+1 of an 8-column n-tile) is exactly half of the A fragment of the next
+// contraction, so z feeds the residual and x' feeds the next conv without touching shared memory.  Measured
+// (tools/hmma_cost.cu): ~680 cycles per layer for that arithmetic on one warp.  Everything else is taken off the chain:
+//   warp 0          the chain; publishes z_l and x_l (two 1.3 KB tiles) through mbarrier-guarded double buffers
+//   warps 1,2,3,5,6,7  skip contraction z_l . SKIP_l (each owns 1/6 of the n-tiles; accumulators in registers), on the
+//                   three schedulers the chain warp does not run on
+//   warp 4          ring buffers: x_l[t] -> HBM, cp.async prefetch of x[t-dil] six layer positions ahead
+//   warp 8          weight producer (cp.async.bulk into the slot ring), as in k_gen2
+// The post-net and the sampler are k_gen2's: all eight compute warps, three barriers per TIMESTEP.
+// =====================================================================================================
+template <int S, int P, bool GC>
+__global__ void __launch_bounds__(g2::THREADS, 1) k_gen3(Gen2Args a) {
+  using namespace g2;
+  constexpr int SLOT = slot_bytes(S, P), NSLOT = n_slots(S, P), HP = hp(S, P);
+  constexpr int NHP = P / 256;
+  constexpr int SKIP_BYTES = chunk_bytes(S), P1_BYTES = chunk_bytes(P), P2_BYTES = chunk_bytes(Q);
+  constexpr int NTS = S / 8, NHW = 6, CNT = (NTS + NHW - 1) / NHW;  // skip n-tiles, helper warps, n-tiles per helper
+  extern __shared__ __align__(1024) unsigned char sm[];
+  unsigned char* wring = sm;                                         // NSLOT x SLOT
+  bf16* x0tab = reinterpret_cast<bf16*>(sm + NSLOT * SLOT);          // [257][32]
+  bf16* xst = x0tab + 257 * 32;                                      // [2][GS][XP]   x_l published for the ring writer
+  bf16* zbuf = xst + 2 * GS * XP;                                    // [2][GS][XP]   z_l published for the skip warps
+  bf16* hbuf = zbuf + 2 * GS * XP;                                   // [2][GS][HP]   h1 / h2
+  float* lgbuf = reinterpret_cast<float*>(hbuf + 2 * GS * HP);       // [GS][LP]
+  bf16* oldbuf = reinterpret_cast<bf16*>(lgbuf + GS * LP);            // [OLD_W][GS][XP] prefetched x[t-dil] tiles
+  float* bias3 = reinterpret_cast<float*>(oldbuf + OLD_W * GS * XP);  // [S + P + Q]
+  __shared__ __align__(8) uint64_t full[NSLOT], empty[NSLOT], z_ready[2], z_free[2], x_ready[2], x_free[2], old_ready[OLD_W];
+  __shared__ int code_s[GS];
+  __shared__ int dil_s[64];
+  __shared__ int64_t roff_s[64];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s0 = blockIdx.x * GS;
+  const int L = a.L;
+
+  if (tid == 0) {
+    for (int i = 0; i < NSLOT; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], NCW);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&z_ready[i], 1);
+      mbar_init(&z_free[i], NHW);
+      mbar_init(&x_ready[i], 1);
+      mbar_init(&x_free[i], 1);
+    }
+    for (int i = 0; i < OLD_W; ++i) mbar_init(&old_ready[i], 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < 257 * 32 / 8; i += THREADS)
+    reinterpret_cast<uint4*>(x0tab)[i] = reinterpret_cast<const uint4*>(a.blob + a.g.x0tab)[i];
+  for (int i = tid; i < S + P + Q; i += THREADS) bias3[i] = reinterpret_cast<const float*>(a.blob + a.g.biases)[i];
+  if (tid < GS) code_s[tid] = (s0 + tid < a.n_streams) ? a.codes[s0 + tid] : -1;
+  if (tid < L) {
+    dil_s[tid] = a.layers[tid].dil;
+    roff_s[tid] = a.ring_off[tid];
+  }
+  __syncthreads();
+
+  const int items_per_step = L + S / 32 + P / 32;
+  if (warp == NCW) {  // ===== weight producer: the same item sequence every timestep (as k_gen2) =====
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t ph = 1;
+      for (int step = 0; step < a.n_steps; ++step) {
+        for (int j = 0; j < items_per_step; ++j) {
+          mbar_wait(&empty[slot], ph);
+          unsigned char* dst = wring + slot * SLOT;
+          if (j < L) {
+            mbar_expect_tx(&full[slot], LAYER_A_BYTES + SKIP_BYTES);
+            bulk_g2s(dst, a.blob + a.g.layer_a + (size_t)j * LAYER_A_BYTES, LAYER_A_BYTES, &full[slot]);
+            bulk_g2s(dst + LAYER_A_BYTES, a.blob + a.g.skip + (size_t)j * SKIP_BYTES, SKIP_BYTES, &full[slot]);
+          } else if (j < L + S / 32) {
+            mbar_expect_tx(&full[slot], P1_BYTES);
+            bulk_g2s(dst, a.blob + a.g.post1 + (size_t)(j - L) * P1_BYTES, P1_BYTES, &full[slot]);
+          } else {
+            mbar_expect_tx(&full[slot], P2_BYTES);
+            bulk_g2s(dst, a.blob + a.g.post2 + (size_t)(j - L - S / 32) * P2_BYTES, P2_BYTES, &full[slot]);
+          }
+          if (++slot == NSLOT) { slot = 0; ph ^= 1u; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== compute warps =====
+  const int g = lane >> 2, t4 = lane & 3;
+  int w_slot = 0, r_slot = 0;
+  uint32_t w_ph = 0;
+  auto slot_wait = [&]() -> const unsigned char* {
+    mbar_wait(&full[w_slot], w_ph);
+    const unsigned char* p = wring + w_slot * SLOT;
+    if (++w_slot == NSLOT) { w_slot = 0; w_ph ^= 1u; }
+    return p;
+  };
+  auto slot_release = [&]() {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[r_slot]);
+    if (++r_slot == NSLOT) r_slot = 0;
+  };
+  auto publish = [&](uint64_t* bar) {  // this warp's shared-memory writes / reads are done: one arrival
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+  };
+  const bool is_chain = warp == 0, is_io = warp == 4;
+  const int hw = warp < 4 ? warp - 1 : warp - 2;                  // skip helper index 0..5 (warps 1,2,3,5,6,7)
+  const int nt0 = is_chain || is_io ? 0 : (hw * NTS) / NHW;       // this helper's skip n-tiles [nt0, nt1)
+  const int nt1 = is_chain || is_io ? 0 : ((hw + 1) * NTS) / NHW;
+
+  // ---- ring-buffer warp state: x[t-dil] of layer position p = step * L + l is prefetched la positions ahead ----
+  const int la = max(1, min(OLD_LA, L - 1));
+  int pf_l = 0, pf_buf = 0;
+  int64_t pf_t = a.t0, pf_left = (int64_t)a.n_steps * L;
+  auto prefetch_next = [&]() {  // warp 4: 64 chunks of 16 bytes, two per lane
+    if (pf_left > 0) {
+      const int dil = dil_s[pf_l];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int q = lane + 32 * u, s = q >> 2, ch = q & 3;
+        if (s0 + s < a.n_streams)
+          cp_async16(oldbuf + ((size_t)pf_buf * GS + s) * XP + ch * 8,
+                     a.rings + roff_s[pf_l] + ((int64_t)(s0 + s) * dil + (pf_t & (int64_t)(dil - 1))) * R + ch * 8);
+      }
+      if (++pf_l == L) { pf_l = 0; ++pf_t; }
+      pf_buf = (pf_buf + 1) & (OLD_W - 1);
+      --pf_left;
+    }
+    cp_async_commit();
+  };
+  if (is_io) {
+    for (int k = 0; k < la; ++k) prefetch_next();
+    cp_async_wait_pending_dyn(la - 1);  // position 0 has landed
+    publish(&old_ready[0]);
+  }
+
+  int64_t pos = 0;  // layer position since the start of this launch
+  for (int step = 0; step < a.n_steps; ++step) {
+    const int64_t t = a.t0 + step;
+    // the sampler's uniforms depend on (seed, t, stream) only: computed here, off the tail of the step
+    const float ua = sampler_uniform(a.seed, (uint64_t)t, (uint32_t)(s0 + warp * 2));
+    const float ub = sampler_uniform(a.seed, (uint64_t)t, (uint32_t)(s0 + warp * 2 + 1));
+    float skip[CNT][4];
+#pragma unroll
+    for (int i = 0; i < CNT; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) skip[i][j] = 0.f;
+
+    if (is_chain) {
+      // ---- input embedding (imodel.py:66-74) straight into A fragments: rows g, g + 8 of the 16-stream tile ----
+      uint32_t xa[2][4];
+      {
+        const int c0 = code_s[g], c1 = code_s[g + 8];
+        const bf16* r0 = x0tab + ((c0 >= 0 && c0 < 256) ? c0 : 256) * 32;
+        const bf16* r1 = x0tab + ((c1 >= 0 && c1 < 256) ? c1 : 256) * 32;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          xa[ks][0] = *reinterpret_cast<const uint32_t*>(r0 + ks * 16 + 2 * t4);
+          xa[ks][1] = *reinterpret_cast<const uint32_t*>(r1 + ks * 16 + 2 * t4);
+          xa[ks][2] = *reinterpret_cast<const uint32_t*>(r0 + ks * 16 + 8 + 2 * t4);
+          xa[ks][3] = *reinterpret_cast<const uint32_t*>(r1 + ks * 16 + 8 + 2 * t4);
+        }
+      }
+      // global conditioning: per-stream projections of the next layer, prefetched (rows g, g + 8; n-tile j: columns
+      // 8j + 2t, +1 of the signal and of the gate half)
+      float2 ngs[2][4], ngg[2][4];
+      auto gc_load = [&](int l) {
+        if constexpr (GC) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int sidx = min(s0 + g + 8 * k, a.n_streams - 1);
+            const float* q = a.gcproj + ((size_t)sidx * L + l) * (2 * D) + 2 * t4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              ngs[k][j] = __ldg(reinterpret_cast<const float2*>(q + 8 * j));
+              ngg[k][j] = __ldg(reinterpret_cast<const float2*>(q + D + 8 * j));
+            }
+          }
+        }
+      };
+      gc_load(0);
+      for (int l = 0; l < L; ++l, ++pos) {
+        const int pb = (int)(pos & 1);
+        const uint32_t ph_prev = (uint32_t)((pos - 2) >> 1) & 1u;
+        // publish x_l[t] for the ring writer (imodel.py:97)
+        bf16* xs = xst + pb * GS * XP;
+        if (pos >= 2) mbar_wait(&x_free[pb], ph_prev);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          *reinterpret_cast<uint32_t*>(xs + g * XP + ks * 16 + 2 * t4) = xa[ks][0];
+          *reinterpret_cast<uint32_t*>(xs + (g + 8) * XP + ks * 16 + 2 * t4) = xa[ks][1];
+          *reinterpret_cast<uint32_t*>(xs + g * XP + ks * 16 + 8 + 2 * t4) = xa[ks][2];
+          *reinterpret_cast<uint32_t*>(xs + (g + 8) * XP + ks * 16 + 8 + 2 * t4) = xa[ks][3];
+        }
+        publish(&x_ready[pb]);
+        float2 gcs[2][4], gcg[2][4];
+        if constexpr (GC) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { gcs[k][j] = ngs[k][j]; gcg[k][j] = ngg[k][j]; }
+          if (l + 1 < L) gc_load(l + 1);
+        }
+        const unsigned char* wa = slot_wait();
+        const float* bias = reinterpret_cast<const float*>(wa + CONV_BYTES + RES_BYTES);
+        // x[t-dil] of this layer (prefetched tile)
+        const int ob = (int)(pos & (OLD_W - 1));
+        mbar_wait(&old_ready[ob], (uint32_t)(pos / OLD_W) & 1u);
+        uint32_t oa[2][4];
+        lda_frag(oa[0], oldbuf + ob * (GS * XP), XP, 0, lane);
+        lda_frag(oa[1], oldbuf + ob * (GS * XP), XP, 16, lane);
+        // conv (imodel.py:107-108): n-tiles 0..3 = SIGNAL channels 8j.., 4..7 = GATE; K = x[t-dil] (32) | x[t] (32)
+        float cv[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cv[nt][j] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            const uint2 b = ldb_frag(wa, nt, ks, 4, lane);
+            if (ks < 2) mma16816(cv[nt], oa[ks], b.x, b.y);
+            else mma16816(cv[nt], xa[ks - 2], b.x, b.y);
+          }
+        }
+        // gate (imodel.py:121) -> z as A fragments of the residual contraction, and as a tile for the skip warps
+        uint32_t za[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 8 * j + 2 * t4;
+          const float2 bs = *reinterpret_cast<const float2*>(bias + c), bg = *reinterpret_cast<const float2*>(bias + 32 + c);
+          float gs0 = 0.f, gs1 = 0.f, gs2 = 0.f, gs3 = 0.f, gg0 = 0.f, gg1 = 0.f, gg2 = 0.f, gg3 = 0.f;
+          if constexpr (GC) {
+            gs0 = gcs[0][j].x; gs1 = gcs[0][j].y; gs2 = gcs[1][j].x; gs3 = gcs[1][j].y;
+            gg0 = gcg[0][j].x; gg1 = gcg[0][j].y; gg2 = gcg[1][j].x; gg3 = gcg[1][j].y;
+          }
+          const float z0 = tanh_fast(cv[j][0] + bs.x + gs0) * sigmoid_fast(cv[4 + j][0] + bg.x + gg0);
+          const float z1 = tanh_fast(cv[j][1] + bs.y + gs1) * sigmoid_fast(cv[4 + j][1] + bg.y + gg1);
+          const float z2 = tanh_fast(cv[j][2] + bs.x + gs2) * sigmoid_fast(cv[4 + j][2] + bg.x + gg2);
+          const float z3 = tanh_fast(cv[j][3] + bs.y + gs3) * sigmoid_fast(cv[4 + j][3] + bg.y + gg3);
+          za[j >> 1][(j & 1) * 2 + 0] = frag_pack(z0, z1);   // row g
+          za[j >> 1][(j & 1) * 2 + 1] = frag_pack(z2, z3);   // row g + 8
+        }
+        bf16* zs = zbuf + pb * GS * XP;
+        if (pos >= 2) mbar_wait(&z_free[pb], ph_prev);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          *reinterpret_cast<uint32_t*>(zs + g * XP + ks * 16 + 2 * t4) = za[ks][0];
+          *reinterpret_cast<uint32_t*>(zs + (g + 8) * XP + ks * 16 + 2 * t4) = za[ks][1];
+          *reinterpret_cast<uint32_t*>(zs + g * XP + ks * 16 + 8 + 2 * t4) = za[ks][2];
+          *reinterpret_cast<uint32_t*>(zs + (g + 8) * XP + ks * 16 + 8 + 2 * t4) = za[ks][3];
+        }
+        publish(&z_ready[pb]);
+        if (l + 1 < L) {
+          // residual 1x1 + add (imodel.py:131,245): x' = bf16(x + z . RESIDUAL + b), straight back into A fragments
+          float rr[4][4];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rr[nt][j] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              const uint2 b = ldb_frag(wa + CONV_BYTES, nt, ks, 2, lane);
+              mma16816(rr[nt], za[ks], b.x, b.y);
+            }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 br = *reinterpret_cast<const float2*>(bias + 64 + 8 * j + 2 * t4);
+            const uint32_t xlo = xa[j >> 1][(j & 1) * 2], xhi = xa[j >> 1][(j & 1) * 2 + 1];
+            xa[j >> 1][(j & 1) * 2] = frag_pack(__uint_as_float(xlo << 16) + rr[j][0] + br.x,
+                                                __uint_as_float(xlo & 0xffff0000u) + rr[j][1] + br.y);
+            xa[j >> 1][(j & 1) * 2 + 1] = frag_pack(__uint_as_float(xhi << 16) + rr[j][2] + br.x,
+                                                    __uint_as_float(xhi & 0xffff0000u) + rr[j][3] + br.y);
+          }
+        }
+        slot_release();
+      }
+    } else if (is_io) {
+      for (int l = 0; l < L; ++l, ++pos) {
+        const int pb = (int)(pos & 1), dil = dil_s[l];
+        (void)slot_wait();
+        slot_release();
+        // ring <- x_l[t] (imodel.py:97), slot t mod dil
+        mbar_wait(&x_ready[pb], (uint32_t)(pos >> 1) & 1u);
+        const bf16* xs = xst + pb * GS * XP;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int q = lane + 32 * u, s = q >> 2, ch = q & 3;
+          const uint4 v = *reinterpret_cast<const uint4*>(xs + s * XP + ch * 8);
+          if (s0 + s < a.n_streams)
+            *reinterpret_cast<uint4*>(a.rings + roff_s[l] + ((int64_t)(s0 + s) * dil + (t & (int64_t)(dil - 1))) * R + ch * 8) = v;
+        }
+        publish(&x_free[pb]);
+        prefetch_next();
+        cp_async_wait_pending_dyn(la - 1);  // the next position's tile has landed
+        if (pos + 1 < (int64_t)a.n_steps * L) publish(&old_ready[(pos + 1) & (OLD_W - 1)]);
+      }
+    } else {
+      for (int l = 0; l < L; ++l, ++pos) {
+        const int pb = (int)(pos & 1);
+        const unsigned char* wsk = slot_wait() + LAYER_A_BYTES;
+        mbar_wait(&z_ready[pb], (uint32_t)(pos >> 1) & 1u);
+        uint32_t zf[2][4];
+        lda_frag(zf[0], zbuf + pb * GS * XP, XP, 0, lane);
+        lda_frag(zf[1], zbuf + pb * GS * XP, XP, 16, lane);
+        publish(&z_free[pb]);
+#pragma unroll
+        for (int j = 0; j < CNT; ++j) {
+          if (nt0 + j < nt1) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint2 b = ldb_frag(wsk, nt0 + j, ks, 2, lane);
+              mma16816(skip[j], zf[ks], b.x, b.y);  // imodel.py:247 (bias added once, below)
+            }
+          }
+        }
+        slot_release();
+      }
+    }
+    // ---- post-net (imodel.py:140-164): as k_gen2, all eight compute warps ----
+    bf16* h1 = hbuf;
+    bf16* h2 = hbuf + GS * HP;
+    if (!is_chain && !is_io) {
+#pragma unroll
+      for (int j = 0; j < CNT; ++j) {
+        if (nt0 + j < nt1) {
+          const int c = (nt0 + j) * 8 + 2 * t4;
+          *reinterpret_cast<uint32_t*>(h1 + g * HP + c) =
+              frag_pack(fmaxf(skip[j][0] + bias3[c], 0.f), fmaxf(skip[j][1] + bias3[c + 1], 0.f));
+          *reinterpret_cast<uint32_t*>(h1 + (g + 8) * HP + c) =
+              frag_pack(fmaxf(skip[j][2] + bias3[c], 0.f), fmaxf(skip[j][3] + bias3[c + 1], 0.f));
+        }
+      }
+    }
+    cbar();
+    float acc[(NHP > 1 ? NHP : 1) * 4][4];
+    auto dense = [&](const bf16* A, auto kc, auto nh) {
+      constexpr int KC = decltype(kc)::value, NH = decltype(nh)::value;
+#pragma unroll
+      for (int i = 0; i < NH * 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int c8 = 0; c8 < KC; ++c8) {
+        const unsigned char* w = slot_wait();
+        uint32_t af[4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          lda_frag(af, A, HP, c8 * 32 + ks * 16, lane);
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint2 b = ldb_frag(w, h * 32 + warp * 4 + j, ks, 2, lane);
+              mma16816(acc[h * 4 + j], af, b.x, b.y);
+            }
+          }
+        }
+        slot_release();
+      }
+    };
+    dense(h1, std::integral_constant<int, S / 32>{}, std::integral_constant<int, NHP>{});
+#pragma unroll
+    for (int hj = 0; hj < NHP * 4; ++hj) {
+      const int c = ((hj >> 2) * 32 + warp * 4 + (hj & 3)) * 8 + 2 * t4;
+      *reinterpret_cast<uint32_t*>(h2 + g * HP + c) =
+          frag_pack(fmaxf(acc[hj][0] + bias3[S + c], 0.f), fmaxf(acc[hj][1] + bias3[S + c + 1], 0.f));
+      *reinterpret_cast<uint32_t*>(h2 + (g + 8) * HP + c) =
+          frag_pack(fmaxf(acc[hj][2] + bias3[S + c], 0.f), fmaxf(acc[hj][3] + bias3[S + c + 1], 0.f));
+    }
+    cbar();
+    dense(h2, std::integral_constant<int, P / 32>{}, std::integral_constant<int, 1>{});
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = (warp * 4 + j) * 8 + 2 * t4;
+      *reinterpret_cast<float2*>(lgbuf + g * LP + c) = make_float2(acc[j][0] + bias3[S + P + c], acc[j][1] + bias3[S + P + c + 1]);
+      *reinterpret_cast<float2*>(lgbuf + (g + 8) * LP + c) = make_float2(acc[j][2] + bias3[S + P + c], acc[j][3] + bias3[S + P + c + 1]);
+    }
+    cbar();
+    // ---- sampling (imodel.py:167-187) + teacher forcing (imodel.py:260-267): warp w -> streams 2w, 2w+1, in lock step ----
+    {
+      const int sa = warp * 2, sb = warp * 2 + 1;
+      if (a.logits_out != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          if (s0 + sa + k < a.n_streams)
+            for (int q = lane; q < Q; q += 32)
+              a.logits_out[((int64_t)(s0 + sa + k) * a.n_steps + step) * Q + q] = lgbuf[(sa + k) * LP + q];
+      }
+      int ra, rb;
+      warp_sample2(lgbuf + sa * LP, lgbuf + sb * LP, ua, ub, ra, rb);
+      if (lane < 2) {
+        const int s = sa + lane, samp = lane == 0 ? ra : rb;
+        if (s0 + s < a.n_streams) {
+          a.out[(int64_t)(s0 + s) * a.n_steps + step] = samp;
+          code_s[s] = (t < a.n_teacher) ? a.teacher[t] : samp;
+        }
+      }
+    }
+    cbar();
+  }
+  // persist the state a later launch continues from: the pending codes (the rings already hold every x[t-dil])
+  if (tid < GS && s0 + tid < a.n_streams) a.codes[s0 + tid] = code_s[tid];
+}
+
 // ---- host ------------------------------------------------------------------------------------------------
 bool gen2_supported(const wn_model* m) {
   static const bool disabled = getenv("WN_DISABLE_GEN2") != nullptr;
@@ -582,13 +995,16 @@ int gen2_prepare(wn_model* m, const float* d_params, unsigned char* blob, cudaSt
 template <int S, int P, bool GC>
 static int gen2_launch(const Gen2Args& a, int n_streams, cudaStream_t st) {
   using namespace g2;
+  // generation 3 (the chain on one warp) by default; WN_GEN2=1 selects the generation-2 kernel (A/B, tests)
+  static const bool use_gen2 = getenv("WN_GEN2") != nullptr;
   constexpr size_t smem = (size_t)n_slots(S, P) * slot_bytes(S, P) + 257 * 32 * 2 +
-                          (size_t)(2 * GS * XP + GS * XP + 2 * GS * hp(S, P)) * 2 + (size_t)GS * LP * 4 +
+                          (size_t)(4 * GS * XP + 2 * GS * hp(S, P)) * 2 + (size_t)GS * LP * 4 +
                           (size_t)OLD_W * GS * XP * 2 + (size_t)(S + P + Q) * 4 + 1024;
   static_assert(smem <= 226 * 1024, "generator shared memory");
-  WN_CUDA_CHECK(cudaFuncSetAttribute(k_gen2<S, P, GC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = use_gen2 ? k_gen2<S, P, GC> : k_gen3<S, P, GC>;
+  WN_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps(PROF_GEN, st);
-  k_gen2<S, P, GC><<<(n_streams + GS - 1) / GS, THREADS, smem, st>>>(a);
+  kern<<<(n_streams + GS - 1) / GS, THREADS, smem, st>>>(a);
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
