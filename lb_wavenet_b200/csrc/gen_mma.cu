@@ -703,6 +703,15 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen3(Gen2Args a) {
   }
 
   int64_t pos = 0;  // layer position since the start of this launch
+  // developer aid (wn_debug_trace): cycles the chain warp of CTA 0 spends per section of a layer, summed over the launch
+  const bool prof = a.trace != nullptr && blockIdx.x == 0 && warp == 0;
+  long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pt = 0;
+#define G3_MARK(k_)                    \
+  if (prof) {                          \
+    const long long now_ = clock64(); \
+    pacc[k_] += now_ - pt;             \
+    pt = now_;                         \
+  }
   for (int step = 0; step < a.n_steps; ++step) {
     const int64_t t = a.t0 + step;
     // the sampler's uniforms depend on (seed, t, stream) only: computed here, off the tail of the step
@@ -747,6 +756,7 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen3(Gen2Args a) {
         }
       };
       gc_load(0);
+      if (prof) pt = clock64();
       for (int l = 0; l < L; ++l, ++pos) {
         const int pb = (int)(pos & 1);
         const uint32_t ph_prev = (uint32_t)((pos - 2) >> 1) & 1u;
@@ -761,6 +771,7 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen3(Gen2Args a) {
           *reinterpret_cast<uint32_t*>(xs + (g + 8) * XP + ks * 16 + 8 + 2 * t4) = xa[ks][3];
         }
         publish(&x_ready[pb]);
+        G3_MARK(0)
         float2 gcs[2][4], gcg[2][4];
         if constexpr (GC) {
 #pragma unroll
@@ -770,6 +781,7 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen3(Gen2Args a) {
           if (l + 1 < L) gc_load(l + 1);
         }
         const unsigned char* wa = slot_wait();
+        G3_MARK(1)
         const float* bias = reinterpret_cast<const float*>(wa + CONV_BYTES + RES_BYTES);
         // x[t-dil] of this layer (prefetched tile)
         const int ob = (int)(pos & (OLD_W - 1));
@@ -777,6 +789,7 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen3(Gen2Args a) {
         uint32_t oa[2][4];
         lda_frag(oa[0], oldbuf + ob * (GS * XP), XP, 0, lane);
         lda_frag(oa[1], oldbuf + ob * (GS * XP), XP, 16, lane);
+        G3_MARK(2)
         // conv (imodel.py:107-108): n-tiles 0..3 = SIGNAL channels 8j.., 4..7 = GATE; K = x[t-dil] (32) | x[t] (32)
         float cv[8][4];
 #pragma unroll
@@ -792,6 +805,7 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen3(Gen2Args a) {
             else mma16816(cv[nt], xa[ks - 2], b.x, b.y);
           }
         }
+        G3_MARK(3)
         // gate (imodel.py:121) -> z as A fragments of the residual contraction, and as a tile for the skip warps
         uint32_t za[2][4];
 #pragma unroll
@@ -810,6 +824,7 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen3(Gen2Args a) {
           za[j >> 1][(j & 1) * 2 + 0] = frag_pack(z0, z1);   // row g
           za[j >> 1][(j & 1) * 2 + 1] = frag_pack(z2, z3);   // row g + 8
         }
+        G3_MARK(4)
         bf16* zs = zbuf + pb * GS * XP;
         if (pos >= 2) mbar_wait(&z_free[pb], ph_prev);
 #pragma unroll
@@ -820,6 +835,7 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen3(Gen2Args a) {
           *reinterpret_cast<uint32_t*>(zs + (g + 8) * XP + ks * 16 + 8 + 2 * t4) = za[ks][3];
         }
         publish(&z_ready[pb]);
+        G3_MARK(5)
         if (l + 1 < L) {
           // residual 1x1 + add (imodel.py:131,245): x' = bf16(x + z . RESIDUAL + b), straight back into A fragments
           float rr[4][4];
@@ -844,7 +860,9 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen3(Gen2Args a) {
                                                     __uint_as_float(xhi & 0xffff0000u) + rr[j][3] + br.y);
           }
         }
+        G3_MARK(6)
         slot_release();
+        G3_MARK(7)
       }
     } else if (is_io) {
       for (int l = 0; l < L; ++l, ++pos) {
@@ -888,6 +906,7 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen3(Gen2Args a) {
         slot_release();
       }
     }
+    G3_MARK(8)
     // ---- post-net (imodel.py:140-164): as k_gen2, all eight compute warps ----
     bf16* h1 = hbuf;
     bf16* h2 = hbuf + GS * HP;
@@ -968,7 +987,11 @@ __global__ void __launch_bounds__(g2::THREADS, 1) k_gen3(Gen2Args a) {
       }
     }
     cbar();
+    G3_MARK(9)
   }
+#undef G3_MARK
+  if (prof && lane == 0)
+    for (int i = 0; i < 10; ++i) a.trace[i] = pacc[i];
   // persist the state a later launch continues from: the pending codes (the rings already hold every x[t-dil])
   if (tid < GS && s0 + tid < a.n_streams) a.codes[s0 + tid] = code_s[tid];
 }
