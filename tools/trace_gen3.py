@@ -3,6 +3,7 @@
 Sections: 0 publish x (+ wait x_free), 1 wait weight slot, 2 wait x[t-dil] + A fragments, 3 conv (32 mma.sync),
 4 gate, 5 publish z (+ wait z_free), 6 residual + x update, 7 slot release, 8 (rest of the layer loop), 9 post-net + sampler."""
 import os, sys
+os.environ["WN_GEN3"] = "1"  # read once per process by the library
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
