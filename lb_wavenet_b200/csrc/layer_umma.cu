@@ -529,13 +529,15 @@ struct LayerBwdFusedArgs {
   // pre-activations and OVERWRITTEN in place with dv = [dv_s | dv_g] (each thread writes exactly the bytes it read):
   // the gradient wrt the plane, consumed by the LC weight / data gradients of phase L + 1
   bf16* cond;
+  const bf16* dz;  // this layer's plane of the skip-path gradient, [B * T][D] (generation 2: read straight from global memory)
   int seq;  // launch sequence number while tracing (tools/trace_layer.py gaps)
   long long* trace;
 };
 
+// Generation 1 of the fused backward (kept for A/B while generation 2 is measured: WN_BWD_V1=1)
 template <int R, int D, bool GC, bool LC>
 __global__ void __launch_bounds__(896, 1)
-k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz,
+k_layer_bwd_fused_v1_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz,
                        const __grid_constant__ CUtensorMap map_yn, const __grid_constant__ CUtensorMap map_pn,
                        const __grid_constant__ CUtensorMap map_yo, const __grid_constant__ CUtensorMap map_po,
                        const __grid_constant__ CUtensorMap map_wc, const __grid_constant__ CUtensorMap map_wrn,
@@ -1078,6 +1080,554 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
   if (warp == 1) tmem_dealloc(tm, 512);
 }
 
+// =====================================================================================================
+// k_layer_bwd_fused_umma, generation 2 (see the file header).  One CTA per SM, 28 warps:
+//   warp 0        TMA producer                                  warps 1, 27   MMA issuers (queue A / queue B)
+//   warps 2..17   gate epilogue E1, two alternating groups      warps 18..25  row warps: E2 (outputs)
+//   warp 26       TMA-store issuer (returns ring stages)
+// Generation 1's in-kernel timeline: a ring stage lived ~12 000 cycles and there were four of them, so a tile left the
+// CTA every ~3100 cycles; the chain  loads landed -> E0 merge (1200) -> wait (1100) -> queue A -> E1 -> queue B -> E2 ->
+// store  was the bound, not HBM (3.0 of 6.5 TB/s), the tensor pipe (28 %) or issue slots (50 %).  Hence:
+//   * the ring stage is X0 | X1 | YN | PN only (32 KB, 5 deep).  dz never goes through shared memory: every E1 thread
+//     fetches its own 2 x 16 bytes of the dz plane with plain global loads issued before it waits for the tile's MMAs;
+//   * there is no E0 phase: dx_{l+1} = YN + PN is never materialised.  By linearity acc_d = YN . Wr^T + PN . Wr^T (two
+//     more N = 32 MMAs) and the MN-major A operand of the weight-gradient MMA is the stage itself, [X0 | X1 | YN | PN]^T:
+//     rows 64..95 and 96..127 of acc_w are the two halves of RESIDUAL's (transposed) gradient, added in the flush;
+//   * with the constant-one panel gone, the SIGNAL / GATE bias gradients (column sums of dv) are summed by E1 itself: a
+//     shuffle transpose-reduce per 8 values (9 shuffles), one accumulator register per (pass, quad);
+//   * the outputs overwrite YN (Y_l) and PN (P0_l) once every MMA reading the stage has completed.
+// Work buffer (24 KB, 2 deep): DVs | DVg | Z as before.  18 + 2 instructions per tile:
+//   A: acc_v (N=64) = X0.W0 + X1.W1 [4] ; acc_d (N=32) = YN . RESIDUAL^T + PN . RESIDUAL^T [4]
+//   B: acc_p (N=64) = [DVs|DVg] . [W0^T|W1^T] [4] ; acc_w (N=96) += [X0|X1|YN|PN]^T . [DVs|DVg|Z] [8]
+// TMEM: per tile parity ab: acc_v [ab*160, +64), acc_d [+64, +32), acc_p [+96, +64); persistent acc_w [320, +96).
+// =====================================================================================================
+// 16-byte read-only global load that the compiler may not move (asm volatile): issued where it is written
+__device__ __forceinline__ uint4 ldg_nc_v4_pinned(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// 8 values x 32 lanes -> every lane L returns the warp total of value (L >> 2) & 7 (9 shuffles instead of 8 warp sums)
+__device__ __forceinline__ float warp_transpose_sum8(float (&w)[8], int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool hi = (lane & 16) != 0;
+    const float send = hi ? w[i] : w[i + 4], keep = hi ? w[i + 4] : w[i];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool hi = (lane & 8) != 0;
+    const float send = hi ? w[i] : w[i + 2], keep = hi ? w[i + 2] : w[i];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const bool hi = (lane & 4) != 0;
+    const float send = hi ? w[0] : w[1], keep = hi ? w[1] : w[0];
+    w[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  w[0] += __shfl_xor_sync(0xffffffffu, w[0], 2);
+  w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
+  return w[0];
+}
+
+template <int R, int D, bool GC, bool LC>
+__global__ void __launch_bounds__(896, 1)
+k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz,
+                       const __grid_constant__ CUtensorMap map_yn, const __grid_constant__ CUtensorMap map_pn,
+                       const __grid_constant__ CUtensorMap map_yo, const __grid_constant__ CUtensorMap map_po,
+                       const __grid_constant__ CUtensorMap map_wc, const __grid_constant__ CUtensorMap map_wrn,
+                       LayerBwdFusedArgs a) {
+  static_assert(R == 32 && D == 32, "tile bookkeeping below assumes 64-byte activation rows");
+  constexpr int XB = 64;
+  constexpr int PANEL = 128 * XB;                 // 8 KB: one [128 x 32] bf16 tile
+  constexpr int P_X0 = 0, P_X1 = 1, P_YN = 2, P_PN = 3;
+  constexpr int STAGE = 4 * PANEL;                // 32 KB
+  constexpr int NST = 5;
+  constexpr int W_DVS = 0, W_DVG = 1, W_Z = 2;
+  constexpr int WBUF = 3 * PANEL;                 // 24 KB
+  constexpr int NE1 = 512, NE1G = 256, NE2 = 256;
+  constexpr uint32_t ACC_V = 0, ACC_D = 64, ACC_P = 96, ACC_STRIDE = 160, ACC_W = 320, ACC_B = 416;
+  constexpr uint32_t HI = desc_hi(XB);
+  constexpr int STG_WC = 0, STG_WR = 64 * 65, STG_WR2 = STG_WR + 32 * 33;  // end-of-kernel staging (floats)
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* wb = smem + NST * STAGE;         // [2] work buffers
+  unsigned char* wc0 = wb + 2 * WBUF;             // [2D rows][R]   4 KB (GATE half pre-scaled by 0.5)
+  unsigned char* wc1 = wc0 + 2 * D * XB;          //                4 KB, directly behind wc0
+  unsigned char* wrn = wc1 + 2 * D * XB;          // [D rows][R]    2 KB
+  unsigned char* ones = wrn + D * XB;             // 1 KB of bf16 1.0: the B operand (16 timesteps x 16 columns) of queue C
+  float* stg = reinterpret_cast<float*>(smem);    // aliases stage 0 (25 KB of its 32)
+  __shared__ __align__(8) uint64_t w_full, in_full[NST], stage_free[NST], out_ready[NST], v_full[2], acc1_free[2],
+      dv_ready[2], p_full[2], acc2_free[2], g_full;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float bias_s[64];  // SIGNAL_BIAS | 0.5 * GATE_BIAS
+  __shared__ float red_s[32];                 // RESIDUAL_BIAS gradient partials
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  pdl_launch_dependents();
+  if (a.trace != nullptr && tid == 0) {  // kernel entry (before barrier init / TMEM allocation)
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 3] = (long long)gt;
+    atomicMin(reinterpret_cast<unsigned long long*>(a.trace) + 32 * WN_TRACE_PER_WARP + 4096 + 2 * (a.seq & 63), gt);
+  }
+
+  if (tid == 0) {
+    mbar_init(&w_full, 1);
+    mbar_init(&g_full, 2);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&in_full[i], 1);
+      mbar_init(&stage_free[i], 1);
+      mbar_init(&out_ready[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&acc1_free[i], NE1G);
+      mbar_init(&dv_ready[i], 1);
+      mbar_init(&p_full[i], 2);  // queue B + queue C
+      mbar_init(&acc2_free[i], NE2);
+    }
+    fence_mbar_init();
+  }
+  if (tid < 32) red_s[tid] = 0.f;
+  if (tid < 64)
+    bias_s[tid] = tid < 32 ? (a.sig_b >= 0 ? a.params[a.sig_b + tid] : 0.f)
+                           : (a.gate_b >= 0 ? 0.5f * a.params[a.gate_b + tid - 32] : 0.f);
+  fill_ones(ones, 1024, tid, 896);
+  fence_proxy_async_smem();
+
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tm = tmem_base_s;
+  pdl_wait();  // the layer above has finished writing (Y, P0) and reading the buffers this layer overwrites
+  Tracer tr;
+  tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
+  if (a.trace != nullptr && tid == 0) {  // per-CTA wall-clock start / SM id (tools/trace_layer.py)
+    unsigned long long gt;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x] = (long long)gt;
+    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 2] = (long long)smid;
+  }
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(&w_full, (uint32_t)(2 * 2 * D * XB + D * XB));
+      tma_load_2d(wc0, &map_wc, &w_full, 0, (a.l * 2 + 0) * 2 * D);
+      tma_load_2d(wc1, &map_wc, &w_full, 0, (a.l * 2 + 1) * 2 * D);
+      tma_load_2d(wrn, &map_wrn, &w_full, 0, a.l * D);
+      for (int i = 0; i < n_my; ++i) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
+        const int s = i % NST;
+        unsigned char* st = smem + s * STAGE;
+        tr.ev(1, i);
+        mbar_wait(&stage_free[s], ((uint32_t)(i / NST) & 1u) ^ 1u);
+        tr.ev(2, i);
+        mbar_expect_tx(&in_full[s], (uint32_t)((a.has_next ? 4 : 2) * PANEL));
+        tma_prefetch_l2_3d(&map_dz, 0, t0, a.z_plane0 + b);  // E1 reads this tile's dz rows from the L2 a few thousand cycles from now
+        tma_load_3d(st + P_X0 * PANEL, &map_x, &in_full[s], 0, t0, b);
+        tma_load_3d(st + P_X1 * PANEL, &map_x, &in_full[s], 0, t0 + a.dil, b);
+        if (a.has_next) {
+          tma_load_3d(st + P_YN * PANEL, &map_yn, &in_full[s], 0, t0, b);
+          tma_load_3d(st + P_PN * PANEL, &map_pn, &in_full[s], 0, t0 + a.dil_next, b);  // rows >= T: zero fill
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 27) {
+    // ===== MMA issuers: warp 1 serves queue A, warp 27 queue B.  One thread spends ~100 cycles per tcgen05.mma it issues
+    // (descriptor arithmetic, the instruction itself, polling) against ~50 cycles of tensor-pipe time.  tcgen05.commit
+    // tracks the issuing thread's own MMAs, and the two queues write disjoint accumulators, so they only meet through the
+    // mbarriers. =====
+    if (lane == 0) {
+      mbar_wait(&w_full, 0);
+      const uint32_t idv = make_idesc_bf16(128, 2 * D), idd = make_idesc_bf16(128, D);
+      const uint32_t idp = make_idesc_bf16(128, 2 * R, false, true);  // A = dv (K-major), B = [W0|W1] (MN-major)
+      const uint32_t idw = make_idesc_bf16(128, 2 * D + R, true, true);
+      // K-major operands: K step of 16 elements = 32 bytes = +2 in the descriptor; MN-major: 16 rows of 64 bytes = +64
+      const uint32_t ring_k = desc_lo_k(smem_u32(smem)), ring_mn = desc_lo(smem_u32(smem), PANEL);
+      const uint32_t wb_k = desc_lo_k(smem_u32(wb)), wb_mn = desc_lo(smem_u32(wb), PANEL);
+      const uint32_t wc0_k = desc_lo_k(smem_u32(wc0)), wc1_k = desc_lo_k(smem_u32(wc1));
+      const uint32_t wc_mn = desc_lo(smem_u32(wc0), 2 * D * XB);  // chunk 0 = wc0 (-> P0), chunk 1 = wc1 (-> Y)
+      const uint32_t wrn_k = desc_lo_k(smem_u32(wrn));
+      // queue C: A = the work buffer re-described MN-major with M = 128 (rows 0..63 = dv channels; 64..95 = z and 96..127
+      // = whatever follows the buffer: never read back), B = 16 rows of ones, the same 1 KB for every K step
+      const uint32_t idb = make_idesc_bf16(128, 16, true, true), ones_mn = desc_lo(smem_u32(ones), PANEL);
+      auto issue_a = [&](int i) {  // recomputed pre-activations; residual part of dz
+        const int s = i % NST, ab = i & 1;
+        const uint32_t x0 = ring_k + (uint32_t)s * (STAGE >> 4), x1 = x0 + (PANEL >> 4);
+        const uint32_t yn = x0 + P_YN * (PANEL >> 4), pn = x0 + P_PN * (PANEL >> 4);
+        const uint32_t av = tm + ab * ACC_STRIDE + ACC_V, ad = tm + ab * ACC_STRIDE + ACC_D;
+        mma_bf16_ss2(av, x0, HI, wc0_k, HI, idv, false);
+        mma_bf16_ss2(av, x0 + 2, HI, wc0_k + 2, HI, idv, true);
+        mma_bf16_ss2(av, x1, HI, wc1_k, HI, idv, true);
+        mma_bf16_ss2(av, x1 + 2, HI, wc1_k + 2, HI, idv, true);
+        if (a.has_next) {  // dz(res) = (Y_{l+1} + P0_{l+1}[t + dil]) . RESIDUAL^T : B = RESIDUAL [D rows][R]
+          mma_bf16_ss2(ad, yn, HI, wrn_k, HI, idd, false);
+          mma_bf16_ss2(ad, yn + 2, HI, wrn_k + 2, HI, idd, true);
+          mma_bf16_ss2(ad, pn, HI, wrn_k, HI, idd, true);
+          mma_bf16_ss2(ad, pn + 2, HI, wrn_k + 2, HI, idd, true);
+        }
+        mma_commit(&v_full[ab]);
+      };
+      auto issue_b = [&](int i) {  // data gradient + weight gradients of tile i
+        const int s = i % NST, ab = i & 1;
+        const uint32_t wk = wb_k + (uint32_t)ab * (WBUF >> 4), wm = wb_mn + (uint32_t)ab * (WBUF >> 4);
+        const uint32_t sm = ring_mn + (uint32_t)s * (STAGE >> 4);
+        const uint32_t ap = tm + ab * ACC_STRIDE + ACC_P;
+        // [P0 | P1] = dv . [W0^T | W1^T]: K = 2D dv channels; B rows 16j.. of the stacked [2D][R] filter copies
+        mma_bf16_ss2(ap, wk + W_DVS * (PANEL >> 4), HI, wc_mn, HI, idp, false);
+        mma_bf16_ss2(ap, wk + W_DVS * (PANEL >> 4) + 2, HI, wc_mn + 64, HI, idp, true);
+        mma_bf16_ss2(ap, wk + W_DVG * (PANEL >> 4), HI, wc_mn + 128, HI, idp, true);
+        mma_bf16_ss2(ap, wk + W_DVG * (PANEL >> 4) + 2, HI, wc_mn + 192, HI, idp, true);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // K = 128 timesteps, 16 per instruction
+          mma_bf16_ss2(tm + ACC_W, sm + k * 64, HI, wm + k * 64, HI, idw, (i | k) != 0);
+        mma_commit(&p_full[ab]);
+      };
+      auto issue_c = [&](int i) {  // column sums of dv over the tile's 128 timesteps: [DVs|DVg|Z|..]^T . 1
+        const int ab = i & 1;
+        const uint32_t wm = wb_mn + (uint32_t)ab * (WBUF >> 4);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          mma_bf16_ss2(tm + ACC_B, wm + k * 64, HI, ones_mn, HI, idb, (i | k) != 0);
+        mma_commit(&p_full[ab]);
+      };
+      uint32_t spins = 0;
+      if (warp == 27) {
+        for (int nb = 0; nb < n_my;) {
+          // tile nb's dv tile is written after its v_full, i.e. after queue A issued tile nb
+          if (mbar_test_wait(&dv_ready[nb & 1], (uint32_t)(nb >> 1) & 1u) &&
+              mbar_test_wait(&acc2_free[nb & 1], ((uint32_t)(nb >> 1) & 1u) ^ 1u)) {
+            tc_fence_after_sync();
+            tr.ev(4, nb);
+            issue_b(nb++);
+            tr.ev(17, nb - 1);
+            spins = 0;
+          } else if (++spins > (1u << 26)) __trap();
+        }
+        mma_commit(&g_full);
+      } else {
+        // queue A first (it feeds E1, the longest phase); queue C (bias-gradient column sums) in its shadow
+        for (int na = 0, nc = 0; nc < n_my;) {
+          bool did = false;
+          if (na < n_my && mbar_test_wait(&in_full[na % NST], (uint32_t)(na / NST) & 1u) &&
+              mbar_test_wait(&acc1_free[na & 1], ((uint32_t)(na >> 1) & 1u) ^ 1u)) {
+            tc_fence_after_sync();
+            tr.ev(3, na);
+            issue_a(na++);
+            tr.ev(16, na - 1);
+            did = true;
+          }
+          if (nc < na && mbar_test_wait(&dv_ready[nc & 1], (uint32_t)(nc >> 1) & 1u)) {
+            tc_fence_after_sync();
+            issue_c(nc++);
+            did = true;
+          }
+          if (did) spins = 0; else if (++spins > (1u << 26)) __trap();
+        }
+        mma_commit(&g_full);
+      }
+    }
+  } else if (warp < 18) {
+    // ===== E1: gate backward, two groups of 8 warps that alternate tiles (group g owns tiles g, g+2, ... and with them
+    // the accumulator / work-buffer parity g), so one group's TMEM round trip, p_full wait, proxy fence and barrier
+    // overlap the other group's arithmetic.  thread <-> (row r, channels [16*half, +16)), two passes of 8 =====
+    const int e = warp - 2;
+    const int g = e >> 3, half = (e >> 2) & 1, q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const int et = e * 32 + lane;  // 0..511
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    const bool elected = ((e & 7) == 0 && lane == 0);
+    const uint32_t sw64 = ((uint32_t)r >> 1) & 3u;
+    const uint32_t o[2] = {(uint32_t)r * 64u + ((((uint32_t)(2 * half)) ^ sw64) << 4),
+                           (uint32_t)r * 64u + ((((uint32_t)(2 * half + 1)) ^ sw64) << 4)};
+    const float4* bs4 = reinterpret_cast<const float4*>(bias_s + 16 * half);
+    const float4* bg4 = reinterpret_cast<const float4*>(bias_s + 32 + 16 * half);
+    for (int i = g; i < n_my; i += 2) {
+      const int ab = g;
+      unsigned char* wbuf = wb + ab * WBUF;
+      const uint32_t tb = tm + ab * ACC_STRIDE + lane_sel;
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const int slot = tile / a.tiles_per_slot, tt = (tile % a.tiles_per_slot) * 128 + r;
+      // this row's 16 dz values (skip-path gradient, plane l) come straight from global memory: the producer prefetched
+      // the tile into the L2 when it issued the stage's loads, and the L2 round trip hides behind the wait for the MMAs.
+      // (Requested a whole tile ahead from DRAM instead, the loads made the arithmetic itself ~1000 cycles slower: a
+      // pending global load shares its scoreboard with the short-latency operations of the gate arithmetic.)
+      uint4 dzr[2];
+      dzr[0] = dzr[1] = make_uint4(0u, 0u, 0u, 0u);
+      if (tt < a.T) {
+        const uint4* row = reinterpret_cast<const uint4*>(a.dz + ((size_t)slot * a.T + tt) * D + 16 * half);
+        dzr[0] = ldg_nc_v4_pinned(row);
+        dzr[1] = ldg_nc_v4_pinned(row + 1);
+      }
+      int gid = 0;  // this row's voice id (global conditioning)
+      if constexpr (GC) gid = tt < a.T ? min(max(__ldg(a.ids + (size_t)slot * a.T + tt), 0), a.C1 - 1) : 0;
+      uint4 lcs[2], lcg[2];
+      uint4* lcrow = nullptr;
+      if constexpr (LC) {
+        lcs[0] = lcs[1] = lcg[0] = lcg[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (tt < a.T) {
+          lcrow = reinterpret_cast<uint4*>(a.cond + ((size_t)slot * a.T + tt) * (2 * D) + 16 * half);
+          lcs[0] = lcrow[0]; lcs[1] = lcrow[1];
+          lcg[0] = lcrow[D / 8]; lcg[1] = lcrow[D / 8 + 1];
+        }
+      }
+      tr.ev(5, i);
+      mbar_wait(&v_full[ab], (uint32_t)(i >> 1) & 1u);
+      tr.ev(6, i);
+      tc_fence_after_sync();
+      if (i >= 2) mbar_wait(&p_full[ab], (uint32_t)((i - 2) >> 1) & 1u);  // the MMAs of tile i-2 have finished reading wb[ab]
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        uint32_t pz[4], pvs[4], pvg[4];
+        const int c0 = 16 * half + 8 * p;
+        uint32_t vs[8], vg[8], vd[8];
+        tmem_ld_32x32b_x8(tb + ACC_V + c0, vs);
+        tmem_ld_32x32b_x8(tb + ACC_V + 32 + c0, vg);
+        if (a.has_next) {
+          tmem_ld_32x32b_x8(tb + ACC_D + c0, vd);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vd[j] = 0u;
+        }
+        const uint32_t dzs[4] = {dzr[p].x, dzr[p].y, dzr[p].z, dzr[p].w};
+        tmem_ld_wait();
+        if (p == 1) {
+          tc_fence_before_sync();
+          mbar_arrive(&acc1_free[ab]);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float4 b_s = bs4[2 * p + q], b_g = bg4[2 * p + q];
+          if constexpr (GC) {  // the accumulator's GATE half holds 0.5 * pre-activation: the table's gate half is halved too
+            const float* gct = a.gc_tbl + (size_t)gid * 2 * D + c0;
+            const float4 c_s = __ldg(reinterpret_cast<const float4*>(gct) + q);
+            const float4 c_g = __ldg(reinterpret_cast<const float4*>(gct + D) + q);
+            b_s.x += c_s.x; b_s.y += c_s.y; b_s.z += c_s.z; b_s.w += c_s.w;
+            b_g.x = fmaf(0.5f, c_g.x, b_g.x); b_g.y = fmaf(0.5f, c_g.y, b_g.y);
+            b_g.z = fmaf(0.5f, c_g.z, b_g.z); b_g.w = fmaf(0.5f, c_g.w, b_g.w);
+          }
+          if constexpr (LC) {
+            const uint32_t ws0 = q == 0 ? lcs[p].x : lcs[p].z, ws1 = q == 0 ? lcs[p].y : lcs[p].w;
+            const uint32_t wg0 = q == 0 ? lcg[p].x : lcg[p].z, wg1 = q == 0 ? lcg[p].y : lcg[p].w;
+            add_bf16x4(b_s, ws0, ws1, 1.f);
+            add_bf16x4(b_g, wg0, wg1, 0.5f);
+          }
+          const float bsv[4] = {b_s.x, b_s.y, b_s.z, b_s.w}, bgv[4] = {b_g.x, b_g.y, b_g.z, b_g.w};
+          float zz[4], ds[4], dg[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int d = 4 * q + k;
+            const float th = tanh_fast(__uint_as_float(vs[d]) + bsv[k]);
+            const float u = tanh_fast(__uint_as_float(vg[d]) + bgv[k]);   // accumulator holds 0.5 * gate pre-activation
+            const float sg = fmaf(0.5f, u, 0.5f);
+            const uint32_t dw = dzs[d >> 1];
+            const float dz = ((d & 1) == 0 ? __uint_as_float(dw << 16) : __uint_as_float(dw & 0xffff0000u)) + __uint_as_float(vd[d]);
+            zz[k] = th * sg;
+            ds[k] = (dz * sg) * fmaf(-th, th, 1.f);
+            dg[k] = (dz * th) * fmaf(-0.5f * u, u, 0.5f);   // = 2 * dz th sg (1 - sg): pairs with the 0.5-scaled GATE filter
+          }
+          pz[2 * q] = pack2(zz[0], zz[1]);  pz[2 * q + 1] = pack2(zz[2], zz[3]);
+          pvs[2 * q] = pack2(ds[0], ds[1]); pvs[2 * q + 1] = pack2(ds[2], ds[3]);
+          pvg[2 * q] = pack2(dg[0], dg[1]); pvg[2 * q + 1] = pack2(dg[2], dg[3]);
+          if constexpr (LC) {  // gradient wrt the conditioning plane: the true dv_g is half of what pairs with the 0.5-scaled filter
+            if (q == 0) { lcg[p].x = pack2(0.5f * dg[0], 0.5f * dg[1]); lcg[p].y = pack2(0.5f * dg[2], 0.5f * dg[3]); }
+            else        { lcg[p].z = pack2(0.5f * dg[0], 0.5f * dg[1]); lcg[p].w = pack2(0.5f * dg[2], 0.5f * dg[3]); }
+          }
+          if constexpr (GC) {
+            // table gradient: dTbl[id][n] += dv[n] (gate half: dv carries 2x).  A warp is 32 consecutive timesteps of
+            // one slot, ids change only at file junctions: reduce over the warp when it is uniform, else per row
+            const int id0 = __shfl_sync(0xffffffffu, gid, 0);
+            const bool uni = __all_sync(0xffffffffu, gid == id0);
+            if (uni) {
+              float w[8] = {ds[0], ds[1], ds[2], ds[3], 0.5f * dg[0], 0.5f * dg[1], 0.5f * dg[2], 0.5f * dg[3]};
+              const float wsum = warp_transpose_sum8(w, lane);
+              const int idx = (lane >> 2) & 7;
+              if ((lane & 3) == 0 && wsum != 0.f)
+                atomicAdd(a.dgc_tbl + (size_t)id0 * 2 * D + (idx < 4 ? 0 : D) + c0 + 4 * q + (idx & 3), wsum);
+            } else {
+              float* drow = a.dgc_tbl + (size_t)gid * 2 * D + c0 + 4 * q;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (ds[k] != 0.f) atomicAdd(drow + k, ds[k]);
+                if (dg[k] != 0.f) atomicAdd(drow + D + k, 0.5f * dg[k]);
+              }
+            }
+          }
+        }
+        *reinterpret_cast<uint4*>(wbuf + W_Z * PANEL + o[p]) = make_uint4(pz[0], pz[1], pz[2], pz[3]);
+        *reinterpret_cast<uint4*>(wbuf + W_DVS * PANEL + o[p]) = make_uint4(pvs[0], pvs[1], pvs[2], pvs[3]);
+        *reinterpret_cast<uint4*>(wbuf + W_DVG * PANEL + o[p]) = make_uint4(pvg[0], pvg[1], pvg[2], pvg[3]);
+        if constexpr (LC) {
+          if (lcrow != nullptr) {
+            lcrow[p] = make_uint4(pvs[0], pvs[1], pvs[2], pvs[3]);
+            lcrow[D / 8 + p] = lcg[p];
+          }
+        }
+      }
+      tr.ev(15, i);
+      fence_proxy_async_smem();
+      tr.ev(7, i);
+      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 4, 256;" ::: "memory");
+      tr.ev(8, i);
+      if (elected) mbar_arrive(&dv_ready[ab]);
+    }
+    // ---- flush: weight gradients TMEM -> staging -> coalesced atomics ----
+    const int cq = 2 * g + half;  // column quarter of the 64 dv columns handled by this warp in the flush
+    const int c0 = 8 * cq;
+    mbar_wait(&g_full, 0);
+    tc_fence_after_sync();
+    if (n_my > 0) mbar_wait(&stage_free[(n_my - 1) % NST], (uint32_t)((n_my - 1) / NST) & 1u);  // last TMA store drained
+    asm volatile("bar.sync 3, 768;" ::: "memory");  // the row warps have published their RESIDUAL_BIAS partials
+    if (n_my > 0) {
+      // acc_w[128 x 96]: rows 0..63, columns 0..63 = conv taps (GATE columns carry 2x); rows 64..95 (YN) and 96..127 (PN),
+      // columns 64..95 = the two halves of dx_{l+1}^T . Z = RESIDUAL's gradient, transposed
+      const float gsc = cq < 2 ? 1.f : 0.5f;
+      if (q4 < 2) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tm + ACC_W + lane_sel + (uint32_t)(16 * cq), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) stg[STG_WC + r * 65 + 16 * cq + j] = gsc * __uint_as_float(v[j]);
+        if (cq == 0) {  // acc_b rows 0..63 (every column alike): column sums of dv = SIGNAL_BIAS | 2 x GATE_BIAS gradients
+          uint32_t bv[8];
+          tmem_ld_32x32b_x8(tm + ACC_B + lane_sel, bv);
+          tmem_ld_wait();
+          const float val = (r < 32 ? 1.f : 0.5f) * __uint_as_float(bv[0]);
+          const int64_t off = r < 32 ? a.sig_b : a.gate_b;
+          if (off >= 0 && val != 0.f) atomicAdd(a.grads + off + (r & 31), val);
+        }
+      } else if (a.has_next) {
+        uint32_t w[8];
+        tmem_ld_32x32b_x8(tm + ACC_W + lane_sel + (uint32_t)(2 * D + c0), w);
+        tmem_ld_wait();
+        float* dst = stg + (q4 == 2 ? STG_WR : STG_WR2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[(c0 + j) * 33 + (r & 31)] = __uint_as_float(w[j]);
+      }
+      asm volatile("bar.sync 5, 512;" ::: "memory");
+      // dWc row m = tap*R + rr, column n: n < D -> SIGNAL[tap][rr][n], else GATE[tap][rr][n-D]
+      for (int idx = et; idx < 64 * 64; idx += NE1) {
+        const int m = idx >> 6, n = idx & 63;
+        const float val = stg[STG_WC + m * 65 + n];
+        const int tap = m >> 5, rr = m & 31;
+        float* dst = a.grads + (n < D ? a.sig : a.gate) + ((size_t)tap * R + rr) * D + (n & 31);
+        if (val != 0.f) atomicAdd(dst, val);
+      }
+      if (a.has_next) {
+        for (int idx = et; idx < 32 * 32; idx += NE1) {
+          const int d = idx >> 5, c = idx & 31;
+          const float val = stg[STG_WR + d * 33 + c] + stg[STG_WR2 + d * 33 + c];
+          if (val != 0.f) atomicAdd(a.grads + a.res + (size_t)d * R + c, val);
+        }
+        if (et < 32 && a.res_b >= 0) {
+          const float val = red_s[et];
+          if (val != 0.f) atomicAdd(a.grads + a.res_b + et, val);
+        }
+      }
+    }
+  } else if (warp < 26) {
+    // ===== row warps: E2 (outputs).  thread <-> (row r, channels [16*rh, +16)), two passes of 8 channels =====
+    const int q4 = warp & 3, rh = (warp - 18) >> 2;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    const bool elected = (warp == 18 && lane == 0);
+    const uint32_t sw64 = ((uint32_t)r >> 1) & 3u;
+    const uint32_t oc[2] = {(uint32_t)r * 64u + ((((uint32_t)(2 * rh)) ^ sw64) << 4),
+                            (uint32_t)r * 64u + ((((uint32_t)(2 * rh + 1)) ^ sw64) << 4)};
+    float rsum[16];  // column sums of dx_{l+1}: RESIDUAL_BIAS gradient
+#pragma unroll
+    for (int c = 0; c < 16; ++c) rsum[c] = 0.f;
+    for (int i = 0; i < n_my; ++i) {
+      const int s = i % NST, ab = i & 1;
+      unsigned char* st = smem + s * STAGE;
+      unsigned char* ynp = st + P_YN * PANEL;  // each thread overwrites exactly the bytes it has just read
+      unsigned char* pnp = st + P_PN * PANEL;
+      const uint32_t tb = tm + ab * ACC_STRIDE + lane_sel;
+      tr.ev(9, i);
+      mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);  // (long complete) the TMA-written YN / PN tiles are visible to this thread
+      mbar_wait(&p_full[ab], (uint32_t)(i >> 1) & 1u);   // every MMA reading this stage has completed
+      tr.ev(10, i);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t p0[8], p1[8];
+        tmem_ld_32x32b_x8(tb + ACC_P + 16 * rh + 8 * c, p0);
+        tmem_ld_32x32b_x8(tb + ACC_P + R + 16 * rh + 8 * c, p1);
+        uint4 y4 = make_uint4(0u, 0u, 0u, 0u), n4 = make_uint4(0u, 0u, 0u, 0u);
+        if (a.has_next) {  // dx_{l+1} = Y_{l+1}[t] + P0_{l+1}[t + dil]: this thread's own 16 bytes of each tile
+          y4 = *reinterpret_cast<const uint4*>(ynp + oc[c]);
+          n4 = *reinterpret_cast<const uint4*>(pnp + oc[c]);
+        }
+        const uint32_t yw[4] = {y4.x, y4.y, y4.z, y4.w}, pw[4] = {n4.x, n4.y, n4.z, n4.w};
+        tmem_ld_wait();
+        if (c == 1) {
+          tc_fence_before_sync();
+          mbar_arrive(&acc2_free[ab]);
+        }
+        uint32_t oy[4], op[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float lo = __uint_as_float(yw[k] << 16) + __uint_as_float(pw[k] << 16);
+          const float hi = __uint_as_float(yw[k] & 0xffff0000u) + __uint_as_float(pw[k] & 0xffff0000u);
+          rsum[8 * c + 2 * k] += lo;
+          rsum[8 * c + 2 * k + 1] += hi;
+          oy[k] = pack2(__uint_as_float(p1[2 * k]) + lo, __uint_as_float(p1[2 * k + 1]) + hi);   // Y_l = P1 + dx_{l+1}
+          op[k] = pack2(__uint_as_float(p0[2 * k]), __uint_as_float(p0[2 * k + 1]));             // P0_l
+        }
+        *reinterpret_cast<uint4*>(ynp + oc[c]) = make_uint4(oy[0], oy[1], oy[2], oy[3]);
+        *reinterpret_cast<uint4*>(pnp + oc[c]) = make_uint4(op[0], op[1], op[2], op[3]);
+      }
+      fence_proxy_async_smem();
+      tr.ev(11, i);
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      tr.ev(12, i);
+      if (elected) mbar_arrive(&out_ready[s]);
+    }
+    if (a.has_next && a.res_b >= 0) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float v = warp_sum(rsum[c]);
+        if (lane == 0) atomicAdd(&red_s[16 * rh + c], v);
+      }
+    }
+    asm volatile("bar.sync 3, 768;" ::: "memory");
+  } else {
+    // ===== TMA-store issuer: the only thread that touches the store path; returns the stage to the ring =====
+    if (lane == 0) {
+      for (int i = 0; i < n_my; ++i) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
+        const int s = i % NST;
+        unsigned char* st = smem + s * STAGE;
+        mbar_wait(&out_ready[s], (uint32_t)(i / NST) & 1u);
+        tma_store_3d(&map_yo, st + P_YN * PANEL, 0, t0, b);
+        tma_store_3d(&map_po, st + P_PN * PANEL, 0, t0, b);
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        tr.ev(13, i);
+        mbar_arrive(&stage_free[s]);
+      }
+      tma_store_wait_all<0>();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (a.trace != nullptr && tid == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 1] = (long long)gt;
+    atomicMax(reinterpret_cast<unsigned long long*>(a.trace) + 32 * WN_TRACE_PER_WARP + 4096 + 2 * (a.seq & 63) + 1, gt);
+  }
+  if (warp == 1) tmem_dealloc(tm, 512);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 static int map3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1,
                  int swizzle) {
@@ -1232,13 +1782,15 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
   ga.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
   static int trace_seq = 0;
   if (ga.trace != nullptr) ga.seq = trace_seq++;
-  // ring 4 x 40 KB | work buffers 2 x 24 KB | wc 2 x 4 KB | RESIDUAL 2 KB
-  const size_t smem = 4 * 5 * 8192 + 2 * 3 * 8192 + 2 * 4096 + 2048 + 1024;
+  // generation 2: ring 5 x 32 KB (generation 1: 4 x 40 KB) | work buffers 2 x 24 KB | wc 2 x 4 KB | RESIDUAL 2 KB
+  // (+ 1 KB of ones)
+  const size_t smem = 4 * 5 * 8192 + 2 * 3 * 8192 + 2 * 4096 + 2048 + 1024 + 1024;
   const int grid = persist_grid(std::max(1, std::min(ga.n_tiles, m->sm_count)));
   const int nx = (l + 1) & 1, cu = l & 1;
   ProfScope ps(PROF_LAYER_BWD_A, st);
   const bool gc = m->a.n_gc_embed > 0, lc = m->a.n_lc_out > 0;
   ga.T = T;
+  ga.dz = reinterpret_cast<const bf16*>(ws + m->wl.dz) + (size_t)l * m->n_slots * T * m->a.n_dil;
   if (gc) {
     const int C1 = m->a.n_gc_category + 1;
     ga.gc_tbl = reinterpret_cast<const float*>(ws + m->wl.gc_tbl) + (size_t)l * C1 * 2 * m->a.n_dil;
@@ -1247,12 +1799,18 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
     ga.C1 = C1;
   }
   if (lc) ga.cond = reinterpret_cast<bf16*>(ws + m->wl.cond) + (size_t)l * m->n_slots * T * 2 * m->a.n_dil;
+  static const bool use_v1 = getenv("WN_BWD_V1") != nullptr;  // A/B against generation 1
 #define WN_BWD(GC_, LC_)                                                                                                  \
-  {                                                                                                                       \
+  if (use_v1) {                                                                                                           \
+    WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_v1_umma<32, 32, GC_, LC_>,                                       \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
+    WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_v1_umma<32, 32, GC_, LC_>, grid, 896, smem, st, mp->x[l], mp->dz,          \
+                             mp->dx[nx], mp->p0[nx], mp->dx[cu], mp->p0[cu], mp->wc, mp->wrn, ga));                       \
+  } else {                                                                                                                \
     WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_umma<32, 32, GC_, LC_>,                                          \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
-    WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_umma<32, 32, GC_, LC_>, grid, 896, smem, st, mp->x[l], mp->dz, mp->dx[nx], \
-                             mp->p0[nx], mp->dx[cu], mp->p0[cu], mp->wc, mp->wrn, ga));                                   \
+    WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_umma<32, 32, GC_, LC_>, grid, 896, smem, st, mp->x[l], mp->dz,             \
+                             mp->dx[nx], mp->p0[nx], mp->dx[cu], mp->p0[cu], mp->wc, mp->wrn, ga));                       \
   }
   if (gc && lc) WN_BWD(true, true)
   else if (gc) WN_BWD(true, false)
