@@ -16,13 +16,14 @@
 // k_layer_bwd_fused_umma: the whole backward of one layer in ONE persistent kernel.  The data gradient is kept
 //   in split form  dx_l[t] = Y_l[t] + P0_l[t + dil_l]  so that no tile ever needs another tile's result:
 //     acc_v = x[t-dil] . W[0] + x[t] . W[1] + bias                    (recomputed pre-activations)
-//     acc_d = (Y_{l+1}[t] + P0_{l+1}[t+dil_{l+1}]) . RESIDUAL^T        (residual part of dz; two MMAs, linearity)
+//     acc_d = Y_{l+1}[t] . RESIDUAL^T + P0_{l+1}[t+dil_{l+1}] . RESIDUAL^T   (residual part of dz; linearity: the merged
+//                                                                      dx_{l+1} is never materialised)
 //     th, sg, z ;  dz = dz_skip + acc_d ;  dv = [dz sg (1-th^2) | dz th sg (1-sg)]        (bf16 tile, smem ONLY)
-//     acc_p = dv . [W[0]^T | W[1]^T]  (+ Y_{l+1} . I + P0_{l+1}[t+dil] . I in the W[1] half)
-//     P0_l = bf16(acc_p[:, :R]) ;  Y_l = bf16(acc_p[:, R:])            -> TMA stores (the only HBM writes)
+//     acc_p = dv . [W[0]^T | W[1]^T]
+//     P0_l = bf16(acc_p[:, :R]) ;  Y_l = bf16(acc_p[:, R:] + Y_{l+1} + P0_{l+1}[t+dil])   -> TMA stores (the only HBM writes)
 //   weight gradients accumulate in tensor memory across ALL tiles of the CTA (the K-major activation tiles are
-//   re-described MN-major, no extra traffic):  acc_wc += [x[t-dil] | x[t] | z | 1]^T . dv ,
-//   acc_wr += [x[t-dil] | x[t] | z | 1]^T . dx_{l+1}; the constant-one panel yields the bias gradients.
+//   re-described MN-major, no extra traffic):  acc_w += [x[t-dil] | x[t] | Y_{l+1} | P0_{l+1}]^T . [dv | z]
+//   (rows 64..95 + rows 96..127 = RESIDUAL's gradient, transposed);  acc_b += [dv | ..]^T . 1  = the bias gradients.
 //   Rows t + dil >= T of P0 are TMA zero fill: the gradient stops at the stage boundary (SAVE is a variable, not
 //   a graph tensor, reference tmodel.py:123-124,165).
 #include <algorithm>
@@ -494,33 +495,11 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
   if (warp == 1) tmem_dealloc(tm, 256);
 }
 
-// =====================================================================================================
-// k_layer_bwd_fused_umma (see the file header).  One CTA per SM, 27 warps:
-//   warp 0        TMA producer (+ L2 prefetch)                  warp 1        MMA issuer
-//   warps 2..17   gate epilogue E1, two alternating groups      warps 18..25  row warps: E0 (dx = Y + P0 merge) and E2 (outputs)
-//   warp 26       TMA-store issuer (returns ring stages)
-// Ring stage (40 KB, 4 deep): X0 | X1 | YN->DX->Y_l | PN->ONES->P0_l | DZ.  E0 merges YN + PN into DX in place as soon as
-// the stage lands and refills PN with 1.0; panels 0..3 are then the MN-major A operand (M = 128) of the weight-gradient
-// MMA, whose rows 96..127 (the ones) deliver the SIGNAL / GATE bias gradients for free; the outputs overwrite DX / ONES
-// once every MMA reading them has completed.  Work buffer (24 KB, 2 deep): DVs | DVg | Z -- three [128 x 32] SW64 panels
-// written by E1: K-major A operands of dv . W^T and, re-described MN-major with N = 96, the B operand of the
-// weight-gradient MMA (so RESIDUAL's gradient appears transposed: DX^T . Z).
-// Every tcgen05.mma (M = 128, K = 16) re-reads its 4 KB A slice from shared memory, ~48 cycles at N <= 64 whatever N is
-// (tools/mma_cost.cu): shared-memory bandwidth, not HBM, bounds this kernel, so the contractions are merged until only
-// 18 instructions per tile remain (the first version had 45):
-//   A: acc_v (N=64) = X0.W0 + X1.W1 [4] ; acc_d (N=32) = DX . RESIDUAL^T [2]
-//   B: acc_p (N=64) = [DVs|DVg] . [W0^T|W1^T] [4] ; acc_w (N=96) += [X0|X1|DX|1]^T . [DVs|DVg|Z] [8]
-// (Y_l = P1 + dx_{l+1} is finished by the row warps from the DX tile; no accumulator is shared between E1 and E2, so
-// tile i+2 never waits for tile i's output epilogue.)
-// TMEM: per tile parity ab: acc_v [ab*160, +64), acc_d [+64, +32), acc_p [+96, +64); persistent acc_w [320, +96).
-// RESIDUAL_BIAS gradient = column sums of dx_{l+1}, kept in the row warps' registers.
-// =====================================================================================================
 struct LayerBwdFusedArgs {
   const float* params;
   float* grads;
   int64_t sig, gate, res, sig_b, gate_b, res_b;
   int dil, dil_next, l, has_next, n_tiles, tiles_per_slot, z_plane0;
-  int pf;  // L2 prefetch distance in tiles beyond the ring (0: off)
   const float* gc_tbl;  // global conditioning: this layer's [C1][2D] projection table, else nullptr
   float* dgc_tbl;       // its gradient (fp32 atomics)
   const int32_t* ids;   // [B][T] voice ids
@@ -529,577 +508,44 @@ struct LayerBwdFusedArgs {
   // pre-activations and OVERWRITTEN in place with dv = [dv_s | dv_g] (each thread writes exactly the bytes it read):
   // the gradient wrt the plane, consumed by the LC weight / data gradients of phase L + 1
   bf16* cond;
-  const bf16* dz;  // this layer's plane of the skip-path gradient, [B * T][D] (generation 2: read straight from global memory)
+  const bf16* dz;  // this layer's plane of the skip-path gradient, [B * T][D] (read straight from global memory by E1)
   int seq;  // launch sequence number while tracing (tools/trace_layer.py gaps)
   long long* trace;
 };
 
-// Generation 1 of the fused backward (kept for A/B while generation 2 is measured: WN_BWD_V1=1)
-template <int R, int D, bool GC, bool LC>
-__global__ void __launch_bounds__(896, 1)
-k_layer_bwd_fused_v1_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz,
-                       const __grid_constant__ CUtensorMap map_yn, const __grid_constant__ CUtensorMap map_pn,
-                       const __grid_constant__ CUtensorMap map_yo, const __grid_constant__ CUtensorMap map_po,
-                       const __grid_constant__ CUtensorMap map_wc, const __grid_constant__ CUtensorMap map_wrn,
-                       LayerBwdFusedArgs a) {
-  static_assert(R == 32 && D == 32, "tile bookkeeping below assumes 64-byte activation rows");
-  constexpr int XB = 64;
-  constexpr int PANEL = 128 * XB;                 // 8 KB: one [128 x 32] bf16 tile
-  constexpr int P_X0 = 0, P_X1 = 1, P_YN = 2, P_PN = 3, P_DZ = 4;
-  constexpr int STAGE = 5 * PANEL;                // 40 KB
-  constexpr int NST = 4;
-  constexpr int W_DVS = 0, W_DVG = 1, W_Z = 2;
-  constexpr int WBUF = 3 * PANEL;                 // 24 KB
-  constexpr int NE1 = 512, NE1G = 256, NE2 = 256;
-  constexpr uint32_t ACC_V = 0, ACC_D = 64, ACC_P = 96, ACC_STRIDE = 160, ACC_W = 320;
-  constexpr uint32_t HI = desc_hi(XB);
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* wb = smem + NST * STAGE;         // [2] work buffers
-  unsigned char* wc0 = wb + 2 * WBUF;             // [2D rows][R]   4 KB (GATE half pre-scaled by 0.5)
-  unsigned char* wc1 = wc0 + 2 * D * XB;          //                4 KB, directly behind wc0
-  unsigned char* wrn = wc1 + 2 * D * XB;          // [D rows][R]    2 KB
-  float* stg = reinterpret_cast<float*>(smem);    // end-of-kernel staging (aliases stage 0)
-  __shared__ __align__(8) uint64_t w_full, in_full[NST], stage_free[NST], out_ready[NST], dx_ready[NST], v_full[2],
-      acc1_free[2], dv_ready[2], p_full[2], acc2_free[2], g_full;
-  __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float bias_s[64];  // SIGNAL_BIAS | 0.5 * GATE_BIAS
-  __shared__ float red_s[32];                 // RESIDUAL_BIAS gradient partials
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  pdl_launch_dependents();
-  if (a.trace != nullptr && tid == 0) {  // kernel entry (before barrier init / TMEM allocation)
-    unsigned long long gt;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 3] = (long long)gt;
-    atomicMin(reinterpret_cast<unsigned long long*>(a.trace) + 32 * WN_TRACE_PER_WARP + 4096 + 2 * (a.seq & 63), gt);
-  }
-
-  if (tid == 0) {
-    mbar_init(&w_full, 1);
-    mbar_init(&g_full, 1);
-    for (int i = 0; i < NST; ++i) {
-      mbar_init(&in_full[i], 1);
-      mbar_init(&stage_free[i], 1);
-      mbar_init(&out_ready[i], 1);
-      mbar_init(&dx_ready[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&v_full[i], 1);
-      mbar_init(&acc1_free[i], NE1G);
-      mbar_init(&dv_ready[i], 1);
-      mbar_init(&p_full[i], 1);
-      mbar_init(&acc2_free[i], NE2);
-    }
-    fence_mbar_init();
-  }
-  if (tid < 32) red_s[tid] = 0.f;
-  if (tid < 64)
-    bias_s[tid] = tid < 32 ? (a.sig_b >= 0 ? a.params[a.sig_b + tid] : 0.f)
-                           : (a.gate_b >= 0 ? 0.5f * a.params[a.gate_b + tid - 32] : 0.f);
-
-  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tm = tmem_base_s;
-  pdl_wait();  // the layer above has finished writing (Y, P0) and reading the buffers this layer overwrites
-  Tracer tr;
-  tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
-  if (a.trace != nullptr && tid == 0) {  // per-CTA wall-clock start / SM id (tools/trace_layer.py)
-    unsigned long long gt;
-    unsigned smid;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x] = (long long)gt;
-    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 2] = (long long)smid;
-  }
-
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      const int PF = NST + a.pf;  // L2 prefetch distance in tiles
-      mbar_expect_tx(&w_full, (uint32_t)(2 * 2 * D * XB + D * XB));
-      tma_load_2d(wc0, &map_wc, &w_full, 0, (a.l * 2 + 0) * 2 * D);
-      tma_load_2d(wc1, &map_wc, &w_full, 0, (a.l * 2 + 1) * 2 * D);
-      tma_load_2d(wrn, &map_wrn, &w_full, 0, a.l * D);
-      auto prefetch = [&](int j) {
-        const int tile = (int)blockIdx.x + j * (int)gridDim.x;
-        const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
-        tma_prefetch_l2_3d(&map_x, 0, t0, b);
-        tma_prefetch_l2_3d(&map_x, 0, t0 + a.dil, b);
-        tma_prefetch_l2_3d(&map_dz, 0, t0, a.z_plane0 + b);
-        if (a.has_next) {
-          tma_prefetch_l2_3d(&map_yn, 0, t0, b);
-          tma_prefetch_l2_3d(&map_pn, 0, t0 + a.dil_next, b);
-        }
-      };
-      for (int j = NST; j < PF && j < n_my; ++j) prefetch(j);
-      for (int i = 0; i < n_my; ++i) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
-        const int s = i % NST;
-        unsigned char* st = smem + s * STAGE;
-        if (a.pf > 0 && i + PF < n_my) prefetch(i + PF);
-        tr.ev(1, i);
-        mbar_wait(&stage_free[s], ((uint32_t)(i / NST) & 1u) ^ 1u);
-        tr.ev(2, i);
-        mbar_expect_tx(&in_full[s], (uint32_t)((a.has_next ? 5 : 3) * PANEL));
-        tma_load_3d(st + P_X0 * PANEL, &map_x, &in_full[s], 0, t0, b);
-        tma_load_3d(st + P_X1 * PANEL, &map_x, &in_full[s], 0, t0 + a.dil, b);
-        tma_load_3d(st + P_DZ * PANEL, &map_dz, &in_full[s], 0, t0, a.z_plane0 + b);
-        if (a.has_next) {
-          tma_load_3d(st + P_YN * PANEL, &map_yn, &in_full[s], 0, t0, b);
-          tma_load_3d(st + P_PN * PANEL, &map_pn, &in_full[s], 0, t0 + a.dil_next, b);  // rows >= T: zero fill
-        }
-      }
-    }
-  } else if (warp == 1 || warp == 27) {
-    // ===== MMA issuers: warp 1 serves queue A, warp 27 queue B.  One thread spends ~100 cycles per tcgen05.mma it issues
-    // (descriptor arithmetic, the instruction itself, polling) against ~50 cycles of tensor-pipe time: a single issuer was
-    // busy 2400 of the 3150 cycles a tile takes.  tcgen05.commit tracks the issuing thread's own MMAs, and the two queues
-    // write disjoint accumulators, so they only meet through the mbarriers they already used. =====
-    if (lane == 0) {
-      mbar_wait(&w_full, 0);
-      const uint32_t idv = make_idesc_bf16(128, 2 * D), idd = make_idesc_bf16(128, D);
-      const uint32_t idp = make_idesc_bf16(128, 2 * R, false, true);  // A = dv (K-major), B = [W0|W1] (MN-major)
-      const uint32_t idw = make_idesc_bf16(128, 2 * D + R, true, true);
-      // K-major operands: K step of 16 elements = 32 bytes = +2 in the descriptor; MN-major: 16 rows of 64 bytes = +64
-      const uint32_t ring_k = desc_lo_k(smem_u32(smem)), ring_mn = desc_lo(smem_u32(smem), PANEL);
-      const uint32_t wb_k = desc_lo_k(smem_u32(wb)), wb_mn = desc_lo(smem_u32(wb), PANEL);
-      const uint32_t wc0_k = desc_lo_k(smem_u32(wc0)), wc1_k = desc_lo_k(smem_u32(wc1));
-      const uint32_t wc_mn = desc_lo(smem_u32(wc0), 2 * D * XB);  // chunk 0 = wc0 (-> P0), chunk 1 = wc1 (-> Y)
-      const uint32_t wrn_k = desc_lo_k(smem_u32(wrn));
-      auto issue_a = [&](int i) {  // recomputed pre-activations; residual part of dz and an fp32 copy of dx
-        const int s = i % NST, ab = i & 1;
-        const uint32_t x0 = ring_k + (uint32_t)s * (STAGE >> 4), x1 = x0 + (PANEL >> 4), dx = x0 + P_YN * (PANEL >> 4);
-        const uint32_t av = tm + ab * ACC_STRIDE + ACC_V, ad = tm + ab * ACC_STRIDE + ACC_D;
-        mma_bf16_ss2(av, x0, HI, wc0_k, HI, idv, false);
-        mma_bf16_ss2(av, x0 + 2, HI, wc0_k + 2, HI, idv, true);
-        mma_bf16_ss2(av, x1, HI, wc1_k, HI, idv, true);
-        mma_bf16_ss2(av, x1 + 2, HI, wc1_k + 2, HI, idv, true);
-        if (a.has_next) {  // dz(res) = dx_{l+1} . RESIDUAL^T : B = RESIDUAL [D rows][R]
-          mma_bf16_ss2(ad, dx, HI, wrn_k, HI, idd, false);
-          mma_bf16_ss2(ad, dx + 2, HI, wrn_k + 2, HI, idd, true);
-        }
-        mma_commit(&v_full[ab]);
-      };
-      auto issue_b = [&](int i) {  // data gradient + weight gradients of tile i
-        const int s = i % NST, ab = i & 1;
-        const uint32_t wk = wb_k + (uint32_t)ab * (WBUF >> 4), wm = wb_mn + (uint32_t)ab * (WBUF >> 4);
-        const uint32_t sm = ring_mn + (uint32_t)s * (STAGE >> 4);
-        const uint32_t ap = tm + ab * ACC_STRIDE + ACC_P;
-        // [P0 | P1] = dv . [W0^T | W1^T]: K = 2D dv channels; B rows 16j.. of the stacked [2D][R] filter copies
-        mma_bf16_ss2(ap, wk + W_DVS * (PANEL >> 4), HI, wc_mn, HI, idp, false);
-        mma_bf16_ss2(ap, wk + W_DVS * (PANEL >> 4) + 2, HI, wc_mn + 64, HI, idp, true);
-        mma_bf16_ss2(ap, wk + W_DVG * (PANEL >> 4), HI, wc_mn + 128, HI, idp, true);
-        mma_bf16_ss2(ap, wk + W_DVG * (PANEL >> 4) + 2, HI, wc_mn + 192, HI, idp, true);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)  // K = 128 timesteps, 16 per instruction
-          mma_bf16_ss2(tm + ACC_W, sm + k * 64, HI, wm + k * 64, HI, idw, (i | k) != 0);
-        mma_commit(&p_full[ab]);
-      };
-      uint32_t spins = 0;
-      if (warp == 27) {
-        for (int nb = 0; nb < n_my;) {
-          // tile nb's dv tile is written after its v_full, i.e. after queue A issued tile nb
-          if (mbar_test_wait(&dv_ready[nb & 1], (uint32_t)(nb >> 1) & 1u) &&
-              mbar_test_wait(&acc2_free[nb & 1], ((uint32_t)(nb >> 1) & 1u) ^ 1u)) {
-            tc_fence_after_sync();
-            tr.ev(4, nb);
-            issue_b(nb++);
-            tr.ev(17, nb - 1);
-            spins = 0;
-          } else if (++spins > (1u << 26)) __trap();
-        }
-        mma_commit(&g_full);
-      } else {
-        for (int na = 0; na < n_my;) {
-          if (mbar_test_wait(&in_full[na % NST], (uint32_t)(na / NST) & 1u) &&
-              mbar_test_wait(&dx_ready[na % NST], (uint32_t)(na / NST) & 1u) &&
-              mbar_test_wait(&acc1_free[na & 1], ((uint32_t)(na >> 1) & 1u) ^ 1u)) {
-            tc_fence_after_sync();
-            tr.ev(3, na);
-            issue_a(na++);
-            tr.ev(16, na - 1);
-            spins = 0;
-          } else if (++spins > (1u << 26)) __trap();
-        }
-      }
-    }
-  } else if (warp < 18) {
-    // ===== E1: gate backward, two groups of 8 warps that alternate tiles (group g owns tiles g, g+2, ... and with them
-    // the accumulator / work-buffer parity g), so one group's TMEM round trip, p_full wait, proxy fence and barrier
-    // overlap the other group's arithmetic.  thread <-> (row r, channels [16*half, +16)), two passes of 8 =====
-    const int e = warp - 2;
-    const int g = e >> 3, half = (e >> 2) & 1, q4 = warp & 3;
-    const int r = q4 * 32 + lane;
-    const int et = e * 32 + lane;  // 0..511
-    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    const bool elected = ((e & 7) == 0 && lane == 0);
-    const uint32_t sw64 = ((uint32_t)r >> 1) & 3u;
-    const uint32_t o[2] = {(uint32_t)r * 64u + ((((uint32_t)(2 * half)) ^ sw64) << 4),
-                           (uint32_t)r * 64u + ((((uint32_t)(2 * half + 1)) ^ sw64) << 4)};
-    const float4* bs4 = reinterpret_cast<const float4*>(bias_s + 16 * half);
-    const float4* bg4 = reinterpret_cast<const float4*>(bias_s + 32 + 16 * half);
-    for (int i = g; i < n_my; i += 2) {
-      const int s = i % NST, ab = g;
-      const unsigned char* dzp = smem + s * STAGE + P_DZ * PANEL;
-      unsigned char* wbuf = wb + ab * WBUF;
-      const uint32_t tb = tm + ab * ACC_STRIDE + lane_sel;
-      int gid = 0;  // this row's voice id (global conditioning)
-      if constexpr (GC) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        const int b = tile / a.tiles_per_slot, t = (tile % a.tiles_per_slot) * 128 + r;
-        gid = t < a.T ? min(max(__ldg(a.ids + (size_t)b * a.T + t), 0), a.C1 - 1) : 0;
-      }
-      uint4 lcs[2], lcg[2];
-      uint4* lcrow = nullptr;
-      if constexpr (LC) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        const int b = tile / a.tiles_per_slot, t = (tile % a.tiles_per_slot) * 128 + r;
-        lcs[0] = lcs[1] = lcg[0] = lcg[1] = make_uint4(0u, 0u, 0u, 0u);
-        if (t < a.T) {
-          lcrow = reinterpret_cast<uint4*>(a.cond + ((size_t)b * a.T + t) * (2 * D) + 16 * half);
-          lcs[0] = lcrow[0]; lcs[1] = lcrow[1];
-          lcg[0] = lcrow[D / 8]; lcg[1] = lcrow[D / 8 + 1];
-        }
-      }
-      tr.ev(5, i);
-      mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);  // dz tile (TMA) visible to this thread
-      tr.ev(14, i);
-      mbar_wait(&v_full[ab], (uint32_t)(i >> 1) & 1u);
-      tr.ev(6, i);
-      tc_fence_after_sync();
-      if (i >= 2) mbar_wait(&p_full[ab], (uint32_t)((i - 2) >> 1) & 1u);  // the MMAs of tile i-2 have finished reading wb[ab]
-#pragma unroll
-      for (int p = 0; p < 2; ++p) {
-        uint32_t pz[4], pvs[4], pvg[4];
-        const int c0 = 16 * half + 8 * p;
-        uint32_t vs[8], vg[8], vd[8];
-        tmem_ld_32x32b_x8(tb + ACC_V + c0, vs);
-        tmem_ld_32x32b_x8(tb + ACC_V + 32 + c0, vg);
-        if (a.has_next) {
-          tmem_ld_32x32b_x8(tb + ACC_D + c0, vd);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) vd[j] = 0u;
-        }
-        const uint4 d0 = *reinterpret_cast<const uint4*>(dzp + o[p]);
-        const uint32_t dzs[4] = {d0.x, d0.y, d0.z, d0.w};
-        tmem_ld_wait();
-        if (p == 1) {
-          tc_fence_before_sync();
-          mbar_arrive(&acc1_free[ab]);
-        }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          float4 b_s = bs4[2 * p + q], b_g = bg4[2 * p + q];
-          if constexpr (GC) {  // the accumulator's GATE half holds 0.5 * pre-activation: the table's gate half is halved too
-            const float* gct = a.gc_tbl + (size_t)gid * 2 * D + c0;
-            const float4 c_s = __ldg(reinterpret_cast<const float4*>(gct) + q);
-            const float4 c_g = __ldg(reinterpret_cast<const float4*>(gct + D) + q);
-            b_s.x += c_s.x; b_s.y += c_s.y; b_s.z += c_s.z; b_s.w += c_s.w;
-            b_g.x = fmaf(0.5f, c_g.x, b_g.x); b_g.y = fmaf(0.5f, c_g.y, b_g.y);
-            b_g.z = fmaf(0.5f, c_g.z, b_g.z); b_g.w = fmaf(0.5f, c_g.w, b_g.w);
-          }
-          if constexpr (LC) {
-            const uint32_t ws0 = q == 0 ? lcs[p].x : lcs[p].z, ws1 = q == 0 ? lcs[p].y : lcs[p].w;
-            const uint32_t wg0 = q == 0 ? lcg[p].x : lcg[p].z, wg1 = q == 0 ? lcg[p].y : lcg[p].w;
-            add_bf16x4(b_s, ws0, ws1, 1.f);
-            add_bf16x4(b_g, wg0, wg1, 0.5f);
-          }
-          const float bsv[4] = {b_s.x, b_s.y, b_s.z, b_s.w}, bgv[4] = {b_g.x, b_g.y, b_g.z, b_g.w};
-          float zz[4], ds[4], dg[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int d = 4 * q + k;
-            const float th = tanh_fast(__uint_as_float(vs[d]) + bsv[k]);
-            const float u = tanh_fast(__uint_as_float(vg[d]) + bgv[k]);   // accumulator holds 0.5 * gate pre-activation
-            const float sg = fmaf(0.5f, u, 0.5f);
-            const uint32_t dw = dzs[d >> 1];
-            const float dz = ((d & 1) == 0 ? __uint_as_float(dw << 16) : __uint_as_float(dw & 0xffff0000u)) + __uint_as_float(vd[d]);
-            zz[k] = th * sg;
-            ds[k] = (dz * sg) * fmaf(-th, th, 1.f);
-            dg[k] = (dz * th) * fmaf(-0.5f * u, u, 0.5f);   // = 2 * dz th sg (1 - sg): pairs with the 0.5-scaled GATE filter
-          }
-          pz[2 * q] = pack2(zz[0], zz[1]);  pz[2 * q + 1] = pack2(zz[2], zz[3]);
-          pvs[2 * q] = pack2(ds[0], ds[1]); pvs[2 * q + 1] = pack2(ds[2], ds[3]);
-          pvg[2 * q] = pack2(dg[0], dg[1]); pvg[2 * q + 1] = pack2(dg[2], dg[3]);
-          if constexpr (LC) {  // gradient wrt the conditioning plane: the true dv_g is half of what pairs with the 0.5-scaled filter
-            if (q == 0) { lcg[p].x = pack2(0.5f * dg[0], 0.5f * dg[1]); lcg[p].y = pack2(0.5f * dg[2], 0.5f * dg[3]); }
-            else        { lcg[p].z = pack2(0.5f * dg[0], 0.5f * dg[1]); lcg[p].w = pack2(0.5f * dg[2], 0.5f * dg[3]); }
-          }
-          if constexpr (GC) {
-            // table gradient: dTbl[id][n] += dv[n] (gate half: dv carries 2x).  A warp is 32 consecutive timesteps of
-            // one slot, ids change only at file junctions: reduce over the warp when it is uniform, else per row
-            const int id0 = __shfl_sync(0xffffffffu, gid, 0);
-            const bool uni = __all_sync(0xffffffffu, gid == id0);
-            if (uni) {
-              // transpose-reduce: 8 values x 32 lanes -> lane L ends up with the warp total of value (L >> 2) & 7
-              // (9 shuffles instead of 8 full warp sums = 40)
-              float w[8] = {ds[0], ds[1], ds[2], ds[3], 0.5f * dg[0], 0.5f * dg[1], 0.5f * dg[2], 0.5f * dg[3]};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const bool hi = (lane & 16) != 0;
-                const float send = hi ? w[i] : w[i + 4], keep = hi ? w[i + 4] : w[i];
-                w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-              }
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const bool hi = (lane & 8) != 0;
-                const float send = hi ? w[i] : w[i + 2], keep = hi ? w[i + 2] : w[i];
-                w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-              }
-              {
-                const bool hi = (lane & 4) != 0;
-                const float send = hi ? w[0] : w[1], keep = hi ? w[1] : w[0];
-                w[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-              }
-              w[0] += __shfl_xor_sync(0xffffffffu, w[0], 2);
-              w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
-              const int idx = (lane >> 2) & 7;
-              if ((lane & 3) == 0 && w[0] != 0.f)
-                atomicAdd(a.dgc_tbl + (size_t)id0 * 2 * D + (idx < 4 ? 0 : D) + c0 + 4 * q + (idx & 3), w[0]);
-            } else {
-              float* drow = a.dgc_tbl + (size_t)gid * 2 * D + c0 + 4 * q;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (ds[k] != 0.f) atomicAdd(drow + k, ds[k]);
-                if (dg[k] != 0.f) atomicAdd(drow + D + k, 0.5f * dg[k]);
-              }
-            }
-          }
-        }
-        *reinterpret_cast<uint4*>(wbuf + W_Z * PANEL + o[p]) = make_uint4(pz[0], pz[1], pz[2], pz[3]);
-        *reinterpret_cast<uint4*>(wbuf + W_DVS * PANEL + o[p]) = make_uint4(pvs[0], pvs[1], pvs[2], pvs[3]);
-        *reinterpret_cast<uint4*>(wbuf + W_DVG * PANEL + o[p]) = make_uint4(pvg[0], pvg[1], pvg[2], pvg[3]);
-        if constexpr (LC) {
-          if (lcrow != nullptr) {
-            lcrow[p] = make_uint4(pvs[0], pvs[1], pvs[2], pvs[3]);
-            lcrow[D / 8 + p] = lcg[p];
-          }
-        }
-      }
-      tr.ev(15, i);
-      fence_proxy_async_smem();
-      tr.ev(7, i);
-      if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 4, 256;" ::: "memory");
-      tr.ev(8, i);
-      if (elected) mbar_arrive(&dv_ready[ab]);
-    }
-    // ---- flush: weight gradients TMEM -> staging -> coalesced atomics ----
-    const int cq = 2 * g + half;  // column quarter of the 64 dv columns handled by this warp in the flush
-    const int c0 = 8 * cq;
-    mbar_wait(&g_full, 0);
-    tc_fence_after_sync();
-    if (n_my > 0) mbar_wait(&stage_free[(n_my - 1) % NST], (uint32_t)((n_my - 1) / NST) & 1u);  // last TMA store drained
-    asm volatile("bar.sync 3, 768;" ::: "memory");  // the row warps have published their RESIDUAL_BIAS partials
-    if (n_my > 0) {
-      // acc_w[128 x 96]: rows 0..63, columns 0..63 = conv taps (GATE columns carry 2x); rows 64..95, columns 64..95 =
-      // DX^T . Z = RESIDUAL's gradient, transposed; row 96 (ones), columns 0..63 = column sums of dv = bias gradients
-      const float gsc = cq < 2 ? 1.f : 0.5f;
-      if (q4 < 2) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tm + ACC_W + lane_sel + (uint32_t)(16 * cq), v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) stg[r * 65 + 16 * cq + j] = gsc * __uint_as_float(v[j]);
-      } else if (q4 == 2 && a.has_next) {
-        uint32_t w[8];
-        tmem_ld_32x32b_x8(tm + ACC_W + lane_sel + (uint32_t)(2 * D + c0), w);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) stg[64 * 65 + (c0 + j) * 33 + (r - 64)] = __uint_as_float(w[j]);
-      } else if (q4 == 3) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tm + ACC_W + lane_sel + (uint32_t)(16 * cq), v);
-        tmem_ld_wait();
-        if (lane == 0 && a.sig_b >= 0) {  // row 96
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float val = gsc * __uint_as_float(v[j]);
-            if (val != 0.f) atomicAdd(a.grads + (cq < 2 ? a.sig_b + 16 * cq : a.gate_b + 16 * (cq - 2)) + j, val);
-          }
-        }
-      }
-      asm volatile("bar.sync 5, 512;" ::: "memory");
-      // dWc row m = tap*R + rr, column n: n < D -> SIGNAL[tap][rr][n], else GATE[tap][rr][n-D]
-      for (int idx = et; idx < 64 * 64; idx += NE1) {
-        const int m = idx >> 6, n = idx & 63;
-        const float val = stg[m * 65 + n];
-        const int tap = m >> 5, rr = m & 31;
-        float* dst = a.grads + (n < D ? a.sig : a.gate) + ((size_t)tap * R + rr) * D + (n & 31);
-        if (val != 0.f) atomicAdd(dst, val);
-      }
-      if (a.has_next) {
-        for (int idx = et; idx < 32 * 32; idx += NE1) {
-          const int d = idx >> 5, c = idx & 31;
-          const float val = stg[64 * 65 + d * 33 + c];
-          if (val != 0.f) atomicAdd(a.grads + a.res + (size_t)d * R + c, val);
-        }
-        if (et < 32 && a.res_b >= 0) {
-          const float val = red_s[et];
-          if (val != 0.f) atomicAdd(a.grads + a.res_b + et, val);
-        }
-      }
-    }
-  } else if (warp < 26) {
-    // ===== row warps: E0 (dx_{l+1} = Y_{l+1} + P0_{l+1}[t + dil] -> one bf16 tile in place; PN := 1.0) and E2 (outputs).
-    // thread <-> (row r, channels [16*rh, +16)) =====
-    const int q4 = warp & 3, rh = (warp - 18) >> 2;
-    const int r = q4 * 32 + lane;
-    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    const bool elected = (warp == 18 && lane == 0);
-    const uint32_t sw64 = ((uint32_t)r >> 1) & 3u;
-    const uint32_t oc[2] = {(uint32_t)r * 64u + ((((uint32_t)(2 * rh)) ^ sw64) << 4),
-                            (uint32_t)r * 64u + ((((uint32_t)(2 * rh + 1)) ^ sw64) << 4)};
-    float rsum[16];  // column sums of dx_{l+1}: RESIDUAL_BIAS gradient
-#pragma unroll
-    for (int c = 0; c < 16; ++c) rsum[c] = 0.f;
-    auto e0 = [&](int i) {
-      const int s = i % NST;
-      unsigned char* st = smem + s * STAGE;
-      unsigned char* dxp = st + P_YN * PANEL;  // each thread overwrites exactly the bytes it has just read
-      unsigned char* pnp = st + P_PN * PANEL;
-      tr.ev(18, i);
-      mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);
-      tr.ev(19, i);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        if (a.has_next) {
-          const uint4 y4 = *reinterpret_cast<const uint4*>(dxp + oc[c]);
-          const uint4 p4 = *reinterpret_cast<const uint4*>(pnp + oc[c]);
-          const uint32_t yw[4] = {y4.x, y4.y, y4.z, y4.w}, pw[4] = {p4.x, p4.y, p4.z, p4.w};
-          uint32_t o[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float lo = __uint_as_float(yw[k] << 16) + __uint_as_float(pw[k] << 16);
-            const float hi = __uint_as_float(yw[k] & 0xffff0000u) + __uint_as_float(pw[k] & 0xffff0000u);
-            rsum[8 * c + 2 * k] += lo;
-            rsum[8 * c + 2 * k + 1] += hi;
-            o[k] = pack2(lo, hi);
-          }
-          *reinterpret_cast<uint4*>(dxp + oc[c]) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-        // top layer: no dx_{l+1}, but the ones panel must be restored (the previous tile's P0 overwrote it)
-        *reinterpret_cast<uint4*>(pnp + oc[c]) = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
-      }
-      fence_proxy_async_smem();
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      tr.ev(20, i);
-      if (elected) mbar_arrive(&dx_ready[s]);
-    };
-    auto e2 = [&](int i) {
-      const int s = i % NST, ab = i & 1;
-      unsigned char* st = smem + s * STAGE;
-      const uint32_t tb = tm + ab * ACC_STRIDE + lane_sel;
-      uint32_t p0[16], p1[16], dxw[8];
-      tr.ev(9, i);
-      mbar_wait(&p_full[ab], (uint32_t)(i >> 1) & 1u);  // every MMA reading this stage has completed
-      tr.ev(10, i);
-      tc_fence_after_sync();
-      tmem_ld_32x32b_x16(tb + ACC_P + 16 * rh, p0);
-      tmem_ld_32x32b_x16(tb + ACC_P + R + 16 * rh, p1);
-      if (a.has_next) {  // dx_{l+1}: this thread's own 32 bytes of the DX tile (about to be overwritten by Y_l)
-        const uint4 xa = *reinterpret_cast<const uint4*>(st + P_YN * PANEL + oc[0]);
-        const uint4 xb = *reinterpret_cast<const uint4*>(st + P_YN * PANEL + oc[1]);
-        dxw[0] = xa.x; dxw[1] = xa.y; dxw[2] = xa.z; dxw[3] = xa.w;
-        dxw[4] = xb.x; dxw[5] = xb.y; dxw[6] = xb.z; dxw[7] = xb.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dxw[j] = 0u;
-      }
-      tmem_ld_wait();
-      tc_fence_before_sync();
-      mbar_arrive(&acc2_free[ab]);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        *reinterpret_cast<uint4*>(st + P_PN * PANEL + oc[c]) =
-            make_uint4(pack2(__uint_as_float(p0[8 * c]), __uint_as_float(p0[8 * c + 1])),
-                       pack2(__uint_as_float(p0[8 * c + 2]), __uint_as_float(p0[8 * c + 3])),
-                       pack2(__uint_as_float(p0[8 * c + 4]), __uint_as_float(p0[8 * c + 5])),
-                       pack2(__uint_as_float(p0[8 * c + 6]), __uint_as_float(p0[8 * c + 7])));
-        *reinterpret_cast<uint4*>(st + P_YN * PANEL + oc[c]) =
-            make_uint4(pack2(__uint_as_float(p1[8 * c]) + __uint_as_float(dxw[4 * c] << 16),
-                             __uint_as_float(p1[8 * c + 1]) + __uint_as_float(dxw[4 * c] & 0xffff0000u)),
-                       pack2(__uint_as_float(p1[8 * c + 2]) + __uint_as_float(dxw[4 * c + 1] << 16),
-                             __uint_as_float(p1[8 * c + 3]) + __uint_as_float(dxw[4 * c + 1] & 0xffff0000u)),
-                       pack2(__uint_as_float(p1[8 * c + 4]) + __uint_as_float(dxw[4 * c + 2] << 16),
-                             __uint_as_float(p1[8 * c + 5]) + __uint_as_float(dxw[4 * c + 2] & 0xffff0000u)),
-                       pack2(__uint_as_float(p1[8 * c + 6]) + __uint_as_float(dxw[4 * c + 3] << 16),
-                             __uint_as_float(p1[8 * c + 7]) + __uint_as_float(dxw[4 * c + 3] & 0xffff0000u)));
-      }
-      fence_proxy_async_smem();
-      tr.ev(11, i);
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      tr.ev(12, i);
-      if (elected) mbar_arrive(&out_ready[s]);
-    };
-    if (n_my > 0) e0(0);
-    if (n_my > 1) e0(1);
-    for (int i = 0; i < n_my; ++i) {
-      if (i + 2 < n_my) e0(i + 2);  // needs only the landed stage: runs two tiles ahead of everything else
-      e2(i);
-    }
-    if (a.has_next && a.res_b >= 0) {
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float v = warp_sum(rsum[c]);
-        if (lane == 0) atomicAdd(&red_s[16 * rh + c], v);
-      }
-    }
-    asm volatile("bar.sync 3, 768;" ::: "memory");
-  } else {
-    // ===== TMA-store issuer: the only thread that touches the store path; returns the stage to the ring =====
-    if (lane == 0) {
-      for (int i = 0; i < n_my; ++i) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
-        const int s = i % NST;
-        unsigned char* st = smem + s * STAGE;
-        mbar_wait(&out_ready[s], (uint32_t)(i / NST) & 1u);
-        tma_store_3d(&map_yo, st + P_YN * PANEL, 0, t0, b);
-        tma_store_3d(&map_po, st + P_PN * PANEL, 0, t0, b);
-        tma_store_commit();
-        tma_store_wait_read<0>();
-        tr.ev(13, i);
-        mbar_arrive(&stage_free[s]);
-      }
-      tma_store_wait_all<0>();
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (a.trace != nullptr && tid == 0) {
-    unsigned long long gt;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-    a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 1] = (long long)gt;
-    atomicMax(reinterpret_cast<unsigned long long*>(a.trace) + 32 * WN_TRACE_PER_WARP + 4096 + 2 * (a.seq & 63) + 1, gt);
-  }
-  if (warp == 1) tmem_dealloc(tm, 512);
-}
-
 // =====================================================================================================
-// k_layer_bwd_fused_umma, generation 2 (see the file header).  One CTA per SM, 28 warps:
+// k_layer_bwd_fused_umma (see the file header).  One CTA per SM, 28 warps:
 //   warp 0        TMA producer                                  warps 1, 27   MMA issuers (queue A / queue B)
 //   warps 2..17   gate epilogue E1, two alternating groups      warps 18..25  row warps: E2 (outputs)
 //   warp 26       TMA-store issuer (returns ring stages)
-// Generation 1's in-kernel timeline: a ring stage lived ~12 000 cycles and there were four of them, so a tile left the
-// CTA every ~3100 cycles; the chain  loads landed -> E0 merge (1200) -> wait (1100) -> queue A -> E1 -> queue B -> E2 ->
-// store  was the bound, not HBM (3.0 of 6.5 TB/s), the tensor pipe (28 %) or issue slots (50 %).  Hence:
+// The first version of this kernel (round 1: 40 KB stages X0 | X1 | YN->DX | PN->ONES | DZ, four of them, and an E0
+// phase that merged YN + PN into one bf16 tile) was bound by ring depth x stage lifetime: in its in-kernel timeline a
+// stage lived ~12 000 cycles, so a tile left the CTA every ~3100 cycles, with HBM at 3.0 of 6.5 TB/s, the tensor pipe
+// 28 % and the issue slots 50 % busy; loads landed -> E0 (1200) -> wait (1100) -> queue A -> E1 -> queue B -> E2 -> store
+// was the chain.  Hence (1.705 -> 1.50 ms for the 30 layers of configs[1], tile period ~2600 cycles):
 //   * the ring stage is X0 | X1 | YN | PN only (32 KB, 5 deep).  dz never goes through shared memory: every E1 thread
 //     fetches its own 2 x 16 bytes of the dz plane with plain global loads issued before it waits for the tile's MMAs;
 //   * there is no E0 phase: dx_{l+1} = YN + PN is never materialised.  By linearity acc_d = YN . Wr^T + PN . Wr^T (two
 //     more N = 32 MMAs) and the MN-major A operand of the weight-gradient MMA is the stage itself, [X0 | X1 | YN | PN]^T:
 //     rows 64..95 and 96..127 of acc_w are the two halves of RESIDUAL's (transposed) gradient, added in the flush;
-//   * with the constant-one panel gone, the SIGNAL / GATE bias gradients (column sums of dv) are summed by E1 itself: a
-//     shuffle transpose-reduce per 8 values (9 shuffles), one accumulator register per (pass, quad);
+//   * with the constant-one panel gone, the SIGNAL / GATE bias gradients (column sums of dv) come from a third MMA queue
+//     (C, issued by queue A's thread in its idle time): [DVs | DVg | ..]^T . 1 with a 1 KB all-ones B operand (N = 16),
+//     accumulated in 16 more TMEM columns.  (Summing them in E1 with warp shuffles cost 0.16 ms per step: E1's
+//     arithmetic is on the critical chain, the tensor pipe is not.);
 //   * the outputs overwrite YN (Y_l) and PN (P0_l) once every MMA reading the stage has completed.
-// Work buffer (24 KB, 2 deep): DVs | DVg | Z as before.  18 + 2 instructions per tile:
+// Work buffer (24 KB, 2 deep): DVs | DVg | Z -- three [128 x 32] SW64 panels written by E1: K-major A operands of
+// dv . W^T and, re-described MN-major, the B operand (N = 96) of the weight-gradient MMA and the A operand of queue C.
+// Every tcgen05.mma (M = 128, K = 16) re-reads its 4 KB A slice from shared memory, ~48 cycles at N <= 64 whatever N is
+// (tools/mma_cost.cu).  28 instructions per tile:
 //   A: acc_v (N=64) = X0.W0 + X1.W1 [4] ; acc_d (N=32) = YN . RESIDUAL^T + PN . RESIDUAL^T [4]
 //   B: acc_p (N=64) = [DVs|DVg] . [W0^T|W1^T] [4] ; acc_w (N=96) += [X0|X1|YN|PN]^T . [DVs|DVg|Z] [8]
-// TMEM: per tile parity ab: acc_v [ab*160, +64), acc_d [+64, +32), acc_p [+96, +64); persistent acc_w [320, +96).
+//   C: acc_b (N=16) += [DVs|DVg|Z|..]^T . 1 [8]
+// TMEM: per tile parity ab: acc_v [ab*160, +64), acc_d [+64, +32), acc_p [+96, +64); persistent acc_w [320, +96),
+// acc_b [416, +16).  RESIDUAL_BIAS gradient = column sums of dx_{l+1}, kept in the row warps' registers.
+// Tried on this version and dropped: dz requested a whole tile ahead from DRAM into registers (the pending loads made
+// E1's arithmetic ~1000 cycles slower; now the producer L2-prefetches the dz tile and E1 loads it at the top of its
+// tile); outputs written with plain 16-byte global stores from E2 instead of shared memory + TMA (the stage is free
+// ~3000 cycles earlier, but a warp's 32 rows x 16 bytes are 32 separate sectors: 1.50 -> 1.70 ms).
 // =====================================================================================================
 // 16-byte read-only global load that the compiler may not move (asm volatile): issued where it is written
 __device__ __forceinline__ uint4 ldg_nc_v4_pinned(const void* p) {
@@ -1778,11 +1224,10 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
   ga.tiles_per_slot = (T + 127) / 128;
   ga.n_tiles = ga.tiles_per_slot * m->n_slots;
   ga.z_plane0 = l * m->n_slots;
-  ga.pf = env_int("WN_PF_BWD", 0);
   ga.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
   static int trace_seq = 0;
   if (ga.trace != nullptr) ga.seq = trace_seq++;
-  // generation 2: ring 5 x 32 KB (generation 1: 4 x 40 KB) | work buffers 2 x 24 KB | wc 2 x 4 KB | RESIDUAL 2 KB
+  // ring 5 x 32 KB | work buffers 2 x 24 KB | wc 2 x 4 KB | RESIDUAL 2 KB
   // (+ 1 KB of ones)
   const size_t smem = 4 * 5 * 8192 + 2 * 3 * 8192 + 2 * 4096 + 2048 + 1024 + 1024;
   const int grid = persist_grid(std::max(1, std::min(ga.n_tiles, m->sm_count)));
@@ -1799,14 +1244,8 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
     ga.C1 = C1;
   }
   if (lc) ga.cond = reinterpret_cast<bf16*>(ws + m->wl.cond) + (size_t)l * m->n_slots * T * 2 * m->a.n_dil;
-  static const bool use_v1 = getenv("WN_BWD_V1") != nullptr;  // A/B against generation 1
 #define WN_BWD(GC_, LC_)                                                                                                  \
-  if (use_v1) {                                                                                                           \
-    WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_v1_umma<32, 32, GC_, LC_>,                                       \
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
-    WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_v1_umma<32, 32, GC_, LC_>, grid, 896, smem, st, mp->x[l], mp->dz,          \
-                             mp->dx[nx], mp->p0[nx], mp->dx[cu], mp->p0[cu], mp->wc, mp->wrn, ga));                       \
-  } else {                                                                                                                \
+  {                                                                                                                       \
     WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_umma<32, 32, GC_, LC_>,                                          \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
     WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_umma<32, 32, GC_, LC_>, grid, 896, smem, st, mp->x[l], mp->dz,             \
