@@ -140,6 +140,7 @@ struct LayerFwdPArgs {
   // local conditioning (tmodel.py:156-160): this layer's plane [B*T][2D] bf16 = lc_upsampled . [LC_SIGNAL | LC_GATE],
   // added to the pre-activations row by row in the gate epilogue
   const bf16* cond;
+  uint64_t pol_x0, pol_z, pol_xout;  // L2 eviction hints (umma.cuh): x[t-dil] tile = last forward use of those rows; z; x'
   long long* trace;
 };
 // 4 bf16 (two packed words) added onto a float4 of pre-activation biases, scaled (GATE half: 0.5, see the file header)
@@ -242,7 +243,7 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
         const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
         tile_s[s] = tile;
         mbar_expect_tx(&in_full[s], (uint32_t)STAGE);
-        tma_load_3d(smem + s * STAGE, &map_x, &in_full[s], 0, t0, b);
+        tma_load_3d_hint(smem + s * STAGE, &map_x, &in_full[s], 0, t0, b, a.pol_x0);
         tma_load_3d(smem + s * STAGE + PANEL, &map_x, &in_full[s], 0, t0 + a.dil, b);
         tile = (int)gridDim.x + atomicAdd(a.tile_ctr, 1);  // the next one, fetched while these loads fly
       }
@@ -456,7 +457,7 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (nz < n_done_s && mbar_test_wait(&zo_ready[nz & 1], (uint32_t)(nz >> 1) & 1u)) {
           const int tile = zo_tile[nz & 1];
           const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
-          tma_store_3d(&map_z, zt + (nz & 1) * PANEL, a.z_col, t0, b);
+          tma_store_3d_hint(&map_z, zt + (nz & 1) * PANEL, a.z_col, t0, b, a.pol_z);
           tma_store_commit();
           release_prev();
           prev_kind = 0; prev_idx = nz++;
@@ -467,7 +468,7 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (!a.last && nx < nz && mbar_test_wait(&xo_ready[nx % NST], (uint32_t)(nx / NST) & 1u)) {
           const int tile = xo_tile[nx % NST];
           const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
-          tma_store_3d(&map_xout, smem + (nx % NST) * STAGE, 0, a.dil_next + t0, b);
+          tma_store_3d_hint(&map_xout, smem + (nx % NST) * STAGE, 0, a.dil_next + t0, b, a.pol_xout);
           tma_store_commit();
           tr.ev(13, nx);
           release_prev();
@@ -508,6 +509,7 @@ struct LayerBwdFusedArgs {
   // pre-activations and OVERWRITTEN in place with dv = [dv_s | dv_g] (each thread writes exactly the bytes it read):
   // the gradient wrt the plane, consumed by the LC weight / data gradients of phase L + 1
   bf16* cond;
+  uint64_t pol_x0, pol_in, pol_out;  // L2 eviction hints: x[t-dil] tile (last use of those rows), Y/P0 in, Y/P0 out
   const bf16* dz;  // this layer's plane of the skip-path gradient, [B * T][D] (read straight from global memory by E1)
   int seq;  // launch sequence number while tracing (tools/trace_layer.py gaps)
   long long* trace;
@@ -677,11 +679,11 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
         tr.ev(2, i);
         mbar_expect_tx(&in_full[s], (uint32_t)((a.has_next ? 4 : 2) * PANEL));
         tma_prefetch_l2_3d(&map_dz, 0, t0, a.z_plane0 + b);  // E1 reads this tile's dz rows from the L2 a few thousand cycles from now
-        tma_load_3d(st + P_X0 * PANEL, &map_x, &in_full[s], 0, t0, b);
+        tma_load_3d_hint(st + P_X0 * PANEL, &map_x, &in_full[s], 0, t0, b, a.pol_x0);
         tma_load_3d(st + P_X1 * PANEL, &map_x, &in_full[s], 0, t0 + a.dil, b);
         if (a.has_next) {
-          tma_load_3d(st + P_YN * PANEL, &map_yn, &in_full[s], 0, t0, b);
-          tma_load_3d(st + P_PN * PANEL, &map_pn, &in_full[s], 0, t0 + a.dil_next, b);  // rows >= T: zero fill
+          tma_load_3d_hint(st + P_YN * PANEL, &map_yn, &in_full[s], 0, t0, b, a.pol_in);
+          tma_load_3d_hint(st + P_PN * PANEL, &map_pn, &in_full[s], 0, t0 + a.dil_next, b, a.pol_in);  // rows >= T: zero fill
         }
       }
     }
@@ -1053,8 +1055,8 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
         const int s = i % NST;
         unsigned char* st = smem + s * STAGE;
         mbar_wait(&out_ready[s], (uint32_t)(i / NST) & 1u);
-        tma_store_3d(&map_yo, st + P_YN * PANEL, 0, t0, b);
-        tma_store_3d(&map_po, st + P_PN * PANEL, 0, t0, b);
+        tma_store_3d_hint(&map_yo, st + P_YN * PANEL, 0, t0, b, a.pol_out);
+        tma_store_3d_hint(&map_po, st + P_PN * PANEL, 0, t0, b, a.pol_out);
         tma_store_commit();
         tma_store_wait_read<0>();
         tr.ev(13, i);
@@ -1100,7 +1102,16 @@ static int persist_grid(int want) {
 
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
-  return e != nullptr ? atoi(e) : dflt;
+  return e != nullptr ? (int)strtol(e, nullptr, 0) : dflt;
+}
+// WN_L2HINT: bit mask of the L2 eviction hints on the layer kernels' TMA traffic.  Measured at configs[1] (ms per step
+// for the 30 forward / backward layer launches): none 0.825 / 1.531; forward x' stores EVICT_LAST (4) 0.752 / 1.52 -- the
+// next launch reads x' back (33.5 MB per layer: it fits in the L2 when the single-use z stash does not push it out);
+// forward x[t-dil] loads and z stores EVICT_FIRST (1, 2): no further change; backward Y / P0 loads EVICT_FIRST, stores
+// EVICT_LAST, x[t-dil] loads EVICT_FIRST (8, 16, 32): no change (one layer writes 67 MB and reads another 67 MB).
+static int l2_hint_mask() {
+  static const int m = env_int("WN_L2HINT", 4);
+  return m;
 }
 
 struct LayerMaps {
@@ -1176,6 +1187,12 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
   pa.z_col = l * a.n_dil;
   pa.tile_ctr = reinterpret_cast<int*>(ws + wl.tile_ctr) + 4 * l;
   pa.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
+  {
+    const int h = l2_hint_mask();
+    pa.pol_x0 = (h & 1) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+    pa.pol_z = (h & 2) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+    pa.pol_xout = (h & 4) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+  }
   // stages 5 x 16 KB | z tiles 2 x 8 KB | wc 2 x 4 KB | wr 2 KB
   const size_t smem = 5 * 2 * 8192 + 2 * 8192 + 2 * 4096 + 2048 + 1024;
   const int nblk = persist_grid(std::max(1, std::min(pa.n_tiles, 2 * m->sm_count)));
@@ -1235,6 +1252,12 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
   ProfScope ps(PROF_LAYER_BWD_A, st);
   const bool gc = m->a.n_gc_embed > 0, lc = m->a.n_lc_out > 0;
   ga.T = T;
+  {
+    const int h = l2_hint_mask();
+    ga.pol_in = (h & 8) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+    ga.pol_out = (h & 16) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+    ga.pol_x0 = (h & 32) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+  }
   ga.dz = reinterpret_cast<const bf16*>(ws + m->wl.dz) + (size_t)l * m->n_slots * T * m->a.n_dil;
   if (gc) {
     const int C1 = m->a.n_gc_category + 1;
