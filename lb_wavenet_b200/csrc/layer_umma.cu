@@ -500,16 +500,20 @@ struct LayerBwdFusedArgs {
   const float* params;
   float* grads;
   int64_t sig, gate, res, sig_b, gate_b, res_b;
-  int dil, dil_next, l, has_next, n_tiles, tiles_per_slot, z_plane0;
+  int dil, l, has_next, n_tiles, tiles_per_slot, z_plane0;
+  int n_stages;  // ring depth (what fits beside the carry slots: 6 for dil <= 128)
+  int n_later;   // ceil(dil / 128): how many later tiles' P0 a tile's outputs can reach into
+  int n_carry;   // n_later + 2 carry slots
   const float* gc_tbl;  // global conditioning: this layer's [C1][2D] projection table, else nullptr
   float* dgc_tbl;       // its gradient (fp32 atomics)
   const int32_t* ids;   // [B][T] voice ids
   int C1, T;
-  // local conditioning: this layer's plane [B*T][2D] bf16, read as the conditioning term of the recomputed
-  // pre-activations and OVERWRITTEN in place with dv = [dv_s | dv_g] (each thread writes exactly the bytes it read):
-  // the gradient wrt the plane, consumed by the LC weight / data gradients of phase L + 1
-  bf16* cond;
-  uint64_t pol_x0, pol_in, pol_out;  // L2 eviction hints: x[t-dil] tile (last use of those rows), Y/P0 in, Y/P0 out
+  // local conditioning: this layer's plane [B*T][2D] bf16, the conditioning term of the recomputed pre-activations, and
+  // the plane of the same shape that receives dv = [dv_s | dv_g], the gradient wrt it (consumed by the LC weight / data
+  // gradients of phase L + 1).  Two buffers: a warm-up tile re-reads conditioning rows that belong to another CTA's run.
+  const bf16* cond;
+  bf16* dcond;
+  uint64_t pol_x0, pol_in, pol_out;  // L2 eviction hints: x[t-dil] tile (last use of those rows), dx_{l+1} in, dx_l out
   const bf16* dz;  // this layer's plane of the skip-path gradient, [B * T][D] (read straight from global memory by E1)
   int seq;  // launch sequence number while tracing (tools/trace_layer.py gaps)
   long long* trace;
@@ -582,22 +586,22 @@ __device__ __forceinline__ float warp_transpose_sum8(float (&w)[8], int lane) {
 template <int R, int D, bool GC, bool LC>
 __global__ void __launch_bounds__(896, 1)
 k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dz,
-                       const __grid_constant__ CUtensorMap map_yn, const __grid_constant__ CUtensorMap map_pn,
-                       const __grid_constant__ CUtensorMap map_yo, const __grid_constant__ CUtensorMap map_po,
+                       const __grid_constant__ CUtensorMap map_dxn, const __grid_constant__ CUtensorMap map_dxo,
                        const __grid_constant__ CUtensorMap map_wc, const __grid_constant__ CUtensorMap map_wrn,
                        LayerBwdFusedArgs a) {
   static_assert(R == 32 && D == 32, "tile bookkeeping below assumes 64-byte activation rows");
   constexpr int XB = 64;
   constexpr int PANEL = 128 * XB;                 // 8 KB: one [128 x 32] bf16 tile
-  constexpr int P_X0 = 0, P_X1 = 1, P_YN = 2, P_PN = 3;
-  constexpr int STAGE = 4 * PANEL;                // 32 KB
-  constexpr int NST = 5;
-  constexpr int W_DVS = 0, W_DVG = 1, W_Z = 2;
-  constexpr int WBUF = 3 * PANEL;                 // 24 KB
+  constexpr int P_X0 = 0, P_X1 = 1, P_DX = 2;
+  constexpr int STAGE = 3 * PANEL;                // 24 KB
+  constexpr int MAX_NST = 6;
+  const int NST = a.n_stages;                     // 6 for dil <= 128 (host: what fits beside the carry slots)
+  constexpr int W_DVS = 0, W_DVG = 1, W_Z = 2, W_ONES = 3;
+  constexpr int WBUF = 4 * PANEL;                 // 32 KB: DVs | DVg | Z | constant 1.0
   constexpr int NE1 = 512, NE1G = 256, NE2 = 256;
-  constexpr uint32_t ACC_V = 0, ACC_D = 64, ACC_P = 96, ACC_STRIDE = 160, ACC_W = 320, ACC_B = 416;
+  constexpr uint32_t ACC_V = 0, ACC_D = 64, ACC_P = 96, ACC_STRIDE = 160, ACC_W = 320, ACC_B = 432;
   constexpr uint32_t HI = desc_hi(XB);
-  constexpr int STG_WC = 0, STG_WR = 64 * 65, STG_WR2 = STG_WR + 32 * 33;  // end-of-kernel staging (floats)
+  constexpr int STG_WC = 0, STG_WR = 64 * 65;  // end-of-kernel staging (floats): 21 KB, inside stage 0
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* wb = smem + NST * STAGE;         // [2] work buffers
@@ -605,14 +609,31 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
   unsigned char* wc1 = wc0 + 2 * D * XB;          //                4 KB, directly behind wc0
   unsigned char* wrn = wc1 + 2 * D * XB;          // [D rows][R]    2 KB
   unsigned char* ones = wrn + D * XB;             // 1 KB of bf16 1.0: the B operand (16 timesteps x 16 columns) of queue C
-  float* stg = reinterpret_cast<float*>(smem);    // aliases stage 0 (25 KB of its 32)
-  __shared__ __align__(8) uint64_t w_full, in_full[NST], stage_free[NST], out_ready[NST], v_full[2], acc1_free[2],
-      dv_ready[2], p_full[2], acc2_free[2], g_full;
+  unsigned char* carry = ones + 1024;             // [n_carry] P0 tiles (bf16, SW64 rows) of this and the later tiles
+  float* stg = reinterpret_cast<float*>(smem);    // aliases stage 0
+  __shared__ __align__(8) uint64_t w_full, in_full[MAX_NST], stage_free[MAX_NST], out_ready[MAX_NST], v_full[2],
+      acc1_free[2], dv_ready[2], p_full[2], acc2_free[2], g_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[64];  // SIGNAL_BIAS | 0.5 * GATE_BIAS
-  __shared__ float red_s[32];                 // RESIDUAL_BIAS gradient partials
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_my = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // Work list of this CTA: a contiguous run [j0, j1) of the tiles in (slot, time DEscending) order, preceded by up to
+  // n_later warm-up tiles (the tiles just later in time than the first one: only their P0 is wanted).
+  const int TPS = a.tiles_per_slot;
+  const int j0 = (int)(((long long)blockIdx.x * a.n_tiles) / gridDim.x), j1 = (int)(((long long)(blockIdx.x + 1) * a.n_tiles) / gridDim.x);
+  const int k_first = TPS - 1 - j0 % TPS;
+  const int n_warm = j1 > j0 ? min(a.n_later, TPS - 1 - k_first) : 0;
+  const int n_my = n_warm + (j1 - j0);
+  // every role walks the same item list: (slot, time tile k, warm-up?), time running backwards inside a slot
+  struct Item {
+    int slot, k, warm_left, tps;
+    __device__ __forceinline__ bool warm() const { return warm_left > 0; }
+    __device__ __forceinline__ void next() {
+      if (warm_left > 0) { --warm_left; --k; }
+      else if (k == 0) { k = tps - 1; ++slot; }
+      else --k;
+    }
+  };
+  const Item item0{j0 / TPS, k_first + n_warm, n_warm, TPS};
   pdl_launch_dependents();
   if (a.trace != nullptr && tid == 0) {  // kernel entry (before barrier init / TMEM allocation)
     unsigned long long gt;
@@ -624,10 +645,10 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
   if (tid == 0) {
     mbar_init(&w_full, 1);
     mbar_init(&g_full, 2);
-    for (int i = 0; i < NST; ++i) {
+    for (int i = 0; i < MAX_NST; ++i) {
       mbar_init(&in_full[i], 1);
       mbar_init(&stage_free[i], 1);
-      mbar_init(&out_ready[i], 1);
+      mbar_init(&out_ready[i], 8);  // one arrival per row warp
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&v_full[i], 1);
@@ -638,11 +659,12 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
     }
     fence_mbar_init();
   }
-  if (tid < 32) red_s[tid] = 0.f;
   if (tid < 64)
     bias_s[tid] = tid < 32 ? (a.sig_b >= 0 ? a.params[a.sig_b + tid] : 0.f)
                            : (a.gate_b >= 0 ? 0.5f * a.params[a.gate_b + tid - 32] : 0.f);
   fill_ones(ones, 1024, tid, 896);
+  fill_ones(wb + W_ONES * PANEL, PANEL, tid, 896);
+  fill_ones(wb + WBUF + W_ONES * PANEL, PANEL, tid, 896);
   fence_proxy_async_smem();
 
   if (warp == 1) tmem_alloc(&tmem_base_s, 512);
@@ -669,22 +691,19 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
       tma_load_2d(wc0, &map_wc, &w_full, 0, (a.l * 2 + 0) * 2 * D);
       tma_load_2d(wc1, &map_wc, &w_full, 0, (a.l * 2 + 1) * 2 * D);
       tma_load_2d(wrn, &map_wrn, &w_full, 0, a.l * D);
-      for (int i = 0; i < n_my; ++i) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
+      Item it = item0;
+      for (int i = 0; i < n_my; ++i, it.next()) {
+        const int b = it.slot, t0 = it.k * 128;
         const int s = i % NST;
         unsigned char* st = smem + s * STAGE;
         tr.ev(1, i);
         mbar_wait(&stage_free[s], ((uint32_t)(i / NST) & 1u) ^ 1u);
         tr.ev(2, i);
-        mbar_expect_tx(&in_full[s], (uint32_t)((a.has_next ? 4 : 2) * PANEL));
+        mbar_expect_tx(&in_full[s], (uint32_t)((a.has_next ? 3 : 2) * PANEL));
         tma_prefetch_l2_3d(&map_dz, 0, t0, a.z_plane0 + b);  // E1 reads this tile's dz rows from the L2 a few thousand cycles from now
         tma_load_3d_hint(st + P_X0 * PANEL, &map_x, &in_full[s], 0, t0, b, a.pol_x0);
         tma_load_3d(st + P_X1 * PANEL, &map_x, &in_full[s], 0, t0 + a.dil, b);
-        if (a.has_next) {
-          tma_load_3d_hint(st + P_YN * PANEL, &map_yn, &in_full[s], 0, t0, b, a.pol_in);
-          tma_load_3d_hint(st + P_PN * PANEL, &map_pn, &in_full[s], 0, t0 + a.dil_next, b, a.pol_in);  // rows >= T: zero fill
-        }
+        if (a.has_next) tma_load_3d_hint(st + P_DX * PANEL, &map_dxn, &in_full[s], 0, t0, b, a.pol_in);
       }
     }
   } else if (warp == 1 || warp == 27) {
@@ -696,7 +715,9 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
       mbar_wait(&w_full, 0);
       const uint32_t idv = make_idesc_bf16(128, 2 * D), idd = make_idesc_bf16(128, D);
       const uint32_t idp = make_idesc_bf16(128, 2 * R, false, true);  // A = dv (K-major), B = [W0|W1] (MN-major)
-      const uint32_t idw = make_idesc_bf16(128, 2 * D + R, true, true);
+      // B = [DVs | DVg | Z | 1] (N = 112): the ones columns make column 96 of acc_w the column sums of the A operand, whose
+      // rows 64..95 (dx_{l+1}) are the RESIDUAL_BIAS gradient -- no instruction, no register, no epilogue time spent on it
+      const uint32_t idw = make_idesc_bf16(128, 2 * D + R + 16, true, true);
       // K-major operands: K step of 16 elements = 32 bytes = +2 in the descriptor; MN-major: 16 rows of 64 bytes = +64
       const uint32_t ring_k = desc_lo_k(smem_u32(smem)), ring_mn = desc_lo(smem_u32(smem), PANEL);
       const uint32_t wb_k = desc_lo_k(smem_u32(wb)), wb_mn = desc_lo(smem_u32(wb), PANEL);
@@ -709,21 +730,20 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
       auto issue_a = [&](int i) {  // recomputed pre-activations; residual part of dz
         const int s = i % NST, ab = i & 1;
         const uint32_t x0 = ring_k + (uint32_t)s * (STAGE >> 4), x1 = x0 + (PANEL >> 4);
-        const uint32_t yn = x0 + P_YN * (PANEL >> 4), pn = x0 + P_PN * (PANEL >> 4);
+        const uint32_t dx = x0 + P_DX * (PANEL >> 4);
         const uint32_t av = tm + ab * ACC_STRIDE + ACC_V, ad = tm + ab * ACC_STRIDE + ACC_D;
         mma_bf16_ss2(av, x0, HI, wc0_k, HI, idv, false);
         mma_bf16_ss2(av, x0 + 2, HI, wc0_k + 2, HI, idv, true);
         mma_bf16_ss2(av, x1, HI, wc1_k, HI, idv, true);
         mma_bf16_ss2(av, x1 + 2, HI, wc1_k + 2, HI, idv, true);
-        if (a.has_next) {  // dz(res) = (Y_{l+1} + P0_{l+1}[t + dil]) . RESIDUAL^T : B = RESIDUAL [D rows][R]
-          mma_bf16_ss2(ad, yn, HI, wrn_k, HI, idd, false);
-          mma_bf16_ss2(ad, yn + 2, HI, wrn_k + 2, HI, idd, true);
-          mma_bf16_ss2(ad, pn, HI, wrn_k, HI, idd, true);
-          mma_bf16_ss2(ad, pn + 2, HI, wrn_k + 2, HI, idd, true);
+        if (a.has_next) {  // dz(res) = dx_{l+1} . RESIDUAL^T : B = RESIDUAL [D rows][R]
+          mma_bf16_ss2(ad, dx, HI, wrn_k, HI, idd, false);
+          mma_bf16_ss2(ad, dx + 2, HI, wrn_k + 2, HI, idd, true);
         }
         mma_commit(&v_full[ab]);
       };
-      auto issue_b = [&](int i) {  // data gradient + weight gradients of tile i
+      bool acc_started = false;  // the persistent accumulators (acc_w / acc_b) start with this thread's first real tile
+      auto issue_b = [&](int i) {  // data gradient + (unless it is a warm-up tile) weight gradients of tile i
         const int s = i % NST, ab = i & 1;
         const uint32_t wk = wb_k + (uint32_t)ab * (WBUF >> 4), wm = wb_mn + (uint32_t)ab * (WBUF >> 4);
         const uint32_t sm = ring_mn + (uint32_t)s * (STAGE >> 4);
@@ -733,17 +753,25 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
         mma_bf16_ss2(ap, wk + W_DVS * (PANEL >> 4) + 2, HI, wc_mn + 64, HI, idp, true);
         mma_bf16_ss2(ap, wk + W_DVG * (PANEL >> 4), HI, wc_mn + 128, HI, idp, true);
         mma_bf16_ss2(ap, wk + W_DVG * (PANEL >> 4) + 2, HI, wc_mn + 192, HI, idp, true);
+        if (i >= n_warm) {
+          // A = the stage re-described MN-major with M = 128: rows 0..63 = x[t-dil] | x[t], 64..95 = dx_{l+1}, 96..127 =
+          // whatever follows the stage (never read back)
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // K = 128 timesteps, 16 per instruction
-          mma_bf16_ss2(tm + ACC_W, sm + k * 64, HI, wm + k * 64, HI, idw, (i | k) != 0);
+          for (int k = 0; k < 8; ++k)  // K = 128 timesteps, 16 per instruction
+            mma_bf16_ss2(tm + ACC_W, sm + k * 64, HI, wm + k * 64, HI, idw, acc_started || k != 0);
+          acc_started = true;
+        }
         mma_commit(&p_full[ab]);
       };
       auto issue_c = [&](int i) {  // column sums of dv over the tile's 128 timesteps: [DVs|DVg|Z|..]^T . 1
         const int ab = i & 1;
         const uint32_t wm = wb_mn + (uint32_t)ab * (WBUF >> 4);
+        if (i >= n_warm) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          mma_bf16_ss2(tm + ACC_B, wm + k * 64, HI, ones_mn, HI, idb, (i | k) != 0);
+          for (int k = 0; k < 8; ++k)
+            mma_bf16_ss2(tm + ACC_B, wm + k * 64, HI, ones_mn, HI, idb, acc_started || k != 0);
+          acc_started = true;
+        }
         mma_commit(&p_full[ab]);
       };
       uint32_t spins = 0;
@@ -797,12 +825,15 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
                            (uint32_t)r * 64u + ((((uint32_t)(2 * half + 1)) ^ sw64) << 4)};
     const float4* bs4 = reinterpret_cast<const float4*>(bias_s + 16 * half);
     const float4* bg4 = reinterpret_cast<const float4*>(bias_s + 32 + 16 * half);
-    for (int i = g; i < n_my; i += 2) {
+    Item it = item0;
+    if (g == 1) it.next();
+    for (int i = g; i < n_my; i += 2, it.next(), it.next()) {
       const int ab = g;
       unsigned char* wbuf = wb + ab * WBUF;
       const uint32_t tb = tm + ab * ACC_STRIDE + lane_sel;
-      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-      const int slot = tile / a.tiles_per_slot, tt = (tile % a.tiles_per_slot) * 128 + r;
+      const int slot = it.slot;
+      const bool warm = it.warm();
+      const int tt = it.k * 128 + r;
       // this row's 16 dz values (skip-path gradient, plane l) come straight from global memory: the producer prefetched
       // the tile into the L2 when it issued the stage's loads, and the L2 round trip hides behind the wait for the MMAs.
       // (Requested a whole tile ahead from DRAM instead, the loads made the arithmetic itself ~1000 cycles slower: a
@@ -821,9 +852,11 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
       if constexpr (LC) {
         lcs[0] = lcs[1] = lcg[0] = lcg[1] = make_uint4(0u, 0u, 0u, 0u);
         if (tt < a.T) {
-          lcrow = reinterpret_cast<uint4*>(a.cond + ((size_t)slot * a.T + tt) * (2 * D) + 16 * half);
-          lcs[0] = lcrow[0]; lcs[1] = lcrow[1];
-          lcg[0] = lcrow[D / 8]; lcg[1] = lcrow[D / 8 + 1];
+          const uint4* crow = reinterpret_cast<const uint4*>(a.cond + ((size_t)slot * a.T + tt) * (2 * D) + 16 * half);
+          lcs[0] = crow[0]; lcs[1] = crow[1];
+          lcg[0] = crow[D / 8]; lcg[1] = crow[D / 8 + 1];
+          // dv goes to the gradient plane (a warm-up tile is another CTA's: only its P0 is wanted here)
+          if (!warm) lcrow = reinterpret_cast<uint4*>(a.dcond + ((size_t)slot * a.T + tt) * (2 * D) + 16 * half);
         }
       }
       tr.ev(5, i);
@@ -888,7 +921,7 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
             if (q == 0) { lcg[p].x = pack2(0.5f * dg[0], 0.5f * dg[1]); lcg[p].y = pack2(0.5f * dg[2], 0.5f * dg[3]); }
             else        { lcg[p].z = pack2(0.5f * dg[0], 0.5f * dg[1]); lcg[p].w = pack2(0.5f * dg[2], 0.5f * dg[3]); }
           }
-          if constexpr (GC) {
+          if (GC && !warm) {
             // table gradient: dTbl[id][n] += dv[n] (gate half: dv carries 2x).  A warp is 32 consecutive timesteps of
             // one slot, ids change only at file junctions: reduce over the warp when it is uniform, else per row
             const int id0 = __shfl_sync(0xffffffffu, gid, 0);
@@ -932,10 +965,10 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
     mbar_wait(&g_full, 0);
     tc_fence_after_sync();
     if (n_my > 0) mbar_wait(&stage_free[(n_my - 1) % NST], (uint32_t)((n_my - 1) / NST) & 1u);  // last TMA store drained
-    asm volatile("bar.sync 3, 768;" ::: "memory");  // the row warps have published their RESIDUAL_BIAS partials
+    asm volatile("bar.sync 3, 768;" ::: "memory");  // the row warps are out of the ring too
     if (n_my > 0) {
-      // acc_w[128 x 96]: rows 0..63, columns 0..63 = conv taps (GATE columns carry 2x); rows 64..95 (YN) and 96..127 (PN),
-      // columns 64..95 = the two halves of dx_{l+1}^T . Z = RESIDUAL's gradient, transposed
+      // acc_w[128 x 96]: rows 0..63, columns 0..63 = conv taps (GATE columns carry 2x); rows 64..95, columns 64..95 =
+      // dx_{l+1}^T . Z = RESIDUAL's gradient, transposed
       const float gsc = cq < 2 ? 1.f : 0.5f;
       if (q4 < 2) {
         uint32_t v[16];
@@ -951,13 +984,19 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
           const int64_t off = r < 32 ? a.sig_b : a.gate_b;
           if (off >= 0 && val != 0.f) atomicAdd(a.grads + off + (r & 31), val);
         }
-      } else if (a.has_next) {
+      } else if (q4 == 2 && a.has_next) {
         uint32_t w[8];
         tmem_ld_32x32b_x8(tm + ACC_W + lane_sel + (uint32_t)(2 * D + c0), w);
         tmem_ld_wait();
-        float* dst = stg + (q4 == 2 ? STG_WR : STG_WR2);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[(c0 + j) * 33 + (r & 31)] = __uint_as_float(w[j]);
+        for (int j = 0; j < 8; ++j) stg[STG_WR + (c0 + j) * 33 + (r - 64)] = __uint_as_float(w[j]);
+        if (cq == 0 && a.res_b >= 0) {  // column 96 (every ones column alike): column sums of dx_{l+1} = RESIDUAL_BIAS gradient
+          uint32_t bv[8];
+          tmem_ld_32x32b_x8(tm + ACC_W + lane_sel + (uint32_t)(2 * D + R), bv);
+          tmem_ld_wait();
+          const float val = __uint_as_float(bv[0]);
+          if (val != 0.f) atomicAdd(a.grads + a.res_b + (r - 64), val);
+        }
       }
       asm volatile("bar.sync 5, 512;" ::: "memory");
       // dWc row m = tap*R + rr, column n: n < D -> SIGNAL[tap][rr][n], else GATE[tap][rr][n-D]
@@ -971,94 +1010,109 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
       if (a.has_next) {
         for (int idx = et; idx < 32 * 32; idx += NE1) {
           const int d = idx >> 5, c = idx & 31;
-          const float val = stg[STG_WR + d * 33 + c] + stg[STG_WR2 + d * 33 + c];
+          const float val = stg[STG_WR + d * 33 + c];
           if (val != 0.f) atomicAdd(a.grads + a.res + (size_t)d * R + c, val);
-        }
-        if (et < 32 && a.res_b >= 0) {
-          const float val = red_s[et];
-          if (val != 0.f) atomicAdd(a.grads + a.res_b + et, val);
         }
       }
     }
   } else if (warp < 26) {
-    // ===== row warps: E2 (outputs).  thread <-> (row r, channels [16*rh, +16)), two passes of 8 channels =====
+    // ===== row warps: E2.  thread <-> (row r, channels [16*rh, +16)).
+    //   P0 of this tile (bf16) -> carry slot k mod n_carry; then (not for warm-up tiles)
+    //   dx_l[t] = P1[t] + dx_{l+1}[t] + P0[t + dil] -> the stage's dead X0 panel -> TMA store.
+    //   P0[t + dil] is row (r + dil) mod 128 of tile k + (r + dil) / 128: a carry slot written by this CTA one or more
+    //   tiles ago (time runs backwards here), or just now; beyond the slot's last tile it is zero, which is where the
+    //   gradient stops at the stage boundary (SAVE is a variable, tmodel.py:123-124).
+    //   One TMEM round trip and at most one barrier per tile: in the in-kernel timeline of the first version (two round
+    //   trips, two barriers) this phase took ~3300 cycles per tile and was the bound of the whole kernel.
+    //   Carry hazards: tile i + 1 writes slot (k - 1) mod n_carry, which tile i never reads (n_carry = n_later + 2);
+    //   tile i + 2's MMAs are not issued before every row thread has arrived on acc2_free of tile i, after its reads. =====
     const int q4 = warp & 3, rh = (warp - 18) >> 2;
     const int r = q4 * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    const bool elected = (warp == 18 && lane == 0);
     const uint32_t sw64 = ((uint32_t)r >> 1) & 3u;
     const uint32_t oc[2] = {(uint32_t)r * 64u + ((((uint32_t)(2 * rh)) ^ sw64) << 4),
                             (uint32_t)r * 64u + ((((uint32_t)(2 * rh + 1)) ^ sw64) << 4)};
-    float rsum[16];  // column sums of dx_{l+1}: RESIDUAL_BIAS gradient
-#pragma unroll
-    for (int c = 0; c < 16; ++c) rsum[c] = 0.f;
+    const int NC = a.n_carry;
+    const int rs = r + (a.dil & 127), dq = (a.dil >> 7) + (rs >> 7);   // P0[t + dil]: dq tiles later, row rs & 127
+    const uint32_t rr = (uint32_t)(rs & 127), swr = (rr >> 1) & 3u;
+    const uint32_t ocr[2] = {rr * 64u + ((((uint32_t)(2 * rh)) ^ swr) << 4), rr * 64u + ((((uint32_t)(2 * rh + 1)) ^ swr) << 4)};
+    const bool own_rows = (a.dil & 127) != 0;  // some rows of this tile's outputs need this tile's own P0
+    Item it = item0;
+    int cslot = it.k % NC;  // carry slot of the current tile
     for (int i = 0; i < n_my; ++i) {
       const int s = i % NST, ab = i & 1;
       unsigned char* st = smem + s * STAGE;
-      unsigned char* ynp = st + P_YN * PANEL;  // each thread overwrites exactly the bytes it has just read
-      unsigned char* pnp = st + P_PN * PANEL;
       const uint32_t tb = tm + ab * ACC_STRIDE + lane_sel;
+      const int k = it.k;
+      const bool warm = it.warm();
       tr.ev(9, i);
-      mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);  // (long complete) the TMA-written YN / PN tiles are visible to this thread
+      mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);  // (long complete) the TMA-written DX tile is visible to this thread
       mbar_wait(&p_full[ab], (uint32_t)(i >> 1) & 1u);   // every MMA reading this stage has completed
       tr.ev(10, i);
       tc_fence_after_sync();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t p0[8], p1[8];
-        tmem_ld_32x32b_x8(tb + ACC_P + 16 * rh + 8 * c, p0);
-        tmem_ld_32x32b_x8(tb + ACC_P + R + 16 * rh + 8 * c, p1);
-        uint4 y4 = make_uint4(0u, 0u, 0u, 0u), n4 = make_uint4(0u, 0u, 0u, 0u);
-        if (a.has_next) {  // dx_{l+1} = Y_{l+1}[t] + P0_{l+1}[t + dil]: this thread's own 16 bytes of each tile
-          y4 = *reinterpret_cast<const uint4*>(ynp + oc[c]);
-          n4 = *reinterpret_cast<const uint4*>(pnp + oc[c]);
-        }
-        const uint32_t yw[4] = {y4.x, y4.y, y4.z, y4.w}, pw[4] = {n4.x, n4.y, n4.z, n4.w};
-        tmem_ld_wait();
-        if (c == 1) {
-          tc_fence_before_sync();
-          mbar_arrive(&acc2_free[ab]);
-        }
-        uint32_t oy[4], op[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float lo = __uint_as_float(yw[k] << 16) + __uint_as_float(pw[k] << 16);
-          const float hi = __uint_as_float(yw[k] & 0xffff0000u) + __uint_as_float(pw[k] & 0xffff0000u);
-          rsum[8 * c + 2 * k] += lo;
-          rsum[8 * c + 2 * k + 1] += hi;
-          oy[k] = pack2(__uint_as_float(p1[2 * k]) + lo, __uint_as_float(p1[2 * k + 1]) + hi);   // Y_l = P1 + dx_{l+1}
-          op[k] = pack2(__uint_as_float(p0[2 * k]), __uint_as_float(p0[2 * k + 1]));             // P0_l
-        }
-        *reinterpret_cast<uint4*>(ynp + oc[c]) = make_uint4(oy[0], oy[1], oy[2], oy[3]);
-        *reinterpret_cast<uint4*>(pnp + oc[c]) = make_uint4(op[0], op[1], op[2], op[3]);
+      unsigned char* cw = carry + cslot * PANEL;
+      uint32_t p0[16], p1[16];
+      tmem_ld_32x32b_x16(tb + ACC_P + 16 * rh, p0);
+      if (!warm) tmem_ld_32x32b_x16(tb + ACC_P + R + 16 * rh, p1);
+      uint4 y4[2];
+      y4[0] = y4[1] = make_uint4(0u, 0u, 0u, 0u);
+      if (a.has_next && !warm) {  // dx_{l+1}: this thread's own 2 x 16 bytes
+        y4[0] = *reinterpret_cast<const uint4*>(st + P_DX * PANEL + oc[0]);
+        y4[1] = *reinterpret_cast<const uint4*>(st + P_DX * PANEL + oc[1]);
       }
-      fence_proxy_async_smem();
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&acc2_free[ab]);
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        *reinterpret_cast<uint4*>(cw + oc[c]) =
+            make_uint4(pack2(__uint_as_float(p0[8 * c]), __uint_as_float(p0[8 * c + 1])),
+                       pack2(__uint_as_float(p0[8 * c + 2]), __uint_as_float(p0[8 * c + 3])),
+                       pack2(__uint_as_float(p0[8 * c + 4]), __uint_as_float(p0[8 * c + 5])),
+                       pack2(__uint_as_float(p0[8 * c + 6]), __uint_as_float(p0[8 * c + 7])));
+      if (!warm) {
+        if (own_rows) asm volatile("bar.sync 2, 256;" ::: "memory");  // this tile's P0 rows are visible to every row thread
+        const int kq = k + dq;
+        int rslot = cslot + dq;   // (k + dq) mod NC without a division: dq <= NC - 2
+        if (rslot >= NC) rslot -= NC;
+        const unsigned char* cr = carry + rslot * PANEL;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint4 n4 = make_uint4(0u, 0u, 0u, 0u);
+          if (kq < TPS) n4 = *reinterpret_cast<const uint4*>(cr + ocr[c]);
+          const uint32_t yw[4] = {y4[c].x, y4[c].y, y4[c].z, y4[c].w}, pw[4] = {n4.x, n4.y, n4.z, n4.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            o[kk] = pack2(__uint_as_float(p1[8 * c + 2 * kk]) + __uint_as_float(yw[kk] << 16) + __uint_as_float(pw[kk] << 16),
+                          __uint_as_float(p1[8 * c + 2 * kk + 1]) + __uint_as_float(yw[kk] & 0xffff0000u) +
+                              __uint_as_float(pw[kk] & 0xffff0000u));
+          *reinterpret_cast<uint4*>(st + P_X0 * PANEL + oc[c]) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        fence_proxy_async_smem();
+      }
       tr.ev(11, i);
-      asm volatile("bar.sync 2, 256;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&out_ready[s]);
       tr.ev(12, i);
-      if (elected) mbar_arrive(&out_ready[s]);
-    }
-    if (a.has_next && a.res_b >= 0) {
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float v = warp_sum(rsum[c]);
-        if (lane == 0) atomicAdd(&red_s[16 * rh + c], v);
-      }
+      it.next();
+      cslot = (it.k == TPS - 1) ? (TPS - 1) % NC : (cslot == 0 ? NC - 1 : cslot - 1);
     }
     asm volatile("bar.sync 3, 768;" ::: "memory");
   } else {
-    // ===== TMA-store issuer: the only thread that touches the store path; returns the stage to the ring =====
+    // ===== warp 26: TMA-store issuer (the only thread that touches the store path; returns the stage to the ring).
+    // (The RESIDUAL_BIAS column sums were tried here, on the otherwise idle lanes, from the stage's DX panel: the stage
+    // was then held ~1000 cycles longer per tile, 1.47 -> 1.59 ms for the 30 layers.) =====
     if (lane == 0) {
-      for (int i = 0; i < n_my; ++i) {
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-        const int b = tile / a.tiles_per_slot, t0 = (tile % a.tiles_per_slot) * 128;
+      Item it = item0;
+      for (int i = 0; i < n_my; ++i, it.next()) {
         const int s = i % NST;
-        unsigned char* st = smem + s * STAGE;
         mbar_wait(&out_ready[s], (uint32_t)(i / NST) & 1u);
-        tma_store_3d_hint(&map_yo, st + P_YN * PANEL, 0, t0, b, a.pol_out);
-        tma_store_3d_hint(&map_po, st + P_PN * PANEL, 0, t0, b, a.pol_out);
-        tma_store_commit();
-        tma_store_wait_read<0>();
+        if (!it.warm()) {
+          tma_store_3d_hint(&map_dxo, smem + s * STAGE + P_X0 * PANEL, 0, it.k * 128, it.slot, a.pol_out);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+        }
         tr.ev(13, i);
         mbar_arrive(&stage_free[s]);
       }
@@ -1117,9 +1171,10 @@ static int l2_hint_mask() {
 struct LayerMaps {
   const void* ws = nullptr;
   const void* model = nullptr;
+  uint64_t serial = 0;  // wn_model::serial: a new model can be allocated at a freed model's address
   int T = -1;
   std::vector<CUtensorMap> x;  // per layer: xfull_l [B][dil+T][R]
-  CUtensorMap z, wc, wr, dx[2], p0[2], dz, wrn;
+  CUtensorMap z, wc, wr, dx[2], dz, wrn;
 };
 
 bool umma_layer_supported(const wn_model* m) {
@@ -1131,7 +1186,8 @@ bool umma_layer_supported(const wn_model* m) {
 static LayerMaps* get_maps(wn_model* m, unsigned char* ws, int T, int* rc) {
   static thread_local LayerMaps cache;  // one model per process in practice; re-encoded when ws/T change
   *rc = WN_OK;
-  if (cache.model == m && cache.ws == ws && cache.T == T && (int)cache.x.size() == m->L) return &cache;
+  if (cache.model == m && cache.serial == m->serial && cache.ws == ws && cache.T == T && (int)cache.x.size() == m->L)
+    return &cache;
   cache.model = nullptr;
   const WorkspaceLayout& wl = m->wl;
   const wn_arch& a = m->a;
@@ -1145,7 +1201,6 @@ static LayerMaps* get_maps(wn_model* m, unsigned char* ws, int T, int* rc) {
   if ((*rc = map2ds(&cache.wr, ws + wl.wrT, D, (uint64_t)m->L * R, (uint32_t)D, (uint32_t)R, (int)D * 2))) return nullptr;
   for (int i = 0; i < 2; ++i) {
     if ((*rc = map3d(&cache.dx[i], ws + wl.dx[i], R, (uint64_t)T, B, (uint32_t)R, 128, (int)R * 2))) return nullptr;
-    if ((*rc = map3d(&cache.p0[i], ws + wl.p0[i], R, (uint64_t)T, B, (uint32_t)R, 128, (int)R * 2))) return nullptr;
   }
   // dz: per-layer planes [L][B][T][D]; the outer TMA coordinate is l * B + slot
   if ((*rc = map3d(&cache.dz, ws + wl.dz, D, (uint64_t)T, (uint64_t)m->L * B, (uint32_t)D, 128, (int)D * 2))) return nullptr;
@@ -1153,6 +1208,7 @@ static LayerMaps* get_maps(wn_model* m, unsigned char* ws, int T, int* rc) {
   cache.ws = ws;
   cache.T = T;
   cache.model = m;
+  cache.serial = m->serial;
   return &cache;
 }
 
@@ -1222,7 +1278,7 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
 
 bool umma_bwd_fused_supported(const wn_model* m) { return umma_layer_supported(m); }
 
-// whole backward of layer l: reads (Y, P0)[(l+1) & 1], writes (Y, P0)[l & 1]; Y lives in dxbuf, P0 in p0buf
+// whole backward of layer l: reads dx_{l+1} from dxbuf[(l+1) & 1], writes dx_l to dxbuf[l & 1]
 int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned char* ws, const int32_t* d_ids, int T, int l,
                                 float* d_grads, cudaStream_t st) {
   int rc;
@@ -1237,16 +1293,22 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
   ga.sig_b = ld.sig_b; ga.gate_b = ld.gate_b; ga.res_b = ld.res_b;
   ga.dil = ld.dil; ga.l = l;
   ga.has_next = (l + 1 < m->L);
-  ga.dil_next = ga.has_next ? m->layers[l + 1].dil : 0;
   ga.tiles_per_slot = (T + 127) / 128;
   ga.n_tiles = ga.tiles_per_slot * m->n_slots;
   ga.z_plane0 = l * m->n_slots;
   ga.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
   static int trace_seq = 0;
   if (ga.trace != nullptr) ga.seq = trace_seq++;
-  // ring 5 x 32 KB | work buffers 2 x 24 KB | wc 2 x 4 KB | RESIDUAL 2 KB
-  // (+ 1 KB of ones)
-  const size_t smem = 4 * 5 * 8192 + 2 * 3 * 8192 + 2 * 4096 + 2048 + 1024 + 1024;
+  // ring n_stages x 24 KB | work buffers 2 x 32 KB | wc 2 x 4 KB | RESIDUAL 2 KB | ones 1 KB | carry n_carry x 8 KB
+  ga.n_later = (ld.dil + 127) / 128;
+  ga.n_carry = ga.n_later + 2;  // one spare: the next tile's P0 never lands in a slot the current tile still reads
+  const int fixed = 2 * 4 * 8192 + 2 * 4096 + 2048 + 1024 + ga.n_carry * 8192 + 1024;
+  ga.n_stages = std::min(6, (232448 /* 227 KB per CTA on sm_100 */ - 2048 - fixed) / (3 * 8192));
+  if (ga.n_stages < 2) {
+    set_error("layer backward: dilation %d needs %d carry tiles, more than shared memory holds", ld.dil, ga.n_carry);
+    return WN_ERR_UNSUPPORTED;
+  }
+  const size_t smem = (size_t)ga.n_stages * 3 * 8192 + fixed;
   const int grid = persist_grid(std::max(1, std::min(ga.n_tiles, m->sm_count)));
   const int nx = (l + 1) & 1, cu = l & 1;
   ProfScope ps(PROF_LAYER_BWD_A, st);
@@ -1266,13 +1328,16 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
     ga.ids = d_ids;
     ga.C1 = C1;
   }
-  if (lc) ga.cond = reinterpret_cast<bf16*>(ws + m->wl.cond) + (size_t)l * m->n_slots * T * 2 * m->a.n_dil;
+  if (lc) {
+    ga.cond = reinterpret_cast<const bf16*>(ws + m->wl.cond) + (size_t)l * m->n_slots * T * 2 * m->a.n_dil;
+    ga.dcond = reinterpret_cast<bf16*>(ws + m->wl.dcond) + (size_t)l * m->n_slots * T * 2 * m->a.n_dil;
+  }
 #define WN_BWD(GC_, LC_)                                                                                                  \
   {                                                                                                                       \
     WN_CUDA_CHECK(cudaFuncSetAttribute(k_layer_bwd_fused_umma<32, 32, GC_, LC_>,                                          \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
     WN_CUDA_CHECK(launch_pdl(k_layer_bwd_fused_umma<32, 32, GC_, LC_>, grid, 896, smem, st, mp->x[l], mp->dz,             \
-                             mp->dx[nx], mp->p0[nx], mp->dx[cu], mp->p0[cu], mp->wc, mp->wrn, ga));                       \
+                             mp->dx[nx], mp->dx[cu], mp->wc, mp->wrn, ga));                                               \
   }
   if (gc && lc) WN_BWD(true, true)
   else if (gc) WN_BWD(true, false)

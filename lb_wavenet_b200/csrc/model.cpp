@@ -2,6 +2,7 @@
 // Needs no GPU (CPU tests call it to check names/shapes against the reference contract).
 #include "model.h"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -61,8 +62,6 @@ const WorkspaceLayout& workspace_layout(wn_model* m, int32_t T) {
   w.dv = take(rows * 2 * D * 2);
   w.dx[0] = take(rows * R * 2);
   w.dx[1] = take(rows * R * 2);
-  w.p0[0] = take(rows * R * 2);
-  w.p0[1] = take(rows * R * 2);
   const int64_t gc_elems = a.n_gc_embed > 0 ? L * (int64_t)(a.n_gc_category + 1) * 2 * D : 0;
   w.gc_tbl = take(gc_elems * 4);
   w.dgc_tbl = take(gc_elems * 4);
@@ -79,7 +78,7 @@ const WorkspaceLayout& workspace_layout(wn_model* m, int32_t T) {
   w.wdP = take(L * R * 4 * D * 2);
   for (int i = 0; i < 9; ++i) w.lc_x[i] = w.lc_dx[i] = 0;
   for (int i = 0; i < 8; ++i) w.lc_wup[i] = w.lc_wupT[i] = 0;
-  w.cond = w.lc_wcat = w.lc_wcatT = w.lc_gtmp = 0;
+  w.cond = w.dcond = w.lc_wcat = w.lc_wcatT = w.lc_gtmp = 0;
   if (a.n_lc_out > 0) {
     const int64_t LCP = 128;
     int64_t r = rows / m->lc_hop, gt = L * LCP * 2 * D;
@@ -94,6 +93,7 @@ const WorkspaceLayout& workspace_layout(wn_model* m, int32_t T) {
       }
     }
     w.cond = take(L * rows * 2 * D * 2);
+    w.dcond = take(L * rows * 2 * D * 2);
     w.lc_wcat = take(L * 2 * D * LCP * 2);
     w.lc_wcatT = take(L * 2 * D * LCP * 2);
     w.lc_gtmp = take(gt * 4);
@@ -177,6 +177,10 @@ int wn_model_create(const wn_arch* arch, int32_t n_slots, wn_model** out) {
   }
 
   wn_model* m = new wn_model();
+  {
+    static std::atomic<uint64_t> next_serial{1};
+    m->serial = next_serial.fetch_add(1);
+  }
   m->a = a;
   m->n_slots = n_slots;
   m->L = a.n_blocks * a.n_block_layers;

@@ -46,7 +46,6 @@ struct WorkspaceLayout {
   int64_t dz;         // [L][B*T][D] bf16: per-layer planes (dense 64-byte rows for the layer backward)
   int64_t dv;         // [B*T][2D] bf16
   int64_t dx[2];      // [B*T][R] bf16 ping/pong: data gradient (GC path) / its Y part (fused backward)
-  int64_t p0[2];      // [B*T][R] bf16 ping/pong: P0 part of the split data gradient dx[t] = Y[t] + P0[t+dil]
   int64_t gc_tbl;     // [L][C+1][2D] fp32 (GC projections incl. nothing else)
   int64_t dgc_tbl;    // same shape, gradient
   int64_t skip_bias;  // [S] fp32, sum over layers of SKIP_BIAS
@@ -63,7 +62,8 @@ struct WorkspaceLayout {
   // beyond n_lc_in / n_lc_out are zero.  lc_x[0] = mel frames, lc_x[i + 1] = output of upsampling level i.
   int64_t lc_x[9];           // [B * T_i][128] bf16, T_i = T / hop * prod(s_0 .. s_{i-1})
   int64_t lc_dx[9];          // gradients of the same (index 0 unused)
-  int64_t cond;              // [L][B*T][2D] bf16: lc_up . [LC_SIGNAL_l | LC_GATE_l]; the layer backward overwrites it with dv
+  int64_t cond;              // [L][B*T][2D] bf16: lc_up . [LC_SIGNAL_l | LC_GATE_l]
+  int64_t dcond;             // [L][B*T][2D] bf16: its gradient, dv_l, written by the layer backward
   int64_t lc_wup[8];         // [s_i * 128][128] bf16: B operand of level i  (row k * 128 + o, column c) = LC_UPSAMPLE_i[k][o][c]
   int64_t lc_wupT[8];        // [128][s_i * 128] bf16: its transpose, B operand of the level's data gradient
   int64_t lc_wcat;           // [L * 2D][128] bf16: row l * 2D + n = (LC_SIGNAL_l | LC_GATE_l)[c][n]
@@ -77,6 +77,7 @@ struct WorkspaceLayout {
 
 struct wn_model {
   wn_arch a;
+  uint64_t serial;  // unique per wn_model_create in this process: keys caches that must not survive a reused address
   int32_t n_slots;
   int32_t L;
   std::vector<wn::ParamEntry> params;

@@ -1416,7 +1416,7 @@ int wn_train_backward_phases(wn_model* m, const float* d_params, const int32_t* 
     const int per_sm = esm <= 96 * 1024 ? 2 : 1;
     const int nblk = (int)std::min<int64_t>(std::min(per_sm * m->sm_count, WN_EMBED_PARTS), (d.rows + 1023) / 1024);
     const int64_t rpc = (d.rows + nblk - 1) / nblk;
-    const bf16* p0 = fused ? reinterpret_cast<const bf16*>(ws + wl.p0[0]) : nullptr;
+    const bf16* p0 = nullptr;  // (the fused backward hands over the merged dx_0 as every other path does)
     float* part = reinterpret_cast<float*>(ws + wl.embed_part);
     k_embed_bwd<<<nblk, 1024, esm, st>>>(dx_next, p0, m->layers[0].dil, T, d_wav, part, d.rows, d.R, d.Q, rpc, ncopy);
     WN_LAUNCH_CHECK();
@@ -1507,27 +1507,24 @@ int wn_debug_read(wn_model* m, const void* d_ws, int32_t T, int32_t what, int32_
     case 2: src = reinterpret_cast<const bf16*>(ws + wl.h1); ncols = d.S; ld = d.S; break;
     case 3: src = reinterpret_cast<const bf16*>(ws + wl.h2); ncols = d.P; ld = d.P; break;
     case 4: src = reinterpret_cast<const bf16*>(ws + wl.dlogits); ncols = d.Q; ld = d.Q; break;
-    case 5:  // gradient wrt the layer-0 input; the fused backward keeps it as Y[t] + P0[t + dil_0]
+    case 5:  // gradient wrt the layer-0 input
       src = reinterpret_cast<const bf16*>(ws + wl.dx[0]); ncols = d.R; ld = d.R;
-      if (umma_bwd_fused_supported(m)) {
-        add = reinterpret_cast<const bf16*>(ws + wl.p0[0]);
-        add_shift = m->layers[0].dil;
-      }
       break;
     case 6:  // dz plane of `layer` ([L][B*T][D]): the skip-path gradient after phase 0 (the wide-layer backward adds the
              // residual part in place while it differentiates that layer)
       if (layer < 0 || layer >= d.L) { set_error("wn_debug_read: bad layer"); return WN_ERR_INVALID; }
       src = reinterpret_cast<const bf16*>(ws + wl.dz) + (size_t)layer * d.rows * d.D; ncols = d.D; ld = d.D;
       break;
-    case 7:  // raw data-gradient buffer of parity `layer` & 1: Y_l of the fused backward, dx_l on the other paths
+    case 7:  // data-gradient buffer of parity `layer` & 1: dx_l right after layer l's backward
       src = reinterpret_cast<const bf16*>(ws + wl.dx[layer & 1]); ncols = d.R; ld = d.R;
       break;
-    case 8:  // raw P0 buffer of parity `layer` & 1 (fused backward: dx_l[t] = Y_l[t] + P0_l[t + dil_l])
-      src = reinterpret_cast<const bf16*>(ws + wl.p0[layer & 1]); ncols = d.R; ld = d.R;
-      break;
-    case 9:  // local-conditioning plane of `layer` [., ., 2 n_dil]: the projections after the forward, dv after that layer's backward
+    case 9:  // local-conditioning plane of `layer` [., ., 2 n_dil]: the projections lc_up . [LC_SIGNAL_l | LC_GATE_l]
       if (layer < 0 || layer >= d.L || m->a.n_lc_out == 0) { set_error("wn_debug_read: bad layer / no local conditioning"); return WN_ERR_INVALID; }
       src = reinterpret_cast<const bf16*>(ws + wl.cond) + (size_t)layer * d.rows * 2 * d.D; ncols = 2 * d.D; ld = 2 * d.D;
+      break;
+    case 11:  // gradient wrt that plane (dv_l), after layer `layer`'s backward
+      if (layer < 0 || layer >= d.L || m->a.n_lc_out == 0) { set_error("wn_debug_read: bad layer / no local conditioning"); return WN_ERR_INVALID; }
+      src = reinterpret_cast<const bf16*>(ws + wl.dcond) + (size_t)layer * d.rows * 2 * d.D; ncols = 2 * d.D; ld = 2 * d.D;
       break;
     case 10:  // upsampled local conditioning [., ., 128] (channels >= n_lc_out are zero)
       if (m->a.n_lc_out == 0) { set_error("wn_debug_read: no local conditioning"); return WN_ERR_INVALID; }

@@ -2040,16 +2040,16 @@ int launch_lc_bwd(wn_model* m, unsigned char* ws, int T, float* d_grads, cudaStr
   float* gtmp = reinterpret_cast<float*>(ws + wl.lc_gtmp);
   WN_CUDA_CHECK(cudaMemsetAsync(gtmp, 0, sizeof(float) * gt, st));
   const bf16* lc_up = reinterpret_cast<const bf16*>(ws + wl.lc_x[n]);
-  const bf16* cond = reinterpret_cast<const bf16*>(ws + wl.cond);
+  const bf16* dcond = reinterpret_cast<const bf16*>(ws + wl.dcond);
   for (int l = 0; l < m->L; ++l)
-    if ((rc = launch_wgrad_umma(m, lc_up, LCP, 0, LCP, cond + (size_t)l * rows * D2, D2, D2, rows,
+    if ((rc = launch_wgrad_umma(m, lc_up, LCP, 0, LCP, dcond + (size_t)l * rows * D2, D2, D2, rows,
                                 gtmp + (size_t)l * LCP * D2, D2, 0, nullptr, st)))
       return rc;
   GemmUmmaArgs ga;
   memset(&ga, 0, sizeof(ga));
   ga.mode = 7;
   ga.a_planes = 1;
-  if ((rc = launch_gemm_umma(m, ws + wl.cond, m->L * D2, ws + wl.lc_wcatT, LCP, ws + wl.lc_dx[n], rows, ga, st))) return rc;
+  if ((rc = launch_gemm_umma(m, ws + wl.dcond, m->L * D2, ws + wl.lc_wcatT, LCP, ws + wl.lc_dx[n], rows, ga, st))) return rc;
   std::vector<int64_t> rws(n + 1);
   rws[0] = rows / m->lc_hop;
   for (int i = 0; i < n; ++i) rws[i + 1] = rws[i] * a.lc_upsample[i];

@@ -220,7 +220,7 @@ class TrainEngine:
         torch = self.torch
         a = self.reg.arch
         ncols = {0: a["n_res"], 1: a["n_dil"], 2: a["n_skip"], 3: a["n_post"], 4: a["n_quant"], 5: a["n_res"],
-                 6: a["n_dil"], 7: a["n_res"], 8: a["n_res"], 9: 2 * a["n_dil"], 10: 128}[what]
+                 6: a["n_dil"], 7: a["n_res"], 9: 2 * a["n_dil"], 10: 128, 11: 2 * a["n_dil"]}[what]
         out = torch.empty(self.reg.n_slots, self.ws_T, ncols, dtype=torch.float32, device=self.device)
         check(self.lib.wn_debug_read(self.reg.handle, ptr(self.ws), self.ws_T, what, layer, ptr(out),
                                      _lib.cur_stream()), "wn_debug_read")

@@ -112,7 +112,7 @@ def test_full_stage_length_vs_oracle(lib, arch, B, T):
                                       (util.TINY_NOBIAS, 2, 200)],
                          ids=["3x10", "arch1_5x10_gc", "wide_1x10", "tiny_nobias"])
 def test_every_layer_in_isolation(lib, arch, B, T):
-    """One layer at a time, at every depth: the kernel's z_l, x_{l+1} (forward) and Y_l / P0_l / dx_l, filter and bias
+    """One layer at a time, at every depth: the kernel's z_l, x_{l+1} (forward) and dx_l, filter and bias
     gradients (backward, issued phase by phase) against the fp64 statement of that single layer (oracle.layer_single,
     reference tmodel.py:117-184,325) evaluated on the KERNEL's own inputs of the layer -- x_l, the skip-path dz_l,
     dx_{l+1}.  No error compounds across layers, so the bound is the bf16 output rounding plus tanh.approx: 1e-2 rel-L2
@@ -129,7 +129,6 @@ def test_every_layer_in_isolation(lib, arch, B, T):
     it = torch.as_tensor(ids).long()
     L = a.n_layers
     dils = a.dilations()
-    fused = arch["n_res"] == 32 and arch["n_dil"] == 32   # split data gradient (layer_umma.cu)
     rd = lambda what, l: eng.debug_read(what, l).double().cpu()
     x = [rd(0, l) for l in range(L)]
     z = [rd(1, l) for l in range(L)]
@@ -154,18 +153,7 @@ def test_every_layer_in_isolation(lib, arch, B, T):
         eng.backward_phases(L - l, L - l + 1)
         torch.cuda.synchronize()
         o = O.layer_single(a, pt, l, full[l], it, dz_skip[l], dx_next)
-        if fused:
-            Y, P0 = rd(7, l), rd(8, l)
-            chk("Y:%d" % l, Y, o["Y"])
-            if T > dils[l]:
-                chk("P0:%d" % l, P0[:, dils[l]:], o["P0"][:, dils[l]:])   # rows < dil feed the SAVE prefix: never read
-            dx = Y.clone()
-            if T > dils[l]:
-                dx[:, :T - dils[l]] += P0[:, dils[l]:]
-            # what the next kernel consumes: the merged tile, rounded to bf16 (layer 0's feeds the PRE gather unrounded)
-            dx_next = dx.float().to(torch.bfloat16).double() if l > 0 else dx
-        else:
-            dx_next = rd(7, l)
+        dx_next = rd(7, l)   # what the next kernel consumes: dx_l, bf16
         chk("dx:%d" % l, dx_next, o["dx"])
         sfx = "%d_%d" % a.layer_ids()[l]
         for nm in ("SIGNAL", "GATE", "RESIDUAL", "SIGNAL_BIAS", "GATE_BIAS", "RESIDUAL_BIAS"):
