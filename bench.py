@@ -494,10 +494,10 @@ def main():
     # ALGORITHMIC HBM bytes per timestep (bf16), independent of how the kernel stores its intermediates:
     #   layer_fwd : read x_l (R), write z_l (D) and x_{l+1} (R)                      = 192 B per layer at R = D = 32
     #   layer_bwd : read x_l (R), dz_l (D), dx_{l+1} (R), write dx_l (R)             = 256 B per layer
-    # (the fused backward's split form dx = Y + P0 moves 384 B: reported as implementation_bytes_per_launch)
+    # (the fused backward also re-reads x_l shifted by dil, an L2 hit: 320 B, reported as implementation_bytes_per_launch)
     hbm_by_cat = {"layer_fwd": L_ * (2 * R_ + D_) * 2, "layer_bwd": L_ * (3 * R_ + D_) * 2,
                   "layer_bwd_data": L_ * (4 * D_ + 2 * R_) * 2}
-    impl_by_cat = {"layer_bwd": L_ * (5 * R_ + D_) * 2} if R_ < 64 else {}
+    impl_by_cat = {"layer_bwd": L_ * (4 * R_ + D_) * 2} if R_ < 64 else {}
     tensor_bound = ("post_fwd_loss", "post_bwd", "wgrad") + (("layer_fwd", "layer_bwd", "layer_bwd_data") if R_ >= 64 else ())
     roofline = None
     if dom is not None:

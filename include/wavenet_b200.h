@@ -152,11 +152,11 @@ int wn_l2_loss(wn_model* m, const float* d_params, double* d_stats, void* stream
 /* test/debug taps into the stash written by the last wn_train_forward / backward:
  * what: 0 = x_l (layer input, [n_slots, T, n_res]), 1 = z_l ([n_slots, T, n_dil]),
  *       2 = h1 ([n_slots,T,n_skip]), 3 = h2 ([n_slots,T,n_post]), 4 = dlogits [.,.,n_quant],
- *       5 = dx_0 (gradient wrt layer-0 input), 6 = dz plane of `layer` [., ., n_dil], 7 / 8 = the raw data-gradient
- *       buffers of parity layer & 1 (Y_l / P0_l of the fused backward: dx_l[t] = Y_l[t] + P0_l[t + dil_l]; dx_l itself in
- *       buffer 7 on the other paths) -- readable between wn_train_backward_phases calls, 9 = local-conditioning plane of
- *       `layer` [., ., 2 n_dil] (projections after the forward, dv after that layer's backward), 10 = upsampled local
- *       conditioning [., ., 128] ; converted to fp32 into d_out */
+ *       5 = dx_0 (gradient wrt layer-0 input), 6 = dz plane of `layer` [., ., n_dil], 7 = the data-gradient buffer of
+ *       parity layer & 1 (dx_l right after layer l's backward) -- readable between wn_train_backward_phases calls,
+ *       9 = local-conditioning plane of `layer` [., ., 2 n_dil] (the projections lc_up . [LC_SIGNAL_l | LC_GATE_l]),
+ *       10 = upsampled local conditioning [., ., 128], 11 = gradient wrt plane 9 (dv_l, after that layer's backward);
+ *       converted to fp32 into d_out */
 int wn_debug_read(wn_model* m, const void* d_ws, int32_t slice_sz, int32_t what, int32_t layer,
                   float* d_out, void* stream);
 
