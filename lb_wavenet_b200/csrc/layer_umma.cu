@@ -609,7 +609,8 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
   unsigned char* wc1 = wc0 + 2 * D * XB;          //                4 KB, directly behind wc0
   unsigned char* wrn = wc1 + 2 * D * XB;          // [D rows][R]    2 KB
   unsigned char* ones = wrn + D * XB;             // 1 KB of bf16 1.0: the B operand (16 timesteps x 16 columns) of queue C
-  unsigned char* carry = ones + 1024;             // [n_carry] P0 tiles (bf16, SW64 rows) of this and the later tiles
+  unsigned char* idn = ones + 1024;               // [64 rows][32] bf16, K-major: rows 0..31 zero, rows 32..63 the identity
+  unsigned char* carry = idn + 4096;              // [n_carry] P0 tiles (bf16, SW64 rows) of this and the later tiles
   float* stg = reinterpret_cast<float*>(smem);    // aliases stage 0
   __shared__ __align__(8) uint64_t w_full, in_full[MAX_NST], stage_free[MAX_NST], out_ready[MAX_NST], v_full[2],
       acc1_free[2], dv_ready[2], p_full[2], acc2_free[2], g_full;
@@ -665,6 +666,14 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
   fill_ones(ones, 1024, tid, 896);
   fill_ones(wb + W_ONES * PANEL, PANEL, tid, 896);
   fill_ones(wb + WBUF + W_ONES * PANEL, PANEL, tid, 896);
+  if (tid < 256) {  // [0 | I]: contracted against the DX tile it adds dx_{l+1} onto the P1 half of acc_p (exact: 1.0 x bf16)
+    const int n = tid >> 2, ch = tid & 3;
+    const int e = (n - 32) & 7, wi = e >> 1;
+    const bool hit = n >= 32 && ch == ((n - 32) >> 3);
+    const uint32_t one = 0x3f80u << (16 * (e & 1));
+    *reinterpret_cast<uint4*>(idn + swizzled_offset((uint32_t)n, (uint32_t)(ch * 16), 64)) =
+        make_uint4(hit && wi == 0 ? one : 0u, hit && wi == 1 ? one : 0u, hit && wi == 2 ? one : 0u, hit && wi == 3 ? one : 0u);
+  }
   fence_proxy_async_smem();
 
   if (warp == 1) tmem_alloc(&tmem_base_s, 512);
@@ -723,7 +732,7 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
       const uint32_t wb_k = desc_lo_k(smem_u32(wb)), wb_mn = desc_lo(smem_u32(wb), PANEL);
       const uint32_t wc0_k = desc_lo_k(smem_u32(wc0)), wc1_k = desc_lo_k(smem_u32(wc1));
       const uint32_t wc_mn = desc_lo(smem_u32(wc0), 2 * D * XB);  // chunk 0 = wc0 (-> P0), chunk 1 = wc1 (-> Y)
-      const uint32_t wrn_k = desc_lo_k(smem_u32(wrn));
+      const uint32_t wrn_k = desc_lo_k(smem_u32(wrn)), idn_k = desc_lo_k(smem_u32(idn));
       // queue C: A = the work buffer re-described MN-major with M = 128 (rows 0..63 = dv channels; 64..95 = z and 96..127
       // = whatever follows the buffer: never read back), B = 16 rows of ones, the same 1 KB for every K step
       const uint32_t idb = make_idesc_bf16(128, 16, true, true), ones_mn = desc_lo(smem_u32(ones), PANEL);
@@ -753,6 +762,11 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
         mma_bf16_ss2(ap, wk + W_DVS * (PANEL >> 4) + 2, HI, wc_mn + 64, HI, idp, true);
         mma_bf16_ss2(ap, wk + W_DVG * (PANEL >> 4), HI, wc_mn + 128, HI, idp, true);
         mma_bf16_ss2(ap, wk + W_DVG * (PANEL >> 4) + 2, HI, wc_mn + 192, HI, idp, true);
+        if (a.has_next && i >= n_warm) {  // P1 += dx_{l+1} . [0 | I]: the row warps never touch the DX tile
+          const uint32_t dx = ring_k + (uint32_t)s * (STAGE >> 4) + P_DX * (PANEL >> 4);
+          mma_bf16_ss2(ap, dx, HI, idn_k, HI, idv, true);
+          mma_bf16_ss2(ap, dx + 2, HI, idn_k + 2, HI, idv, true);
+        }
         if (i >= n_warm) {
           // A = the stage re-described MN-major with M = 128: rows 0..63 = x[t-dil] | x[t], 64..95 = dx_{l+1}, 96..127 =
           // whatever follows the stage (never read back)
@@ -1018,7 +1032,8 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
   } else if (warp < 26) {
     // ===== row warps: E2.  thread <-> (row r, channels [16*rh, +16)).
     //   P0 of this tile (bf16) -> carry slot k mod n_carry; then (not for warm-up tiles)
-    //   dx_l[t] = P1[t] + dx_{l+1}[t] + P0[t + dil] -> the stage's dead X0 panel -> TMA store.
+    //   dx_l[t] = P1[t] (dx_{l+1}[t] included: two identity MMAs of queue B) + P0[t + dil] -> the stage's dead X0 panel
+    //   -> TMA store.
     //   P0[t + dil] is row (r + dil) mod 128 of tile k + (r + dil) / 128: a carry slot written by this CTA one or more
     //   tiles ago (time runs backwards here), or just now; beyond the slot's last tile it is zero, which is where the
     //   gradient stops at the stage boundary (SAVE is a variable, tmodel.py:123-124).
@@ -1046,7 +1061,6 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
       const int k = it.k;
       const bool warm = it.warm();
       tr.ev(9, i);
-      mbar_wait(&in_full[s], (uint32_t)(i / NST) & 1u);  // (long complete) the TMA-written DX tile is visible to this thread
       mbar_wait(&p_full[ab], (uint32_t)(i >> 1) & 1u);   // every MMA reading this stage has completed
       tr.ev(10, i);
       tc_fence_after_sync();
@@ -1054,12 +1068,6 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
       uint32_t p0[16], p1[16];
       tmem_ld_32x32b_x16(tb + ACC_P + 16 * rh, p0);
       if (!warm) tmem_ld_32x32b_x16(tb + ACC_P + R + 16 * rh, p1);
-      uint4 y4[2];
-      y4[0] = y4[1] = make_uint4(0u, 0u, 0u, 0u);
-      if (a.has_next && !warm) {  // dx_{l+1}: this thread's own 2 x 16 bytes
-        y4[0] = *reinterpret_cast<const uint4*>(st + P_DX * PANEL + oc[0]);
-        y4[1] = *reinterpret_cast<const uint4*>(st + P_DX * PANEL + oc[1]);
-      }
       tmem_ld_wait();
       tc_fence_before_sync();
       mbar_arrive(&acc2_free[ab]);
@@ -1080,13 +1088,12 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
         for (int c = 0; c < 2; ++c) {
           uint4 n4 = make_uint4(0u, 0u, 0u, 0u);
           if (kq < TPS) n4 = *reinterpret_cast<const uint4*>(cr + ocr[c]);
-          const uint32_t yw[4] = {y4[c].x, y4[c].y, y4[c].z, y4[c].w}, pw[4] = {n4.x, n4.y, n4.z, n4.w};
+          const uint32_t pw[4] = {n4.x, n4.y, n4.z, n4.w};
           uint32_t o[4];
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            o[kk] = pack2(__uint_as_float(p1[8 * c + 2 * kk]) + __uint_as_float(yw[kk] << 16) + __uint_as_float(pw[kk] << 16),
-                          __uint_as_float(p1[8 * c + 2 * kk + 1]) + __uint_as_float(yw[kk] & 0xffff0000u) +
-                              __uint_as_float(pw[kk] & 0xffff0000u));
+            o[kk] = pack2(__uint_as_float(p1[8 * c + 2 * kk]) + __uint_as_float(pw[kk] << 16),
+                          __uint_as_float(p1[8 * c + 2 * kk + 1]) + __uint_as_float(pw[kk] & 0xffff0000u));
           *reinterpret_cast<uint4*>(st + P_X0 * PANEL + oc[c]) = make_uint4(o[0], o[1], o[2], o[3]);
         }
         fence_proxy_async_smem();
@@ -1299,10 +1306,10 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
   ga.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
   static int trace_seq = 0;
   if (ga.trace != nullptr) ga.seq = trace_seq++;
-  // ring n_stages x 24 KB | work buffers 2 x 32 KB | wc 2 x 4 KB | RESIDUAL 2 KB | ones 1 KB | carry n_carry x 8 KB
+  // ring n_stages x 24 KB | work buffers 2 x 32 KB | wc 2 x 4 KB | RESIDUAL 2 KB | ones 1 KB | [0 | I] 4 KB | carry n_carry x 8 KB
   ga.n_later = (ld.dil + 127) / 128;
   ga.n_carry = ga.n_later + 2;  // one spare: the next tile's P0 never lands in a slot the current tile still reads
-  const int fixed = 2 * 4 * 8192 + 2 * 4096 + 2048 + 1024 + ga.n_carry * 8192 + 1024;
+  const int fixed = 2 * 4 * 8192 + 2 * 4096 + 2048 + 1024 + 4096 + ga.n_carry * 8192 + 1024;
   ga.n_stages = std::min(6, (232448 /* 227 KB per CTA on sm_100 */ - 2048 - fixed) / (3 * 8192));
   if (ga.n_stages < 2) {
     set_error("layer backward: dilation %d needs %d carry tiles, more than shared memory holds", ld.dil, ga.n_carry);

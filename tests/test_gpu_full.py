@@ -230,10 +230,12 @@ def test_four_stage_trajectory_vs_oracle(lib):
 def test_sixty_step_loss_curve_vs_oracle(lib):
     """Training quality against the fp64 reference graph over a longer run: 60 consecutive stages of the 3x10
     stack (forward + backward + TF-Adam, SAVE carried from stage to stage, lr = 1e-3, l2 = 1e-3) on the GPU and in the
-    oracle, each evolving its OWN weights from the same start.  The two loss curves must stay together (6e-3 relative at
-    every step; the CPU evaluation of the same bf16 contract drifts 2.3e-3 from fp64 over these 60 steps) while the loss
-    itself falls from 8.26 to 5.01 -- a systematic gradient or optimiser defect bends the GPU curve away within a few
-    steps."""
+    oracle, each evolving its OWN weights from the same start.  The two loss curves must stay together (1.5e-2 relative
+    at every step) while the loss itself falls from 8.26 to 5.01 -- a systematic gradient or optimiser defect bends the
+    GPU curve away within a few steps (10 % less progress is a 6 % deviation at the end).  Calibration: the CPU
+    evaluation of the same bf16 contract drifts 2.3e-3 from fp64 over these 60 steps; the GPU run is not repeatable to
+    the last bit (fp32 atomics in the weight gradients) and the two trajectories amplify that: four runs of ONE binary
+    measured 5.4e-3, 6.6e-3, 7.2e-3 and 9.4e-3 (round 2's first bound, 6e-3, sat inside that spread)."""
     arch, B, T, K = util.CLASSIC, 4, 1024, 60
     lr, l2 = 1e-3, 1e-3
     a = util.oracle_arch(arch)
@@ -267,4 +269,4 @@ def test_sixty_step_loss_curve_vs_oracle(lib):
     util.record("loss_curve_60_steps_3x10", dict(max_rel_dev=float(dev.max()), at=int(dev.argmax()), first=float(ref[0]),
                                                  last=float(ref[-1]), gpu_last=float(gpu[-1])))
     assert ref[0] - ref[-1] > 2.0, (ref[0], ref[-1])      # the run learns: the loss falls by >> the tolerance
-    assert dev.max() <= 6e-3, (int(dev.argmax()), float(dev.max()))
+    assert dev.max() <= 1.5e-2, (int(dev.argmax()), float(dev.max()))
