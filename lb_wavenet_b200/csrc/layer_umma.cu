@@ -608,14 +608,13 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
   unsigned char* wc0 = wb + 2 * WBUF;             // [2D rows][R]   4 KB (GATE half pre-scaled by 0.5)
   unsigned char* wc1 = wc0 + 2 * D * XB;          //                4 KB, directly behind wc0
   unsigned char* wrn = wc1 + 2 * D * XB;          // [D rows][R]    2 KB
-  unsigned char* ones = wrn + D * XB;             // 1 KB of bf16 1.0: the B operand (16 timesteps x 16 columns) of queue C
-  unsigned char* idn = ones + 1024;               // [64 rows][32] bf16, K-major: rows 0..31 zero, rows 32..63 the identity
+  unsigned char* bt = wrn + D * XB;               // [64 rows][16] bf16, K-major SW32: SIGNAL_BIAS | 0.5 GATE_BIAS as hi + lo
+  unsigned char* idn = bt + 2048;                 // [64 rows][32] bf16, K-major: rows 0..31 zero, rows 32..63 the identity
   unsigned char* carry = idn + 4096;              // [n_carry] P0 tiles (bf16, SW64 rows) of this and the later tiles
   float* stg = reinterpret_cast<float*>(smem);    // aliases stage 0
   __shared__ __align__(8) uint64_t w_full, in_full[MAX_NST], stage_free[MAX_NST], out_ready[MAX_NST], v_full[2],
       acc1_free[2], dv_ready[2], p_full[2], acc2_free[2], g_full;
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float bias_s[64];  // SIGNAL_BIAS | 0.5 * GATE_BIAS
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // Work list of this CTA: a contiguous run [j0, j1) of the tiles in (slot, time DEscending) order, preceded by up to
   // n_later warm-up tiles (the tiles just later in time than the first one: only their P0 is wanted).
@@ -660,10 +659,11 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
     }
     fence_mbar_init();
   }
-  if (tid < 64)
-    bias_s[tid] = tid < 32 ? (a.sig_b >= 0 ? a.params[a.sig_b + tid] : 0.f)
-                           : (a.gate_b >= 0 ? 0.5f * a.params[a.gate_b + tid - 32] : 0.f);
-  fill_ones(ones, 1024, tid, 896);
+  // the pre-activation biases enter acc_v as one more K = 16 step, (constant ones) x (bias as hi + lo bf16, 2^-17
+  // relative): 32 adds and 8 shared-memory loads less per gate-epilogue thread and tile, where issue slots are scarce
+  build_bias_tile(bt, 64, tid, 896, [&](int n) {
+    return n < 32 ? (a.sig_b >= 0 ? a.params[a.sig_b + n] : 0.f) : (a.gate_b >= 0 ? 0.5f * a.params[a.gate_b + n - 32] : 0.f);
+  });
   fill_ones(wb + W_ONES * PANEL, PANEL, tid, 896);
   fill_ones(wb + WBUF + W_ONES * PANEL, PANEL, tid, 896);
   if (tid < 256) {  // [0 | I]: contracted against the DX tile it adds dx_{l+1} onto the P1 half of acc_p (exact: 1.0 x bf16)
@@ -734,8 +734,10 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
       const uint32_t wc_mn = desc_lo(smem_u32(wc0), 2 * D * XB);  // chunk 0 = wc0 (-> P0), chunk 1 = wc1 (-> Y)
       const uint32_t wrn_k = desc_lo_k(smem_u32(wrn)), idn_k = desc_lo_k(smem_u32(idn));
       // queue C: A = the work buffer re-described MN-major with M = 128 (rows 0..63 = dv channels; 64..95 = z and 96..127
-      // = whatever follows the buffer: never read back), B = 16 rows of ones, the same 1 KB for every K step
-      const uint32_t idb = make_idesc_bf16(128, 16, true, true), ones_mn = desc_lo(smem_u32(ones), PANEL);
+      // = the ones panel: never read back), B = 16 rows of the ones panel of work buffer 0, the same for every K step
+      const uint32_t idb = make_idesc_bf16(128, 16, true, true), ones_mn = desc_lo(smem_u32(wb + W_ONES * PANEL), PANEL);
+      const uint32_t ones_k = desc_lo_k(smem_u32(wb + W_ONES * PANEL)), bt_k = desc_lo_k(smem_u32(bt));
+      constexpr uint32_t HI32 = desc_hi(32);
       auto issue_a = [&](int i) {  // recomputed pre-activations; residual part of dz
         const int s = i % NST, ab = i & 1;
         const uint32_t x0 = ring_k + (uint32_t)s * (STAGE >> 4), x1 = x0 + (PANEL >> 4);
@@ -745,6 +747,7 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
         mma_bf16_ss2(av, x0 + 2, HI, wc0_k + 2, HI, idv, true);
         mma_bf16_ss2(av, x1, HI, wc1_k, HI, idv, true);
         mma_bf16_ss2(av, x1 + 2, HI, wc1_k + 2, HI, idv, true);
+        mma_bf16_ss2(av, ones_k, HI, bt_k, HI32, idv, true);  // + biases
         if (a.has_next) {  // dz(res) = dx_{l+1} . RESIDUAL^T : B = RESIDUAL [D rows][R]
           mma_bf16_ss2(ad, dx, HI, wrn_k, HI, idd, false);
           mma_bf16_ss2(ad, dx + 2, HI, wrn_k + 2, HI, idd, true);
@@ -837,8 +840,6 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
     const uint32_t sw64 = ((uint32_t)r >> 1) & 3u;
     const uint32_t o[2] = {(uint32_t)r * 64u + ((((uint32_t)(2 * half)) ^ sw64) << 4),
                            (uint32_t)r * 64u + ((((uint32_t)(2 * half + 1)) ^ sw64) << 4)};
-    const float4* bs4 = reinterpret_cast<const float4*>(bias_s + 16 * half);
-    const float4* bg4 = reinterpret_cast<const float4*>(bias_s + 32 + 16 * half);
     Item it = item0;
     if (g == 1) it.next();
     for (int i = g; i < n_my; i += 2, it.next(), it.next()) {
@@ -899,14 +900,14 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          float4 b_s = bs4[2 * p + q], b_g = bg4[2 * p + q];
+          // per-row conditioning on top of the biases (which are in the accumulator already)
+          float4 b_s = make_float4(0.f, 0.f, 0.f, 0.f), b_g = make_float4(0.f, 0.f, 0.f, 0.f);
           if constexpr (GC) {  // the accumulator's GATE half holds 0.5 * pre-activation: the table's gate half is halved too
             const float* gct = a.gc_tbl + (size_t)gid * 2 * D + c0;
             const float4 c_s = __ldg(reinterpret_cast<const float4*>(gct) + q);
             const float4 c_g = __ldg(reinterpret_cast<const float4*>(gct + D) + q);
-            b_s.x += c_s.x; b_s.y += c_s.y; b_s.z += c_s.z; b_s.w += c_s.w;
-            b_g.x = fmaf(0.5f, c_g.x, b_g.x); b_g.y = fmaf(0.5f, c_g.y, b_g.y);
-            b_g.z = fmaf(0.5f, c_g.z, b_g.z); b_g.w = fmaf(0.5f, c_g.w, b_g.w);
+            b_s = c_s;
+            b_g = make_float4(0.5f * c_g.x, 0.5f * c_g.y, 0.5f * c_g.z, 0.5f * c_g.w);
           }
           if constexpr (LC) {
             const uint32_t ws0 = q == 0 ? lcs[p].x : lcs[p].z, ws1 = q == 0 ? lcs[p].y : lcs[p].w;
@@ -919,8 +920,10 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int d = 4 * q + k;
-            const float th = tanh_fast(__uint_as_float(vs[d]) + bsv[k]);
-            const float u = tanh_fast(__uint_as_float(vg[d]) + bgv[k]);   // accumulator holds 0.5 * gate pre-activation
+            float as = __uint_as_float(vs[d]), ag = __uint_as_float(vg[d]);   // ag: 0.5 * gate pre-activation
+            if constexpr (GC || LC) { as += bsv[k]; ag += bgv[k]; }
+            const float th = tanh_fast(as);
+            const float u = tanh_fast(ag);
             const float sg = fmaf(0.5f, u, 0.5f);
             const uint32_t dw = dzs[d >> 1];
             const float dz = ((d & 1) == 0 ? __uint_as_float(dw << 16) : __uint_as_float(dw & 0xffff0000u)) + __uint_as_float(vd[d]);
@@ -1306,10 +1309,10 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
   ga.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
   static int trace_seq = 0;
   if (ga.trace != nullptr) ga.seq = trace_seq++;
-  // ring n_stages x 24 KB | work buffers 2 x 32 KB | wc 2 x 4 KB | RESIDUAL 2 KB | ones 1 KB | [0 | I] 4 KB | carry n_carry x 8 KB
+  // ring n_stages x 24 KB | work buffers 2 x 32 KB | wc 2 x 4 KB | RESIDUAL 2 KB | bias tile 2 KB | [0 | I] 4 KB | carry n_carry x 8 KB
   ga.n_later = (ld.dil + 127) / 128;
   ga.n_carry = ga.n_later + 2;  // one spare: the next tile's P0 never lands in a slot the current tile still reads
-  const int fixed = 2 * 4 * 8192 + 2 * 4096 + 2048 + 1024 + 4096 + ga.n_carry * 8192 + 1024;
+  const int fixed = 2 * 4 * 8192 + 2 * 4096 + 2048 + 2048 + 4096 + ga.n_carry * 8192 + 1024;
   ga.n_stages = std::min(6, (232448 /* 227 KB per CTA on sm_100 */ - 2048 - fixed) / (3 * 8192));
   if (ga.n_stages < 2) {
     set_error("layer backward: dilation %d needs %d carry tiles, more than shared memory holds", ld.dil, ga.n_carry);
