@@ -103,6 +103,27 @@ struct Tracer {
   }
 };
 
+// ---- global loads that stay where they are written -------------------------------------------------
+// 16-byte read-only global load (asm volatile: the compiler may not move it), zero when !pred
+__device__ __forceinline__ uint4 ldg_nc_v4_pred(const void* p, bool pred) {
+  uint4 v;
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.u32 q, %5, 0;\n"
+      "mov.u32 %0, 0;\n"
+      "mov.u32 %1, 0;\n"
+      "mov.u32 %2, 0;\n"
+      "mov.u32 %3, 0;\n"
+      "@q ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+      "}\n"
+      : "=&r"(v.x), "=&r"(v.y), "=&r"(v.z), "=&r"(v.w)
+      : "l"(p), "r"((uint32_t)pred));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg_nc_v4_pinned(const void* p) { return ldg_nc_v4_pred(p, true); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- math ------------------------------------------------------------------------------
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;

@@ -553,12 +553,6 @@ struct LayerBwdFusedArgs {
 // tile); outputs written with plain 16-byte global stores from E2 instead of shared memory + TMA (the stage is free
 // ~3000 cycles earlier, but a warp's 32 rows x 16 bytes are 32 separate sectors: 1.50 -> 1.70 ms).
 // =====================================================================================================
-// 16-byte read-only global load that the compiler may not move (asm volatile): issued where it is written
-__device__ __forceinline__ uint4 ldg_nc_v4_pinned(const void* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
 // 8 values x 32 lanes -> every lane L returns the warp total of value (L >> 2) & 7 (9 shuffles instead of 8 warp sums)
 __device__ __forceinline__ float warp_transpose_sum8(float (&w)[8], int lane) {
 #pragma unroll
@@ -1252,7 +1246,7 @@ int launch_layer_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws,
   pa.n_tiles = pa.tiles_per_slot * m->n_slots;
   pa.z_col = l * a.n_dil;
   pa.tile_ctr = reinterpret_cast<int*>(ws + wl.tile_ctr) + 4 * l;
-  pa.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
+  pa.trace = (g_trace_layer == -1 || g_trace_layer == l) ? g_trace_buf : nullptr;
   {
     const int h = l2_hint_mask();
     pa.pol_x0 = (h & 1) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
@@ -1306,7 +1300,7 @@ int launch_layer_bwd_fused_umma(wn_model* m, const float* d_params, unsigned cha
   ga.tiles_per_slot = (T + 127) / 128;
   ga.n_tiles = ga.tiles_per_slot * m->n_slots;
   ga.z_plane0 = l * m->n_slots;
-  ga.trace = (g_trace_layer < 0 || g_trace_layer == l) ? g_trace_buf : nullptr;
+  ga.trace = (g_trace_layer == -1 || g_trace_layer == l) ? g_trace_buf : nullptr;
   static int trace_seq = 0;
   if (ga.trace != nullptr) ga.seq = trace_seq++;
   // ring n_stages x 24 KB | work buffers 2 x 32 KB | wc 2 x 4 KB | RESIDUAL 2 KB | bias tile 2 KB | [0 | I] 4 KB | carry n_carry x 8 KB

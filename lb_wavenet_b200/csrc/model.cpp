@@ -55,6 +55,8 @@ const WorkspaceLayout& workspace_layout(wn_model* m, int32_t T) {
   w.z = take(rows * L * D * 2);
   w.h1 = take(rows * S * 2);
   w.h2 = take(rows * P * 2);
+  w.hm1 = take(align_up(rows, 128) * 32);
+  w.hm2 = take(align_up(rows, 128) * 32);
   w.dlogits = take(rows * Q * 2);
   w.dp1 = take(rows * P * 2);
   w.dskip = take(rows * S * 2);

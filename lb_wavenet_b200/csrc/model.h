@@ -41,6 +41,8 @@ struct WorkspaceLayout {
   int64_t wbf;        // bf16 mirror of the parameter arena
   int64_t z;          // [B*T][L*D] bf16
   int64_t h1, h2;     // [B*T][S], [B*T][P] bf16
+  int64_t hm1, hm2;   // relu masks of h1 / h2 as bits: [ceil(B*T / 128) * 128][8] uint32 (bit c % 32 of word c / 32 = h[.][c] > 0),
+                      // written by the fused post-net forward, read by its backward instead of the activations themselves
   int64_t dlogits;    // [B*T][Q] bf16
   int64_t dp1, dskip; // [B*T][P], [B*T][S] bf16
   int64_t dz;         // [L][B*T][D] bf16: per-layer planes (dense 64-byte rows for the layer backward)

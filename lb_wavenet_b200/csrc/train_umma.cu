@@ -39,6 +39,8 @@ struct PostUmmaArgs {
   float* logits_out;
   int T, S, P, Q, LD, use_bias;
   int64_t rows;
+  uint32_t *hm1, *hm2;  // relu masks of h1 / h2 as bits, [rows padded to 128][8] (model.h)
+  long long* trace;  // wn_debug_trace(buf, -2): in-kernel timeline of CTA 0 (tools/trace_layer.py postfwd)
 };
 
 // ---- weight preparation -------------------------------------------------------------------------
@@ -90,6 +92,22 @@ __device__ __forceinline__ void htile_store32(unsigned char* htile, int row, int
   }
 }
 
+// relu of 32 pre-activations (accumulator + bias), packed to bf16, and the mask word: bit j = 1 unless x_j carries a sign
+// bit, i.e. "h_j > 0" (x = +0 counts as positive: measure zero, and where whole columns are exactly zero -- channel
+// padding -- the weights that would carry a gradient are zero too).  Two instructions per column: the sign bits are
+// shifted into the word one after the other.
+__device__ __forceinline__ uint32_t relu_pack32(const uint32_t (&v)[32], const float* bias, uint32_t (&pk)[16]) {
+  uint32_t nb = 0u;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float x0 = __uint_as_float(v[2 * j]) + bias[2 * j], x1 = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
+    nb = (nb >> 1) | (__float_as_uint(x0) & 0x80000000u);
+    nb = (nb >> 1) | (__float_as_uint(x1) & 0x80000000u);
+    pk[j] = pack_bf16x2(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+  }
+  return ~nb;
+}
+
 constexpr int UPOST_P_THREADS = 320;  // producer warp, MMA warp, 8 epilogue warps
 
 __device__ __forceinline__ void epi_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -107,6 +125,7 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
   unsigned char* stage_a = smem;                                  // USTAGES x 16 KB
   unsigned char* stage_b = smem + USTAGES * UA_BYTES;             // USTAGES x 32 KB
   unsigned char* htile = stage_b + USTAGES * UB_BYTES;            // 64 KB
+  uint32_t* mtile = reinterpret_cast<uint32_t*>(htile + UH_BYTES);  // 4 KB: [128 rows][8 words] relu mask bits of the tile
   __shared__ __align__(8) uint64_t full_bar[USTAGES], empty_bar[USTAGES], acc_full[2], acc_empty[2], h_ready[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[3 * 256];  // skip-bias sum | POST1_BIAS | POST2_BIAS (broadcast reads in the epilogues)
@@ -128,6 +147,8 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
     bias_s[i] = v;
   }
   const int nkb1 = (a.LD + UKB - 1) / UKB, nkb2 = S / UKB, nkb3 = P / UKB;
+  Tracer tr;
+  tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
 
   if (tid == 0) {
     for (int i = 0; i < USTAGES; ++i) {
@@ -159,7 +180,9 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
         const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * UM;
         for (int kb = 0; kb < nkb1 + nkb2 + nkb3; ++kb, ++it) {
           const int st = it % USTAGES;
+          tr.ev(1, it);
           mbar_wait(&empty_bar[st], ((uint32_t)(it / USTAGES) & 1u) ^ 1u);
+          tr.ev(2, it);
           unsigned char* sa = stage_a + st * UA_BYTES;
           unsigned char* sb = stage_b + st * UB_BYTES;
           if (kb < nkb1) {
@@ -183,12 +206,15 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
       uint32_t use[2] = {0, 0};  // number of contractions issued into each accumulator buffer so far
       const uint32_t idesc1 = make_idesc_bf16(UM, S), idesc2 = make_idesc_bf16(UM, P), idesc3 = make_idesc_bf16(UM, Q);
       auto gemm = [&](int buf, int nkb, uint32_t idesc, bool a_from_htile) {
+        tr.ev(3, it);
         mbar_wait(&acc_empty[buf], (use[buf] & 1u) ^ 1u);  // the previous contraction of this buffer has been drained
+        tr.ev(4, it);
         tc_fence_after_sync();
         const uint32_t acc = tmem_base + (uint32_t)buf * 256;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int st = it % USTAGES;
           mbar_wait(&full_bar[st], (uint32_t)(it / USTAGES) & 1u);
+          tr.ev(16, it);
           tc_fence_after_sync();
           const uint32_t sa = a_from_htile ? smem_u32(htile + kb * UA_BYTES) : smem_u32(stage_a + st * UA_BYTES);
           const uint32_t sb = smem_u32(stage_b + st * UB_BYTES);
@@ -198,6 +224,7 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
           mma_commit(&empty_bar[st]);
         }
         mma_commit(&acc_full[buf]);
+        tr.ev(17, it);
         ++use[buf];
       };
       for (int i = 0; i < n_my; ++i) {
@@ -221,14 +248,18 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
     uint32_t v[32];
     uint32_t pk[16];
     float acc_x = 0.f, acc_n = 0.f, acc_d = 0.f;  // loss statistics over all tiles of this CTA
+    int n_epi = 0;  // epilogue phases so far (trace only)
     auto acc_wait = [&](int buf) -> uint32_t {
+      tr.ev(5, n_epi);
       mbar_wait(&acc_full[buf], use[buf] & 1u);
+      tr.ev(6, n_epi);
       tc_fence_after_sync();
       return tmem_base + (uint32_t)buf * 256 + lane_sel;
     };
     auto acc_release = [&](int buf) {
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[buf]);
+      tr.ev(7, n_epi++);
       ++use[buf];
     };
     for (int i = 0; i < n_my; ++i) {
@@ -244,10 +275,7 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
         for (int c0 = cb; c0 < cb + S / 2; c0 += 32) {
           tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
           tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            pk[j] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + bias_s[c0 + 2 * j], 0.f),
-                                fmaxf(__uint_as_float(v[2 * j + 1]) + bias_s[c0 + 2 * j + 1], 0.f));
+          mtile[r * 8 + (c0 >> 5)] = relu_pack32(v, bias_s + c0, pk);
           htile_store32(htile, r, c0, pk);
         }
         acc_release(p);
@@ -256,6 +284,7 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
         if (elected) {
           mbar_arrive(&h_ready[0]);
           for (int kb = 0; kb < nkb2; ++kb) tma_store_2d(&map_h1, htile + kb * UA_BYTES, kb * UKB, (int)row0);
+          bulk_store_1d(a.hm1 + (size_t)row0 * 8, mtile, 128 * 32);  // (the mask buffers are padded to whole tiles)
           tma_store_commit();
         }
       }
@@ -268,10 +297,7 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
         for (int c0 = cb; c0 < cb + P / 2; c0 += 32) {
           tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
           tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            pk[j] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + bias_s[256 + c0 + 2 * j], 0.f),
-                                fmaxf(__uint_as_float(v[2 * j + 1]) + bias_s[256 + c0 + 2 * j + 1], 0.f));
+          mtile[r * 8 + (c0 >> 5)] = relu_pack32(v, bias_s + 256 + c0, pk);
           htile_store32(htile, r, c0, pk);
         }
         acc_release(p ^ 1);
@@ -280,6 +306,7 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
         if (elected) {
           mbar_arrive(&h_ready[1]);
           for (int kb = 0; kb < nkb3; ++kb) tma_store_2d(&map_h2, htile + kb * UA_BYTES, kb * UKB, (int)row0);
+          bulk_store_1d(a.hm2 + (size_t)row0 * 8, mtile, 128 * 32);
           tma_store_commit();
         }
       }
@@ -393,6 +420,8 @@ struct PostBwdUmmaArgs {
   float* g_skip_b0;   // SKIP_BIAS of layer 0 (broadcast to the other layers afterwards)
   int S, P, Q, LD, D;
   int64_t rows;
+  const uint32_t *hm1, *hm2;  // relu masks of h1 / h2 as bits (written by k_post_fwd_umma)
+  long long* trace;  // wn_debug_trace(buf, -2) (tools/trace_layer.py postbwd)
 };
 
 // partial column sums of a [128 x ncols] K-major SW128 tile: thread et of the 256 epilogue threads owns the column
@@ -414,6 +443,27 @@ __device__ __forceinline__ void tile_colsum_acc(const unsigned char* tile, int n
 }
 
 // relu mask from 32 stored activations (64 bytes of one row), applied while packing to bf16
+// the same with the mask as 32 bits (bit j <-> column j), written by the fused forward: one word instead of 64 bytes
+__device__ __forceinline__ void mask_pack32_bits(const uint32_t (&v)[32], uint32_t bits, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float m0 = (bits >> (2 * j)) & 1u ? 1.f : 0.f, m1 = (bits >> (2 * j + 1)) & 1u ? 1.f : 0.f;
+    pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]) * m0, __uint_as_float(v[2 * j + 1]) * m1);
+  }
+}
+__device__ __forceinline__ uint32_t ldg_u32_pred(const uint32_t* p, bool pred) {
+  uint32_t v;
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.u32 q, %2, 0;\n"
+      "mov.u32 %0, 0;\n"
+      "@q ld.global.nc.u32 %0, [%1];\n"
+      "}\n"
+      : "=&r"(v)
+      : "l"(p), "r"((uint32_t)pred));
+  return v;
+}
 __device__ __forceinline__ void mask_pack32(const uint32_t (&v)[32], const bf16* hrow, uint32_t (&pk)[16]) {
   const uint4* h4 = reinterpret_cast<const uint4*>(hrow);
 #pragma unroll
@@ -453,6 +503,8 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
   const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int nkb4 = Q / UKB, nkb5 = P / UKB, nkb6 = S / UKB;
   const int nchunk = (LD + 255) / 256;
+  Tracer tr;
+  tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
 
   if (tid == 0) {
     for (int i = 0; i < UBSTAGES; ++i) {
@@ -483,7 +535,9 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
       int it = 0;
       auto load_b = [&](const CUtensorMap* mp, int k0, int n0, uint32_t bytes) {
         const int st = it % UBSTAGES;
+        tr.ev(1, it);
         mbar_wait(&empty_bar[st], ((uint32_t)(it / UBSTAGES) & 1u) ^ 1u);
+        tr.ev(2, it);
         mbar_expect_tx(&full_bar[st], bytes);
         tma_load_2d(stage_b + st * UB_BYTES, mp, &full_bar[st], k0, n0);
         ++it;
@@ -504,12 +558,15 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
       int it = 0, use = 0;
       auto gemm = [&](const unsigned char* atile, int nkb, uint32_t idesc) {
         const int buf = use & 1, k_use = use >> 1;
+        tr.ev(3, use);
         mbar_wait(&acc_empty[buf], ((uint32_t)k_use & 1u) ^ 1u);  // accumulator drained by the epilogue
+        tr.ev(4, use);
         tc_fence_after_sync();
         const uint32_t acc = tmem_base + (uint32_t)buf * 256;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int st = it % UBSTAGES;
           mbar_wait(&full_bar[st], (uint32_t)(it / UBSTAGES) & 1u);
+          tr.ev(16, it);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(atile + kb * UA_BYTES), sb = smem_u32(stage_b + st * UB_BYTES);
 #pragma unroll
@@ -518,6 +575,7 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
           mma_commit(&empty_bar[st]);
         }
         mma_commit(&acc_full[buf]);
+        tr.ev(17, use);
         ++use;
       };
       for (int i = 0; i < n_my; ++i) {
@@ -545,13 +603,16 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
     float b2acc[2] = {0.f, 0.f}, b1acc[2] = {0.f, 0.f}, bsacc[2] = {0.f, 0.f};
     auto acc_wait = [&]() -> uint32_t {
       const int buf = use & 1, k_use = use >> 1;
+      tr.ev(5, use);
       mbar_wait(&acc_full[buf], (uint32_t)k_use & 1u);
+      tr.ev(6, use);
       tc_fence_after_sync();
       return tmem_base + (uint32_t)buf * 256 + lane_sel;
     };
     auto acc_release = [&]() {
       tc_fence_before_sync();
       mbar_arrive(&acc_empty[use & 1]);
+      tr.ev(7, use);
       ++use;
     };
     for (int i = 0; i < n_my; ++i) {
@@ -559,6 +620,16 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
       const int64_t row = row0 + r;
       const bool in_range = row < a.rows;
       const int rows_valid = (int)min((int64_t)UM, a.rows - row0);
+      // this row's relu masks (one bit per column, written by the forward): requested here, a contraction and more before
+      // they are used.  (Read as the 2 x 256 bytes of h2 / h1 themselves inside the epilogue steps, every step exposed a
+      // global-memory round trip on the tile's critical chain: in-kernel timeline 6600 + 7700 cycles for the two masked
+      // epilogues against ~1100 for an unmasked one of the same size.)
+      uint32_t mw2[4], mw1[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        mw2[k] = ldg_u32_pred(a.hm2 + (size_t)(in_range ? row : 0) * 8 + half * (P / 64) + k, in_range && 32 * k < P / 2);
+        mw1[k] = ldg_u32_pred(a.hm1 + (size_t)(in_range ? row : 0) * 8 + half * (S / 64) + k, in_range && 32 * k < S / 2);
+      }
       // POST2_BIAS gradient from the dlogits tile while the first contraction runs
       mbar_wait(&a_full, (uint32_t)i & 1u);
       if (a.g_post2_b != nullptr) tile_colsum_acc(tile0, Q, et, rows_valid, b2acc);
@@ -571,12 +642,8 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
         for (int c0 = cb; c0 < cb + P / 2; c0 += 32) {
           tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
           tmem_ld_wait();
-          if (in_range) {
-            mask_pack32(v, a.h2 + (size_t)row * P + c0, pk);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = 0u;
-          }
+          mask_pack32_bits(v, mw2[0], pk);  // (rows beyond the batch: bits 0 on an accumulator row of zeros)
+          mw2[0] = mw2[1]; mw2[1] = mw2[2]; mw2[2] = mw2[3];
           htile_store32(tile1, r, c0, pk);
         }
         acc_release();
@@ -596,12 +663,8 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
         for (int c0 = cb; c0 < cb + S / 2; c0 += 32) {
           tmem_ld_32x32b_x32(acc + (uint32_t)c0, v);
           tmem_ld_wait();
-          if (in_range) {
-            mask_pack32(v, a.h1 + (size_t)row * S + c0, pk);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = 0u;
-          }
+          mask_pack32_bits(v, mw1[0], pk);
+          mw1[0] = mw1[1]; mw1[1] = mw1[2]; mw1[2] = mw1[3];
           htile_store32(tile0, r, c0, pk);
         }
         acc_release();
@@ -622,6 +685,7 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
         const uint32_t acc = acc_wait();
         if (elected) tma_store_wait_read<0>();  // previous stores (dp1 / dskip / previous chunk) done reading smem
         epi_bar_sync256();
+        tr.ev(8, use);
         const int ncols = min(256, LD - c * 256);
         const int cb = half * 128, ce = min(ncols, cb + 128);
         for (int c0 = cb; c0 < ce; c0 += 32) {
@@ -641,6 +705,7 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
         acc_release();
         fence_proxy_async_smem();
         epi_bar_sync256();
+        tr.ev(9, use);
         if (elected) {
           for (int pn = 0; pn * a.D < ncols; ++pn)
             tma_store_3d(&map_dz, tile1 + pn * panel_bytes, 0, (int)row0, (c * 256) / a.D + pn);
@@ -713,6 +778,7 @@ int launch_post_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws, 
   if ((rc = map2d(&mdl, ws + wl.dlogits, Q, (uint64_t)rows, UKB, UM))) return rc;
   PostUmmaArgs pa;
   memset(&pa, 0, sizeof(pa));
+  pa.trace = g_trace_layer == -2 ? g_trace_buf : nullptr;
   pa.params = d_params;
   pa.skip_bias = reinterpret_cast<const float*>(ws + wl.skip_bias);
   pa.off_post1_b = m->off_post1_b;
@@ -723,7 +789,9 @@ int launch_post_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws, 
   pa.logits_out = d_logits;
   pa.T = T; pa.S = a.n_skip; pa.P = a.n_post; pa.Q = a.n_quant; pa.LD = (int)LD; pa.use_bias = a.use_bias;
   pa.rows = rows;
-  const size_t smem = (size_t)USTAGES * (UA_BYTES + UB_BYTES) + UH_BYTES + 1024;
+  pa.hm1 = reinterpret_cast<uint32_t*>(ws + wl.hm1);
+  pa.hm2 = reinterpret_cast<uint32_t*>(ws + wl.hm2);
+  const size_t smem = (size_t)USTAGES * (UA_BYTES + UB_BYTES) + UH_BYTES + 4096 + 1024;
   WN_CUDA_CHECK(cudaFuncSetAttribute(k_post_fwd_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps(PROF_POST_FWD, st);
   const int n_tiles = (int)((rows + UM - 1) / UM);
@@ -768,8 +836,11 @@ int launch_post_bwd_umma(wn_model* m, unsigned char* ws, int T, float* d_grads, 
   }
   PostBwdUmmaArgs pa;
   memset(&pa, 0, sizeof(pa));
+  pa.trace = g_trace_layer == -2 ? g_trace_buf : nullptr;
   pa.h1 = reinterpret_cast<const bf16*>(ws + wl.h1);
   pa.h2 = reinterpret_cast<const bf16*>(ws + wl.h2);
+  pa.hm1 = reinterpret_cast<const uint32_t*>(ws + wl.hm1);
+  pa.hm2 = reinterpret_cast<const uint32_t*>(ws + wl.hm2);
   if (a.use_bias) {
     pa.g_post2_b = d_grads + m->off_post2_b;
     pa.g_post1_b = d_grads + m->off_post1_b;

@@ -33,7 +33,21 @@ torch.cuda.synchronize()
 buf = torch.zeros(32 * 2048 + 4 * 1024 + 128, dtype=torch.int64, device="cuda")
 buf[32 * 2048 + 4096::2] = 2 ** 62
 L = len(eng.reg.saves)
-if which == "fwd":
+if which in ("postfwd", "postbwd"):
+    # layer -2 selects the post-net kernels (train_umma.cu); both log into the same buffer, so trace one at a time
+    if which == "postfwd":
+        lib.wn_debug_trace(buf.data_ptr(), -2)
+        eng.forward(wav, ids)
+        torch.cuda.synchronize()
+        lib.wn_debug_trace(None, -1)
+    else:
+        eng.forward(wav, ids)
+        torch.cuda.synchronize()
+        lib.wn_debug_trace(buf.data_ptr(), -2)
+        eng.backward_phases(0, 1)
+        torch.cuda.synchronize()
+        lib.wn_debug_trace(None, -1)
+elif which == "fwd":
     # tracing stays on for the whole forward: every layer overwrites the buffer, the LAST layer that logged wins;
     # so run the forward with tracing and keep only the wanted layer via phases is not possible -> trace layer L-2
     lib.wn_debug_trace(buf.data_ptr(), layer)
@@ -97,6 +111,10 @@ names = {1: "prod:wait_free", 2: "prod:got_free", 3: "mma:issueA", 4: "mma:issue
          16: "mma:doneA", 17: "mma:doneB", 18: "e0:begin", 19: "e0:in_full", 20: "e0:done",
          30: "k:entry", 31: "k:init_done", 32: "k:role_done", 33: "k:all_done", 34: "k:bar_init", 35: "k:bias",
          36: "k:tmem_alloc", 37: "k:synced"}
+if which in ("postfwd", "postbwd"):
+    names = {1: "prod:wait_empty", 2: "prod:got_empty", 3: "mma:wait_acc_empty", 4: "mma:gemm_begin", 16: "mma:stage_full",
+             17: "mma:gemm_issued", 5: "epi:wait_acc", 6: "epi:acc_full", 7: "epi:acc_released", 8: "epi:staging_free",
+             9: "epi:staged"}
 rows = []
 for w in range(32):
     for x in ev[w]:
