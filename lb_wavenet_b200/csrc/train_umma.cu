@@ -1748,6 +1748,7 @@ struct WgradUmmaArgs {
   int a_T, a_row_off;  // a_T > 0: A is a layer input in the prefix layout [slot][dil + T][R] (3-D map): flat row r is
                        // (slot r / a_T, row r % a_T + a_row_off); a_T % 64 == 0 keeps a K block inside one slot
   int64_t kblocks_total, kblocks_per_cta;
+  long long* trace;  // wn_debug_trace(buf, -3) (tools/trace_layer.py wgrad): timeline of CTA 0 of the LAST launch
 };
 
 // 16-byte vector reduction into global memory (sm_90+): one L2 operation for four fp32 adds
@@ -1777,6 +1778,9 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   while (ncols < (uint32_t)N) ncols <<= 1;
 
   pdl_launch_dependents();
+  Tracer tr;
+  tr.init(a.trace, warp, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0);
+  tr.ev(30, 0);
   if (tid == 0) {
     for (int i = 0; i < WG_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -1789,6 +1793,7 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
   pdl_wait();
+  tr.ev(31, 0);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -1799,7 +1804,9 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       if (lane == 0) {
         for (int it = 0; it < nkb; ++it) {
           const int st = it % WG_STAGES;
+          if ((it & 15) == 0) tr.ev(1, it);
           mbar_wait(&empty_bar[st], ((uint32_t)(it / WG_STAGES) & 1u) ^ 1u);
+          if ((it & 15) == 0) tr.ev(2, it);
           mbar_expect_tx(&full_bar[st], (uint32_t)((2 + npan) * WG_PANEL));
           const int row = (int)((kb0 + it) * WG_BK);
           for (int c = 0; c < 2; ++c) {
@@ -1818,7 +1825,9 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const uint32_t idesc = make_idesc_bf16(128, N, true, true);
         for (int it = 0; it < nkb; ++it) {
           const int st = it % WG_STAGES;
+          if ((it & 15) == 0) tr.ev(3, it);
           mbar_wait(&full_bar[st], (uint32_t)(it / WG_STAGES) & 1u);
+          if ((it & 15) == 0) tr.ev(16, it);
           tc_fence_after_sync();
           const uint32_t sa = smem_u32(stage_a + st * WG_A_BYTES), sb = smem_u32(stage_b + st * WG_B_BYTES);
 #pragma unroll
@@ -1836,7 +1845,9 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       const int et = (warp - 2) * 32 + lane;
       float* stg = reinterpret_cast<float*>(smem);  // [128][N + 1]
       const int lds = N + 1;
+      tr.ev(5, 0);
       mbar_wait(&acc_full, 0);
+      tr.ev(6, 0);
       tc_fence_after_sync();
       uint32_t v[32];
       for (int c0 = 0; c0 < N; c0 += 32) {
@@ -1876,8 +1887,10 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       }
     }
   }
+  tr.ev(32, 0);
   tc_fence_before_sync();
   __syncthreads();
+  tr.ev(33, 0);
   if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
@@ -1914,6 +1927,7 @@ static int launch_wgrad_umma_at(wn_model* m, const bf16* A, int lda, int a_col0,
   wa.out = out; wa.layers = m->d_layers; wa.grads = grads; wa.mode = mode; wa.D = m->a.n_dil; wa.ldo = ldo;
   wa.M_total = M_total; wa.N = N; wa.a_col0 = a_col0; wa.out_col0 = out_col0;
   wa.kblocks_total = (rows + WG_BK - 1) / WG_BK;
+  wa.trace = g_trace_layer == -3 ? g_trace_buf : nullptr;
   const int m_tiles = (M_total + 127) / 128;
   const int sms = std::max(1, m->sm_count);
   int64_t splits = std::max<int64_t>(1, std::min<int64_t>(wa.kblocks_total, sms / m_tiles));

@@ -33,7 +33,15 @@ torch.cuda.synchronize()
 buf = torch.zeros(32 * 2048 + 4 * 1024 + 128, dtype=torch.int64, device="cuda")
 buf[32 * 2048 + 4096::2] = 2 ** 62
 L = len(eng.reg.saves)
-if which in ("postfwd", "postbwd"):
+if which == "wgrad":
+    # layer -3 selects k_wgrad_umma: every launch of the backward logs, the LAST one (SKIP gradient) wins
+    eng.forward(wav, ids)
+    torch.cuda.synchronize()
+    lib.wn_debug_trace(buf.data_ptr(), -3)
+    eng.backward_phases(0, 1)
+    torch.cuda.synchronize()
+    lib.wn_debug_trace(None, -1)
+elif which in ("postfwd", "postbwd"):
     # layer -2 selects the post-net kernels (train_umma.cu); both log into the same buffer, so trace one at a time
     if which == "postfwd":
         lib.wn_debug_trace(buf.data_ptr(), -2)
@@ -111,6 +119,9 @@ names = {1: "prod:wait_free", 2: "prod:got_free", 3: "mma:issueA", 4: "mma:issue
          16: "mma:doneA", 17: "mma:doneB", 18: "e0:begin", 19: "e0:in_full", 20: "e0:done",
          30: "k:entry", 31: "k:init_done", 32: "k:role_done", 33: "k:all_done", 34: "k:bar_init", 35: "k:bias",
          36: "k:tmem_alloc", 37: "k:synced"}
+if which == "wgrad":
+    names = {1: "prod:wait_empty", 2: "prod:got_empty", 3: "mma:wait_full", 16: "mma:stage_full", 5: "epi:wait_acc",
+             6: "epi:acc_full", 30: "k:entry", 31: "k:pdl_wait_done", 32: "k:role_done", 33: "k:all_done"}
 if which in ("postfwd", "postbwd"):
     names = {1: "prod:wait_empty", 2: "prod:got_empty", 3: "mma:wait_acc_empty", 4: "mma:gemm_begin", 16: "mma:stage_full",
              17: "mma:gemm_issued", 5: "epi:wait_acc", 6: "epi:acc_full", 7: "epi:acc_released", 8: "epi:staging_free",
