@@ -226,6 +226,10 @@ int wn_selftest_umma_gemm(const void* d_a, const void* d_b, float* d_c, int32_t 
  * is the slow one in memory) through the split-K weight-gradient kernel; zero d_c first. */
 int wn_selftest_umma_gemm_tn(const void* d_a, const void* d_b, float* d_c, int32_t M, int32_t N,
                              int32_t K, void* stream);
+/* the same contraction on CTA pairs (tcgen05 cta_group::2): two CTAs of a cluster share one copy of every B block;
+ * M any, N multiple of 32 <= 256, K multiple of 64 */
+int wn_selftest_umma_gemm_pair(const void* d_a, const void* d_b, float* d_c, int32_t M, int32_t N,
+                               int32_t K, void* stream);
 
 /* Per-category kernel timing with CUDA events recorded on the launch stream around every kernel
  * launch (bench.py's roofline figures).  Categories: 0 prep/embed/SAVE, 1 layer forward, 2 post-net

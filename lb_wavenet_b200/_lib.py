@@ -76,6 +76,7 @@ SIGNATURES = {
     "wn_codes_u8_to_i32": (C.c_int, [_vp, _vp, _i64, _vp]),
     "wn_selftest_umma_gemm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "wn_selftest_umma_gemm_tn": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "wn_selftest_umma_gemm_pair": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "wn_prof_enable": (C.c_int, [_i32]),
     "wn_debug_trace": (C.c_int, [_vp, _i32]),
     "wn_prof_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(_i64)]),

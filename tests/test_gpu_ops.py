@@ -71,6 +71,23 @@ def test_umma_selftest_gemm(lib, sw, M, N, K):
     assert err <= 1e-3 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (256, 256, 256), (512, 128, 192), (300, 64, 960)])
+def test_umma_selftest_gemm_cta_pair(lib, M, N, K):
+    """The same contraction on CTA pairs (tcgen05 cta_group::2): a cluster of two CTAs shares one copy of every B block
+    (each loads half of its rows), the leader's M = 256 MMAs read both CTAs' shared memory and fill both CTAs' tensor
+    memory.  The recipe check for moving the post-net GEMMs onto pairs."""
+    from lb_wavenet_b200 import _lib
+    g = torch.Generator().manual_seed(M * 5 + N * 3 + K)
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16).cuda()
+    B = torch.randn(N, K, generator=g).to(torch.bfloat16).cuda()
+    Cd = torch.zeros(M, N, dtype=torch.float32, device="cuda")
+    _lib.check(lib.wn_selftest_umma_gemm_pair(A.data_ptr(), B.data_ptr(), Cd.data_ptr(), M, N, K, _lib.cur_stream()))
+    torch.cuda.synchronize()
+    ref = A.float().cpu() @ B.float().cpu().T
+    err = (Cd.cpu() - ref).abs().max().item()
+    assert err <= 1e-3 * max(1.0, ref.abs().max().item()), err
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 256, 640), (960, 256, 1000), (64, 64, 200), (256, 96, 4096), (200, 16, 77)])
 def test_umma_selftest_gemm_tn_mn_major(lib, M, N, K):
     """The split-K weight-gradient kernel (both operands MN-major, TMA SW128 panels, fp32 atomics) against
