@@ -115,6 +115,13 @@ __device__ __forceinline__ void epi_bar_sync256() { asm volatile("bar.sync 1, 25
 // Persistent: one CTA per SM loops over 128-row tiles.  TMEM holds two 256-column accumulators whose roles rotate
 // with the tile parity p: GEMM1 -> buf[p], GEMM2 -> buf[p^1], GEMM3 -> buf[p]; therefore the MMA warp can issue
 // tile i+1's skip GEMM (the long one, K = L*D) while the epilogue warps are still busy with tile i's loss.
+// PAIR: the same kernel on CTA pairs (clusters of two, tcgen05 cta_group::2).  The kernel runs at the rate the L2 delivers
+// its operands (~35 B/clk/SM) and three quarters of them are weights re-streamed for every 128-row tile: in a pair each
+// CTA loads only HALF of every weight block (its N / 2 rows); the leader's M = 256 MMAs read both CTAs' shared memory
+// and fill both CTAs' tensor memory; everything else (A tiles, accumulators, epilogues, stores) stays per CTA.  What
+// the MMA issuer waits for -- stage landed, accumulator drained, activation tile written -- it waits for from BOTH
+// CTAs (TMA completions and arrivals directed at the leader's barriers); what it signals, it multicasts.
+template <bool PAIR>
 __global__ void __launch_bounds__(UPOST_P_THREADS, 1)
 k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_wsT,
                 const __grid_constant__ CUtensorMap map_w1T, const __grid_constant__ CUtensorMap map_w2T,
@@ -122,11 +129,13 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
                 const __grid_constant__ CUtensorMap map_dlog, PostUmmaArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* stage_a = smem;                                  // USTAGES x 16 KB
-  unsigned char* stage_b = smem + USTAGES * UA_BYTES;             // USTAGES x 32 KB
-  unsigned char* htile = stage_b + USTAGES * UB_BYTES;            // 64 KB
+  constexpr int NSTG = PAIR ? 4 : USTAGES;                         // ring depth
+  constexpr int B_BYTES = PAIR ? UB_BYTES / 2 : UB_BYTES;           // this CTA's part of a weight block
+  unsigned char* stage_a = smem;                                  // NSTG x 16 KB
+  unsigned char* stage_b = smem + NSTG * UA_BYTES;                // NSTG x 32 (16) KB
+  unsigned char* htile = stage_b + NSTG * B_BYTES;                // 64 KB
   uint32_t* mtile = reinterpret_cast<uint32_t*>(htile + UH_BYTES);  // 4 KB: [128 rows][8 words] relu mask bits of the tile
-  __shared__ __align__(8) uint64_t full_bar[USTAGES], empty_bar[USTAGES], acc_full[2], acc_empty[2], h_ready[2];
+  __shared__ __align__(8) uint64_t full_bar[NSTG], empty_bar[NSTG], acc_full[2], acc_empty[2], h_ready[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[3 * 256];  // skip-bias sum | POST1_BIAS | POST2_BIAS (broadcast reads in the epilogues)
   __shared__ float x_mx[2][128], x_sum[2][128], x_vl[2][128];  // softmax partials exchanged between the two
@@ -135,7 +144,16 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = a.S, P = a.P, Q = a.Q;
   const int n_tiles = (int)((a.rows + UM - 1) / UM);
-  const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // work unit: a tile (one CTA) or a pair of consecutive tiles (one cluster; CTA `rank` takes tile 2 * pair + rank, which
+  // may lie beyond the batch: TMA zero fill in, clipped stores out)
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_work = PAIR ? (n_tiles + 1) / 2 : n_tiles;
+  const int n_my = (n_work - unit0 + n_units - 1) / n_units;
+  auto tile_row0 = [&](int i) -> int64_t {
+    const int64_t u = (int64_t)unit0 + (int64_t)i * n_units;
+    return (PAIR ? 2 * u + rank : u) * UM;
+  };
   for (int i = tid; i < 3 * 256; i += UPOST_P_THREADS) {
     float v = 0.f;
     if (a.use_bias) {
@@ -151,14 +169,14 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
   tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
 
   if (tid == 0) {
-    for (int i = 0; i < USTAGES; ++i) {
+    for (int i = 0; i < NSTG; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 256);
-      mbar_init(&h_ready[i], 1);
+      mbar_init(&acc_empty[i], PAIR ? 2 : 256);  // pair: one arrival per CTA (its elected epilogue thread), at the leader
+      mbar_init(&h_ready[i], PAIR ? 2 : 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&map_z);
@@ -166,9 +184,12 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
     tma_prefetch_desc(&map_w1T);
     tma_prefetch_desc(&map_w2T);
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair(&tmem_base_s, 512); else tmem_alloc(&tmem_base_s, 512);
+  }
   tc_fence_before_sync();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // both CTAs' barriers exist before a remote completion or arrival can hit them
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
 
@@ -176,35 +197,44 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
     // ===== TMA producer =====
     if (lane == 0) {
       int it = 0;
+      auto load = [&](void* dst, const CUtensorMap* mp, uint64_t* bar, int c0, int c1) {
+        if constexpr (PAIR) tma_load_2d_pair(dst, mp, bar, c0, c1); else tma_load_2d(dst, mp, bar, c0, c1);
+      };
       for (int i = 0; i < n_my; ++i) {
-        const int row0 = ((int)blockIdx.x + i * (int)gridDim.x) * UM;
+        const int row0 = (int)tile_row0(i);
         for (int kb = 0; kb < nkb1 + nkb2 + nkb3; ++kb, ++it) {
-          const int st = it % USTAGES;
+          const int st = it % NSTG;
           tr.ev(1, it);
-          mbar_wait(&empty_bar[st], ((uint32_t)(it / USTAGES) & 1u) ^ 1u);
+          mbar_wait(&empty_bar[st], ((uint32_t)(it / NSTG) & 1u) ^ 1u);
           tr.ev(2, it);
           unsigned char* sa = stage_a + st * UA_BYTES;
-          unsigned char* sb = stage_b + st * UB_BYTES;
+          unsigned char* sb = stage_b + st * B_BYTES;
+          // bytes of the WHOLE stage (pair: both CTAs' loads complete on the leader's barrier, which alone expects them)
+          const int nrows = kb < nkb1 ? S : kb < nkb1 + nkb2 ? P : Q;  // N of this contraction
+          const uint32_t bytes = (uint32_t)(nrows * 128 + (kb < nkb1 ? (PAIR ? 2 : 1) * UA_BYTES : 0));
+          if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[st], bytes);
+          const int brow = PAIR ? rank * (nrows / 2) : 0;  // this CTA's rows of the weight block
           if (kb < nkb1) {
-            mbar_expect_tx(&full_bar[st], (uint32_t)(UA_BYTES + S * 128));
-            tma_load_2d(sa, &map_z, &full_bar[st], kb * UKB, row0);
-            tma_load_2d(sb, &map_wsT, &full_bar[st], kb * UKB, 0);
+            load(sa, &map_z, &full_bar[st], kb * UKB, row0);
+            load(sb, &map_wsT, &full_bar[st], kb * UKB, brow);
           } else if (kb < nkb1 + nkb2) {
-            mbar_expect_tx(&full_bar[st], (uint32_t)(P * 128));
-            tma_load_2d(sb, &map_w1T, &full_bar[st], (kb - nkb1) * UKB, 0);
+            load(sb, &map_w1T, &full_bar[st], (kb - nkb1) * UKB, brow);
           } else {
-            mbar_expect_tx(&full_bar[st], (uint32_t)(Q * 128));
-            tma_load_2d(sb, &map_w2T, &full_bar[st], (kb - nkb1 - nkb2) * UKB, 0);
+            load(sb, &map_w2T, &full_bar[st], (kb - nkb1 - nkb2) * UKB, brow);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer (pair: the leader's only) =====
+    if (lane == 0 && rank == 0) {
       int it = 0;
       uint32_t use[2] = {0, 0};  // number of contractions issued into each accumulator buffer so far
-      const uint32_t idesc1 = make_idesc_bf16(UM, S), idesc2 = make_idesc_bf16(UM, P), idesc3 = make_idesc_bf16(UM, Q);
+      constexpr int MM = PAIR ? 2 * UM : UM;
+      const uint32_t idesc1 = make_idesc_bf16(MM, S), idesc2 = make_idesc_bf16(MM, P), idesc3 = make_idesc_bf16(MM, Q);
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (PAIR) mma_commit_pair(bar, 3); else mma_commit(bar);
+      };
       auto gemm = [&](int buf, int nkb, uint32_t idesc, bool a_from_htile) {
         tr.ev(3, it);
         mbar_wait(&acc_empty[buf], (use[buf] & 1u) ^ 1u);  // the previous contraction of this buffer has been drained
@@ -212,18 +242,21 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
         tc_fence_after_sync();
         const uint32_t acc = tmem_base + (uint32_t)buf * 256;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int st = it % USTAGES;
-          mbar_wait(&full_bar[st], (uint32_t)(it / USTAGES) & 1u);
+          const int st = it % NSTG;
+          mbar_wait(&full_bar[st], (uint32_t)(it / NSTG) & 1u);
           tr.ev(16, it);
           tc_fence_after_sync();
           const uint32_t sa = a_from_htile ? smem_u32(htile + kb * UA_BYTES) : smem_u32(stage_a + st * UA_BYTES);
-          const uint32_t sb = smem_u32(stage_b + st * UB_BYTES);
+          const uint32_t sb = smem_u32(stage_b + st * B_BYTES);
 #pragma unroll
-          for (int k = 0; k < UKB / 16; ++k)
-            mma_bf16_ss(acc, make_kmajor_desc(sa, 128, k * 32), make_kmajor_desc(sb, 128, k * 32), idesc, (kb | k) != 0);
-          mma_commit(&empty_bar[st]);
+          for (int k = 0; k < UKB / 16; ++k) {
+            const uint64_t ad = make_kmajor_desc(sa, 128, k * 32), bd = make_kmajor_desc(sb, 128, k * 32);
+            if constexpr (PAIR) mma_bf16_ss_pair(acc, ad, bd, idesc, (kb | k) != 0);
+            else mma_bf16_ss(acc, ad, bd, idesc, (kb | k) != 0);
+          }
+          commit(&empty_bar[st]);
         }
-        mma_commit(&acc_full[buf]);
+        commit(&acc_full[buf]);
         tr.ev(17, it);
         ++use[buf];
       };
@@ -258,13 +291,13 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
     };
     auto acc_release = [&](int buf) {
       tc_fence_before_sync();
-      mbar_arrive(&acc_empty[buf]);
+      if constexpr (!PAIR) mbar_arrive(&acc_empty[buf]);  // (pair: one arrival per CTA, by the elected thread after the barrier)
       tr.ev(7, n_epi++);
       ++use[buf];
     };
     for (int i = 0; i < n_my; ++i) {
       const int p = i & 1;
-      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * UM;
+      const int64_t row0 = tile_row0(i);
       const int64_t row = row0 + r;
       // ---- h1 = relu(skip_sum + bias) ----
       {
@@ -282,9 +315,14 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
         fence_proxy_async_smem();
         epi_bar_sync256();
         if (elected) {
-          mbar_arrive(&h_ready[0]);
+          if constexpr (PAIR) {
+            mbar_arrive_remote(&acc_empty[p], 0);
+            mbar_arrive_remote(&h_ready[0], 0);
+          } else {
+            mbar_arrive(&h_ready[0]);
+          }
           for (int kb = 0; kb < nkb2; ++kb) tma_store_2d(&map_h1, htile + kb * UA_BYTES, kb * UKB, (int)row0);
-          bulk_store_1d(a.hm1 + (size_t)row0 * 8, mtile, 128 * 32);  // (the mask buffers are padded to whole tiles)
+          if (row0 < a.rows) bulk_store_1d(a.hm1 + (size_t)row0 * 8, mtile, 128 * 32);  // (the mask buffers are padded to whole tiles)
           tma_store_commit();
         }
       }
@@ -304,9 +342,14 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
         fence_proxy_async_smem();
         epi_bar_sync256();
         if (elected) {
-          mbar_arrive(&h_ready[1]);
+          if constexpr (PAIR) {
+            mbar_arrive_remote(&acc_empty[p ^ 1], 0);
+            mbar_arrive_remote(&h_ready[1], 0);
+          } else {
+            mbar_arrive(&h_ready[1]);
+          }
           for (int kb = 0; kb < nkb3; ++kb) tma_store_2d(&map_h2, htile + kb * UA_BYTES, kb * UKB, (int)row0);
-          bulk_store_1d(a.hm2 + (size_t)row0 * 8, mtile, 128 * 32);
+          if (row0 < a.rows) bulk_store_1d(a.hm2 + (size_t)row0 * 8, mtile, 128 * 32);
           tma_store_commit();
         }
       }
@@ -374,6 +417,7 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
         fence_proxy_async_smem();
         epi_bar_sync256();
         if (elected) {
+          if constexpr (PAIR) mbar_arrive_remote(&acc_empty[p], 0);
           for (int kb = 0; kb < Q / UKB; ++kb) tma_store_2d(&map_dlog, htile + kb * UA_BYTES, kb * UKB, (int)row0);
           tma_store_commit();
         }
@@ -399,7 +443,10 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if constexpr (PAIR) cluster_sync_all();  // neither CTA leaves while the other may still be served by its memories
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // =====================================================================================================
@@ -770,9 +817,13 @@ int launch_post_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws, 
   CUtensorMap mz, mwsT, mw1T, mw2T, mh1, mh2, mdl;
   int rc;
   if ((rc = map2d(&mz, ws + wl.z, LD, (uint64_t)rows, UKB, UM))) return rc;
-  if ((rc = map2d(&mwsT, ws + wl.wsT, LD, S, UKB, (uint32_t)S))) return rc;
-  if ((rc = map2d(&mw1T, ws + wl.w1T, S, P, UKB, (uint32_t)P))) return rc;
-  if ((rc = map2d(&mw2T, ws + wl.w2T, P, Q, UKB, (uint32_t)Q))) return rc;
+  static const bool single = getenv("WN_POST_SINGLE") != nullptr;  // A/B: one CTA per tile as in round 1
+  const bool pair = !single && m->sm_count >= 2;
+  // CTA pairs: every CTA loads half of the rows of a weight block
+  const uint32_t bdiv = pair ? 2 : 1;
+  if ((rc = map2d(&mwsT, ws + wl.wsT, LD, S, UKB, (uint32_t)S / bdiv))) return rc;
+  if ((rc = map2d(&mw1T, ws + wl.w1T, S, P, UKB, (uint32_t)P / bdiv))) return rc;
+  if ((rc = map2d(&mw2T, ws + wl.w2T, P, Q, UKB, (uint32_t)Q / bdiv))) return rc;
   if ((rc = map2d(&mh1, ws + wl.h1, S, (uint64_t)rows, UKB, UM))) return rc;
   if ((rc = map2d(&mh2, ws + wl.h2, P, (uint64_t)rows, UKB, UM))) return rc;
   if ((rc = map2d(&mdl, ws + wl.dlogits, Q, (uint64_t)rows, UKB, UM))) return rc;
@@ -791,13 +842,37 @@ int launch_post_fwd_umma(wn_model* m, const float* d_params, unsigned char* ws, 
   pa.rows = rows;
   pa.hm1 = reinterpret_cast<uint32_t*>(ws + wl.hm1);
   pa.hm2 = reinterpret_cast<uint32_t*>(ws + wl.hm2);
+  if (pair) {
+    // CTA pairs: every CTA loads half of the rows of a weight block
+    const size_t smem = (size_t)4 * (UA_BYTES + UB_BYTES / 2) + UH_BYTES + 4096 + 1024;
+    WN_CUDA_CHECK(cudaFuncSetAttribute(k_post_fwd_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope ps(PROF_POST_FWD, st);
+    const int n_pairs = (int)((rows + 2 * UM - 1) / (2 * UM));
+    int cap = m->sm_count;  // (test knob WN_PERSIST_GRID: many pairs per cluster)
+    if (const char* e = getenv("WN_PERSIST_GRID")) if (atoi(e) > 0) cap = std::max(2, std::min(cap, atoi(e)));
+    const int clusters = std::max(1, std::min(n_pairs, cap / 2));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(UPOST_P_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    WN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_post_fwd_umma<true>, mz, mwsT, mw1T, mw2T, mh1, mh2, mdl, pa));
+    WN_LAUNCH_CHECK();
+    return WN_OK;
+  }
   const size_t smem = (size_t)USTAGES * (UA_BYTES + UB_BYTES) + UH_BYTES + 4096 + 1024;
-  WN_CUDA_CHECK(cudaFuncSetAttribute(k_post_fwd_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  WN_CUDA_CHECK(cudaFuncSetAttribute(k_post_fwd_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps(PROF_POST_FWD, st);
   const int n_tiles = (int)((rows + UM - 1) / UM);
   int grid = std::max(1, std::min(n_tiles, m->sm_count));
   if (const char* e = getenv("WN_PERSIST_GRID")) if (atoi(e) > 0) grid = std::max(1, std::min(grid, atoi(e)));
-  k_post_fwd_umma<<<grid, UPOST_P_THREADS, smem, st>>>(mz, mwsT, mw1T, mw2T, mh1, mh2, mdl, pa);
+  k_post_fwd_umma<false><<<grid, UPOST_P_THREADS, smem, st>>>(mz, mwsT, mw1T, mw2T, mh1, mh2, mdl, pa);
   WN_LAUNCH_CHECK();
   return WN_OK;
 }
