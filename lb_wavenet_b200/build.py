@@ -20,7 +20,7 @@ SOURCES = ["model.cpp", "dealer.cpp", "train_kernels.cu", "train_umma.cu", "laye
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
-]
+] + os.environ.get("NVCC_EXTRA", "").split()  # e.g. NVCC_EXTRA=-DWN_POST_TRACE: timeline hooks in the post-net kernels
 
 
 def _nvcc() -> str:

@@ -124,6 +124,19 @@ __device__ __forceinline__ uint4 ldg_nc_v4_pred(const void* p, bool pred) {
 __device__ __forceinline__ uint4 ldg_nc_v4_pinned(const void* p) { return ldg_nc_v4_pred(p, true); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// The same interface compiled to nothing: the post-net and weight-gradient kernels log only when the library is built
+// with -DWN_POST_TRACE (tools/trace_layer.py postfwd | postbwd | wgrad); left in, the hooks cost their single-thread
+// producer / issuer loops ~0.02 ms per step each.
+struct NoTracer {
+  __device__ __forceinline__ void init(long long*, int, bool) {}
+  __device__ __forceinline__ void ev(int, int) {}
+};
+#ifdef WN_POST_TRACE
+using PostTracer = Tracer;
+#else
+using PostTracer = NoTracer;
+#endif
+
 // ---- math ------------------------------------------------------------------------------
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;

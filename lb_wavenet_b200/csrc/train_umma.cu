@@ -165,7 +165,7 @@ k_post_fwd_umma(const __grid_constant__ CUtensorMap map_z, const __grid_constant
     bias_s[i] = v;
   }
   const int nkb1 = (a.LD + UKB - 1) / UKB, nkb2 = S / UKB, nkb3 = P / UKB;
-  Tracer tr;
+  PostTracer tr;
   tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
 
   if (tid == 0) {
@@ -550,7 +550,7 @@ k_post_bwd_umma(const __grid_constant__ CUtensorMap map_dlog, const __grid_const
   const int n_my = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int nkb4 = Q / UKB, nkb5 = P / UKB, nkb6 = S / UKB;
   const int nchunk = (LD + 255) / 256;
-  Tracer tr;
+  PostTracer tr;
   tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
 
   if (tid == 0) {
@@ -1853,7 +1853,7 @@ k_wgrad_umma(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   while (ncols < (uint32_t)N) ncols <<= 1;
 
   pdl_launch_dependents();
-  Tracer tr;
+  PostTracer tr;
   tr.init(a.trace, warp, blockIdx.x == 0 && blockIdx.y == 0 && lane == 0);
   tr.ev(30, 0);
   if (tid == 0) {
