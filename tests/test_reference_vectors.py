@@ -1,0 +1,212 @@
+"""The oracle -- and, on a GPU, the CUDA path -- against vectors produced by the REFERENCE'S OWN PYTHON.
+
+tests/golden/reference_*.npz were written by tests/golden/make_reference_vectors.py, which imports tmodel.py / arch.py /
+ops.py / data.py unmodified from the reference tree and runs them on oracle/tf1_shim (TensorFlow itself is not
+installable here).  Inputs and parameters are rebuilt from the seeds that script exports; nothing here reads
+/root/reference.
+"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wavenet_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("make_reference_vectors", os.path.join(HERE, "golden", "make_reference_vectors.py"))
+G = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(G)
+
+
+def _golden(name):
+    return np.load(os.path.join(HERE, "golden", "reference_%s.npz" % name))
+
+
+def _close(a, b, rtol, atol=0.0):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() <= atol + rtol * max(np.abs(b).max(), 1e-300) if a.size else True
+
+
+# ---------------------------------------------------------------- training graph (tmodel.py:284-339) -------------
+@pytest.mark.parametrize("name", sorted(G.TRAIN_CASES))
+@pytest.mark.parametrize("conv_impl", ["taps", "conv1d"])
+def test_oracle_training_graph_equals_the_reference_run(name, conv_impl):
+    """Two consecutive stages with the SAVE state carried by the reference itself: loss, logits, every gradient (a
+    strided sample of each tensor + its norm), the SAVE variables after each stage and the two counters.  fp64 on both
+    sides: agreement to 1e-9."""
+    arch, B, T, l2, _ = G.TRAIN_CASES[name]
+    a = G.oracle_arch(arch)
+    gold = _golden("train_" + name)
+    p = G.train_params(name)
+    # variable names and creation order are the checkpoint contract (arch.py:112-142)
+    assert list(gold["var_order"]) == [k for k in O.param_shapes(a, B).keys()]
+    n_valid_cumul = 0
+    for stage in range(G.N_STAGES):
+        wav, ids, mel = G.train_inputs(name, stage)
+        pt, save, kinds = O.to_torch_params(a, p, B, torch.float64)
+        w, i = torch.as_tensor(wav).long(), torch.as_tensor(ids).long()
+        mt = None if mel is None else torch.as_tensor(mel, dtype=torch.float64)
+        fwd = O.train_forward(a, pt, save, w, i, torch.float64, conv_impl=conv_impl, mel=mt)
+        L = O.loss_fn(a, fwd.logits, w, i, pt, kinds, l2)
+        L.total.backward()
+        s = "s%d_" % stage
+        assert abs(float(L.total) - float(gold[s + "loss"])) <= 1e-10 * abs(float(gold[s + "loss"])), (stage, float(L.total))
+        assert _close(fwd.logits.detach().numpy()[:, ::4, :], gold[s + "logits"], 1e-6)  # stored as float32
+        for k, v in pt.items():
+            g = v.grad.numpy() if v.grad is not None else np.zeros(tuple(v.shape))
+            ref = gold[s + "grad_" + k]
+            assert _close(G.sample_of(g), ref, 1e-9, 1e-14), (stage, k)
+            assert abs(np.sqrt((g ** 2).sum()) - float(gold[s + "gradnorm_" + k])) <= 1e-9 * max(float(gold[s + "gradnorm_" + k]), 1e-12), (stage, k)
+        n_valid_cumul += L.n_valid
+        assert int(gold[s + "global_step"]) == stage + 1  # tmodel.py:276
+        assert int(gold[s + "valid_samples"]) == n_valid_cumul  # tmodel.py:277
+        for li, ((b, bl), dil) in enumerate(zip(a.layer_ids(), a.dilations())):
+            key = "SAVE_%d_%d_%d" % (dil, b, bl)
+            assert _close(fwd.new_save[li].numpy(), gold[s + key], 1e-12, 1e-15), (stage, key)
+            p[key] = fwd.new_save[li].numpy()  # carried into the next stage (tmodel.py:165)
+
+
+def test_reference_run_covers_the_quirks_the_oracle_documents():
+    """The r32 case holds an out-of-range code at a valid position: in the reference run its label row is all zero, so
+    it adds nothing to the loss yet is counted in n_valid, and its logits row still receives softmax as gradient (TF's
+    fused xent kernel) -- the oracle statement of that (loss_fn) is what the test above compares gradients through.
+    Here: dropping the position from the mask changes the oracle's loss, i.e. the case is sensitive to the quirk."""
+    name = "r32"
+    arch, B, T, l2, _ = G.TRAIN_CASES[name]
+    a = G.oracle_arch(arch)
+    p = G.train_params(name)
+    wav, ids, _ = G.train_inputs(name, 0)
+    assert wav[0, 9] == -1 and ids[0, 9] != 0
+    pt, save, kinds = O.to_torch_params(a, p, B, torch.float64, requires_grad=False)
+    w = torch.as_tensor(wav).long()
+    fwd = O.train_forward(a, pt, save, w, torch.as_tensor(ids).long(), torch.float64)
+    L1 = O.loss_fn(a, fwd.logits, w, torch.as_tensor(ids).long(), pt, kinds, l2)
+    ids2 = ids.copy()
+    ids2[0, 9] = 0
+    L2 = O.loss_fn(a, fwd.logits, w, torch.as_tensor(ids2).long(), pt, kinds, l2)
+    assert L1.n_valid == L2.n_valid + 1 and abs(float(L1.total) - float(L2.total)) > 1e-4
+    assert abs(float(L1.total) - float(_golden("train_r32")["s0_loss"])) < 1e-9
+
+
+# ---------------------------------------------------------------- mu-law (ops.py:4-39) ---------------------------
+def test_mu_law_equals_the_reference_run():
+    gold = _golden("mu")
+    x = G.mu_inputs()
+    # the reference's two statements: the numpy twins (ops.py:23-39) run as they are, the tf ones through the shim in float32
+    assert np.array_equal(O.mu_encode_np(x), gold["codes_np"]) or _mu_diff_is_numpy2_promotion(x, gold["codes_np"])
+    assert np.array_equal(O.mu_encode_np(x), gold["codes_tf"])
+    dec = O.mu_decode_np(np.arange(256))
+    assert np.array_equal(dec, gold["decoded_np"])  # ops.mu_decode_np run as it is
+    # ops.mu_decode through the shim: torch's float32 pow against numpy's, a last-bit difference of the shim's arithmetic
+    assert np.abs(dec - gold["decoded_tf"]).max() <= 1.2e-7
+
+
+def _mu_diff_is_numpy2_promotion(x, codes_np):
+    """ops.mu_encode_np run under numpy >= 2 divides by the float64 scalar log1p(mu) in float64 (NEP 50 keeps float32
+    only for python scalars) -- the reference was written against numpy 1.x, where every intermediate stays float32
+    (oracle mu_encode_np docstring).  Differences, if any, are single codes at float32 threshold neighbours."""
+    d = O.mu_encode_np(x).astype(np.int64) - codes_np.astype(np.int64)
+    return np.abs(d).max() <= 1 and (d != 0).mean() < 1e-3
+
+
+# ---------------------------------------------------------------- slot dealer (data.py:110-227) ------------------
+def _deal_catalog():
+    return G.deal_files()
+
+
+def test_oracle_dealer_equals_the_reference_run():
+    c = G.DEAL_CASE
+    gold = _golden("dealer")
+    files, order = _deal_catalog(), G.deal_order()
+
+    def file_iter():
+        for cnt, idx in enumerate(order, start=1):
+            yield cnt, files[idx][0], files[idx][1]
+    T = O.align_slice_sz(c["slice_sz"], c["mel_hop_sz"])
+    gen = O.gen_slice_batches(file_iter(), c["batch_sz"], T, c["recep_field_sz"], c["mel_hop_sz"])
+    for n in range(c["n_batches"]):
+        cnt, wav, ids = next(gen)
+        assert cnt == int(gold["b%d_count" % n]), n
+        assert np.array_equal(wav, gold["b%d_wav" % n]) and np.array_equal(ids, gold["b%d_ids" % n]), n
+
+
+def test_product_dealer_equals_the_reference_run():
+    """the C slot dealer behind MaskedSliceWav (wn_deal_plan / wn_deal_fill), mel frames included, whole and sharded"""
+    from lb_wavenet_b200.data import SlotDealer
+    c = G.DEAL_CASE
+    gold = _golden("dealer")
+    files, order = _deal_catalog(), G.deal_order()
+    B, T = c["batch_sz"], O.align_slice_sz(c["slice_sz"], c["mel_hop_sz"])
+
+    def dealer(lo, hi):
+        d = SlotDealer(files, B, T, c["recep_field_sz"], c["mel_hop_sz"], 0, 0, slot_lo=lo, slot_hi=hi, quiet=True,
+                       mel_channels=c["mel_spectrum_sz"])
+        d._order = iter(int(i) for i in order)  # the reference run's file order instead of the dealer's own shuffle
+        d._order_buf = np.empty(0, np.int32)
+        return d
+    whole, shard = dealer(0, B), dealer(1, 3)
+    for n in range(c["n_batches"]):
+        cnt, wav, ids = whole.next_batch()
+        assert cnt == int(gold["b%d_count" % n]), n
+        assert np.array_equal(wav, gold["b%d_wav" % n]) and np.array_equal(ids, gold["b%d_ids" % n]), n
+        assert np.array_equal(whole.last_mel, gold["b%d_mel" % n]), n
+        cnt2, wav2, ids2 = shard.next_batch()
+        assert cnt2 == cnt and np.array_equal(wav2, wav[1:3]) and np.array_equal(ids2, ids[1:3])
+        assert np.array_equal(shard.last_mel, gold["b%d_mel" % n][1:3])
+
+
+# ---------------------------------------------------------------- CUDA path --------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(G.TRAIN_CASES))
+def test_cuda_training_step_against_the_reference_run(name):
+    """wn_train_forward / wn_train_backward through the C ABI on the reference run's inputs, two stages with carried
+    SAVE: logits and loss within the bf16 contract of DESIGN.md section 4 (operands and stored activations are bf16, the
+    reference is fp32 -- here fp64), gradients per tensor within the bound the emulated-oracle tests establish."""
+    from lb_wavenet_b200 import config
+    from lb_wavenet_b200.engine import TrainEngine
+    arch, B, T, l2, _ = G.TRAIN_CASES[name]
+    gold = _golden("train_" + name)
+    p = G.train_params(name)
+    eng_arch = config.engine_arch(config.normalize_arch(dict(arch)))
+    eng = TrainEngine(eng_arch, B)
+    eng.load_state(p)
+    a = G.oracle_arch(arch)
+    for stage in range(G.N_STAGES):
+        wav, ids, mel = G.train_inputs(name, stage)
+        kw = {} if mel is None else dict(mel=torch.as_tensor(mel).cuda())
+        logits = eng.forward(torch.as_tensor(wav).cuda(), torch.as_tensor(ids).cuda(), want_logits=True, **kw)
+        eng.backward()
+        torch.cuda.synchronize()
+        s = "s%d_" % stage
+        lg = logits.float().cpu().numpy()[:, ::4, :arch["n_quant"]]
+        ref = gold[s + "logits"]
+        assert np.abs(lg - ref).max() <= 0.03 * max(1.0, np.abs(ref).max()), (stage, np.abs(lg - ref).max())
+        st = eng.read_stats()
+        # total loss = mean xent + l2_factor * L2 (tmodel.py:261); the engine reports the parts
+        xent_ref = float(gold[s + "loss"]) - l2 * float(O.l2_term(*_torch_params(a, p, B)))
+        assert abs(st["xent_sum"] / max(st["n_valid"], 1) - xent_ref) <= 5e-3 * xent_ref, (stage, st, xent_ref)
+        worst = {}
+        for k in eng.reg.params:
+            g = eng.view(k, eng.grads).float().cpu().numpy() / max(st["n_valid"], 1)  # unnormalised, no L2 term
+            if eng.reg.params[k].kind == 0 and "BIAS" not in k:
+                g = g + l2 * np.asarray(p[k], np.float64).reshape(g.shape)  # tmodel.py:250-261
+            refs = gold[s + "grad_" + k]
+            got = G.sample_of(g)
+            nrm = float(gold[s + "gradnorm_" + k])
+            if nrm == 0:
+                continue
+            scale = nrm / np.sqrt(g.size) * np.sqrt(got.size)  # norm of a sample of that size
+            worst[k] = float(np.sqrt(((got - refs) ** 2).sum()) / max(scale, 1e-30))
+        bad = {k: v for k, v in worst.items() if v > 0.12}
+        assert not bad, (stage, bad)
+        for li, ((b, bl), dil) in enumerate(zip(a.layer_ids(), a.dilations())):
+            key = "SAVE_%d_%d_%d" % (dil, b, bl)
+            sv = eng.save_view(li).float().cpu().numpy()[:, :, :arch["n_res"]]
+            assert np.abs(sv - gold[s + key]).max() <= 0.02 * max(1.0, np.abs(gold[s + key]).max()), (stage, key)
+
+
+def _torch_params(a, p, B):
+    pt, _, kinds = O.to_torch_params(a, p, B, torch.float64, requires_grad=False)
+    return pt, kinds
