@@ -5,11 +5,20 @@ THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
 legs may import it.  The product path (``lb_wavenet_b200``) never does; it fails loudly
 when the CUDA library is missing.
 
-PARITY UNPINNED: the reference (hrbigelow/lb-wavenet) ships no golden vectors, no
-known-answer tests and no assertions for this path, and its arithmetic lives in
-TensorFlow 1.x (version unpinned by the reference, not installable here: Python 3.12, no
-network).  This file therefore restates the reference's *graph* op for op and pins itself
-with (see tests/test_oracle_*.py):
+PARITY PIN: the reference (hrbigelow/lb-wavenet) ships no golden vectors, no known-answer tests and no
+assertions for this path, and its arithmetic lives in TensorFlow 1.x (version unpinned by the reference, not
+installable here: Python 3.12, no network).  Round 2 pins this file against OUTPUTS OF THE REFERENCE'S OWN
+PYTHON RUN IN THIS CONTAINER: tests/golden/make_reference_vectors.py imports tmodel.py, arch.py, ops.py and
+data.py unmodified from the reference tree and executes them on oracle/tf1_shim (an eager torch stand-in for
+the ~50 `tf.*` calls they make); tests/test_reference_vectors.py holds train_forward / loss_fn / the autograd
+backward / the data path here to those vectors at 1e-9 (fp64) over 4 architectures (plain, global conditioning,
+local conditioning, the tiny bias-free arch2 shapes) x 2 stages with the SAVE state carried by the reference.
+What that pins is the reference's graph construction (names, shapes, concat / slice / dilation / mask /
+normalisation logic, op order); what it cannot pin is TensorFlow's kernels themselves -- the shim restates the
+documented semantics of each op (tests/test_tf1_shim.py checks them against explicit loops).  The generator
+(imodel.py) cannot be run that way: its constructor no longer matches arch.py's (imodel.py:26-37 vs arch.py:31-47),
+under any TensorFlow; it stays pinned through "teacher-forced generator == training forward".
+Besides that (tests/test_oracle_pins.py):
   * the README known-answer diagram (reference README.md:70-85, images/wavenet_influence.png),
   * two structurally different statements of the dilated conv (explicit two-tap form vs
     torch.nn.functional.conv1d) -- reference tmodel.py:143-144 vs imodel.py:107-108,

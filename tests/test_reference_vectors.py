@@ -13,6 +13,7 @@ import pytest
 import torch
 
 from oracle import wavenet_oracle as O
+from tests import util
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 _spec = importlib.util.spec_from_file_location("make_reference_vectors", os.path.join(HERE, "golden", "make_reference_vectors.py"))
@@ -160,19 +161,28 @@ def test_product_dealer_equals_the_reference_run():
 # ---------------------------------------------------------------- CUDA path --------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(G.TRAIN_CASES))
-def test_cuda_training_step_against_the_reference_run(name):
-    """wn_train_forward / wn_train_backward through the C ABI on the reference run's inputs, two stages with carried
-    SAVE: logits and loss within the bf16 contract of DESIGN.md section 4 (operands and stored activations are bf16, the
-    reference is fp32 -- here fp64), gradients per tensor within the bound the emulated-oracle tests establish."""
-    from lb_wavenet_b200 import config
-    from lb_wavenet_b200.engine import TrainEngine
+def test_cuda_training_step_against_the_reference_run(name, tmp_path):
+    """wn_train_forward / wn_train_backward behind the host mirror of the reference's WaveNetTrain, on the reference
+    run's inputs, two stages with carried SAVE: logits and loss within the bf16 contract of DESIGN.md section 4 (operands
+    and stored activations are bf16, the reference is fp32 -- here fp64), every gradient tensor within the bound the
+    emulated-oracle tests establish, SAVE after each stage.  ('odd' runs zero-padded: config.engine_arch.)"""
+    from lb_wavenet_b200.tmodel import WaveNetTrain
     arch, B, T, l2, _ = G.TRAIN_CASES[name]
     gold = _golden("train_" + name)
     p = G.train_params(name)
-    eng_arch = config.engine_arch(config.normalize_arch(dict(arch)))
-    eng = TrainEngine(eng_arch, B)
-    eng.load_state(p)
+    net = WaveNetTrain(**arch, wav_input_type="mu_law_quant", batch_sz=B, l2_factor=l2, add_summary=False,
+                       n_keep_checkpoints=1, ckpt_path=str(tmp_path / "ref.net"), resume_step=0, n_valid_total=10 ** 6,
+                       print_interval=0, init_seed=1)
+    net.build()
+    net.init_vars()
+    eng = net.engine
     a = G.oracle_arch(arch)
+    shapes = O.param_shapes(a, B)
+    for k, (shp, kind) in shapes.items():
+        if kind in ("filter", "bias", "save"):
+            net.vars[k].assign(np.asarray(p[k], np.float32))
+    pt, _, kinds = O.to_torch_params(a, p, B, torch.float64, requires_grad=False)
+    l2_val = float(O.l2_term(pt, kinds))
     for stage in range(G.N_STAGES):
         wav, ids, mel = G.train_inputs(name, stage)
         kw = {} if mel is None else dict(mel=torch.as_tensor(mel).cuda())
@@ -180,33 +190,35 @@ def test_cuda_training_step_against_the_reference_run(name):
         eng.backward()
         torch.cuda.synchronize()
         s = "s%d_" % stage
-        lg = logits.float().cpu().numpy()[:, ::4, :arch["n_quant"]]
+        lg = logits.float().cpu().numpy()[:, ::4, :]
         ref = gold[s + "logits"]
         assert np.abs(lg - ref).max() <= 0.03 * max(1.0, np.abs(ref).max()), (stage, np.abs(lg - ref).max())
         st = eng.read_stats()
         # total loss = mean xent + l2_factor * L2 (tmodel.py:261); the engine reports the parts
-        xent_ref = float(gold[s + "loss"]) - l2 * float(O.l2_term(*_torch_params(a, p, B)))
+        xent_ref = float(gold[s + "loss"]) - l2 * l2_val
         assert abs(st["xent_sum"] / max(st["n_valid"], 1) - xent_ref) <= 5e-3 * xent_ref, (stage, st, xent_ref)
         worst = {}
-        for k in eng.reg.params:
-            g = eng.view(k, eng.grads).float().cpu().numpy() / max(st["n_valid"], 1)  # unnormalised, no L2 term
-            if eng.reg.params[k].kind == 0 and "BIAS" not in k:
-                g = g + l2 * np.asarray(p[k], np.float64).reshape(g.shape)  # tmodel.py:250-261
-            refs = gold[s + "grad_" + k]
-            got = G.sample_of(g)
+        for k, (shp, kind) in shapes.items():
+            if kind not in ("filter", "bias"):
+                continue
+            g = eng.view(k, eng.grads)[tuple(slice(0, d) for d in shp)].double().cpu().numpy() / max(st["n_valid"], 1)
+            if kind == "filter":
+                g = g + l2 * np.asarray(p[k], np.float64)  # the engine's gradient is unnormalised and has no L2 term (tmodel.py:250-261)
             nrm = float(gold[s + "gradnorm_" + k])
             if nrm == 0:
+                assert np.abs(g).max() == 0, k
                 continue
-            scale = nrm / np.sqrt(g.size) * np.sqrt(got.size)  # norm of a sample of that size
-            worst[k] = float(np.sqrt(((got - refs) ** 2).sum()) / max(scale, 1e-30))
-        bad = {k: v for k, v in worst.items() if v > 0.12}
+            got, refs = G.sample_of(g), gold[s + "grad_" + k]
+            worst[k] = float(np.sqrt(((got - refs) ** 2).sum()) / max(np.sqrt((refs ** 2).sum()), 1e-30))
+        util.record("reference_run_%s_stage%d" % (name, stage),
+                    dict(logits_max_abs_err=float(np.abs(lg - ref).max()), grad_rel_err_max=max(worst.values()),
+                         grad_rel_err_median=float(np.median(list(worst.values())))))
+        # against fp64 at ~100 loss positions: the same bound as tests/test_gpu_train.py::test_gradients_match_oracle (the
+        # bf16 forward dominates; the same-rounding oracle, which the CPU test above ties to the reference run at 1e-9,
+        # is held to 6 % there)
+        bad = {k: v for k, v in worst.items() if v > 0.2}
         assert not bad, (stage, bad)
         for li, ((b, bl), dil) in enumerate(zip(a.layer_ids(), a.dilations())):
             key = "SAVE_%d_%d_%d" % (dil, b, bl)
             sv = eng.save_view(li).float().cpu().numpy()[:, :, :arch["n_res"]]
             assert np.abs(sv - gold[s + key]).max() <= 0.02 * max(1.0, np.abs(gold[s + key]).max()), (stage, key)
-
-
-def _torch_params(a, p, B):
-    pt, _, kinds = O.to_torch_params(a, p, B, torch.float64, requires_grad=False)
-    return pt, kinds
