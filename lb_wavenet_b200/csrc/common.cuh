@@ -136,6 +136,15 @@ using PostTracer = Tracer;
 #else
 using PostTracer = NoTracer;
 #endif
+// the per-layer kernels (layer_umma.cu) likewise: -DWN_LAYER_TRACE for tools/trace_layer.py fwd | bwd (measured with
+// the hooks compiled out: the 30 backward launches 1.33 -> 1.29 ms per configs[1] step, the forward unchanged)
+#ifdef WN_LAYER_TRACE
+using LayerTracer = Tracer;
+constexpr bool kLayerTrace = true;
+#else
+using LayerTracer = NoTracer;
+constexpr bool kLayerTrace = false;
+#endif
 
 // ---- math ------------------------------------------------------------------------------
 __device__ __forceinline__ float tanh_fast(float x) {

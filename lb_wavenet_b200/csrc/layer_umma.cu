@@ -180,10 +180,10 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_launch_dependents();  // the next layer's CTAs may take this SM's resources as soon as they are released
   if (tid == 0) n_done_s = 0x7fffffff;
-  Tracer tr;
+  LayerTracer tr;
   tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
   tr.ev(30, 0);
-  if (a.trace != nullptr && tid == 0) {  // per-CTA wall-clock start / SM id (tools/trace_layer.py)
+  if (kLayerTrace && a.trace != nullptr && tid == 0) {  // per-CTA wall-clock start / SM id (tools/trace_layer.py)
     unsigned long long gt;
     unsigned smid;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
@@ -488,7 +488,7 @@ k_layer_fwd_p_umma(const __grid_constant__ CUtensorMap map_x, const __grid_const
     a.tile_ctr[0] = 0;
     a.tile_ctr[1] = 0;
   }
-  if (a.trace != nullptr && tid == 0) {
+  if (kLayerTrace && a.trace != nullptr && tid == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 1] = (long long)gt;
@@ -629,7 +629,7 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
   };
   const Item item0{j0 / TPS, k_first + n_warm, n_warm, TPS};
   pdl_launch_dependents();
-  if (a.trace != nullptr && tid == 0) {  // kernel entry (before barrier init / TMEM allocation)
+  if (kLayerTrace && a.trace != nullptr && tid == 0) {  // kernel entry (before barrier init / TMEM allocation)
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 3] = (long long)gt;
@@ -676,9 +676,9 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
   tc_fence_after_sync();
   const uint32_t tm = tmem_base_s;
   pdl_wait();  // the layer above has finished writing (Y, P0) and reading the buffers this layer overwrites
-  Tracer tr;
+  LayerTracer tr;
   tr.init(a.trace, warp, blockIdx.x == 0 && lane == 0);
-  if (a.trace != nullptr && tid == 0) {  // per-CTA wall-clock start / SM id (tools/trace_layer.py)
+  if (kLayerTrace && a.trace != nullptr && tid == 0) {  // per-CTA wall-clock start / SM id (tools/trace_layer.py)
     unsigned long long gt;
     unsigned smid;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
@@ -1125,7 +1125,7 @@ k_layer_bwd_fused_umma(const __grid_constant__ CUtensorMap map_x, const __grid_c
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (a.trace != nullptr && tid == 0) {
+  if (kLayerTrace && a.trace != nullptr && tid == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     a.trace[32 * WN_TRACE_PER_WARP + 4 * blockIdx.x + 1] = (long long)gt;

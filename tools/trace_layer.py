@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """In-kernel timeline of the persistent layer kernels (developer aid, GPU box only).
 
-    python tools/trace_layer.py [fwd|bwd] [layer]
+    python tools/trace_layer.py [fwd|bwd] [layer]                 (library built with NVCC_EXTRA=-DWN_LAYER_TRACE)
     python tools/trace_layer.py postfwd | postbwd | wgrad     (library built with NVCC_EXTRA=-DWN_POST_TRACE)
 
 Runs BASELINE configs[1] once with tracing off, then one forward (+ backward) with wn_debug_trace pointing at a
