@@ -36,8 +36,28 @@ TRAIN_CASES = {
     # the reference's par/arch2.json channel counts, no biases
     "odd": (dict(n_blocks=2, n_block_layers=3, n_quant=256, n_res=3, n_dil=4, n_skip=8, n_post=6, n_gc_embed=0,
                  n_gc_category=0, n_lc_in=0, n_lc_out=0, lc_upsample=[], use_bias=False), 2, 32, 1e-2, 104),
+    # the reference's par/arch5.json as shipped -- the one architecture file train.py accepts as written: 5 x 10 layers,
+    # S = P = 512, 16-wide voice embedding over 376 categories, 80 -> 80 local conditioning upsampled 4 x 4 x 4 x 4 = 256
+    "arch5": (dict(n_blocks=5, n_block_layers=10, n_quant=256, n_res=32, n_dil=32, n_skip=512, n_post=512, n_gc_embed=16,
+                   n_gc_category=376, n_lc_in=80, n_lc_out=80, lc_upsample=[4, 4, 4, 4], use_bias=True), 2, 256, 1e-4, 105),
 }
 N_STAGES = 2
+SAMPLE_LIMIT = {"arch5": 48}  # elements stored per gradient tensor (default 256): arch5 has 760 variables
+LOGIT_STRIDE = {"arch5": 16}  # every k-th timestep of the logits is stored (default 4)
+
+
+def save_sample(x):
+    """what is stored of a SAVE variable: all of it up to 4096 elements, else a strided sample of 512"""
+    x = np.asarray(x)
+    return x if x.size <= 4096 else sample_of(x, 512)
+
+
+def sample_limit(name):
+    return SAMPLE_LIMIT.get(name, 256)
+
+
+def logit_stride(name):
+    return LOGIT_STRIDE.get(name, 4)
 
 
 def train_inputs(name, stage):
@@ -165,17 +185,17 @@ def run_train_case(tf, tmodel, name):
         grads_vars, loss = call_build(stage)
         names = {id(v): k for k, v in net.vars.items()}
         out["s%d_loss" % stage] = np.float64(loss.detach().numpy())
-        out["s%d_logits" % stage] = captured["logits"][:, ::4, :].astype(np.float32)
+        out["s%d_logits" % stage] = captured["logits"][:, ::logit_stride(name), :].astype(np.float32)
         out["s%d_global_step" % stage] = net.vars["GLOBAL_STEP"].numpy().copy()
         out["s%d_valid_samples" % stage] = net.vars["VALID_SAMPLES"].numpy().copy()
         for g, v in grads_vars:
             k = names[id(v)]
             g = np.zeros(v.shape) if g is None else g.detach().numpy()
-            out["s%d_grad_%s" % (stage, k)] = sample_of(g).astype(np.float64)
+            out["s%d_grad_%s" % (stage, k)] = sample_of(g, sample_limit(name)).astype(np.float64)
             out["s%d_gradnorm_%s" % (stage, k)] = np.float64(np.sqrt((g ** 2).sum()))
         for k, v in net.vars.items():
             if k.startswith("SAVE"):
-                out["s%d_%s" % (stage, k)] = v.numpy().astype(np.float64).copy()
+                out["s%d_%s" % (stage, k)] = save_sample(v.numpy().astype(np.float64)).copy()
     return out
 
 

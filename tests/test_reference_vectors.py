@@ -54,18 +54,18 @@ def test_oracle_training_graph_equals_the_reference_run(name, conv_impl):
         L.total.backward()
         s = "s%d_" % stage
         assert abs(float(L.total) - float(gold[s + "loss"])) <= 1e-10 * abs(float(gold[s + "loss"])), (stage, float(L.total))
-        assert _close(fwd.logits.detach().numpy()[:, ::4, :], gold[s + "logits"], 1e-6)  # stored as float32
+        assert _close(fwd.logits.detach().numpy()[:, ::G.logit_stride(name), :], gold[s + "logits"], 1e-6)  # stored as float32
         for k, v in pt.items():
             g = v.grad.numpy() if v.grad is not None else np.zeros(tuple(v.shape))
             ref = gold[s + "grad_" + k]
-            assert _close(G.sample_of(g), ref, 1e-9, 1e-14), (stage, k)
+            assert _close(G.sample_of(g, G.sample_limit(name)), ref, 1e-9, 1e-14), (stage, k)
             assert abs(np.sqrt((g ** 2).sum()) - float(gold[s + "gradnorm_" + k])) <= 1e-9 * max(float(gold[s + "gradnorm_" + k]), 1e-12), (stage, k)
         n_valid_cumul += L.n_valid
         assert int(gold[s + "global_step"]) == stage + 1  # tmodel.py:276
         assert int(gold[s + "valid_samples"]) == n_valid_cumul  # tmodel.py:277
         for li, ((b, bl), dil) in enumerate(zip(a.layer_ids(), a.dilations())):
             key = "SAVE_%d_%d_%d" % (dil, b, bl)
-            assert _close(fwd.new_save[li].numpy(), gold[s + key], 1e-12, 1e-15), (stage, key)
+            assert _close(G.save_sample(fwd.new_save[li].numpy()), gold[s + key], 1e-12, 1e-15), (stage, key)
             p[key] = fwd.new_save[li].numpy()  # carried into the next stage (tmodel.py:165)
 
 
@@ -190,7 +190,7 @@ def test_cuda_training_step_against_the_reference_run(name, tmp_path):
         eng.backward()
         torch.cuda.synchronize()
         s = "s%d_" % stage
-        lg = logits.float().cpu().numpy()[:, ::4, :]
+        lg = logits.float().cpu().numpy()[:, ::G.logit_stride(name), :]
         ref = gold[s + "logits"]
         assert np.abs(lg - ref).max() <= 0.03 * max(1.0, np.abs(ref).max()), (stage, np.abs(lg - ref).max())
         st = eng.read_stats()
@@ -208,7 +208,7 @@ def test_cuda_training_step_against_the_reference_run(name, tmp_path):
             if nrm == 0:
                 assert np.abs(g).max() == 0, k
                 continue
-            got, refs = G.sample_of(g), gold[s + "grad_" + k]
+            got, refs = G.sample_of(g, G.sample_limit(name)), gold[s + "grad_" + k]
             worst[k] = float(np.sqrt(((got - refs) ** 2).sum()) / max(np.sqrt((refs ** 2).sum()), 1e-30))
         util.record("reference_run_%s_stage%d" % (name, stage),
                     dict(logits_max_abs_err=float(np.abs(lg - ref).max()), grad_rel_err_max=max(worst.values()),
@@ -216,9 +216,18 @@ def test_cuda_training_step_against_the_reference_run(name, tmp_path):
         # against fp64 at ~100 loss positions: the same bound as tests/test_gpu_train.py::test_gradients_match_oracle (the
         # bf16 forward dominates; the same-rounding oracle, which the CPU test above ties to the reference run at 1e-9,
         # is held to 6 % there)
-        bad = {k: v for k, v in worst.items() if v > 0.2}
+        # (arch5: 50 layers at 512 loss positions -- the bf16 residual stream decorrelates over the depth, DESIGN.md section 4;
+        # tests/test_gpu_full.py holds the same stack to 8 % at the benchmark's stage length)
+        deep = a.n_layers >= 30
+        bad = {k: v for k, v in worst.items() if v > (0.4 if deep else 0.2)}
         assert not bad, (stage, bad)
+        assert float(np.median(list(worst.values()))) <= (0.2 if deep else 0.1)
+        save_worst = 0.0
         for li, ((b, bl), dil) in enumerate(zip(a.layer_ids(), a.dilations())):
             key = "SAVE_%d_%d_%d" % (dil, b, bl)
-            sv = eng.save_view(li).float().cpu().numpy()[:, :, :arch["n_res"]]
-            assert np.abs(sv - gold[s + key]).max() <= 0.02 * max(1.0, np.abs(gold[s + key]).max()), (stage, key)
+            sv = G.save_sample(eng.save_view(li).float().cpu().numpy()[:, :, :arch["n_res"]])
+            err = float(np.abs(sv - gold[s + key]).max() / max(1.0, np.abs(gold[s + key]).max()))
+            save_worst = max(save_worst, err)
+            # rows of the bf16 residual stream: one rounding (2^-9) per layer on top of the layers below
+            assert err <= (0.05 if deep else 0.02), (stage, key, err)
+        util.record("reference_run_%s_stage%d_save" % (name, stage), dict(save_rel_err_max=save_worst))
