@@ -109,13 +109,18 @@ cat = [(int(rng.integers(1, 11)), rng.integers(0, 256, int(rng.integers(300, 900
 lo, hi = ctx.slot_range(B)
 deal = SlotDealer(cat, B, T, net.get_recep_field_sz(), 1, 5, 0, lo, hi, quiet=True)
 losses = []
+first = None
 for step in range(3):
     _, w, i = deal.next_batch()
     losses.append(net.train_step(torch.as_tensor(w), torch.as_tensor(i), opt))
+    if step == 0:
+        torch.cuda.synchronize()
+        first = {k: v.tolist() for k, v in net.engine.export_state().items() if not k.startswith("SAVE")}
 torch.cuda.synchronize()
 if ctx.rank == 0:
     st = {k: v.tolist() for k, v in net.engine.export_state().items() if not k.startswith("SAVE")}
-    json.dump(dict(losses=losses, state=st, mode=net._allreduce_mode() if ctx.world > 1 else "none"), open(sys.argv[1], "w"))
+    json.dump(dict(losses=losses, state=st, first=first, mode=net._allreduce_mode() if ctx.world > 1 else "none"),
+              open(sys.argv[1], "w"))
 ctx.barrier()
 if ctx.world > 1:
     torch.distributed.destroy_process_group()
@@ -125,8 +130,12 @@ if ctx.world > 1:
 @pytest.mark.parametrize("mode", ["single", "buckets"])
 def test_two_rank_nccl_step_equals_one_rank_step(lib, tmp_path, mode):
     """3 optimiser steps with the 4 slots sharded over 2 GPUs (NCCL all-reduce of statistics + gradient arena, both
-    all-reduce schedules) == the same 3 steps on one GPU: losses to 1e-5 relative, weights to the fp32 atomics'
-    summation-order noise."""
+    all-reduce schedules) against the same 3 steps on one GPU.  After the FIRST step -- identical weights going in -- every
+    variable agrees to the fp32 atomics' summation-order noise (measured 2e-7 relative: tools/diag_two_rank.py).  Later
+    steps are compared as far as they are comparable at all: two runs of the SAME single-GPU program already differ by
+    2e-4 (step 2) and 3e-2 (step 3) in the bias gradients -- a last-bit difference in a weight flips the bf16 rounding
+    of its operand copy, and at random initialisation the bias gradients are small differences of large sums -- so the
+    bound there is the losses (1e-5) and what three Adam steps can move an element."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "rank.py"
@@ -142,11 +151,14 @@ def test_two_rank_nccl_step_equals_one_rank_step(lib, tmp_path, mode):
     assert b["mode"] == mode
     for la, lb in zip(a["losses"], b["losses"]):
         assert abs(la - lb) <= 1e-5 * abs(la), (a["losses"], b["losses"])
+    for k in a["first"]:
+        x, y = np.asarray(a["first"][k]), np.asarray(b["first"][k])
+        assert util.rel_err(y - 0, x - 0) <= 2e-6, (k, util.rel_err(y - 0, x - 0))
     for k in a["state"]:
         x, y = np.asarray(a["state"][k]), np.asarray(b["state"][k])
-        # 3 Adam steps of <= 1e-3 each; a gradient element near zero may flip its (sign-like) first steps
-        assert np.abs(x - y).max() <= 2.5e-3, k
-        assert util.rel_err(y - 0, x - 0) <= 2e-3, k
+        # 3 Adam steps of <= 1e-3 each; an element whose gradient is near zero may take its (sign-like) steps in the
+        # other direction (measured: 7e-4 between the 2-rank and a 1-rank run, 3e-4 between two 1-rank runs)
+        assert np.abs(x - y).max() <= 2.5e-3, (k, np.abs(x - y).max())
 
 
 def test_train_cli_checkpoint_then_generate_cli(lib, tmp_path):
