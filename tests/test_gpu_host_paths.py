@@ -133,8 +133,8 @@ def test_two_rank_nccl_step_equals_one_rank_step(lib, tmp_path, mode):
     all-reduce schedules) against the same 3 steps on one GPU.  After the FIRST step -- identical weights going in -- every
     variable agrees to the fp32 atomics' summation-order noise (measured 2e-7 relative: tools/diag_two_rank.py).  Later
     steps are compared as far as they are comparable at all: two runs of the SAME single-GPU program already differ by
-    2e-4 (step 2) and 3e-2 (step 3) in the bias gradients -- a last-bit difference in a weight flips the bf16 rounding
-    of its operand copy, and at random initialisation the bias gradients are small differences of large sums -- so the
+    2e-4 (step 2) and 3e-2 (step 3) in the gradients -- a last-bit difference in a weight is re-quantised into whole
+    bf16 ulps by the rounding points downstream (profiles/r02e_two_rank_vs_one_rank.md) -- so the
     bound there is the losses (1e-5) and what three Adam steps can move an element."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
