@@ -290,6 +290,8 @@ def main():
     arch = config.load_arch(ARCH_FILE)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries ONE JSON line: whatever NCCL has to say (NCCL_DEBUG=VERSION / INFO in the environment) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
     base = {
         "metric": "train output timesteps/s", "unit": "timesteps/s", "n_gpus": args.gpus, "steps": args.steps,
