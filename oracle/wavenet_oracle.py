@@ -259,8 +259,13 @@ def bf16_round(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.float32).to(torch.bfloat16).to(t.dtype)
 
 
-def _maybe(t: torch.Tensor, emulate: bool) -> torch.Tensor:
-    return bf16_round(t) if emulate else t
+# Rounding sites of the CUDA path's contract, by name; tools/error_budget.py switches single sites off (ROUND_OFF) to
+# attribute the bf16 error of a gradient to where it comes from.  Empty = the contract as it is (every test uses that).
+ROUND_OFF: set = set()
+
+
+def _maybe(t: torch.Tensor, emulate: bool, site: str = "") -> torch.Tensor:
+    return bf16_round(t) if (emulate and site not in ROUND_OFF) else t
 
 
 # --------------------------------------------------------------------------------------
@@ -293,9 +298,9 @@ def lc_upsample(a: Arch, p: Dict[str, torch.Tensor], mel: torch.Tensor, emulate_
     impl 'gemm' = that formula as one matmul per level; 'conv_transpose' = torch.nn.functional.conv_transpose1d, a
     structurally different statement of the same op.  emulate_bf16: the CUDA path's rounding points (mel, every level's
     output and the filters are bf16 operands).  keep: list that receives every level's input (for the backward)."""
-    lc = _maybe(mel, emulate_bf16)
+    lc = _maybe(mel, emulate_bf16, "lc")
     for i, s_ in enumerate(a.lc_upsample):
-        filt = _maybe(p["LC_UPSAMPLE_{}".format(i)], emulate_bf16)  # [s, n_out, n_in]
+        filt = _maybe(p["LC_UPSAMPLE_{}".format(i)], emulate_bf16, "w")  # [s, n_out, n_in]
         if keep is not None:
             keep.append(lc)
         B, Ti, _ = lc.shape
@@ -304,7 +309,7 @@ def lc_upsample(a: Arch, p: Dict[str, torch.Tensor], mel: torch.Tensor, emulate_
         else:
             w = filt.permute(2, 1, 0)  # conv_transpose1d weight: [in_channels, out_channels, width]
             out = torch.nn.functional.conv_transpose1d(lc.transpose(1, 2), w, stride=int(s_)).transpose(1, 2)
-        lc = _maybe(out, emulate_bf16)
+        lc = _maybe(out, emulate_bf16, "lc")
     return lc
 
 
@@ -326,7 +331,7 @@ def train_forward(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.Tensor],
     em = emulate_bf16
 
     def W(name):  # contraction operand (bf16 in the CUDA path)
-        return _maybe(p[name], em)
+        return _maybe(p[name], em, "w")
 
     # tmodel.py:53-66 one-hot (out-of-range index -> zero row) ; tmodel.py:96-100 PRE 1x1.
     # one_hot @ PRE == row gather, which is how the CUDA path does it (fp32 table).
@@ -334,7 +339,7 @@ def train_forward(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.Tensor],
     cur = p["PRE"][wav.clamp(0, a.n_quant - 1)] * valid
     if a.use_bias:
         cur = cur + p["PRE_BIAS"]
-    cur = _maybe(cur, em)
+    cur = _maybe(cur, em, "x")
 
     if a.has_gc():
         gathered = p["GC_EMBED"][ids]  # tmodel.py:112  [B,T,G]
@@ -361,11 +366,11 @@ def train_forward(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.Tensor],
             if a.has_gc():  # tmodel.py:150-154 (fp32 table in the CUDA path, no bf16 rounding)
                 vv = vv + gathered @ p["GC_{}_{}".format(nm, sfx)]
             if a.has_lc():  # tmodel.py:156-160 (the CUDA path stores the projection as a bf16 plane)
-                vv = vv + _maybe(lc_up @ W("LC_{}_{}".format(nm, sfx)), em)
+                vv = vv + _maybe(lc_up @ W("LC_{}_{}".format(nm, sfx)), em, "lc")
             v[nm] = vv
         new_save.append(full[:, full.shape[1] - dil:, :].detach())  # tmodel.py:165
         z = torch.tanh(v["SIGNAL"]) * torch.sigmoid(v["GATE"])  # tmodel.py:167
-        z = _maybe(z, em)
+        z = _maybe(z, em, "z")
         sig = z @ W("RESIDUAL_" + sfx)  # tmodel.py:171-181
         skp = z @ W("SKIP_" + sfx)
         if a.use_bias:
@@ -375,14 +380,14 @@ def train_forward(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.Tensor],
         if keep:
             xs.append(cur)
             zs.append(z)
-        cur = _maybe(cur + sig, em)  # tmodel.py:325
+        cur = _maybe(cur + sig, em, "x")  # tmodel.py:325
 
     # tmodel.py:187-215 (softmax output unused)
-    h1 = _maybe(torch.relu(skp_sum), em)
+    h1 = _maybe(torch.relu(skp_sum), em, "h")
     d1 = h1 @ W("POST1")
     if a.use_bias:
         d1 = d1 + p["POST1_BIAS"]
-    h2 = _maybe(torch.relu(d1), em)
+    h2 = _maybe(torch.relu(d1), em, "h")
     logits = h2 @ W("POST2")
     if a.use_bias:
         logits = logits + p["POST2_BIAS"]
@@ -491,7 +496,7 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
         pd = {k: v.detach().to(dtype) for k, v in p.items()}
 
         def W(name):
-            return _maybe(pd[name], em)
+            return _maybe(pd[name], em, "w")
 
         fwd = train_forward(a, pd, save, wav, ids, dtype, em, keep=True, mel=mel)
         lc_in: list = []
@@ -500,9 +505,9 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
             lc_up = lc_upsample(a, pd, mel.to(dtype), em, keep=lc_in)
             dlc_up = torch.zeros_like(lc_up)
         # recompute post-net intermediates
-        h1 = _maybe(torch.relu(fwd.skip_sum), em)
+        h1 = _maybe(torch.relu(fwd.skip_sum), em, "h")
         d1 = h1 @ W("POST1") + (pd["POST1_BIAS"] if a.use_bias else 0)
-        h2 = _maybe(torch.relu(d1), em)
+        h2 = _maybe(torch.relu(d1), em, "h")
         logits = fwd.logits
         # loss gradient wrt logits (unnormalised), tmodel.py:230-237
         mask = torch.zeros(B, T, dtype=dtype)
@@ -513,17 +518,17 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
         lab_ok = ((labels >= 0) & (labels < a.n_quant))
         onehot = torch.nn.functional.one_hot(labels.clamp(0, a.n_quant - 1), a.n_quant).to(dtype)
         onehot = onehot * lab_ok.unsqueeze(-1).to(dtype)  # out-of-range code: all-zero one-hot row (tmodel.py:64)
-        dlog = _maybe((sm - onehot) * mask.unsqueeze(-1), em)
+        dlog = _maybe((sm - onehot) * mask.unsqueeze(-1), em, "dlog")
         g: Dict[str, torch.Tensor] = {}
         flat = lambda t: t.reshape(-1, t.shape[-1])
         g["POST2"] = flat(h2).T @ flat(dlog)
         if a.use_bias:
             g["POST2_BIAS"] = flat(dlog).sum(0)
-        dp1 = _maybe((dlog @ W("POST2").T) * (h2 > 0).to(dtype), em)
+        dp1 = _maybe((dlog @ W("POST2").T) * (h2 > 0).to(dtype), em, "dpost")
         g["POST1"] = flat(h1).T @ flat(dp1)
         if a.use_bias:
             g["POST1_BIAS"] = flat(dp1).sum(0)
-        dskip = _maybe((dp1 @ W("POST1").T) * (h1 > 0).to(dtype), em)  # [B,T,S]
+        dskip = _maybe((dp1 @ W("POST1").T) * (h1 > 0).to(dtype), em, "dpost")  # [B,T,S]
         dx = torch.zeros(B, T, a.n_res, dtype=dtype)  # grad wrt x_{l+1}; zero after last layer
         if a.has_gc():
             gathered = pd["GC_EMBED"][ids]
@@ -543,7 +548,7 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
                 if a.has_gc():
                     vv = vv + gathered @ pd["GC_{}_{}".format(nm, sfx)]
                 if a.has_lc():
-                    vv = vv + _maybe(lc_up @ W("LC_{}_{}".format(nm, sfx)), em)
+                    vv = vv + _maybe(lc_up @ W("LC_{}_{}".format(nm, sfx)), em, "lc")
                 v[nm] = vv
             th, sg = torch.tanh(v["SIGNAL"]), torch.sigmoid(v["GATE"])
             g["SKIP_" + sfx] = flat(z).T @ flat(dskip)
@@ -551,10 +556,10 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
             if a.use_bias:
                 g["SKIP_BIAS_" + sfx] = flat(dskip).sum(0)
                 g["RESIDUAL_BIAS_" + sfx] = flat(dx).sum(0)
-            dz_skip = _maybe(dskip @ W("SKIP_" + sfx).T, em)
+            dz_skip = _maybe(dskip @ W("SKIP_" + sfx).T, em, "dz")
             dz = dz_skip + dx @ W("RESIDUAL_" + sfx).T
-            dvs = _maybe(dz * sg * (1 - th * th), em)
-            dvg = _maybe(dz * th * sg * (1 - sg), em)
+            dvs = _maybe(dz * sg * (1 - th * th), em, "dv")
+            dvg = _maybe(dz * th * sg * (1 - sg), em, "dv")
             for nm, dv in (("SIGNAL", dvs), ("GATE", dvg)):
                 gw = torch.stack([flat(xa).T @ flat(dv), flat(xb).T @ flat(dv)])
                 g["{}_{}".format(nm, sfx)] = gw
@@ -575,12 +580,12 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
             # CUDA path rounding points: the data gradient is stored in split form
             # dx_l[t] = Y_l[t] + P0_l[t+dil] with Y_l = bf16(dx_{l+1} + cur_part), P0_l = bf16(old_part)
             # and the consuming layer merges the two into one bf16 tile: dx_l = bf16(Y_l[t] + P0_l[t+dil])
-            dxl = _maybe(dx + cur_part, em)
+            dxl = _maybe(dx + cur_part, em, "dx")
             if T > dil:
-                dxl[:, :T - dil, :] += _maybe(old_part, em)[:, dil:, :]
-            dx = _maybe(dxl, em) if li > 0 else dxl  # layer 0's gradient feeds the PRE gather in split form
+                dxl[:, :T - dil, :] += _maybe(old_part, em, "dx")[:, dil:, :]
+            dx = _maybe(dxl, em, "dx") if li > 0 else dxl  # layer 0's gradient feeds the PRE gather in split form
         if a.has_lc():  # the upsampling chain in reverse (tmodel.py:68-83)
-            d = _maybe(dlc_up, em)
+            d = _maybe(dlc_up, em, "lc")
             for i in reversed(range(len(a.lc_upsample))):
                 s_ = int(a.lc_upsample[i])
                 filt = W("LC_UPSAMPLE_{}".format(i))  # [s, n_out, n_in]
@@ -588,7 +593,7 @@ def train_backward_manual(a: Arch, p: Dict[str, torch.Tensor], save: List[torch.
                 dv_ = d.reshape(xin.shape[0], xin.shape[1], s_, filt.shape[1])  # [B, Ti, k, o]
                 g["LC_UPSAMPLE_{}".format(i)] = torch.einsum("btko,btc->koc", dv_, xin)
                 if i > 0:
-                    d = _maybe(torch.einsum("btko,koc->btc", dv_, filt), em)
+                    d = _maybe(torch.einsum("btko,koc->btc", dv_, filt), em, "lc")
         # PRE gather backward
         g["PRE"] = torch.zeros_like(pd["PRE"])
         okay = ((wav >= 0) & (wav < a.n_quant)).reshape(-1)
