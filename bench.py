@@ -262,6 +262,15 @@ def configs0_leg(dev, lib):
     return out
 
 
+_JSON_OUT = None
+
+
+def _emit(text):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -290,8 +299,12 @@ def main():
     arch = config.load_arch(ARCH_FILE)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # stdout carries ONE JSON line: whatever NCCL has to say (NCCL_DEBUG=VERSION / INFO in the environment) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries ONE JSON line: keep a handle on the real stdout for it and point file descriptor 1 at stderr, so that
+    # whatever a library prints on the way (NCCL's version banner under NCCL_DEBUG=VERSION is a plain printf) lands there
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     base = {
         "metric": "train output timesteps/s", "unit": "timesteps/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -324,7 +337,7 @@ def main():
                                       "sample": r["sample"]},
                      "e2e": {"value": r["value"], "unit": "timesteps/s", "h2d_bytes_per_step": 0,
                              "d2h_bytes_per_step": 0}})
-        print(json.dumps(line))
+        _emit(json.dumps(line))
         return 0
 
     import torch
@@ -566,7 +579,7 @@ def main():
         r = cpu_reference_run(arch, 3, 1)
         line["cpu_baseline"] = {"value": r["value"], "unit": "timesteps/s", "cores": r["cores"], "kind": "port",
                                 "sample": r["sample"]}
-    print(json.dumps(line))
+    _emit(json.dumps(line))
     if world > 1:
         ctx.barrier()
         import torch.distributed as dist
