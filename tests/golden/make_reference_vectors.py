@@ -41,6 +41,8 @@ TRAIN_CASES = {
     "arch5": (dict(n_blocks=5, n_block_layers=10, n_quant=256, n_res=32, n_dil=32, n_skip=512, n_post=512, n_gc_embed=16,
                    n_gc_category=376, n_lc_in=80, n_lc_out=80, lc_upsample=[4, 4, 4, 4], use_bias=True), 2, 256, 1e-4, 105),
 }
+RAW_CASES = {"raw"}  # wav_input_type 'raw': the graph receives float audio and encodes it itself (tmodel.py:59-62, ops.py:4-9)
+TRAIN_CASES["raw"] = (dict(TRAIN_CASES["odd"][0], use_bias=True), 2, 32, 1e-2, 106)
 N_STAGES = 2
 SAMPLE_LIMIT = {"arch5": 48}  # elements stored per gradient tensor (default 256): arch5 has 760 variables
 LOGIT_STRIDE = {"arch5": 16}  # every k-th timestep of the logits is stored (default 4)
@@ -78,7 +80,25 @@ def train_inputs(name, stage):
     if arch["n_lc_out"] > 0:
         hop = int(np.prod(arch["lc_upsample"]))
         mel = rng.standard_normal((B, T // hop, arch["n_lc_in"])).astype(np.float32)
+    if name in RAW_CASES:
+        wav[0, 9] = 7  # (float audio has no out-of-range code)
     return wav, ids, mel
+
+
+_RAW_TABLE = None
+
+
+def raw_audio(codes):
+    """float32 audio whose mu-law code is `codes`: the middle of the code's interval of the encoder (between two
+    thresholds of ops.py:4-9), so that encoding it in float32 (TensorFlow) or float64 (the shim's default) gives the same code"""
+    global _RAW_TABLE
+    if _RAW_TABLE is None:
+        from oracle import wavenet_oracle as O
+        thr = O.mu_encode_thresholds(256).astype(np.float64)
+        edges = np.concatenate([[-1.0], thr, [1.0]])
+        _RAW_TABLE = (0.5 * (edges[:-1] + edges[1:])).astype(np.float32)
+        assert np.array_equal(O.mu_encode_np(_RAW_TABLE), np.arange(256))
+    return _RAW_TABLE[np.asarray(codes)]
 
 
 def train_params(name):
@@ -157,7 +177,7 @@ def run_train_case(tf, tmodel, name):
     tf._reset()
     tf._set_float(torch.float64)
     tf._set_eager(False)
-    net = tmodel.WaveNetTrain(**arch, wav_input_type="mu_law_quant", batch_sz=B, l2_factor=l2, add_summary=False,
+    net = tmodel.WaveNetTrain(**arch, wav_input_type="raw" if name in RAW_CASES else "mu_law_quant", batch_sz=B, l2_factor=l2, add_summary=False,
                               n_keep_checkpoints=1, ckpt_path="/tmp/none", resume_step=0, n_valid_total=10 ** 6,
                               sess=None, print_interval=10 ** 6)
     captured = {}
@@ -172,6 +192,8 @@ def run_train_case(tf, tmodel, name):
     def call_build(stage):
         wav, ids, mel = train_inputs(name, stage)
         lc = None if mel is None else torch.as_tensor(mel, dtype=torch.float64)
+        if name in RAW_CASES:
+            return net.build(torch.as_tensor(raw_audio(wav), dtype=torch.float64), lc, torch.as_tensor(ids))
         return net.build(torch.as_tensor(wav), lc, torch.as_tensor(ids))
 
     call_build(0)  # creates the variables (Xavier-initialised by the reference's own get_variable wrapper) ...

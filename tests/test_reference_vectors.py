@@ -170,7 +170,8 @@ def test_cuda_training_step_against_the_reference_run(name, tmp_path):
     arch, B, T, l2, _ = G.TRAIN_CASES[name]
     gold = _golden("train_" + name)
     p = G.train_params(name)
-    net = WaveNetTrain(**arch, wav_input_type="mu_law_quant", batch_sz=B, l2_factor=l2, add_summary=False,
+    raw = name in G.RAW_CASES  # float audio in, mu-law encoded on the device (wn_mu_encode) as tmodel.py:59-62 does in the graph
+    net = WaveNetTrain(**arch, wav_input_type="raw" if raw else "mu_law_quant", batch_sz=B, l2_factor=l2, add_summary=False,
                        n_keep_checkpoints=1, ckpt_path=str(tmp_path / "ref.net"), resume_step=0, n_valid_total=10 ** 6,
                        print_interval=0, init_seed=1)
     net.build()
@@ -186,7 +187,10 @@ def test_cuda_training_step_against_the_reference_run(name, tmp_path):
     for stage in range(G.N_STAGES):
         wav, ids, mel = G.train_inputs(name, stage)
         kw = {} if mel is None else dict(mel=torch.as_tensor(mel).cuda())
-        logits = eng.forward(torch.as_tensor(wav).cuda(), torch.as_tensor(ids).cuda(), want_logits=True, **kw)
+        dw, di = net._prepare_inputs(torch.as_tensor(G.raw_audio(wav)) if raw else torch.as_tensor(wav), torch.as_tensor(ids))
+        if raw:
+            assert np.array_equal(dw.cpu().numpy(), wav)
+        logits = eng.forward(dw, di, want_logits=True, **kw)
         eng.backward()
         torch.cuda.synchronize()
         s = "s%d_" % stage
