@@ -91,6 +91,37 @@ def test_reference_run_covers_the_quirks_the_oracle_documents():
     assert abs(float(L1.total) - float(_golden("train_r32")["s0_loss"])) < 1e-9
 
 
+def test_the_vectors_have_teeth():
+    """Mutations of the kind a misreading of the reference would produce move the loss far outside the 1e-10 the comparison
+    allows: the two conv taps swapped in one layer, the SAVE rows of one layer rotated by one timestep, another voice id,
+    one input code changed, one bias scaled by 0.1 %."""
+    name = "gc"
+    arch, B, T, l2, _ = G.TRAIN_CASES[name]
+    a = G.oracle_arch(arch)
+    gold = float(_golden("train_" + name)["s0_loss"])
+    p = G.train_params(name)
+    wav, ids, _ = G.train_inputs(name, 0)
+
+    def loss(p_, wav_, ids_):
+        pt, save, kinds = O.to_torch_params(a, p_, B, torch.float64, requires_grad=False)
+        w, i = torch.as_tensor(wav_).long(), torch.as_tensor(ids_).long()
+        return float(O.loss_fn(a, O.train_forward(a, pt, save, w, i, torch.float64).logits, w, i, pt, kinds, l2).total)
+    assert abs(loss(p, wav, ids) - gold) <= 1e-10 * gold
+    ids2 = ids.copy()
+    ids2[ids2 == 2] = 3
+    wav2 = wav.copy()
+    wav2[1, 5] = (wav2[1, 5] + 1) % 256
+    mutants = {
+        "taps swapped": (dict(p, SIGNAL_0_1=p["SIGNAL_0_1"][::-1].copy()), wav, ids),
+        "SAVE rotated": (dict(p, SAVE_2_0_1=np.roll(p["SAVE_2_0_1"], 1, axis=1)), wav, ids),
+        "voice id": (p, wav, ids2),
+        "input code": (p, wav2, ids),
+        "bias scaled": (dict(p, POST1_BIAS=p["POST1_BIAS"] * 1.001), wav, ids),
+    }
+    for what, (p_, w_, i_) in mutants.items():
+        assert abs(loss(p_, w_, i_) - gold) > 1e-6, what
+
+
 # ---------------------------------------------------------------- mu-law (ops.py:4-39) ---------------------------
 def test_mu_law_equals_the_reference_run():
     gold = _golden("mu")
