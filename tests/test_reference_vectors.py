@@ -91,6 +91,24 @@ def test_reference_run_covers_the_quirks_the_oracle_documents():
     assert abs(float(L1.total) - float(_golden("train_r32")["s0_loss"])) < 1e-9
 
 
+@pytest.mark.parametrize("name", sorted(G.TRAIN_CASES))
+def test_product_registry_equals_the_reference_runs_variable_list(name):
+    """wn_param_info / wn_save_info (the C ABI's registry; no GPU needed) against `net.vars` of the reference run: the same
+    serial names in the same creation order -- the checkpoint contract (arch.py:112-142, tmodel.py:292-328)."""
+    from lb_wavenet_b200 import config
+    from lb_wavenet_b200.engine import Registry
+    arch, B, T, _, _ = G.TRAIN_CASES[name]
+    order = [str(k) for k in _golden("train_" + name)["var_order"]]
+    reg = Registry(config.engine_arch(dict(arch)), B)  # (tiny channel counts are zero-padded: names and order are what is compared)
+    ours, it_p, it_s = [], iter(reg.params), iter(reg.saves)
+    for k in order:  # trainable variables and SAVE state are two lists in the ABI: merge them along the reference's order
+        if k in ("GLOBAL_STEP", "VALID_SAMPLES"):
+            continue  # host-side counters of the mirror (tmodel.py:223-226)
+        ours.append(next(it_s).name if k.startswith("SAVE") else next(it_p))
+    assert ours == [k for k in order if k not in ("GLOBAL_STEP", "VALID_SAMPLES")]
+    assert next(it_p, None) is None and next(it_s, None) is None
+
+
 def test_the_vectors_have_teeth():
     """Mutations of the kind a misreading of the reference would produce move the loss far outside the 1e-10 the comparison
     allows: the two conv taps swapped in one layer, the SAVE rows of one layer rotated by one timestep, another voice id,
